@@ -1,0 +1,177 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own numpy code.
+
+Run in the build container only (needs /root/reference; the GPU box has none):
+
+    python -m oracle.gen_goldens
+
+TensorFlow / matplotlib / easydict are absent here, so tiny stand-in modules are
+put in sys.modules before the reference files are imported;
+no reference source is copied -- the files are imported where they lie.
+
+Every fixture stores the outputs the reference produced plus a sha256 of the
+inputs, which tests regenerate from the same seed through oracle/synth.py.
+"""
+import hashlib
+import os
+import sys
+import types
+
+import numpy as np
+
+from oracle import synth
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _install_stubs():
+    tf = types.ModuleType("tensorflow")
+    tf.contrib = types.SimpleNamespace(slim=types.SimpleNamespace())
+    sys.modules.setdefault("tensorflow", tf)
+    mpl = types.ModuleType("matplotlib")
+    plt = types.ModuleType("matplotlib.pyplot")
+    mpl.pyplot = plt
+    sys.modules.setdefault("matplotlib", mpl)
+    sys.modules.setdefault("matplotlib.pyplot", plt)
+    ed = types.ModuleType("easydict")
+
+    class EasyDict(dict):
+        __getattr__ = dict.__getitem__
+        __setattr__ = dict.__setitem__
+    ed.EasyDict = EasyDict
+    sys.modules.setdefault("easydict", ed)
+
+
+def import_avod():
+    _install_stubs()
+    for p in (REF + "/avod", REF + "/avod/wavedata"):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import avod.utils.sparse_pool_utils as spu
+    return spu
+
+
+def import_mv3d_construct_voxel():
+    _install_stubs()
+    p = REF + "/MV3D_TF_release/lib"
+    if p not in sys.path:
+        sys.path.append(p)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mv3d_config_voxels", p + "/utils/config_voxels.py")
+    cfgmod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cfgmod)
+    # construct_voxel does `from utils.config_voxels import cfg` and `from utils.transform import ...`
+    pkg = types.ModuleType("utils")
+    pkg.__path__ = [p + "/utils"]
+    sys.modules["utils"] = pkg
+    sys.modules["utils.config_voxels"] = cfgmod
+    spec = importlib.util.spec_from_file_location("utils.construct_voxel", p + "/utils/construct_voxel.py")
+    cv = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(cv)
+    finally:
+        pass
+    return cv
+
+
+def digest(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(str(a.dtype).encode() + str(a.shape).encode())
+        h.update(a.tobytes())
+    return h.hexdigest()
+
+
+class _Calib:
+    def __init__(self, p2):
+        self.p2 = p2
+
+
+def ref_gen_and_produce(spu, frame, stride):
+    d = spu.gen_sparse_pooling_input_avod(frame["points"], frame["voxel_indices"], _Calib(frame["P"]),
+                                          frame["im_size"], frame["bv_size"])
+    gen = {k: np.array(v, copy=True) for k, v in d.items()}
+    out = spu.produce_sparse_pooling_input(d, stride=list(stride))
+    return gen, out, d
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    spu = import_avod()
+
+    # ---- KAT-1 / KAT-2 --------------------------------
+    P = np.array([[1.0, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]])
+    uv = [(0.5, 0.5), (1.5, 1.5), (2.5, 2.5), (-0.0, 0.0), (-1e-9, 0.0), (8.999, 3.0), (9.0, 3.0), (8.4999, 4.999), (3.0, 5.0)]
+    pts = np.array([[u, v, 1.0] for u, v in uv])
+    vox = np.array([[k, z] for k, z in enumerate([1, 2, 3, 4, 5, 6, 7, 8, 0])])
+    frame = dict(points=pts, voxel_indices=vox, P=P, im_size=[10, 6], bv_size=(8, 16))
+    gen, out, mutated = ref_gen_and_produce(spu, frame, (2, 2))
+    np.savez_compressed(os.path.join(OUT, "kat1.npz"), points=pts, voxel_indices=vox, P=P, im_size=[10, 6],
+                        bv_size=[8, 16], stride=[2, 2], gen_bv_index=gen["bv_index"], gen_img_index=gen["img_index"],
+                        Mij_pool=out["Mij_pool"], M_val=out["M_val"], M_size=out["M_size"],
+                        img_index_flip_pool=out["img_index_flip_pool"], img_index_after=mutated["img_index"])
+    d2 = dict(bv_index=np.array([[3, 8], [3, 7], [15, 7], [16, 6]]), img_index=np.array([[1.0, 2, 3, 4], [1, 1, 2, 2], [0, 0, 0, 0]]),
+              bv_size=np.array([8, 16]), img_size=np.array([10, 6]))
+    o2 = spu.produce_sparse_pooling_input({k: np.array(v, copy=True) for k, v in d2.items()}, stride=[1, 1])
+    np.savez_compressed(os.path.join(OUT, "kat2.npz"), **{"in_" + k: v for k, v in d2.items()},
+                        Mij_pool=o2["Mij_pool"], M_val=o2["M_val"], M_size=o2["M_size"],
+                        img_index_flip_pool=o2["img_index_flip_pool"])
+
+    # ---- avod frame through the reference builder at the three strides -------
+    for seed, az in ((1, 0.09), (2, 0.05)):
+        frame = synth.avod_frame(seed, az_step_deg=az)
+        rec = dict(input_sha=digest(frame["points"], frame["voxel_indices"]), seed=seed, az=az,
+                   n_in=frame["points"].shape[0])
+        for s in (1, 4, 8):
+            gen, out, _ = ref_gen_and_produce(spu, frame, (s, s))
+            if s == 1:
+                rec["gen_bv_index"] = gen["bv_index"]
+                rec["gen_img_index"] = gen["img_index"].astype(np.int32)   # integer-valued f64, stored compactly
+            rec["Mij_pool_s%d" % s] = out["Mij_pool"][:, 0].astype(np.int32)  # col is arange (checked below)
+            assert (out["Mij_pool"][:, 1] == np.arange(out["Mij_pool"].shape[0])).all()
+            assert out["Mij_pool"].dtype == np.int64 and out["img_index_flip_pool"].dtype == np.int64
+            assert out["M_val"].dtype == np.float64 and (out["M_val"] == 1).all()
+            rec["M_size_s%d" % s] = out["M_size"]
+            rec["flip_s%d" % s] = out["img_index_flip_pool"].astype(np.int32)
+        np.savez_compressed(os.path.join(OUT, "avod_frame_seed%d.npz" % seed), **rec)
+        print("avod_frame seed", seed, "N", rec["n_in"], "nnz", {s: int(rec["M_size_s%d" % s][1]) for s in (1, 4, 8)})
+
+    # ---- direct pairs (config 1 'direct', and skewed stress shapes) ----------
+    for name, kw in (("direct_uniform", dict(seed=0, n=20000)),
+                     ("direct_ground", dict(seed=3, n=50000, skew="ground")),
+                     ("direct_zipf", dict(seed=4, n=30000, skew="zipf"))):
+        d = synth.direct_pairs(**kw)
+        rec = dict(input_sha=digest(d["bv_index"], d["img_index"]))
+        for s in ((1, 1), (8, 8), (8, 2)):
+            o = spu.produce_sparse_pooling_input({k: np.array(v, copy=True) for k, v in d.items()}, stride=list(s))
+            tag = "s%d_%d" % s
+            rec["row_" + tag] = o["Mij_pool"][:, 0].astype(np.int32)
+            rec["M_size_" + tag] = o["M_size"]
+            rec["flip_" + tag] = o["img_index_flip_pool"].astype(np.int32)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+        print(name, {k: v.tolist() for k, v in rec.items() if k.startswith("M_size")})
+
+    # ---- MV3D feeder: reference point_cloud_2_top_sparse ---------------------
+    try:
+        cv = import_mv3d_construct_voxel()
+        f = synth.mv3d_frame(seed=5, n_points=6000)
+        cam4 = np.c_[f["points_fsh"][:, [1, 2, 0]], np.zeros(len(f["points_fsh"]))]   # x, y, z, reflectance
+        calib = np.zeros((4, 12))
+        calib[0] = synth.P2_KITTI.reshape(-1)
+        _, vfs, img_index, bv_index, M_val = cv.point_cloud_2_top_sparse(
+            cam4.copy(), points_in_cam=True, calib=calib, img_index2=f["img_index2"].copy())
+        o = spu.produce_sparse_pooling_input(dict(img_index=np.array(img_index, dtype=np.float64), img_size=f["img_size"],
+                                                  bv_index=bv_index, bv_size=[vfs[1], vfs[2]]), M_val=M_val, stride=[8, 2])
+        np.savez_compressed(os.path.join(OUT, "mv3d_seed5.npz"), input_sha=digest(f["points_fsh"], f["img_index2"]),
+                            voxel_full_size=vfs, img_index=np.asarray(img_index).astype(np.int32), bv_index=bv_index.astype(np.int32),
+                            M_val=M_val, row=o["Mij_pool"][:, 0].astype(np.int32), M_size=o["M_size"],
+                            flip=o["img_index_flip_pool"].astype(np.int32))
+        print("mv3d", vfs, "pairs", len(M_val), "M_size", o["M_size"], "min w", M_val.min())
+    except Exception as e:  # pragma: no cover
+        print("MV3D golden skipped:", repr(e))
+        raise
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,236 @@
+"""Pins the CPU oracle (numpy restatement AND the plain-C port) against what the
+REFERENCE's own code produced (tests/golden/*.npz, made by oracle/gen_goldens.py
+from /root/reference) and against the known-answer vectors of SURVEY.md
+Appendix B.  No GPU needed."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cref, index_oracle as io, synth, value_oracle as vo
+
+
+def digest(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(str(a.dtype).encode() + str(a.shape).encode())
+        h.update(a.tobytes())
+    return h.hexdigest()
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+# ------------------------------------------------------------------ KAT-1 / 2
+def test_kat1_expected_literals(golden_dir):
+    """SURVEY.md Appendix B KAT-1, literal expectations + the reference-run fixture."""
+    g = load(golden_dir, "kat1.npz")
+    d = io.gen_sparse_pooling_input_avod(g["points"], g["voxel_indices"], g["P"], list(g["im_size"]), tuple(g["bv_size"]))
+    assert d["img_index"][0].tolist() == [0, 2, 2, 0, 9, 8]          # ties to even: 0.5->0 1.5->2 2.5->2
+    assert d["img_index"][1].tolist() == [0, 2, 2, 0, 3, 5]
+    assert d["bv_index"].tolist() == [[0, 1], [1, 2], [2, 3], [3, 4], [5, 6], [7, 8]]
+    np.testing.assert_array_equal(d["bv_index"], g["gen_bv_index"])
+    np.testing.assert_array_equal(d["img_index"], g["gen_img_index"])
+    assert d["img_index"].dtype == np.float64 and d["img_index"].shape[0] == 3
+    o = io.produce_sparse_pooling_input(d, stride=[2, 2])
+    assert o["M_size"].tolist() == [32, 5]
+    assert o["Mij_pool"].tolist() == [[0, 0], [8, 1], [9, 2], [17, 3], [26, 4]]
+    assert o["img_index_flip_pool"].tolist() == [[0, 0, 0], [0, 1, 1], [0, 1, 1], [0, 0, 0], [0, 1, 4]]
+    for k in ("Mij_pool", "M_val", "M_size", "img_index_flip_pool"):
+        np.testing.assert_array_equal(o[k], g[k])
+        assert o[k].dtype == g[k].dtype, k
+    np.testing.assert_array_equal(d["img_index"], g["img_index_after"])   # in-place mutation (quirk A.4-6)
+    assert o["bev_index_flip_pool"].shape == (0, 3)
+
+
+def test_kat1_c_oracle(golden_dir):
+    g = load(golden_dir, "kat1.npz")
+    c = cref.build_avod(g["points"], g["voxel_indices"], g["P"], g["im_size"], g["bv_size"], g["stride"])
+    np.testing.assert_array_equal(c["Mij_pool"], g["Mij_pool"])
+    np.testing.assert_array_equal(c["img_index_flip_pool"], g["img_index_flip_pool"])
+    np.testing.assert_array_equal(c["M_size"], g["M_size"])
+    np.testing.assert_array_equal(c["gen"]["bv_index"], g["gen_bv_index"])
+    np.testing.assert_array_equal(c["gen"]["img_index"], g["gen_img_index"])
+
+
+def test_kat2_row_filter_and_x_wrap(golden_dir):
+    g = load(golden_dir, "kat2.npz")
+    d = {k[3:]: np.array(g[k]) for k in g.files if k.startswith("in_")}
+    o = io.produce_sparse_pooling_input(d, stride=[1, 1])
+    assert o["Mij_pool"].tolist() == [[115, 0], [127, 1], [112, 2]]   # row 131 dropped; x=16 wraps
+    for k in ("Mij_pool", "M_val", "M_size", "img_index_flip_pool"):
+        np.testing.assert_array_equal(o[k], g[k])
+
+
+def test_wrong_img_index_shape_asserts():
+    d = synth.direct_pairs(0, 10)
+    d["img_index"] = d["img_index"][:2]
+    with pytest.raises(AssertionError):
+        io.produce_sparse_pooling_input(d)
+
+
+# ------------------------------------------------- reference-run frame fixtures
+@pytest.mark.parametrize("seed,az", [(1, 0.09), (2, 0.05)])
+def test_avod_frame_matches_reference(golden_dir, seed, az):
+    g = load(golden_dir, "avod_frame_seed%d.npz" % seed)
+    frame = synth.avod_frame(seed, az_step_deg=az)
+    assert digest(frame["points"], frame["voxel_indices"]) == str(g["input_sha"]), "synthetic input drifted"
+    for s in (1, 4, 8):
+        d = io.gen_sparse_pooling_input_avod(frame["points"], frame["voxel_indices"], frame["P"], frame["im_size"], frame["bv_size"])
+        if s == 1:
+            np.testing.assert_array_equal(d["bv_index"], g["gen_bv_index"])
+            np.testing.assert_array_equal(d["img_index"], g["gen_img_index"].astype(np.float64))
+        o = io.produce_sparse_pooling_input(d, stride=[s, s])
+        np.testing.assert_array_equal(o["Mij_pool"][:, 0], g["Mij_pool_s%d" % s])
+        np.testing.assert_array_equal(o["Mij_pool"][:, 1], np.arange(len(o["Mij_pool"])))
+        np.testing.assert_array_equal(o["M_size"], g["M_size_s%d" % s])
+        np.testing.assert_array_equal(o["img_index_flip_pool"], g["flip_s%d" % s])
+        assert o["Mij_pool"].dtype == np.int64 and o["img_index_flip_pool"].dtype == np.int64
+        # plain-C port (fma-chain projection) agrees bit for bit as well
+        c = cref.build_avod(frame["points"], frame["voxel_indices"], frame["P"], frame["im_size"], frame["bv_size"], (s, s))
+        np.testing.assert_array_equal(c["Mij_pool"][:, 0], g["Mij_pool_s%d" % s])
+        np.testing.assert_array_equal(c["img_index_flip_pool"], g["flip_s%d" % s])
+        np.testing.assert_array_equal(c["M_size"], g["M_size_s%d" % s])
+
+
+@pytest.mark.parametrize("name,kw", [("direct_uniform", dict(seed=0, n=20000)),
+                                     ("direct_ground", dict(seed=3, n=50000, skew="ground")),
+                                     ("direct_zipf", dict(seed=4, n=30000, skew="zipf"))])
+def test_direct_pairs_match_reference(golden_dir, name, kw):
+    g = load(golden_dir, name + ".npz")
+    d0 = synth.direct_pairs(**kw)
+    assert digest(d0["bv_index"], d0["img_index"]) == str(g["input_sha"])
+    for s in ((1, 1), (8, 8), (8, 2)):
+        d = {k: np.array(v, copy=True) for k, v in d0.items()}
+        o = io.produce_sparse_pooling_input(d, stride=list(s))
+        tag = "s%d_%d" % s
+        np.testing.assert_array_equal(o["Mij_pool"][:, 0], g["row_" + tag])
+        np.testing.assert_array_equal(o["M_size"], g["M_size_" + tag])
+        np.testing.assert_array_equal(o["img_index_flip_pool"], g["flip_" + tag])
+
+
+def test_mv3d_feeder_weights_match_reference(golden_dir):
+    g = load(golden_dir, "mv3d_seed5.npz")
+    f = synth.mv3d_frame(seed=5, n_points=6000)
+    assert digest(f["points_fsh"], f["img_index2"]) == str(g["input_sha"])
+    inrange, kept, bv_index, m_val = io.mv3d_voxel_weights(f["points_fsh"], f["res"], f["zres"], f["side_range"],
+                                                          f["fwd_range"], f["height_range"], f["max_points"])
+    np.testing.assert_array_equal(bv_index, g["bv_index"])
+    np.testing.assert_array_equal(m_val, g["M_val"])                    # 1/count, float64, bit-exact
+    img2 = f["img_index2"][:, inrange][:, kept]
+    np.testing.assert_array_equal(img2, g["img_index"][:2])
+    assert f["bv_size"] == [int(g["voxel_full_size"][1]), int(g["voxel_full_size"][2])]
+    img_index = np.vstack((img2, np.zeros((1, img2.shape[1])))).astype(np.float64)
+    o = io.produce_sparse_pooling_input(dict(img_index=img_index, img_size=f["img_size"], bv_index=bv_index,
+                                             bv_size=f["bv_size"]), M_val=m_val, stride=f["stride"])
+    np.testing.assert_array_equal(o["Mij_pool"][:, 0], g["row"])
+    np.testing.assert_array_equal(o["M_size"], g["M_size"])
+    np.testing.assert_array_equal(o["img_index_flip_pool"], g["flip"])
+    assert m_val.min() == 1.0 / 45
+
+
+# ------------------------------------------------------------ canonical CSR
+def test_plan_is_stable_sort_of_coo():
+    d = synth.direct_pairs(7, 5000, bev_hw=(40, 50), img_wh=(60, 30))
+    o = io.produce_sparse_pooling_input(d, stride=[1, 1])
+    R, (Hs, Ws) = int(o["M_size"][0]), (30, 60)
+    val = np.random.default_rng(0).random(len(o["Mij_pool"])).astype(np.float32)
+    p = io.build_plan(o["Mij_pool"], val, o["img_index_flip_pool"], R, Hs, Ws)
+    rows = o["Mij_pool"][:, 0]
+    assert p["n_oob"] == 0 and p["row_ptr"][-1] == len(rows) == p["pix_ptr"][-1]
+    for r in np.unique(rows)[:200]:
+        seg = slice(p["row_ptr"][r], p["row_ptr"][r + 1])
+        ks = p["csr_ent"][seg]
+        np.testing.assert_array_equal(ks, np.nonzero(rows == r)[0])      # ascending k inside a row
+        np.testing.assert_array_equal(p["csr_val"][seg], val[ks])
+    pix = o["img_index_flip_pool"][:, 1] * Ws + o["img_index_flip_pool"][:, 2]
+    np.testing.assert_array_equal(pix[p["csr_ent"]], p["csr_src"])
+    for q in np.unique(pix)[:200]:
+        seg = slice(p["pix_ptr"][q], p["pix_ptr"][q + 1])
+        np.testing.assert_array_equal(p["csrT_ent"][seg], np.nonzero(pix == q)[0])
+        np.testing.assert_array_equal(p["csrT_dst"][seg], rows[p["csrT_ent"][seg]])
+
+
+def test_plan_drops_out_of_range_entries():
+    Mij = np.array([[0, 0], [5, 1], [-1, 2], [2, 3], [1, 4]])
+    flip = np.array([[0, 0, 0], [0, 1, 1], [0, 0, 1], [0, -1, 0], [0, 1, 3]])
+    p = io.build_plan(Mij, np.ones(5), flip, n_rows=4, src_h=2, src_w=3)
+    assert p["n_oob"] == 4                       # row 5>=4, row -1, v=-1, u=3>=W
+    assert p["row_ptr"].tolist() == [0, 1, 1, 1, 1] and p["csr_src"].tolist() == [0]
+
+
+# ---------------------------------------------------------------- value path
+def _small_case(seed=0, dual=True):
+    rng = np.random.default_rng(seed)
+    Hb, Wb, Hi, Wi, Cb, Ci = 9, 11, 7, 13, 8, 12
+    d = synth.direct_pairs(seed, 400, bev_hw=(Hb, Wb), img_wh=(Wi, Hi))
+    o = io.produce_sparse_pooling_input(d, stride=[1, 1])
+    val = rng.random(len(o["Mij_pool"])).astype(np.float32) if seed % 2 else np.ones(len(o["Mij_pool"]), np.float32)
+    bev = rng.standard_normal((1, Hb, Wb, Cb), dtype=np.float32)
+    img = rng.standard_normal((1, Hi, Wi, Ci), dtype=np.float32)
+    return o, val, bev, img
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_value_oracle_numpy_vs_c_bitexact(seed):
+    o, val, bev, img = _small_case(seed)
+    M = (o["Mij_pool"], val, o["M_size"])
+    flip = o["img_index_flip_pool"]
+    bv_fused, img_fused = vo.sparse_pool_layer([bev, img], [img.shape[3], bev.shape[3]], M, flip, np.zeros((1, 3)))
+    c_bv = cref.forward(bev[0], img[0], o["Mij_pool"], val, flip)
+    c_img = cref.forward_trans(img[0], bev[0], o["Mij_pool"], val, flip)
+    np.testing.assert_array_equal(bv_fused[0], c_bv)
+    np.testing.assert_array_equal(img_fused[0], c_img)
+    rng = np.random.default_rng(seed + 10)
+    g_bv = rng.standard_normal(bv_fused.shape, dtype=np.float32)
+    g_im = rng.standard_normal(img_fused.shape, dtype=np.float32)
+    gb, gi = vo.sparse_pool_layer_grad([bev, img], None, M, flip, np.zeros((1, 3)), g_bv, g_im)
+    gd1, gs1 = cref.backward(g_bv[0], o["Mij_pool"], val, flip, bev.shape[3], img.shape[1:])
+    gi2, gb2 = cref.backward_trans(g_im[0], o["Mij_pool"], val, flip, img.shape[3], bev.shape[1:])
+    np.testing.assert_array_equal(gb[0], gd1 + gb2)
+    np.testing.assert_array_equal(gi[0], gi2 + gs1)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_value_oracle_vs_torch_autograd(seed):
+    """Cross-check of the restated TF semantics against an independent engine:
+    torch CPU index_select / index_add / autograd (fp32 tolerance 1e-5 relative,
+    the north_star's bound; summation order differs)."""
+    torch = pytest.importorskip("torch")
+    o, val, bev, img = _small_case(seed)
+    flip = o["img_index_flip_pool"]
+    rows = torch.from_numpy(o["Mij_pool"][:, 0].copy())
+    Hb, Wb, Cb = bev.shape[1:]
+    Hi, Wi, Ci = img.shape[1:]
+    pix = torch.from_numpy(flip[:, 1] * Wi + flip[:, 2])
+    w = torch.from_numpy(val)[:, None]
+    tb = torch.from_numpy(bev).clone().requires_grad_(True)
+    ti = torch.from_numpy(img).clone().requires_grad_(True)
+    G = ti.reshape(-1, Ci).index_select(0, pix) * w
+    Y = torch.zeros(Hb * Wb, Ci).index_add(0, rows, G)
+    bv_fused = torch.cat([tb, Y.reshape(1, Hb, Wb, Ci)], dim=3)
+    S = tb.reshape(-1, Cb).index_select(0, rows) * w
+    Pm = torch.zeros(Hi * Wi, Cb).index_add(0, pix, S)
+    img_fused = torch.cat([ti, Pm.reshape(1, Hi, Wi, Cb)], dim=3)
+    M = (o["Mij_pool"], val, o["M_size"])
+    o_bv, o_img = vo.sparse_pool_layer([bev, img], [Ci, Cb], M, flip, np.zeros((1, 3)))
+    np.testing.assert_allclose(o_bv, bv_fused.detach().numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(o_img, img_fused.detach().numpy(), rtol=1e-5, atol=1e-5)
+    rng = np.random.default_rng(seed + 10)
+    g_bv = rng.standard_normal(o_bv.shape, dtype=np.float32)
+    g_im = rng.standard_normal(o_img.shape, dtype=np.float32)
+    (bv_fused * torch.from_numpy(g_bv)).sum().add((img_fused * torch.from_numpy(g_im)).sum()).backward()
+    gb, gi = vo.sparse_pool_layer_grad([bev, img], None, M, flip, np.zeros((1, 3)), g_bv, g_im)
+    np.testing.assert_allclose(gb, tb.grad.numpy(), rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(gi, ti.grad.numpy(), rtol=1e-5, atol=2e-5)
+
+
+def test_value_oracle_rejects_out_of_range_like_tf_cpu():
+    x = np.zeros((1, 4, 5, 2), np.float32)
+    with pytest.raises(IndexError):
+        vo.gather_nd(x, np.array([[0, 4, 0]]))
+    with pytest.raises(IndexError):
+        vo.spmm(np.array([[9, 0]]), np.ones(1), [4, 1], np.zeros((1, 2), np.float32))
