@@ -1,0 +1,157 @@
+/* shpl.h -- C ABI of libshpl.so: the B200 (sm_100a) implementation of the Sparse
+ * Non-homogeneous Pooling Layer (SHPL) hot path of YeungLy/Sparse_Pooling.
+ *
+ * The reference has no native boundary for this path (it is numpy + TensorFlow
+ * graph ops); each entry point below names the reference interface it replaces
+ * (paths relative to /root/reference).  INTEGRATION.md shows the ctypes binding a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns every buffer (PyTorch in this repo); the library keeps no
+ *     state between calls and allocates nothing;
+ *   - every function takes the cudaStream_t (as void*) to launch on, is
+ *     asynchronous and never synchronises;
+ *   - return value: 0 on success, negative shpl_status on failure, with a
+ *     thread-local message available from shpl_last_error();
+ *   - feature maps are NHWC fp32, contiguous, channel counts multiples of 4 and
+ *     base addresses 16-byte aligned (128-bit vector access).
+ */
+#ifndef SHPL_H_
+#define SHPL_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHPL_ABI_VERSION 1
+
+typedef enum shpl_status {
+    SHPL_OK = 0,
+    SHPL_ERR_INVALID_ARGUMENT = -1, /* reference: Python assert / TF InvalidArgumentError */
+    SHPL_ERR_CUDA = -2,
+    SHPL_ERR_WORKSPACE_TOO_SMALL = -3,
+    SHPL_ERR_UNSUPPORTED = -4
+} shpl_status;
+
+/* Canonical sparse structure of one M (one frame, or several frames stacked).
+ * It is the stable sort of the reference's COO  tf.SparseTensor(Mij_pool, M_val,
+ * M_size)  (avod/avod/core/models/rpn_model.py:292-293, :330-331) by destination
+ * row (CSR) and by source pixel (CSR^T); inside a row / pixel the entries keep the
+ * reference's column order k, which is TF-CPU's accumulation order.
+ * All arrays are caller-allocated device memory of the stated capacity. */
+typedef struct shpl_plan {
+    int32_t  n_rows;    /* R  = H_b' * W_b' * frames   (destination cells)            */
+    int32_t  n_src;     /* Q  = H_i' * W_i' * frames   (source pixels)                */
+    int32_t  capacity;  /* entries the arrays below can hold (>= candidate pairs)     */
+    int32_t* row_ptr;   /* [n_rows+1]  CSR offsets by destination row                 */
+    int32_t* csr_src;   /* [capacity]  linear source pixel of each entry              */
+    float*   csr_val;   /* [capacity]  non-homogeneous weight of each entry           */
+    int32_t* pix_ptr;   /* [n_src+1]   CSR^T offsets by source pixel                  */
+    int32_t* csrT_dst;  /* [capacity]  destination row of each entry                  */
+    float*   csrT_val;  /* [capacity]                                                 */
+    int32_t* counts;    /* [8] device: [0]=n after image clip, [1]=nnz (columns of M),
+                           [2]=entries left out of the CSRs because an index is out of
+                           range (TF-CPU raises InvalidArgumentError for those),
+                           [3]=entries in the CSRs; [4..7] reserved                   */
+} shpl_plan;
+
+int         shpl_abi_version(void);
+const char* shpl_last_error(void);
+
+/* Bytes of scratch the shpl_build_* / shpl_plan_from_coo calls need for up to
+ * n_max candidate pairs. */
+size_t shpl_build_workspace_bytes(int64_t n_max);
+
+/* gen_sparse_pooling_input_avod  (avod/avod/utils/sparse_pool_utils.py:6-20) with
+ * projectToImage / clip3DwithinImage (avod/avod/utils/transform.py:3-40) inlined.
+ *   points f64 [N,3] camera frame, voxel_indices i64 [N,2] = (x, zflip),
+ *   P_host f64 [12] = stereo_calib.p2 row-major, image size (W, H) in pixels.
+ * Writes the n surviving pairs, input order kept:
+ *   bv_index_out i64 [N,2] (first n rows), img_u_out / img_v_out f64 [N] (first n;
+ *   rows 0 and 1 of the reference's [3,n] img_index; row 2 is all zero),
+ *   counts[0] = n. */
+int shpl_gen_input_avod(const double* points, const int64_t* voxel_indices, int64_t N,
+                        const double* P_host, int32_t im_w, int32_t im_h,
+                        int64_t* bv_index_out, double* img_u_out, double* img_v_out,
+                        int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+
+/* produce_sparse_pooling_input  (avod/avod/utils/sparse_pool_utils.py:22-58; twin
+ * MV3D_TF_release/lib/utils/sparse_pool_utils.py:22-54; MV3D entry
+ * MV3D_TF_release/lib/networks/MV3D_voxel_train.py:89-91), plus the canonical
+ * CSR / CSR^T of the resulting M.
+ *   img_u, img_v f64 [n]  rows 0,1 of img_index -- FLOORED AND CLAMPED IN PLACE like
+ *                         the reference does (:30-34);
+ *   bv_index i64 [n,2]; image size (W,H); BEV size (H,W); stride_img = stride[0],
+ *   stride_bv = stride[1] (the reference's comment has them swapped, :23 vs :30,:38);
+ *   m_val f64 [>=nnz] or NULL (-> ones), indexed by output column k like the
+ *   reference (:56-57; it is NOT filtered by the row test);
+ *   src_h, src_w: height/width of the feature map that will be gathered from; pass
+ *   0,0 to use floor(H/stride_img), floor(W/stride_img).
+ * Outputs (any of the first four may be NULL):
+ *   Mij_pool i64 [n,2], img_index_flip_pool i64 [n,3], M_val_out f32 [n]
+ *   (first nnz rows valid), M_size_out i64 [2] (device), plan (see shpl_plan).
+ * row_base / pix_base are added to every destination row / source pixel and
+ * entry_base_dev (device int32*, may be NULL = 0) to every CSR offset, so that the
+ * frames of a batch can be stacked into one plan by consecutive calls;
+ * plan->row_ptr then points at the sub-array of this frame. */
+int shpl_produce_input(double* img_u, double* img_v, const int64_t* bv_index, int64_t n,
+                       int32_t im_w, int32_t im_h, int32_t bv_h, int32_t bv_w,
+                       int32_t stride_img, int32_t stride_bv, const double* m_val,
+                       int32_t src_h, int32_t src_w,
+                       int64_t* Mij_pool, int64_t* img_index_flip_pool, float* M_val_out, int64_t* M_size_out,
+                       const shpl_plan* plan, int32_t row_base, int32_t pix_base, const int32_t* entry_base_dev,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* The two functions above fused (the call kitti_dataset.py:376-378 makes per
+ * sample): no intermediate dict is materialised. */
+int shpl_build_avod(const double* points, const int64_t* voxel_indices, int64_t N,
+                    const double* P_host, int32_t im_w, int32_t im_h, int32_t bv_h, int32_t bv_w,
+                    int32_t stride_img, int32_t stride_bv, const double* m_val,
+                    int32_t src_h, int32_t src_w,
+                    int64_t* Mij_pool, int64_t* img_index_flip_pool, float* M_val_out, int64_t* M_size_out,
+                    const shpl_plan* plan, int32_t row_base, int32_t pix_base, const int32_t* entry_base_dev,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Plan from an arbitrary COO -- the tf.SparseTensor + gather index that crosses the
+ * reference's host->device boundary (placeholders avod/avod/core/models/rpn_model.py:219-242):
+ *   Mij i64 [m,2] = (row, col), val f32 [m], source_index [ncol,3] = (0, v, u) as int32
+ *   (index_is_i64 = 0) or int64 (= 1).  Entry e gathers pixel v*src_w+u of column col_e.
+ * counts[1] = m, counts[2] = entries with an out-of-range row / col / pixel. */
+int shpl_plan_from_coo(const int64_t* Mij, const float* val, int64_t m,
+                       const void* source_index, int32_t index_is_i64, int64_t ncol,
+                       int32_t src_h, int32_t src_w,
+                       const shpl_plan* plan, int32_t row_base, int32_t pix_base, const int32_t* entry_base_dev,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Forward of one direction: _sparse_pool_op + tf.concat
+ * (avod/avod/utils/sparse_pool_utils.py:96-103 with :67-72; for the reverse
+ * direction _sparse_pool_trans_op :105-117 with :82-87 -- pass the CSR^T arrays):
+ *   fused[r, 0:C_d]       = dst[r, :]
+ *   fused[r, C_d:C_d+C_s] = sum over the entries of row r, in stored order, of
+ *                           val * src[idx, :]      (0 for an empty row)
+ * dst [n_rows, C_d], src [n_src, C_s], fused [n_rows, C_d+C_s], all fp32.
+ * dst may be NULL with C_d = 0 (pooled map only: _sparse_pool_op without concat). */
+int shpl_pool_forward(const float* dst, const float* src,
+                      const int32_t* ptr, const int32_t* idx, const float* val,
+                      int32_t n_rows, int32_t C_d, int32_t n_src, int32_t C_s,
+                      float* fused, void* stream);
+
+/* Backward of shpl_pool_forward (what TF autodiff derives, SURVEY.md row a13;
+ * trainer.py:91-95 builds it): deterministic, no atomics.
+ *   g_dst[r, :] = g_fused[r, 0:C_d]
+ *   g_src[p, :] = sum over the entries of source p (transposed arrays: ptrT, idxT =
+ *                 destination row, valT), in stored order, of valT * g_fused[idxT, C_d:]
+ * g_dst may be NULL (no slice copy). */
+int shpl_pool_backward(const float* g_fused,
+                       const int32_t* ptrT, const int32_t* idxT, const float* valT,
+                       int32_t n_rows, int32_t C_d, int32_t n_src, int32_t C_s,
+                       float* g_dst, float* g_src, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHPL_H_ */

@@ -1,0 +1,19 @@
+"""sparse_pooling_b200 -- the Sparse Non-homogeneous Pooling Layer (SHPL) of
+YeungLy/Sparse_Pooling, rebuilt for B200 (sm_100a).
+
+Layout (only what the hot path needs):
+  csrc/                CUDA kernels + the C ABI of include/shpl.h  -> libshpl.so
+  _cabi.py             ctypes binding (no fallback: import fails without the library)
+  ops.py               CSR plan, workspace, autograd op around the pooling kernels
+  sparse_pool_utils.py drop-in mirror of the reference module (same names / signatures)
+  builder.py           batched device-resident correspondence builder
+  config.py            the model.proto / kitti_dataset.proto sparse-pooling switches
+"""
+from . import _cabi  # noqa: F401  (raises ImportError when libshpl.so is missing)
+from .config import (KittiDatasetSparsePoolingConfig, RetinaNetSparsePoolingConfig,  # noqa: F401
+                     RpnSparsePoolingConfig)
+from .ops import SparsePoolFunction, SparsePoolPlan, sparse_pool  # noqa: F401
+from .sparse_pool_utils import (SparsePoolLayer, SparseTensor, _sparse_pool_op, _sparse_pool_trans_op,  # noqa: F401
+                                concat_bn_op, gen_sparse_pooling_input_avod, produce_sparse_pooling_input,
+                                sparse_pool_layer)
+from .builder import build_avod_plan  # noqa: F401

@@ -1,0 +1,105 @@
+"""ctypes binding of libshpl.so -- the C ABI declared in include/shpl.h.
+
+The library is built in-tree by ``sparse_pooling_b200/csrc/Makefile`` (nvcc,
+sm_100a only).  There is NO fallback: if the shared object is missing or a symbol
+cannot be resolved, importing this module raises, and every op of the package
+fails loudly rather than computing on the CPU.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libshpl.so")
+
+c_void_p = ctypes.c_void_p
+c_int32 = ctypes.c_int32
+c_int64 = ctypes.c_int64
+c_size_t = ctypes.c_size_t
+
+SHPL_OK = 0
+SHPL_ERR_INVALID_ARGUMENT = -1
+SHPL_ERR_CUDA = -2
+SHPL_ERR_WORKSPACE_TOO_SMALL = -3
+SHPL_ERR_UNSUPPORTED = -4
+
+ABI_VERSION = 1
+
+
+class ShplPlan(ctypes.Structure):
+    """struct shpl_plan of include/shpl.h (device pointers are plain integers)."""
+    _fields_ = [
+        ("n_rows", c_int32),
+        ("n_src", c_int32),
+        ("capacity", c_int32),
+        ("row_ptr", c_void_p),
+        ("csr_src", c_void_p),
+        ("csr_val", c_void_p),
+        ("pix_ptr", c_void_p),
+        ("csrT_dst", c_void_p),
+        ("csrT_val", c_void_p),
+        ("counts", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); exactly the functions include/shpl.h declares
+SIGNATURES = {
+    "shpl_abi_version": (ctypes.c_int, []),
+    "shpl_last_error": (ctypes.c_char_p, []),
+    "shpl_build_workspace_bytes": (c_size_t, [c_int64]),
+    "shpl_gen_input_avod": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "shpl_produce_input": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64,
+                                          c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                          c_int32, c_int32,
+                                          c_void_p, c_void_p, c_void_p, c_void_p,
+                                          ctypes.POINTER(ShplPlan), c_int32, c_int32, c_void_p,
+                                          c_void_p, c_size_t, c_void_p]),
+    "shpl_build_avod": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p,
+                                       c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                       c_int32, c_int32,
+                                       c_void_p, c_void_p, c_void_p, c_void_p,
+                                       ctypes.POINTER(ShplPlan), c_int32, c_int32, c_void_p,
+                                       c_void_p, c_size_t, c_void_p]),
+    "shpl_plan_from_coo": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int64,
+                                          c_int32, c_int32,
+                                          ctypes.POINTER(ShplPlan), c_int32, c_int32, c_void_p,
+                                          c_void_p, c_size_t, c_void_p]),
+    "shpl_pool_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "shpl_pool_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+}
+
+
+class ShplError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libshpl.so not found at %s -- build it with `make -C sparse_pooling_b200/csrc` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.shpl_abi_version()
+    if got != ABI_VERSION:
+        raise ImportError("libshpl.so ABI version %d, binding expects %d" % (got, ABI_VERSION))
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what):
+    """Map the C status to the Python exceptions the reference's callers would see:
+    invalid arguments -> ValueError (reference: assert / TF InvalidArgumentError)."""
+    if rc == SHPL_OK:
+        return
+    msg = lib.shpl_last_error().decode("utf-8", "replace")
+    if rc in (SHPL_ERR_INVALID_ARGUMENT, SHPL_ERR_UNSUPPORTED):
+        raise ValueError("%s: %s" % (what, msg))
+    raise ShplError("%s failed (%d): %s" % (what, rc, msg))

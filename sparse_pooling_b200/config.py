@@ -1,0 +1,41 @@
+"""The sparse-pooling switches of the reference's protobuf configs, as dataclasses
+(`protoc` is not available here, and only these fields concern the SHPL path).
+
+Field names, numbers and defaults follow
+  /root/reference/avod/avod/protos/model.proto:86-91   (RpnConfig fields 6-10)
+  /root/reference/avod/avod/protos/model.proto:120-121 (RetinaNetConfig)
+  /root/reference/avod/avod/protos/kitti_dataset.proto:38-40
+Meanings: /root/reference/avod/README.md:120-125.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class RpnSparsePoolingConfig:
+    rpn_use_sparse_pooling: bool = False                # SHPL right before the RPN (rpn_model.py:328)
+    rpn_sparse_pooling_use_batch_norm: bool = False     # concat_bn_op instead of tf.concat
+    rpn_sparse_pooling_conv_after_fusion: bool = False  # caller's 3x3 conv back to C (rpn_model.py:338-354)
+    rpn_sparse_pooling_after_vgg: bool = False          # SHPL at conv4 inside FusionVggPyr (rpn_model.py:291)
+    rpn_dual_sparse_pooling_after_vgg: bool = False     # also pool BEV -> image there (rpn_model.py:294-298)
+
+    def bv_index_indicator(self):
+        """rpn_model.py:294-298: the dual switch is a non-None dummy array."""
+        return np.zeros((1, 3)) if self.rpn_dual_sparse_pooling_after_vgg else None
+
+
+@dataclass
+class RetinaNetSparsePoolingConfig:
+    use_sparse_pooling: bool = False
+    use_pyramid_level_at_SHPL: str = "P2"
+
+
+@dataclass
+class KittiDatasetSparsePoolingConfig:
+    output_indices: bool = False                        # SHPL is silently off when false (rpn_model.py:111-118)
+    use_pyramid_level_at_SHPL: str = "P0"
+
+    def feat_stride(self):
+        """kitti_dataset.py:375: 2 ** int(level[-1])."""
+        return 2 ** int(self.use_pyramid_level_at_SHPL[-1])

@@ -1,0 +1,34 @@
+// libshpl.so: error reporting and device queries behind the C ABI (include/shpl.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "shpl_common.cuh"
+
+namespace shpl {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static thread_local int cached_dev = -1;
+    static thread_local int cached = 148;  // B200
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return cached;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+}  // namespace shpl
+
+extern "C" int shpl_abi_version(void) { return SHPL_ABI_VERSION; }
+extern "C" const char* shpl_last_error(void) { return shpl::g_error; }

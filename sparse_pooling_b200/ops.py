@@ -1,0 +1,214 @@
+"""Device-side objects of the SHPL path: the CSR plan, the workspace, and the
+PyTorch autograd op around the two pooling kernels of libshpl.so.
+
+PyTorch is used only for device memory, streams and autograd bookkeeping; all
+arithmetic happens in the CUDA kernels reached through the ctypes C ABI
+(``_cabi.py`` / ``include/shpl.h``).  Nothing here computes on the CPU.
+"""
+import ctypes
+
+import torch
+
+from . import _cabi
+
+_lib = _cabi.lib
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: the SHPL kernels run on the GPU only (no CPU fallback)" % name)
+
+
+_workspaces = {}
+
+
+def workspace(device, n_max):
+    """Scratch for the builder, cached per device and grown on demand."""
+    need = int(_lib.shpl_build_workspace_bytes(int(n_max)))
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+class SparsePoolPlan:
+    """Canonical CSR (by destination BEV cell) + CSR^T (by source pixel) of one M,
+    or of the Ms of several frames stacked (struct shpl_plan of include/shpl.h).
+
+    rows_per_frame = H_b'*W_b', src_per_frame = H_i'*W_i'; with `frames` > 1 the
+    rows / pixels of frame f are offset by f*rows_per_frame / f*src_per_frame so a
+    [B,H,W,C] batch is pooled by one launch."""
+
+    def __init__(self, rows_per_frame, src_hw, capacity, device, frames=1):
+        self.frames = int(frames)
+        self.rows_per_frame = int(rows_per_frame)
+        self.src_hw = (int(src_hw[0]), int(src_hw[1]))
+        self.src_per_frame = self.src_hw[0] * self.src_hw[1]
+        self.capacity = int(max(capacity, 1))
+        self.device = device
+        R, Q = self.rows_per_frame * self.frames, self.src_per_frame * self.frames
+        if max(R, Q, self.capacity) >= 2 ** 31 - 1:
+            raise ValueError("SHPL plan too large for 32-bit indices")
+        i32 = dict(dtype=torch.int32, device=device)
+        self.row_ptr = torch.empty(R + 1, **i32)
+        self.pix_ptr = torch.empty(Q + 1, **i32)
+        self.csr_src = torch.empty(self.capacity, **i32)
+        self.csrT_dst = torch.empty(self.capacity, **i32)
+        self.csr_val = torch.empty(self.capacity, dtype=torch.float32, device=device)
+        self.csrT_val = torch.empty(self.capacity, dtype=torch.float32, device=device)
+        self.counts = torch.zeros((self.frames, 8), dtype=torch.int32, device=device)
+        self.nnz = None       # columns of M per frame (host ints), known after the builder's read-back
+        self.n_oob = None     # entries TF-CPU would reject, per frame
+
+    @property
+    def n_rows(self):
+        return self.rows_per_frame * self.frames
+
+    @property
+    def n_src(self):
+        return self.src_per_frame * self.frames
+
+    def frame_struct(self, f):
+        """shpl_plan for frame f: ptr arrays point at the frame's sub-array; entry arrays are shared."""
+        s = _cabi.ShplPlan()
+        s.n_rows = self.rows_per_frame
+        s.n_src = self.src_per_frame
+        s.capacity = self.capacity
+        s.row_ptr = self.row_ptr.data_ptr() + 4 * f * self.rows_per_frame
+        s.pix_ptr = self.pix_ptr.data_ptr() + 4 * f * self.src_per_frame
+        s.csr_src = self.csr_src.data_ptr()
+        s.csr_val = self.csr_val.data_ptr()
+        s.csrT_dst = self.csrT_dst.data_ptr()
+        s.csrT_val = self.csrT_val.data_ptr()
+        s.counts = self.counts.data_ptr() + 32 * f
+        return s
+
+    def entry_base(self, f):
+        """Device pointer to the running entry offset frame f must start at (None for frame 0)."""
+        if f == 0:
+            return None
+        return ctypes.c_void_p(self.counts.data_ptr() + 32 * (f - 1) + 16)   # counts[f-1][4]
+
+    def read_counts(self):
+        """One small device->host copy: fills nnz / n_oob (synchronises the stream)."""
+        c = self.counts.cpu()
+        self.nnz = [int(x) for x in c[:, 1]]
+        self.n_oob = [int(x) for x in c[:, 2]]
+        return c
+
+
+def plan_from_coo(indices, values, source_index, n_rows, src_hw, device=None):
+    """Plan of an arbitrary tf.SparseTensor-like COO (shpl_plan_from_coo)."""
+    require_cuda(indices, "M.indices")
+    device = indices.device
+    Mij = indices.to(torch.int64).contiguous().reshape(-1, 2)
+    val = values.to(device=device, dtype=torch.float32).contiguous().reshape(-1)
+    src_index = source_index.to(device=device)
+    if src_index.dtype not in (torch.int32, torch.int64):
+        src_index = src_index.to(torch.int64)
+    src_index = src_index.contiguous().reshape(-1, 3)
+    m = Mij.shape[0]
+    if val.shape[0] != m:
+        raise ValueError("M.values has %d entries, M.indices %d" % (val.shape[0], m))
+    plan = SparsePoolPlan(n_rows, src_hw, m, device)
+    ws = workspace(device, m)
+    st = plan.frame_struct(0)
+    rc = _lib.shpl_plan_from_coo(_ptr(Mij), _ptr(val), m, _ptr(src_index), int(src_index.dtype == torch.int64),
+                                 src_index.shape[0], plan.src_hw[0], plan.src_hw[1], ctypes.byref(st), 0, 0, None,
+                                 _ptr(ws), ws.numel(), _stream())
+    _cabi.check(rc, "shpl_plan_from_coo")
+    plan._keep = (Mij, val, src_index)
+    return plan
+
+
+def pool_forward(dst, src, ptr, idx, val, n_rows, n_src):
+    """fused[r] = concat(dst[r], sum_k val_k * src[idx_k])  (shpl_pool_forward)."""
+    require_cuda(src, "source feature map")
+    C_s = src.shape[-1]
+    C_d = 0 if dst is None else dst.shape[-1]
+    fused = torch.empty((n_rows, C_d + C_s), dtype=torch.float32, device=src.device)
+    rc = _lib.shpl_pool_forward(_ptr(dst), _ptr(src), _ptr(ptr), _ptr(idx), _ptr(val), n_rows, C_d, n_src, C_s,
+                                _ptr(fused), _stream())
+    _cabi.check(rc, "shpl_pool_forward")
+    return fused
+
+
+def pool_backward(g_fused, ptrT, idxT, valT, n_rows, C_d, n_src, C_s, want_dst=True):
+    g_dst = torch.empty((n_rows, C_d), dtype=torch.float32, device=g_fused.device) if (want_dst and C_d) else None
+    g_src = torch.empty((n_src, C_s), dtype=torch.float32, device=g_fused.device)
+    rc = _lib.shpl_pool_backward(_ptr(g_fused), _ptr(ptrT), _ptr(idxT), _ptr(valT), n_rows, C_d, n_src, C_s,
+                                 _ptr(g_dst), _ptr(g_src), _stream())
+    _cabi.check(rc, "shpl_pool_backward")
+    return g_dst, g_src
+
+
+class SparsePoolFunction(torch.autograd.Function):
+    """One direction of SHPL with the channel concat fused in.
+
+    transposed=False: img -> bev  (_sparse_pool_op + tf.concat, sparse_pool_utils.py:65-72)
+    transposed=True : bev -> img  (_sparse_pool_trans_op + tf.concat, :79-87)
+    dst may be None: the pooled map alone (the bare _sparse_pool_op / _sparse_pool_trans_op).
+    Backward is the deterministic transpose-CSR kernel; no gradient
+    flows to M's values (they are a placeholder in the reference, rpn_model.py:219-242)."""
+
+    @staticmethod
+    def forward(ctx, dst, src, plan, transposed):
+        require_cuda(src, "source feature map")
+        B = src.shape[0]
+        if B != plan.frames:
+            raise ValueError("feature batch %d != frames in the plan %d" % (B, plan.frames))
+        if transposed:
+            ptr, idx, val, n_rows, n_src = plan.pix_ptr, plan.csrT_dst, plan.csrT_val, plan.n_src, plan.n_rows
+        else:
+            ptr, idx, val, n_rows, n_src = plan.row_ptr, plan.csr_src, plan.csr_val, plan.n_rows, plan.n_src
+        src_c = src.contiguous()
+        if src_c.dtype != torch.float32:
+            raise ValueError("SHPL feature maps must be float32 (the reference's dtype)")
+        if src_c.shape[0] * src_c.shape[1] * src_c.shape[2] != n_src:
+            raise ValueError("source map %s does not match the plan (%d cells)" % (tuple(src.shape), n_src))
+        dst_c = None
+        if dst is not None:
+            require_cuda(dst, "destination feature map")
+            dst_c = dst.contiguous()
+            if dst_c.shape[0] * dst_c.shape[1] * dst_c.shape[2] != n_rows:
+                raise ValueError("destination map %s does not match the plan (%d cells)" % (tuple(dst.shape), n_rows))
+        fused = pool_forward(dst_c, src_c, ptr, idx, val, n_rows, n_src)
+        ctx.plan = plan
+        ctx.transposed = transposed
+        ctx.src_shape = tuple(src.shape)
+        ctx.dst_shape = None if dst is None else tuple(dst.shape)
+        return fused
+
+    @staticmethod
+    def backward(ctx, g_fused):
+        plan = ctx.plan
+        if ctx.transposed:   # entries grouped by what was the *source* of the forward
+            ptrT, idxT, valT, n_rows, n_src = plan.row_ptr, plan.csr_src, plan.csr_val, plan.n_src, plan.n_rows
+        else:
+            ptrT, idxT, valT, n_rows, n_src = plan.pix_ptr, plan.csrT_dst, plan.csrT_val, plan.n_rows, plan.n_src
+        C_s = ctx.src_shape[-1]
+        C_d = 0 if ctx.dst_shape is None else ctx.dst_shape[-1]
+        g = g_fused.contiguous()
+        g_dst, g_src = pool_backward(g, ptrT, idxT, valT, n_rows, C_d, n_src, C_s,
+                                     want_dst=ctx.needs_input_grad[0] and C_d > 0)
+        if g_dst is not None:
+            g_dst = g_dst.reshape(ctx.dst_shape)
+        return g_dst, g_src.reshape(ctx.src_shape), None, None
+
+
+def sparse_pool(dst, src, plan, transposed=False):
+    """[B,Hd,Wd,Cd] (or None), [B,Hs,Ws,Cs] -> [B,Hd,Wd,Cd+Cs]."""
+    fused = SparsePoolFunction.apply(dst, src, plan, transposed)
+    if dst is not None:
+        return fused.reshape(dst.shape[0], dst.shape[1], dst.shape[2], -1)
+    return fused

@@ -1,0 +1,93 @@
+"""CPU-side checks of the drop-in boundary: libshpl.so loads, exports exactly the
+symbols include/shpl.h declares, and rejects bad arguments before touching a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "shpl.h")
+LIB = os.path.join(ROOT, "sparse_pooling_b200", "libshpl.so")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(shpl_[a-z_0-9]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        import __graft_entry__
+        __graft_entry__.build()
+    return ctypes.CDLL(LIB)
+
+
+def test_header_declares_the_expected_entry_points():
+    assert declared_functions() == sorted([
+        "shpl_abi_version", "shpl_last_error", "shpl_build_workspace_bytes", "shpl_gen_input_avod",
+        "shpl_produce_input", "shpl_build_avod", "shpl_plan_from_coo", "shpl_pool_forward", "shpl_pool_backward"])
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in declared_functions():
+        assert hasattr(lib, name), "libshpl.so does not export %s" % name
+
+
+def test_binding_covers_the_header(lib):
+    from sparse_pooling_b200 import _cabi
+    assert sorted(_cabi.SIGNATURES) == declared_functions()
+    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 1
+
+
+def test_workspace_query_grows_with_n(lib):
+    lib.shpl_build_workspace_bytes.restype = ctypes.c_size_t
+    lib.shpl_build_workspace_bytes.argtypes = [ctypes.c_int64]
+    a, b = lib.shpl_build_workspace_bytes(1000), lib.shpl_build_workspace_bytes(1000000)
+    assert 0 < a < b and b >= 1000000 * (4 * 8 + 12)
+
+
+def test_invalid_arguments_return_error_codes_without_a_gpu(lib):
+    from sparse_pooling_b200 import _cabi
+    L = _cabi.lib
+    assert L.shpl_pool_forward(None, None, None, None, None, 10, 4, 10, 0, None, None) == _cabi.SHPL_ERR_INVALID_ARGUMENT
+    assert b"bad sizes" in L.shpl_last_error()
+    assert L.shpl_pool_backward(None, None, None, None, 10, 4, 10, 4, None, None, None) == _cabi.SHPL_ERR_INVALID_ARGUMENT
+    with pytest.raises(ValueError):
+        _cabi.check(L.shpl_pool_forward(None, None, None, None, None, -1, 4, 10, 4, None, None), "shpl_pool_forward")
+    st = _cabi.ShplPlan()
+    rc = L.shpl_produce_input(None, None, None, 0, 8, 8, 8, 8, 0, 1, None, 0, 0, None, None, None, None,
+                              ctypes.byref(st), 0, 0, None, None, 0, None)
+    assert rc == _cabi.SHPL_ERR_INVALID_ARGUMENT and b"stride" in L.shpl_last_error()
+
+
+def test_product_package_does_not_import_the_oracle():
+    """The oracle is test infrastructure: nothing under sparse_pooling_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "sparse_pooling_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "libshpl_oracle" not in src, f
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from sparse_pooling_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.require_cuda(torch.zeros(2), "x")
+
+
+def test_config_dataclasses_mirror_the_proto_fields():
+    import numpy as np
+    from sparse_pooling_b200 import KittiDatasetSparsePoolingConfig, RpnSparsePoolingConfig
+    c = RpnSparsePoolingConfig()
+    assert [c.rpn_use_sparse_pooling, c.rpn_sparse_pooling_use_batch_norm, c.rpn_sparse_pooling_conv_after_fusion,
+            c.rpn_sparse_pooling_after_vgg, c.rpn_dual_sparse_pooling_after_vgg] == [False] * 5   # model.proto:87-91
+    assert c.bv_index_indicator() is None
+    c.rpn_dual_sparse_pooling_after_vgg = True
+    assert np.array_equal(c.bv_index_indicator(), np.zeros((1, 3)))                            # rpn_model.py:295
+    assert KittiDatasetSparsePoolingConfig(use_pyramid_level_at_SHPL="P3").feat_stride() == 8    # kitti_dataset.py:375

@@ -1,0 +1,409 @@
+"""GPU parity tests: the CUDA path (through the ctypes C ABI of libshpl.so) against
+the CPU oracle and the reference-run golden fixtures.  Index / CSR work must be
+bit-exact; pooled features and gradients are compared bit-exact too where the
+summation order equals the oracle's, and within 1e-5 relative (the north_star's
+fp32 bound) otherwise.  Run with `pytest -m gpu` on a B200."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import cref, index_oracle as io, synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def shpl():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import sparse_pooling_b200 as m
+    return m
+
+
+class Calib:
+    def __init__(self, p2):
+        self.p2 = p2
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def plan_arrays(plan, f=0):
+    """Host copies of one frame's CSR / CSR^T (entry offsets made frame-local)."""
+    c = plan.counts.cpu().numpy()
+    R, Q = plan.rows_per_frame, plan.src_per_frame
+    row_ptr = plan.row_ptr.cpu().numpy()[f * R:(f + 1) * R + 1]
+    pix_ptr = plan.pix_ptr.cpu().numpy()[f * Q:(f + 1) * Q + 1]
+    lo, hi = int(row_ptr[0]), int(row_ptr[-1])
+    return dict(row_ptr=row_ptr - lo, pix_ptr=pix_ptr - lo,
+                csr_src=plan.csr_src.cpu().numpy()[lo:hi] - f * Q, csr_val=plan.csr_val.cpu().numpy()[lo:hi],
+                csrT_dst=plan.csrT_dst.cpu().numpy()[lo:hi] - f * R, csrT_val=plan.csrT_val.cpu().numpy()[lo:hi],
+                counts=c[f])
+
+
+def assert_plan_equals_oracle(plan, Mij, val, flip, n_rows, src_hw, f=0):
+    ref = io.build_plan(Mij, val, flip, n_rows, src_hw[0], src_hw[1])
+    got = plan_arrays(plan, f)
+    for k in ("row_ptr", "pix_ptr", "csr_src", "csr_val", "csrT_dst", "csrT_val"):
+        np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
+    assert int(got["counts"][2]) == ref["n_oob"]
+    assert int(got["counts"][3]) == len(ref["csr_src"])
+
+
+# ------------------------------------------------------------------ builder: KATs
+def test_kat1_through_the_dropin_api(shpl, golden_dir):
+    g = load(golden_dir, "kat1.npz")
+    d = shpl.gen_sparse_pooling_input_avod(g["points"], g["voxel_indices"], Calib(g["P"]), list(g["im_size"]), tuple(g["bv_size"]))
+    assert isinstance(d["img_index"], np.ndarray) and d["img_index"].dtype == np.float64
+    np.testing.assert_array_equal(d["bv_index"], g["gen_bv_index"])
+    np.testing.assert_array_equal(d["img_index"], g["gen_img_index"])
+    assert d["img_index"][0].tolist() == [0, 2, 2, 0, 9, 8]       # 0.5->0, 1.5->2, 2.5->2, -0.0 kept, -1e-9 dropped
+    o = shpl.produce_sparse_pooling_input(d, stride=[2, 2])
+    for k in ("Mij_pool", "M_val", "M_size", "img_index_flip_pool"):
+        np.testing.assert_array_equal(o[k], g[k], err_msg=k)
+        assert o[k].dtype == g[k].dtype, k
+    np.testing.assert_array_equal(d["img_index"], g["img_index_after"])      # in-place mutation reproduced
+    assert o["bev_index_flip_pool"].shape == (0, 3)
+    assert_plan_equals_oracle(o["shpl_plan"], g["Mij_pool"], np.ones(5), g["img_index_flip_pool"], 32, (3, 5))
+
+
+def test_kat2_row_filter_and_x_wrap(shpl, golden_dir):
+    g = load(golden_dir, "kat2.npz")
+    d = {k[3:]: np.array(g[k]) for k in g.files if k.startswith("in_")}
+    o = shpl.produce_sparse_pooling_input(d, stride=[1, 1])
+    assert o["Mij_pool"].tolist() == [[115, 0], [127, 1], [112, 2]]
+    for k in ("Mij_pool", "M_val", "M_size", "img_index_flip_pool"):
+        np.testing.assert_array_equal(o[k], g[k], err_msg=k)
+
+
+def test_wrong_img_index_shape_asserts(shpl):
+    d = synth.direct_pairs(0, 10)
+    d["img_index"] = d["img_index"][:2]
+    with pytest.raises(AssertionError):
+        shpl.produce_sparse_pooling_input(d)
+
+
+def test_cpu_feature_maps_are_rejected(shpl):
+    d = synth.direct_pairs(0, 50, bev_hw=(8, 8), img_wh=(8, 8))
+    o = shpl.produce_sparse_pooling_input(d)
+    with pytest.raises(RuntimeError):
+        shpl.sparse_pool_layer([torch.zeros(1, 8, 8, 4), torch.zeros(1, 8, 8, 4)], [4, 4], o,
+                               img_index_flip=o["img_index_flip_pool"])
+
+
+# ------------------------------------------- builder: reference-run frame fixtures
+@pytest.mark.parametrize("seed,az", [(1, 0.09), (2, 0.05)])
+def test_avod_frame_matches_reference_fixture(shpl, golden_dir, seed, az):
+    g = load(golden_dir, "avod_frame_seed%d.npz" % seed)
+    frame = synth.avod_frame(seed, az_step_deg=az)
+    for s in (1, 4, 8):
+        d = shpl.gen_sparse_pooling_input_avod(frame["points"], frame["voxel_indices"], Calib(frame["P"]),
+                                               frame["im_size"], frame["bv_size"])
+        if s == 1:
+            np.testing.assert_array_equal(d["bv_index"], g["gen_bv_index"])
+            np.testing.assert_array_equal(d["img_index"], g["gen_img_index"].astype(np.float64))
+        o = shpl.produce_sparse_pooling_input(d, stride=[s, s])
+        np.testing.assert_array_equal(o["Mij_pool"][:, 0], g["Mij_pool_s%d" % s])
+        np.testing.assert_array_equal(o["Mij_pool"][:, 1], np.arange(len(o["Mij_pool"])))
+        np.testing.assert_array_equal(o["M_size"], g["M_size_s%d" % s])
+        np.testing.assert_array_equal(o["img_index_flip_pool"], g["flip_s%d" % s])
+        assert o["Mij_pool"].dtype == np.int64 and o["img_index_flip_pool"].dtype == np.int64
+        R = int(o["M_size"][0])
+        assert_plan_equals_oracle(o["shpl_plan"], o["Mij_pool"], np.ones(len(o["Mij_pool"])), o["img_index_flip_pool"],
+                                  R, (360 // s, 1200 // s))
+        # fused device-resident builder gives the same COO and plan
+        plan, coo = shpl.build_avod_plan(frame["points"], frame["voxel_indices"], frame["P"], frame["im_size"],
+                                         frame["bv_size"], stride=(s, s), want_coo=True)
+        nnz = plan.nnz[0]
+        np.testing.assert_array_equal(coo[0][0][:nnz].cpu().numpy(), o["Mij_pool"])
+        np.testing.assert_array_equal(coo[0][1][:nnz].cpu().numpy(), o["img_index_flip_pool"])
+        np.testing.assert_array_equal(coo[0][3].cpu().numpy(), o["M_size"])
+        assert_plan_equals_oracle(plan, o["Mij_pool"], np.ones(nnz), o["img_index_flip_pool"], R, (360 // s, 1200 // s))
+
+
+@pytest.mark.parametrize("name,kw", [("direct_uniform", dict(seed=0, n=20000)),
+                                     ("direct_ground", dict(seed=3, n=50000, skew="ground")),
+                                     ("direct_zipf", dict(seed=4, n=30000, skew="zipf"))])
+def test_direct_pairs_match_reference_fixture(shpl, golden_dir, name, kw):
+    g = load(golden_dir, name + ".npz")
+    d0 = synth.direct_pairs(**kw)
+    for s in ((1, 1), (8, 8), (8, 2)):
+        d = {k: np.array(v, copy=True) for k, v in d0.items()}
+        o = shpl.produce_sparse_pooling_input(d, stride=list(s))
+        tag = "s%d_%d" % s
+        np.testing.assert_array_equal(o["Mij_pool"][:, 0], g["row_" + tag])
+        np.testing.assert_array_equal(o["M_size"], g["M_size_" + tag])
+        np.testing.assert_array_equal(o["img_index_flip_pool"], g["flip_" + tag])
+        R = int(o["M_size"][0])
+        assert_plan_equals_oracle(o["shpl_plan"], o["Mij_pool"], np.ones(len(o["Mij_pool"])), o["img_index_flip_pool"],
+                                  R, (360 // s[0], 1200 // s[0]))
+
+
+def test_mv3d_weights_and_strides(shpl, golden_dir):
+    """MV3D entry (MV3D_voxel_train.py:89-91): external non-homogeneous M_val = 1/count, stride [8,2]."""
+    g = load(golden_dir, "mv3d_seed5.npz")
+    img_index = np.vstack((g["img_index"][:2], np.zeros((1, g["img_index"].shape[1])))).astype(np.float64)
+    d = dict(img_index=img_index, img_size=np.array([1280, 384]), bv_index=g["bv_index"].astype(np.int64), bv_size=[200, 240])
+    o = shpl.produce_sparse_pooling_input(d, M_val=g["M_val"], stride=[8, 2])
+    np.testing.assert_array_equal(o["Mij_pool"][:, 0], g["row"])
+    np.testing.assert_array_equal(o["M_size"], g["M_size"])
+    np.testing.assert_array_equal(o["img_index_flip_pool"], g["flip"])
+    assert o["M_val"] is not None and np.array_equal(o["M_val"], g["M_val"])
+    assert_plan_equals_oracle(o["shpl_plan"], o["Mij_pool"], g["M_val"].astype(np.float32), o["img_index_flip_pool"],
+                              12000, (48, 160))
+
+
+def test_torch_cuda_inputs_stay_on_device(shpl):
+    d0 = synth.direct_pairs(11, 3000, bev_hw=(64, 80), img_wh=(96, 40))
+    ref = io.produce_sparse_pooling_input({k: np.array(v, copy=True) for k, v in d0.items()}, stride=[2, 2])
+    d = dict(bv_index=torch.from_numpy(d0["bv_index"]).cuda(), img_index=torch.from_numpy(d0["img_index"]).cuda(),
+             bv_size=d0["bv_size"], img_size=d0["img_size"])
+    o = shpl.produce_sparse_pooling_input(d, stride=[2, 2])
+    assert o["Mij_pool"].is_cuda and o["img_index_flip_pool"].is_cuda
+    np.testing.assert_array_equal(o["Mij_pool"].cpu().numpy(), ref["Mij_pool"])
+    np.testing.assert_array_equal(o["img_index_flip_pool"].cpu().numpy(), ref["img_index_flip_pool"])
+    ref_after = {k: np.array(v, copy=True) for k, v in d0.items()}
+    io.produce_sparse_pooling_input(ref_after, stride=[2, 2])
+    np.testing.assert_array_equal(d["img_index"].cpu().numpy(), ref_after["img_index"])   # mutated in place on the device
+
+
+# --------------------------------------------------------------- builder: edge cases
+def test_empty_frame(shpl):
+    d = dict(bv_index=np.zeros((0, 2), dtype=np.int64), img_index=np.zeros((3, 0)), bv_size=np.array([8, 8]), img_size=np.array([8, 8]))
+    o = shpl.produce_sparse_pooling_input(d)
+    assert o["Mij_pool"].shape == (0, 2) and o["M_size"].tolist() == [64, 0]
+    p = plan_arrays(o["shpl_plan"])
+    assert (p["row_ptr"] == 0).all() and (p["pix_ptr"] == 0).all()
+    bev = torch.randn(1, 8, 8, 8, device="cuda")
+    img = torch.randn(1, 8, 8, 4, device="cuda")
+    fused, _ = shpl.sparse_pool_layer([bev, img], [4, 8], o, img_index_flip=o["img_index_flip_pool"])
+    assert torch.equal(fused[..., :8], bev) and (fused[..., 8:] == 0).all()
+
+
+def test_all_points_outside_image(shpl):
+    pts = np.array([[100.0, 0.0, 1.0], [0.0, 100.0, 1.0], [0.0, 0.0, -1.0]])
+    d = shpl.gen_sparse_pooling_input_avod(pts, np.zeros((3, 2), dtype=np.int64), Calib(synth.P2_KITTI), [1200, 360], (700, 800))
+    assert d["img_index"].shape == (3, 0) and d["bv_index"].shape == (0, 2)
+
+
+def test_out_of_range_indices_are_counted_not_read(shpl):
+    """Negative pixels / rows (possible after MV3D's augment_fv, quirk A.4-10): TF-CPU raises;
+    here the COO is reproduced bit-exact, the CSR leaves the entries out and the layer raises."""
+    d = dict(bv_index=np.array([[0, 0], [1, 0], [-5, 0], [2, 1]], dtype=np.int64),
+             img_index=np.array([[1.0, -3.0, 2.0, 7.0], [1.0, 1.0, 1.0, -1.0], [0, 0, 0, 0]]),
+             bv_size=np.array([4, 4]), img_size=np.array([8, 8]))
+    ref = io.produce_sparse_pooling_input({k: np.array(v, copy=True) for k, v in d.items()})
+    o = shpl.produce_sparse_pooling_input(d)
+    np.testing.assert_array_equal(o["Mij_pool"], ref["Mij_pool"])
+    np.testing.assert_array_equal(o["img_index_flip_pool"], ref["img_index_flip_pool"])
+    plan = o["shpl_plan"]
+    assert plan.n_oob == [3]
+    assert_plan_equals_oracle(plan, ref["Mij_pool"], np.ones(4), ref["img_index_flip_pool"], 16, (8, 8))
+    bev = torch.randn(1, 4, 4, 4, device="cuda")
+    img = torch.randn(1, 8, 8, 4, device="cuda")
+    with pytest.raises(ValueError):
+        shpl.sparse_pool_layer([bev, img], [4, 4], o, img_index_flip=o["img_index_flip_pool"])
+
+
+def test_plan_from_arbitrary_coo(shpl):
+    """M handed over as a bare tf.SparseTensor-like triple + int32 gather index (rpn_model.py:219-242)."""
+    rng = np.random.default_rng(5)
+    m, R, Hs, Ws = 7000, 900, 20, 30
+    Mij = np.stack((rng.integers(0, R, m), rng.permutation(m)), axis=1).astype(np.int64)
+    flip = np.stack((np.zeros(m, np.int64), rng.integers(0, Hs, m), rng.integers(0, Ws, m)), axis=1)
+    val = rng.random(m).astype(np.float32)
+    M = shpl.SparseTensor(torch.from_numpy(Mij).cuda(), torch.from_numpy(val).cuda(), np.array([R, m]))
+    from sparse_pooling_b200 import sparse_pool_utils as spu
+    plan = spu._resolve_plan(M, torch.from_numpy(flip.astype(np.int32)).cuda(), R, (Hs, Ws), torch.device("cuda"))
+    assert_plan_equals_oracle(plan, Mij, val, flip, R, (Hs, Ws))
+
+
+def test_stacked_batch_plan(shpl):
+    frames = [synth.avod_frame(s, az_step_deg=0.4) for s in (3, 4, 5)]
+    plan = shpl.build_avod_plan([f["points"] for f in frames], [f["voxel_indices"] for f in frames],
+                                [f["P"] for f in frames], [1200, 360], (700, 800), stride=(4, 4))
+    for i, f in enumerate(frames):
+        d = io.gen_sparse_pooling_input_avod(f["points"], f["voxel_indices"], f["P"], [1200, 360], (700, 800))
+        o = io.produce_sparse_pooling_input(d, stride=[4, 4])
+        assert plan.nnz[i] == len(o["Mij_pool"])
+        assert_plan_equals_oracle(plan, o["Mij_pool"], np.ones(len(o["Mij_pool"])), o["img_index_flip_pool"], 175 * 200, (90, 300), f=i)
+
+
+# ----------------------------------------------------------------- pooling kernels
+def _case(seed, n, bev_hw, img_hw, cb, ci, skew="uniform", weights=False):
+    d = synth.direct_pairs(seed, n, bev_hw=bev_hw, img_wh=(img_hw[1], img_hw[0]), skew=skew)
+    o = io.produce_sparse_pooling_input(d, stride=[1, 1])
+    rng = np.random.default_rng(seed + 100)
+    nnz = len(o["Mij_pool"])
+    val = (1.0 / rng.integers(1, 46, nnz)).astype(np.float32) if weights else np.ones(nnz, np.float32)
+    bev = rng.standard_normal((1,) + tuple(bev_hw) + (cb,), dtype=np.float32)
+    img = rng.standard_normal((1,) + tuple(img_hw) + (ci,), dtype=np.float32)
+    return o, val, bev, img
+
+
+POOL_CASES = [
+    # seed, pairs, bev HxW, img HxW, C_bev, C_img, skew, weights
+    (0, 400, (9, 11), (7, 13), 8, 12, "uniform", True),
+    (1, 3000, (40, 50), (30, 60), 32, 32, "uniform", False),
+    (2, 3000, (40, 50), (30, 60), 16, 64, "ground", True),
+    (3, 2000, (33, 47), (21, 35), 3, 3, "uniform", True),       # raw RGB pooling (MV3D tests/test_sparse_pooling.py:55-69)
+    (4, 2000, (33, 47), (21, 35), 6, 10, "zipf", True),         # float2 path
+    (5, 4000, (25, 30), (12, 40), 256, 256, "uniform", False),  # stride-8 VGG conv4 depth
+    (6, 5000, (20, 24), (12, 40), 768, 768, "ground", True),    # MV3D depth, long rows
+]
+
+
+@pytest.mark.parametrize("case", POOL_CASES, ids=lambda c: "seed%d_C%dx%d_%s" % (c[0], c[4], c[5], c[6]))
+def test_layer_forward_backward_dual_bitexact(shpl, case):
+    seed, n, bev_hw, img_hw, cb, ci, skew, weights = case
+    o, val, bev, img = _case(seed, n, bev_hw, img_hw, cb, ci, skew, weights)
+    Mij, flip = o["Mij_pool"], o["img_index_flip_pool"]
+    M = shpl.SparseTensor(torch.from_numpy(Mij).cuda(), torch.from_numpy(val).cuda(), o["M_size"])
+    tb = torch.from_numpy(bev).cuda().requires_grad_(True)
+    ti = torch.from_numpy(img).cuda().requires_grad_(True)
+    bv_fused, img_fused = shpl.sparse_pool_layer([tb, ti], [ci, cb], M, img_index_flip=torch.from_numpy(flip.astype(np.int32)).cuda(),
+                                                 bv_index=np.zeros((1, 3)))
+    ref_bv = cref.forward(bev[0], img[0], Mij, val, flip)
+    ref_img = cref.forward_trans(img[0], bev[0], Mij, val, flip)
+    np.testing.assert_array_equal(bv_fused[0].detach().cpu().numpy(), ref_bv)
+    np.testing.assert_array_equal(img_fused[0].detach().cpu().numpy(), ref_img)
+    rng = np.random.default_rng(seed + 200)
+    g1 = rng.standard_normal(ref_bv.shape, dtype=np.float32)
+    g2 = rng.standard_normal(ref_img.shape, dtype=np.float32)
+    torch.autograd.backward([bv_fused, img_fused], [torch.from_numpy(g1[None]).cuda(), torch.from_numpy(g2[None]).cuda()])
+    gd, gs = cref.backward(g1, Mij, val, flip, cb, img.shape[1:])
+    gi, gb = cref.backward_trans(g2, Mij, val, flip, ci, bev.shape[1:])
+    np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd + gb)
+    np.testing.assert_array_equal(ti.grad[0].cpu().numpy(), gi + gs)
+
+
+def test_bare_ops_match_reference_shapes(shpl):
+    """_sparse_pool_op / _sparse_pool_trans_op as MV3D's Network.sparse_pool calls them (network.py:242-246)."""
+    o, val, bev, img = _case(7, 1500, (20, 24), (12, 40), 8, 16, "uniform", True)
+    Mij, flip = o["Mij_pool"], o["img_index_flip_pool"]
+    M = shpl.SparseTensor(torch.from_numpy(Mij).cuda(), torch.from_numpy(val).cuda(), o["M_size"])
+    idx = torch.from_numpy(flip.astype(np.int32)).cuda()
+    pooled = shpl._sparse_pool_op(M, torch.from_numpy(img).cuda(), idx, [1, 20, 24, 16])
+    assert tuple(pooled.shape) == (1, 20, 24, 16)
+    ref = cref.forward(bev[0], img[0], Mij, val, flip)[..., 8:]
+    np.testing.assert_array_equal(pooled[0].cpu().numpy(), ref)
+    pooled_t = shpl._sparse_pool_trans_op(M, torch.from_numpy(bev).cuda(), idx, [1, 12, 40, 8])
+    ref_t = cref.forward_trans(img[0], bev[0], Mij, val, flip)[..., 16:]
+    np.testing.assert_array_equal(pooled_t[0].cpu().numpy(), ref_t)
+
+
+def test_batched_frames_one_launch(shpl):
+    frames = [synth.avod_frame(s, az_step_deg=0.4) for s in (6, 7)]
+    plan = shpl.build_avod_plan([f["points"] for f in frames], [f["voxel_indices"] for f in frames],
+                                [f["P"] for f in frames], [1200, 360], (700, 800), stride=(8, 8))
+    rng = np.random.default_rng(0)
+    bev = rng.standard_normal((2, 87, 100, 16), dtype=np.float32)
+    img = rng.standard_normal((2, 45, 150, 8), dtype=np.float32)
+    tb, ti = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
+    fused = shpl.sparse_pool(tb, ti, plan)
+    g = rng.standard_normal(tuple(fused.shape), dtype=np.float32)
+    fused.backward(torch.from_numpy(g).cuda())
+    for i, f in enumerate(frames):
+        d = io.gen_sparse_pooling_input_avod(f["points"], f["voxel_indices"], f["P"], [1200, 360], (700, 800))
+        o = io.produce_sparse_pooling_input(d, stride=[8, 8])
+        val = np.ones(len(o["Mij_pool"]), np.float32)
+        np.testing.assert_array_equal(fused[i].detach().cpu().numpy(), cref.forward(bev[i], img[i], o["Mij_pool"], val, o["img_index_flip_pool"]))
+        gd, gs = cref.backward(g[i], o["Mij_pool"], val, o["img_index_flip_pool"], 16, (45, 150, 8))
+        np.testing.assert_array_equal(tb.grad[i].cpu().numpy(), gd)
+        np.testing.assert_array_equal(ti.grad[i].cpu().numpy(), gs)
+
+
+def test_batch_norm_variant(shpl):
+    """use_bn=True (concat_bn_op, sparse_pool_utils.py:120-124): each map normalised on its own, then concat."""
+    o, val, bev, img = _case(8, 1500, (20, 24), (12, 40), 8, 16, "uniform", False)
+    tb, ti = torch.from_numpy(bev).cuda(), torch.from_numpy(img).cuda()
+    fused, _ = shpl.sparse_pool_layer([tb, ti], [16, 8], o | {"M_val": val}, img_index_flip=o["img_index_flip_pool"], use_bn=True)
+    ref = cref.forward(bev[0], img[0], o["Mij_pool"], val, o["img_index_flip_pool"])
+
+    def bn(x):
+        x = x.astype(np.float64)
+        return (x - x.mean(axis=(0, 1))) / np.sqrt(x.var(axis=(0, 1)) + 1e-3)
+    want = np.concatenate([bn(ref[..., :8]), bn(ref[..., 8:])], axis=2)
+    np.testing.assert_allclose(fused[0].cpu().numpy(), want, rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------- full KITTI size (BASELINE configs)
+def test_kitti_stride1_full_size_against_c_oracle(shpl):
+    """Config 1: BEV 700x800x32 <- image 360x1200x32, ~20k pairs, forward + backward, bit-exact
+    against the plain-C oracle at the full size."""
+    frame = synth.avod_frame(2, az_step_deg=0.05)
+    d = shpl.gen_sparse_pooling_input_avod(frame["points"], frame["voxel_indices"], Calib(frame["P"]), frame["im_size"], frame["bv_size"])
+    o = shpl.produce_sparse_pooling_input(d, stride=[1, 1])
+    rng = np.random.default_rng(1)
+    bev = rng.standard_normal((1, 700, 800, 32), dtype=np.float32)
+    img = rng.standard_normal((1, 360, 1200, 32), dtype=np.float32)
+    tb, ti = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
+    M = shpl.SparseTensor.from_sparse_pooling_input(o)
+    fused, img_out = shpl.sparse_pool_layer([tb, ti], [32, 32], M, img_index_flip=o["img_index_flip_pool"], bv_index=None)
+    assert img_out is ti
+    nnz = len(o["Mij_pool"])
+    val = np.ones(nnz, np.float32)
+    ref = cref.forward(bev[0], img[0], o["Mij_pool"], val, o["img_index_flip_pool"])
+    np.testing.assert_array_equal(fused[0].detach().cpu().numpy(), ref)
+    g = rng.standard_normal(ref.shape, dtype=np.float32)
+    fused.backward(torch.from_numpy(g[None]).cuda())
+    gd, gs = cref.backward(g, o["Mij_pool"], val, o["img_index_flip_pool"], 32, (360, 1200, 32))
+    np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd)
+    np.testing.assert_array_equal(ti.grad[0].cpu().numpy(), gs)
+    # size-independent properties: the dense half is a copy, the pooled half is linear in the source map
+    assert torch.equal(fused[..., :32].detach(), tb.detach())
+    fused2, _ = shpl.sparse_pool_layer([tb.detach(), 2.0 * ti.detach()], [32, 32], M, img_index_flip=o["img_index_flip_pool"])
+    assert torch.equal(fused2[..., 32:], 2.0 * fused[..., 32:].detach())
+    # checksum of checksums: sum of the pooled half equals the sum of the gathered rows (fp64 on the host)
+    pix = o["img_index_flip_pool"][:, 1] * 1200 + o["img_index_flip_pool"][:, 2]
+    want = img[0].reshape(-1, 32)[pix].astype(np.float64).sum()
+    got = fused[0, :, :, 32:].detach().double().sum().item()
+    assert abs(got - want) <= 1e-5 * np.abs(img[0].reshape(-1, 32)[pix]).astype(np.float64).sum()
+
+
+def test_full_scan_c128_skewed_rows(shpl):
+    """Config 4 / 5 shape: 120k pairs, C=128, ground-plane-skewed rows, non-homogeneous weights."""
+    o, val, bev, img = _case(9, 120000, (700, 800), (360, 1200), 128, 128, "ground", True)
+    Mij, flip = o["Mij_pool"], o["img_index_flip_pool"]
+    M = shpl.SparseTensor(torch.from_numpy(Mij).cuda(), torch.from_numpy(val).cuda(), o["M_size"])
+    tb, ti = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
+    fused, _ = shpl.sparse_pool_layer([tb, ti], [128, 128], M, img_index_flip=torch.from_numpy(flip).cuda())
+    ref = cref.forward(bev[0], img[0], Mij, val, flip)
+    np.testing.assert_array_equal(fused[0].detach().cpu().numpy(), ref)
+    del ref
+    g = np.random.default_rng(3).standard_normal((700, 800, 256), dtype=np.float32)
+    fused.backward(torch.from_numpy(g[None]).cuda())
+    gd, gs = cref.backward(g, Mij, val, flip, 128, (360, 1200, 128))
+    np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd)
+    np.testing.assert_array_equal(ti.grad[0].cpu().numpy(), gs)
+
+
+def test_one_very_long_row(shpl):
+    """Stress: every pair lands in the same BEV cell (a 30k-entry row) and 1k pairs share one pixel."""
+    n = 30000
+    rng = np.random.default_rng(12)
+    u = rng.integers(0, 64, n)
+    u[:1000] = 5
+    v = rng.integers(0, 32, n)
+    v[:1000] = 7
+    d = dict(bv_index=np.stack((np.full(n, 3), np.full(n, 2)), axis=1).astype(np.int64),
+             img_index=np.stack((u, v, np.zeros(n))).astype(np.float64), bv_size=np.array([16, 16]), img_size=np.array([64, 32]))
+    o = shpl.produce_sparse_pooling_input(d)
+    val = (1.0 / rng.integers(1, 46, n)).astype(np.float32)
+    bev = rng.standard_normal((1, 16, 16, 32), dtype=np.float32)
+    img = rng.standard_normal((1, 32, 64, 32), dtype=np.float32)
+    M = shpl.SparseTensor(torch.from_numpy(o["Mij_pool"]).cuda(), torch.from_numpy(val).cuda(), o["M_size"])
+    tb, ti = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
+    fused, _ = shpl.sparse_pool_layer([tb, ti], [32, 32], M, img_index_flip=torch.from_numpy(o["img_index_flip_pool"]).cuda())
+    ref = cref.forward(bev[0], img[0], o["Mij_pool"], val, o["img_index_flip_pool"])
+    # same ascending-k order as the sequential oracle -> identical; tolerance stated for the record (north_star: 1e-5 rel)
+    np.testing.assert_allclose(fused[0].detach().cpu().numpy(), ref, rtol=1e-5, atol=1e-4)
+    np.testing.assert_array_equal(fused[0].detach().cpu().numpy(), ref)
+    g = rng.standard_normal(ref.shape, dtype=np.float32)
+    fused.backward(torch.from_numpy(g[None]).cuda())
+    gd, gs = cref.backward(g, o["Mij_pool"], val, o["img_index_flip_pool"], 32, (32, 64, 32))
+    np.testing.assert_array_equal(ti.grad[0].cpu().numpy(), gs)
+    np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd)
