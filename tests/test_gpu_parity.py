@@ -184,7 +184,7 @@ def test_empty_frame(shpl):
 
 
 def test_all_points_outside_image(shpl):
-    pts = np.array([[100.0, 0.0, 1.0], [0.0, 100.0, 1.0], [0.0, 0.0, -1.0]])
+    pts = np.array([[100.0, 0.0, 1.0], [0.0, 100.0, 1.0], [-100.0, 0.0, 1.0]])
     d = shpl.gen_sparse_pooling_input_avod(pts, np.zeros((3, 2), dtype=np.int64), Calib(synth.P2_KITTI), [1200, 360], (700, 800))
     assert d["img_index"].shape == (3, 0) and d["bv_index"].shape == (0, 2)
 
