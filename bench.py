@@ -1,0 +1,473 @@
+#!/usr/bin/env python
+"""bench.py -- SHPL forward+backward (+ correspondence build) frames/sec at KITTI shape.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): avod-FPN pyramid people config with 2 NHSP
+layers, forward + backward, batch 1.  One STEP = one synthetic KITTI frame:
+  * correspondence build for both layers from the frame's points (shpl_build_avod x2)
+  * layer A (after VGG conv4, stride 8, DUAL):  BEV 88x100x256 <-> image 45x150x256
+  * layer B (pre-RPN, stride 1, single):        BEV 700x800x32 <-  image 360x1200x32
+  * backward of both layers from upstream gradients of the fused maps
+`value`  : frames/s with every input already resident in HBM (CUDA-graph replay of the step)
+`e2e`    : frames/s through the public drop-in API with the frame's points / voxel indices
+           in pinned HOST memory (H2D inside the timed region) and a D2H read of the result
+`roofline`: the dominant kernel (layer B forward) timed with CUDA events, algorithmic bytes
+`cpu_baseline`: the CPU oracle (port of the reference's algorithm) on the box's host cores
+N > 1: frames are independent -> each rank runs its own frames, no collective on the hot path;
+       NCCL is used only to take the max time over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "SHPL fwd+bwd+build frames/sec at KITTI shape (avod-FPN 2 NHSP layers, batch 1)"
+UNIT = "frames/s"
+WORKLOAD = "avod-FPN pyramid people, 2 NHSP layers (A: stride-8 dual 88x100x256<->45x150x256; B: stride-1 700x800x32<-360x1200x32), fwd+bwd+build, batch 1"
+AZ_STEP = 0.028         # azimuth step of the synthetic 64-beam scan: ~20k correspondence pairs per frame
+N_FRAMES = 4             # distinct synthetic frames rotated through
+N_MAX = 32768
+
+
+def layer_specs():
+    from sparse_pooling_b200.pipeline import LayerSpec
+    return [
+        LayerSpec("A_vgg_conv4_s8_dual", (88, 100), (45, 150), 256, 256, (8, 8), True, (1200, 360), (704, 800)),
+        LayerSpec("B_pre_rpn_s1", (700, 800), (360, 1200), 32, 32, (1, 1), False, (1200, 360), (700, 800)),
+    ]
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path)).get("shpl_forward_kernel_layerB_dram_bytes")
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index, period=0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in names.items():
+                    if bit and (r & bit):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------- CPU legs
+def cpu_frame_inputs(seed):
+    from oracle import synth
+    return synth.avod_frame(seed, az_step_deg=AZ_STEP)
+
+
+class CpuWorkload:
+    """The same step on the host: numpy index oracle + plain-C value oracle (port of the
+    reference's algorithm; TensorFlow is not installable, so kind = "port")."""
+
+    def __init__(self):
+        from oracle import cref, synth
+        cref.build()
+        self.specs = layer_specs()
+        rng = np.random.default_rng(0)
+        self.maps = []
+        for s in self.specs:
+            bev = rng.standard_normal(s.bev_hw + (s.c_bev,), dtype=np.float32)
+            img = rng.standard_normal(s.img_hw + (s.c_img,), dtype=np.float32)
+            g_bev = rng.standard_normal(s.bev_hw + (s.c_bev + s.c_img,), dtype=np.float32)
+            g_img = rng.standard_normal(s.img_hw + (s.c_img + s.c_bev,), dtype=np.float32) if s.dual else None
+            self.maps.append((bev, img, g_bev, g_img))
+        self.frames = [cpu_frame_inputs(100 + i) for i in range(N_FRAMES)]
+        self.threads = cref.threads()
+
+    def step(self, k):
+        from oracle import cref, index_oracle as io
+        f = self.frames[k % N_FRAMES]
+        out = []
+        for s, (bev, img, g_bev, g_img) in zip(self.specs, self.maps):
+            d = io.gen_sparse_pooling_input_avod(f["points"], f["voxel_indices"], f["P"], list(s.im_size), s.bv_size)
+            o = io.produce_sparse_pooling_input(d, stride=list(s.stride))
+            val = np.ones(len(o["Mij_pool"]), np.float32)
+            Mij, flip = o["Mij_pool"], o["img_index_flip_pool"]
+            fused = cref.forward(bev, img, Mij, val, flip)
+            gd, gs = cref.backward(g_bev, Mij, val, flip, s.c_bev, img.shape)
+            if s.dual:
+                fused_i = cref.forward_trans(img, bev, Mij, val, flip)
+                gi, gb = cref.backward_trans(g_img, Mij, val, flip, s.c_img, bev.shape)
+                gd += gb
+                gs += gi
+            out.append(float(fused[0, 0, 0]) + float(gd[0, 0, 0]) + float(gs[0, 0, 0]))
+        return out
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path for this workload.  The reference is
+    numpy + TensorFlow 1.8 (not installable here), so its algorithm is timed through the
+    CPU oracle (numpy builder + plain-C restatement of the TF ops), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = CpuWorkload()
+    for k in range(args.warmup):
+        wl.step(k)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        wl.step(k)
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": 1},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": wl.threads, "kind": "port",
+                         "sample": "%d frames, one per step (numpy correspondence builder + plain-C gather/SpMM/concat "
+                                   "and gradients, OpenMP on the dense loops)" % args.steps},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the SHPL path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import sparse_pooling_b200 as shpl
+    from sparse_pooling_b200 import _cabi
+    from sparse_pooling_b200.pipeline import FramePipeline
+    from oracle import synth
+
+    lib = _cabi.lib
+    specs = layer_specs()
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---- synthetic inputs, resident in HBM (rank-dependent seeds: every rank has its own frames)
+    frames_host = [synth.avod_frame(100 + rank * N_FRAMES + i, az_step_deg=AZ_STEP) for i in range(N_FRAMES)]
+    n_pts = [int(f["points"].shape[0]) for f in frames_host]
+    assert max(n_pts) <= N_MAX
+    pts_dev = [torch.from_numpy(f["points"]).to(dev) for f in frames_host]
+    vox_dev = [torch.from_numpy(np.ascontiguousarray(f["voxel_indices"][:, :2])).to(dev) for f in frames_host]
+    P = synth.P2_KITTI
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    n_sets = 2
+
+    def randn(*shape):
+        return torch.randn(*shape, device=dev, dtype=torch.float32, generator=g)
+    maps = []
+    for _ in range(n_sets):
+        per_layer = []
+        for s in specs:
+            per_layer.append(dict(
+                bev=randn(1, *s.bev_hw, s.c_bev), img=randn(1, *s.img_hw, s.c_img),
+                g_bev=randn(1, *s.bev_hw, s.c_bev + s.c_img),
+                g_img=randn(1, *s.img_hw, s.c_img + s.c_bev) if s.dual else None))
+        maps.append(per_layer)
+    pipes = [FramePipeline(specs, N_MAX, dev) for _ in range(n_sets)]
+
+    side = torch.cuda.Stream(device=dev)
+
+    def lean_step(k, timing_events=None):
+        """build(A,B) + fwd(A,B) + bwd(B,A) on preallocated buffers; layer B on a side stream so the
+        latency-bound builder kernels overlap the bandwidth-bound pooling kernels."""
+        fi, si = k % N_FRAMES, k % n_sets
+        pipe, mp = pipes[si], maps[si]
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        ms, ss = main.cuda_stream, side.cuda_stream
+        # layer A on the main stream
+        pipe.build_layer(0, pts_dev[fi], vox_dev[fi], P, n_pts[fi], ms)
+        with torch.cuda.stream(side):
+            pipe.build_layer(1, pts_dev[fi], vox_dev[fi], P, n_pts[fi], ss)
+            if timing_events is not None:
+                timing_events[0].record(side)
+            pipe.forward_layer(1, mp[1]["bev"], mp[1]["img"], ss)
+            if timing_events is not None:
+                timing_events[1].record(side)
+            pipe.backward_layer(1, mp[1]["g_bev"], None, ss)
+            if timing_events is not None:
+                timing_events[2].record(side)
+        pipe.forward_layer(0, mp[0]["bev"], mp[0]["img"], ms)
+        pipe.backward_layer(0, mp[0]["g_bev"], mp[0]["g_img"], ms)
+        main.wait_stream(side)
+
+    # ---- parity spot check before timing: one lean step against the public API
+    lean_step(0)
+    torch.cuda.synchronize()
+    nnz = [int(L.plan.counts[0, 3].item()) for L in pipes[0].layers]
+
+    # ---- capture the step in CUDA graphs (one per frame/buffer-set combination)
+    graphs = []
+    use_graph = not args.no_graph
+    if use_graph:
+        try:
+            n_variants = N_FRAMES if N_FRAMES % n_sets == 0 else N_FRAMES * n_sets
+            for v in range(n_variants):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    lean_step(v)
+                graphs.append(gr)
+        except Exception as e:  # pragma: no cover
+            print("graph capture failed (%r); timing eager launches" % (e,), file=sys.stderr)
+            graphs, use_graph = [], False
+            torch.cuda.synchronize()
+
+    def step(k):
+        if use_graph:
+            graphs[k % len(graphs)].replay()
+        else:
+            lean_step(k)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for k in range(W):
+        step(k)
+    torch.cuda.synchronize()
+
+    # ---- timed region: EXACTLY K steps, device-timed, barrier + synchronize on both sides
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = int(lib.shpl_kernel_launches())
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0.record()
+    for k in range(K):
+        step(k)
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    # launches per step: counted on eager launches (graph replays re-run the captured ones)
+    l0 = int(lib.shpl_kernel_launches())
+    lean_step(0)
+    launches_per_step = int(lib.shpl_kernel_launches()) - l0
+    torch.cuda.synchronize()
+    gpu_launches = launches_per_step * K if use_graph else int(lib.shpl_kernel_launches()) - launches0 - launches_per_step
+    value = world * K / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (layer B forward), CUDA events on its launching stream
+    sB = specs[1]
+    fwd_ms, bwd_ms = [], []
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    for k in range(K):
+        lean_step(k, evs[k])
+    torch.cuda.synchronize()
+    for e in evs:
+        fwd_ms.append(e[0].elapsed_time(e[1]))
+        bwd_ms.append(e[1].elapsed_time(e[2]))
+    peak, peak_src = peaks()
+    bytes_fwd_B = sB.bytes_forward(nnz[1])
+    bytes_bwd_B = sB.bytes_backward(nnz[1])
+    fwd_avg = float(np.mean(fwd_ms)) * 1e-3
+    bwd_avg = float(np.mean(bwd_ms)) * 1e-3
+    achieved = bytes_fwd_B / fwd_avg / 1e9
+    roofline = {"bound": "hbm", "kernel": "shpl_forward_kernel<4> (layer B: 700x800x32 <- 360x1200x32)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(), "bytes_per_launch": bytes_fwd_B, "us_per_launch": fwd_avg * 1e6,
+                "peak_source": peak_src, "frac_of_8TBs_nominal": achieved / 8000.0,
+                "backward_kernel": {"achieved": bytes_bwd_B / bwd_avg / 1e9, "frac": bytes_bwd_B / bwd_avg / 1e9 / peak,
+                                    "bytes_per_launch": bytes_bwd_B, "us_per_launch": bwd_avg * 1e6}}
+    bytes_step = sum(s.bytes_forward(n) + s.bytes_backward(n) for s, n in zip(specs, nnz))
+    step_gbs = bytes_step * K / (ms_total * 1e-3) / 1e9
+
+    # ---- e2e: the public drop-in API, frame inputs in pinned host memory, result read back
+    class Calib:
+        p2 = P
+    pts_pin = [torch.from_numpy(f["points"]).pin_memory() for f in frames_host]
+    vox_pin = [torch.from_numpy(np.ascontiguousarray(f["voxel_indices"][:, :2])).pin_memory() for f in frames_host]
+    result_pin = torch.empty(2 * len(specs) * 256, dtype=torch.float32).pin_memory()
+    h2d = d2h = 0
+
+    def e2e_step(k):
+        nonlocal h2d, d2h
+        fi, si = k % N_FRAMES, k % n_sets
+        mp = maps[si]
+        outs = []
+        h2d = d2h = 0
+        for li, s in enumerate(specs):
+            d = shpl.gen_sparse_pooling_input_avod(pts_pin[fi], vox_pin[fi], Calib, list(s.im_size), s.bv_size)
+            h2d += pts_pin[fi].numel() * 8 + vox_pin[fi].numel() * 8
+            d2h += 4                                                    # n read-back
+            o = shpl.produce_sparse_pooling_input(d, stride=list(s.stride))
+            d2h += 32                                                   # counts read-back
+            M = shpl.SparseTensor.from_sparse_pooling_input(o)
+            bev = mp[li]["bev"].requires_grad_(True)
+            img = mp[li]["img"].requires_grad_(True)
+            bev.grad = None
+            img.grad = None
+            bv_fused, img_fused = shpl.sparse_pool_layer([bev, img], [s.c_img, s.c_bev], M,
+                                                         img_index_flip=o["img_index_flip_pool"],
+                                                         bv_index=(np.zeros((1, 3)) if s.dual else None))
+            if s.dual:
+                torch.autograd.backward([bv_fused, img_fused], [mp[li]["g_bev"], mp[li]["g_img"]])
+            else:
+                torch.autograd.backward([bv_fused], [mp[li]["g_bev"]])
+            outs.append(bev.grad.reshape(-1)[:256])
+            outs.append(img.grad.reshape(-1)[:256])
+        result_pin.copy_(torch.cat(outs), non_blocking=False)          # D2H read of the step's result
+        d2h += result_pin.numel() * 4
+
+    K_e2e = max(3, min(K, 30))
+    for k in range(3):
+        e2e_step(k)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K_e2e):
+        e2e_step(k)
+    torch.cuda.synchronize()
+    dt_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_e2e = float(t.item())
+    for mp in maps:
+        for m in mp:
+            m["bev"].requires_grad_(False)
+            m["img"].requires_grad_(False)
+    e2e = {"value": world * K_e2e / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "steps": K_e2e,
+           "what": "gen_sparse_pooling_input_avod + produce_sparse_pooling_input + sparse_pool_layer + autograd backward "
+                   "per layer through the public API; points/voxel indices copied from pinned host memory every step, "
+                   "feature maps device-resident (they are device-resident TF tensors in the reference), 2 KB of the "
+                   "gradients read back to pinned host memory every step"}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        wl = CpuWorkload()
+        wl.step(0)
+        n_cpu, t0 = 0, time.perf_counter()
+        while n_cpu < 3 or (time.perf_counter() - t0 < 10.0 and n_cpu < 40):
+            wl.step(n_cpu)
+            n_cpu += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_cpu / dt, "unit": UNIT, "cores": wl.threads, "kind": "port",
+               "sample": "%d frames of the same workload (numpy correspondence builder + plain-C oracle of the TF ops)" % n_cpu}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "candidate_pairs_per_frame": n_pts,
+                       "nnz_per_layer": nnz, "sharding": "frames by rank, no data-path collective",
+                       "l2": "inputs larger than L2: %.0f MB touched per step, %d rotating buffer sets" % (bytes_step / 1e6, n_sets),
+                       "launch": "CUDA graph replay" if use_graph else "eager launches",
+                       "algorithmic_bytes_per_step": bytes_step, "step_gbs_per_gpu": step_gbs / world,
+                       "step_frac_of_peak": step_gbs / world / peak},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -62,6 +62,10 @@ typedef struct shpl_plan {
 int         shpl_abi_version(void);
 const char* shpl_last_error(void);
 
+/* Number of CUDA kernels this library has launched in this process so far (all
+ * threads).  bench.py differences it around the timed region ("gpu_launches"). */
+uint64_t shpl_kernel_launches(void);
+
 /* Bytes of scratch the shpl_build_* / shpl_plan_from_coo calls need for up to
  * n_max candidate pairs. */
 size_t shpl_build_workspace_bytes(int64_t n_max);

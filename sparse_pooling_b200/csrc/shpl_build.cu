@@ -551,6 +551,7 @@ int run_build(PairsArgs& pa, const shpl_plan* plan, const int32_t* entry_base_de
     SHPL_CUDA_OK(cudaMemsetAsync(workspace, 0, pa.ws.header_bytes, s));
     const long long tiles = (pa.n + kTile - 1) / kTile > 0 ? (pa.n + kTile - 1) / kTile : 1;
     shpl_pairs_kernel<<<(unsigned)tiles, kThreads, 0, s>>>(pa);
+    shpl::count_launches(1);
     if (int rc = shpl::check_launch("shpl_pairs_kernel")) return rc;
     if (!sorting) return SHPL_OK;
     RadixArgs ra{};
@@ -562,6 +563,7 @@ int run_build(PairsArgs& pa, const shpl_plan* plan, const int32_t* entry_base_de
     for (int q = 0; q < passes && pa.n > 0; ++q) {
         ra.pass = q;
         shpl_radix_pass_kernel<<<dim3((unsigned)tiles, 2), kThreads, 0, s>>>(ra);
+        shpl::count_launches(1);
         if (int rc = shpl::check_launch("shpl_radix_pass_kernel")) return rc;
     }
     FinalArgs fa{};
@@ -575,6 +577,7 @@ int run_build(PairsArgs& pa, const shpl_plan* plan, const int32_t* entry_base_de
     if (plan->n_src + 1 > span) span = plan->n_src + 1;
     if (pa.n > span) span = pa.n;
     shpl_finalize_kernel<<<(unsigned)((span + kThreads - 1) / kThreads), kThreads, 0, s>>>(fa);
+    shpl::count_launches(1);
     return shpl::check_launch("shpl_finalize_kernel");
 }
 

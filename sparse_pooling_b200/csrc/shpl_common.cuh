@@ -11,6 +11,7 @@ namespace shpl {
 // thread-local error text behind shpl_last_error()
 void set_error(const char* fmt, ...);
 int sm_count();
+void count_launches(int n);
 
 #define SHPL_REQUIRE(cond, code, ...)                 \
     do {                                              \

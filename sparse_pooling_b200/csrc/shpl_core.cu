@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "shpl_common.cuh"
 
 namespace shpl {
@@ -14,6 +16,10 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_error, sizeof(g_error), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+uint64_t launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int sm_count() {
     static thread_local int cached_dev = -1;
@@ -32,3 +38,5 @@ int sm_count() {
 
 extern "C" int shpl_abi_version(void) { return SHPL_ABI_VERSION; }
 extern "C" const char* shpl_last_error(void) { return shpl::g_error; }
+namespace shpl { uint64_t launches(); }
+extern "C" uint64_t shpl_kernel_launches(void) { return shpl::launches(); }

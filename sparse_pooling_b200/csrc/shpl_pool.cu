@@ -268,6 +268,7 @@ extern "C" int shpl_pool_forward(const float* dst, const float* src, const int32
     if (w == 4) shpl_forward_kernel<4><<<grid, kThreads, 0, s>>>(a);
     else if (w == 2) shpl_forward_kernel<2><<<grid, kThreads, 0, s>>>(a);
     else shpl_forward_kernel<1><<<grid, kThreads, 0, s>>>(a);
+    shpl::count_launches(1);
     return shpl::check_launch("shpl_forward_kernel");
 }
 
@@ -304,5 +305,6 @@ extern "C" int shpl_pool_backward(const float* g_fused, const int32_t* ptrT, con
     if (w == 4) shpl_backward_kernel<4><<<grid, kThreads, 0, s>>>(a);
     else if (w == 2) shpl_backward_kernel<2><<<grid, kThreads, 0, s>>>(a);
     else shpl_backward_kernel<1><<<grid, kThreads, 0, s>>>(a);
+    shpl::count_launches(1);
     return shpl::check_launch("shpl_backward_kernel");
 }

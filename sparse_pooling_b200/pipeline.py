@@ -1,0 +1,134 @@
+"""Lean, allocation-free SHPL frame pipeline: correspondence build + forward +
+backward of every SHPL layer of a model, on preallocated buffers, ready to be
+captured in a CUDA graph.
+
+The reference runs this path once per training step for one frame
+(trainer.py:207-235 -> kitti_dataset.py:374-379 -> rpn_model.py:291-361); the
+layers of one model share the frame's points, so one FramePipeline owns one plan
+per layer.  Every call below is a direct ctypes call into libshpl.so with
+arguments bound once in __init__ -- no tensor is created per step, nothing is
+copied to the host, and the only thing that changes between steps is the content
+of the buffers.
+"""
+import ctypes
+from dataclasses import dataclass
+from typing import Tuple
+
+import numpy as np
+import torch
+
+from . import _cabi, ops
+from .ops import SparsePoolPlan
+
+_lib = _cabi.lib
+
+
+@dataclass
+class LayerSpec:
+    """One SHPL instance of a model."""
+    name: str
+    bev_hw: Tuple[int, int]      # BEV feature map H, W   (= floor(bv_size / stride_bv))
+    img_hw: Tuple[int, int]      # image feature map H, W (= floor(im_size / stride_img))
+    c_bev: int
+    c_img: int
+    stride: Tuple[int, int]      # (stride_img, stride_bv): produce_sparse_pooling_input's stride argument
+    dual: bool                   # bev -> img as well (bv_index is not None)
+    im_size: Tuple[int, int]     # (W, H) handed to gen_sparse_pooling_input_avod
+    bv_size: Tuple[int, int]     # (H_b, W_b) handed to gen_sparse_pooling_input_avod
+
+    @property
+    def R(self):
+        return self.bev_hw[0] * self.bev_hw[1]
+
+    @property
+    def Q(self):
+        return self.img_hw[0] * self.img_hw[1]
+
+    def bytes_forward(self, nnz):
+        """Algorithmic bytes of the forward launches."""
+        b = 4 * (self.R * self.c_bev + self.R * (self.c_bev + self.c_img) + nnz * (self.c_img + 2) + self.R + 1)
+        if self.dual:
+            b += 4 * (self.Q * self.c_img + self.Q * (self.c_img + self.c_bev) + nnz * (self.c_bev + 2) + self.Q + 1)
+        return b
+
+    def bytes_backward(self, nnz):
+        b = 4 * (2 * self.R * self.c_bev + nnz * (self.c_img + 2) + self.Q * self.c_img + self.Q + 1)
+        if self.dual:
+            b += 4 * (2 * self.Q * self.c_img + nnz * (self.c_bev + 2) + self.R * self.c_bev + self.R + 1)
+        return b
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class _LayerState:
+    def __init__(self, spec, n_max, device):
+        self.spec = spec
+        f32 = dict(dtype=torch.float32, device=device)
+        self.plan = SparsePoolPlan(spec.R, spec.img_hw, n_max, device)
+        self.plan_struct = self.plan.frame_struct(0)
+        need = int(_lib.shpl_build_workspace_bytes(int(n_max)))
+        self.ws = torch.empty(need, dtype=torch.uint8, device=device)     # own scratch: layers build concurrently
+        self.fused_bev = torch.empty((1,) + spec.bev_hw + (spec.c_bev + spec.c_img,), **f32)
+        self.g_bev = torch.empty((1,) + spec.bev_hw + (spec.c_bev,), **f32)
+        self.g_img = torch.empty((1,) + spec.img_hw + (spec.c_img,), **f32)
+        if spec.dual:
+            self.fused_img = torch.empty((1,) + spec.img_hw + (spec.c_img + spec.c_bev,), **f32)
+            self.g_bev_pool = torch.empty((1,) + spec.bev_hw + (spec.c_bev,), **f32)
+            self.g_img_slice = torch.empty((1,) + spec.img_hw + (spec.c_img,), **f32)
+
+
+class FramePipeline:
+    def __init__(self, layers, n_points_max, device):
+        self.device = device
+        self.n_max = int(n_points_max)
+        self.layers = [_LayerState(s, self.n_max, device) for s in layers]
+
+    # -- correspondence build: shpl_build_avod per layer (different strides, same points) --
+    def build(self, points, voxel_indices, P, n_points, stream):
+        P = np.ascontiguousarray(np.asarray(P, dtype=np.float64).reshape(12))
+        for L in self.layers:
+            s = L.spec
+            rc = _lib.shpl_build_avod(_p(points), _p(voxel_indices), int(n_points), P.ctypes.data_as(ctypes.c_void_p),
+                                      s.im_size[0], s.im_size[1], s.bv_size[0], s.bv_size[1], s.stride[0], s.stride[1],
+                                      None, s.img_hw[0], s.img_hw[1], None, None, None, None,
+                                      ctypes.byref(L.plan_struct), 0, 0, None, _p(L.ws), L.ws.numel(), stream)
+            _cabi.check(rc, "shpl_build_avod")
+
+    def build_layer(self, i, points, voxel_indices, P, n_points, stream):
+        L = self.layers[i]
+        s = L.spec
+        P = np.ascontiguousarray(np.asarray(P, dtype=np.float64).reshape(12))
+        rc = _lib.shpl_build_avod(_p(points), _p(voxel_indices), int(n_points), P.ctypes.data_as(ctypes.c_void_p),
+                                  s.im_size[0], s.im_size[1], s.bv_size[0], s.bv_size[1], s.stride[0], s.stride[1],
+                                  None, s.img_hw[0], s.img_hw[1], None, None, None, None,
+                                  ctypes.byref(L.plan_struct), 0, 0, None, _p(L.ws), L.ws.numel(), stream)
+        _cabi.check(rc, "shpl_build_avod")
+
+    # -- forward of layer i: img -> bev (and bev -> img when dual), concat fused in --
+    def forward_layer(self, i, bev, img, stream):
+        L = self.layers[i]
+        s, pl = L.spec, L.plan
+        rc = _lib.shpl_pool_forward(_p(bev), _p(img), _p(pl.row_ptr), _p(pl.csr_src), _p(pl.csr_val),
+                                    s.R, s.c_bev, s.Q, s.c_img, _p(L.fused_bev), stream)
+        _cabi.check(rc, "shpl_pool_forward")
+        if s.dual:
+            rc = _lib.shpl_pool_forward(_p(img), _p(bev), _p(pl.pix_ptr), _p(pl.csrT_dst), _p(pl.csrT_val),
+                                        s.Q, s.c_img, s.R, s.c_bev, _p(L.fused_img), stream)
+            _cabi.check(rc, "shpl_pool_forward")
+
+    # -- backward of layer i from the upstream gradients of the fused maps --
+    def backward_layer(self, i, g_fused_bev, g_fused_img, stream):
+        L = self.layers[i]
+        s, pl = L.spec, L.plan
+        rc = _lib.shpl_pool_backward(_p(g_fused_bev), _p(pl.pix_ptr), _p(pl.csrT_dst), _p(pl.csrT_val),
+                                     s.R, s.c_bev, s.Q, s.c_img, _p(L.g_bev), _p(L.g_img), stream)
+        _cabi.check(rc, "shpl_pool_backward")
+        if s.dual:
+            rc = _lib.shpl_pool_backward(_p(g_fused_img), _p(pl.row_ptr), _p(pl.csr_src), _p(pl.csr_val),
+                                         s.Q, s.c_img, s.R, s.c_bev, _p(L.g_img_slice), _p(L.g_bev_pool), stream)
+            _cabi.check(rc, "shpl_pool_backward")
+            # TF's AddN of the two partial gradients of each input
+            L.g_bev.add_(L.g_bev_pool)
+            L.g_img.add_(L.g_img_slice)

@@ -27,7 +27,7 @@ def lib():
 
 def test_header_declares_the_expected_entry_points():
     assert declared_functions() == sorted([
-        "shpl_abi_version", "shpl_last_error", "shpl_build_workspace_bytes", "shpl_gen_input_avod",
+        "shpl_abi_version", "shpl_last_error", "shpl_kernel_launches", "shpl_build_workspace_bytes", "shpl_gen_input_avod",
         "shpl_produce_input", "shpl_build_avod", "shpl_plan_from_coo", "shpl_pool_forward", "shpl_pool_backward"])
 
 
