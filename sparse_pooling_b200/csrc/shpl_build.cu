@@ -27,8 +27,9 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kChunks = 8;                       // 32-wide chunks per warp
-constexpr int kTile = kThreads * kChunks;        // 2048 candidates (or sort items) per CTA
+constexpr int kChunks = 8;                       // 32-wide chunks per warp in a radix tile
+constexpr int kTile = kThreads * kChunks;        // 2048 sort items per radix CTA
+constexpr int kPairsTile = kThreads;             // one candidate pair per thread in shpl_pairs_kernel
 constexpr int kMaxRadixBits = 10;
 constexpr int kMaxRadix = 1 << kMaxRadixBits;
 constexpr int kMaxPasses = 4;
@@ -60,12 +61,13 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 Workspace carve(void* base, long long n, const SortPlan* sp /* [2] or null for worst case */) {
     Workspace w{};
     const long long tiles = (n + kTile - 1) / kTile > 0 ? (n + kTile - 1) / kTile : 1;
+    const long long ptiles = (n + kPairsTile - 1) / kPairsTile > 0 ? (n + kPairsTile - 1) / kPairsTile : 1;
     char* p = static_cast<char*>(base);
     size_t off = 0;
     w.ticket = reinterpret_cast<unsigned*>(p + off);
     off += 64;
     w.status = reinterpret_cast<unsigned long long*>(p + off);
-    off = align_up(off + sizeof(unsigned long long) * tiles, 64);
+    off = align_up(off + sizeof(unsigned long long) * ptiles, 64);
     for (int s = 0; s < 2; ++s)
         for (int q = 0; q < kMaxPasses; ++q) {
             const int radix = sp ? (q < sp[s].passes ? (1 << sp[s].bits[q]) : 0) : kMaxRadix;
@@ -141,9 +143,16 @@ struct PairsArgs {
     SortPlan sp[2];
 };
 
-__device__ __forceinline__ long long floordiv_ll(long long a, long long s) {
+// floor(a / s) for s > 0; cell indices fit 32 bits in practice, 64-bit division is the slow path
+__device__ __forceinline__ long long floordiv_ll(long long a, int s) {
+    if (a == (long long)(int)a) {
+        const int ai = (int)a;
+        int q = ai / s;
+        if (ai - q * s < 0) --q;
+        return q;
+    }
     long long q = a / s;
-    if ((a % s != 0) && ((a < 0) != (s < 0))) --q;
+    if (a - q * s < 0) --q;
     return q;
 }
 
@@ -193,102 +202,105 @@ __device__ unsigned long long lookback(unsigned long long* status, int tile, uns
     return excl;
 }
 
-__global__ void __launch_bounds__(kThreads) shpl_pairs_kernel(PairsArgs a) {
+// What one candidate pair contributes (recomputed in both passes of shpl_pairs_kernel: the
+// kernel is latency-bound and straight-line code this size costs more in instruction fetch
+// than the arithmetic does, so the chunk loops are kept rolled and nothing is cached per chunk).
+struct Cand {
+    bool clip, keep;
+    long long row;
+    int up, vp;
+    double gu, gv;      // rounded (u, v) before the stride is applied: the gen dict's img_index
+    double us, vs;      // after floor(/stride) and clamp: what the reference writes back in place
+    long long bx, bz;
+};
+
+__device__ __forceinline__ Cand eval_candidate(const PairsArgs& a, long long i, long long R) {
+    Cand c;
+    c.clip = c.keep = false;
+    c.row = 0; c.up = 0; c.vp = 0; c.gu = 0; c.gv = 0; c.us = 0; c.vs = 0; c.bx = 0; c.bz = 0;
+    if (i >= a.n) return c;
+    if (a.mode == kModeCoo) {
+        const long long r = a.coo[2 * i], col = a.coo[2 * i + 1];
+        c.clip = c.keep = true;
+        c.row = r;
+        long long b = -1, v = -1, u = -1;
+        if (col >= 0 && col < a.ncol) {
+            if (a.index_is_i64) {
+                const long long* q = static_cast<const long long*>(a.src_index) + 3 * col;
+                b = q[0]; v = q[1]; u = q[2];
+            } else {
+                const int* q = static_cast<const int*>(a.src_index) + 3 * col;
+                b = q[0]; v = q[1]; u = q[2];
+            }
+        }
+        const bool ok = (b == 0) && v >= 0 && v < a.src_h && u >= 0 && u < a.src_w;
+        c.vp = ok ? (int)v : -1;
+        c.up = ok ? (int)u : -1;
+        return c;
+    }
+    double u, v;
+    if (a.mode == kModePairs) {
+        u = a.img_u[i];
+        v = a.img_v[i];
+        c.bx = a.bv_index[2 * i];
+        c.bz = a.bv_index[2 * i + 1];
+        c.clip = true;
+    } else {
+        const double x = a.points[3 * i], y = a.points[3 * i + 1], z = a.points[3 * i + 2];
+        const double w = prow(a.P + 8, x, y, z);
+        u = __ddiv_rn(prow(a.P + 0, x, y, z), w);
+        v = __ddiv_rn(prow(a.P + 4, x, y, z), w);
+        // transform.py:36-38 (NaN compares false)
+        c.clip = (u < (double)(a.im_w - 1)) && (u >= 0.0) && (v >= 0.0) && (v < (double)(a.im_h - 1));
+        u = rint(u);   // sparse_pool_utils.py:18, ties to even
+        v = rint(v);
+        c.bx = a.vox[2 * i];
+        c.bz = a.vox[2 * i + 1];
+    }
+    c.gu = u;
+    c.gv = v;
+    if (c.clip && a.mode != kModeGenOnly) {
+        // sparse_pool_utils.py:30-34
+        double us = floor(u / (double)a.s_img), vs = floor(v / (double)a.s_img);
+        if (us >= (double)a.Wp) us = (double)(a.Wp - 1);
+        if (vs >= (double)a.Hp) vs = (double)(a.Hp - 1);
+        c.us = us;
+        c.vs = vs;
+        const long long ul = (long long)floor(us), vl = (long long)floor(vs);
+        // :38-44
+        const long long xs = floordiv_ll(c.bx, a.s_bv), zs = floordiv_ll(c.bz, a.s_bv);
+        c.row = zs * (long long)a.Wb + xs;
+        c.keep = c.row < R;
+        // exact integers for the COO output (clamped to int32 range only)
+        c.up = (int)max(min(ul, (long long)INT32_MAX), (long long)INT32_MIN);
+        c.vp = (int)max(min(vl, (long long)INT32_MAX), (long long)INT32_MIN);
+    }
+    return c;
+}
+
+// One candidate pair per thread: evaluate, count survivors (warp ballots), single-pass prefix over
+// the CTAs (decoupled look-back), write the compacted outputs.  Many small CTAs on purpose: the
+// kernel is a chain of dependent latencies (loads -> fp64 -> look-back -> stores), so the only
+// lever is to run every candidate's chain concurrently.
+__global__ void __launch_bounds__(kThreads) shpl_pairs_kernel(PairsArgs a, int use_ticket) {
     __shared__ int s_tile;
     __shared__ unsigned s_warp_clip[kWarps], s_warp_keep[kWarps];
     __shared__ unsigned long long s_excl;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_tile = (int)atomicAdd(a.ws.ticket, 1u);
-    __syncthreads();
-    const int tile = s_tile;
-    const long long base = (long long)tile * kTile + warp * (kChunks * 32);
-    const long long R = (long long)a.Hb * a.Wb;
-
-    // per candidate: flags and the values that survive to the outputs
-    bool clip[kChunks], keep[kChunks];
-    long long row[kChunks];
-    int up[kChunks], vp[kChunks];
-    double gu[kChunks], gv[kChunks];
-    long long bx[kChunks], bz[kChunks];
-    unsigned pre_clip[kChunks], pre_keep[kChunks];
-    unsigned run_clip = 0, run_keep = 0;
-#pragma unroll
-    for (int c = 0; c < kChunks; ++c) {
-        const long long i = base + c * 32 + lane;
-        clip[c] = false; keep[c] = false; row[c] = 0; up[c] = 0; vp[c] = 0; gu[c] = 0; gv[c] = 0; bx[c] = 0; bz[c] = 0;
-        if (i < a.n) {
-            if (a.mode == kModeCoo) {
-                const long long r = a.coo[2 * i], col = a.coo[2 * i + 1];
-                clip[c] = keep[c] = true;
-                row[c] = r;
-                long long b = -1, v = -1, u = -1;
-                if (col >= 0 && col < a.ncol) {
-                    if (a.index_is_i64) {
-                        const long long* q = static_cast<const long long*>(a.src_index) + 3 * col;
-                        b = q[0]; v = q[1]; u = q[2];
-                    } else {
-                        const int* q = static_cast<const int*>(a.src_index) + 3 * col;
-                        b = q[0]; v = q[1]; u = q[2];
-                    }
-                }
-                const bool ok = (b == 0) && v >= 0 && v < a.src_h && u >= 0 && u < a.src_w;
-                vp[c] = ok ? (int)v : -1;
-                up[c] = ok ? (int)u : -1;
-            } else {
-                double u, v;
-                if (a.mode == kModePairs) {
-                    u = a.img_u[i];
-                    v = a.img_v[i];
-                    bx[c] = a.bv_index[2 * i];
-                    bz[c] = a.bv_index[2 * i + 1];
-                    clip[c] = true;
-                } else {
-                    const double x = a.points[3 * i], y = a.points[3 * i + 1], z = a.points[3 * i + 2];
-                    const double w = prow(a.P + 8, x, y, z);
-                    u = __ddiv_rn(prow(a.P + 0, x, y, z), w);
-                    v = __ddiv_rn(prow(a.P + 4, x, y, z), w);
-                    // transform.py:36-38 (NaN compares false)
-                    clip[c] = (u < (double)(a.im_w - 1)) && (u >= 0.0) && (v >= 0.0) && (v < (double)(a.im_h - 1));
-                    u = rint(u);   // sparse_pool_utils.py:18, ties to even
-                    v = rint(v);
-                    bx[c] = a.vox[2 * i];
-                    bz[c] = a.vox[2 * i + 1];
-                }
-                gu[c] = u;
-                gv[c] = v;
-                if (clip[c] && a.mode != kModeGenOnly) {
-                    // sparse_pool_utils.py:30-34
-                    double us = floor(u / (double)a.s_img), vs = floor(v / (double)a.s_img);
-                    if (us >= (double)a.Wp) us = (double)(a.Wp - 1);
-                    if (vs >= (double)a.Hp) vs = (double)(a.Hp - 1);
-                    if (a.mode == kModePairs) {     // the reference mutates img_index in place (:30)
-                        a.img_u[i] = us;
-                        a.img_v[i] = vs;
-                    }
-                    const long long ul = (long long)floor(us), vl = (long long)floor(vs);
-                    // :38-44
-                    const long long xs = floordiv_ll(bx[c], a.s_bv), zs = floordiv_ll(bz[c], a.s_bv);
-                    row[c] = zs * (long long)a.Wb + xs;
-                    keep[c] = row[c] < R;
-                    const bool ok = vl >= 0 && vl < a.src_h && ul >= 0 && ul < a.src_w;
-                    // keep the exact integers for the COO output, clamp what feeds the CSR
-                    up[c] = (int)max(min(ul, (long long)INT32_MAX), (long long)INT32_MIN);
-                    vp[c] = (int)max(min(vl, (long long)INT32_MAX), (long long)INT32_MIN);
-                    if (!ok) { /* marked below through pix = -1 */ }
-                }
-            }
-        }
-        const unsigned mc = __ballot_sync(kFull, clip[c]);
-        const unsigned mk = __ballot_sync(kFull, keep[c]);
-        const unsigned lt = (1u << lane) - 1u;
-        pre_clip[c] = run_clip + __popc(mc & lt);
-        pre_keep[c] = run_keep + __popc(mk & lt);
-        run_clip += __popc(mc);
-        run_keep += __popc(mk);
+    int tile = blockIdx.x;
+    if (use_ticket) {          // more CTAs than can be resident: order the look-back by arrival
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(a.ws.ticket, 1u);
+        __syncthreads();
+        tile = s_tile;
     }
+    const long long i = (long long)tile * kPairsTile + threadIdx.x;
+    const long long R = (long long)a.Hb * a.Wb;
+    const Cand cd = eval_candidate(a, i, R);
+    const unsigned mc = __ballot_sync(kFull, cd.clip);
+    const unsigned mk = __ballot_sync(kFull, cd.keep);
     if (lane == 0) {
-        s_warp_clip[warp] = run_clip;
-        s_warp_keep[warp] = run_keep;
+        s_warp_clip[warp] = __popc(mc);
+        s_warp_keep[warp] = __popc(mk);
     }
     __syncthreads();
     unsigned wb_clip = 0, wb_keep = 0, tot_clip = 0, tot_keep = 0;
@@ -300,15 +312,16 @@ __global__ void __launch_bounds__(kThreads) shpl_pairs_kernel(PairsArgs a) {
     }
     if (warp == 0) {
         unsigned long long excl = 0ull;
-        if (a.mode == kModeCoo) excl = ((unsigned long long)tile * kTile) * ((1ull << 31) + 1ull);
+        if (a.mode == kModeCoo) excl = ((unsigned long long)tile * kPairsTile) * ((1ull << 31) + 1ull);
         else excl = lookback(a.ws.status, tile, ((unsigned long long)tot_clip << 31) | tot_keep, lane);
         if (lane == 0) s_excl = excl;
     }
     __syncthreads();
-    const long long g_clip = (long long)(s_excl >> 31) + wb_clip;
-    const long long g_keep = (long long)(s_excl & ((1ull << 31) - 1)) + wb_keep;
+    const unsigned lt = (1u << lane) - 1u;
+    const long long j = (long long)(s_excl >> 31) + wb_clip + __popc(mc & lt);
+    const long long k = (long long)(s_excl & ((1ull << 31) - 1)) + wb_keep + __popc(mk & lt);
 
-    const long long n_tiles = (a.n + kTile - 1) / kTile > 0 ? (a.n + kTile - 1) / kTile : 1;
+    const long long n_tiles = (a.n + kPairsTile - 1) / kPairsTile > 0 ? (a.n + kPairsTile - 1) / kPairsTile : 1;
     if (tile == n_tiles - 1 && threadIdx.x == 0) {   // inclusive prefix of the last tile = totals
         const long long n_clip = (long long)(s_excl >> 31) + tot_clip;
         const long long nnz = (long long)(s_excl & ((1ull << 31) - 1)) + tot_keep;
@@ -317,38 +330,37 @@ __global__ void __launch_bounds__(kThreads) shpl_pairs_kernel(PairsArgs a) {
         if (a.msize_out) { a.msize_out[0] = R; a.msize_out[1] = nnz; }
     }
 
-#pragma unroll
-    for (int c = 0; c < kChunks; ++c) {
-        if (clip[c] && a.gen_bv) {
-            const long long j = g_clip + pre_clip[c];
-            a.gen_bv[2 * j] = bx[c];
-            a.gen_bv[2 * j + 1] = bz[c];
-            a.gen_u[j] = gu[c];
-            a.gen_v[j] = gv[c];
-        }
-        if (!keep[c]) continue;
-        const long long k = g_keep + pre_keep[c];
-        const long long r = row[c];
-        float w = 1.0f;
-        if (a.mode == kModeCoo) w = a.coo_val[k];
-        else if (a.m_val) w = (float)a.m_val[k];          // indexed by output column (:56-57), f64 -> f32 like the feed
-        const bool pix_ok = vp[c] >= 0 && vp[c] < a.src_h && up[c] >= 0 && up[c] < a.src_w;
-        const bool ok = pix_ok && r >= 0 && r < (long long)a.n_rows;
-        const int pix = vp[c] * a.src_w + up[c];
-        if (a.mij) { a.mij[2 * k] = r; a.mij[2 * k + 1] = k; }
-        if (a.flip) { a.flip[3 * k] = 0; a.flip[3 * k + 1] = vp[c]; a.flip[3 * k + 2] = up[c]; }
-        if (a.mval_out) a.mval_out[k] = w;
-        a.ws.valk[k] = w;
-        a.ws.rowk[k] = ok ? (int)r + a.row_base : -1;
-        a.ws.pixk[k] = ok ? pix + a.pix_base : -1;
-        const unsigned key_r = ok ? (unsigned)r : (unsigned)a.sp[0].n_keys;
-        const unsigned key_p = ok ? (unsigned)pix : (unsigned)a.sp[1].n_keys;
-        a.ws.items[0][0][k] = ((unsigned long long)key_r << 32) | (unsigned)k;
-        a.ws.items[1][0][k] = ((unsigned long long)key_p << 32) | (unsigned)k;
-        const int t0 = (int)(k / kTile);
-        atomicAdd(a.ws.hist[0][0] + ((size_t)t0 << a.sp[0].bits[0]) + (key_r & ((1u << a.sp[0].bits[0]) - 1u)), 1u);
-        atomicAdd(a.ws.hist[1][0] + ((size_t)t0 << a.sp[1].bits[0]) + (key_p & ((1u << a.sp[1].bits[0]) - 1u)), 1u);
+    if (a.mode == kModePairs && cd.clip) {      // the reference mutates img_index in place (:30-34)
+        a.img_u[i] = cd.us;
+        a.img_v[i] = cd.vs;
     }
+    if (cd.clip && a.gen_bv) {
+        a.gen_bv[2 * j] = cd.bx;
+        a.gen_bv[2 * j + 1] = cd.bz;
+        a.gen_u[j] = cd.gu;
+        a.gen_v[j] = cd.gv;
+    }
+    if (!cd.keep) return;
+    const long long r = cd.row;
+    float w = 1.0f;
+    if (a.mode == kModeCoo) w = a.coo_val[k];
+    else if (a.m_val) w = (float)a.m_val[k];      // indexed by output column (:56-57), f64 -> f32 like the feed
+    const bool pix_ok = cd.vp >= 0 && cd.vp < a.src_h && cd.up >= 0 && cd.up < a.src_w;
+    const bool ok = pix_ok && r >= 0 && r < (long long)a.n_rows;
+    const int pix = cd.vp * a.src_w + cd.up;
+    if (a.mij) { a.mij[2 * k] = r; a.mij[2 * k + 1] = k; }
+    if (a.flip) { a.flip[3 * k] = 0; a.flip[3 * k + 1] = cd.vp; a.flip[3 * k + 2] = cd.up; }
+    if (a.mval_out) a.mval_out[k] = w;
+    a.ws.valk[k] = w;
+    a.ws.rowk[k] = ok ? (int)r + a.row_base : -1;
+    a.ws.pixk[k] = ok ? pix + a.pix_base : -1;
+    const unsigned key_r = ok ? (unsigned)r : (unsigned)a.sp[0].n_keys;
+    const unsigned key_p = ok ? (unsigned)pix : (unsigned)a.sp[1].n_keys;
+    a.ws.items[0][0][k] = ((unsigned long long)key_r << 32) | (unsigned)k;
+    a.ws.items[1][0][k] = ((unsigned long long)key_p << 32) | (unsigned)k;
+    const int t0 = (int)(k / kTile);
+    atomicAdd(a.ws.hist[0][0] + ((size_t)t0 << a.sp[0].bits[0]) + (key_r & ((1u << a.sp[0].bits[0]) - 1u)), 1u);
+    atomicAdd(a.ws.hist[1][0] + ((size_t)t0 << a.sp[1].bits[0]) + (key_p & ((1u << a.sp[1].bits[0]) - 1u)), 1u);
 }
 
 struct RadixArgs {
@@ -359,8 +371,13 @@ struct RadixArgs {
 };
 
 // One stable LSD pass over (key<<32 | k) items.  grid.y selects the sort (0 = by cell, 1 = by pixel).
+// The tile is staged in shared memory with every load in flight at once; ranks come from warp
+// match-any over 32-item chunks taken in order (stability); the tile's base per digit comes from the
+// per-tile digit counts the previous kernel accumulated.
 __global__ void __launch_bounds__(kThreads) shpl_radix_pass_kernel(RadixArgs a) {
+    __shared__ unsigned long long s_items[kTile];
     __shared__ unsigned short s_wh[kWarps][kMaxRadix];   // per-warp digit counts, then exclusive warp prefix
+    __shared__ unsigned short s_rank[kTile];
     __shared__ unsigned s_gb[kMaxRadix];                 // global base of each digit for this tile
     __shared__ unsigned s_scan[kWarps];
     const int sort = blockIdx.y;
@@ -379,21 +396,46 @@ __global__ void __launch_bounds__(kThreads) shpl_radix_pass_kernel(RadixArgs a) 
     unsigned long long* out = a.ws.items[sort][(pass + 1) & 1];
     const unsigned* hist = a.ws.hist[sort][pass];
     const int n_tiles = (n + kTile - 1) / kTile;
+    constexpr int kDigitsPerThread = kMaxRadix / kThreads;
 
+    // stage the tile (coalesced, all loads in flight) and clear the warp histograms
+#pragma unroll
+    for (int j = 0; j < kChunks; ++j) {
+        const int i = tile_base + j * kThreads + threadIdx.x;
+        s_items[j * kThreads + threadIdx.x] = i < n ? in[i] : ~0ull;
+    }
     for (int d = threadIdx.x; d < radix * kWarps; d += kThreads) (&s_wh[0][0])[(d / radix) * kMaxRadix + (d % radix)] = 0;
+
+    // this thread's digits: how many such items sit in earlier tiles / in all tiles (loads overlap phase A)
+    unsigned below[kDigitsPerThread], all[kDigitsPerThread];
+#pragma unroll
+    for (int j = 0; j < kDigitsPerThread; ++j) {
+        const int d = threadIdx.x * kDigitsPerThread + j;   // consecutive digits per thread (for the scan below)
+        below[j] = all[j] = 0;
+        if (d < radix) {
+            for (int t0 = 0; t0 < n_tiles; t0 += 8) {      // 8 independent loads in flight
+                unsigned h[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) h[u] = (t0 + u < n_tiles) ? __ldg(hist + ((size_t)(t0 + u) << bits) + d) : 0u;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    all[j] += h[u];
+                    if (t0 + u < tile) below[j] += h[u];
+                }
+            }
+        }
+    }
     __syncthreads();
 
-    // phase A: rank of every item inside (warp, digit), chunks taken in order
-    unsigned long long item[kChunks];
-    unsigned short rank[kChunks];
-    const int wbase = tile_base + warp * (kChunks * 32);
+    // phase A: rank of every item inside (warp, digit); a warp owns 256 consecutive items, in order
+    const int wofs = warp * (kChunks * 32);
     const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < kChunks; ++c) {
-        const int i = wbase + c * 32 + lane;
-        const bool live = i < n;
-        item[c] = live ? in[i] : 0ull;
-        const unsigned digit = live ? (unsigned)((item[c] >> (32 + shift)) & mask) : (unsigned)radix + lane;
+        const int li = wofs + c * 32 + lane;
+        const bool live = tile_base + li < n;
+        const unsigned long long it = s_items[li];
+        const unsigned digit = live ? (unsigned)((it >> (32 + shift)) & mask) : (unsigned)radix + lane;
         const unsigned peers = __match_any_sync(kFull, digit);
         const int leader = __ffs(peers) - 1;
         unsigned prev = 0;
@@ -402,18 +444,16 @@ __global__ void __launch_bounds__(kThreads) shpl_radix_pass_kernel(RadixArgs a) 
             s_wh[warp][digit] = (unsigned short)(prev + __popc(peers));
         }
         prev = __shfl_sync(kFull, prev, leader);
-        rank[c] = (unsigned short)(prev + __popc(peers & lt));
+        s_rank[li] = (unsigned short)(prev + __popc(peers & lt));
         __syncwarp();
     }
     __syncthreads();
 
-    // phase B: exclusive prefix over warps per digit; tile base of each digit from the global per-tile counts
-    unsigned tot4[kMaxRadix / kThreads];
+    // phase B: exclusive prefix over warps per digit, exclusive scan of the digit totals over the block
     unsigned local_sum = 0;
 #pragma unroll
-    for (int j = 0; j < kMaxRadix / kThreads; ++j) {
-        const int d = threadIdx.x * (kMaxRadix / kThreads) + j;   // consecutive digits per thread
-        tot4[j] = 0;
+    for (int j = 0; j < kDigitsPerThread; ++j) {
+        const int d = threadIdx.x * kDigitsPerThread + j;
         if (d < radix) {
             unsigned run = 0;
 #pragma unroll
@@ -422,18 +462,9 @@ __global__ void __launch_bounds__(kThreads) shpl_radix_pass_kernel(RadixArgs a) 
                 s_wh[w][d] = (unsigned short)run;
                 run += t;
             }
-            unsigned below = 0, all = 0;
-            for (int t = 0; t < n_tiles; ++t) {
-                const unsigned h = hist[((size_t)t << bits) + d];
-                all += h;
-                if (t < tile) below += h;
-            }
-            s_gb[d] = below;
-            tot4[j] = all;
         }
-        local_sum += tot4[j];
+        local_sum += all[j];
     }
-    // block-wide exclusive scan of the digit totals (digits are blocked 4 per thread)
     unsigned incl = local_sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -448,10 +479,10 @@ __global__ void __launch_bounds__(kThreads) shpl_radix_pass_kernel(RadixArgs a) 
         if (w < warp) wpre += s_scan[w];
     unsigned run = wpre + incl - local_sum;
 #pragma unroll
-    for (int j = 0; j < kMaxRadix / kThreads; ++j) {
-        const int d = threadIdx.x * (kMaxRadix / kThreads) + j;
-        if (d < radix) s_gb[d] += run;
-        run += tot4[j];
+    for (int j = 0; j < kDigitsPerThread; ++j) {
+        const int d = threadIdx.x * kDigitsPerThread + j;
+        if (d < radix) s_gb[d] = run + below[j];
+        run += all[j];
     }
     __syncthreads();
 
@@ -459,15 +490,16 @@ __global__ void __launch_bounds__(kThreads) shpl_radix_pass_kernel(RadixArgs a) 
     const bool more = pass + 1 < sp.passes;
     const int nbits = more ? sp.bits[pass + 1] : 0, nshift = more ? sp.shift[pass + 1] : 0;
     unsigned* nhist = more ? a.ws.hist[sort][pass + 1] : nullptr;
-#pragma unroll
+#pragma unroll 2
     for (int c = 0; c < kChunks; ++c) {
-        const int i = wbase + c * 32 + lane;
-        if (i < n) {
-            const unsigned digit = (unsigned)((item[c] >> (32 + shift)) & mask);
-            const unsigned dest = s_gb[digit] + s_wh[warp][digit] + rank[c];
-            out[dest] = item[c];
+        const int li = wofs + c * 32 + lane;
+        if (tile_base + li < n) {
+            const unsigned long long it = s_items[li];
+            const unsigned digit = (unsigned)((it >> (32 + shift)) & mask);
+            const unsigned dest = s_gb[digit] + s_wh[warp][digit] + s_rank[li];
+            out[dest] = it;
             if (more) {
-                const unsigned nd = (unsigned)((item[c] >> (32 + nshift)) & ((1u << nbits) - 1u));
+                const unsigned nd = (unsigned)((it >> (32 + nshift)) & ((1u << nbits) - 1u));
                 atomicAdd(nhist + ((size_t)(dest / kTile) << nbits) + nd, 1u);
             }
         }
@@ -482,33 +514,79 @@ struct FinalArgs {
     const int* entry_base_dev;
 };
 
-__device__ __forceinline__ int lower_bound_key(const unsigned long long* items, int n, unsigned key) {
-    int lo = 0, hi = n;
+__device__ __forceinline__ unsigned key_of(const unsigned long long* items, int i) {
+    return (unsigned)(__ldg(items + i) >> 32);
+}
+
+// lower bound of `key` in items[lo, hi) by plain binary search (window already narrowed)
+__device__ __forceinline__ int lower_bound_key(const unsigned long long* items, int lo, int hi, unsigned key) {
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if ((unsigned)(__ldg(items + mid) >> 32) < key) lo = mid + 1;
+        if (key_of(items, mid) < key) lo = mid + 1;
         else hi = mid;
     }
     return lo;
 }
 
-__global__ void __launch_bounds__(kThreads) shpl_finalize_kernel(FinalArgs a) {
-    const int j = blockIdx.x * kThreads + threadIdx.x;
+// lower bound over the whole array by one warp: 32 probes per round (3 rounds for 32k items)
+__device__ int warp_lower_bound(const unsigned long long* items, int n, unsigned key, int lane) {
+    int lo = 0, hi = n;                      // answer in [lo, hi]
+    while (hi - lo > 32) {
+        const int step = (hi - lo + 32) / 33;          // probes at lo + step*(lane+1) - 1
+        const int pos = min(lo + step * (lane + 1) - 1, hi - 1);
+        const bool less = key_of(items, pos) < key;    // monotone: true for a prefix of the lanes
+        const unsigned m = __ballot_sync(kFull, less);
+        const int c = __popc(m);                        // probes strictly below the key
+        const int new_lo = c == 0 ? lo : min(lo + step * c, hi);   // items up to probe c-1 are < key
+        const int new_hi = c == 32 ? hi : min(lo + step * (c + 1) - 1, hi - 1);
+        lo = new_lo;
+        hi = max(new_hi, new_lo);
+    }
+    // final: each lane tests one position
+    const int pos = lo + lane;
+    const bool less = pos < hi && key_of(items, pos) < key;
+    return lo + __popc(__ballot_sync(kFull, less));
+}
+
+constexpr int kFinalKeys = 256;    // offsets written per CTA (one window search per thread)
+
+// Roles by blockIdx.x: [0, nb_row) row_ptr chunks, [nb_row, nb_row+nb_pix) pix_ptr chunks, the rest
+// gather the payloads of kFinalKeys sorted entries each.
+__global__ void __launch_bounds__(kThreads) shpl_finalize_kernel(FinalArgs a, int nb_row, int nb_pix) {
+    __shared__ int s_lb[2];
     const int n = a.counts[1];
     const int ebase = a.entry_base_dev ? *a.entry_base_dev : 0;
     const unsigned long long* by_row = a.ws.items[0][a.sp[0].passes & 1];
     const unsigned long long* by_pix = a.ws.items[1][a.sp[1].passes & 1];
-    if (j <= a.plan.n_rows) {
-        const int lb = lower_bound_key(by_row, n, (unsigned)j);
-        a.plan.row_ptr[j] = ebase + lb;
-        if (j == a.plan.n_rows) {
-            a.counts[2] = n - lb;
-            a.counts[3] = lb;
-            a.counts[4] = ebase + lb;     // entry base of the next stacked frame
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int b = blockIdx.x;
+    if (b < nb_row + nb_pix) {
+        const bool is_row = b < nb_row;
+        if (!is_row) b -= nb_row;
+        const unsigned long long* items = is_row ? by_row : by_pix;
+        const int n_keys = is_row ? a.plan.n_rows : a.plan.n_src;
+        int* ptr = is_row ? a.plan.row_ptr : a.plan.pix_ptr;
+        const int j0 = b * kFinalKeys;
+        const int j1 = min(j0 + kFinalKeys, n_keys + 1);          // offsets [j0, j1) belong to this CTA
+        if (warp < 2) {
+            const int lb = warp_lower_bound(items, n, (unsigned)(warp == 0 ? j0 : j1), lane);
+            if (lane == 0) s_lb[warp] = lb;
         }
+        __syncthreads();
+        const int w0 = s_lb[0], w1 = s_lb[1];
+        for (int j = j0 + threadIdx.x; j < j1; j += kThreads) {
+            const int lb = lower_bound_key(items, w0, w1, (unsigned)j);
+            ptr[j] = ebase + lb;
+            if (is_row && j == n_keys) {
+                a.counts[2] = n - lb;
+                a.counts[3] = lb;
+                a.counts[4] = ebase + lb;     // entry base of the next stacked frame
+            }
+        }
+        return;
     }
-    if (j <= a.plan.n_src) a.plan.pix_ptr[j] = ebase + lower_bound_key(by_pix, n, (unsigned)j);
-    if (j < n) {
+    b -= nb_row + nb_pix;
+    for (int j = b * kFinalKeys + threadIdx.x; j < min((b + 1) * kFinalKeys, n); j += kThreads) {
         const unsigned long long ir = by_row[j];
         if ((unsigned)(ir >> 32) < (unsigned)a.plan.n_rows) {
             const unsigned k = (unsigned)ir;
@@ -550,7 +628,10 @@ int run_build(PairsArgs& pa, const shpl_plan* plan, const int32_t* entry_base_de
                  "%s: workspace %zu bytes < %zu needed", who, workspace_bytes, pa.ws.total_bytes);
     SHPL_CUDA_OK(cudaMemsetAsync(workspace, 0, pa.ws.header_bytes, s));
     const long long tiles = (pa.n + kTile - 1) / kTile > 0 ? (pa.n + kTile - 1) / kTile : 1;
-    shpl_pairs_kernel<<<(unsigned)tiles, kThreads, 0, s>>>(pa);
+    const long long ptiles = (pa.n + kPairsTile - 1) / kPairsTile > 0 ? (pa.n + kPairsTile - 1) / kPairsTile : 1;
+    // the look-back spins on earlier CTAs: safe without an arrival ticket while every CTA is resident
+    const int use_ticket = ptiles > (long long)shpl::sm_count() * 4 ? 1 : 0;
+    shpl_pairs_kernel<<<(unsigned)ptiles, kThreads, 0, s>>>(pa, use_ticket);
     shpl::count_launches(1);
     if (int rc = shpl::check_launch("shpl_pairs_kernel")) return rc;
     if (!sorting) return SHPL_OK;
@@ -573,10 +654,10 @@ int run_build(PairsArgs& pa, const shpl_plan* plan, const int32_t* entry_base_de
     fa.sp[1] = pa.sp[1];
     fa.plan = *plan;
     fa.entry_base_dev = entry_base_dev;
-    long long span = plan->n_rows + 1;
-    if (plan->n_src + 1 > span) span = plan->n_src + 1;
-    if (pa.n > span) span = pa.n;
-    shpl_finalize_kernel<<<(unsigned)((span + kThreads - 1) / kThreads), kThreads, 0, s>>>(fa);
+    const int nb_row = (plan->n_rows + 1 + kFinalKeys - 1) / kFinalKeys;
+    const int nb_pix = (plan->n_src + 1 + kFinalKeys - 1) / kFinalKeys;
+    const int nb_ent = (int)((pa.n + kFinalKeys - 1) / kFinalKeys);
+    shpl_finalize_kernel<<<(unsigned)(nb_row + nb_pix + nb_ent), kThreads, 0, s>>>(fa, nb_row, nb_pix);
     shpl::count_launches(1);
     return shpl::check_launch("shpl_finalize_kernel");
 }

@@ -82,6 +82,124 @@ __device__ __forceinline__ void copy_tile(const V* __restrict__ in, int in_strid
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Wide cells (>= 32 vectors per cell, i.e. C_s >= 128 with float4): a WARP PER OUTPUT CELL.
+// A CTA owns a tile of 32 cells.  All 8 warps stream the dense part of the tile; the cells that
+// receive contributions are dealt round-robin (by rank among the busy cells) to the warps, so a
+// run of adjacent crowded cells -- the near-range ground cells of a stride-8 BEV map -- is spread
+// over the CTA instead of being walked by one warp.  Inside a cell the lanes own channel vectors
+// q = lane + 32*a; the cell's (idx, val) entries are fetched 32 at a time with one coalesced load
+// and handed round by shuffles, so kGatherUnroll entries x ACC vectors are in flight per lane
+// while the adds still run in ascending k.
+constexpr int kGatherUnroll = 8;
+constexpr int kWideTile = 32;
+
+template <typename V, int ACC>
+__device__ __forceinline__ void pool_row_wide(const V* __restrict__ src, int src_stride, int beg, int end,
+                                              const int* __restrict__ idx, const float* __restrict__ val,
+                                              V* __restrict__ orow, int nv, int lane) {
+    for (int q0 = 0; q0 < nv; q0 += 32 * ACC) {
+        V acc[ACC];
+#pragma unroll
+        for (int a = 0; a < ACC; ++a) acc[a] = vzero((V*)nullptr);
+        for (int c = beg; c < end; c += 32) {
+            int my_p = 0;
+            float my_w = 0.f;
+            if (c + lane < end) {
+                my_p = __ldg(idx + c + lane);
+                my_w = __ldg(val + c + lane);
+            }
+            const int cnt = min(32, end - c);
+            for (int e = 0; e < cnt; e += kGatherUnroll) {
+                V x[kGatherUnroll][ACC];
+                float w[kGatherUnroll];
+#pragma unroll
+                for (int j = 0; j < kGatherUnroll; ++j) {
+                    const int p = __shfl_sync(kFull, my_p, (e + j) & 31);
+                    w[j] = __shfl_sync(kFull, my_w, (e + j) & 31);
+                    const V* row = src + (size_t)p * src_stride;
+#pragma unroll
+                    for (int a = 0; a < ACC; ++a) {
+                        const int q = q0 + a * 32 + lane;
+                        if (e + j < cnt && q < nv) x[j][a] = __ldg(row + q);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kGatherUnroll; ++j) {
+#pragma unroll
+                    for (int a = 0; a < ACC; ++a) {
+                        const int q = q0 + a * 32 + lane;
+                        if (e + j < cnt && q < nv) axpy(acc[a], w[j], x[j][a]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < ACC; ++a) {
+            const int q = q0 + a * 32 + lane;
+            if (q < nv) __stcs(orow + q, acc[a]);
+        }
+    }
+}
+
+// CTA-cooperative dense copy of `rows` cells (flat over rows*nv vectors, kUnroll loads in flight per lane)
+template <typename V>
+__device__ __forceinline__ void cta_copy_tile(const V* __restrict__ in, int in_stride, V* __restrict__ out,
+                                              int out_stride, int nv, int shift, int rows, int warp, int lane) {
+    const int n = rows * nv;
+    for (int s0 = warp * 32 * kUnroll; s0 < n; s0 += kWarps * 32 * kUnroll) {
+        V v[kUnroll];
+        int o[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const int s = s0 + j * 32 + lane;
+            if (s < n) {
+                int r, q;
+                split(s, nv, shift, r, q);
+                v[j] = __ldcs(in + r * in_stride + q);
+                o[j] = r * out_stride + q;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const int s = s0 + j * 32 + lane;
+            if (s < n) __stcs(out + o[j], v[j]);
+        }
+    }
+}
+
+// CTA-cooperative sparse part of a tile of <= 32 wide cells
+template <typename V, int ACC>
+__device__ __forceinline__ void cta_pool_tile_wide(const V* __restrict__ src, int src_stride,
+                                                   const int* __restrict__ ptr, const int* __restrict__ idx,
+                                                   const float* __restrict__ val, V* __restrict__ out,
+                                                   int out_stride, int nv, int rows, int warp, int lane) {
+    int lo = 0, hi = 0;
+    if (lane < rows) {
+        lo = __ldg(ptr + lane);
+        hi = __ldg(ptr + lane + 1);
+    }
+    const unsigned busy = __ballot_sync(kFull, hi > lo);
+    // empty cells: zeros, one cell per warp at a time
+    const V z = vzero((V*)nullptr);
+    for (int r = warp; r < rows; r += kWarps) {
+        if ((busy >> r) & 1u) continue;
+        V* orow = out + r * out_stride;
+        for (int q = lane; q < nv; q += 32) __stcs(orow + q, z);
+    }
+    // busy cells: rank j among the busy ones goes to warp j % kWarps
+    unsigned m = busy;
+    int j = 0;
+    while (m) {
+        const int r = __ffs(m) - 1;
+        m &= m - 1;
+        if ((j++ % kWarps) != warp) continue;
+        const int beg = __shfl_sync(kFull, lo, r);
+        const int end = __shfl_sync(kFull, hi, r);
+        pool_row_wide<V, ACC>(src, src_stride, beg, end, idx, val, out + r * out_stride, nv, lane);
+    }
+}
+
 // Sparse part: out[r*out_stride + q] = sum_k val[k] * src[idx[k]*src_stride + q], k in [ptr[r], ptr[r+1]).
 // `src` and `out` already carry their channel offset.
 template <typename V>
@@ -111,6 +229,7 @@ __device__ __forceinline__ void pool_tile(const V* __restrict__ src, int src_str
         }
         return;
     }
+    // narrow rows: nv lanes per cell, 32/nv cells side by side
     for (int s0 = 0; s0 < n; s0 += 32) {  // warp-uniform trip count
         const int s = s0 + lane;
         int r, q;
@@ -160,7 +279,7 @@ struct PoolArgs {
     int rows_dense, rows_pool;  // cells per warp tile
 };
 
-// Forward: one tile = `rows` destination cells; dense part then sparse part of the same cells.
+// Forward, narrow cells: a WARP owns a tile of `rows` destination cells; dense part then sparse part.
 template <int W>
 __global__ void __launch_bounds__(kThreads) shpl_forward_kernel(PoolArgs a) {
     using V = typename VecOf<W>::type;
@@ -181,8 +300,26 @@ __global__ void __launch_bounds__(kThreads) shpl_forward_kernel(PoolArgs a) {
     }
 }
 
-// Backward: tiles [0, tiles_dense) slice-copy g_fused[:, :C_d] -> g_dst; the rest gather
-// g_fused[:, C_d:] rows through the transposed CSR into the dense g_src (zeros included).
+// Forward, wide cells: a CTA owns a tile of 32 destination cells (one tile per CTA: the hardware
+// block scheduler balances tiles of very different cost).
+template <int W, int ACC>
+__global__ void __launch_bounds__(kThreads, 2) shpl_forward_wide_kernel(PoolArgs a) {
+    using V = typename VecOf<W>::type;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int vf = a.vd + a.vs;
+    const V* dst = static_cast<const V*>(a.dense_in);
+    const V* src = static_cast<const V*>(a.gather_in);
+    V* fused = static_cast<V*>(a.pool_out);
+    const int r0 = blockIdx.x * kWideTile;
+    const int rows = min(kWideTile, a.n_pool - r0);
+    V* out = fused + (size_t)r0 * vf;
+    if (a.vd > 0) cta_copy_tile<V>(dst + (size_t)r0 * a.vd, a.vd, out, vf, a.vd, a.vd_shift, rows, warp, lane);
+    cta_pool_tile_wide<V, ACC>(src, a.vs, a.ptr + r0, a.idx, a.val, out + a.vd, vf, a.vs, rows, warp, lane);
+}
+
+// Backward, narrow cells: warp tiles [0, tiles_dense) slice-copy g_fused[:, :C_d] -> g_dst; the rest
+// gather g_fused[:, C_d:] rows through the transposed CSR into the dense g_src (zeros included).
 template <int W>
 __global__ void __launch_bounds__(kThreads) shpl_backward_kernel(PoolArgs a) {
     using V = typename VecOf<W>::type;
@@ -208,6 +345,32 @@ __global__ void __launch_bounds__(kThreads) shpl_backward_kernel(PoolArgs a) {
     }
 }
 
+// Backward, wide cells: CTA tiles of 32 cells; the first `tiles_pool` CTAs gather (they are the
+// expensive ones and start first), the rest slice-copy.
+template <int W, int ACC>
+__global__ void __launch_bounds__(kThreads, 2) shpl_backward_wide_kernel(PoolArgs a) {
+    using V = typename VecOf<W>::type;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int vf = a.vd + a.vs;
+    const int tiles_pool = (a.n_pool + kWideTile - 1) / kWideTile;
+    const V* g_fused = static_cast<const V*>(a.dense_in);
+    V* g_dst = static_cast<V*>(a.dense_out);
+    V* g_src = static_cast<V*>(a.pool_out);
+    const int t = blockIdx.x;
+    if (t < tiles_pool) {
+        const int p0 = t * kWideTile;
+        const int rows = min(kWideTile, a.n_pool - p0);
+        cta_pool_tile_wide<V, ACC>(g_fused + a.vd, vf, a.ptr + p0, a.idx, a.val, g_src + (size_t)p0 * a.vs, a.vs,
+                                   a.vs, rows, warp, lane);
+    } else {
+        const int r0 = (t - tiles_pool) * kWideTile;
+        const int rows = min(kWideTile, a.n_dense - r0);
+        cta_copy_tile<V>(g_fused + (size_t)r0 * vf, vf, g_dst + (size_t)r0 * a.vd, a.vd, a.vd, a.vd_shift, rows, warp,
+                         lane);
+    }
+}
+
 int log2_or_neg(int v) {
     if (v <= 0 || (v & (v - 1))) return -1;
     int s = 0;
@@ -217,8 +380,9 @@ int log2_or_neg(int v) {
 
 // cells per warp tile: about 1024 vectors of traffic per tile, at most 32 (one lane per cell)
 int tile_rows(int vectors_per_cell) {
+    const int budget = vectors_per_cell >= 64 ? 512 : 1024;   // wide cells are gathered a cell at a time: keep tiles short
     int r = 32;
-    while (r > 1 && r * vectors_per_cell > 1024) r >>= 1;
+    while (r > 1 && r * vectors_per_cell > budget) r >>= 1;
     return r;
 }
 
@@ -265,7 +429,16 @@ extern "C" int shpl_pool_forward(const float* dst, const float* src, const int32
     const long long tiles = ((long long)n_rows + a.rows_pool - 1) / a.rows_pool;
     const int grid = grid_for(tiles);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (w == 4) shpl_forward_kernel<4><<<grid, kThreads, 0, s>>>(a);
+    if (a.vs >= 32) {   // wide cells: one CTA per tile of 32 cells
+        const unsigned g = (unsigned)((n_rows + kWideTile - 1) / kWideTile);
+        const bool one = a.vs <= 32;
+        if (w == 4 && one) shpl_forward_wide_kernel<4, 1><<<g, kThreads, 0, s>>>(a);
+        else if (w == 4) shpl_forward_wide_kernel<4, 2><<<g, kThreads, 0, s>>>(a);
+        else if (w == 2 && one) shpl_forward_wide_kernel<2, 1><<<g, kThreads, 0, s>>>(a);
+        else if (w == 2) shpl_forward_wide_kernel<2, 2><<<g, kThreads, 0, s>>>(a);
+        else if (one) shpl_forward_wide_kernel<1, 1><<<g, kThreads, 0, s>>>(a);
+        else shpl_forward_wide_kernel<1, 2><<<g, kThreads, 0, s>>>(a);
+    } else if (w == 4) shpl_forward_kernel<4><<<grid, kThreads, 0, s>>>(a);
     else if (w == 2) shpl_forward_kernel<2><<<grid, kThreads, 0, s>>>(a);
     else shpl_forward_kernel<1><<<grid, kThreads, 0, s>>>(a);
     shpl::count_launches(1);
@@ -302,7 +475,16 @@ extern "C" int shpl_pool_backward(const float* g_fused, const int32_t* ptrT, con
     if (tiles == 0) return SHPL_OK;
     const int grid = grid_for(tiles);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (w == 4) shpl_backward_kernel<4><<<grid, kThreads, 0, s>>>(a);
+    if (a.vs >= 32) {
+        const unsigned g = (unsigned)((n_src + kWideTile - 1) / kWideTile + (a.n_dense + kWideTile - 1) / kWideTile);
+        const bool one = a.vs <= 32;
+        if (w == 4 && one) shpl_backward_wide_kernel<4, 1><<<g, kThreads, 0, s>>>(a);
+        else if (w == 4) shpl_backward_wide_kernel<4, 2><<<g, kThreads, 0, s>>>(a);
+        else if (w == 2 && one) shpl_backward_wide_kernel<2, 1><<<g, kThreads, 0, s>>>(a);
+        else if (w == 2) shpl_backward_wide_kernel<2, 2><<<g, kThreads, 0, s>>>(a);
+        else if (one) shpl_backward_wide_kernel<1, 1><<<g, kThreads, 0, s>>>(a);
+        else shpl_backward_wide_kernel<1, 2><<<g, kThreads, 0, s>>>(a);
+    } else if (w == 4) shpl_backward_kernel<4><<<grid, kThreads, 0, s>>>(a);
     else if (w == 2) shpl_backward_kernel<2><<<grid, kThreads, 0, s>>>(a);
     else shpl_backward_kernel<1><<<grid, kThreads, 0, s>>>(a);
     shpl::count_launches(1);
