@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SHPL_ABI_VERSION 1
+#define SHPL_ABI_VERSION 2
 
 typedef enum shpl_status {
     SHPL_OK = 0,
@@ -48,9 +48,12 @@ typedef struct shpl_plan {
     int32_t  n_src;     /* Q  = H_i' * W_i' * frames   (source pixels)                */
     int32_t  capacity;  /* entries the arrays below can hold (>= candidate pairs)     */
     int32_t* row_ptr;   /* [n_rows+1]  CSR offsets by destination row                 */
+    int32_t* csr_row;   /* [capacity]  destination row of each entry (the sort key):
+                           lets the kernels split work by ENTRY, not by row          */
     int32_t* csr_src;   /* [capacity]  linear source pixel of each entry              */
     float*   csr_val;   /* [capacity]  non-homogeneous weight of each entry           */
     int32_t* pix_ptr;   /* [n_src+1]   CSR^T offsets by source pixel                  */
+    int32_t* csrT_pix;  /* [capacity]  source pixel of each entry (the sort key)      */
     int32_t* csrT_dst;  /* [capacity]  destination row of each entry                  */
     float*   csrT_val;  /* [capacity]                                                 */
     int32_t* counts;    /* [8] device: [0]=n after image clip, [1]=nnz (columns of M),
@@ -138,10 +141,13 @@ int shpl_plan_from_coo(const int64_t* Mij, const float* val, int64_t m,
  *   fused[r, C_d:C_d+C_s] = sum over the entries of row r, in stored order, of
  *                           val * src[idx, :]      (0 for an empty row)
  * dst [n_rows, C_d], src [n_src, C_s], fused [n_rows, C_d+C_s], all fp32.
- * dst may be NULL with C_d = 0 (pooled map only: _sparse_pool_op without concat). */
+ * dst may be NULL with C_d = 0 (pooled map only: _sparse_pool_op without concat).
+ * key [nnz] = destination row of each entry (plan.csr_row / plan.csrT_pix) and
+ * nnz_max >= number of entries (e.g. plan.capacity) let the kernel balance the
+ * gathers by entry; key may be NULL (then rows are walked cell by cell). */
 int shpl_pool_forward(const float* dst, const float* src,
-                      const int32_t* ptr, const int32_t* idx, const float* val,
-                      int32_t n_rows, int32_t C_d, int32_t n_src, int32_t C_s,
+                      const int32_t* ptr, const int32_t* key, const int32_t* idx, const float* val,
+                      int32_t nnz_max, int32_t n_rows, int32_t C_d, int32_t n_src, int32_t C_s,
                       float* fused, void* stream);
 
 /* Backward of shpl_pool_forward (what TF autodiff derives, SURVEY.md row a13;
@@ -149,10 +155,10 @@ int shpl_pool_forward(const float* dst, const float* src,
  *   g_dst[r, :] = g_fused[r, 0:C_d]
  *   g_src[p, :] = sum over the entries of source p (transposed arrays: ptrT, idxT =
  *                 destination row, valT), in stored order, of valT * g_fused[idxT, C_d:]
- * g_dst may be NULL (no slice copy). */
+ * g_dst may be NULL (no slice copy).  keyT / nnz_max as in shpl_pool_forward. */
 int shpl_pool_backward(const float* g_fused,
-                       const int32_t* ptrT, const int32_t* idxT, const float* valT,
-                       int32_t n_rows, int32_t C_d, int32_t n_src, int32_t C_s,
+                       const int32_t* ptrT, const int32_t* keyT, const int32_t* idxT, const float* valT,
+                       int32_t nnz_max, int32_t n_rows, int32_t C_d, int32_t n_src, int32_t C_s,
                        float* g_dst, float* g_src, void* stream);
 
 #ifdef __cplusplus

@@ -171,10 +171,12 @@ def build_plan(Mij, M_val, img_index_flip, n_rows, src_h, src_w, batch_stride_ro
     pix_ptr, order_p, _ = coo_to_csr(pix_key, src_h * src_w)
     return {
         "row_ptr": row_ptr,
+        "csr_row": row[order_r].astype(np.int32),      # destination row of each entry (the sort key)
         "csr_src": pix[order_r].astype(np.int32),      # source pixel of each entry, row-major order
         "csr_val": val[order_r].astype(np.float32),
         "csr_ent": order_r.astype(np.int32),           # COO entry id (k) of each CSR slot
         "pix_ptr": pix_ptr,
+        "csrT_pix": pix[order_p].astype(np.int32),     # source pixel of each entry (the sort key)
         "csrT_dst": row[order_p].astype(np.int32),     # destination row of each entry, pixel-major order
         "csrT_val": val[order_p].astype(np.float32),
         "csrT_ent": order_p.astype(np.int32),

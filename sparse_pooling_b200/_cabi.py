@@ -22,7 +22,7 @@ SHPL_ERR_CUDA = -2
 SHPL_ERR_WORKSPACE_TOO_SMALL = -3
 SHPL_ERR_UNSUPPORTED = -4
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class ShplPlan(ctypes.Structure):
@@ -32,9 +32,11 @@ class ShplPlan(ctypes.Structure):
         ("n_src", c_int32),
         ("capacity", c_int32),
         ("row_ptr", c_void_p),
+        ("csr_row", c_void_p),
         ("csr_src", c_void_p),
         ("csr_val", c_void_p),
         ("pix_ptr", c_void_p),
+        ("csrT_pix", c_void_p),
         ("csrT_dst", c_void_p),
         ("csrT_val", c_void_p),
         ("counts", c_void_p),
@@ -65,10 +67,10 @@ SIGNATURES = {
                                           c_int32, c_int32,
                                           ctypes.POINTER(ShplPlan), c_int32, c_int32, c_void_p,
                                           c_void_p, c_size_t, c_void_p]),
-    "shpl_pool_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                         c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
-    "shpl_pool_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p,
-                                          c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "shpl_pool_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "shpl_pool_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -590,12 +590,14 @@ __global__ void __launch_bounds__(kThreads) shpl_finalize_kernel(FinalArgs a, in
         const unsigned long long ir = by_row[j];
         if ((unsigned)(ir >> 32) < (unsigned)a.plan.n_rows) {
             const unsigned k = (unsigned)ir;
+            a.plan.csr_row[ebase + j] = a.ws.rowk[k];
             a.plan.csr_src[ebase + j] = a.ws.pixk[k];
             a.plan.csr_val[ebase + j] = a.ws.valk[k];
         }
         const unsigned long long ip = by_pix[j];
         if ((unsigned)(ip >> 32) < (unsigned)a.plan.n_src) {
             const unsigned k = (unsigned)ip;
+            a.plan.csrT_pix[ebase + j] = a.ws.pixk[k];
             a.plan.csrT_dst[ebase + j] = a.ws.rowk[k];
             a.plan.csrT_val[ebase + j] = a.ws.valk[k];
         }
@@ -614,7 +616,7 @@ int run_build(PairsArgs& pa, const shpl_plan* plan, const int32_t* entry_base_de
     SHPL_REQUIRE(pa.counts != nullptr, SHPL_ERR_INVALID_ARGUMENT, "%s: counts is null", who);
     if (sorting) {
         SHPL_REQUIRE(plan && plan->row_ptr && plan->pix_ptr && plan->csr_src && plan->csr_val && plan->csrT_dst &&
-                         plan->csrT_val, SHPL_ERR_INVALID_ARGUMENT, "%s: plan has a null array", who);
+                         plan->csrT_val && plan->csr_row && plan->csrT_pix, SHPL_ERR_INVALID_ARGUMENT, "%s: plan has a null array", who);
         SHPL_REQUIRE(plan->n_rows >= 0 && plan->n_src >= 0 && plan->capacity >= pa.n, SHPL_ERR_INVALID_ARGUMENT,
                      "%s: plan capacity %d < %lld candidates", who, plan->capacity, pa.n);
         pa.sp[0] = make_sort_plan(plan->n_rows);

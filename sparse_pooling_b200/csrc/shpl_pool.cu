@@ -200,6 +200,127 @@ __device__ __forceinline__ void cta_pool_tile_wide(const V* __restrict__ src, in
     }
 }
 
+// Entry-parallel gather for wide cells: one warp takes 32 consecutive entries of the key-sorted
+// entry list and owns every cell whose FIRST entry lies in that chunk (a cell is never split, so
+// its sum keeps the ascending-k order; the warp reads on past the chunk until the cell ends, and
+// skips leading entries that continue a cell begun in the previous chunk).  Work per warp is
+// 32 entries +- one cell, whatever the row-length skew: the crowded near-range cells of a
+// stride-8 BEV map no longer serialise on one CTA.  Entries are streamed through a segmented sum:
+// kGatherUnroll x ACC gathers in flight, the accumulator is flushed when the key changes.
+constexpr int kEntryChunk = 32;
+
+template <typename V, int ACC>
+__device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int src_stride,
+                                                  const int* __restrict__ key, const int* __restrict__ idx,
+                                                  const float* __restrict__ val, int e0, int e1, int e_begin,
+                                                  int e_end, V* __restrict__ out, int out_stride, int nv, int lane) {
+    const int prev_row = (e0 > e_begin) ? __ldg(key + e0 - 1) : -1;
+    for (int q0 = 0; q0 < nv; q0 += 32 * ACC) {
+        int base = e0;
+        int my_row = -1, my_p = 0;
+        float my_w = 0.f;
+        if (base + lane < e_end) {
+            my_row = __ldg(key + base + lane);
+            my_p = __ldg(idx + base + lane);
+            my_w = __ldg(val + base + lane);
+        }
+        int pos = 0;
+        if (prev_row >= 0) {
+            const unsigned fresh = __ballot_sync(kFull, base + lane < e_end && my_row != prev_row);
+            pos = fresh ? __ffs(fresh) - 1 : 32;
+        }
+        if (base + pos >= e1) return;          // no cell starts in this chunk
+        int cur_row = -1;
+        bool finished = false;
+        V acc[ACC];
+#pragma unroll
+        for (int a = 0; a < ACC; ++a) acc[a] = vzero((V*)nullptr);
+        while (true) {
+            const int cnt = min(32, e_end - base);
+            while (pos < cnt) {
+                V x[kGatherUnroll][ACC];
+                float w[kGatherUnroll];
+                int row[kGatherUnroll];
+#pragma unroll
+                for (int j = 0; j < kGatherUnroll; ++j) {
+                    const int ej = pos + j;
+                    row[j] = __shfl_sync(kFull, my_row, ej & 31);
+                    const int p = __shfl_sync(kFull, my_p, ej & 31);
+                    w[j] = __shfl_sync(kFull, my_w, ej & 31);
+                    const V* srow = src + (size_t)p * src_stride;
+#pragma unroll
+                    for (int a = 0; a < ACC; ++a) {
+                        const int q = q0 + a * 32 + lane;
+                        if (ej < cnt && q < nv) x[j][a] = __ldg(srow + q);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kGatherUnroll; ++j) {
+                    if (finished || pos + j >= cnt) continue;
+                    if (row[j] != cur_row) {
+                        if (cur_row >= 0) {
+#pragma unroll
+                            for (int a = 0; a < ACC; ++a) {
+                                const int q = q0 + a * 32 + lane;
+                                if (q < nv) __stcs(out + (size_t)cur_row * out_stride + q, acc[a]);
+                                acc[a] = vzero((V*)nullptr);
+                            }
+                        }
+                        if (base + pos + j >= e1) {   // the next cell belongs to the next warp
+                            finished = true;
+                            cur_row = -1;
+                            continue;
+                        }
+                        cur_row = row[j];
+                    }
+#pragma unroll
+                    for (int a = 0; a < ACC; ++a) {
+                        const int q = q0 + a * 32 + lane;
+                        if (q < nv) axpy(acc[a], w[j], x[j][a]);
+                    }
+                }
+                if (finished) break;
+                pos += kGatherUnroll;
+            }
+            if (finished) break;
+            base += 32;
+            if (base >= e_end) break;
+            my_row = -1;
+            if (base + lane < e_end) {
+                my_row = __ldg(key + base + lane);
+                my_p = __ldg(idx + base + lane);
+                my_w = __ldg(val + base + lane);
+            }
+            pos = 0;
+        }
+        if (cur_row >= 0) {
+#pragma unroll
+            for (int a = 0; a < ACC; ++a) {
+                const int q = q0 + a * 32 + lane;
+                if (q < nv) __stcs(out + (size_t)cur_row * out_stride + q, acc[a]);
+            }
+        }
+    }
+}
+
+// Zeros for the cells of a tile that receive nothing (the busy ones are written by pool_entries_wide)
+template <typename V>
+__device__ __forceinline__ void cta_zero_empty_cells(const int* __restrict__ ptr, V* __restrict__ out, int out_stride,
+                                                     int nv, int rows, int warp, int lane) {
+    int lo = 0, hi = 0;
+    if (lane < rows) {
+        lo = __ldg(ptr + lane);
+        hi = __ldg(ptr + lane + 1);
+    }
+    const unsigned busy = __ballot_sync(kFull, hi > lo);
+    const V z = vzero((V*)nullptr);
+    for (int r = warp; r < rows; r += kWarps) {
+        if ((busy >> r) & 1u) continue;
+        V* orow = out + r * out_stride;
+        for (int q = lane; q < nv; q += 32) __stcs(orow + q, z);
+    }
+}
+
 // Sparse part: out[r*out_stride + q] = sum_k val[k] * src[idx[k]*src_stride + q], k in [ptr[r], ptr[r+1]).
 // `src` and `out` already carry their channel offset.
 template <typename V>
@@ -270,8 +391,10 @@ struct PoolArgs {
     void* dense_out;        // forward: fused              backward: g_dst
     void* pool_out;         // forward: fused              backward: g_src
     const int* ptr;
+    const int* key;         // destination cell of each entry (NULL: walk cells instead of entries)
     const int* idx;
     const float* val;
+    int entry_ctas;         // leading CTAs that gather by entry (wide kernels, key != NULL)
     int n_dense;            // cells of the dense part (0 = skip)
     int n_pool;             // cells of the sparse part
     int vd, vs;             // vectors per cell: own channels, pooled channels
@@ -311,11 +434,20 @@ __global__ void __launch_bounds__(kThreads, 2) shpl_forward_wide_kernel(PoolArgs
     const V* dst = static_cast<const V*>(a.dense_in);
     const V* src = static_cast<const V*>(a.gather_in);
     V* fused = static_cast<V*>(a.pool_out);
-    const int r0 = blockIdx.x * kWideTile;
+    if ((int)blockIdx.x < a.entry_ctas) {       // gather CTAs come first: they are the long pole
+        const int e_begin = __ldg(a.ptr), e_end = __ldg(a.ptr + a.n_pool);
+        const int e0 = e_begin + (blockIdx.x * kWarps + warp) * kEntryChunk;
+        if (e0 >= e_end) return;
+        pool_entries_wide<V, ACC>(src, a.vs, a.key, a.idx, a.val, e0, min(e0 + kEntryChunk, e_end), e_begin, e_end,
+                                  fused + a.vd, vf, a.vs, lane);
+        return;
+    }
+    const int r0 = (blockIdx.x - a.entry_ctas) * kWideTile;
     const int rows = min(kWideTile, a.n_pool - r0);
     V* out = fused + (size_t)r0 * vf;
     if (a.vd > 0) cta_copy_tile<V>(dst + (size_t)r0 * a.vd, a.vd, out, vf, a.vd, a.vd_shift, rows, warp, lane);
-    cta_pool_tile_wide<V, ACC>(src, a.vs, a.ptr + r0, a.idx, a.val, out + a.vd, vf, a.vs, rows, warp, lane);
+    if (a.key != nullptr) cta_zero_empty_cells<V>(a.ptr + r0, out + a.vd, vf, a.vs, rows, warp, lane);
+    else cta_pool_tile_wide<V, ACC>(src, a.vs, a.ptr + r0, a.idx, a.val, out + a.vd, vf, a.vs, rows, warp, lane);
 }
 
 // Backward, narrow cells: warp tiles [0, tiles_dense) slice-copy g_fused[:, :C_d] -> g_dst; the rest
@@ -357,12 +489,21 @@ __global__ void __launch_bounds__(kThreads, 2) shpl_backward_wide_kernel(PoolArg
     const V* g_fused = static_cast<const V*>(a.dense_in);
     V* g_dst = static_cast<V*>(a.dense_out);
     V* g_src = static_cast<V*>(a.pool_out);
-    const int t = blockIdx.x;
+    if ((int)blockIdx.x < a.entry_ctas) {
+        const int e_begin = __ldg(a.ptr), e_end = __ldg(a.ptr + a.n_pool);
+        const int e0 = e_begin + (blockIdx.x * kWarps + warp) * kEntryChunk;
+        if (e0 >= e_end) return;
+        pool_entries_wide<V, ACC>(g_fused + a.vd, vf, a.key, a.idx, a.val, e0, min(e0 + kEntryChunk, e_end), e_begin,
+                                  e_end, g_src, a.vs, a.vs, lane);
+        return;
+    }
+    const int t = blockIdx.x - a.entry_ctas;
     if (t < tiles_pool) {
         const int p0 = t * kWideTile;
         const int rows = min(kWideTile, a.n_pool - p0);
-        cta_pool_tile_wide<V, ACC>(g_fused + a.vd, vf, a.ptr + p0, a.idx, a.val, g_src + (size_t)p0 * a.vs, a.vs,
-                                   a.vs, rows, warp, lane);
+        if (a.key != nullptr) cta_zero_empty_cells<V>(a.ptr + p0, g_src + (size_t)p0 * a.vs, a.vs, a.vs, rows, warp, lane);
+        else cta_pool_tile_wide<V, ACC>(g_fused + a.vd, vf, a.ptr + p0, a.idx, a.val, g_src + (size_t)p0 * a.vs, a.vs,
+                                        a.vs, rows, warp, lane);
     } else {
         const int r0 = (t - tiles_pool) * kWideTile;
         const int rows = min(kWideTile, a.n_dense - r0);
@@ -402,9 +543,9 @@ int grid_for(long long tiles) {
 
 }  // namespace
 
-extern "C" int shpl_pool_forward(const float* dst, const float* src, const int32_t* ptr, const int32_t* idx,
-                                 const float* val, int32_t n_rows, int32_t C_d, int32_t n_src, int32_t C_s,
-                                 float* fused, void* stream) {
+extern "C" int shpl_pool_forward(const float* dst, const float* src, const int32_t* ptr, const int32_t* key,
+                                 const int32_t* idx, const float* val, int32_t nnz_max, int32_t n_rows, int32_t C_d,
+                                 int32_t n_src, int32_t C_s, float* fused, void* stream) {
     SHPL_REQUIRE(n_rows >= 0 && n_src >= 0 && C_d >= 0 && C_s > 0, SHPL_ERR_INVALID_ARGUMENT,
                  "shpl_pool_forward: bad sizes n_rows=%d n_src=%d C_d=%d C_s=%d", n_rows, n_src, C_d, C_s);
     SHPL_REQUIRE(src && ptr && fused && (C_d == 0 || dst), SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_forward: null pointer");
@@ -417,8 +558,10 @@ extern "C" int shpl_pool_forward(const float* dst, const float* src, const int32
     a.dense_out = fused;
     a.pool_out = fused;
     a.ptr = ptr;
+    a.key = (key && nnz_max > 0) ? key : nullptr;
     a.idx = idx;
     a.val = val;
+    a.entry_ctas = a.key ? (nnz_max + kEntryChunk * kWarps - 1) / (kEntryChunk * kWarps) : 0;
     a.n_dense = n_rows;
     a.n_pool = n_rows;
     a.vd = C_d / w;
@@ -430,7 +573,7 @@ extern "C" int shpl_pool_forward(const float* dst, const float* src, const int32
     const int grid = grid_for(tiles);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (a.vs >= 32) {   // wide cells: one CTA per tile of 32 cells
-        const unsigned g = (unsigned)((n_rows + kWideTile - 1) / kWideTile);
+        const unsigned g = (unsigned)(a.entry_ctas + (n_rows + kWideTile - 1) / kWideTile);
         const bool one = a.vs <= 32;
         if (w == 4 && one) shpl_forward_wide_kernel<4, 1><<<g, kThreads, 0, s>>>(a);
         else if (w == 4) shpl_forward_wide_kernel<4, 2><<<g, kThreads, 0, s>>>(a);
@@ -445,9 +588,9 @@ extern "C" int shpl_pool_forward(const float* dst, const float* src, const int32
     return shpl::check_launch("shpl_forward_kernel");
 }
 
-extern "C" int shpl_pool_backward(const float* g_fused, const int32_t* ptrT, const int32_t* idxT, const float* valT,
-                                  int32_t n_rows, int32_t C_d, int32_t n_src, int32_t C_s, float* g_dst,
-                                  float* g_src, void* stream) {
+extern "C" int shpl_pool_backward(const float* g_fused, const int32_t* ptrT, const int32_t* keyT, const int32_t* idxT,
+                                  const float* valT, int32_t nnz_max, int32_t n_rows, int32_t C_d, int32_t n_src,
+                                  int32_t C_s, float* g_dst, float* g_src, void* stream) {
     SHPL_REQUIRE(n_rows >= 0 && n_src >= 0 && C_d >= 0 && C_s > 0, SHPL_ERR_INVALID_ARGUMENT,
                  "shpl_pool_backward: bad sizes n_rows=%d n_src=%d C_d=%d C_s=%d", n_rows, n_src, C_d, C_s);
     SHPL_REQUIRE(g_fused && ptrT && idxT && valT && g_src, SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_backward: null pointer");
@@ -460,8 +603,10 @@ extern "C" int shpl_pool_backward(const float* g_fused, const int32_t* ptrT, con
     a.dense_out = g_dst;
     a.pool_out = g_src;
     a.ptr = ptrT;
+    a.key = (keyT && nnz_max > 0) ? keyT : nullptr;
     a.idx = idxT;
     a.val = valT;
+    a.entry_ctas = a.key ? (nnz_max + kEntryChunk * kWarps - 1) / (kEntryChunk * kWarps) : 0;
     a.n_dense = dense ? n_rows : 0;
     a.n_pool = n_src;
     a.vd = C_d / w;
@@ -476,7 +621,7 @@ extern "C" int shpl_pool_backward(const float* g_fused, const int32_t* ptrT, con
     const int grid = grid_for(tiles);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (a.vs >= 32) {
-        const unsigned g = (unsigned)((n_src + kWideTile - 1) / kWideTile + (a.n_dense + kWideTile - 1) / kWideTile);
+        const unsigned g = (unsigned)(a.entry_ctas + (n_src + kWideTile - 1) / kWideTile + (a.n_dense + kWideTile - 1) / kWideTile);
         const bool one = a.vs <= 32;
         if (w == 4 && one) shpl_backward_wide_kernel<4, 1><<<g, kThreads, 0, s>>>(a);
         else if (w == 4) shpl_backward_wide_kernel<4, 2><<<g, kThreads, 0, s>>>(a);

@@ -62,7 +62,9 @@ class SparsePoolPlan:
         i32 = dict(dtype=torch.int32, device=device)
         self.row_ptr = torch.empty(R + 1, **i32)
         self.pix_ptr = torch.empty(Q + 1, **i32)
+        self.csr_row = torch.empty(self.capacity, **i32)
         self.csr_src = torch.empty(self.capacity, **i32)
+        self.csrT_pix = torch.empty(self.capacity, **i32)
         self.csrT_dst = torch.empty(self.capacity, **i32)
         self.csr_val = torch.empty(self.capacity, dtype=torch.float32, device=device)
         self.csrT_val = torch.empty(self.capacity, dtype=torch.float32, device=device)
@@ -78,6 +80,14 @@ class SparsePoolPlan:
     def n_src(self):
         return self.src_per_frame * self.frames
 
+    def by_row(self):
+        """(ptr, key, idx, val, nnz_max) of the CSR keyed by destination BEV cell."""
+        return (self.row_ptr, self.csr_row, self.csr_src, self.csr_val, self.capacity)
+
+    def by_pixel(self):
+        """(ptr, key, idx, val, nnz_max) of the CSR^T keyed by source pixel."""
+        return (self.pix_ptr, self.csrT_pix, self.csrT_dst, self.csrT_val, self.capacity)
+
     def frame_struct(self, f):
         """shpl_plan for frame f: ptr arrays point at the frame's sub-array; entry arrays are shared."""
         s = _cabi.ShplPlan()
@@ -86,7 +96,9 @@ class SparsePoolPlan:
         s.capacity = self.capacity
         s.row_ptr = self.row_ptr.data_ptr() + 4 * f * self.rows_per_frame
         s.pix_ptr = self.pix_ptr.data_ptr() + 4 * f * self.src_per_frame
+        s.csr_row = self.csr_row.data_ptr()
         s.csr_src = self.csr_src.data_ptr()
+        s.csrT_pix = self.csrT_pix.data_ptr()
         s.csr_val = self.csr_val.data_ptr()
         s.csrT_dst = self.csrT_dst.data_ptr()
         s.csrT_val = self.csrT_val.data_ptr()
@@ -131,23 +143,26 @@ def plan_from_coo(indices, values, source_index, n_rows, src_hw, device=None):
     return plan
 
 
-def pool_forward(dst, src, ptr, idx, val, n_rows, n_src):
-    """fused[r] = concat(dst[r], sum_k val_k * src[idx_k])  (shpl_pool_forward)."""
+def pool_forward(dst, src, csr, n_rows, n_src):
+    """fused[r] = concat(dst[r], sum_k val_k * src[idx_k])  (shpl_pool_forward).
+    csr = (ptr, key, idx, val, nnz_max)."""
+    ptr, key, idx, val, nnz_max = csr
     require_cuda(src, "source feature map")
     C_s = src.shape[-1]
     C_d = 0 if dst is None else dst.shape[-1]
     fused = torch.empty((n_rows, C_d + C_s), dtype=torch.float32, device=src.device)
-    rc = _lib.shpl_pool_forward(_ptr(dst), _ptr(src), _ptr(ptr), _ptr(idx), _ptr(val), n_rows, C_d, n_src, C_s,
-                                _ptr(fused), _stream())
+    rc = _lib.shpl_pool_forward(_ptr(dst), _ptr(src), _ptr(ptr), _ptr(key), _ptr(idx), _ptr(val), int(nnz_max),
+                                n_rows, C_d, n_src, C_s, _ptr(fused), _stream())
     _cabi.check(rc, "shpl_pool_forward")
     return fused
 
 
-def pool_backward(g_fused, ptrT, idxT, valT, n_rows, C_d, n_src, C_s, want_dst=True):
+def pool_backward(g_fused, csrT, n_rows, C_d, n_src, C_s, want_dst=True):
+    ptrT, keyT, idxT, valT, nnz_max = csrT
     g_dst = torch.empty((n_rows, C_d), dtype=torch.float32, device=g_fused.device) if (want_dst and C_d) else None
     g_src = torch.empty((n_src, C_s), dtype=torch.float32, device=g_fused.device)
-    rc = _lib.shpl_pool_backward(_ptr(g_fused), _ptr(ptrT), _ptr(idxT), _ptr(valT), n_rows, C_d, n_src, C_s,
-                                 _ptr(g_dst), _ptr(g_src), _stream())
+    rc = _lib.shpl_pool_backward(_ptr(g_fused), _ptr(ptrT), _ptr(keyT), _ptr(idxT), _ptr(valT), int(nnz_max),
+                                 n_rows, C_d, n_src, C_s, _ptr(g_dst), _ptr(g_src), _stream())
     _cabi.check(rc, "shpl_pool_backward")
     return g_dst, g_src
 
@@ -168,9 +183,9 @@ class SparsePoolFunction(torch.autograd.Function):
         if B != plan.frames:
             raise ValueError("feature batch %d != frames in the plan %d" % (B, plan.frames))
         if transposed:
-            ptr, idx, val, n_rows, n_src = plan.pix_ptr, plan.csrT_dst, plan.csrT_val, plan.n_src, plan.n_rows
+            csr, n_rows, n_src = plan.by_pixel(), plan.n_src, plan.n_rows
         else:
-            ptr, idx, val, n_rows, n_src = plan.row_ptr, plan.csr_src, plan.csr_val, plan.n_rows, plan.n_src
+            csr, n_rows, n_src = plan.by_row(), plan.n_rows, plan.n_src
         src_c = src.contiguous()
         if src_c.dtype != torch.float32:
             raise ValueError("SHPL feature maps must be float32 (the reference's dtype)")
@@ -182,7 +197,7 @@ class SparsePoolFunction(torch.autograd.Function):
             dst_c = dst.contiguous()
             if dst_c.shape[0] * dst_c.shape[1] * dst_c.shape[2] != n_rows:
                 raise ValueError("destination map %s does not match the plan (%d cells)" % (tuple(dst.shape), n_rows))
-        fused = pool_forward(dst_c, src_c, ptr, idx, val, n_rows, n_src)
+        fused = pool_forward(dst_c, src_c, csr, n_rows, n_src)
         ctx.plan = plan
         ctx.transposed = transposed
         ctx.src_shape = tuple(src.shape)
@@ -193,13 +208,13 @@ class SparsePoolFunction(torch.autograd.Function):
     def backward(ctx, g_fused):
         plan = ctx.plan
         if ctx.transposed:   # entries grouped by what was the *source* of the forward
-            ptrT, idxT, valT, n_rows, n_src = plan.row_ptr, plan.csr_src, plan.csr_val, plan.n_src, plan.n_rows
+            csrT, n_rows, n_src = plan.by_row(), plan.n_src, plan.n_rows
         else:
-            ptrT, idxT, valT, n_rows, n_src = plan.pix_ptr, plan.csrT_dst, plan.csrT_val, plan.n_rows, plan.n_src
+            csrT, n_rows, n_src = plan.by_pixel(), plan.n_rows, plan.n_src
         C_s = ctx.src_shape[-1]
         C_d = 0 if ctx.dst_shape is None else ctx.dst_shape[-1]
         g = g_fused.contiguous()
-        g_dst, g_src = pool_backward(g, ptrT, idxT, valT, n_rows, C_d, n_src, C_s,
+        g_dst, g_src = pool_backward(g, csrT, n_rows, C_d, n_src, C_s,
                                      want_dst=ctx.needs_input_grad[0] and C_d > 0)
         if g_dst is not None:
             g_dst = g_dst.reshape(ctx.dst_shape)

@@ -110,24 +110,24 @@ class FramePipeline:
     def forward_layer(self, i, bev, img, stream):
         L = self.layers[i]
         s, pl = L.spec, L.plan
-        rc = _lib.shpl_pool_forward(_p(bev), _p(img), _p(pl.row_ptr), _p(pl.csr_src), _p(pl.csr_val),
-                                    s.R, s.c_bev, s.Q, s.c_img, _p(L.fused_bev), stream)
+        rc = _lib.shpl_pool_forward(_p(bev), _p(img), _p(pl.row_ptr), _p(pl.csr_row), _p(pl.csr_src), _p(pl.csr_val),
+                                    pl.capacity, s.R, s.c_bev, s.Q, s.c_img, _p(L.fused_bev), stream)
         _cabi.check(rc, "shpl_pool_forward")
         if s.dual:
-            rc = _lib.shpl_pool_forward(_p(img), _p(bev), _p(pl.pix_ptr), _p(pl.csrT_dst), _p(pl.csrT_val),
-                                        s.Q, s.c_img, s.R, s.c_bev, _p(L.fused_img), stream)
+            rc = _lib.shpl_pool_forward(_p(img), _p(bev), _p(pl.pix_ptr), _p(pl.csrT_pix), _p(pl.csrT_dst),
+                                        _p(pl.csrT_val), pl.capacity, s.Q, s.c_img, s.R, s.c_bev, _p(L.fused_img), stream)
             _cabi.check(rc, "shpl_pool_forward")
 
     # -- backward of layer i from the upstream gradients of the fused maps --
     def backward_layer(self, i, g_fused_bev, g_fused_img, stream):
         L = self.layers[i]
         s, pl = L.spec, L.plan
-        rc = _lib.shpl_pool_backward(_p(g_fused_bev), _p(pl.pix_ptr), _p(pl.csrT_dst), _p(pl.csrT_val),
-                                     s.R, s.c_bev, s.Q, s.c_img, _p(L.g_bev), _p(L.g_img), stream)
+        rc = _lib.shpl_pool_backward(_p(g_fused_bev), _p(pl.pix_ptr), _p(pl.csrT_pix), _p(pl.csrT_dst), _p(pl.csrT_val),
+                                     pl.capacity, s.R, s.c_bev, s.Q, s.c_img, _p(L.g_bev), _p(L.g_img), stream)
         _cabi.check(rc, "shpl_pool_backward")
         if s.dual:
-            rc = _lib.shpl_pool_backward(_p(g_fused_img), _p(pl.row_ptr), _p(pl.csr_src), _p(pl.csr_val),
-                                         s.Q, s.c_img, s.R, s.c_bev, _p(L.g_img_slice), _p(L.g_bev_pool), stream)
+            rc = _lib.shpl_pool_backward(_p(g_fused_img), _p(pl.row_ptr), _p(pl.csr_row), _p(pl.csr_src), _p(pl.csr_val),
+                                         pl.capacity, s.Q, s.c_img, s.R, s.c_bev, _p(L.g_img_slice), _p(L.g_bev_pool), stream)
             _cabi.check(rc, "shpl_pool_backward")
             # TF's AddN of the two partial gradients of each input
             L.g_bev.add_(L.g_bev_pool)

@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_binding_covers_the_header(lib):
     from sparse_pooling_b200 import _cabi
     assert sorted(_cabi.SIGNATURES) == declared_functions()
-    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 1
+    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 2
 
 
 def test_workspace_query_grows_with_n(lib):
@@ -52,11 +52,11 @@ def test_workspace_query_grows_with_n(lib):
 def test_invalid_arguments_return_error_codes_without_a_gpu(lib):
     from sparse_pooling_b200 import _cabi
     L = _cabi.lib
-    assert L.shpl_pool_forward(None, None, None, None, None, 10, 4, 10, 0, None, None) == _cabi.SHPL_ERR_INVALID_ARGUMENT
+    assert L.shpl_pool_forward(None, None, None, None, None, None, 0, 10, 4, 10, 0, None, None) == _cabi.SHPL_ERR_INVALID_ARGUMENT
     assert b"bad sizes" in L.shpl_last_error()
-    assert L.shpl_pool_backward(None, None, None, None, 10, 4, 10, 4, None, None, None) == _cabi.SHPL_ERR_INVALID_ARGUMENT
+    assert L.shpl_pool_backward(None, None, None, None, None, 0, 10, 4, 10, 4, None, None, None) == _cabi.SHPL_ERR_INVALID_ARGUMENT
     with pytest.raises(ValueError):
-        _cabi.check(L.shpl_pool_forward(None, None, None, None, None, -1, 4, 10, 4, None, None), "shpl_pool_forward")
+        _cabi.check(L.shpl_pool_forward(None, None, None, None, None, None, 0, -1, 4, 10, 4, None, None), "shpl_pool_forward")
     st = _cabi.ShplPlan()
     rc = L.shpl_produce_input(None, None, None, 0, 8, 8, 8, 8, 0, 1, None, 0, 0, None, None, None, None,
                               ctypes.byref(st), 0, 0, None, None, 0, None)

@@ -40,6 +40,7 @@ def plan_arrays(plan, f=0):
     lo, hi = int(row_ptr[0]), int(row_ptr[-1])
     return dict(row_ptr=row_ptr - lo, pix_ptr=pix_ptr - lo,
                 csr_src=plan.csr_src.cpu().numpy()[lo:hi] - f * Q, csr_val=plan.csr_val.cpu().numpy()[lo:hi],
+                csr_row=plan.csr_row.cpu().numpy()[lo:hi] - f * R, csrT_pix=plan.csrT_pix.cpu().numpy()[lo:hi] - f * Q,
                 csrT_dst=plan.csrT_dst.cpu().numpy()[lo:hi] - f * R, csrT_val=plan.csrT_val.cpu().numpy()[lo:hi],
                 counts=c[f])
 
@@ -47,7 +48,7 @@ def plan_arrays(plan, f=0):
 def assert_plan_equals_oracle(plan, Mij, val, flip, n_rows, src_hw, f=0):
     ref = io.build_plan(Mij, val, flip, n_rows, src_hw[0], src_hw[1])
     got = plan_arrays(plan, f)
-    for k in ("row_ptr", "pix_ptr", "csr_src", "csr_val", "csrT_dst", "csrT_val"):
+    for k in ("row_ptr", "pix_ptr", "csr_row", "csr_src", "csr_val", "csrT_pix", "csrT_dst", "csrT_val"):
         np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
     assert int(got["counts"][2]) == ref["n_oob"]
     assert int(got["counts"][3]) == len(ref["csr_src"])
