@@ -161,6 +161,29 @@ int shpl_pool_backward(const float* g_fused,
                        int32_t nnz_max, int32_t n_rows, int32_t C_d, int32_t n_src, int32_t C_s,
                        float* g_dst, float* g_src, void* stream);
 
+/* Both directions of sparse_pool_layer in ONE launch (the `bv_index is not None` branch,
+ * avod/avod/utils/sparse_pool_utils.py:79-87, on top of :65-72):
+ *   fused_bev[r] = concat(bev[r], sum_{k in row r}   val_k * img[pix_k])     [n_rows, C_b+C_i]
+ *   fused_img[p] = concat(img[p], sum_{k at pixel p} val_k * bev[row_k])     [n_src,  C_i+C_b]
+ * The eight index arrays are the fields of shpl_plan. */
+int shpl_pool_forward_dual(const float* bev, const float* img,
+                           const int32_t* row_ptr, const int32_t* csr_row, const int32_t* csr_src, const float* csr_val,
+                           const int32_t* pix_ptr, const int32_t* csrT_pix, const int32_t* csrT_dst, const float* csrT_val,
+                           int32_t nnz_max, int32_t n_rows, int32_t C_b, int32_t n_src, int32_t C_i,
+                           float* fused_bev, float* fused_img, void* stream);
+
+/* Backward of shpl_pool_forward_dual in one launch.  Each input of the layer feeds two
+ * consumers, so TF adds two partial gradients (AddN); here the sum is formed in registers:
+ *   g_bev[r] = g_fused_bev[r, :C_b] + sum_{k in row r}   val_k * g_fused_img[pix_k, C_i:]
+ *   g_img[p] = g_fused_img[p, :C_i] + sum_{k at pixel p} val_k * g_fused_bev[row_k, C_b:]
+ * (the pooled sum is accumulated from zero in stored order, then added to the slice: the same
+ * roundings as slice + pooled computed separately). */
+int shpl_pool_backward_dual(const float* g_fused_bev, const float* g_fused_img,
+                            const int32_t* row_ptr, const int32_t* csr_row, const int32_t* csr_src, const float* csr_val,
+                            const int32_t* pix_ptr, const int32_t* csrT_pix, const int32_t* csrT_dst, const float* csrT_val,
+                            int32_t nnz_max, int32_t n_rows, int32_t C_b, int32_t n_src, int32_t C_i,
+                            float* g_bev, float* g_img, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

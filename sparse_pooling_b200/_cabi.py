@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libshpl.so")
+LIB_PATH = os.environ.get("SHPL_LIB") or os.path.join(_HERE, "libshpl.so")   # SHPL_LIB: try an experimental build
 
 c_void_p = ctypes.c_void_p
 c_int32 = ctypes.c_int32
@@ -71,6 +71,8 @@ SIGNATURES = {
                                          c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "shpl_pool_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "shpl_pool_forward_dual": (ctypes.c_int, [c_void_p] * 10 + [c_int32] * 5 + [c_void_p] * 3),
+    "shpl_pool_backward_dual": (ctypes.c_int, [c_void_p] * 10 + [c_int32] * 5 + [c_void_p] * 3),
 }
 
 

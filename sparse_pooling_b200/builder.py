@@ -86,6 +86,7 @@ def build_avod_plan(points, voxel_indices, P, im_size, bv_size, stride=(1, 1), s
                                   f * plan.rows_per_frame, f * plan.src_per_frame, plan.entry_base(f),
                                   _ptr(ws), ws.numel(), _stream())
         _cabi.check(rc, "shpl_build_avod")
+    plan.entry_bound = max(n_total, 1)
     plan._keep = (pts, vox, keep)
     if read_counts:
         plan.read_counts()

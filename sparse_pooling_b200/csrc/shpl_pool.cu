@@ -7,21 +7,41 @@
 //   :72,:87  tf.concat(axis=3)
 // and the gradients TF autodiff derives for them.
 //
-// The work is a streaming copy with rare gathers (2 % of BEV cells are hit at KITTI
-// stride 1), so the design is a copy-class kernel: 128-bit coalesced accesses, 8
-// independent loads in flight per lane, streaming cache hints on the dense traffic,
-// a warp per tile of destination cells.  A tile is <= 32 cells so that one lane per
-// cell holds the CSR offsets and the whole tile's emptiness is one ballot.
-// Sums are accumulated in stored (ascending k) order with separately rounded
-// multiply and add, which makes the result bit-identical to the sequential oracle.
+// Every launch executes a short list of JOBS.  A job is "for each of n cells: a dense part
+// (copy vd vectors) and/or a pooled part (sum over the cell's CSR entries of val * gathered
+// row, vs vectors), written side by side (concat) or added together (AddN of two gradient
+// paths)".  Forward of one direction = 1 job; backward of one direction = 2 jobs (slice copy
+// over destination cells, gather over source cells); the dual-direction forms are the two
+// directions' jobs in one launch, and the dual backward uses the add form so that no
+// intermediate gradient is materialised.
+//
+// Two kernel families, picked by the pooled width:
+//   narrow (vs < 32 vectors, C_s < 128): the work is a streaming copy with rare gathers (2 % of
+//     BEV cells are hit at KITTI stride 1).  A WARP owns a tile of <= 32 cells: 128-bit coalesced
+//     accesses, 8 independent loads in flight per lane, streaming cache hints, one lane per cell
+//     holds the CSR offsets and the tile's emptiness is one ballot.
+//   wide (vs >= 32): a WARP PER OUTPUT CELL, lanes own channel vectors.  Dense tiles of 32 cells
+//     are streamed by whole CTAs; the gathers are split BY ENTRY (chunks of the key-sorted entry
+//     list), not by cell, so crowded near-range cells of a stride-8 BEV map cannot serialise.
+// Sums run in stored (ascending k) order with separately rounded multiply and add, which makes
+// the result bit-identical to the sequential oracle.
 #include "shpl_common.cuh"
 
 namespace {
 
+#ifndef SHPL_NARROW_MIN_CTAS
+#define SHPL_NARROW_MIN_CTAS 3
+#endif
+#ifndef SHPL_UNROLL
+#define SHPL_UNROLL 8
+#endif
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kUnroll = 8;
+constexpr int kUnroll = SHPL_UNROLL;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kMaxJobs = 4;
+constexpr int kGatherUnroll = 8;
+constexpr int kWideTile = 32;
 
 template <int W> struct VecOf;
 template <> struct VecOf<4> { using type = float4; };
@@ -45,6 +65,40 @@ __device__ __forceinline__ void axpy(float2& a, float w, const float2& x) {
 }
 __device__ __forceinline__ void axpy(float& a, float w, const float& x) { a = __fadd_rn(a, __fmul_rn(w, x)); }
 
+__device__ __forceinline__ float4 vadd(const float4& a, const float4& b) {
+    return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+}
+__device__ __forceinline__ float2 vadd(const float2& a, const float2& b) {
+    return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+}
+__device__ __forceinline__ float vadd(const float& a, const float& b) { return __fadd_rn(a, b); }
+
+struct Job {
+    const void* dense_in;    // [n_cells, dense_in_stride] vectors; first vd of each cell are used
+    const void* gather_in;   // rows gathered through idx, gather_stride vectors apart (channel offset applied)
+    void* dense_out;         // concat form: where the dense part goes
+    void* pool_out;          // where the pooled part goes (add form: dense + pooled)
+    const int* ptr;          // [n_cells+1]
+    const int* key;          // [nnz] cell of each entry, or NULL (then cells are walked one by one)
+    const int* idx;
+    const float* val;
+    int dense_in_stride, dense_out_stride, gather_stride, pool_out_stride;
+    int vd, vs;              // vectors per cell: dense part / pooled part (either may be 0)
+    int vd_shift, vs_shift;  // log2 or -1
+    int n_cells;
+    int add;                 // 1: pool_out[c] = dense_in[c] + sum (vd == vs); 0: concat form
+    int rows_per_tile;       // narrow: cells per warp tile
+    int entry_ctas;          // wide: leading CTAs of this job that gather by entry; narrow: CTAs serving the job
+    int entry_chunk;         // wide: entries per warp
+    int tiles;               // narrow: warp tiles; wide: CTA tiles of kWideTile cells
+};
+
+struct PoolArgs {
+    Job job[kMaxJobs];
+    int n_jobs;
+    int begin[kMaxJobs + 1];   // narrow: first warp tile of each job; wide: first CTA of each job
+};
+
 // slot s of a tile -> (cell r inside the tile, vector q inside the cell); nv = vectors per cell
 __device__ __forceinline__ void split(int s, int nv, int shift, int& r, int& q) {
     if (shift >= 0) {
@@ -56,7 +110,8 @@ __device__ __forceinline__ void split(int s, int nv, int shift, int& r, int& q) 
     }
 }
 
-// Dense part: `rows` cells of `nv` vectors, in[r*in_stride + q] -> out[r*out_stride + q].
+// ------------------------------------------------------------------------------------ narrow
+// Dense part by one warp: `rows` cells of `nv` vectors, in[r*in_stride + q] -> out[r*out_stride + q].
 template <typename V>
 __device__ __forceinline__ void copy_tile(const V* __restrict__ in, int in_stride, V* __restrict__ out,
                                           int out_stride, int nv, int shift, int rows, int lane) {
@@ -82,22 +137,128 @@ __device__ __forceinline__ void copy_tile(const V* __restrict__ in, int in_strid
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Wide cells (>= 32 vectors per cell, i.e. C_s >= 128 with float4): a WARP PER OUTPUT CELL.
-// A CTA owns a tile of 32 cells.  All 8 warps stream the dense part of the tile; the cells that
-// receive contributions are dealt round-robin (by rank among the busy cells) to the warps, so a
-// run of adjacent crowded cells -- the near-range ground cells of a stride-8 BEV map -- is spread
-// over the CTA instead of being walked by one warp.  Inside a cell the lanes own channel vectors
-// q = lane + 32*a; the cell's (idx, val) entries are fetched 32 at a time with one coalesced load
-// and handed round by shuffles, so kGatherUnroll entries x ACC vectors are in flight per lane
-// while the adds still run in ascending k.
-constexpr int kGatherUnroll = 8;
-constexpr int kWideTile = 32;
+// Pooled part by one warp: out[r*out_stride + q] = (addend ? addend[r*add_stride + q] : 0) +
+// sum_k val[k] * src[idx[k]*src_stride + q], k in [ptr[r], ptr[r+1]).  nv lanes per cell, 32/nv cells
+// side by side.
+template <typename V, bool kAdd>
+__device__ __forceinline__ void pool_tile(const V* __restrict__ src, int src_stride, const int* __restrict__ ptr,
+                                          const int* __restrict__ idx, const float* __restrict__ val,
+                                          V* __restrict__ out, int out_stride, const V* __restrict__ addend,
+                                          int add_stride, int nv, int shift, int rows, int lane) {
+    int lo = 0, hi = 0;
+    if (lane < rows) {
+        lo = __ldg(ptr + lane);
+        hi = __ldg(ptr + lane + 1);
+    }
+    const unsigned busy = __ballot_sync(kFull, hi > lo);
+    const int n = rows * nv;
+    if (busy == 0u) {  // the common case: nothing projects into this tile
+        if constexpr (kAdd) {
+            copy_tile<V>(addend, add_stride, out, out_stride, nv, shift, rows, lane);
+            return;
+        }
+        const V z = vzero((V*)nullptr);
+        for (int s0 = 0; s0 < n; s0 += 32 * kUnroll) {
+#pragma unroll
+            for (int j = 0; j < kUnroll; ++j) {
+                const int s = s0 + j * 32 + lane;
+                if (s < n) {
+                    int r, q;
+                    split(s, nv, shift, r, q);
+                    __stcs(out + r * out_stride + q, z);
+                }
+            }
+        }
+        return;
+    }
+    for (int s0 = 0; s0 < n; s0 += 32) {  // warp-uniform trip count
+        const int s = s0 + lane;
+        int r, q;
+        split(s, nv, shift, r, q);
+        int beg = __shfl_sync(kFull, lo, r & 31);
+        int end = __shfl_sync(kFull, hi, r & 31);
+        if (s >= n) end = beg;
+        V base = vzero((V*)nullptr);
+        if constexpr (kAdd) {
+            if (s < n) base = __ldcs(addend + r * add_stride + q);
+        }
+        V acc = vzero((V*)nullptr);
+        int k = beg;
+        // four gathers in flight; the adds stay in ascending k
+        for (; k + 4 <= end; k += 4) {
+            int p[4];
+            float w[4];
+            V x[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                p[j] = __ldg(idx + k + j);
+                w[j] = __ldg(val + k + j);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = __ldg(src + (size_t)p[j] * src_stride + q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) axpy(acc, w[j], x[j]);
+        }
+        for (; k < end; ++k) {
+            const int p = __ldg(idx + k);
+            const float w = __ldg(val + k);
+            const V x = __ldg(src + (size_t)p * src_stride + q);
+            axpy(acc, w, x);
+        }
+        if constexpr (kAdd) acc = vadd(base, acc);
+        if (s < n) __stcs(out + r * out_stride + q, acc);
+    }
+}
 
+// job of this CTA: static indices only, so the job's fields stay in (uniform) registers instead of a
+// local-memory copy of the parameter block
+__device__ __forceinline__ Job select_job(const PoolArgs& a, int cta, int& first) {
+    Job jb = a.job[0];
+    first = a.begin[0];
+#pragma unroll
+    for (int i = 1; i < kMaxJobs; ++i)
+        if (i < a.n_jobs && cta >= a.begin[i]) {
+            jb = a.job[i];
+            first = a.begin[i];
+        }
+    return jb;
+}
+
+// A CTA belongs to one job (begin[] partitions the grid); its warps stride over that job's tiles.
+template <int W, bool kAdd>
+__global__ void __launch_bounds__(kThreads, SHPL_NARROW_MIN_CTAS) shpl_pool_narrow_kernel(PoolArgs a) {
+    using V = typename VecOf<W>::type;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    int first;
+    const Job jb = select_job(a, blockIdx.x, first);
+    const int ctas = jb.entry_ctas;            // narrow: CTAs assigned to this job
+    const V* dense_in = static_cast<const V*>(jb.dense_in);
+    const V* gather_in = static_cast<const V*>(jb.gather_in);
+    V* dense_out = static_cast<V*>(jb.dense_out);
+    V* pool_out = static_cast<V*>(jb.pool_out);
+    for (int t = (blockIdx.x - first) * kWarps + warp; t < jb.tiles; t += ctas * kWarps) {
+        const int r0 = t * jb.rows_per_tile;
+        const int rows = min(jb.rows_per_tile, jb.n_cells - r0);
+        const V* din = dense_in + (size_t)r0 * jb.dense_in_stride;
+        if constexpr (!kAdd) {
+            if (jb.vd > 0)
+                copy_tile<V>(din, jb.dense_in_stride, dense_out + (size_t)r0 * jb.dense_out_stride,
+                             jb.dense_out_stride, jb.vd, jb.vd_shift, rows, lane);
+        }
+        if (jb.vs > 0)
+            pool_tile<V, kAdd>(gather_in, jb.gather_stride, jb.ptr + r0, jb.idx, jb.val,
+                               pool_out + (size_t)r0 * jb.pool_out_stride, jb.pool_out_stride, din,
+                               jb.dense_in_stride, jb.vs, jb.vs_shift, rows, lane);
+    }
+}
+
+// -------------------------------------------------------------------------------------- wide
+// Cell-serial gather (used when no key array is supplied): one cell by one warp.
 template <typename V, int ACC>
 __device__ __forceinline__ void pool_row_wide(const V* __restrict__ src, int src_stride, int beg, int end,
                                               const int* __restrict__ idx, const float* __restrict__ val,
-                                              V* __restrict__ orow, int nv, int lane) {
+                                              V* __restrict__ orow, const V* __restrict__ arow, int nv, int lane) {
     for (int q0 = 0; q0 < nv; q0 += 32 * ACC) {
         V acc[ACC];
 #pragma unroll
@@ -137,83 +298,26 @@ __device__ __forceinline__ void pool_row_wide(const V* __restrict__ src, int src
 #pragma unroll
         for (int a = 0; a < ACC; ++a) {
             const int q = q0 + a * 32 + lane;
-            if (q < nv) __stcs(orow + q, acc[a]);
-        }
-    }
-}
-
-// CTA-cooperative dense copy of `rows` cells (flat over rows*nv vectors, kUnroll loads in flight per lane)
-template <typename V>
-__device__ __forceinline__ void cta_copy_tile(const V* __restrict__ in, int in_stride, V* __restrict__ out,
-                                              int out_stride, int nv, int shift, int rows, int warp, int lane) {
-    const int n = rows * nv;
-    for (int s0 = warp * 32 * kUnroll; s0 < n; s0 += kWarps * 32 * kUnroll) {
-        V v[kUnroll];
-        int o[kUnroll];
-#pragma unroll
-        for (int j = 0; j < kUnroll; ++j) {
-            const int s = s0 + j * 32 + lane;
-            if (s < n) {
-                int r, q;
-                split(s, nv, shift, r, q);
-                v[j] = __ldcs(in + r * in_stride + q);
-                o[j] = r * out_stride + q;
+            if (q < nv) {
+                if (arow != nullptr) acc[a] = vadd(__ldcs(arow + q), acc[a]);
+                __stcs(orow + q, acc[a]);
             }
         }
-#pragma unroll
-        for (int j = 0; j < kUnroll; ++j) {
-            const int s = s0 + j * 32 + lane;
-            if (s < n) __stcs(out + o[j], v[j]);
-        }
     }
 }
 
-// CTA-cooperative sparse part of a tile of <= 32 wide cells
-template <typename V, int ACC>
-__device__ __forceinline__ void cta_pool_tile_wide(const V* __restrict__ src, int src_stride,
-                                                   const int* __restrict__ ptr, const int* __restrict__ idx,
-                                                   const float* __restrict__ val, V* __restrict__ out,
-                                                   int out_stride, int nv, int rows, int warp, int lane) {
-    int lo = 0, hi = 0;
-    if (lane < rows) {
-        lo = __ldg(ptr + lane);
-        hi = __ldg(ptr + lane + 1);
-    }
-    const unsigned busy = __ballot_sync(kFull, hi > lo);
-    // empty cells: zeros, one cell per warp at a time
-    const V z = vzero((V*)nullptr);
-    for (int r = warp; r < rows; r += kWarps) {
-        if ((busy >> r) & 1u) continue;
-        V* orow = out + r * out_stride;
-        for (int q = lane; q < nv; q += 32) __stcs(orow + q, z);
-    }
-    // busy cells: rank j among the busy ones goes to warp j % kWarps
-    unsigned m = busy;
-    int j = 0;
-    while (m) {
-        const int r = __ffs(m) - 1;
-        m &= m - 1;
-        if ((j++ % kWarps) != warp) continue;
-        const int beg = __shfl_sync(kFull, lo, r);
-        const int end = __shfl_sync(kFull, hi, r);
-        pool_row_wide<V, ACC>(src, src_stride, beg, end, idx, val, out + r * out_stride, nv, lane);
-    }
-}
-
-// Entry-parallel gather for wide cells: one warp takes 32 consecutive entries of the key-sorted
-// entry list and owns every cell whose FIRST entry lies in that chunk (a cell is never split, so
-// its sum keeps the ascending-k order; the warp reads on past the chunk until the cell ends, and
-// skips leading entries that continue a cell begun in the previous chunk).  Work per warp is
-// 32 entries +- one cell, whatever the row-length skew: the crowded near-range cells of a
-// stride-8 BEV map no longer serialise on one CTA.  Entries are streamed through a segmented sum:
-// kGatherUnroll x ACC gathers in flight, the accumulator is flushed when the key changes.
-constexpr int kEntryChunk = 32;
-
+// Entry-parallel gather: one warp takes `chunk` consecutive entries of the key-sorted entry list and
+// owns every cell whose FIRST entry lies in that chunk (a cell is never split, so its sum keeps the
+// ascending-k order; the warp reads on past the chunk until the cell ends, and skips leading entries
+// that continue a cell begun in an earlier chunk).  Work per warp is `chunk` entries +- one cell,
+// whatever the row-length skew.  Entries are streamed through a segmented sum: kGatherUnroll x ACC
+// gathers in flight, the accumulator is flushed when the key changes.
 template <typename V, int ACC>
 __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int src_stride,
                                                   const int* __restrict__ key, const int* __restrict__ idx,
                                                   const float* __restrict__ val, int e0, int e1, int e_begin,
-                                                  int e_end, V* __restrict__ out, int out_stride, int nv, int lane) {
+                                                  int e_end, V* __restrict__ out, int out_stride,
+                                                  const V* __restrict__ addend, int add_stride, int nv, int lane) {
     const int prev_row = (e0 > e_begin) ? __ldg(key + e0 - 1) : -1;
     for (int q0 = 0; q0 < nv; q0 += 32 * ACC) {
         int base = e0;
@@ -262,11 +366,15 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
 #pragma unroll
                             for (int a = 0; a < ACC; ++a) {
                                 const int q = q0 + a * 32 + lane;
-                                if (q < nv) __stcs(out + (size_t)cur_row * out_stride + q, acc[a]);
+                                if (q < nv) {
+                                    if (addend != nullptr)
+                                        acc[a] = vadd(__ldcs(addend + (size_t)cur_row * add_stride + q), acc[a]);
+                                    __stcs(out + (size_t)cur_row * out_stride + q, acc[a]);
+                                }
                                 acc[a] = vzero((V*)nullptr);
                             }
                         }
-                        if (base + pos + j >= e1) {   // the next cell belongs to the next warp
+                        if (base + pos + j >= e1) {   // the next cell belongs to a later warp
                             finished = true;
                             cur_row = -1;
                             continue;
@@ -297,221 +405,114 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
 #pragma unroll
             for (int a = 0; a < ACC; ++a) {
                 const int q = q0 + a * 32 + lane;
-                if (q < nv) __stcs(out + (size_t)cur_row * out_stride + q, acc[a]);
-            }
-        }
-    }
-}
-
-// Zeros for the cells of a tile that receive nothing (the busy ones are written by pool_entries_wide)
-template <typename V>
-__device__ __forceinline__ void cta_zero_empty_cells(const int* __restrict__ ptr, V* __restrict__ out, int out_stride,
-                                                     int nv, int rows, int warp, int lane) {
-    int lo = 0, hi = 0;
-    if (lane < rows) {
-        lo = __ldg(ptr + lane);
-        hi = __ldg(ptr + lane + 1);
-    }
-    const unsigned busy = __ballot_sync(kFull, hi > lo);
-    const V z = vzero((V*)nullptr);
-    for (int r = warp; r < rows; r += kWarps) {
-        if ((busy >> r) & 1u) continue;
-        V* orow = out + r * out_stride;
-        for (int q = lane; q < nv; q += 32) __stcs(orow + q, z);
-    }
-}
-
-// Sparse part: out[r*out_stride + q] = sum_k val[k] * src[idx[k]*src_stride + q], k in [ptr[r], ptr[r+1]).
-// `src` and `out` already carry their channel offset.
-template <typename V>
-__device__ __forceinline__ void pool_tile(const V* __restrict__ src, int src_stride,
-                                          const int* __restrict__ ptr, const int* __restrict__ idx,
-                                          const float* __restrict__ val, V* __restrict__ out, int out_stride,
-                                          int nv, int shift, int rows, int lane) {
-    int lo = 0, hi = 0;
-    if (lane < rows) {
-        lo = __ldg(ptr + lane);
-        hi = __ldg(ptr + lane + 1);
-    }
-    const unsigned busy = __ballot_sync(kFull, hi > lo);
-    const int n = rows * nv;
-    if (busy == 0u) {  // the common case: nothing projects into this tile
-        const V z = vzero((V*)nullptr);
-        for (int s0 = 0; s0 < n; s0 += 32 * kUnroll) {
-#pragma unroll
-            for (int j = 0; j < kUnroll; ++j) {
-                const int s = s0 + j * 32 + lane;
-                if (s < n) {
-                    int r, q;
-                    split(s, nv, shift, r, q);
-                    __stcs(out + r * out_stride + q, z);
+                if (q < nv) {
+                    if (addend != nullptr) acc[a] = vadd(__ldcs(addend + (size_t)cur_row * add_stride + q), acc[a]);
+                    __stcs(out + (size_t)cur_row * out_stride + q, acc[a]);
                 }
             }
         }
-        return;
     }
-    // narrow rows: nv lanes per cell, 32/nv cells side by side
-    for (int s0 = 0; s0 < n; s0 += 32) {  // warp-uniform trip count
-        const int s = s0 + lane;
-        int r, q;
-        split(s, nv, shift, r, q);
-        int beg = __shfl_sync(kFull, lo, r & 31);
-        int end = __shfl_sync(kFull, hi, r & 31);
-        if (s >= n) end = beg;
-        V acc = vzero((V*)nullptr);
-        int k = beg;
-        // four gathers in flight; the adds stay in ascending k
-        for (; k + 4 <= end; k += 4) {
-            int p[4];
-            float w[4];
-            V x[4];
+}
+
+// CTA-cooperative dense copy of `rows` cells (flat over rows*nv vectors, kUnroll loads in flight per
+// lane); cells whose bit is set in `skip` are left alone (the gather warps write them).
+template <typename V>
+__device__ __forceinline__ void cta_copy_tile(const V* __restrict__ in, int in_stride, V* __restrict__ out,
+                                              int out_stride, int nv, int shift, int rows, unsigned skip, int warp,
+                                              int lane) {
+    const int n = rows * nv;
+    for (int s0 = warp * 32 * kUnroll; s0 < n; s0 += kWarps * 32 * kUnroll) {
+        V v[kUnroll];
+        int o[kUnroll];
+        bool on[kUnroll];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                p[j] = __ldg(idx + k + j);
-                w[j] = __ldg(val + k + j);
+        for (int j = 0; j < kUnroll; ++j) {
+            const int s = s0 + j * 32 + lane;
+            on[j] = false;
+            if (s < n) {
+                int r, q;
+                split(s, nv, shift, r, q);
+                on[j] = !((skip >> r) & 1u);
+                if (on[j]) {
+                    v[j] = __ldcs(in + r * in_stride + q);
+                    o[j] = r * out_stride + q;
+                }
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = __ldg(src + (size_t)p[j] * src_stride + q);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) axpy(acc, w[j], x[j]);
         }
-        for (; k < end; ++k) {
-            const int p = __ldg(idx + k);
-            const float w = __ldg(val + k);
-            const V x = __ldg(src + (size_t)p * src_stride + q);
-            axpy(acc, w, x);
-        }
-        if (s < n) __stcs(out + r * out_stride + q, acc);
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j)
+            if (on[j]) __stcs(out + o[j], v[j]);
     }
 }
 
-struct PoolArgs {
-    const void* dense_in;   // forward: dst map            backward: g_fused
-    const void* gather_in;  // forward: src map            backward: g_fused
-    void* dense_out;        // forward: fused              backward: g_dst
-    void* pool_out;         // forward: fused              backward: g_src
-    const int* ptr;
-    const int* key;         // destination cell of each entry (NULL: walk cells instead of entries)
-    const int* idx;
-    const float* val;
-    int entry_ctas;         // leading CTAs that gather by entry (wide kernels, key != NULL)
-    int n_dense;            // cells of the dense part (0 = skip)
-    int n_pool;             // cells of the sparse part
-    int vd, vs;             // vectors per cell: own channels, pooled channels
-    int vd_shift, vs_shift; // log2 or -1
-    int rows_dense, rows_pool;  // cells per warp tile
-};
-
-// Forward, narrow cells: a WARP owns a tile of `rows` destination cells; dense part then sparse part.
-template <int W>
-__global__ void __launch_bounds__(kThreads) shpl_forward_kernel(PoolArgs a) {
-    using V = typename VecOf<W>::type;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int vf = a.vd + a.vs;
-    const int rows_per = a.rows_pool;
-    const int n_tiles = (a.n_pool + rows_per - 1) / rows_per;
-    const V* dst = static_cast<const V*>(a.dense_in);
-    const V* src = static_cast<const V*>(a.gather_in);
-    V* fused = static_cast<V*>(a.pool_out);
-    for (int t = blockIdx.x * kWarps + warp; t < n_tiles; t += gridDim.x * kWarps) {
-        const int r0 = t * rows_per;
-        const int rows = min(rows_per, a.n_pool - r0);
-        V* out = fused + (size_t)r0 * vf;
-        if (a.vd > 0) copy_tile<V>(dst + (size_t)r0 * a.vd, a.vd, out, vf, a.vd, a.vd_shift, rows, lane);
-        pool_tile<V>(src, a.vs, a.ptr + r0, a.idx, a.val, out + a.vd, vf, a.vs, a.vs_shift, rows, lane);
-    }
-}
-
-// Forward, wide cells: a CTA owns a tile of 32 destination cells (one tile per CTA: the hardware
-// block scheduler balances tiles of very different cost).
 template <int W, int ACC>
-__global__ void __launch_bounds__(kThreads, 2) shpl_forward_wide_kernel(PoolArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) shpl_pool_wide_kernel(PoolArgs a) {
     using V = typename VecOf<W>::type;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int vf = a.vd + a.vs;
-    const V* dst = static_cast<const V*>(a.dense_in);
-    const V* src = static_cast<const V*>(a.gather_in);
-    V* fused = static_cast<V*>(a.pool_out);
-    if ((int)blockIdx.x < a.entry_ctas) {       // gather CTAs come first: they are the long pole
-        const int e_begin = __ldg(a.ptr), e_end = __ldg(a.ptr + a.n_pool);
-        const int e0 = e_begin + (blockIdx.x * kWarps + warp) * kEntryChunk;
+    int first;
+    const Job jb = select_job(a, blockIdx.x, first);
+    const int b = blockIdx.x - first;
+    const V* din = static_cast<const V*>(jb.dense_in);
+    const V* src = static_cast<const V*>(jb.gather_in);
+    V* pout = static_cast<V*>(jb.pool_out);
+    if (b < jb.entry_ctas) {       // gather CTAs come first: they are the long pole
+        const int e_begin = __ldg(jb.ptr), e_end = __ldg(jb.ptr + jb.n_cells);
+        const int e0 = e_begin + (b * kWarps + warp) * jb.entry_chunk;
         if (e0 >= e_end) return;
-        pool_entries_wide<V, ACC>(src, a.vs, a.key, a.idx, a.val, e0, min(e0 + kEntryChunk, e_end), e_begin, e_end,
-                                  fused + a.vd, vf, a.vs, lane);
+        pool_entries_wide<V, ACC>(src, jb.gather_stride, jb.key, jb.idx, jb.val, e0, min(e0 + jb.entry_chunk, e_end),
+                                  e_begin, e_end, pout, jb.pool_out_stride, jb.add ? din : nullptr,
+                                  jb.dense_in_stride, jb.vs, lane);
         return;
     }
-    const int r0 = (blockIdx.x - a.entry_ctas) * kWideTile;
-    const int rows = min(kWideTile, a.n_pool - r0);
-    V* out = fused + (size_t)r0 * vf;
-    if (a.vd > 0) cta_copy_tile<V>(dst + (size_t)r0 * a.vd, a.vd, out, vf, a.vd, a.vd_shift, rows, warp, lane);
-    if (a.key != nullptr) cta_zero_empty_cells<V>(a.ptr + r0, out + a.vd, vf, a.vs, rows, warp, lane);
-    else cta_pool_tile_wide<V, ACC>(src, a.vs, a.ptr + r0, a.idx, a.val, out + a.vd, vf, a.vs, rows, warp, lane);
-}
-
-// Backward, narrow cells: warp tiles [0, tiles_dense) slice-copy g_fused[:, :C_d] -> g_dst; the rest
-// gather g_fused[:, C_d:] rows through the transposed CSR into the dense g_src (zeros included).
-template <int W>
-__global__ void __launch_bounds__(kThreads) shpl_backward_kernel(PoolArgs a) {
-    using V = typename VecOf<W>::type;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int vf = a.vd + a.vs;
-    const int tiles_dense = a.n_dense > 0 ? (a.n_dense + a.rows_dense - 1) / a.rows_dense : 0;
-    const int tiles_pool = (a.n_pool + a.rows_pool - 1) / a.rows_pool;
-    const V* g_fused = static_cast<const V*>(a.dense_in);
-    V* g_dst = static_cast<V*>(a.dense_out);
-    V* g_src = static_cast<V*>(a.pool_out);
-    for (int t = blockIdx.x * kWarps + warp; t < tiles_dense + tiles_pool; t += gridDim.x * kWarps) {
-        if (t < tiles_dense) {
-            const int r0 = t * a.rows_dense;
-            const int rows = min(a.rows_dense, a.n_dense - r0);
-            copy_tile<V>(g_fused + (size_t)r0 * vf, vf, g_dst + (size_t)r0 * a.vd, a.vd, a.vd, a.vd_shift, rows, lane);
-        } else {
-            const int p0 = (t - tiles_dense) * a.rows_pool;
-            const int rows = min(a.rows_pool, a.n_pool - p0);
-            pool_tile<V>(g_fused + a.vd, vf, a.ptr + p0, a.idx, a.val, g_src + (size_t)p0 * a.vs, a.vs, a.vs,
-                         a.vs_shift, rows, lane);
+    const int r0 = (b - jb.entry_ctas) * kWideTile;
+    const int rows = min(kWideTile, jb.n_cells - r0);
+    unsigned busy = 0u;
+    int lo = 0, hi = 0;
+    if (jb.vs > 0) {
+        if (lane < rows) {
+            lo = __ldg(jb.ptr + r0 + lane);
+            hi = __ldg(jb.ptr + r0 + lane + 1);
+        }
+        busy = __ballot_sync(kFull, hi > lo);
+    }
+    const bool by_entry = jb.key != nullptr;
+    if (jb.vd > 0) {
+        if (!jb.add)
+            cta_copy_tile<V>(din + (size_t)r0 * jb.dense_in_stride, jb.dense_in_stride,
+                             static_cast<V*>(jb.dense_out) + (size_t)r0 * jb.dense_out_stride, jb.dense_out_stride,
+                             jb.vd, jb.vd_shift, rows, 0u, warp, lane);
+        else   // add form: cells that receive nothing are a plain copy; the busy ones get dense + sum
+            cta_copy_tile<V>(din + (size_t)r0 * jb.dense_in_stride, jb.dense_in_stride,
+                             pout + (size_t)r0 * jb.pool_out_stride, jb.pool_out_stride, jb.vd, jb.vd_shift, rows,
+                             busy, warp, lane);
+    }
+    if (jb.vs == 0) return;
+    V* out = pout + (size_t)r0 * jb.pool_out_stride;
+    if (!jb.add) {                 // zeros for the cells that receive nothing
+        const V z = vzero((V*)nullptr);
+        for (int r = warp; r < rows; r += kWarps) {
+            if ((busy >> r) & 1u) continue;
+            V* orow = out + r * jb.pool_out_stride;
+            for (int q = lane; q < jb.vs; q += 32) __stcs(orow + q, z);
         }
     }
-}
-
-// Backward, wide cells: CTA tiles of 32 cells; the first `tiles_pool` CTAs gather (they are the
-// expensive ones and start first), the rest slice-copy.
-template <int W, int ACC>
-__global__ void __launch_bounds__(kThreads, 2) shpl_backward_wide_kernel(PoolArgs a) {
-    using V = typename VecOf<W>::type;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int vf = a.vd + a.vs;
-    const int tiles_pool = (a.n_pool + kWideTile - 1) / kWideTile;
-    const V* g_fused = static_cast<const V*>(a.dense_in);
-    V* g_dst = static_cast<V*>(a.dense_out);
-    V* g_src = static_cast<V*>(a.pool_out);
-    if ((int)blockIdx.x < a.entry_ctas) {
-        const int e_begin = __ldg(a.ptr), e_end = __ldg(a.ptr + a.n_pool);
-        const int e0 = e_begin + (blockIdx.x * kWarps + warp) * kEntryChunk;
-        if (e0 >= e_end) return;
-        pool_entries_wide<V, ACC>(g_fused + a.vd, vf, a.key, a.idx, a.val, e0, min(e0 + kEntryChunk, e_end), e_begin,
-                                  e_end, g_src, a.vs, a.vs, lane);
-        return;
-    }
-    const int t = blockIdx.x - a.entry_ctas;
-    if (t < tiles_pool) {
-        const int p0 = t * kWideTile;
-        const int rows = min(kWideTile, a.n_pool - p0);
-        if (a.key != nullptr) cta_zero_empty_cells<V>(a.ptr + p0, g_src + (size_t)p0 * a.vs, a.vs, a.vs, rows, warp, lane);
-        else cta_pool_tile_wide<V, ACC>(g_fused + a.vd, vf, a.ptr + p0, a.idx, a.val, g_src + (size_t)p0 * a.vs, a.vs,
-                                        a.vs, rows, warp, lane);
-    } else {
-        const int r0 = (t - tiles_pool) * kWideTile;
-        const int rows = min(kWideTile, a.n_dense - r0);
-        cta_copy_tile<V>(g_fused + (size_t)r0 * vf, vf, g_dst + (size_t)r0 * a.vd, a.vd, a.vd, a.vd_shift, rows, warp,
-                         lane);
+    if (by_entry) return;
+    // no key array: busy cells dealt round-robin (by rank) to the warps of this CTA
+    unsigned m = busy;
+    int rank = 0;
+    while (m) {
+        const int r = __ffs(m) - 1;
+        m &= m - 1;
+        if ((rank++ % kWarps) != warp) continue;
+        const int beg = __shfl_sync(kFull, lo, r);
+        const int end = __shfl_sync(kFull, hi, r);
+        pool_row_wide<V, ACC>(src, jb.gather_stride, beg, end, jb.idx, jb.val, out + r * jb.pool_out_stride,
+                              jb.add ? din + (size_t)(r0 + r) * jb.dense_in_stride : nullptr, jb.vs, lane);
     }
 }
 
+// --------------------------------------------------------------------------------------- host
 int log2_or_neg(int v) {
     if (v <= 0 || (v & (v - 1))) return -1;
     int s = 0;
@@ -519,26 +520,156 @@ int log2_or_neg(int v) {
     return s;
 }
 
-// cells per warp tile: about 1024 vectors of traffic per tile, at most 32 (one lane per cell)
-int tile_rows(int vectors_per_cell) {
-    const int budget = vectors_per_cell >= 64 ? 512 : 1024;   // wide cells are gathered a cell at a time: keep tiles short
+// cells per warp tile (narrow): about 1024 float4 of traffic per tile, at most 32 (one lane per cell)
+int tile_rows(int float4_per_cell) {
     int r = 32;
-    while (r > 1 && r * vectors_per_cell > budget) r >>= 1;
+    while (r > 1 && r * float4_per_cell > 1024) r >>= 1;
     return r;
 }
 
-int pick_width(int C_d, int C_s, std::initializer_list<const void*> ptrs) {
+int pick_width(std::initializer_list<int> channels, std::initializer_list<const void*> ptrs) {
     int w = 4;
-    while (w > 1 && ((C_d % w) || (C_s % w))) w >>= 1;
+    for (int c : channels)
+        while (w > 1 && (c % w)) w >>= 1;
     for (const void* p : ptrs)
         while (w > 1 && p && !shpl::aligned(p, sizeof(float) * w)) w >>= 1;
     return w;
 }
 
-int grid_for(long long tiles) {
-    const long long ctas = (tiles + kWarps - 1) / kWarps;
-    const long long cap = (long long)shpl::sm_count() * 8;  // 8 resident CTAs of 256 threads per SM
-    return (int)(ctas < 1 ? 1 : (ctas < cap ? ctas : cap));
+struct JobSpec {            // in floats / cells, before the vector width is chosen
+    const float* dense_in = nullptr;
+    int dense_in_stride = 0;
+    int c_dense = 0;
+    const float* gather_in = nullptr;
+    int gather_stride = 0;
+    int c_pool = 0;
+    float* dense_out = nullptr;
+    int dense_out_stride = 0;
+    float* pool_out = nullptr;
+    int pool_out_stride = 0;
+    const int* ptr = nullptr;
+    const int* key = nullptr;
+    const int* idx = nullptr;
+    const float* val = nullptr;
+    int nnz_max = 0;
+    int n_cells = 0;
+    int add = 0;
+};
+
+int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* who) {
+    int w = 4, max_vs = 0;
+    for (int i = 0; i < n_specs; ++i) {
+        const JobSpec& j = specs[i];
+        if (j.n_cells <= 0) continue;
+        const int wi = pick_width({j.c_dense, j.c_pool, j.dense_in_stride, j.dense_out_stride, j.gather_stride,
+                                   j.pool_out_stride},
+                                  {j.dense_in, j.gather_in, j.dense_out, j.pool_out});
+        w = wi < w ? wi : w;
+    }
+    PoolArgs a{};
+    const JobSpec* src_spec[kMaxJobs];
+    a.n_jobs = 0;
+    for (int i = 0; i < n_specs && a.n_jobs < kMaxJobs; ++i) {
+        const JobSpec& j = specs[i];
+        if (j.n_cells <= 0) continue;
+        src_spec[a.n_jobs] = &j;
+        Job& o = a.job[a.n_jobs++];
+        o.dense_in = j.dense_in;
+        o.gather_in = j.gather_in;
+        o.dense_out = j.dense_out;
+        o.pool_out = j.pool_out;
+        o.ptr = j.ptr;
+        o.key = (j.key && j.nnz_max > 0) ? j.key : nullptr;
+        o.idx = j.idx;
+        o.val = j.val;
+        o.dense_in_stride = j.dense_in_stride / w;
+        o.dense_out_stride = j.dense_out_stride / w;
+        o.gather_stride = j.gather_stride / w;
+        o.pool_out_stride = j.pool_out_stride / w;
+        o.vd = j.c_dense / w;
+        o.vs = j.c_pool / w;
+        o.vd_shift = log2_or_neg(o.vd);
+        o.vs_shift = log2_or_neg(o.vs);
+        o.n_cells = j.n_cells;
+        o.add = j.add;
+        max_vs = o.vs > max_vs ? o.vs : max_vs;
+    }
+    if (a.n_jobs == 0) return SHPL_OK;
+    const bool wide = max_vs >= 32;
+    a.begin[0] = 0;
+    for (int i = 0; i < a.n_jobs; ++i) {
+        Job& o = a.job[i];
+        const int nnz_max = src_spec[i]->nnz_max;
+        if (wide) {
+            o.entry_chunk = nnz_max > (1 << 18) ? 32 : 8;   // small problems are latency-bound: more, shorter chains
+            o.entry_ctas = (o.key && o.vs > 0) ? (nnz_max + o.entry_chunk * kWarps - 1) / (o.entry_chunk * kWarps) : 0;
+            o.tiles = (o.n_cells + kWideTile - 1) / kWideTile;
+            a.begin[i + 1] = a.begin[i] + o.entry_ctas + o.tiles;
+        } else {
+            const int f4 = ((o.add ? o.vs : o.vd + o.vs) * w + 3) / 4;
+            o.rows_per_tile = tile_rows(f4 > 0 ? f4 : 1);
+            o.tiles = (o.n_cells + o.rows_per_tile - 1) / o.rows_per_tile;
+            a.begin[i + 1] = a.begin[i] + o.tiles;
+        }
+    }
+    if (wide) {
+        const unsigned g = (unsigned)a.begin[a.n_jobs];
+        const bool one = max_vs <= 32;
+        if (w == 4 && one) shpl_pool_wide_kernel<4, 1><<<g, kThreads, 0, s>>>(a);
+        else if (w == 4) shpl_pool_wide_kernel<4, 2><<<g, kThreads, 0, s>>>(a);
+        else if (w == 2 && one) shpl_pool_wide_kernel<2, 1><<<g, kThreads, 0, s>>>(a);
+        else if (w == 2) shpl_pool_wide_kernel<2, 2><<<g, kThreads, 0, s>>>(a);
+        else if (one) shpl_pool_wide_kernel<1, 1><<<g, kThreads, 0, s>>>(a);
+        else shpl_pool_wide_kernel<1, 2><<<g, kThreads, 0, s>>>(a);
+    } else {
+        // partition the resident grid between the jobs in proportion to their tiles (a CTA serves one job)
+        long long total_tiles = 0;
+        for (int i = 0; i < a.n_jobs; ++i) total_tiles += a.job[i].tiles;
+        const long long cap = (long long)shpl::sm_count() * 8;   // resident CTAs of 256 threads per SM
+        long long want = (total_tiles + kWarps - 1) / kWarps;
+        if (want > cap) want = cap;
+        a.begin[0] = 0;
+        for (int i = 0; i < a.n_jobs; ++i) {
+            long long c = (want * a.job[i].tiles + total_tiles - 1) / (total_tiles > 0 ? total_tiles : 1);
+            const long long need = ((long long)a.job[i].tiles + kWarps - 1) / kWarps;
+            if (c > need) c = need;
+            if (c < 1) c = 1;
+            a.job[i].entry_ctas = (int)c;          // narrow kernels: number of CTAs serving this job
+            a.begin[i + 1] = a.begin[i] + (int)c;
+        }
+        const unsigned g = (unsigned)a.begin[a.n_jobs];
+        const bool add = a.job[0].add != 0;      // the jobs of one launch share the form
+        if (w == 4 && add) shpl_pool_narrow_kernel<4, true><<<g, kThreads, 0, s>>>(a);
+        else if (w == 4) shpl_pool_narrow_kernel<4, false><<<g, kThreads, 0, s>>>(a);
+        else if (w == 2 && add) shpl_pool_narrow_kernel<2, true><<<g, kThreads, 0, s>>>(a);
+        else if (w == 2) shpl_pool_narrow_kernel<2, false><<<g, kThreads, 0, s>>>(a);
+        else if (add) shpl_pool_narrow_kernel<1, true><<<g, kThreads, 0, s>>>(a);
+        else shpl_pool_narrow_kernel<1, false><<<g, kThreads, 0, s>>>(a);
+    }
+    shpl::count_launches(1);
+    return shpl::check_launch(who);
+}
+
+JobSpec forward_job(const float* dst, const float* src, const int32_t* ptr, const int32_t* key, const int32_t* idx,
+                    const float* val, int nnz_max, int n_rows, int C_d, int C_s, float* fused) {
+    JobSpec j;
+    j.dense_in = dst;
+    j.dense_in_stride = C_d;
+    j.c_dense = C_d;
+    j.gather_in = src;
+    j.gather_stride = C_s;
+    j.c_pool = C_s;
+    j.dense_out = fused;
+    j.dense_out_stride = C_d + C_s;
+    j.pool_out = fused + C_d;
+    j.pool_out_stride = C_d + C_s;
+    j.ptr = ptr;
+    j.key = key;
+    j.idx = idx;
+    j.val = val;
+    j.nnz_max = nnz_max;
+    j.n_cells = n_rows;
+    return j;
 }
 
 }  // namespace
@@ -551,41 +682,8 @@ extern "C" int shpl_pool_forward(const float* dst, const float* src, const int32
     SHPL_REQUIRE(src && ptr && fused && (C_d == 0 || dst), SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_forward: null pointer");
     SHPL_REQUIRE(idx && val, SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_forward: null idx/val");
     if (n_rows == 0) return SHPL_OK;
-    const int w = pick_width(C_d, C_s, {dst, src, fused});
-    PoolArgs a{};
-    a.dense_in = dst;
-    a.gather_in = src;
-    a.dense_out = fused;
-    a.pool_out = fused;
-    a.ptr = ptr;
-    a.key = (key && nnz_max > 0) ? key : nullptr;
-    a.idx = idx;
-    a.val = val;
-    a.entry_ctas = a.key ? (nnz_max + kEntryChunk * kWarps - 1) / (kEntryChunk * kWarps) : 0;
-    a.n_dense = n_rows;
-    a.n_pool = n_rows;
-    a.vd = C_d / w;
-    a.vs = C_s / w;
-    a.vd_shift = log2_or_neg(a.vd);
-    a.vs_shift = log2_or_neg(a.vs);
-    a.rows_pool = a.rows_dense = tile_rows((a.vd + a.vs) * w / 4 > 0 ? (a.vd + a.vs) * w / 4 : 1);
-    const long long tiles = ((long long)n_rows + a.rows_pool - 1) / a.rows_pool;
-    const int grid = grid_for(tiles);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (a.vs >= 32) {   // wide cells: one CTA per tile of 32 cells
-        const unsigned g = (unsigned)(a.entry_ctas + (n_rows + kWideTile - 1) / kWideTile);
-        const bool one = a.vs <= 32;
-        if (w == 4 && one) shpl_forward_wide_kernel<4, 1><<<g, kThreads, 0, s>>>(a);
-        else if (w == 4) shpl_forward_wide_kernel<4, 2><<<g, kThreads, 0, s>>>(a);
-        else if (w == 2 && one) shpl_forward_wide_kernel<2, 1><<<g, kThreads, 0, s>>>(a);
-        else if (w == 2) shpl_forward_wide_kernel<2, 2><<<g, kThreads, 0, s>>>(a);
-        else if (one) shpl_forward_wide_kernel<1, 1><<<g, kThreads, 0, s>>>(a);
-        else shpl_forward_wide_kernel<1, 2><<<g, kThreads, 0, s>>>(a);
-    } else if (w == 4) shpl_forward_kernel<4><<<grid, kThreads, 0, s>>>(a);
-    else if (w == 2) shpl_forward_kernel<2><<<grid, kThreads, 0, s>>>(a);
-    else shpl_forward_kernel<1><<<grid, kThreads, 0, s>>>(a);
-    shpl::count_launches(1);
-    return shpl::check_launch("shpl_forward_kernel");
+    const JobSpec j = forward_job(dst, src, ptr, key, idx, val, nnz_max, n_rows, C_d, C_s, fused);
+    return launch_jobs(&j, 1, static_cast<cudaStream_t>(stream), "shpl_pool_forward");
 }
 
 extern "C" int shpl_pool_backward(const float* g_fused, const int32_t* ptrT, const int32_t* keyT, const int32_t* idxT,
@@ -594,44 +692,88 @@ extern "C" int shpl_pool_backward(const float* g_fused, const int32_t* ptrT, con
     SHPL_REQUIRE(n_rows >= 0 && n_src >= 0 && C_d >= 0 && C_s > 0, SHPL_ERR_INVALID_ARGUMENT,
                  "shpl_pool_backward: bad sizes n_rows=%d n_src=%d C_d=%d C_s=%d", n_rows, n_src, C_d, C_s);
     SHPL_REQUIRE(g_fused && ptrT && idxT && valT && g_src, SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_backward: null pointer");
-    if (n_rows == 0 && n_src == 0) return SHPL_OK;
-    const bool dense = g_dst != nullptr && C_d > 0 && n_rows > 0;
-    const int w = pick_width(C_d, C_s, {g_fused, g_dst, g_src});
-    PoolArgs a{};
-    a.dense_in = g_fused;
-    a.gather_in = g_fused;
-    a.dense_out = g_dst;
-    a.pool_out = g_src;
-    a.ptr = ptrT;
-    a.key = (keyT && nnz_max > 0) ? keyT : nullptr;
-    a.idx = idxT;
-    a.val = valT;
-    a.entry_ctas = a.key ? (nnz_max + kEntryChunk * kWarps - 1) / (kEntryChunk * kWarps) : 0;
-    a.n_dense = dense ? n_rows : 0;
-    a.n_pool = n_src;
-    a.vd = C_d / w;
-    a.vs = C_s / w;
-    a.vd_shift = log2_or_neg(a.vd);
-    a.vs_shift = log2_or_neg(a.vs);
-    a.rows_dense = tile_rows(a.vd * w / 4 > 0 ? a.vd * w / 4 * 2 : 1);
-    a.rows_pool = tile_rows(a.vs * w / 4 > 0 ? a.vs * w / 4 : 1);
-    const long long tiles = (dense ? ((long long)n_rows + a.rows_dense - 1) / a.rows_dense : 0) +
-                            ((long long)n_src + a.rows_pool - 1) / a.rows_pool;
-    if (tiles == 0) return SHPL_OK;
-    const int grid = grid_for(tiles);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (a.vs >= 32) {
-        const unsigned g = (unsigned)(a.entry_ctas + (n_src + kWideTile - 1) / kWideTile + (a.n_dense + kWideTile - 1) / kWideTile);
-        const bool one = a.vs <= 32;
-        if (w == 4 && one) shpl_backward_wide_kernel<4, 1><<<g, kThreads, 0, s>>>(a);
-        else if (w == 4) shpl_backward_wide_kernel<4, 2><<<g, kThreads, 0, s>>>(a);
-        else if (w == 2 && one) shpl_backward_wide_kernel<2, 1><<<g, kThreads, 0, s>>>(a);
-        else if (w == 2) shpl_backward_wide_kernel<2, 2><<<g, kThreads, 0, s>>>(a);
-        else if (one) shpl_backward_wide_kernel<1, 1><<<g, kThreads, 0, s>>>(a);
-        else shpl_backward_wide_kernel<1, 2><<<g, kThreads, 0, s>>>(a);
-    } else if (w == 4) shpl_backward_kernel<4><<<grid, kThreads, 0, s>>>(a);
-    else if (w == 2) shpl_backward_kernel<2><<<grid, kThreads, 0, s>>>(a);
-    else shpl_backward_kernel<1><<<grid, kThreads, 0, s>>>(a);
-    shpl::count_launches(1);
-    return shpl::check_launch("shpl_backward_kernel");
+    JobSpec js[2];
+    // job 0: g_src[p] = sum over the entries of source p of valT * g_fused[idxT, C_d:]
+    js[0].gather_in = g_fused + C_d;
+    js[0].gather_stride = C_d + C_s;
+    js[0].c_pool = C_s;
+    js[0].pool_out = g_src;
+    js[0].pool_out_stride = C_s;
+    js[0].ptr = ptrT;
+    js[0].key = keyT;
+    js[0].idx = idxT;
+    js[0].val = valT;
+    js[0].nnz_max = nnz_max;
+    js[0].n_cells = n_src;
+    // job 1: g_dst = g_fused[:, :C_d]
+    if (g_dst != nullptr && C_d > 0) {
+        js[1].dense_in = g_fused;
+        js[1].dense_in_stride = C_d + C_s;
+        js[1].c_dense = C_d;
+        js[1].dense_out = g_dst;
+        js[1].dense_out_stride = C_d;
+        js[1].n_cells = n_rows;
+    }
+    return launch_jobs(js, 2, static_cast<cudaStream_t>(stream), "shpl_pool_backward");
+}
+
+extern "C" int shpl_pool_forward_dual(const float* bev, const float* img, const int32_t* row_ptr,
+                                      const int32_t* csr_row, const int32_t* csr_src, const float* csr_val,
+                                      const int32_t* pix_ptr, const int32_t* csrT_pix, const int32_t* csrT_dst,
+                                      const float* csrT_val, int32_t nnz_max, int32_t n_rows, int32_t C_b,
+                                      int32_t n_src, int32_t C_i, float* fused_bev, float* fused_img, void* stream) {
+    SHPL_REQUIRE(n_rows >= 0 && n_src >= 0 && C_b > 0 && C_i > 0, SHPL_ERR_INVALID_ARGUMENT,
+                 "shpl_pool_forward_dual: bad sizes n_rows=%d n_src=%d C_b=%d C_i=%d", n_rows, n_src, C_b, C_i);
+    SHPL_REQUIRE(bev && img && row_ptr && csr_src && csr_val && pix_ptr && csrT_dst && csrT_val && fused_bev && fused_img,
+                 SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_forward_dual: null pointer");
+    JobSpec js[2];
+    js[0] = forward_job(bev, img, row_ptr, csr_row, csr_src, csr_val, nnz_max, n_rows, C_b, C_i, fused_bev);
+    js[1] = forward_job(img, bev, pix_ptr, csrT_pix, csrT_dst, csrT_val, nnz_max, n_src, C_i, C_b, fused_img);
+    return launch_jobs(js, 2, static_cast<cudaStream_t>(stream), "shpl_pool_forward_dual");
+}
+
+extern "C" int shpl_pool_backward_dual(const float* g_fused_bev, const float* g_fused_img, const int32_t* row_ptr,
+                                       const int32_t* csr_row, const int32_t* csr_src, const float* csr_val,
+                                       const int32_t* pix_ptr, const int32_t* csrT_pix, const int32_t* csrT_dst,
+                                       const float* csrT_val, int32_t nnz_max, int32_t n_rows, int32_t C_b,
+                                       int32_t n_src, int32_t C_i, float* g_bev, float* g_img, void* stream) {
+    SHPL_REQUIRE(n_rows >= 0 && n_src >= 0 && C_b > 0 && C_i > 0, SHPL_ERR_INVALID_ARGUMENT,
+                 "shpl_pool_backward_dual: bad sizes n_rows=%d n_src=%d C_b=%d C_i=%d", n_rows, n_src, C_b, C_i);
+    SHPL_REQUIRE(g_fused_bev && g_fused_img && row_ptr && csr_src && csr_val && pix_ptr && csrT_dst && csrT_val &&
+                     g_bev && g_img, SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_backward_dual: null pointer");
+    const int Fb = C_b + C_i, Fi = C_i + C_b;
+    JobSpec js[2];
+    // g_bev[r] = g_fused_bev[r, :C_b] + sum_{k in row r} val * g_fused_img[pix_k, C_i:]
+    js[0].dense_in = g_fused_bev;
+    js[0].dense_in_stride = Fb;
+    js[0].c_dense = C_b;
+    js[0].gather_in = g_fused_img + C_i;
+    js[0].gather_stride = Fi;
+    js[0].c_pool = C_b;
+    js[0].pool_out = g_bev;
+    js[0].pool_out_stride = C_b;
+    js[0].ptr = row_ptr;
+    js[0].key = csr_row;
+    js[0].idx = csr_src;
+    js[0].val = csr_val;
+    js[0].nnz_max = nnz_max;
+    js[0].n_cells = n_rows;
+    js[0].add = 1;
+    // g_img[p] = g_fused_img[p, :C_i] + sum_{k at pixel p} val * g_fused_bev[row_k, C_b:]
+    js[1].dense_in = g_fused_img;
+    js[1].dense_in_stride = Fi;
+    js[1].c_dense = C_i;
+    js[1].gather_in = g_fused_bev + C_b;
+    js[1].gather_stride = Fb;
+    js[1].c_pool = C_i;
+    js[1].pool_out = g_img;
+    js[1].pool_out_stride = C_i;
+    js[1].ptr = pix_ptr;
+    js[1].key = csrT_pix;
+    js[1].idx = csrT_dst;
+    js[1].val = csrT_val;
+    js[1].nnz_max = nnz_max;
+    js[1].n_cells = n_src;
+    js[1].add = 1;
+    return launch_jobs(js, 2, static_cast<cudaStream_t>(stream), "shpl_pool_backward_dual");
 }

@@ -69,6 +69,7 @@ class SparsePoolPlan:
         self.csr_val = torch.empty(self.capacity, dtype=torch.float32, device=device)
         self.csrT_val = torch.empty(self.capacity, dtype=torch.float32, device=device)
         self.counts = torch.zeros((self.frames, 8), dtype=torch.int32, device=device)
+        self.entry_bound = self.capacity   # host-known upper bound on the entries (builders tighten it)
         self.nnz = None       # columns of M per frame (host ints), known after the builder's read-back
         self.n_oob = None     # entries TF-CPU would reject, per frame
 
@@ -82,11 +83,11 @@ class SparsePoolPlan:
 
     def by_row(self):
         """(ptr, key, idx, val, nnz_max) of the CSR keyed by destination BEV cell."""
-        return (self.row_ptr, self.csr_row, self.csr_src, self.csr_val, self.capacity)
+        return (self.row_ptr, self.csr_row, self.csr_src, self.csr_val, self.entry_bound)
 
     def by_pixel(self):
         """(ptr, key, idx, val, nnz_max) of the CSR^T keyed by source pixel."""
-        return (self.pix_ptr, self.csrT_pix, self.csrT_dst, self.csrT_val, self.capacity)
+        return (self.pix_ptr, self.csrT_pix, self.csrT_dst, self.csrT_val, self.entry_bound)
 
     def frame_struct(self, f):
         """shpl_plan for frame f: ptr arrays point at the frame's sub-array; entry arrays are shared."""
@@ -219,6 +220,58 @@ class SparsePoolFunction(torch.autograd.Function):
         if g_dst is not None:
             g_dst = g_dst.reshape(ctx.dst_shape)
         return g_dst, g_src.reshape(ctx.src_shape), None, None
+
+
+def _plan_ptrs(plan):
+    return [_ptr(t) for t in (plan.row_ptr, plan.csr_row, plan.csr_src, plan.csr_val,
+                              plan.pix_ptr, plan.csrT_pix, plan.csrT_dst, plan.csrT_val)]
+
+
+class SparsePoolDualFunction(torch.autograd.Function):
+    """Both directions of sparse_pool_layer (bv_index is not None, sparse_pool_utils.py:65-87) in one
+    launch each way: shpl_pool_forward_dual / shpl_pool_backward_dual.  The backward forms TF's AddN
+    of the two partial gradients of each input in registers (no intermediate tensors)."""
+
+    @staticmethod
+    def forward(ctx, bev, img, plan):
+        require_cuda(bev, "inputs[0]")
+        require_cuda(img, "inputs[1]")
+        if bev.dtype != torch.float32 or img.dtype != torch.float32:
+            raise ValueError("SHPL feature maps must be float32 (the reference's dtype)")
+        if bev.shape[0] != plan.frames or img.shape[0] != plan.frames:
+            raise ValueError("feature batch does not match the frames in the plan")
+        b, i = bev.contiguous(), img.contiguous()
+        R, Q, Cb, Ci = plan.n_rows, plan.n_src, bev.shape[-1], img.shape[-1]
+        if b.numel() != R * Cb or i.numel() != Q * Ci:
+            raise ValueError("feature maps %s / %s do not match the plan (%d cells, %d pixels)"
+                             % (tuple(bev.shape), tuple(img.shape), R, Q))
+        fused_bev = torch.empty(tuple(bev.shape[:3]) + (Cb + Ci,), dtype=torch.float32, device=bev.device)
+        fused_img = torch.empty(tuple(img.shape[:3]) + (Ci + Cb,), dtype=torch.float32, device=bev.device)
+        rc = _lib.shpl_pool_forward_dual(_ptr(b), _ptr(i), *_plan_ptrs(plan), int(plan.entry_bound), R, Cb, Q, Ci,
+                                         _ptr(fused_bev), _ptr(fused_img), _stream())
+        _cabi.check(rc, "shpl_pool_forward_dual")
+        ctx.plan = plan
+        ctx.shapes = (tuple(bev.shape), tuple(img.shape))
+        return fused_bev, fused_img
+
+    @staticmethod
+    def backward(ctx, g_fused_bev, g_fused_img):
+        plan = ctx.plan
+        (sb, si) = ctx.shapes
+        R, Q, Cb, Ci = plan.n_rows, plan.n_src, sb[-1], si[-1]
+        gb = g_fused_bev.contiguous()
+        gi = g_fused_img.contiguous()
+        g_bev = torch.empty(sb, dtype=torch.float32, device=gb.device)
+        g_img = torch.empty(si, dtype=torch.float32, device=gb.device)
+        rc = _lib.shpl_pool_backward_dual(_ptr(gb), _ptr(gi), *_plan_ptrs(plan), int(plan.entry_bound), R, Cb, Q, Ci,
+                                          _ptr(g_bev), _ptr(g_img), _stream())
+        _cabi.check(rc, "shpl_pool_backward_dual")
+        return g_bev, g_img, None
+
+
+def sparse_pool_dual(bev, img, plan):
+    """(bv_fused, img_fused) of the dual-direction layer."""
+    return SparsePoolDualFunction.apply(bev, img, plan)
 
 
 def sparse_pool(dst, src, plan, transposed=False):

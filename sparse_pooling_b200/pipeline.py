@@ -75,8 +75,9 @@ class _LayerState:
         self.g_img = torch.empty((1,) + spec.img_hw + (spec.c_img,), **f32)
         if spec.dual:
             self.fused_img = torch.empty((1,) + spec.img_hw + (spec.c_img + spec.c_bev,), **f32)
-            self.g_bev_pool = torch.empty((1,) + spec.bev_hw + (spec.c_bev,), **f32)
-            self.g_img_slice = torch.empty((1,) + spec.img_hw + (spec.c_img,), **f32)
+        pl = self.plan
+        self.plan_ptrs = [_p(t) for t in (pl.row_ptr, pl.csr_row, pl.csr_src, pl.csr_val,
+                                          pl.pix_ptr, pl.csrT_pix, pl.csrT_dst, pl.csrT_val)]
 
 
 class FramePipeline:
@@ -106,29 +107,30 @@ class FramePipeline:
                                   ctypes.byref(L.plan_struct), 0, 0, None, _p(L.ws), L.ws.numel(), stream)
         _cabi.check(rc, "shpl_build_avod")
 
-    # -- forward of layer i: img -> bev (and bev -> img when dual), concat fused in --
-    def forward_layer(self, i, bev, img, stream):
+    # -- forward of layer i: img -> bev (and bev -> img when dual, same launch), concat fused in --
+    def forward_layer(self, i, bev, img, stream, nnz_max=None):
         L = self.layers[i]
         s, pl = L.spec, L.plan
-        rc = _lib.shpl_pool_forward(_p(bev), _p(img), _p(pl.row_ptr), _p(pl.csr_row), _p(pl.csr_src), _p(pl.csr_val),
-                                    pl.capacity, s.R, s.c_bev, s.Q, s.c_img, _p(L.fused_bev), stream)
-        _cabi.check(rc, "shpl_pool_forward")
+        bound = int(nnz_max) if nnz_max else pl.capacity
         if s.dual:
-            rc = _lib.shpl_pool_forward(_p(img), _p(bev), _p(pl.pix_ptr), _p(pl.csrT_pix), _p(pl.csrT_dst),
-                                        _p(pl.csrT_val), pl.capacity, s.Q, s.c_img, s.R, s.c_bev, _p(L.fused_img), stream)
-            _cabi.check(rc, "shpl_pool_forward")
+            rc = _lib.shpl_pool_forward_dual(_p(bev), _p(img), *L.plan_ptrs, bound, s.R, s.c_bev, s.Q, s.c_img,
+                                             _p(L.fused_bev), _p(L.fused_img), stream)
+            _cabi.check(rc, "shpl_pool_forward_dual")
+            return
+        rc = _lib.shpl_pool_forward(_p(bev), _p(img), _p(pl.row_ptr), _p(pl.csr_row), _p(pl.csr_src), _p(pl.csr_val),
+                                    bound, s.R, s.c_bev, s.Q, s.c_img, _p(L.fused_bev), stream)
+        _cabi.check(rc, "shpl_pool_forward")
 
     # -- backward of layer i from the upstream gradients of the fused maps --
-    def backward_layer(self, i, g_fused_bev, g_fused_img, stream):
+    def backward_layer(self, i, g_fused_bev, g_fused_img, stream, nnz_max=None):
         L = self.layers[i]
         s, pl = L.spec, L.plan
+        bound = int(nnz_max) if nnz_max else pl.capacity
+        if s.dual:   # AddN of the two partial gradients of each input formed in the kernel
+            rc = _lib.shpl_pool_backward_dual(_p(g_fused_bev), _p(g_fused_img), *L.plan_ptrs, bound, s.R, s.c_bev,
+                                              s.Q, s.c_img, _p(L.g_bev), _p(L.g_img), stream)
+            _cabi.check(rc, "shpl_pool_backward_dual")
+            return
         rc = _lib.shpl_pool_backward(_p(g_fused_bev), _p(pl.pix_ptr), _p(pl.csrT_pix), _p(pl.csrT_dst), _p(pl.csrT_val),
-                                     pl.capacity, s.R, s.c_bev, s.Q, s.c_img, _p(L.g_bev), _p(L.g_img), stream)
+                                     bound, s.R, s.c_bev, s.Q, s.c_img, _p(L.g_bev), _p(L.g_img), stream)
         _cabi.check(rc, "shpl_pool_backward")
-        if s.dual:
-            rc = _lib.shpl_pool_backward(_p(g_fused_img), _p(pl.row_ptr), _p(pl.csr_row), _p(pl.csr_src), _p(pl.csr_val),
-                                         pl.capacity, s.Q, s.c_img, s.R, s.c_bev, _p(L.g_img_slice), _p(L.g_bev_pool), stream)
-            _cabi.check(rc, "shpl_pool_backward")
-            # TF's AddN of the two partial gradients of each input
-            L.g_bev.add_(L.g_bev_pool)
-            L.g_img.add_(L.g_img_slice)

@@ -271,6 +271,12 @@ def sparse_pool_layer(inputs, feature_depths, M, img_index_flip=None, bv_index=N
         plan = _resolve_plan(M, img_index_flip, input_bv.shape[1] * input_bv.shape[2],
                              (input_img.shape[1], input_img.shape[2]), input_bv.device)
         _check_oob(plan)
+    if img_index_flip is not None and bv_index is not None and not use_bn:
+        if int(feature_depths[0]) != input_img.shape[3] or int(feature_depths[1]) != input_bv.shape[3]:
+            raise ValueError("feature_depths %r do not match the maps (%d image, %d BEV channels)"
+                             % (list(feature_depths), input_img.shape[3], input_bv.shape[3]))
+        print('using dual sparse pooling')       # the reference prints this (:80)
+        return ops.sparse_pool_dual(input_bv, input_img, plan)
     if img_index_flip is not None:
         if int(feature_depths[0]) != input_img.shape[3]:
             raise ValueError("feature_depths[0]=%d but the image map has %d channels" % (feature_depths[0], input_img.shape[3]))

@@ -22,6 +22,8 @@ def specs_for(name):
     if name == "bench":
         return [LayerSpec("A_s8_dual_c256", (88, 100), (45, 150), 256, 256, (8, 8), True, (1200, 360), (704, 800)),
                 LayerSpec("B_s1_c32", (700, 800), (360, 1200), 32, 32, (1, 1), False, (1200, 360), (700, 800))]
+    if name == "b":
+        return [LayerSpec("B_s1_c32", (700, 800), (360, 1200), 32, 32, (1, 1), False, (1200, 360), (700, 800))]
     if name == "retina":
         return [LayerSpec("P2_s4_c256", (175, 200), (90, 300), 256, 256, (4, 4), False, (1200, 360), (700, 800))]
     if name == "c128":
@@ -93,11 +95,11 @@ def main():
         nnz = int(pipe.layers[i].plan.counts[0, 3].item())
         out["pieces"][s.name + ".nnz"] = nnz
         for label, fl in (("warmL2", None), ("coldL2", flush)):
-            r = timeit(lambda: pipe.forward_layer(i, bev, img, st()), args.iters, fl)
+            r = timeit(lambda: pipe.forward_layer(i, bev, img, st(), n), args.iters, fl)
             r["GBs"] = s.bytes_forward(nnz) / r["us_median"] / 1e3
             r["frac_of_peak"] = r["GBs"] / peak
             out["pieces"][s.name + ".forward." + label] = r
-            r = timeit(lambda: pipe.backward_layer(i, g_bev, g_img, st()), args.iters, fl)
+            r = timeit(lambda: pipe.backward_layer(i, g_bev, g_img, st(), n), args.iters, fl)
             r["GBs"] = s.bytes_backward(nnz) / r["us_median"] / 1e3
             r["frac_of_peak"] = r["GBs"] / peak
             out["pieces"][s.name + ".backward." + label] = r
