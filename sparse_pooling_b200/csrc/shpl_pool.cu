@@ -35,9 +35,31 @@ namespace {
 #ifndef SHPL_UNROLL
 #define SHPL_UNROLL 8
 #endif
+#ifndef SHPL_LD_POLICY
+#define SHPL_LD_POLICY 1      // 0 = default, 1 = ld.global.cs (streaming)
+#endif
+#ifndef SHPL_ST_POLICY
+#define SHPL_ST_POLICY 1      // 0 = default, 1 = st.global.cs (streaming)
+#endif
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kUnroll = SHPL_UNROLL;
+
+// dense-stream accessors (the policy is a build-time experiment knob)
+template <typename V> __device__ __forceinline__ V ld_stream(const V* p) {
+#if SHPL_LD_POLICY == 1
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+template <typename V> __device__ __forceinline__ void st_stream(V* p, const V& v) {
+#if SHPL_ST_POLICY == 1
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxJobs = 4;
 constexpr int kGatherUnroll = 8;
@@ -125,14 +147,14 @@ __device__ __forceinline__ void copy_tile(const V* __restrict__ in, int in_strid
             if (s < n) {
                 int r, q;
                 split(s, nv, shift, r, q);
-                v[j] = __ldcs(in + r * in_stride + q);
+                v[j] = ld_stream(in + r * in_stride + q);
                 o[j] = r * out_stride + q;
             }
         }
 #pragma unroll
         for (int j = 0; j < kUnroll; ++j) {
             const int s = s0 + j * 32 + lane;
-            if (s < n) __stcs(out + o[j], v[j]);
+            if (s < n) st_stream(out + o[j], v[j]);
         }
     }
 }
@@ -165,7 +187,7 @@ __device__ __forceinline__ void pool_tile(const V* __restrict__ src, int src_str
                 if (s < n) {
                     int r, q;
                     split(s, nv, shift, r, q);
-                    __stcs(out + r * out_stride + q, z);
+                    st_stream(out + r * out_stride + q, z);
                 }
             }
         }
@@ -180,7 +202,7 @@ __device__ __forceinline__ void pool_tile(const V* __restrict__ src, int src_str
         if (s >= n) end = beg;
         V base = vzero((V*)nullptr);
         if constexpr (kAdd) {
-            if (s < n) base = __ldcs(addend + r * add_stride + q);
+            if (s < n) base = ld_stream(addend + r * add_stride + q);
         }
         V acc = vzero((V*)nullptr);
         int k = beg;
@@ -206,7 +228,7 @@ __device__ __forceinline__ void pool_tile(const V* __restrict__ src, int src_str
             axpy(acc, w, x);
         }
         if constexpr (kAdd) acc = vadd(base, acc);
-        if (s < n) __stcs(out + r * out_stride + q, acc);
+        if (s < n) st_stream(out + r * out_stride + q, acc);
     }
 }
 
@@ -299,8 +321,8 @@ __device__ __forceinline__ void pool_row_wide(const V* __restrict__ src, int src
         for (int a = 0; a < ACC; ++a) {
             const int q = q0 + a * 32 + lane;
             if (q < nv) {
-                if (arow != nullptr) acc[a] = vadd(__ldcs(arow + q), acc[a]);
-                __stcs(orow + q, acc[a]);
+                if (arow != nullptr) acc[a] = vadd(ld_stream(arow + q), acc[a]);
+                st_stream(orow + q, acc[a]);
             }
         }
     }
@@ -368,8 +390,8 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
                                 const int q = q0 + a * 32 + lane;
                                 if (q < nv) {
                                     if (addend != nullptr)
-                                        acc[a] = vadd(__ldcs(addend + (size_t)cur_row * add_stride + q), acc[a]);
-                                    __stcs(out + (size_t)cur_row * out_stride + q, acc[a]);
+                                        acc[a] = vadd(ld_stream(addend + (size_t)cur_row * add_stride + q), acc[a]);
+                                    st_stream(out + (size_t)cur_row * out_stride + q, acc[a]);
                                 }
                                 acc[a] = vzero((V*)nullptr);
                             }
@@ -406,8 +428,8 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
             for (int a = 0; a < ACC; ++a) {
                 const int q = q0 + a * 32 + lane;
                 if (q < nv) {
-                    if (addend != nullptr) acc[a] = vadd(__ldcs(addend + (size_t)cur_row * add_stride + q), acc[a]);
-                    __stcs(out + (size_t)cur_row * out_stride + q, acc[a]);
+                    if (addend != nullptr) acc[a] = vadd(ld_stream(addend + (size_t)cur_row * add_stride + q), acc[a]);
+                    st_stream(out + (size_t)cur_row * out_stride + q, acc[a]);
                 }
             }
         }
@@ -434,14 +456,14 @@ __device__ __forceinline__ void cta_copy_tile(const V* __restrict__ in, int in_s
                 split(s, nv, shift, r, q);
                 on[j] = !((skip >> r) & 1u);
                 if (on[j]) {
-                    v[j] = __ldcs(in + r * in_stride + q);
+                    v[j] = ld_stream(in + r * in_stride + q);
                     o[j] = r * out_stride + q;
                 }
             }
         }
 #pragma unroll
         for (int j = 0; j < kUnroll; ++j)
-            if (on[j]) __stcs(out + o[j], v[j]);
+            if (on[j]) st_stream(out + o[j], v[j]);
     }
 }
 
@@ -494,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, 2) shpl_pool_wide_kernel(PoolArgs a)
         for (int r = warp; r < rows; r += kWarps) {
             if ((busy >> r) & 1u) continue;
             V* orow = out + r * jb.pool_out_stride;
-            for (int q = lane; q < jb.vs; q += 32) __stcs(orow + q, z);
+            for (int q = lane; q < jb.vs; q += 32) st_stream(orow + q, z);
         }
     }
     if (by_entry) return;

@@ -71,94 +71,117 @@ class SparseTensor:
 
 
 # --------------------------------------------------------------------------- host half
+class SparsePoolingInput(dict):
+    """The dict gen_sparse_pooling_input_avod returns (sparse_pool_utils.py:20), evaluated lazily.
+
+    'bv_size' and 'img_size' are there at once.  'bv_index' [n,2] and 'img_index' [3,n] need the
+    number of pairs that survive the image clip, i.e. a device->host read; they are computed (by
+    shpl_gen_input_avod) the first time anything looks at them.  When the dict goes straight into
+    produce_sparse_pooling_input -- the reference's own call pattern, kitti_dataset.py:376-378 -- nobody
+    looks, and produce runs the fused builder (shpl_build_avod) instead: one pipeline, one read-back.
+    Looking later still shows what the reference would show, including produce's in-place floor/clamp
+    of img_index (:30-34)."""
+
+    _LAZY = ("bv_index", "img_index")
+
+    def __init__(self, pts, vox, P, im_size, bv_size, as_numpy, device):
+        super().__init__(bv_size=np.array([bv_size[0], bv_size[1]]), img_size=np.array(im_size))
+        self._pts, self._vox, self._P = pts, vox, P
+        self._as_numpy, self._device = as_numpy, device
+        self._done = False
+        self._mutations = []          # image strides applied in place by produce calls made before materialisation
+
+    def _materialize(self):
+        if self._done:
+            return
+        self._done = True
+        dev, pts, vox = self._device, self._pts, self._vox
+        im_size = dict.__getitem__(self, "img_size")
+        N = pts.shape[0]
+        bv_out = torch.empty((max(N, 1), 2), dtype=torch.int64, device=dev)
+        uv_out = torch.empty((2, max(N, 1)), dtype=torch.float64, device=dev)
+        counts = torch.zeros(8, dtype=torch.int32, device=dev)
+        ws = ops.workspace(dev, N)
+        rc = _lib.shpl_gen_input_avod(_ptr(pts), _ptr(vox), N, self._P.ctypes.data_as(ctypes.c_void_p),
+                                      _as_int(im_size[0], "im_size"), _as_int(im_size[1], "im_size"),
+                                      _ptr(bv_out), _ptr(uv_out[0]), _ptr(uv_out[1]), _ptr(counts), _ptr(ws),
+                                      ws.numel(), _stream())
+        _cabi.check(rc, "shpl_gen_input_avod")
+        n = int(counts[0].item())
+        img_index = torch.zeros((3, n), dtype=torch.float64, device=dev)
+        img_index[0:2] = uv_out[:, :n]
+        for s_img in self._mutations:          # what an earlier produce call did to the reference's array (:30-34)
+            for axis in (0, 1):
+                lim = float(int(im_size[axis]) // s_img)
+                row = torch.floor(img_index[axis] / s_img)
+                img_index[axis] = torch.where(row >= lim, torch.full_like(row, lim - 1), row)
+        bv_index = bv_out[:n]
+        if self._as_numpy:
+            bv_index, img_index = bv_index.cpu().numpy(), img_index.cpu().numpy()
+        dict.__setitem__(self, "bv_index", bv_index)
+        dict.__setitem__(self, "img_index", img_index)
+
+    def __missing__(self, key):
+        if key in self._LAZY:
+            self._materialize()
+            return dict.__getitem__(self, key)
+        raise KeyError(key)
+
+    def get(self, key, default=None):
+        if key in self._LAZY:
+            self._materialize()
+        return dict.get(self, key, default)
+
+    def __contains__(self, key):
+        return key in self._LAZY or dict.__contains__(self, key)
+
+    def __iter__(self):
+        self._materialize()
+        return dict.__iter__(self)
+
+    def __len__(self):
+        return 4
+
+    def keys(self):
+        self._materialize()
+        return dict.keys(self)
+
+    def items(self):
+        self._materialize()
+        return dict.items(self)
+
+    def values(self):
+        self._materialize()
+        return dict.values(self)
+
+    def copy(self):
+        self._materialize()
+        return dict(self)
+
+
 def gen_sparse_pooling_input_avod(points, voxel_indices, stereo_calib, im_size, bv_size):
     """sparse_pool_utils.py:6-20 on the GPU (shpl_gen_input_avod).
 
     points [N,3] f64 camera frame, voxel_indices [N,>=2] (x, zflip), stereo_calib.p2 [3,4],
-    im_size [W,H], bv_size [H_b,W_b].  Returns the reference's dict."""
+    im_size [W,H], bv_size [H_b,W_b].  Returns the reference's dict (a lazily evaluated
+    SparsePoolingInput: see there)."""
     as_numpy = not isinstance(points, torch.Tensor)
     dev = points.device if (not as_numpy and points.is_cuda) else _device()
     pts = _to_dev(points, torch.float64, dev).reshape(-1, 3)
     vox = voxel_indices if isinstance(voxel_indices, torch.Tensor) else np.asarray(voxel_indices)
     vox = _to_dev(vox[:, :2], torch.int64, dev)
     P = np.ascontiguousarray(np.asarray(stereo_calib.p2, dtype=np.float64).reshape(12))
-    N = pts.shape[0]
-    bv_out = torch.empty((max(N, 1), 2), dtype=torch.int64, device=dev)
-    u_out = torch.empty(max(N, 1), dtype=torch.float64, device=dev)
-    v_out = torch.empty(max(N, 1), dtype=torch.float64, device=dev)
-    counts = torch.zeros(8, dtype=torch.int32, device=dev)
-    ws = ops.workspace(dev, N)
-    rc = _lib.shpl_gen_input_avod(_ptr(pts), _ptr(vox), N, P.ctypes.data_as(ctypes.c_void_p),
-                                  _as_int(im_size[0], "im_size"), _as_int(im_size[1], "im_size"),
-                                  _ptr(bv_out), _ptr(u_out), _ptr(v_out), _ptr(counts), _ptr(ws), ws.numel(), _stream())
-    _cabi.check(rc, "shpl_gen_input_avod")
-    n = int(counts[0].item())
-    img_index = torch.zeros((3, n), dtype=torch.float64, device=dev)
-    img_index[0] = u_out[:n]
-    img_index[1] = v_out[:n]
-    bv_index = bv_out[:n]
-    if as_numpy:
-        bv_index = bv_index.cpu().numpy()
-        img_index = img_index.cpu().numpy()
-    return {"bv_index": bv_index, "img_index": img_index,
-            "bv_size": np.array([bv_size[0], bv_size[1]]), "img_size": np.array(im_size)}
+    _as_int(im_size[0], "im_size"), _as_int(im_size[1], "im_size")
+    return SparsePoolingInput(pts, vox, P, im_size, bv_size, as_numpy, dev)
 
 
-def produce_sparse_pooling_input(input_dict, M_val=None, stride=[1, 1]):
-    """sparse_pool_utils.py:22-58 on the GPU (shpl_produce_input), plus the CSR plan.
-
-    stride[0] scales the image, stride[1] the BEV (the reference's comment has them
-    swapped).  Mutates input_dict['img_index'] in place like the reference (:30).
-    The returned dict has the reference's five keys and one extra, 'shpl_plan'."""
-    bv_index = input_dict["bv_index"]
-    img_index = input_dict["img_index"]
-    bv_size = input_dict["bv_size"]
-    im_size = input_dict["img_size"]
-    assert img_index.shape[0] == 3, 'wrong img_index shape, should be 3xN instead ' + str(tuple(img_index.shape))
-    as_numpy = not isinstance(img_index, torch.Tensor)
-    dev = img_index.device if (not as_numpy and img_index.is_cuda) else _device()
-    s_img, s_bv = _as_int(stride[0], "stride[0]"), _as_int(stride[1], "stride[1]")
-    im_w, im_h = _as_int(im_size[0], "img_size"), _as_int(im_size[1], "img_size")
-    bv_h, bv_w = _as_int(bv_size[0], "bv_size"), _as_int(bv_size[1], "bv_size")
-    n = int(img_index.shape[1])
-
-    uv = _to_dev(img_index[0:2], torch.float64, dev)
-    bv = _to_dev(bv_index, torch.int64, dev).reshape(-1, 2)
-    if bv.shape[0] != n:
-        raise ValueError("bv_index has %d rows, img_index %d columns" % (bv.shape[0], n))
-    mval_dev = None
-    if M_val is not None:
-        mval_dev = _to_dev(M_val, torch.float64, dev).reshape(-1)
-        n_mval = mval_dev.shape[0]
-        if n_mval < n:      # the kernel indexes it by output column k < nnz <= n: keep every read in bounds
-            mval_dev = torch.cat([mval_dev, torch.zeros(n - n_mval, dtype=torch.float64, device=dev)])
-
-    Hp, Wp = im_h // s_img, im_w // s_img
-    R = (bv_h // s_bv) * (bv_w // s_bv)
-    plan = SparsePoolPlan(R, (Hp, Wp), n, dev)
-    cap = max(n, 1)
-    Mij = torch.empty((cap, 2), dtype=torch.int64, device=dev)
-    flip = torch.empty((cap, 3), dtype=torch.int64, device=dev)
-    mval_f32 = torch.empty(cap, dtype=torch.float32, device=dev)
-    msize = torch.zeros(2, dtype=torch.int64, device=dev)
-    ws = ops.workspace(dev, n)
-    st = plan.frame_struct(0)
-    rc = _lib.shpl_produce_input(_ptr(uv[0]), _ptr(uv[1]), _ptr(bv), n, im_w, im_h, bv_h, bv_w, s_img, s_bv,
-                                 _ptr(mval_dev), 0, 0, _ptr(Mij), _ptr(flip), _ptr(mval_f32), _ptr(msize),
-                                 ctypes.byref(st), 0, 0, None, _ptr(ws), ws.numel(), _stream())
-    _cabi.check(rc, "shpl_produce_input")
+def _produce_outputs(plan, Mij, flip, R, M_val, n_mval, as_numpy, dev):
     plan.read_counts()
     nnz = plan.nnz[0]
     if M_val is not None and n_mval != nnz:
         raise ValueError("M_val has %d entries but M has %d columns (tf.SparseTensor would reject it)" % (n_mval, nnz))
-    plan.values_f32 = mval_f32[:nnz]
     plan.flip = flip[:nnz]
     plan.Mij = Mij[:nnz]
-    # the in-place mutation of the caller's img_index (:30-34)
-    if as_numpy:
-        img_index[0:2, :] = uv.cpu().numpy()
-    elif uv.data_ptr() != img_index.data_ptr():
-        img_index[0:2] = uv.to(img_index.device)
     M_size = np.array([R, nnz]).astype(int)
     if as_numpy:
         out_Mij, out_flip = Mij[:nnz].cpu().numpy(), flip[:nnz].cpu().numpy()
@@ -170,6 +193,80 @@ def produce_sparse_pooling_input(input_dict, M_val=None, stride=[1, 1]):
         bev_flip = torch.zeros((0, 3), device=dev)
     return {"Mij_pool": out_Mij, "M_val": out_val, "M_size": M_size, "img_index_flip_pool": out_flip,
             "bev_index_flip_pool": bev_flip, PLAN_KEY: plan}
+
+
+def _mval_to_dev(M_val, n, dev):
+    mval_dev = _to_dev(M_val, torch.float64, dev).reshape(-1)
+    n_mval = mval_dev.shape[0]
+    if n_mval < n:      # the kernel indexes it by output column k < nnz <= n: keep every read in bounds
+        mval_dev = torch.cat([mval_dev, torch.zeros(n - n_mval, dtype=torch.float64, device=dev)])
+    return mval_dev, n_mval
+
+
+def produce_sparse_pooling_input(input_dict, M_val=None, stride=[1, 1]):
+    """sparse_pool_utils.py:22-58 on the GPU (shpl_produce_input), plus the CSR plan.
+
+    stride[0] scales the image, stride[1] the BEV (the reference's comment has them
+    swapped).  Mutates input_dict['img_index'] in place like the reference (:30).
+    The returned dict has the reference's five keys and one extra, 'shpl_plan'."""
+    s_img, s_bv = _as_int(stride[0], "stride[0]"), _as_int(stride[1], "stride[1]")
+    bv_size = input_dict["bv_size"]
+    im_size = input_dict["img_size"]
+    im_w, im_h = _as_int(im_size[0], "img_size"), _as_int(im_size[1], "img_size")
+    bv_h, bv_w = _as_int(bv_size[0], "bv_size"), _as_int(bv_size[1], "bv_size")
+    Hp, Wp = im_h // s_img, im_w // s_img
+    R = (bv_h // s_bv) * (bv_w // s_bv)
+
+    if isinstance(input_dict, SparsePoolingInput) and not input_dict._done and not input_dict._mutations:
+        # straight from gen_sparse_pooling_input_avod: fused builder, the intermediate dict is never made
+        dev, pts, vox = input_dict._device, input_dict._pts, input_dict._vox
+        N = int(pts.shape[0])
+        mval_dev, n_mval = (None, 0) if M_val is None else _mval_to_dev(M_val, N, dev)
+        plan = SparsePoolPlan(R, (Hp, Wp), N, dev)
+        plan.entry_bound = max(N, 1)
+        cap = max(N, 1)
+        Mij = torch.empty((cap, 2), dtype=torch.int64, device=dev)
+        flip = torch.empty((cap, 3), dtype=torch.int64, device=dev)
+        ws = ops.workspace(dev, N)
+        st = plan.frame_struct(0)
+        rc = _lib.shpl_build_avod(_ptr(pts), _ptr(vox), N, input_dict._P.ctypes.data_as(ctypes.c_void_p),
+                                  im_w, im_h, bv_h, bv_w, s_img, s_bv, _ptr(mval_dev), 0, 0, _ptr(Mij), _ptr(flip),
+                                  None, None, ctypes.byref(st), 0, 0, None, _ptr(ws), ws.numel(), _stream())
+        _cabi.check(rc, "shpl_build_avod")
+        input_dict._mutations.append(s_img)
+        return _produce_outputs(plan, Mij, flip, R, M_val, n_mval, input_dict._as_numpy, dev)
+
+    bv_index = input_dict["bv_index"]
+    img_index = input_dict["img_index"]
+    assert img_index.shape[0] == 3, 'wrong img_index shape, should be 3xN instead ' + str(tuple(img_index.shape))
+    as_numpy = not isinstance(img_index, torch.Tensor)
+    dev = img_index.device if (not as_numpy and img_index.is_cuda) else _device()
+    n = int(img_index.shape[1])
+
+    uv = _to_dev(img_index[0:2], torch.float64, dev)
+    bv = _to_dev(bv_index, torch.int64, dev).reshape(-1, 2)
+    if bv.shape[0] != n:
+        raise ValueError("bv_index has %d rows, img_index %d columns" % (bv.shape[0], n))
+    mval_dev, n_mval = (None, 0) if M_val is None else _mval_to_dev(M_val, n, dev)
+
+    plan = SparsePoolPlan(R, (Hp, Wp), n, dev)
+    plan.entry_bound = max(n, 1)
+    cap = max(n, 1)
+    Mij = torch.empty((cap, 2), dtype=torch.int64, device=dev)
+    flip = torch.empty((cap, 3), dtype=torch.int64, device=dev)
+    ws = ops.workspace(dev, n)
+    st = plan.frame_struct(0)
+    rc = _lib.shpl_produce_input(_ptr(uv[0]), _ptr(uv[1]), _ptr(bv), n, im_w, im_h, bv_h, bv_w, s_img, s_bv,
+                                 _ptr(mval_dev), 0, 0, _ptr(Mij), _ptr(flip), None, None,
+                                 ctypes.byref(st), 0, 0, None, _ptr(ws), ws.numel(), _stream())
+    _cabi.check(rc, "shpl_produce_input")
+    out = _produce_outputs(plan, Mij, flip, R, M_val, n_mval, as_numpy, dev)
+    # the in-place mutation of the caller's img_index (:30-34)
+    if as_numpy:
+        img_index[0:2, :] = uv.cpu().numpy()
+    elif uv.data_ptr() != img_index.data_ptr():
+        img_index[0:2] = uv.to(img_index.device)
+    return out
 
 
 # ------------------------------------------------------------------------- device half
@@ -204,6 +301,18 @@ def _resolve_plan(M, source_index, n_rows, src_hw, device):
     except AttributeError:
         pass
     return plan
+
+
+_dual_announced = False
+
+
+def _announce_dual():
+    """The reference prints this while it builds the TF graph, i.e. once (:80); an eager layer would
+    print it every step, so it is printed on first use only."""
+    global _dual_announced
+    if not _dual_announced:
+        _dual_announced = True
+        print('using dual sparse pooling')
 
 
 def _check_oob(plan):
@@ -275,7 +384,7 @@ def sparse_pool_layer(inputs, feature_depths, M, img_index_flip=None, bv_index=N
         if int(feature_depths[0]) != input_img.shape[3] or int(feature_depths[1]) != input_bv.shape[3]:
             raise ValueError("feature_depths %r do not match the maps (%d image, %d BEV channels)"
                              % (list(feature_depths), input_img.shape[3], input_bv.shape[3]))
-        print('using dual sparse pooling')       # the reference prints this (:80)
+        _announce_dual()
         return ops.sparse_pool_dual(input_bv, input_img, plan)
     if img_index_flip is not None:
         if int(feature_depths[0]) != input_img.shape[3]:

@@ -408,3 +408,27 @@ def test_one_very_long_row(shpl):
     gd, gs = cref.backward(g, o["Mij_pool"], val, o["img_index_flip_pool"], 32, (32, 64, 32))
     np.testing.assert_array_equal(ti.grad[0].cpu().numpy(), gs)
     np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd)
+
+
+def test_lazy_gen_dict_behaves_like_the_reference_dict(shpl, golden_dir):
+    """gen's dict is evaluated lazily so that gen -> produce runs the fused builder; looking at it
+    before or after produce must still show what the reference shows (incl. the in-place mutation
+    and the compounding of a second produce call, quirk A.4-6)."""
+    frame = synth.avod_frame(1, az_step_deg=0.09)
+    ref = io.gen_sparse_pooling_input_avod(frame["points"], frame["voxel_indices"], frame["P"], frame["im_size"], frame["bv_size"])
+    ref_o1 = io.produce_sparse_pooling_input(ref, stride=[4, 4])
+    ref_after1 = ref["img_index"].copy()
+    ref_o2 = io.produce_sparse_pooling_input(ref, stride=[2, 2])
+    # fused path: produce before anyone looks
+    d = shpl.gen_sparse_pooling_input_avod(frame["points"], frame["voxel_indices"], Calib(frame["P"]), frame["im_size"], frame["bv_size"])
+    assert "img_index" in d and len(d) == 4 and not d._done
+    o1 = shpl.produce_sparse_pooling_input(d, stride=[4, 4])
+    assert not d._done                                             # nothing was read back for the gen dict
+    np.testing.assert_array_equal(o1["Mij_pool"], ref_o1["Mij_pool"])
+    np.testing.assert_array_equal(o1["img_index_flip_pool"], ref_o1["img_index_flip_pool"])
+    np.testing.assert_array_equal(d["img_index"], ref_after1)      # materialised now, mutation included
+    o2 = shpl.produce_sparse_pooling_input(d, stride=[2, 2])       # compounds, like the reference
+    np.testing.assert_array_equal(o2["Mij_pool"], ref_o2["Mij_pool"])
+    np.testing.assert_array_equal(o2["img_index_flip_pool"], ref_o2["img_index_flip_pool"])
+    np.testing.assert_array_equal(d["img_index"], ref["img_index"])
+    assert sorted(d.keys()) == ["bv_index", "bv_size", "img_index", "img_size"]
