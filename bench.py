@@ -471,6 +471,53 @@ def run_gpu(args):
                    "feature maps device-resident (they are device-resident TF tensors in the reference), 2 KB of the "
                    "gradients read back to pinned host memory every step"}
 
+    # ---- e2e through the bare C ABI (the lean ctypes pipeline): frame inputs copied from pinned host memory and a
+    #      result read back every step, no cross-frame pipelining (the step ends with a host read)
+    stage_pts = torch.empty((N_MAX, 3), dtype=torch.float64, device=dev)
+    stage_vox = torch.empty((N_MAX, 2), dtype=torch.int64, device=dev)
+    res_dev = torch.empty(2 * len(specs) * 256 + 16, dtype=torch.float32, device=dev)
+    res_pin = torch.empty_like(res_dev, device="cpu").pin_memory()
+
+    def cabi_step(k):
+        fi, si = k % N_FRAMES, k % n_sets
+        pipe, mp = pipes[si], maps[si]
+        n = n_pts[fi]
+        stage_pts[:n].copy_(pts_pin[fi], non_blocking=True)
+        stage_vox[:n].copy_(vox_pin[fi], non_blocking=True)
+        ms = torch.cuda.current_stream().cuda_stream
+        for li in range(len(specs)):
+            pipe.build_layer(li, stage_pts, stage_vox, P, n, ms)
+        for li in range(len(specs)):
+            pipe.forward_layer(li, mp[li]["bev"], mp[li]["img"], ms, n)
+        for li in reversed(range(len(specs))):
+            pipe.backward_layer(li, mp[li]["g_bev"], mp[li]["g_img"], ms, n)
+        off = 0
+        for li in range(len(specs)):
+            res_dev[off:off + 256].copy_(pipe.layers[li].g_bev.reshape(-1)[:256])
+            res_dev[off + 256:off + 512].copy_(pipe.layers[li].g_img.reshape(-1)[:256])
+            off += 512
+        res_dev[off:off + 16].copy_(torch.cat([L.plan.counts.reshape(-1)[:8] for L in pipe.layers]).float())
+        res_pin.copy_(res_dev, non_blocking=False)
+
+    for k in range(3):
+        cabi_step(k)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K_e2e):
+        cabi_step(k)
+    torch.cuda.synchronize()
+    dt_cabi = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt_cabi], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_cabi = float(t.item())
+    e2e["c_abi_pipeline"] = {"value": world * K_e2e / dt_cabi, "unit": UNIT,
+                             "h2d_bytes_per_step": int(n_pts[0] * 40), "d2h_bytes_per_step": int(res_pin.numel() * 4),
+                             "what": "same step through the ctypes C-ABI calls on preallocated buffers: points/voxel indices "
+                                     "copied from pinned host memory, both plans built, forward+backward of both layers, "
+                                     "4 KB of gradients + the plan counters read back to pinned host memory, every step"}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -27,7 +27,12 @@
 extern "C" {
 #endif
 
-#define SHPL_ABI_VERSION 2
+#define SHPL_ABI_VERSION 3
+
+/* Cells with more entries than this are "heavy": the builder lists them in the plan and their sum
+ * is formed by shpl_pool_heavy (a thread-block cluster per cell, fixed summation tree) instead of
+ * one warp walking the cell. */
+#define SHPL_HEAVY_LEN 2048
 
 typedef enum shpl_status {
     SHPL_OK = 0,
@@ -56,6 +61,10 @@ typedef struct shpl_plan {
     int32_t* csrT_pix;  /* [capacity]  source pixel of each entry (the sort key)      */
     int32_t* csrT_dst;  /* [capacity]  destination row of each entry                  */
     float*   csrT_val;  /* [capacity]                                                 */
+    int32_t  heavy_cap; /* capacity of heavy_row / heavy_pix (0: do not list heavy cells)  */
+    int32_t* heavy_row; /* [heavy_cap] destination rows with more than SHPL_HEAVY_LEN entries */
+    int32_t* heavy_pix; /* [heavy_cap] source pixels with more than SHPL_HEAVY_LEN entries    */
+    int32_t* heavy_count; /* [2] device: number of listed rows, pixels (all stacked frames)  */
     int32_t* counts;    /* [8] device: [0]=n after image clip, [1]=nnz (columns of M),
                            [2]=entries left out of the CSRs because an index is out of
                            range (TF-CPU raises InvalidArgumentError for those),
@@ -144,10 +153,13 @@ int shpl_plan_from_coo(const int64_t* Mij, const float* val, int64_t m,
  * dst may be NULL with C_d = 0 (pooled map only: _sparse_pool_op without concat).
  * key [nnz] = destination row of each entry (plan.csr_row / plan.csrT_pix) and
  * nnz_max >= number of entries (e.g. plan.capacity) let the kernel balance the
- * gathers by entry; key may be NULL (then rows are walked cell by cell). */
+ * gathers by entry; key may be NULL (then rows are walked cell by cell).
+ * heavy_len > 0: cells with more than heavy_len entries are NOT summed here (their pooled part is
+ * left zero / their dense part copied); the caller follows with shpl_pool_heavy on the listed
+ * cells.  heavy_len = 0: every cell is summed here, strictly sequentially. */
 int shpl_pool_forward(const float* dst, const float* src,
                       const int32_t* ptr, const int32_t* key, const int32_t* idx, const float* val,
-                      int32_t nnz_max, int32_t n_rows, int32_t C_d, int32_t n_src, int32_t C_s,
+                      int32_t nnz_max, int32_t heavy_len, int32_t n_rows, int32_t C_d, int32_t n_src, int32_t C_s,
                       float* fused, void* stream);
 
 /* Backward of shpl_pool_forward (what TF autodiff derives, SURVEY.md row a13;
@@ -158,7 +170,7 @@ int shpl_pool_forward(const float* dst, const float* src,
  * g_dst may be NULL (no slice copy).  keyT / nnz_max as in shpl_pool_forward. */
 int shpl_pool_backward(const float* g_fused,
                        const int32_t* ptrT, const int32_t* keyT, const int32_t* idxT, const float* valT,
-                       int32_t nnz_max, int32_t n_rows, int32_t C_d, int32_t n_src, int32_t C_s,
+                       int32_t nnz_max, int32_t heavy_len, int32_t n_rows, int32_t C_d, int32_t n_src, int32_t C_s,
                        float* g_dst, float* g_src, void* stream);
 
 /* Both directions of sparse_pool_layer in ONE launch (the `bv_index is not None` branch,
@@ -169,7 +181,7 @@ int shpl_pool_backward(const float* g_fused,
 int shpl_pool_forward_dual(const float* bev, const float* img,
                            const int32_t* row_ptr, const int32_t* csr_row, const int32_t* csr_src, const float* csr_val,
                            const int32_t* pix_ptr, const int32_t* csrT_pix, const int32_t* csrT_dst, const float* csrT_val,
-                           int32_t nnz_max, int32_t n_rows, int32_t C_b, int32_t n_src, int32_t C_i,
+                           int32_t nnz_max, int32_t heavy_len, int32_t n_rows, int32_t C_b, int32_t n_src, int32_t C_i,
                            float* fused_bev, float* fused_img, void* stream);
 
 /* Backward of shpl_pool_forward_dual in one launch.  Each input of the layer feeds two
@@ -181,8 +193,23 @@ int shpl_pool_forward_dual(const float* bev, const float* img,
 int shpl_pool_backward_dual(const float* g_fused_bev, const float* g_fused_img,
                             const int32_t* row_ptr, const int32_t* csr_row, const int32_t* csr_src, const float* csr_val,
                             const int32_t* pix_ptr, const int32_t* csrT_pix, const int32_t* csrT_dst, const float* csrT_val,
-                            int32_t nnz_max, int32_t n_rows, int32_t C_b, int32_t n_src, int32_t C_i,
+                            int32_t nnz_max, int32_t heavy_len, int32_t n_rows, int32_t C_b, int32_t n_src, int32_t C_i,
                             float* g_bev, float* g_img, void* stream);
+
+/* Heavy cells (more than SHPL_HEAVY_LEN entries; none at KITTI / MV3D shapes, the Zipf stress case has
+ * a 178 000-entry cell): one thread-block CLUSTER of 8 CTAs per listed cell.  The cell's entries are cut
+ * into 64 contiguous pieces (8 CTAs x 8 warps); every warp sums its piece in stored order, the 8 warp sums
+ * of a CTA are added in order in shared memory, and CTA 0 adds the 8 CTA sums in order through
+ * distributed shared memory: a fixed tree, deterministic, within fp32 rounding of the sequential sum
+ * (not bit-identical to it).  Overwrites what the main kernel left for those cells:
+ *   out[c*out_stride + 0:C] = (addend ? addend[c*addend_stride + 0:C] : 0) + sum_k val[k] * gather_in[idx[k]*gather_stride + 0:C]
+ * for every c in list[0:*count_dev].  All strides in floats; the channel offsets are folded into the
+ * pointers (e.g. out = fused + C_d, out_stride = C_d + C_s for the forward). */
+int shpl_pool_heavy(const float* gather_in, int32_t gather_stride, int32_t C,
+                    const int32_t* ptr, const int32_t* idx, const float* val,
+                    const int32_t* list, const int32_t* count_dev, int32_t list_cap,
+                    const float* addend, int32_t addend_stride,
+                    float* out, int32_t out_stride, void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,8 @@ SHPL_ERR_CUDA = -2
 SHPL_ERR_WORKSPACE_TOO_SMALL = -3
 SHPL_ERR_UNSUPPORTED = -4
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+HEAVY_LEN = 2048          # SHPL_HEAVY_LEN of include/shpl.h
 
 
 class ShplPlan(ctypes.Structure):
@@ -39,6 +40,10 @@ class ShplPlan(ctypes.Structure):
         ("csrT_pix", c_void_p),
         ("csrT_dst", c_void_p),
         ("csrT_val", c_void_p),
+        ("heavy_cap", c_int32),
+        ("heavy_row", c_void_p),
+        ("heavy_pix", c_void_p),
+        ("heavy_count", c_void_p),
         ("counts", c_void_p),
     ]
 
@@ -68,11 +73,13 @@ SIGNATURES = {
                                           ctypes.POINTER(ShplPlan), c_int32, c_int32, c_void_p,
                                           c_void_p, c_size_t, c_void_p]),
     "shpl_pool_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                         c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+                                         c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "shpl_pool_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                          c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
-    "shpl_pool_forward_dual": (ctypes.c_int, [c_void_p] * 10 + [c_int32] * 5 + [c_void_p] * 3),
-    "shpl_pool_backward_dual": (ctypes.c_int, [c_void_p] * 10 + [c_int32] * 5 + [c_void_p] * 3),
+                                          c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "shpl_pool_forward_dual": (ctypes.c_int, [c_void_p] * 10 + [c_int32] * 6 + [c_void_p] * 3),
+    "shpl_pool_backward_dual": (ctypes.c_int, [c_void_p] * 10 + [c_int32] * 6 + [c_void_p] * 3),
+    "shpl_pool_heavy": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p]),
 }
 
 

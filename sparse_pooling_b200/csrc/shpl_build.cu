@@ -139,6 +139,7 @@ struct PairsArgs {
     float* mval_out;
     long long* msize_out;
     int* counts;
+    int* heavy_count;            // zeroed by the first frame of a plan (row_base == pix_base == 0)
     Workspace ws;
     SortPlan sp[2];
 };
@@ -322,6 +323,10 @@ __global__ void __launch_bounds__(kThreads) shpl_pairs_kernel(PairsArgs a, int u
     const long long k = (long long)(s_excl & ((1ull << 31) - 1)) + wb_keep + __popc(mk & lt);
 
     const long long n_tiles = (a.n + kPairsTile - 1) / kPairsTile > 0 ? (a.n + kPairsTile - 1) / kPairsTile : 1;
+    if (tile == 0 && threadIdx.x == 0 && a.heavy_count != nullptr && a.row_base == 0 && a.pix_base == 0) {
+        a.heavy_count[0] = 0;
+        a.heavy_count[1] = 0;
+    }
     if (tile == n_tiles - 1 && threadIdx.x == 0) {   // inclusive prefix of the last tile = totals
         const long long n_clip = (long long)(s_excl >> 31) + tot_clip;
         const long long nnz = (long long)(s_excl & ((1ull << 31) - 1)) + tot_keep;
@@ -507,6 +512,7 @@ __global__ void __launch_bounds__(kThreads) shpl_radix_pass_kernel(RadixArgs a) 
 }
 
 struct FinalArgs {
+    int row_base, pix_base;
     int* counts;
     Workspace ws;
     SortPlan sp[2];
@@ -554,6 +560,8 @@ constexpr int kFinalKeys = 256;    // offsets written per CTA (one window search
 // gather the payloads of kFinalKeys sorted entries each.
 __global__ void __launch_bounds__(kThreads) shpl_finalize_kernel(FinalArgs a, int nb_row, int nb_pix) {
     __shared__ int s_lb[2];
+    __shared__ int s_off[kThreads];
+    static_assert(kFinalKeys == kThreads, "one offset per thread");
     const int n = a.counts[1];
     const int ebase = a.entry_base_dev ? *a.entry_base_dev : 0;
     const unsigned long long* by_row = a.ws.items[0][a.sp[0].passes & 1];
@@ -574,13 +582,25 @@ __global__ void __launch_bounds__(kThreads) shpl_finalize_kernel(FinalArgs a, in
         }
         __syncthreads();
         const int w0 = s_lb[0], w1 = s_lb[1];
-        for (int j = j0 + threadIdx.x; j < j1; j += kThreads) {
-            const int lb = lower_bound_key(items, w0, w1, (unsigned)j);
+        const int j = j0 + threadIdx.x;          // kFinalKeys == kThreads: one offset per thread
+        int lb = w1;
+        if (j < j1) {
+            lb = lower_bound_key(items, w0, w1, (unsigned)j);
             ptr[j] = ebase + lb;
             if (is_row && j == n_keys) {
                 a.counts[2] = n - lb;
                 a.counts[3] = lb;
                 a.counts[4] = ebase + lb;     // entry base of the next stacked frame
+            }
+        }
+        // heavy cells (more than SHPL_HEAVY_LEN entries) are listed for shpl_pool_heavy
+        s_off[threadIdx.x] = lb;
+        __syncthreads();
+        if (a.plan.heavy_cap > 0 && j < j1 && j < n_keys) {
+            const int next = (threadIdx.x + 1 < kThreads && j + 1 < j1) ? s_off[threadIdx.x + 1] : w1;
+            if (next - lb > SHPL_HEAVY_LEN) {
+                const int slot = atomicAdd(a.plan.heavy_count + (is_row ? 0 : 1), 1);
+                if (slot < a.plan.heavy_cap) (is_row ? a.plan.heavy_row : a.plan.heavy_pix)[slot] = j + (is_row ? a.row_base : a.pix_base);
             }
         }
         return;
@@ -621,6 +641,9 @@ int run_build(PairsArgs& pa, const shpl_plan* plan, const int32_t* entry_base_de
                      "%s: plan capacity %d < %lld candidates", who, plan->capacity, pa.n);
         pa.sp[0] = make_sort_plan(plan->n_rows);
         pa.sp[1] = make_sort_plan(plan->n_src);
+        SHPL_REQUIRE(plan->heavy_cap == 0 || (plan->heavy_row && plan->heavy_pix && plan->heavy_count),
+                     SHPL_ERR_INVALID_ARGUMENT, "%s: heavy_cap > 0 but a heavy array is null", who);
+        pa.heavy_count = plan->heavy_cap > 0 ? plan->heavy_count : nullptr;
     } else {
         pa.sp[0] = make_sort_plan(1);
         pa.sp[1] = make_sort_plan(1);
@@ -656,6 +679,8 @@ int run_build(PairsArgs& pa, const shpl_plan* plan, const int32_t* entry_base_de
     fa.sp[1] = pa.sp[1];
     fa.plan = *plan;
     fa.entry_base_dev = entry_base_dev;
+    fa.row_base = pa.row_base;
+    fa.pix_base = pa.pix_base;
     const int nb_row = (plan->n_rows + 1 + kFinalKeys - 1) / kFinalKeys;
     const int nb_pix = (plan->n_src + 1 + kFinalKeys - 1) / kFinalKeys;
     const int nb_ent = (int)((pa.n + kFinalKeys - 1) / kFinalKeys);

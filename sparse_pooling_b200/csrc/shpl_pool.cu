@@ -25,7 +25,11 @@
 //     list), not by cell, so crowded near-range cells of a stride-8 BEV map cannot serialise.
 // Sums run in stored (ascending k) order with separately rounded multiply and add, which makes
 // the result bit-identical to the sequential oracle.
+#include <cooperative_groups.h>
+
 #include "shpl_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -109,6 +113,7 @@ struct Job {
     int vd_shift, vs_shift;  // log2 or -1
     int n_cells;
     int add;                 // 1: pool_out[c] = dense_in[c] + sum (vd == vs); 0: concat form
+    int heavy_len;           // > 0: cells with more entries are left to shpl_pool_heavy (treated as empty here)
     int rows_per_tile;       // narrow: cells per warp tile
     int entry_ctas;          // wide: leading CTAs of this job that gather by entry; narrow: CTAs serving the job
     int entry_chunk;         // wide: entries per warp
@@ -166,11 +171,12 @@ template <typename V, bool kAdd>
 __device__ __forceinline__ void pool_tile(const V* __restrict__ src, int src_stride, const int* __restrict__ ptr,
                                           const int* __restrict__ idx, const float* __restrict__ val,
                                           V* __restrict__ out, int out_stride, const V* __restrict__ addend,
-                                          int add_stride, int nv, int shift, int rows, int lane) {
+                                          int add_stride, int nv, int shift, int rows, int heavy_len, int lane) {
     int lo = 0, hi = 0;
     if (lane < rows) {
         lo = __ldg(ptr + lane);
         hi = __ldg(ptr + lane + 1);
+        if (heavy_len > 0 && hi - lo > heavy_len) hi = lo;     // heavy cell: shpl_pool_heavy writes it
     }
     const unsigned busy = __ballot_sync(kFull, hi > lo);
     const int n = rows * nv;
@@ -271,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, SHPL_NARROW_MIN_CTAS) shpl_pool_narr
         if (jb.vs > 0)
             pool_tile<V, kAdd>(gather_in, jb.gather_stride, jb.ptr + r0, jb.idx, jb.val,
                                pool_out + (size_t)r0 * jb.pool_out_stride, jb.pool_out_stride, din,
-                               jb.dense_in_stride, jb.vs, jb.vs_shift, rows, lane);
+                               jb.dense_in_stride, jb.vs, jb.vs_shift, rows, jb.heavy_len, lane);
     }
 }
 
@@ -339,7 +345,8 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
                                                   const int* __restrict__ key, const int* __restrict__ idx,
                                                   const float* __restrict__ val, int e0, int e1, int e_begin,
                                                   int e_end, V* __restrict__ out, int out_stride,
-                                                  const V* __restrict__ addend, int add_stride, int nv, int lane) {
+                                                  const V* __restrict__ addend, int add_stride, int nv,
+                                                  const int* __restrict__ ptr, int heavy_len, int lane) {
     const int prev_row = (e0 > e_begin) ? __ldg(key + e0 - 1) : -1;
     for (int q0 = 0; q0 < nv; q0 += 32 * ACC) {
         int base = e0;
@@ -357,11 +364,29 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
         }
         if (base + pos >= e1) return;          // no cell starts in this chunk
         int cur_row = -1;
+        int run_len = 0;               // entries of cur_row summed so far
         bool finished = false;
         V acc[ACC];
 #pragma unroll
         for (int a = 0; a < ACC; ++a) acc[a] = vzero((V*)nullptr);
         while (true) {
+            if (heavy_len > 0 && run_len > heavy_len) {
+                // a heavy cell: shpl_pool_heavy sums it; drop the partial sum and jump to the cell's end
+                const int cell_end = __ldg(ptr + cur_row + 1);
+                cur_row = -1;
+                run_len = 0;
+#pragma unroll
+                for (int a = 0; a < ACC; ++a) acc[a] = vzero((V*)nullptr);
+                if (cell_end >= e1 || cell_end >= e_end) break;
+                base = cell_end;
+                my_row = -1;
+                if (base + lane < e_end) {
+                    my_row = __ldg(key + base + lane);
+                    my_p = __ldg(idx + base + lane);
+                    my_w = __ldg(val + base + lane);
+                }
+                pos = 0;
+            }
             const int cnt = min(32, e_end - base);
             while (pos < cnt) {
                 V x[kGatherUnroll][ACC];
@@ -402,7 +427,9 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
                             continue;
                         }
                         cur_row = row[j];
+                        run_len = 0;
                     }
+                    ++run_len;
 #pragma unroll
                     for (int a = 0; a < ACC; ++a) {
                         const int q = q0 + a * 32 + lane;
@@ -411,8 +438,10 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
                 }
                 if (finished) break;
                 pos += kGatherUnroll;
+                if (heavy_len > 0 && run_len > heavy_len) break;
             }
             if (finished) break;
+            if (heavy_len > 0 && run_len > heavy_len) continue;     // handled at the top of the loop
             base += 32;
             if (base >= e_end) break;
             my_row = -1;
@@ -423,7 +452,7 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
             }
             pos = 0;
         }
-        if (cur_row >= 0) {
+        if (cur_row >= 0 && !(heavy_len > 0 && run_len > heavy_len)) {
 #pragma unroll
             for (int a = 0; a < ACC; ++a) {
                 const int q = q0 + a * 32 + lane;
@@ -484,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, 2) shpl_pool_wide_kernel(PoolArgs a)
         if (e0 >= e_end) return;
         pool_entries_wide<V, ACC>(src, jb.gather_stride, jb.key, jb.idx, jb.val, e0, min(e0 + jb.entry_chunk, e_end),
                                   e_begin, e_end, pout, jb.pool_out_stride, jb.add ? din : nullptr,
-                                  jb.dense_in_stride, jb.vs, lane);
+                                  jb.dense_in_stride, jb.vs, jb.ptr, jb.heavy_len, lane);
         return;
     }
     const int r0 = (b - jb.entry_ctas) * kWideTile;
@@ -495,6 +524,7 @@ __global__ void __launch_bounds__(kThreads, 2) shpl_pool_wide_kernel(PoolArgs a)
         if (lane < rows) {
             lo = __ldg(jb.ptr + r0 + lane);
             hi = __ldg(jb.ptr + r0 + lane + 1);
+            if (jb.heavy_len > 0 && hi - lo > jb.heavy_len) hi = lo;   // heavy cell: written as empty here
         }
         busy = __ballot_sync(kFull, hi > lo);
     }
@@ -531,6 +561,110 @@ __global__ void __launch_bounds__(kThreads, 2) shpl_pool_wide_kernel(PoolArgs a)
         const int end = __shfl_sync(kFull, hi, r);
         pool_row_wide<V, ACC>(src, jb.gather_stride, beg, end, jb.idx, jb.val, out + r * jb.pool_out_stride,
                               jb.add ? din + (size_t)(r0 + r) * jb.dense_in_stride : nullptr, jb.vs, lane);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------- heavy
+// One thread-block cluster (8 CTAs x 8 warps) per heavy cell: 64 contiguous pieces of the cell's entry
+// range, each summed in stored order by one warp; warp sums added in order inside the CTA (shared
+// memory), CTA sums added in order by CTA 0 through distributed shared memory.  A fixed tree.
+constexpr int kClusterSize = 8;
+
+struct HeavyArgs {
+    const void* gather_in;
+    const void* addend;
+    void* out;
+    const int* ptr;
+    const int* idx;
+    const float* val;
+    const int* list;
+    const int* count_dev;
+    int list_cap;
+    int gather_stride, addend_stride, out_stride;   // in vectors
+    int nv;                                          // vectors per cell
+};
+
+template <int W>
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads) shpl_pool_heavy_kernel(HeavyArgs a) {
+    using V = typename VecOf<W>::type;
+    extern __shared__ float4 heavy_smem[];
+    V* part = reinterpret_cast<V*>(heavy_smem);        // [kWarps][nv] warp sums
+    V* cta_part = part + kWarps * a.nv;                // [nv] this CTA's sum
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_clusters = gridDim.x / kClusterSize;
+    const int n_heavy = min(__ldg(a.count_dev), a.list_cap);
+    const V* src = static_cast<const V*>(a.gather_in);
+    const V* addend = static_cast<const V*>(a.addend);
+    V* out = static_cast<V*>(a.out);
+    for (int h = blockIdx.x / kClusterSize; h < n_heavy; h += n_clusters) {
+        const int cell = __ldg(a.list + h);
+        const int beg = __ldg(a.ptr + cell), end = __ldg(a.ptr + cell + 1);
+        const long long L = end - beg;
+        const int piece = crank * kWarps + warp;
+        const int pb = beg + (int)(L * piece / (kClusterSize * kWarps));
+        const int pe = beg + (int)(L * (piece + 1) / (kClusterSize * kWarps));
+        for (int q0 = 0; q0 < a.nv; q0 += 64) {
+            V acc[2];
+            acc[0] = vzero((V*)nullptr);
+            acc[1] = vzero((V*)nullptr);
+            for (int c = pb; c < pe; c += 32) {
+                int my_p = 0;
+                float my_w = 0.f;
+                if (c + lane < pe) {
+                    my_p = __ldg(a.idx + c + lane);
+                    my_w = __ldg(a.val + c + lane);
+                }
+                const int cnt = min(32, pe - c);
+                for (int e = 0; e < cnt; e += kGatherUnroll) {
+                    V x[kGatherUnroll][2];
+                    float w[kGatherUnroll];
+#pragma unroll
+                    for (int j = 0; j < kGatherUnroll; ++j) {
+                        const int p = __shfl_sync(kFull, my_p, (e + j) & 31);
+                        w[j] = __shfl_sync(kFull, my_w, (e + j) & 31);
+                        const V* row = src + (size_t)p * a.gather_stride;
+#pragma unroll
+                        for (int b = 0; b < 2; ++b) {
+                            const int q = q0 + b * 32 + lane;
+                            if (e + j < cnt && q < a.nv) x[j][b] = __ldg(row + q);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < kGatherUnroll; ++j) {
+#pragma unroll
+                        for (int b = 0; b < 2; ++b) {
+                            const int q = q0 + b * 32 + lane;
+                            if (e + j < cnt && q < a.nv) axpy(acc[b], w[j], x[j][b]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const int q = q0 + b * 32 + lane;
+                if (q < a.nv) part[warp * a.nv + q] = acc[b];
+            }
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < a.nv; q += kThreads) {
+            V s = part[q];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) s = vadd(s, part[w * a.nv + q]);
+            cta_part[q] = s;
+        }
+        cluster.sync();
+        if (crank == 0) {
+            for (int q = threadIdx.x; q < a.nv; q += kThreads) {
+                V s = cta_part[q];
+                for (int r = 1; r < kClusterSize; ++r) s = vadd(s, *cluster.map_shared_rank(cta_part + q, r));
+                if (addend != nullptr) s = vadd(addend[(size_t)cell * a.addend_stride + q], s);
+                out[(size_t)cell * a.out_stride + q] = s;
+            }
+        }
+        cluster.sync();      // the peers' shared memory stays valid until CTA 0 has read it
     }
 }
 
@@ -576,6 +710,7 @@ struct JobSpec {            // in floats / cells, before the vector width is cho
     int nnz_max = 0;
     int n_cells = 0;
     int add = 0;
+    int heavy_len = 0;
 };
 
 int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* who) {
@@ -614,6 +749,7 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
         o.vs_shift = log2_or_neg(o.vs);
         o.n_cells = j.n_cells;
         o.add = j.add;
+        o.heavy_len = j.heavy_len;
         max_vs = o.vs > max_vs ? o.vs : max_vs;
     }
     if (a.n_jobs == 0) return SHPL_OK;
@@ -673,7 +809,7 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
 }
 
 JobSpec forward_job(const float* dst, const float* src, const int32_t* ptr, const int32_t* key, const int32_t* idx,
-                    const float* val, int nnz_max, int n_rows, int C_d, int C_s, float* fused) {
+                    const float* val, int nnz_max, int heavy_len, int n_rows, int C_d, int C_s, float* fused) {
     JobSpec j;
     j.dense_in = dst;
     j.dense_in_stride = C_d;
@@ -690,6 +826,7 @@ JobSpec forward_job(const float* dst, const float* src, const int32_t* ptr, cons
     j.idx = idx;
     j.val = val;
     j.nnz_max = nnz_max;
+    j.heavy_len = heavy_len;
     j.n_cells = n_rows;
     return j;
 }
@@ -697,20 +834,20 @@ JobSpec forward_job(const float* dst, const float* src, const int32_t* ptr, cons
 }  // namespace
 
 extern "C" int shpl_pool_forward(const float* dst, const float* src, const int32_t* ptr, const int32_t* key,
-                                 const int32_t* idx, const float* val, int32_t nnz_max, int32_t n_rows, int32_t C_d,
-                                 int32_t n_src, int32_t C_s, float* fused, void* stream) {
+                                 const int32_t* idx, const float* val, int32_t nnz_max, int32_t heavy_len,
+                                 int32_t n_rows, int32_t C_d, int32_t n_src, int32_t C_s, float* fused, void* stream) {
     SHPL_REQUIRE(n_rows >= 0 && n_src >= 0 && C_d >= 0 && C_s > 0, SHPL_ERR_INVALID_ARGUMENT,
                  "shpl_pool_forward: bad sizes n_rows=%d n_src=%d C_d=%d C_s=%d", n_rows, n_src, C_d, C_s);
     SHPL_REQUIRE(src && ptr && fused && (C_d == 0 || dst), SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_forward: null pointer");
     SHPL_REQUIRE(idx && val, SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_forward: null idx/val");
     if (n_rows == 0) return SHPL_OK;
-    const JobSpec j = forward_job(dst, src, ptr, key, idx, val, nnz_max, n_rows, C_d, C_s, fused);
+    const JobSpec j = forward_job(dst, src, ptr, key, idx, val, nnz_max, heavy_len, n_rows, C_d, C_s, fused);
     return launch_jobs(&j, 1, static_cast<cudaStream_t>(stream), "shpl_pool_forward");
 }
 
 extern "C" int shpl_pool_backward(const float* g_fused, const int32_t* ptrT, const int32_t* keyT, const int32_t* idxT,
-                                  const float* valT, int32_t nnz_max, int32_t n_rows, int32_t C_d, int32_t n_src,
-                                  int32_t C_s, float* g_dst, float* g_src, void* stream) {
+                                  const float* valT, int32_t nnz_max, int32_t heavy_len, int32_t n_rows, int32_t C_d,
+                                  int32_t n_src, int32_t C_s, float* g_dst, float* g_src, void* stream) {
     SHPL_REQUIRE(n_rows >= 0 && n_src >= 0 && C_d >= 0 && C_s > 0, SHPL_ERR_INVALID_ARGUMENT,
                  "shpl_pool_backward: bad sizes n_rows=%d n_src=%d C_d=%d C_s=%d", n_rows, n_src, C_d, C_s);
     SHPL_REQUIRE(g_fused && ptrT && idxT && valT && g_src, SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_backward: null pointer");
@@ -726,6 +863,7 @@ extern "C" int shpl_pool_backward(const float* g_fused, const int32_t* ptrT, con
     js[0].idx = idxT;
     js[0].val = valT;
     js[0].nnz_max = nnz_max;
+    js[0].heavy_len = heavy_len;
     js[0].n_cells = n_src;
     // job 1: g_dst = g_fused[:, :C_d]
     if (g_dst != nullptr && C_d > 0) {
@@ -742,23 +880,25 @@ extern "C" int shpl_pool_backward(const float* g_fused, const int32_t* ptrT, con
 extern "C" int shpl_pool_forward_dual(const float* bev, const float* img, const int32_t* row_ptr,
                                       const int32_t* csr_row, const int32_t* csr_src, const float* csr_val,
                                       const int32_t* pix_ptr, const int32_t* csrT_pix, const int32_t* csrT_dst,
-                                      const float* csrT_val, int32_t nnz_max, int32_t n_rows, int32_t C_b,
-                                      int32_t n_src, int32_t C_i, float* fused_bev, float* fused_img, void* stream) {
+                                      const float* csrT_val, int32_t nnz_max, int32_t heavy_len, int32_t n_rows,
+                                      int32_t C_b, int32_t n_src, int32_t C_i, float* fused_bev, float* fused_img,
+                                      void* stream) {
     SHPL_REQUIRE(n_rows >= 0 && n_src >= 0 && C_b > 0 && C_i > 0, SHPL_ERR_INVALID_ARGUMENT,
                  "shpl_pool_forward_dual: bad sizes n_rows=%d n_src=%d C_b=%d C_i=%d", n_rows, n_src, C_b, C_i);
     SHPL_REQUIRE(bev && img && row_ptr && csr_src && csr_val && pix_ptr && csrT_dst && csrT_val && fused_bev && fused_img,
                  SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_forward_dual: null pointer");
     JobSpec js[2];
-    js[0] = forward_job(bev, img, row_ptr, csr_row, csr_src, csr_val, nnz_max, n_rows, C_b, C_i, fused_bev);
-    js[1] = forward_job(img, bev, pix_ptr, csrT_pix, csrT_dst, csrT_val, nnz_max, n_src, C_i, C_b, fused_img);
+    js[0] = forward_job(bev, img, row_ptr, csr_row, csr_src, csr_val, nnz_max, heavy_len, n_rows, C_b, C_i, fused_bev);
+    js[1] = forward_job(img, bev, pix_ptr, csrT_pix, csrT_dst, csrT_val, nnz_max, heavy_len, n_src, C_i, C_b, fused_img);
     return launch_jobs(js, 2, static_cast<cudaStream_t>(stream), "shpl_pool_forward_dual");
 }
 
 extern "C" int shpl_pool_backward_dual(const float* g_fused_bev, const float* g_fused_img, const int32_t* row_ptr,
                                        const int32_t* csr_row, const int32_t* csr_src, const float* csr_val,
                                        const int32_t* pix_ptr, const int32_t* csrT_pix, const int32_t* csrT_dst,
-                                       const float* csrT_val, int32_t nnz_max, int32_t n_rows, int32_t C_b,
-                                       int32_t n_src, int32_t C_i, float* g_bev, float* g_img, void* stream) {
+                                       const float* csrT_val, int32_t nnz_max, int32_t heavy_len, int32_t n_rows,
+                                       int32_t C_b, int32_t n_src, int32_t C_i, float* g_bev, float* g_img,
+                                       void* stream) {
     SHPL_REQUIRE(n_rows >= 0 && n_src >= 0 && C_b > 0 && C_i > 0, SHPL_ERR_INVALID_ARGUMENT,
                  "shpl_pool_backward_dual: bad sizes n_rows=%d n_src=%d C_b=%d C_i=%d", n_rows, n_src, C_b, C_i);
     SHPL_REQUIRE(g_fused_bev && g_fused_img && row_ptr && csr_src && csr_val && pix_ptr && csrT_dst && csrT_val &&
@@ -781,6 +921,7 @@ extern "C" int shpl_pool_backward_dual(const float* g_fused_bev, const float* g_
     js[0].nnz_max = nnz_max;
     js[0].n_cells = n_rows;
     js[0].add = 1;
+    js[0].heavy_len = heavy_len;
     // g_img[p] = g_fused_img[p, :C_i] + sum_{k at pixel p} val * g_fused_bev[row_k, C_b:]
     js[1].dense_in = g_fused_img;
     js[1].dense_in_stride = Fi;
@@ -797,5 +938,49 @@ extern "C" int shpl_pool_backward_dual(const float* g_fused_bev, const float* g_
     js[1].nnz_max = nnz_max;
     js[1].n_cells = n_src;
     js[1].add = 1;
+    js[1].heavy_len = heavy_len;
     return launch_jobs(js, 2, static_cast<cudaStream_t>(stream), "shpl_pool_backward_dual");
+}
+
+extern "C" int shpl_pool_heavy(const float* gather_in, int32_t gather_stride, int32_t C, const int32_t* ptr,
+                               const int32_t* idx, const float* val, const int32_t* list, const int32_t* count_dev,
+                               int32_t list_cap, const float* addend, int32_t addend_stride, float* out,
+                               int32_t out_stride, void* stream) {
+    SHPL_REQUIRE(gather_in && ptr && idx && val && list && count_dev && out, SHPL_ERR_INVALID_ARGUMENT,
+                 "shpl_pool_heavy: null pointer");
+    SHPL_REQUIRE(C > 0 && list_cap >= 0, SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_heavy: bad sizes C=%d list_cap=%d", C,
+                 list_cap);
+    if (list_cap == 0) return SHPL_OK;
+    const int w = pick_width({C, gather_stride, addend ? addend_stride : 0, out_stride}, {gather_in, addend, out});
+    HeavyArgs a{};
+    a.gather_in = gather_in;
+    a.addend = addend;
+    a.out = out;
+    a.ptr = ptr;
+    a.idx = idx;
+    a.val = val;
+    a.list = list;
+    a.count_dev = count_dev;
+    a.list_cap = list_cap;
+    a.gather_stride = gather_stride / w;
+    a.addend_stride = addend_stride / w;
+    a.out_stride = out_stride / w;
+    a.nv = C / w;
+    const size_t smem = (size_t)(kWarps + 1) * a.nv * sizeof(float) * w;
+    SHPL_REQUIRE(smem <= 200 * 1024, SHPL_ERR_UNSUPPORTED, "shpl_pool_heavy: C=%d needs %zu bytes of shared memory", C, smem);
+    const int clusters = list_cap < 64 ? list_cap : 64;
+    const unsigned grid = (unsigned)(clusters * kClusterSize);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (w == 4) {
+        if (smem > 48 * 1024) SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_pool_heavy_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        shpl_pool_heavy_kernel<4><<<grid, kThreads, smem, s>>>(a);
+    } else if (w == 2) {
+        if (smem > 48 * 1024) SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_pool_heavy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        shpl_pool_heavy_kernel<2><<<grid, kThreads, smem, s>>>(a);
+    } else {
+        if (smem > 48 * 1024) SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_pool_heavy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        shpl_pool_heavy_kernel<1><<<grid, kThreads, smem, s>>>(a);
+    }
+    shpl::count_launches(1);
+    return shpl::check_launch("shpl_pool_heavy_kernel");
 }

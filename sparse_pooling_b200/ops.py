@@ -66,7 +66,9 @@ class SparsePoolPlan:
 
         def up(x):
             return (x + 3) // 4 * 4
-        sizes = [up(R + 1), up(Q + 1), up(cap), up(cap), up(cap), up(cap), up(8 * self.frames)]
+        self.heavy_cap = cap // _cabi.HEAVY_LEN + 1      # cells that can hold more than HEAVY_LEN of `cap` entries
+        hc = up(self.heavy_cap)
+        sizes = [up(R + 1), up(Q + 1), up(cap), up(cap), up(cap), up(cap), hc, hc, up(8 * self.frames) + 4]
         ints = torch.empty(sum(sizes), dtype=torch.int32, device=device)
         parts, off = [], 0
         for n in sizes:
@@ -75,8 +77,12 @@ class SparsePoolPlan:
         self.row_ptr = parts[0][:R + 1]
         self.pix_ptr = parts[1][:Q + 1]
         self.csr_row, self.csr_src, self.csrT_pix, self.csrT_dst = (p[:cap] for p in parts[2:6])
-        self.counts = parts[6][:8 * self.frames].view(self.frames, 8)
-        self.counts.zero_()
+        self.heavy_row, self.heavy_pix = parts[6][:self.heavy_cap], parts[7][:self.heavy_cap]
+        self._meta = parts[8]                                        # counts of every frame, then the 2 heavy counters
+        self.counts = self._meta[:8 * self.frames].view(self.frames, 8)
+        self.heavy_count = self._meta[up(8 * self.frames):up(8 * self.frames) + 2]
+        self._meta.zero_()
+        self.n_heavy = None   # (rows, pixels) with more than HEAVY_LEN entries; host ints after read_counts
         vals = torch.empty(2 * up(cap), dtype=torch.float32, device=device)
         self.csr_val = vals[:cap]
         self.csrT_val = vals[up(cap):up(cap) + cap]
@@ -94,11 +100,11 @@ class SparsePoolPlan:
 
     def by_row(self):
         """(ptr, key, idx, val, nnz_max) of the CSR keyed by destination BEV cell."""
-        return (self.row_ptr, self.csr_row, self.csr_src, self.csr_val, self.entry_bound)
+        return (self.row_ptr, self.csr_row, self.csr_src, self.csr_val, self.entry_bound, self.heavy(False))
 
     def by_pixel(self):
         """(ptr, key, idx, val, nnz_max) of the CSR^T keyed by source pixel."""
-        return (self.pix_ptr, self.csrT_pix, self.csrT_dst, self.csrT_val, self.entry_bound)
+        return (self.pix_ptr, self.csrT_pix, self.csrT_dst, self.csrT_val, self.entry_bound, self.heavy(True))
 
     def frame_struct(self, f):
         """shpl_plan for frame f: ptr arrays point at the frame's sub-array; entry arrays are shared."""
@@ -114,6 +120,10 @@ class SparsePoolPlan:
         s.csr_val = self.csr_val.data_ptr()
         s.csrT_dst = self.csrT_dst.data_ptr()
         s.csrT_val = self.csrT_val.data_ptr()
+        s.heavy_cap = self.heavy_cap
+        s.heavy_row = self.heavy_row.data_ptr()
+        s.heavy_pix = self.heavy_pix.data_ptr()
+        s.heavy_count = self.heavy_count.data_ptr()
         s.counts = self.counts.data_ptr() + 32 * f
         return s
 
@@ -125,10 +135,19 @@ class SparsePoolPlan:
 
     def read_counts(self):
         """One small device->host copy: fills nnz / n_oob (synchronises the stream)."""
-        c = self.counts.cpu()
+        m = self._meta.cpu()
+        c = m[:8 * self.frames].view(self.frames, 8)
         self.nnz = [int(x) for x in c[:, 1]]
         self.n_oob = [int(x) for x in c[:, 2]]
+        h = m[(8 * self.frames + 3) // 4 * 4:]
+        self.n_heavy = (min(int(h[0]), self.heavy_cap), min(int(h[1]), self.heavy_cap))
         return c
+
+    def heavy(self, by_pixel):
+        """(list, count_dev, how many to expect or None when the counters have not been read back)."""
+        k = 1 if by_pixel else 0
+        return ((self.heavy_pix if by_pixel else self.heavy_row), self.heavy_count[k:k + 1],
+                None if self.n_heavy is None else self.n_heavy[k])
 
 
 def plan_from_coo(indices, values, source_index, n_rows, src_hw, device=None):
@@ -155,27 +174,43 @@ def plan_from_coo(indices, values, source_index, n_rows, src_hw, device=None):
     return plan
 
 
+def _run_heavy(heavy, gather_in, gather_stride, C, ptr, idx, val, addend, addend_stride, out, out_stride):
+    """shpl_pool_heavy on the listed heavy cells, unless the host already knows there are none."""
+    lst, count_dev, expected = heavy
+    if expected == 0:
+        return
+    rc = _lib.shpl_pool_heavy(gather_in, gather_stride, C, _ptr(ptr), _ptr(idx), _ptr(val), _ptr(lst), _ptr(count_dev),
+                              int(lst.numel()), addend, addend_stride, out, out_stride, _stream())
+    _cabi.check(rc, "shpl_pool_heavy")
+
+
+def _off(t, n_floats):
+    return ctypes.c_void_p(t.data_ptr() + 4 * n_floats)
+
+
 def pool_forward(dst, src, csr, n_rows, n_src):
-    """fused[r] = concat(dst[r], sum_k val_k * src[idx_k])  (shpl_pool_forward).
-    csr = (ptr, key, idx, val, nnz_max)."""
-    ptr, key, idx, val, nnz_max = csr
+    """fused[r] = concat(dst[r], sum_k val_k * src[idx_k])  (shpl_pool_forward, then shpl_pool_heavy for
+    cells with more than HEAVY_LEN entries).  csr = (ptr, key, idx, val, nnz_max, heavy)."""
+    ptr, key, idx, val, nnz_max, heavy = csr
     require_cuda(src, "source feature map")
     C_s = src.shape[-1]
     C_d = 0 if dst is None else dst.shape[-1]
     fused = torch.empty((n_rows, C_d + C_s), dtype=torch.float32, device=src.device)
     rc = _lib.shpl_pool_forward(_ptr(dst), _ptr(src), _ptr(ptr), _ptr(key), _ptr(idx), _ptr(val), int(nnz_max),
-                                n_rows, C_d, n_src, C_s, _ptr(fused), _stream())
+                                _cabi.HEAVY_LEN, n_rows, C_d, n_src, C_s, _ptr(fused), _stream())
     _cabi.check(rc, "shpl_pool_forward")
+    _run_heavy(heavy, _ptr(src), C_s, C_s, ptr, idx, val, None, 0, _off(fused, C_d), C_d + C_s)
     return fused
 
 
 def pool_backward(g_fused, csrT, n_rows, C_d, n_src, C_s, want_dst=True):
-    ptrT, keyT, idxT, valT, nnz_max = csrT
+    ptrT, keyT, idxT, valT, nnz_max, heavy = csrT
     g_dst = torch.empty((n_rows, C_d), dtype=torch.float32, device=g_fused.device) if (want_dst and C_d) else None
     g_src = torch.empty((n_src, C_s), dtype=torch.float32, device=g_fused.device)
     rc = _lib.shpl_pool_backward(_ptr(g_fused), _ptr(ptrT), _ptr(keyT), _ptr(idxT), _ptr(valT), int(nnz_max),
-                                 n_rows, C_d, n_src, C_s, _ptr(g_dst), _ptr(g_src), _stream())
+                                 _cabi.HEAVY_LEN, n_rows, C_d, n_src, C_s, _ptr(g_dst), _ptr(g_src), _stream())
     _cabi.check(rc, "shpl_pool_backward")
+    _run_heavy(heavy, _off(g_fused, C_d), C_d + C_s, C_s, ptrT, idxT, valT, None, 0, _ptr(g_src), C_s)
     return g_dst, g_src
 
 
@@ -258,9 +293,13 @@ class SparsePoolDualFunction(torch.autograd.Function):
                              % (tuple(bev.shape), tuple(img.shape), R, Q))
         fused_bev = torch.empty(tuple(bev.shape[:3]) + (Cb + Ci,), dtype=torch.float32, device=bev.device)
         fused_img = torch.empty(tuple(img.shape[:3]) + (Ci + Cb,), dtype=torch.float32, device=bev.device)
-        rc = _lib.shpl_pool_forward_dual(_ptr(b), _ptr(i), *_plan_ptrs(plan), int(plan.entry_bound), R, Cb, Q, Ci,
-                                         _ptr(fused_bev), _ptr(fused_img), _stream())
+        rc = _lib.shpl_pool_forward_dual(_ptr(b), _ptr(i), *_plan_ptrs(plan), int(plan.entry_bound), _cabi.HEAVY_LEN,
+                                         R, Cb, Q, Ci, _ptr(fused_bev), _ptr(fused_img), _stream())
         _cabi.check(rc, "shpl_pool_forward_dual")
+        _run_heavy(plan.heavy(False), _ptr(i), Ci, Ci, plan.row_ptr, plan.csr_src, plan.csr_val, None, 0,
+                   _off(fused_bev, Cb), Cb + Ci)
+        _run_heavy(plan.heavy(True), _ptr(b), Cb, Cb, plan.pix_ptr, plan.csrT_dst, plan.csrT_val, None, 0,
+                   _off(fused_img, Ci), Ci + Cb)
         ctx.plan = plan
         ctx.shapes = (tuple(bev.shape), tuple(img.shape))
         return fused_bev, fused_img
@@ -274,9 +313,14 @@ class SparsePoolDualFunction(torch.autograd.Function):
         gi = g_fused_img.contiguous()
         g_bev = torch.empty(sb, dtype=torch.float32, device=gb.device)
         g_img = torch.empty(si, dtype=torch.float32, device=gb.device)
-        rc = _lib.shpl_pool_backward_dual(_ptr(gb), _ptr(gi), *_plan_ptrs(plan), int(plan.entry_bound), R, Cb, Q, Ci,
-                                          _ptr(g_bev), _ptr(g_img), _stream())
+        rc = _lib.shpl_pool_backward_dual(_ptr(gb), _ptr(gi), *_plan_ptrs(plan), int(plan.entry_bound), _cabi.HEAVY_LEN,
+                                          R, Cb, Q, Ci, _ptr(g_bev), _ptr(g_img), _stream())
         _cabi.check(rc, "shpl_pool_backward_dual")
+        # g_bev[r] = g_fused_bev[r,:Cb] + sum_{k in row r} val * g_fused_img[pix_k, Ci:]   (heavy rows)
+        _run_heavy(plan.heavy(False), _off(gi, Ci), Ci + Cb, Cb, plan.row_ptr, plan.csr_src, plan.csr_val,
+                   _ptr(gb), Cb + Ci, _ptr(g_bev), Cb)
+        _run_heavy(plan.heavy(True), _off(gb, Cb), Cb + Ci, Ci, plan.pix_ptr, plan.csrT_dst, plan.csrT_val,
+                   _ptr(gi), Ci + Cb, _ptr(g_img), Ci)
         return g_bev, g_img, None
 
 

@@ -68,6 +68,7 @@ class _LayerState:
         f32 = dict(dtype=torch.float32, device=device)
         self.plan = SparsePoolPlan(spec.R, spec.img_hw, n_max, device)
         self.plan_struct = self.plan.frame_struct(0)
+        self.plan_struct.heavy_cap = 0      # lean path: every cell summed sequentially in the main kernels (heavy_len = 0)
         need = int(_lib.shpl_build_workspace_bytes(int(n_max)))
         self.ws = torch.empty(need, dtype=torch.uint8, device=device)     # own scratch: layers build concurrently
         self.fused_bev = torch.empty((1,) + spec.bev_hw + (spec.c_bev + spec.c_img,), **f32)
@@ -113,12 +114,12 @@ class FramePipeline:
         s, pl = L.spec, L.plan
         bound = int(nnz_max) if nnz_max else pl.capacity
         if s.dual:
-            rc = _lib.shpl_pool_forward_dual(_p(bev), _p(img), *L.plan_ptrs, bound, s.R, s.c_bev, s.Q, s.c_img,
+            rc = _lib.shpl_pool_forward_dual(_p(bev), _p(img), *L.plan_ptrs, bound, 0, s.R, s.c_bev, s.Q, s.c_img,
                                              _p(L.fused_bev), _p(L.fused_img), stream)
             _cabi.check(rc, "shpl_pool_forward_dual")
             return
         rc = _lib.shpl_pool_forward(_p(bev), _p(img), _p(pl.row_ptr), _p(pl.csr_row), _p(pl.csr_src), _p(pl.csr_val),
-                                    bound, s.R, s.c_bev, s.Q, s.c_img, _p(L.fused_bev), stream)
+                                    bound, 0, s.R, s.c_bev, s.Q, s.c_img, _p(L.fused_bev), stream)
         _cabi.check(rc, "shpl_pool_forward")
 
     # -- backward of layer i from the upstream gradients of the fused maps --
@@ -127,10 +128,10 @@ class FramePipeline:
         s, pl = L.spec, L.plan
         bound = int(nnz_max) if nnz_max else pl.capacity
         if s.dual:   # AddN of the two partial gradients of each input formed in the kernel
-            rc = _lib.shpl_pool_backward_dual(_p(g_fused_bev), _p(g_fused_img), *L.plan_ptrs, bound, s.R, s.c_bev,
+            rc = _lib.shpl_pool_backward_dual(_p(g_fused_bev), _p(g_fused_img), *L.plan_ptrs, bound, 0, s.R, s.c_bev,
                                               s.Q, s.c_img, _p(L.g_bev), _p(L.g_img), stream)
             _cabi.check(rc, "shpl_pool_backward_dual")
             return
         rc = _lib.shpl_pool_backward(_p(g_fused_bev), _p(pl.pix_ptr), _p(pl.csrT_pix), _p(pl.csrT_dst), _p(pl.csrT_val),
-                                     bound, s.R, s.c_bev, s.Q, s.c_img, _p(L.g_bev), _p(L.g_img), stream)
+                                     bound, 0, s.R, s.c_bev, s.Q, s.c_img, _p(L.g_bev), _p(L.g_img), stream)
         _cabi.check(rc, "shpl_pool_backward")

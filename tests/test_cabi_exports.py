@@ -29,7 +29,7 @@ def test_header_declares_the_expected_entry_points():
     assert declared_functions() == sorted([
         "shpl_abi_version", "shpl_last_error", "shpl_kernel_launches", "shpl_build_workspace_bytes", "shpl_gen_input_avod",
         "shpl_produce_input", "shpl_build_avod", "shpl_plan_from_coo", "shpl_pool_forward", "shpl_pool_backward",
-        "shpl_pool_forward_dual", "shpl_pool_backward_dual"])
+        "shpl_pool_forward_dual", "shpl_pool_backward_dual", "shpl_pool_heavy"])
 
 
 def test_library_exports_every_declared_symbol(lib):
@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_binding_covers_the_header(lib):
     from sparse_pooling_b200 import _cabi
     assert sorted(_cabi.SIGNATURES) == declared_functions()
-    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 2
+    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 3
 
 
 def test_workspace_query_grows_with_n(lib):
@@ -53,11 +53,11 @@ def test_workspace_query_grows_with_n(lib):
 def test_invalid_arguments_return_error_codes_without_a_gpu(lib):
     from sparse_pooling_b200 import _cabi
     L = _cabi.lib
-    assert L.shpl_pool_forward(None, None, None, None, None, None, 0, 10, 4, 10, 0, None, None) == _cabi.SHPL_ERR_INVALID_ARGUMENT
+    assert L.shpl_pool_forward(None, None, None, None, None, None, 0, 0, 10, 4, 10, 0, None, None) == _cabi.SHPL_ERR_INVALID_ARGUMENT
     assert b"bad sizes" in L.shpl_last_error()
-    assert L.shpl_pool_backward(None, None, None, None, None, 0, 10, 4, 10, 4, None, None, None) == _cabi.SHPL_ERR_INVALID_ARGUMENT
+    assert L.shpl_pool_backward(None, None, None, None, None, 0, 0, 10, 4, 10, 4, None, None, None) == _cabi.SHPL_ERR_INVALID_ARGUMENT
     with pytest.raises(ValueError):
-        _cabi.check(L.shpl_pool_forward(None, None, None, None, None, None, 0, -1, 4, 10, 4, None, None), "shpl_pool_forward")
+        _cabi.check(L.shpl_pool_forward(None, None, None, None, None, None, 0, 0, -1, 4, 10, 4, None, None), "shpl_pool_forward")
     st = _cabi.ShplPlan()
     rc = L.shpl_produce_input(None, None, None, 0, 8, 8, 8, 8, 0, 1, None, 0, 0, None, None, None, None,
                               ctypes.byref(st), 0, 0, None, None, 0, None)

@@ -73,14 +73,10 @@ def case(name, bev_hw, img_hw, C, n_pairs, skew, stride=(1, 1), weights=False, p
     P = ops._ptr
 
     def fwd():
-        rc = lib.shpl_pool_forward(P(bev), P(img), P(plan.row_ptr), P(plan.csr_row), P(plan.csr_src), P(plan.csr_val),
-                                   plan.entry_bound, R, C, Q, C, P(fused), ops._stream())
-        assert rc == 0
+        ops.pool_forward(bev, img, plan.by_row(), R, Q)
 
     def bwd():
-        rc = lib.shpl_pool_backward(P(g), P(plan.pix_ptr), P(plan.csrT_pix), P(plan.csrT_dst), P(plan.csrT_val),
-                                    plan.entry_bound, R, C, Q, C, P(g_dst), P(g_src), ops._stream())
-        assert rc == 0
+        ops.pool_backward(g, plan.by_pixel(), R, C, Q, C)
 
     tf, tb = timeit(fwd), timeit(bwd)
     bf = 4 * (R * C + R * 2 * C + nnz * (C + 2) + R + 1)
