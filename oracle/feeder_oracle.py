@@ -1,0 +1,101 @@
+"""Feeder oracle: CPU restatement (numpy) of the avod BEV slicing / voxelisation step that
+produces the SHPL builder's inputs (rows a1/a2).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Follows
+
+  * BevSlices.generate_bev(..., output_indices=True)
+        /root/reference/avod/avod/core/bev_generators/bev_slices.py:33-156
+  * BevGenerator._create_density_map
+        /root/reference/avod/avod/core/bev_generators/bev_generator.py:23-41
+  * VoxelGrid2D.voxelize_2d
+        /root/reference/avod/wavedata/wavedata/tools/core/voxel_grid_2d.py:43-162
+  * KittiUtils.create_slice_filter   /root/reference/avod/avod/datasets/kitti/kitti_utils.py:79-107
+  * obj_utils.get_point_filter       /root/reference/avod/wavedata/wavedata/tools/obj_detection/obj_utils.py:444-491
+  * geometry_utils.dist_to_plane     /root/reference/avod/wavedata/wavedata/tools/core/geometry_utils.py:25-40
+
+Pinned against the reference's own output (tests/golden/bev_slices_seed*.npz, made by
+oracle/gen_goldens.py, which imports those files where they lie).
+"""
+import numpy as np
+
+
+def point_filter(point_cloud, extents, ground_plane, offset_dist):
+    """obj_utils.py:444-491: strict extents, and below the plane shifted up by offset_dist."""
+    pc = np.asarray(point_cloud)
+    inside = ((pc[0] > extents[0][0]) & (pc[0] < extents[0][1]) & (pc[1] > extents[1][0]) & (pc[1] < extents[1][1])
+              & (pc[2] > extents[2][0]) & (pc[2] < extents[2][1]))
+    plane = np.array(ground_plane) + [0, 0, 0, -offset_dist]                     # :479
+    hom = np.vstack([pc, np.ones(pc.shape[1])])
+    return inside & (np.dot(plane, hom) < 0)                                     # :482-486
+
+
+def slice_filter(point_cloud, extents, ground_plane, lo, hi):
+    """kitti_utils.py:97-107: between the planes at lo and hi above the ground."""
+    return np.logical_xor(point_filter(point_cloud, extents, ground_plane, hi),
+                          point_filter(point_cloud, extents, ground_plane, lo))
+
+
+def grid_geometry(extents, voxel_size):
+    """voxel_grid_2d.py:119-149: min/max voxel coordinate and divisions from the extents."""
+    ext = np.array(extents).transpose()
+    lo = np.floor(ext[0] / voxel_size)
+    hi = np.ceil((ext[1] / voxel_size) - 1)
+    lo[1] = 0
+    hi[1] = 0
+    return lo, hi, ((hi - lo) + 1).astype(np.int32)
+
+
+def voxelize_2d(pts, voxel_size, extents, ground_plane):
+    """voxel_grid_2d.py:59-152.  Returns (voxel_indices int [m,3], unique_pts f64 [m,3],
+    heights f64 [m], num_pts int [m], num_divisions int32 [3])."""
+    disc = np.floor(pts / voxel_size).astype(np.int32)                           # :67
+    order = np.lexsort((disc[:, 1], disc[:, 2], disc[:, 0]))                     # :70-73 x, then z, then y
+    spts, sdisc = pts[order], disc[order]
+    first = np.ones(len(spts), dtype=bool)
+    if len(spts) > 1:
+        first[1:] = (sdisc[1:, 0] != sdisc[:-1, 0]) | (sdisc[1:, 2] != sdisc[:-1, 2])   # :86-94 unique on (x, 0, z)
+    starts = np.nonzero(first)[0]
+    coords = sdisc[starts].copy()
+    coords[:, 1] = 0
+    unique_pts = spts[starts]                                                    # :97-98
+    num_pts = np.diff(np.r_[starts, len(spts)])                                  # :101-104
+    a, b, c, d = ground_plane
+    heights = (a * unique_pts[:, 0] + b * unique_pts[:, 1] + c * unique_pts[:, 2] + d) / np.sqrt(a ** 2 + b ** 2 + c ** 2)
+    lo, hi, ndiv = grid_geometry(extents, voxel_size)
+    if not (lo <= np.amin(coords, axis=0)).all() or not (hi >= np.amax(coords, axis=0)).all():
+        raise ValueError("Extents are smaller than the voxel coordinates")       # :133-138
+    return (coords - lo).astype(int), unique_pts, heights, num_pts, ndiv         # :152
+
+
+def generate_bev(point_cloud, ground_plane, area_extents, voxel_size, height_lo, height_hi, num_slices,
+                 norm_value=np.log(16)):
+    """bev_slices.py:33-156 with output_indices=True.  point_cloud f64 [3,P].
+    Returns (height_maps list of [Z,X] f64, density_map [Z,X] f64, voxel_indices int [N,2], unique_pts f64 [N,3])."""
+    all_points = np.transpose(point_cloud)
+    hpd = (height_hi - height_lo) / num_slices                                   # :29-31
+    height_maps, idx_stack, pts_stack = [], [], []
+    grid = None
+    for s in range(num_slices):
+        lo = height_lo + s * hpd                                                 # :66-67
+        hi = lo + hpd
+        pts = all_points[slice_filter(point_cloud, area_extents, ground_plane, lo, hi)]
+        if len(pts) > 1:                                                         # :79
+            vi, upts, heights, _, ndiv = voxelize_2d(pts, voxel_size, area_extents, ground_plane)
+            grid = dict(vi=vi[:, [0, 2]], upts=upts, heights=heights, ndiv=ndiv)
+        elif grid is None:
+            raise NameError("voxel_grid_2d")                                     # quirk A.4-7: first slice empty
+        hm = np.zeros((grid["ndiv"][0], grid["ndiv"][2]))
+        grid["heights"] = grid["heights"] - lo                                   # :100 (compounds when a grid is reused)
+        hm[grid["vi"][:, 0], grid["vi"][:, 1]] = np.asarray(grid["heights"]) / hpd
+        height_maps.append(hm)
+        rot = np.copy(grid["vi"])
+        rot[:, 1] = grid["ndiv"][2] - rot[:, 1]                                  # :106-108
+        idx_stack.append(rot)
+        pts_stack.append(grid["upts"])
+    height_maps = [np.flip(h.transpose(), axis=0) for h in height_maps]          # :116-118
+    dens_pts = all_points[slice_filter(point_cloud, area_extents, ground_plane, height_lo, height_hi)]
+    vi, _, _, num_pts, ndiv = voxelize_2d(dens_pts, voxel_size, area_extents, ground_plane)
+    dm = np.zeros((ndiv[0], ndiv[2]))
+    dm[vi[:, 0], vi[:, 2]] = np.minimum(1.0, np.log(num_pts + 1) / norm_value)   # bev_generator.py:35-36
+    dm = np.flip(dm.transpose(), axis=0)
+    return height_maps, dm, np.vstack(idx_stack), np.vstack(pts_stack)

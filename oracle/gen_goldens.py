@@ -173,5 +173,36 @@ def main():
         raise
 
 
+def feeder_goldens():
+    """BevSlices.generate_bev(output_indices=True) of the reference on the synthetic scan."""
+    import_avod()
+    from avod.core.bev_generators.bev_slices import BevSlices
+    from wavedata.tools.obj_detection import obj_utils
+
+    class KU:   # the two calls of KittiUtils.create_slice_filter (kitti_utils.py:97-107)
+        def create_slice_filter(self, pc, ext, gp, lo, hi):
+            return np.logical_xor(obj_utils.get_point_filter(pc, ext, gp, hi), obj_utils.get_point_filter(pc, ext, gp, lo))
+
+    cfg = types.SimpleNamespace(height_lo=-0.2, height_hi=2.3, num_slices=5)
+    for seed, az in ((1, 0.09), (2, 0.05)):
+        pts = synth.lidar_scan(seed, az_step_deg=az)
+        gp = np.array([0.0, -1.0, 0.0, 1.65])
+        maps, idx, upts = BevSlices(cfg, KU()).generate_bev("lidar", pts.T, gp, synth.AVOD_EXTENTS, synth.AVOD_VOXEL,
+                                                            output_indices=True)
+        rec = dict(input_sha=digest(pts), n_points=len(pts), voxel_indices=idx.astype(np.int32), unique_pts=upts)
+        for i, hm in enumerate(maps["height_maps"]):
+            nz = np.nonzero(hm)
+            rec["hm%d_idx" % i] = np.stack(nz, axis=1).astype(np.int32)
+            rec["hm%d_val" % i] = hm[nz]
+            assert hm.shape == (700, 800) and hm.dtype == np.float64
+        dm = maps["density_map"]
+        nz = np.nonzero(dm)
+        rec["dm_idx"] = np.stack(nz, axis=1).astype(np.int32)
+        rec["dm_val"] = dm[nz]
+        np.savez_compressed(os.path.join(OUT, "bev_slices_seed%d.npz" % seed), **rec)
+        print("bev_slices seed", seed, "points", len(pts), "pairs", len(idx))
+
+
 if __name__ == "__main__":
     main()
+    feeder_goldens()

@@ -234,3 +234,29 @@ def test_value_oracle_rejects_out_of_range_like_tf_cpu():
         vo.gather_nd(x, np.array([[0, 4, 0]]))
     with pytest.raises(IndexError):
         vo.spmm(np.array([[9, 0]]), np.ones(1), [4, 1], np.zeros((1, 2), np.float32))
+
+
+# ------------------------------------------------------------ feeder
+@pytest.mark.parametrize("seed,az", [(1, 0.09), (2, 0.05)])
+def test_feeder_oracle_matches_reference_bev_slices(golden_dir, seed, az):
+    """oracle/feeder_oracle.py against BevSlices.generate_bev(output_indices=True) of the reference."""
+    from oracle import feeder_oracle as fo
+    g = load(golden_dir, "bev_slices_seed%d.npz" % seed)
+    pts = synth.lidar_scan(seed, az_step_deg=az)
+    assert digest(pts) == str(g["input_sha"])
+    hms, dm, idx, upts = fo.generate_bev(pts.T, np.array([0.0, -1.0, 0.0, 1.65]), synth.AVOD_EXTENTS, synth.AVOD_VOXEL,
+                                         -0.2, 2.3, 5)
+    np.testing.assert_array_equal(idx, g["voxel_indices"])
+    np.testing.assert_array_equal(upts, g["unique_pts"])
+    for i, hm in enumerate(hms):
+        assert hm.shape == (700, 800)
+        nz = np.nonzero(hm)
+        np.testing.assert_array_equal(np.stack(nz, axis=1), g["hm%d_idx" % i])
+        np.testing.assert_array_equal(hm[nz], g["hm%d_val" % i])
+    nz = np.nonzero(dm)
+    np.testing.assert_array_equal(np.stack(nz, axis=1), g["dm_idx"])
+    np.testing.assert_array_equal(dm[nz], g["dm_val"])
+    # the stand-in the other fixtures use (synth.one_point_per_cell) is the same feeder for this scan
+    p2, i2 = synth.one_point_per_cell(pts)
+    np.testing.assert_array_equal(i2, idx)
+    np.testing.assert_array_equal(p2, upts)
