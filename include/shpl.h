@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SHPL_ABI_VERSION 3
+#define SHPL_ABI_VERSION 4
 
 /* Cells with more entries than this are "heavy": the builder lists them in the plan and their sum
  * is formed by shpl_pool_heavy (a thread-block cluster per cell, fixed summation tree) instead of
@@ -86,11 +86,13 @@ size_t shpl_build_workspace_bytes(int64_t n_max);
  * projectToImage / clip3DwithinImage (avod/avod/utils/transform.py:3-40) inlined.
  *   points f64 [N,3] camera frame, voxel_indices i64 [N,2] = (x, zflip),
  *   P_host f64 [12] = stereo_calib.p2 row-major, image size (W, H) in pixels.
+ *   N_dev (device int32*, may be NULL): when given, only the first min(N, *N_dev) candidates exist --
+ *   lets the feeder's device-side pair count (shpl_bev_slices counts[0]) flow in without a host read.
  * Writes the n surviving pairs, input order kept:
  *   bv_index_out i64 [N,2] (first n rows), img_u_out / img_v_out f64 [N] (first n;
  *   rows 0 and 1 of the reference's [3,n] img_index; row 2 is all zero),
  *   counts[0] = n. */
-int shpl_gen_input_avod(const double* points, const int64_t* voxel_indices, int64_t N,
+int shpl_gen_input_avod(const double* points, const int64_t* voxel_indices, int64_t N, const int32_t* N_dev,
                         const double* P_host, int32_t im_w, int32_t im_h,
                         int64_t* bv_index_out, double* img_u_out, double* img_v_out,
                         int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
@@ -124,7 +126,7 @@ int shpl_produce_input(double* img_u, double* img_v, const int64_t* bv_index, in
 
 /* The two functions above fused (the call kitti_dataset.py:376-378 makes per
  * sample): no intermediate dict is materialised. */
-int shpl_build_avod(const double* points, const int64_t* voxel_indices, int64_t N,
+int shpl_build_avod(const double* points, const int64_t* voxel_indices, int64_t N, const int32_t* N_dev,
                     const double* P_host, int32_t im_w, int32_t im_h, int32_t bv_h, int32_t bv_w,
                     int32_t stride_img, int32_t stride_bv, const double* m_val,
                     int32_t src_h, int32_t src_w,
@@ -210,6 +212,52 @@ int shpl_pool_heavy(const float* gather_in, int32_t gather_stride, int32_t C,
                     const int32_t* list, const int32_t* count_dev, int32_t list_cap,
                     const float* addend, int32_t addend_stride,
                     float* out, int32_t out_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Feeder: BEV slicing / voxelisation.  Replaces
+ *   BevSlices.generate_bev(..., output_indices=True)   avod/avod/core/bev_generators/bev_slices.py:33-156
+ *   VoxelGrid2D.voxelize_2d                             avod/wavedata/wavedata/tools/core/voxel_grid_2d.py:43-162
+ *   KittiUtils.create_slice_filter                      avod/avod/datasets/kitti/kitti_utils.py:79-107
+ *   obj_utils.get_point_filter                          avod/wavedata/wavedata/tools/obj_detection/obj_utils.py:444-491
+ *   BevGenerator._create_density_map                    avod/avod/core/bev_generators/bev_generator.py:23-41
+ * whose outputs (voxel_indices, unique_pts) are the inputs of shpl_build_avod. */
+#define SHPL_BEV_MAX_SLICES 8
+#define SHPL_BEV_COUNTS 32
+/* bits of counts[1]: conditions under which the reference raises */
+#define SHPL_BEV_ERR_FIRST_SLICE_EMPTY 1 /* first slice has <= 1 point: NameError (bev_slices.py:79,93)    */
+#define SHPL_BEV_ERR_EXTENTS 2           /* a voxel coordinate outside the extents: ValueError (voxel_grid_2d.py:133-138) */
+#define SHPL_BEV_ERR_CAPACITY 4          /* more (slice, cell) pairs than `capacity` (not a reference condition) */
+#define SHPL_BEV_ERR_NO_POINTS 8         /* no point in the density band: voxelize_2d of nothing raises     */
+
+/* Grid the extents imply: nx = num_divisions[0] (800 at KITTI), nz = num_divisions[2] (700)
+ * (voxel_grid_2d.py:126-149).  extents_host f64 [6] = x_lo, x_hi, y_lo, y_hi, z_lo, z_hi. */
+int shpl_bev_grid_dims(const double* extents_host, double voxel_size, int32_t* nx, int32_t* nz);
+
+/* Scratch shpl_bev_slices needs (0 on invalid arguments). */
+size_t shpl_bev_workspace_bytes(const double* extents_host, double voxel_size, int32_t num_slices);
+
+/* generate_bev(output_indices=True).
+ *   points f64: coordinate c of point i at points[c*coord_stride + i*point_stride] -- the reference's
+ *   point_cloud [3,P] is (coord_stride=P, point_stride=1), an [P,3] array (1, 3);
+ *   ground_plane_host f64 [4]; extents_host f64 [6]; slices of (height_hi-height_lo)/num_slices above the plane;
+ *   log_norm = NORM_VALUES[source] (log 16 for lidar, bev_slices.py:12-14);
+ *   density_lut (DEVICE f64 [lut_len], may be NULL): the density value of a cell holding n points for
+ *   n < lut_len, 1.0 beyond -- lets the host tabulate min(1, log(n+1)/log_norm) with the reference's own
+ *   libm so the map is bit-identical; with NULL the kernel evaluates the formula (CUDA log, <= 1 ulp).
+ * Outputs, in the reference's order (slice, then x, then z ascending):
+ *   voxel_indices_out i64 [capacity,2] = (x, nz - z)  (the reference's flipped row index, :106-108),
+ *   unique_pts_out f64 [capacity,3] = first point of each cell in the lexsort (x, z, y) order (:97-98),
+ *   bev_maps_out f64 [num_slices+1, nz, nx] (may be NULL): the height maps (:116-118) then the density map,
+ *   counts i32 [SHPL_BEV_COUNTS] (device): [0] = number of pairs N, [1] = SHPL_BEV_ERR_* bits,
+ *   [2] = points in the density band, [8+s] = output offset where slice s starts, [16+s] = points in slice s.
+ * A slice with <= 1 point repeats the previous slice's cells and compounds its heights, like the
+ * reference does (:79-112). */
+int shpl_bev_slices(const double* points, int64_t coord_stride, int64_t point_stride, int64_t P,
+                    const double* ground_plane_host, const double* extents_host, double voxel_size,
+                    double height_lo, double height_hi, int32_t num_slices, double log_norm,
+                    const double* density_lut, int32_t lut_len,
+                    int64_t* voxel_indices_out, double* unique_pts_out, int64_t capacity,
+                    double* bev_maps_out, int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

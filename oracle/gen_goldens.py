@@ -184,8 +184,8 @@ def feeder_goldens():
             return np.logical_xor(obj_utils.get_point_filter(pc, ext, gp, hi), obj_utils.get_point_filter(pc, ext, gp, lo))
 
     cfg = types.SimpleNamespace(height_lo=-0.2, height_hi=2.3, num_slices=5)
-    for seed, az in ((1, 0.09), (2, 0.05)):
-        pts = synth.lidar_scan(seed, az_step_deg=az)
+    for seed, az in ((1, 0.09), (2, 0.05), (3, None)):
+        pts = synth.lidar_scan_gappy(seed) if az is None else synth.lidar_scan(seed, az_step_deg=az)
         gp = np.array([0.0, -1.0, 0.0, 1.65])
         maps, idx, upts = BevSlices(cfg, KU()).generate_bev("lidar", pts.T, gp, synth.AVOD_EXTENTS, synth.AVOD_VOXEL,
                                                             output_indices=True)
@@ -201,6 +201,10 @@ def feeder_goldens():
         rec["dm_val"] = dm[nz]
         np.savez_compressed(os.path.join(OUT, "bev_slices_seed%d.npz" % seed), **rec)
         print("bev_slices seed", seed, "points", len(pts), "pairs", len(idx))
+        if az is None:      # the fixture must exercise the re-use quirk
+            n_in = [int(KU().create_slice_filter(pts.T, synth.AVOD_EXTENTS, gp, -0.2 + i * 0.5, -0.2 + (i + 1) * 0.5).sum())
+                    for i in range(5)]
+            assert n_in[2] == 1 and n_in[4] == 0 and min(n_in[0], n_in[1], n_in[3]) > 1, n_in
 
 
 if __name__ == "__main__":

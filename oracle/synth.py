@@ -57,6 +57,20 @@ def lidar_scan(seed, az_step_deg=0.09, n_beams=64, obstacle_p=0.35):
     return np.ascontiguousarray(pts[keep])
 
 
+def lidar_scan_gappy(seed, az_step_deg=0.3):
+    """lidar_scan with two height slices (of the 5 avod slices, -0.2..2.3 m) thinned out: slice 2 keeps exactly
+    one point and slice 4 none, so BevSlices re-uses the previous slice's grid there."""
+    pts = lidar_scan(seed, az_step_deg=az_step_deg)
+    h = 1.65 - pts[:, 1]
+    in2 = (h > 0.75) & (h < 1.35)
+    in4 = (h > 1.75) & (h < 2.35)
+    keep = ~(in2 | in4)
+    one = np.nonzero((h > 0.9) & (h < 1.2))[0]
+    if one.size:
+        keep[one[0]] = True
+    return np.ascontiguousarray(pts[keep])
+
+
 def one_point_per_cell(points, n_slices=5, h_lo=-0.2, h_hi=2.3, ground_y=1.65):
     """A light stand-in for the avod feeder (BevSlices + VoxelGrid2D):
     per height slice, the first point (in x,z,y lexicographic cell order) of every

@@ -7,6 +7,7 @@ Layout (only what the hot path needs):
   ops.py               CSR plan, workspace, autograd op around the pooling kernels
   sparse_pool_utils.py drop-in mirror of the reference module (same names / signatures)
   builder.py           batched device-resident correspondence builder
+  bev_slices.py        drop-in mirror of the BEV slicing feeder (BevSlices.generate_bev)
   config.py            the model.proto / kitti_dataset.proto sparse-pooling switches
 """
 from . import _cabi  # noqa: F401  (raises ImportError when libshpl.so is missing)
@@ -17,3 +18,4 @@ from .sparse_pool_utils import (SparsePoolLayer, SparseTensor, _sparse_pool_op, 
                                 concat_bn_op, gen_sparse_pooling_input_avod, produce_sparse_pooling_input,
                                 sparse_pool_layer)
 from .builder import build_avod_plan  # noqa: F401
+from .bev_slices import BevSlices  # noqa: F401

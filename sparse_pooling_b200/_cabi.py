@@ -22,7 +22,7 @@ SHPL_ERR_CUDA = -2
 SHPL_ERR_WORKSPACE_TOO_SMALL = -3
 SHPL_ERR_UNSUPPORTED = -4
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 HEAVY_LEN = 2048          # SHPL_HEAVY_LEN of include/shpl.h
 
 
@@ -54,7 +54,7 @@ SIGNATURES = {
     "shpl_last_error": (ctypes.c_char_p, []),
     "shpl_kernel_launches": (ctypes.c_uint64, []),
     "shpl_build_workspace_bytes": (c_size_t, [c_int64]),
-    "shpl_gen_input_avod": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32, c_int32,
+    "shpl_gen_input_avod": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32,
                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "shpl_produce_input": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64,
                                           c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
@@ -62,7 +62,7 @@ SIGNATURES = {
                                           c_void_p, c_void_p, c_void_p, c_void_p,
                                           ctypes.POINTER(ShplPlan), c_int32, c_int32, c_void_p,
                                           c_void_p, c_size_t, c_void_p]),
-    "shpl_build_avod": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p,
+    "shpl_build_avod": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                                        c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                        c_int32, c_int32,
                                        c_void_p, c_void_p, c_void_p, c_void_p,
@@ -78,6 +78,11 @@ SIGNATURES = {
                                           c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "shpl_pool_forward_dual": (ctypes.c_int, [c_void_p] * 10 + [c_int32] * 6 + [c_void_p] * 3),
     "shpl_pool_backward_dual": (ctypes.c_int, [c_void_p] * 10 + [c_int32] * 6 + [c_void_p] * 3),
+    "shpl_bev_grid_dims": (ctypes.c_int, [c_void_p, ctypes.c_double, c_void_p, c_void_p]),
+    "shpl_bev_workspace_bytes": (c_size_t, [c_void_p, ctypes.c_double, c_int32]),
+    "shpl_bev_slices": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, ctypes.c_double,
+                                       ctypes.c_double, ctypes.c_double, c_int32, ctypes.c_double, c_void_p, c_int32,
+                                       c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "shpl_pool_heavy": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p]),
 }

@@ -80,7 +80,7 @@ def build_avod_plan(points, voxel_indices, P, im_size, bv_size, stride=(1, 1), s
         else:
             Mij = flip = val = msize = None
         st = plan.frame_struct(f)
-        rc = _lib.shpl_build_avod(_ptr(pts[f]), _ptr(vox[f]), N, Pf.ctypes.data_as(ctypes.c_void_p),
+        rc = _lib.shpl_build_avod(_ptr(pts[f]), _ptr(vox[f]), N, None, Pf.ctypes.data_as(ctypes.c_void_p),
                                   im_w, im_h, bv_h, bv_w, s_img, s_bv, _ptr(mv), int(src_hw[0]), int(src_hw[1]),
                                   _ptr(Mij), _ptr(flip), _ptr(val), _ptr(msize), ctypes.byref(st),
                                   f * plan.rows_per_frame, f * plan.src_per_frame, plan.entry_base(f),

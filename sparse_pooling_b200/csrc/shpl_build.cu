@@ -24,6 +24,8 @@
 #include "shpl_common.cuh"
 
 namespace {
+using shpl::kFull;
+using shpl::lookback;
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
@@ -33,7 +35,6 @@ constexpr int kPairsTile = kThreads;             // one candidate pair per threa
 constexpr int kMaxRadixBits = 10;
 constexpr int kMaxRadix = 1 << kMaxRadixBits;
 constexpr int kMaxPasses = 4;
-constexpr unsigned kFull = 0xffffffffu;
 
 enum Mode { kModeAvod = 0, kModePairs = 1, kModeCoo = 2, kModeGenOnly = 3 };
 
@@ -109,6 +110,7 @@ SortPlan make_sort_plan(int n_keys) {
 struct PairsArgs {
     int mode;
     long long n;                 // candidates
+    const int* n_dev;            // optional device count: candidates i >= *n_dev do not exist
     // kModeAvod / kModeGenOnly
     const double* points;
     const long long* vox;
@@ -166,43 +168,6 @@ __device__ __forceinline__ double prow(const double* p, double x, double y, doub
     return t;
 }
 
-constexpr unsigned long long kFlagAgg = 1ull << 62;
-constexpr unsigned long long kFlagIncl = 2ull << 62;
-constexpr unsigned long long kValMask = (1ull << 62) - 1;
-
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
-    return *reinterpret_cast<const volatile unsigned long long*>(p);
-}
-
-// Single-pass exclusive prefix over tiles (decoupled look-back), executed by warp 0.
-// `agg` packs (count_clip << 31 | count_nnz) of this tile; returns the packed sum of all earlier tiles.
-__device__ unsigned long long lookback(unsigned long long* status, int tile, unsigned long long agg, int lane) {
-    if (tile == 0) {
-        if (lane == 0) atomicExch(status, kFlagIncl | agg);
-        return 0ull;
-    }
-    if (lane == 0) atomicExch(status + tile, kFlagAgg | agg);
-    unsigned long long excl = 0ull;
-    int t = tile - 1;
-    while (true) {
-        const int i = t - lane;
-        unsigned long long sv = kFlagIncl;       // virtual tile before tile 0: inclusive prefix 0
-        do {
-            if (i >= 0) sv = ld_volatile_u64(status + i);
-        } while (__any_sync(kFull, (sv >> 62) == 0ull));
-        const unsigned incl = __ballot_sync(kFull, (sv >> 62) == 2ull);
-        const int first = incl ? (__ffs(incl) - 1) : 32;
-        unsigned long long c = (lane <= first) ? (sv & kValMask) : 0ull;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(kFull, c, d);
-        excl += c;
-        if (incl) break;
-        t -= 32;
-    }
-    if (lane == 0) atomicExch(status + tile, kFlagIncl | (excl + agg));
-    return excl;
-}
-
 // What one candidate pair contributes (recomputed in both passes of shpl_pairs_kernel: the
 // kernel is latency-bound and straight-line code this size costs more in instruction fetch
 // than the arithmetic does, so the chunk loops are kept rolled and nothing is cached per chunk).
@@ -219,7 +184,7 @@ __device__ __forceinline__ Cand eval_candidate(const PairsArgs& a, long long i, 
     Cand c;
     c.clip = c.keep = false;
     c.row = 0; c.up = 0; c.vp = 0; c.gu = 0; c.gv = 0; c.us = 0; c.vs = 0; c.bx = 0; c.bz = 0;
-    if (i >= a.n) return c;
+    if (i >= a.n || (a.n_dev != nullptr && i >= (long long)*a.n_dev)) return c;
     if (a.mode == kModeCoo) {
         const long long r = a.coo[2 * i], col = a.coo[2 * i + 1];
         c.clip = c.keep = true;
@@ -719,7 +684,8 @@ extern "C" size_t shpl_build_workspace_bytes(int64_t n_max) {
     return carve(nullptr, n_max, nullptr).total_bytes;
 }
 
-extern "C" int shpl_gen_input_avod(const double* points, const int64_t* voxel_indices, int64_t N, const double* P_host,
+extern "C" int shpl_gen_input_avod(const double* points, const int64_t* voxel_indices, int64_t N, const int32_t* N_dev,
+                                   const double* P_host,
                                    int32_t im_w, int32_t im_h, int64_t* bv_index_out, double* img_u_out,
                                    double* img_v_out, int32_t* counts, void* workspace, size_t workspace_bytes,
                                    void* stream) {
@@ -729,6 +695,7 @@ extern "C" int shpl_gen_input_avod(const double* points, const int64_t* voxel_in
     PairsArgs pa{};
     pa.mode = kModeGenOnly;
     pa.n = N;
+    pa.n_dev = N_dev;
     pa.points = points;
     pa.vox = reinterpret_cast<const long long*>(voxel_indices);
     for (int i = 0; i < 12; ++i) pa.P[i] = P_host[i];
@@ -769,7 +736,8 @@ extern "C" int shpl_produce_input(double* img_u, double* img_v, const int64_t* b
     return run_build(pa, plan, entry_base_dev, workspace, workspace_bytes, stream, who);
 }
 
-extern "C" int shpl_build_avod(const double* points, const int64_t* voxel_indices, int64_t N, const double* P_host,
+extern "C" int shpl_build_avod(const double* points, const int64_t* voxel_indices, int64_t N, const int32_t* N_dev,
+                               const double* P_host,
                                int32_t im_w, int32_t im_h, int32_t bv_h, int32_t bv_w, int32_t stride_img,
                                int32_t stride_bv, const double* m_val, int32_t src_h, int32_t src_w, int64_t* Mij_pool,
                                int64_t* img_index_flip_pool, float* M_val_out, int64_t* M_size_out,
@@ -781,6 +749,7 @@ extern "C" int shpl_build_avod(const double* points, const int64_t* voxel_indice
     PairsArgs pa{};
     pa.mode = kModeAvod;
     pa.n = N;
+    pa.n_dev = N_dev;
     pa.points = points;
     pa.vox = reinterpret_cast<const long long*>(voxel_indices);
     for (int i = 0; i < 12; ++i) pa.P[i] = P_host[i];

@@ -41,4 +41,47 @@ inline int check_launch(const char* what) {
 
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
+
+#ifdef __CUDACC__
+// ---- single-pass prefix over CTAs (decoupled look-back), shared by the builder and the feeder
+constexpr unsigned kFull = 0xffffffffu;
+constexpr unsigned long long kFlagAgg = 1ull << 62;
+constexpr unsigned long long kFlagIncl = 2ull << 62;
+constexpr unsigned long long kValMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+
+// Single-pass exclusive prefix over tiles (decoupled look-back), executed by warp 0.
+// `agg` packs (count_clip << 31 | count_nnz) of this tile; returns the packed sum of all earlier tiles.
+__device__ inline unsigned long long lookback(unsigned long long* status, int tile, unsigned long long agg, int lane) {
+    if (tile == 0) {
+        if (lane == 0) atomicExch(status, kFlagIncl | agg);
+        return 0ull;
+    }
+    if (lane == 0) atomicExch(status + tile, kFlagAgg | agg);
+    unsigned long long excl = 0ull;
+    int t = tile - 1;
+    while (true) {
+        const int i = t - lane;
+        unsigned long long sv = kFlagIncl;       // virtual tile before tile 0: inclusive prefix 0
+        do {
+            if (i >= 0) sv = ld_volatile_u64(status + i);
+        } while (__any_sync(kFull, (sv >> 62) == 0ull));
+        const unsigned incl = __ballot_sync(kFull, (sv >> 62) == 2ull);
+        const int first = incl ? (__ffs(incl) - 1) : 32;
+        unsigned long long c = (lane <= first) ? (sv & kValMask) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(kFull, c, d);
+        excl += c;
+        if (incl) break;
+        t -= 32;
+    }
+    if (lane == 0) atomicExch(status + tile, kFlagIncl | (excl + agg));
+    return excl;
+}
+
+#endif  // __CUDACC__
+
 }  // namespace shpl

@@ -1,0 +1,397 @@
+// BEV slicing / voxelisation feeder for sm_100a.
+//
+// Replaces the numpy step that produces the SHPL builder's inputs:
+//   /root/reference/avod/avod/core/bev_generators/bev_slices.py:33-156        BevSlices.generate_bev(output_indices=True)
+//   /root/reference/avod/avod/core/bev_generators/bev_generator.py:23-41      _create_density_map
+//   /root/reference/avod/wavedata/wavedata/tools/core/voxel_grid_2d.py:43-162 VoxelGrid2D.voxelize_2d
+//   /root/reference/avod/avod/datasets/kitti/kitti_utils.py:79-107            create_slice_filter
+//   /root/reference/avod/wavedata/wavedata/tools/obj_detection/obj_utils.py:444-491  get_point_filter
+//   /root/reference/avod/wavedata/wavedata/tools/core/geometry_utils.py:25-40 dist_to_plane
+//
+// The reference sorts every slice (np.lexsort by x, z, y; stable) and keeps the first point of every
+// (x, z) run.  "First" = smallest (floor(y/voxel), original index) of the cell, so no sort is needed:
+//   memset   grid[S][X*Z] = ~0, density counts = 0, maps = 0
+//   K1       shpl_bev_scatter_kernel: one point per thread -- extents + plane filters (fp64, the reference's
+//            comparisons), floor(p / voxel), 64-bit atomicMin of (y_disc, index) into the slice's cell,
+//            integer atomicAdd of the density band (both order-independent: deterministic)
+//   K2       shpl_bev_emit_kernel: the (slice, x, z) cells in the reference's output order; STABLE compaction
+//            of the occupied ones (decoupled look-back) -> voxel_indices (x, Z - z), unique_pts, and the
+//            sparse non-zeros of the height / density maps (the maps were zero-filled by the memset)
+// The grid is 8 B x 560 000 cells x 5 slices = 22 MB: L2-resident on B200 (126 MB).
+#include "shpl_common.cuh"
+
+namespace {
+using shpl::kFull;
+using shpl::lookback;
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kCellsPerThread = 8;
+constexpr int kEmitTile = kThreads * kCellsPerThread;
+constexpr unsigned long long kEmpty = ~0ull;
+
+struct BevGeom {
+    double plane[4];              // ground plane a, b, c, d
+    double ext[6];                // x_lo, x_hi, y_lo, y_hi, z_lo, z_hi
+    double voxel;
+    double d_lo[SHPL_BEV_MAX_SLICES], d_hi[SHPL_BEV_MAX_SLICES];   // d - offset of the two planes of each slice (obj_utils.py:479)
+    double d_band_lo, d_band_hi;                                   // the density band [height_lo, height_hi]
+    double lo[SHPL_BEV_MAX_SLICES];                                // height_lo of each slice (bev_slices.py:66)
+    double hpd;                                                    // height_per_division (:30-31)
+    double norm;                                                   // sqrt(a^2 + b^2 + c^2) (geometry_utils.py:40)
+    double log_norm;                                               // NORM_VALUES[source] (bev_slices.py:12-14)
+    int S, X, Z;
+    int min_x, min_z;
+};
+
+struct ScatterArgs {
+    const double* pts;
+    long long coord_stride, point_stride;
+    long long P;
+    BevGeom g;
+    unsigned long long* grid;     // [S][X*Z]
+    int* dcount;                  // [X*Z]
+    int* counts;
+};
+
+// get_point_filter's plane test: np.dot(offset_plane, [x y z 1]) < 0.  The reference's BLAS (dgemv, OpenBLAS 0.3.30
+// Haswell kernel, probed on this image) rounds the 4-term dot as b*y, fma(a,x,.), fma(c,z,.), + d'.
+__device__ __forceinline__ double plane_base(const BevGeom& g, double x, double y, double z) {
+    double t = __dmul_rn(g.plane[1], y);
+    t = __fma_rn(g.plane[0], x, t);
+    t = __fma_rn(g.plane[2], z, t);
+    return t;
+}
+
+__global__ void __launch_bounds__(kThreads) shpl_bev_scatter_kernel(ScatterArgs a) {
+    const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const BevGeom& g = a.g;
+    bool inside = false;
+    double x = 0, y = 0, z = 0;
+    if (i < a.P) {
+        const double* p = a.pts + i * a.point_stride;
+        x = p[0];
+        y = p[a.coord_stride];
+        z = p[2 * a.coord_stride];
+        // obj_utils.py:467-472: strict on both sides
+        inside = (x > g.ext[0]) && (x < g.ext[1]) && (y > g.ext[2]) && (y < g.ext[3]) && (z > g.ext[4]) && (z < g.ext[5]);
+    }
+    const double base = plane_base(g, x, y, z);
+    // voxel_grid_2d.py:67
+    const int xd = (int)floor(__ddiv_rn(x, g.voxel)), yd = (int)floor(__ddiv_rn(y, g.voxel)), zd = (int)floor(__ddiv_rn(z, g.voxel));
+    const int xi = xd - g.min_x, zi = zd - g.min_z;
+    const bool in_grid = xi >= 0 && xi < g.X && zi >= 0 && zi < g.Z;
+    const long long cell = (long long)xi * g.Z + zi;
+    const unsigned long long word = ((unsigned long long)((unsigned)yd ^ 0x80000000u) << 32) | (unsigned)i;
+    bool bad = false;
+    for (int s = 0; s < g.S; ++s) {
+        // kitti_utils.py:97-107: xor of the two point filters
+        const bool in_s = inside && ((__dadd_rn(base, g.d_hi[s]) < 0.0) != (__dadd_rn(base, g.d_lo[s]) < 0.0));
+        const unsigned m = __ballot_sync(kFull, in_s);
+        if (m && lane == 0) atomicAdd(a.counts + 16 + s, __popc(m));
+        if (in_s) {
+            if (in_grid) atomicMin(a.grid + (size_t)s * g.X * g.Z + cell, word);
+            else bad = true;       // voxel_grid_2d.py:133-138 raises ValueError
+        }
+    }
+    const bool in_band = inside && ((__dadd_rn(base, g.d_band_hi) < 0.0) != (__dadd_rn(base, g.d_band_lo) < 0.0));
+    const unsigned mb = __ballot_sync(kFull, in_band);
+    if (mb && lane == 0) atomicAdd(a.counts + 2, __popc(mb));
+    if (in_band) {
+        if (in_grid) atomicAdd(a.dcount + cell, 1);
+        else bad = true;
+    }
+    if (bad) atomicOr(a.counts + 1, SHPL_BEV_ERR_EXTENTS);
+}
+
+struct EmitArgs {
+    const double* pts;
+    long long coord_stride, point_stride;
+    BevGeom g;
+    const unsigned long long* grid;
+    const int* dcount;
+    unsigned* ticket;
+    unsigned long long* status;
+    int n_tiles, use_ticket;
+    long long cap;
+    long long* vox_out;           // [cap,2]
+    double* pts_out;              // [cap,3]
+    double* maps;                 // [S+1][Z][X] or null
+    const double* lut;            // density value for n points, n < lut_len (device) or null
+    int lut_len;
+    int* counts;
+};
+
+__global__ void __launch_bounds__(kThreads) shpl_bev_emit_kernel(EmitArgs a) {
+    __shared__ int s_tile;
+    __shared__ unsigned s_cnt[kCellsPerThread][kWarps];
+    __shared__ unsigned long long s_excl;
+    __shared__ int s_src[SHPL_BEV_MAX_SLICES];
+    const BevGeom& g = a.g;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int tile = blockIdx.x;
+    if (a.use_ticket) {
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        tile = s_tile;
+    }
+    // bev_slices.py:79: a slice with <= 1 point re-uses the previous slice's grid (quirk A.4-7)
+    if (threadIdx.x == 0) {
+        int src = -1;
+        for (int s = 0; s < g.S; ++s) {
+            if (a.counts[16 + s] > 1) src = s;
+            s_src[s] = src;
+        }
+        if (tile == 0) {
+            if (s_src[0] < 0) atomicOr(a.counts + 1, SHPL_BEV_ERR_FIRST_SLICE_EMPTY);   // NameError in the reference
+            if (a.counts[2] == 0) atomicOr(a.counts + 1, SHPL_BEV_ERR_NO_POINTS);       // voxelize_2d of nothing raises
+        }
+    }
+    __syncthreads();
+    const long long XZ = (long long)g.X * g.Z;
+    const long long total = XZ * (g.S + 1);
+    const long long v0 = (long long)tile * kEmitTile;
+
+    unsigned long long word[kCellsPerThread];
+    bool occ[kCellsPerThread];
+#pragma unroll
+    for (int j = 0; j < kCellsPerThread; ++j) {
+        const long long v = v0 + j * kThreads + threadIdx.x;
+        word[j] = kEmpty;
+        if (v < total) {
+            const int s = (int)(v / XZ);
+            const long long cell = v - (long long)s * XZ;
+            if (s < g.S) {
+                if (s_src[s] >= 0) word[j] = a.grid[(size_t)s_src[s] * XZ + cell];
+            } else {
+                const int n = a.dcount[cell];
+                if (n > 0) word[j] = (unsigned long long)n;
+            }
+        }
+    }
+    // the density plane (s == S) is not part of the compaction
+    unsigned my_before[kCellsPerThread];
+#pragma unroll
+    for (int j = 0; j < kCellsPerThread; ++j) {
+        const long long v = v0 + j * kThreads + threadIdx.x;
+        occ[j] = word[j] != kEmpty && v < XZ * g.S;
+        const unsigned m = __ballot_sync(kFull, occ[j]);
+        my_before[j] = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0) s_cnt[j][warp] = __popc(m);
+    }
+    __syncthreads();
+    unsigned tot = 0;
+    unsigned chunk_base[kCellsPerThread];       // occupied cells of the tile before chunk j
+#pragma unroll
+    for (int j = 0; j < kCellsPerThread; ++j) {
+        chunk_base[j] = tot;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const unsigned c = s_cnt[j][w];
+            if (w < warp) my_before[j] += c;
+            tot += c;
+        }
+    }
+    if (warp == 0) {
+        const unsigned long long excl = lookback(a.status, tile, (unsigned long long)tot, lane);
+        if (lane == 0) s_excl = excl;
+    }
+    __syncthreads();
+    const long long base = (long long)s_excl;
+    if (tile == a.n_tiles - 1 && threadIdx.x == 0) {
+        a.counts[0] = (int)(base + tot);
+        if (base + tot > a.cap) atomicOr(a.counts + 1, SHPL_BEV_ERR_CAPACITY);
+    }
+
+#pragma unroll
+    for (int j = 0; j < kCellsPerThread; ++j) {
+        const long long v = v0 + j * kThreads + threadIdx.x;
+        if (v >= total) continue;
+        const int s = (int)(v / XZ);
+        const long long cell = v - (long long)s * XZ;
+        const long long pos = base + chunk_base[j] + my_before[j];
+        if (cell == 0 && s < g.S) a.counts[8 + s] = (int)pos;          // where slice s starts in the output
+        if (word[j] == kEmpty) continue;
+        const int xi = (int)(cell / g.Z), zi = (int)(cell - (long long)xi * g.Z);
+        const size_t map_at = (size_t)(g.Z - 1 - zi) * g.X + xi;       // np.flip(map.transpose(), axis=0)  (:116-118)
+        if (s == g.S) {
+            if (a.maps) {
+                // bev_generator.py:35-36: min(1, log(n + 1) / norm)
+                const int n = (int)word[j];
+                double dv;
+                if (a.lut) dv = n < a.lut_len ? a.lut[n] : 1.0;
+                else dv = fmin(1.0, __ddiv_rn(log((double)n + 1.0), g.log_norm));
+                a.maps[(size_t)g.S * XZ + map_at] = dv;
+            }
+            continue;
+        }
+        const long long i = (long long)(unsigned)word[j];
+        const double* p = a.pts + i * a.point_stride;
+        const double x = p[0], y = p[a.coord_stride], z = p[2 * a.coord_stride];
+        if (pos < a.cap) {
+            a.vox_out[2 * pos] = xi;
+            a.vox_out[2 * pos + 1] = g.Z - zi;                         // bev_slices.py:106-108 (num_divisions - z)
+            a.pts_out[3 * pos] = x;
+            a.pts_out[3 * pos + 1] = y;
+            a.pts_out[3 * pos + 2] = z;
+        }
+        if (a.maps) {
+            // geometry_utils.py:40: (a*x + b*y + c*z + d) / norm, numpy elementwise (no contraction)
+            double h = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(g.plane[0], x), __dmul_rn(g.plane[1], y)), __dmul_rn(g.plane[2], z)), g.plane[3]);
+            h = __ddiv_rn(h, g.norm);
+            // bev_slices.py:100: heights -= height_lo, once per slice the grid is used for
+            for (int t = s_src[s]; t <= s; ++t) h = __dsub_rn(h, g.lo[t]);
+            a.maps[(size_t)s * XZ + map_at] = __ddiv_rn(h, g.hpd);
+        }
+    }
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct FeederWs {
+    unsigned* ticket;
+    unsigned long long* status;
+    int* dcount;
+    size_t zero_bytes;            // header + status + dcount: zeroed
+    unsigned long long* grid;
+    size_t grid_bytes;
+    size_t total_bytes;
+};
+
+FeederWs carve(void* base, int S, long long XZ) {
+    FeederWs w{};
+    char* p = static_cast<char*>(base);
+    const long long total = XZ * (S + 1);
+    const long long tiles = (total + kEmitTile - 1) / kEmitTile > 0 ? (total + kEmitTile - 1) / kEmitTile : 1;
+    size_t off = 0;
+    w.ticket = reinterpret_cast<unsigned*>(p + off);
+    off += 64;
+    w.status = reinterpret_cast<unsigned long long*>(p + off);
+    off = align_up(off + sizeof(unsigned long long) * tiles, 64);
+    w.dcount = reinterpret_cast<int*>(p + off);
+    off = align_up(off + sizeof(int) * XZ, 256);
+    w.zero_bytes = off;
+    w.grid = reinterpret_cast<unsigned long long*>(p + off);
+    w.grid_bytes = sizeof(unsigned long long) * (size_t)S * XZ;
+    off = align_up(off + w.grid_bytes, 256);
+    w.total_bytes = off;
+    return w;
+}
+
+int make_geometry(BevGeom& g, const double* plane, const double* ext, double voxel, double height_lo, double height_hi,
+                  int S, double log_norm, const char* who) {
+    SHPL_REQUIRE(plane && ext, SHPL_ERR_INVALID_ARGUMENT, "%s: null pointer", who);
+    SHPL_REQUIRE(S >= 1 && S <= SHPL_BEV_MAX_SLICES, SHPL_ERR_INVALID_ARGUMENT, "%s: num_slices=%d not in [1, %d]", who, S,
+                 SHPL_BEV_MAX_SLICES);
+    SHPL_REQUIRE(voxel > 0.0, SHPL_ERR_INVALID_ARGUMENT, "%s: voxel_size must be positive", who);
+    for (int i = 0; i < 4; ++i) g.plane[i] = plane[i];
+    for (int i = 0; i < 6; ++i) g.ext[i] = ext[i];
+    g.voxel = voxel;
+    g.S = S;
+    // voxel_grid_2d.py:126-149
+    const double min_x = floor(ext[0] / voxel), max_x = ceil(ext[1] / voxel - 1.0);
+    const double min_z = floor(ext[4] / voxel), max_z = ceil(ext[5] / voxel - 1.0);
+    const double nx = max_x - min_x + 1.0, nz = max_z - min_z + 1.0;
+    SHPL_REQUIRE(nx >= 1.0 && nz >= 1.0 && nx * nz * (S + 1) < 2147483647.0 && fabs(min_x) < 1e9 && fabs(min_z) < 1e9,
+                 SHPL_ERR_INVALID_ARGUMENT, "%s: extents / voxel_size give a %g x %g grid", who, nx, nz);
+    g.X = (int)nx;
+    g.Z = (int)nz;
+    g.min_x = (int)min_x;
+    g.min_z = (int)min_z;
+    // bev_slices.py:29-31, :66-67
+    g.hpd = (height_hi - height_lo) / (double)S;
+    for (int s = 0; s < S; ++s) {
+        volatile double lo = height_lo + (double)s * g.hpd;     // volatile: each step rounded to double like Python's floats
+        volatile double hi = lo + g.hpd;
+        g.lo[s] = lo;
+        g.d_lo[s] = plane[3] + (-lo);                           // obj_utils.py:479: ground_plane + [0, 0, 0, -offset]
+        g.d_hi[s] = plane[3] + (-hi);
+    }
+    g.d_band_lo = plane[3] + (-height_lo);
+    g.d_band_hi = plane[3] + (-height_hi);
+    g.norm = sqrt(plane[0] * plane[0] + plane[1] * plane[1] + plane[2] * plane[2]);
+    g.log_norm = log_norm;
+    return SHPL_OK;
+}
+
+}  // namespace
+
+extern "C" int shpl_bev_grid_dims(const double* extents_host, double voxel_size, int32_t* nx, int32_t* nz) {
+    const double plane[4] = {0, -1, 0, 0};
+    BevGeom g{};
+    if (int rc = make_geometry(g, plane, extents_host, voxel_size, 0.0, 1.0, 1, 1.0, "shpl_bev_grid_dims")) return rc;
+    if (nx) *nx = g.X;
+    if (nz) *nz = g.Z;
+    return SHPL_OK;
+}
+
+extern "C" size_t shpl_bev_workspace_bytes(const double* extents_host, double voxel_size, int32_t num_slices) {
+    const double plane[4] = {0, -1, 0, 0};
+    BevGeom g{};
+    if (make_geometry(g, plane, extents_host, voxel_size, 0.0, 1.0, num_slices, 1.0, "shpl_bev_workspace_bytes")) return 0;
+    return carve(nullptr, g.S, (long long)g.X * g.Z).total_bytes;
+}
+
+extern "C" int shpl_bev_slices(const double* points, int64_t coord_stride, int64_t point_stride, int64_t P,
+                               const double* ground_plane_host, const double* extents_host, double voxel_size,
+                               double height_lo, double height_hi, int32_t num_slices, double log_norm,
+                               const double* density_lut, int32_t lut_len,
+                               int64_t* voxel_indices_out, double* unique_pts_out, int64_t capacity,
+                               double* bev_maps_out, int32_t* counts, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+    const char* who = "shpl_bev_slices";
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SHPL_REQUIRE(P >= 0 && P < (1ll << 31), SHPL_ERR_INVALID_ARGUMENT, "%s: P=%lld out of range", who, (long long)P);
+    SHPL_REQUIRE((P == 0 || points) && counts && workspace && capacity >= 0 && (capacity == 0 || (voxel_indices_out && unique_pts_out)),
+                 SHPL_ERR_INVALID_ARGUMENT, "%s: null pointer", who);
+    SHPL_REQUIRE(shpl::aligned(workspace, 256), SHPL_ERR_INVALID_ARGUMENT, "%s: workspace must be 256-byte aligned", who);
+    SHPL_REQUIRE(log_norm > 0.0 && (density_lut == nullptr || lut_len > 0), SHPL_ERR_INVALID_ARGUMENT, "%s: bad density normalisation", who);
+    BevGeom g{};
+    if (int rc = make_geometry(g, ground_plane_host, extents_host, voxel_size, height_lo, height_hi, num_slices, log_norm, who)) return rc;
+    const long long XZ = (long long)g.X * g.Z;
+    FeederWs w = carve(workspace, g.S, XZ);
+    SHPL_REQUIRE(w.total_bytes <= workspace_bytes, SHPL_ERR_WORKSPACE_TOO_SMALL, "%s: workspace %zu bytes < %zu needed", who,
+                 workspace_bytes, w.total_bytes);
+    SHPL_CUDA_OK(cudaMemsetAsync(workspace, 0, w.zero_bytes, s));
+    SHPL_CUDA_OK(cudaMemsetAsync(w.grid, 0xff, w.grid_bytes, s));
+    SHPL_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * SHPL_BEV_COUNTS, s));
+    if (bev_maps_out) SHPL_CUDA_OK(cudaMemsetAsync(bev_maps_out, 0, sizeof(double) * (size_t)(g.S + 1) * XZ, s));
+
+    if (P > 0) {
+        ScatterArgs sa{};
+        sa.pts = points;
+        sa.coord_stride = coord_stride;
+        sa.point_stride = point_stride;
+        sa.P = P;
+        sa.g = g;
+        sa.grid = w.grid;
+        sa.dcount = w.dcount;
+        sa.counts = counts;
+        shpl_bev_scatter_kernel<<<(unsigned)((P + kThreads - 1) / kThreads), kThreads, 0, s>>>(sa);
+        shpl::count_launches(1);
+        if (int rc = shpl::check_launch("shpl_bev_scatter_kernel")) return rc;
+    }
+    EmitArgs ea{};
+    ea.pts = points;
+    ea.coord_stride = coord_stride;
+    ea.point_stride = point_stride;
+    ea.g = g;
+    ea.grid = w.grid;
+    ea.dcount = w.dcount;
+    ea.ticket = w.ticket;
+    ea.status = w.status;
+    const long long total = XZ * (g.S + 1);
+    ea.n_tiles = (int)((total + kEmitTile - 1) / kEmitTile);
+    ea.use_ticket = ea.n_tiles > shpl::sm_count() * 4 ? 1 : 0;
+    ea.cap = capacity;
+    ea.vox_out = reinterpret_cast<long long*>(voxel_indices_out);
+    ea.pts_out = unique_pts_out;
+    ea.maps = bev_maps_out;
+    ea.lut = density_lut;
+    ea.lut_len = lut_len;
+    ea.counts = counts;
+    shpl_bev_emit_kernel<<<(unsigned)ea.n_tiles, kThreads, 0, s>>>(ea);
+    shpl::count_launches(1);
+    return shpl::check_launch("shpl_bev_emit_kernel");
+}

@@ -88,21 +88,21 @@ class FramePipeline:
         self.layers = [_LayerState(s, self.n_max, device) for s in layers]
 
     # -- correspondence build: shpl_build_avod per layer (different strides, same points) --
-    def build(self, points, voxel_indices, P, n_points, stream):
+    def build(self, points, voxel_indices, P, n_points, stream, n_dev=None):
         P = np.ascontiguousarray(np.asarray(P, dtype=np.float64).reshape(12))
         for L in self.layers:
             s = L.spec
-            rc = _lib.shpl_build_avod(_p(points), _p(voxel_indices), int(n_points), P.ctypes.data_as(ctypes.c_void_p),
+            rc = _lib.shpl_build_avod(_p(points), _p(voxel_indices), int(n_points), n_dev, P.ctypes.data_as(ctypes.c_void_p),
                                       s.im_size[0], s.im_size[1], s.bv_size[0], s.bv_size[1], s.stride[0], s.stride[1],
                                       None, s.img_hw[0], s.img_hw[1], None, None, None, None,
                                       ctypes.byref(L.plan_struct), 0, 0, None, _p(L.ws), L.ws.numel(), stream)
             _cabi.check(rc, "shpl_build_avod")
 
-    def build_layer(self, i, points, voxel_indices, P, n_points, stream):
+    def build_layer(self, i, points, voxel_indices, P, n_points, stream, n_dev=None):
         L = self.layers[i]
         s = L.spec
         P = np.ascontiguousarray(np.asarray(P, dtype=np.float64).reshape(12))
-        rc = _lib.shpl_build_avod(_p(points), _p(voxel_indices), int(n_points), P.ctypes.data_as(ctypes.c_void_p),
+        rc = _lib.shpl_build_avod(_p(points), _p(voxel_indices), int(n_points), n_dev, P.ctypes.data_as(ctypes.c_void_p),
                                   s.im_size[0], s.im_size[1], s.bv_size[0], s.bv_size[1], s.stride[0], s.stride[1],
                                   None, s.img_hw[0], s.img_hw[1], None, None, None, None,
                                   ctypes.byref(L.plan_struct), 0, 0, None, _p(L.ws), L.ws.numel(), stream)

@@ -84,9 +84,10 @@ class SparsePoolingInput(dict):
 
     _LAZY = ("bv_index", "img_index")
 
-    def __init__(self, pts, vox, P, im_size, bv_size, as_numpy, device):
+    def __init__(self, pts, vox, P, im_size, bv_size, as_numpy, device, n_dev=None):
         super().__init__(bv_size=np.array([bv_size[0], bv_size[1]]), img_size=np.array(im_size))
         self._pts, self._vox, self._P = pts, vox, P
+        self._n_dev = n_dev           # device int32 count of valid candidates (feeder output not yet read back)
         self._as_numpy, self._device = as_numpy, device
         self._done = False
         self._mutations = []          # image strides applied in place by produce calls made before materialisation
@@ -102,7 +103,7 @@ class SparsePoolingInput(dict):
         uv_out = torch.empty((2, max(N, 1)), dtype=torch.float64, device=dev)
         counts = torch.zeros(8, dtype=torch.int32, device=dev)
         ws = ops.workspace(dev, N)
-        rc = _lib.shpl_gen_input_avod(_ptr(pts), _ptr(vox), N, self._P.ctypes.data_as(ctypes.c_void_p),
+        rc = _lib.shpl_gen_input_avod(_ptr(pts), _ptr(vox), N, self._n_dev, self._P.ctypes.data_as(ctypes.c_void_p),
                                       _as_int(im_size[0], "im_size"), _as_int(im_size[1], "im_size"),
                                       _ptr(bv_out), _ptr(uv_out[0]), _ptr(uv_out[1]), _ptr(counts), _ptr(ws),
                                       ws.numel(), _stream())
@@ -229,7 +230,7 @@ def produce_sparse_pooling_input(input_dict, M_val=None, stride=[1, 1]):
         flip = torch.empty((cap, 3), dtype=torch.int64, device=dev)
         ws = ops.workspace(dev, N)
         st = plan.frame_struct(0)
-        rc = _lib.shpl_build_avod(_ptr(pts), _ptr(vox), N, input_dict._P.ctypes.data_as(ctypes.c_void_p),
+        rc = _lib.shpl_build_avod(_ptr(pts), _ptr(vox), N, input_dict._n_dev, input_dict._P.ctypes.data_as(ctypes.c_void_p),
                                   im_w, im_h, bv_h, bv_w, s_img, s_bv, _ptr(mval_dev), 0, 0, _ptr(Mij), _ptr(flip),
                                   None, None, ctypes.byref(st), 0, 0, None, _ptr(ws), ws.numel(), _stream())
         _cabi.check(rc, "shpl_build_avod")

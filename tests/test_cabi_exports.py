@@ -29,7 +29,8 @@ def test_header_declares_the_expected_entry_points():
     assert declared_functions() == sorted([
         "shpl_abi_version", "shpl_last_error", "shpl_kernel_launches", "shpl_build_workspace_bytes", "shpl_gen_input_avod",
         "shpl_produce_input", "shpl_build_avod", "shpl_plan_from_coo", "shpl_pool_forward", "shpl_pool_backward",
-        "shpl_pool_forward_dual", "shpl_pool_backward_dual", "shpl_pool_heavy"])
+        "shpl_pool_forward_dual", "shpl_pool_backward_dual", "shpl_pool_heavy",
+        "shpl_bev_grid_dims", "shpl_bev_workspace_bytes", "shpl_bev_slices"])
 
 
 def test_library_exports_every_declared_symbol(lib):
@@ -40,7 +41,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_binding_covers_the_header(lib):
     from sparse_pooling_b200 import _cabi
     assert sorted(_cabi.SIGNATURES) == declared_functions()
-    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 3
+    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 4
 
 
 def test_workspace_query_grows_with_n(lib):
