@@ -10,14 +10,17 @@
 //
 // The reference sorts every slice (np.lexsort by x, z, y; stable) and keeps the first point of every
 // (x, z) run.  "First" = smallest (floor(y/voxel), original index) of the cell, so no sort is needed:
-//   memset   grid[S][X*Z] = ~0, density counts = 0, maps = 0
+//   memset   header + occupancy bitmaps + density counts = 0 (one memset), winner grid = ~0, maps = 0
 //   K1       shpl_bev_scatter_kernel: one point per thread -- extents + plane filters (fp64, the reference's
-//            comparisons), floor(p / voxel), 64-bit atomicMin of (y_disc, index) into the slice's cell,
-//            integer atomicAdd of the density band (both order-independent: deterministic)
-//   K2       shpl_bev_emit_kernel: the (slice, x, z) cells in the reference's output order; STABLE compaction
-//            of the occupied ones (decoupled look-back) -> voxel_indices (x, Z - z), unique_pts, and the
-//            sparse non-zeros of the height / density maps (the maps were zero-filled by the memset)
-// The grid is 8 B x 560 000 cells x 5 slices = 22 MB: L2-resident on B200 (126 MB).
+//            comparisons), floor(p / voxel), atomicMin of (y_disc, index) into the slice's cell of the winner
+//            grid, atomicOr of the cell's bit in the slice's occupancy bitmap, integer atomicAdd for the
+//            density band (all order-independent: deterministic)
+//   K2       shpl_bev_emit_kernel: walks the BITMAPS (420 KB instead of the 22 MB grid) in the reference's
+//            output order (slice, x, z): popc + block scan + decoupled look-back give every occupied cell its
+//            output row (stable compaction); the tile's occupied cells are listed in shared memory and then
+//            spread over the CTA's threads, so crowded near-range words do not serialise one thread.
+//            Emits voxel_indices (x, Z - z), unique_pts and the non-zeros of the height / density maps.
+// The winner grid uses 32-bit words (y bin | index) whenever the y extent and the point count fit, else 64-bit.
 #include "shpl_common.cuh"
 
 namespace {
@@ -26,9 +29,7 @@ using shpl::lookback;
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kCellsPerThread = 8;
-constexpr int kEmitTile = kThreads * kCellsPerThread;
-constexpr unsigned long long kEmpty = ~0ull;
+constexpr int kTileCells = kThreads * 32;     // one bitmap word per thread
 
 struct BevGeom {
     double plane[4];              // ground plane a, b, c, d
@@ -42,6 +43,23 @@ struct BevGeom {
     double log_norm;                                               // NORM_VALUES[source] (bev_slices.py:12-14)
     int S, X, Z;
     int min_x, min_z;
+    int yd_min, ybits;            // y bins the extents allow: floor(y/voxel) - yd_min fits ybits bits
+    int W, tiles_per_plane;       // bitmap words per plane (ceil(X*Z/32)) and emit tiles per plane
+};
+
+// internal counters, in the zeroed workspace header (the caller's counts are written once, at the end)
+enum { kCtrFlags = 1, kCtrBand = 2, kCtrSlice = 16 };
+
+struct FeederWs {
+    unsigned* ticket;             // [1]
+    int* ctr;                     // [32]
+    unsigned long long* status;   // [tiles]
+    unsigned* bitmap;             // [S+1][W]: slices, then the density band
+    int* dcount;                  // [X*Z]
+    size_t zero_bytes;            // everything above: zeroed by one memset
+    void* grid;                   // [S][X*Z] winner words, memset to ~0
+    size_t grid_bytes;
+    size_t total_bytes;
 };
 
 struct ScatterArgs {
@@ -49,9 +67,7 @@ struct ScatterArgs {
     long long coord_stride, point_stride;
     long long P;
     BevGeom g;
-    unsigned long long* grid;     // [S][X*Z]
-    int* dcount;                  // [X*Z]
-    int* counts;
+    FeederWs ws;
 };
 
 // get_point_filter's plane test: np.dot(offset_plane, [x y z 1]) < 0.  The reference's BLAS (dgemv, OpenBLAS 0.3.30
@@ -63,6 +79,23 @@ __device__ __forceinline__ double plane_base(const BevGeom& g, double x, double 
     return t;
 }
 
+template <typename Word> struct WordOps;
+template <> struct WordOps<unsigned> {
+    static __device__ __forceinline__ unsigned make(const BevGeom& g, int yd, long long i) {
+        return g.ybits ? (((unsigned)(yd - g.yd_min) << (32 - g.ybits)) | (unsigned)i) : (unsigned)i;
+    }
+    static __device__ __forceinline__ long long index(const BevGeom& g, unsigned w) {
+        return (long long)(g.ybits ? (w & (0xffffffffu >> g.ybits)) : w);
+    }
+};
+template <> struct WordOps<unsigned long long> {
+    static __device__ __forceinline__ unsigned long long make(const BevGeom&, int yd, long long i) {
+        return ((unsigned long long)((unsigned)yd ^ 0x80000000u) << 32) | (unsigned)i;
+    }
+    static __device__ __forceinline__ long long index(const BevGeom&, unsigned long long w) { return (long long)(unsigned)w; }
+};
+
+template <typename Word>
 __global__ void __launch_bounds__(kThreads) shpl_bev_scatter_kernel(ScatterArgs a) {
     const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
     const int lane = threadIdx.x & 31;
@@ -82,57 +115,67 @@ __global__ void __launch_bounds__(kThreads) shpl_bev_scatter_kernel(ScatterArgs 
     const int xd = (int)floor(__ddiv_rn(x, g.voxel)), yd = (int)floor(__ddiv_rn(y, g.voxel)), zd = (int)floor(__ddiv_rn(z, g.voxel));
     const int xi = xd - g.min_x, zi = zd - g.min_z;
     const bool in_grid = xi >= 0 && xi < g.X && zi >= 0 && zi < g.Z;
+    const long long XZ = (long long)g.X * g.Z;
     const long long cell = (long long)xi * g.Z + zi;
-    const unsigned long long word = ((unsigned long long)((unsigned)yd ^ 0x80000000u) << 32) | (unsigned)i;
+    const Word word = WordOps<Word>::make(g, yd, i);
+    const unsigned bit = 1u << (cell & 31);
+    Word* grid = static_cast<Word*>(a.ws.grid);
     bool bad = false;
     for (int s = 0; s < g.S; ++s) {
         // kitti_utils.py:97-107: xor of the two point filters
         const bool in_s = inside && ((__dadd_rn(base, g.d_hi[s]) < 0.0) != (__dadd_rn(base, g.d_lo[s]) < 0.0));
         const unsigned m = __ballot_sync(kFull, in_s);
-        if (m && lane == 0) atomicAdd(a.counts + 16 + s, __popc(m));
+        if (m && lane == 0) atomicAdd(a.ws.ctr + kCtrSlice + s, __popc(m));
         if (in_s) {
-            if (in_grid) atomicMin(a.grid + (size_t)s * g.X * g.Z + cell, word);
-            else bad = true;       // voxel_grid_2d.py:133-138 raises ValueError
+            if (in_grid) {
+                atomicMin(grid + (size_t)s * XZ + cell, word);
+                atomicOr(a.ws.bitmap + (size_t)s * g.W + (cell >> 5), bit);
+            } else {
+                bad = true;       // voxel_grid_2d.py:133-138 raises ValueError
+            }
         }
     }
     const bool in_band = inside && ((__dadd_rn(base, g.d_band_hi) < 0.0) != (__dadd_rn(base, g.d_band_lo) < 0.0));
     const unsigned mb = __ballot_sync(kFull, in_band);
-    if (mb && lane == 0) atomicAdd(a.counts + 2, __popc(mb));
+    if (mb && lane == 0) atomicAdd(a.ws.ctr + kCtrBand, __popc(mb));
     if (in_band) {
-        if (in_grid) atomicAdd(a.dcount + cell, 1);
-        else bad = true;
+        if (in_grid) {
+            atomicAdd(a.ws.dcount + cell, 1);
+            atomicOr(a.ws.bitmap + (size_t)g.S * g.W + (cell >> 5), bit);
+        } else {
+            bad = true;
+        }
     }
-    if (bad) atomicOr(a.counts + 1, SHPL_BEV_ERR_EXTENTS);
+    if (bad) atomicOr(a.ws.ctr + kCtrFlags, SHPL_BEV_ERR_EXTENTS);
 }
 
 struct EmitArgs {
     const double* pts;
     long long coord_stride, point_stride;
     BevGeom g;
-    const unsigned long long* grid;
-    const int* dcount;
-    unsigned* ticket;
-    unsigned long long* status;
-    int n_tiles, use_ticket;
+    FeederWs ws;
+    int use_ticket;
     long long cap;
     long long* vox_out;           // [cap,2]
     double* pts_out;              // [cap,3]
     double* maps;                 // [S+1][Z][X] or null
     const double* lut;            // density value for n points, n < lut_len (device) or null
     int lut_len;
-    int* counts;
+    int* counts;                  // the caller's [SHPL_BEV_COUNTS]
 };
 
+template <typename Word>
 __global__ void __launch_bounds__(kThreads) shpl_bev_emit_kernel(EmitArgs a) {
     __shared__ int s_tile;
-    __shared__ unsigned s_cnt[kCellsPerThread][kWarps];
+    __shared__ unsigned s_wtot[kWarps];
     __shared__ unsigned long long s_excl;
     __shared__ int s_src[SHPL_BEV_MAX_SLICES];
+    __shared__ unsigned short s_list[kTileCells];     // occupied cells of the tile (bit offset inside the tile), in order
     const BevGeom& g = a.g;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int tile = blockIdx.x;
-    if (a.use_ticket) {
-        if (threadIdx.x == 0) s_tile = (int)atomicAdd(a.ticket, 1u);
+    if (a.use_ticket) {          // more CTAs than can be resident: order the look-back by arrival
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(a.ws.ticket, 1u);
         __syncthreads();
         tile = s_tile;
     }
@@ -140,85 +183,66 @@ __global__ void __launch_bounds__(kThreads) shpl_bev_emit_kernel(EmitArgs a) {
     if (threadIdx.x == 0) {
         int src = -1;
         for (int s = 0; s < g.S; ++s) {
-            if (a.counts[16 + s] > 1) src = s;
+            if (a.ws.ctr[kCtrSlice + s] > 1) src = s;
             s_src[s] = src;
         }
-        if (tile == 0) {
-            if (s_src[0] < 0) atomicOr(a.counts + 1, SHPL_BEV_ERR_FIRST_SLICE_EMPTY);   // NameError in the reference
-            if (a.counts[2] == 0) atomicOr(a.counts + 1, SHPL_BEV_ERR_NO_POINTS);       // voxelize_2d of nothing raises
-        }
     }
     __syncthreads();
+    const int plane = tile / g.tiles_per_plane;              // < S: a height slice; == S: the density band
+    const int tip = tile - plane * g.tiles_per_plane;
+    const int n_slice_tiles = g.S * g.tiles_per_plane;
     const long long XZ = (long long)g.X * g.Z;
-    const long long total = XZ * (g.S + 1);
-    const long long v0 = (long long)tile * kEmitTile;
-
-    unsigned long long word[kCellsPerThread];
-    bool occ[kCellsPerThread];
+    const int w = tip * kThreads + threadIdx.x;              // bitmap word of this thread inside the plane
+    const int src = plane < g.S ? s_src[plane] : g.S;
+    unsigned bits = 0;
+    if (w < g.W && src >= 0) bits = a.ws.bitmap[(size_t)src * g.W + w];
+    const unsigned cnt = __popc(bits);
+    unsigned incl = cnt;
 #pragma unroll
-    for (int j = 0; j < kCellsPerThread; ++j) {
-        const long long v = v0 + j * kThreads + threadIdx.x;
-        word[j] = kEmpty;
-        if (v < total) {
-            const int s = (int)(v / XZ);
-            const long long cell = v - (long long)s * XZ;
-            if (s < g.S) {
-                if (s_src[s] >= 0) word[j] = a.grid[(size_t)s_src[s] * XZ + cell];
-            } else {
-                const int n = a.dcount[cell];
-                if (n > 0) word[j] = (unsigned long long)n;
-            }
-        }
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned v = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += v;
     }
-    // the density plane (s == S) is not part of the compaction
-    unsigned my_before[kCellsPerThread];
-#pragma unroll
-    for (int j = 0; j < kCellsPerThread; ++j) {
-        const long long v = v0 + j * kThreads + threadIdx.x;
-        occ[j] = word[j] != kEmpty && v < XZ * g.S;
-        const unsigned m = __ballot_sync(kFull, occ[j]);
-        my_before[j] = __popc(m & ((1u << lane) - 1u));
-        if (lane == 0) s_cnt[j][warp] = __popc(m);
-    }
+    if (lane == 31) s_wtot[warp] = incl;
     __syncthreads();
-    unsigned tot = 0;
-    unsigned chunk_base[kCellsPerThread];       // occupied cells of the tile before chunk j
+    unsigned before = incl - cnt, tot = 0;
 #pragma unroll
-    for (int j = 0; j < kCellsPerThread; ++j) {
-        chunk_base[j] = tot;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const unsigned c = s_cnt[j][w];
-            if (w < warp) my_before[j] += c;
-            tot += c;
-        }
+    for (int q = 0; q < kWarps; ++q) {
+        if (q < warp) before += s_wtot[q];
+        tot += s_wtot[q];
     }
-    if (warp == 0) {
-        const unsigned long long excl = lookback(a.status, tile, (unsigned long long)tot, lane);
+    for (unsigned b = bits, r = before; b; b &= b - 1, ++r) s_list[r] = (unsigned short)(threadIdx.x * 32 + (__ffs(b) - 1));
+    if (warp == 0 && plane < g.S) {
+        const unsigned long long excl = lookback(a.ws.status, tile, (unsigned long long)tot, lane);
         if (lane == 0) s_excl = excl;
     }
     __syncthreads();
-    const long long base = (long long)s_excl;
-    if (tile == a.n_tiles - 1 && threadIdx.x == 0) {
-        a.counts[0] = (int)(base + tot);
-        if (base + tot > a.cap) atomicOr(a.counts + 1, SHPL_BEV_ERR_CAPACITY);
+    const long long base = plane < g.S ? (long long)s_excl : 0;
+    if (threadIdx.x == 0 && plane < g.S) {
+        if (tip == 0) a.counts[8 + plane] = (int)base;                 // where slice `plane` starts in the output
+        if (tile == n_slice_tiles - 1) {                               // inclusive prefix of the last slice tile = totals
+            const long long n = base + tot;
+            int flags = a.ws.ctr[kCtrFlags];
+            if (s_src[0] < 0) flags |= SHPL_BEV_ERR_FIRST_SLICE_EMPTY;           // NameError in the reference
+            if (a.ws.ctr[kCtrBand] == 0) flags |= SHPL_BEV_ERR_NO_POINTS;         // voxelize_2d of nothing raises
+            if (n > a.cap) flags |= SHPL_BEV_ERR_CAPACITY;
+            a.counts[0] = (int)n;
+            a.counts[1] = flags;
+            a.counts[2] = a.ws.ctr[kCtrBand];
+            for (int q = 3; q < 8; ++q) a.counts[q] = 0;
+            for (int q = 8 + g.S; q < 16; ++q) a.counts[q] = 0;
+            for (int q = 0; q < 16; ++q) a.counts[16 + q] = q < g.S ? a.ws.ctr[kCtrSlice + q] : 0;
+        }
     }
-
-#pragma unroll
-    for (int j = 0; j < kCellsPerThread; ++j) {
-        const long long v = v0 + j * kThreads + threadIdx.x;
-        if (v >= total) continue;
-        const int s = (int)(v / XZ);
-        const long long cell = v - (long long)s * XZ;
-        const long long pos = base + chunk_base[j] + my_before[j];
-        if (cell == 0 && s < g.S) a.counts[8 + s] = (int)pos;          // where slice s starts in the output
-        if (word[j] == kEmpty) continue;
+    const Word* grid = static_cast<const Word*>(a.ws.grid);
+    for (unsigned it = threadIdx.x; it < tot; it += kThreads) {
+        const long long cell = (long long)tip * kTileCells + s_list[it];
         const int xi = (int)(cell / g.Z), zi = (int)(cell - (long long)xi * g.Z);
         const size_t map_at = (size_t)(g.Z - 1 - zi) * g.X + xi;       // np.flip(map.transpose(), axis=0)  (:116-118)
-        if (s == g.S) {
+        if (plane == g.S) {
             if (a.maps) {
                 // bev_generator.py:35-36: min(1, log(n + 1) / norm)
-                const int n = (int)word[j];
+                const int n = a.ws.dcount[cell];
                 double dv;
                 if (a.lut) dv = n < a.lut_len ? a.lut[n] : 1.0;
                 else dv = fmin(1.0, __ddiv_rn(log((double)n + 1.0), g.log_norm));
@@ -226,7 +250,8 @@ __global__ void __launch_bounds__(kThreads) shpl_bev_emit_kernel(EmitArgs a) {
             }
             continue;
         }
-        const long long i = (long long)(unsigned)word[j];
+        const long long pos = base + it;
+        const long long i = WordOps<Word>::index(g, grid[(size_t)src * XZ + cell]);
         const double* p = a.pts + i * a.point_stride;
         const double x = p[0], y = p[a.coord_stride], z = p[2 * a.coord_stride];
         if (pos < a.cap) {
@@ -241,39 +266,33 @@ __global__ void __launch_bounds__(kThreads) shpl_bev_emit_kernel(EmitArgs a) {
             double h = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(g.plane[0], x), __dmul_rn(g.plane[1], y)), __dmul_rn(g.plane[2], z)), g.plane[3]);
             h = __ddiv_rn(h, g.norm);
             // bev_slices.py:100: heights -= height_lo, once per slice the grid is used for
-            for (int t = s_src[s]; t <= s; ++t) h = __dsub_rn(h, g.lo[t]);
-            a.maps[(size_t)s * XZ + map_at] = __ddiv_rn(h, g.hpd);
+            for (int t = src; t <= plane; ++t) h = __dsub_rn(h, g.lo[t]);
+            a.maps[(size_t)plane * XZ + map_at] = __ddiv_rn(h, g.hpd);
         }
     }
 }
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-struct FeederWs {
-    unsigned* ticket;
-    unsigned long long* status;
-    int* dcount;
-    size_t zero_bytes;            // header + status + dcount: zeroed
-    unsigned long long* grid;
-    size_t grid_bytes;
-    size_t total_bytes;
-};
-
-FeederWs carve(void* base, int S, long long XZ) {
+FeederWs carve(void* base, const BevGeom& g, bool wide) {
     FeederWs w{};
     char* p = static_cast<char*>(base);
-    const long long total = XZ * (S + 1);
-    const long long tiles = (total + kEmitTile - 1) / kEmitTile > 0 ? (total + kEmitTile - 1) / kEmitTile : 1;
+    const long long XZ = (long long)g.X * g.Z;
+    const long long tiles = (long long)(g.S + 1) * g.tiles_per_plane;
     size_t off = 0;
     w.ticket = reinterpret_cast<unsigned*>(p + off);
     off += 64;
+    w.ctr = reinterpret_cast<int*>(p + off);
+    off += 192;
     w.status = reinterpret_cast<unsigned long long*>(p + off);
     off = align_up(off + sizeof(unsigned long long) * tiles, 64);
+    w.bitmap = reinterpret_cast<unsigned*>(p + off);
+    off = align_up(off + sizeof(unsigned) * (size_t)(g.S + 1) * g.W, 64);
     w.dcount = reinterpret_cast<int*>(p + off);
     off = align_up(off + sizeof(int) * XZ, 256);
     w.zero_bytes = off;
-    w.grid = reinterpret_cast<unsigned long long*>(p + off);
-    w.grid_bytes = sizeof(unsigned long long) * (size_t)S * XZ;
+    w.grid = p + off;
+    w.grid_bytes = (wide ? sizeof(unsigned long long) : sizeof(unsigned)) * (size_t)g.S * XZ;
     off = align_up(off + w.grid_bytes, 256);
     w.total_bytes = off;
     return w;
@@ -299,6 +318,18 @@ int make_geometry(BevGeom& g, const double* plane, const double* ext, double vox
     g.Z = (int)nz;
     g.min_x = (int)min_x;
     g.min_z = (int)min_z;
+    g.W = (int)(((long long)g.X * g.Z + 31) / 32);
+    g.tiles_per_plane = (g.W + kThreads - 1) / kThreads;
+    // y strictly inside the extents => floor(y / voxel) inside [floor(y_lo / voxel), floor(y_hi / voxel)] (division is monotone)
+    const double yd_lo = floor(ext[2] / voxel), yd_hi = floor(ext[3] / voxel);
+    g.yd_min = 0;
+    g.ybits = 32;                                     // 32: the 32-bit winner words cannot be used
+    if (yd_hi >= yd_lo && fabs(yd_lo) < 1e9 && yd_hi - yd_lo < 1e9) {
+        g.yd_min = (int)yd_lo;
+        const unsigned span = (unsigned)(yd_hi - yd_lo);
+        g.ybits = 0;
+        while (g.ybits < 32 && (span >> g.ybits) != 0u) ++g.ybits;
+    }
     // bev_slices.py:29-31, :66-67
     g.hpd = (height_hi - height_lo) / (double)S;
     for (int s = 0; s < S; ++s) {
@@ -330,7 +361,7 @@ extern "C" size_t shpl_bev_workspace_bytes(const double* extents_host, double vo
     const double plane[4] = {0, -1, 0, 0};
     BevGeom g{};
     if (make_geometry(g, plane, extents_host, voxel_size, 0.0, 1.0, num_slices, 1.0, "shpl_bev_workspace_bytes")) return 0;
-    return carve(nullptr, g.S, (long long)g.X * g.Z).total_bytes;
+    return carve(nullptr, g, true).total_bytes;       // sized for the 64-bit winner words
 }
 
 extern "C" int shpl_bev_slices(const double* points, int64_t coord_stride, int64_t point_stride, int64_t P,
@@ -350,12 +381,13 @@ extern "C" int shpl_bev_slices(const double* points, int64_t coord_stride, int64
     BevGeom g{};
     if (int rc = make_geometry(g, ground_plane_host, extents_host, voxel_size, height_lo, height_hi, num_slices, log_norm, who)) return rc;
     const long long XZ = (long long)g.X * g.Z;
-    FeederWs w = carve(workspace, g.S, XZ);
+    // 32-bit winner words (y bin | point index) when both fit; the all-ones word must stay unused ("empty")
+    const bool wide = !(g.ybits < 32 && (unsigned long long)P < (1ull << (32 - g.ybits)));
+    FeederWs w = carve(workspace, g, wide);
     SHPL_REQUIRE(w.total_bytes <= workspace_bytes, SHPL_ERR_WORKSPACE_TOO_SMALL, "%s: workspace %zu bytes < %zu needed", who,
                  workspace_bytes, w.total_bytes);
     SHPL_CUDA_OK(cudaMemsetAsync(workspace, 0, w.zero_bytes, s));
     SHPL_CUDA_OK(cudaMemsetAsync(w.grid, 0xff, w.grid_bytes, s));
-    SHPL_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * SHPL_BEV_COUNTS, s));
     if (bev_maps_out) SHPL_CUDA_OK(cudaMemsetAsync(bev_maps_out, 0, sizeof(double) * (size_t)(g.S + 1) * XZ, s));
 
     if (P > 0) {
@@ -365,10 +397,10 @@ extern "C" int shpl_bev_slices(const double* points, int64_t coord_stride, int64
         sa.point_stride = point_stride;
         sa.P = P;
         sa.g = g;
-        sa.grid = w.grid;
-        sa.dcount = w.dcount;
-        sa.counts = counts;
-        shpl_bev_scatter_kernel<<<(unsigned)((P + kThreads - 1) / kThreads), kThreads, 0, s>>>(sa);
+        sa.ws = w;
+        const unsigned blocks = (unsigned)((P + kThreads - 1) / kThreads);
+        if (wide) shpl_bev_scatter_kernel<unsigned long long><<<blocks, kThreads, 0, s>>>(sa);
+        else shpl_bev_scatter_kernel<unsigned><<<blocks, kThreads, 0, s>>>(sa);
         shpl::count_launches(1);
         if (int rc = shpl::check_launch("shpl_bev_scatter_kernel")) return rc;
     }
@@ -377,13 +409,9 @@ extern "C" int shpl_bev_slices(const double* points, int64_t coord_stride, int64
     ea.coord_stride = coord_stride;
     ea.point_stride = point_stride;
     ea.g = g;
-    ea.grid = w.grid;
-    ea.dcount = w.dcount;
-    ea.ticket = w.ticket;
-    ea.status = w.status;
-    const long long total = XZ * (g.S + 1);
-    ea.n_tiles = (int)((total + kEmitTile - 1) / kEmitTile);
-    ea.use_ticket = ea.n_tiles > shpl::sm_count() * 4 ? 1 : 0;
+    ea.ws = w;
+    const int n_tiles = (g.S + 1) * g.tiles_per_plane;
+    ea.use_ticket = n_tiles > shpl::sm_count() * 2 ? 1 : 0;
     ea.cap = capacity;
     ea.vox_out = reinterpret_cast<long long*>(voxel_indices_out);
     ea.pts_out = unique_pts_out;
@@ -391,7 +419,8 @@ extern "C" int shpl_bev_slices(const double* points, int64_t coord_stride, int64
     ea.lut = density_lut;
     ea.lut_len = lut_len;
     ea.counts = counts;
-    shpl_bev_emit_kernel<<<(unsigned)ea.n_tiles, kThreads, 0, s>>>(ea);
+    if (wide) shpl_bev_emit_kernel<unsigned long long><<<(unsigned)n_tiles, kThreads, 0, s>>>(ea);
+    else shpl_bev_emit_kernel<unsigned><<<(unsigned)n_tiles, kThreads, 0, s>>>(ea);
     shpl::count_launches(1);
     return shpl::check_launch("shpl_bev_emit_kernel");
 }

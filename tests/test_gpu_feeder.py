@@ -65,7 +65,7 @@ def test_bev_slices_matches_reference_fixture(shpl, golden_dir, seed, az):
 
 
 # ------------------------------------------------------------------ against the oracle, other shapes
-@pytest.mark.parametrize("case", ["tilted_plane", "coarse_voxels", "dense_ties", "three_slices"])
+@pytest.mark.parametrize("case", ["tilted_plane", "coarse_voxels", "dense_ties", "three_slices", "wide_words", "flat_y"])
 def test_bev_slices_matches_oracle(shpl, case):
     rng = np.random.default_rng(11)
     gp, ext, vox, cfg = GP, synth.AVOD_EXTENTS, synth.AVOD_VOXEL, CFG
@@ -79,6 +79,16 @@ def test_bev_slices_matches_oracle(shpl, case):
         # 60k points in a 3 m x 3 m patch on a 0.05 m lattice: many points share (cell, y bin); the lowest index must win
         pts = np.stack((rng.integers(-30, 30, 60000) * 0.05 + 0.013, 1.65 - rng.integers(0, 40, 60000) * 0.05 - 0.011,
                         rng.integers(200, 260, 60000) * 0.05 + 0.017), axis=1)
+    elif case == "wide_words":
+        # a y extent of 10^7 m needs 27 bits of y bin: the kernels fall back to 64-bit winner words
+        pts = synth.lidar_scan(10, az_step_deg=0.2)
+        ext = np.array([[-40.0, 40.0], [-1.0e7, 3.0], [0.0, 70.0]])
+    elif case == "flat_y":
+        # every point in one y bin: the winner is decided by the point index alone
+        pts = synth.lidar_scan(10, az_step_deg=0.2)
+        pts = pts[(pts[:, 1] > 1.601) & (pts[:, 1] < 1.699)]
+        ext = np.array([[-40.0, 40.0], [1.6001, 1.6999], [0.0, 70.0]])
+        cfg = types.SimpleNamespace(height_lo=-0.2, height_hi=0.3, num_slices=2)
     else:
         pts = synth.lidar_scan(7, az_step_deg=0.2)
         cfg = types.SimpleNamespace(height_lo=0.0, height_hi=1.5, num_slices=3)
