@@ -259,6 +259,31 @@ int shpl_bev_slices(const double* points, int64_t coord_stride, int64_t point_st
                     int64_t* voxel_indices_out, double* unique_pts_out, int64_t capacity,
                     double* bev_maps_out, int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * MV3D voxel feeder: the source of the non-homogeneous weights.  Replaces
+ *   point_cloud_2_top_sparse(points, ..., points_in_cam=True, img_index2=...)
+ *                                        MV3D_TF_release/lib/utils/construct_voxel.py:37-162
+ * (call site MV3D_TF_release/lib/roi_data_layer/minibatch_mv3d_img.py:93).
+ *   points f64 [n,4] camera frame (x, y, z, reflectance); img_index2 i64 [2,n] rounded pixel (u; v) of every point;
+ *   ranges_host f64 [6] = side_lo, side_hi, fwd_lo, fwd_hi, height_lo, height_hi (construct_voxel.py:11-13);
+ *   res / zres: horizontal / vertical voxel size; max_points = cfg.VOXEL_POINT_COUNT (:17).
+ * Outputs (n_in = points strictly inside the ranges, m = points kept after the per-voxel cap, V = voxels):
+ *   voxel_full_size_host i32 [3] (HOST, may be NULL) = (z_max+1, x_max+1, y_max+1)  (:84);
+ *   img_index_out i64 [3,capacity] rows (u, v, 0), first m columns valid, row stride = capacity  (:156-158);
+ *   bv_index_out i64 [capacity,2] = (forward cell, side cell)  (:159);
+ *   m_val_out f64 [capacity] = 1 / (points kept in the pair's voxel)  (:160);
+ *   feature_buffer f64 [voxel_capacity, max_points, 7], coordinate_buffer i64 [voxel_capacity,4] = (0, z, x, y),
+ *   number_buffer i64 [voxel_capacity]: the VoxelNet buffers of voxel_dict (:126-148), voxels in np.unique's
+ *   lexicographic (x, y, z) order; any of the three may be NULL;
+ *   counts i32 [8] (device): [0] = n_in, [1] = m, [2] = V, [3] = error bits (1: cell outside the grid,
+ *   2: m > capacity, 4: V > voxel_capacity). */
+size_t shpl_mv3d_workspace_bytes(int64_t n_max);
+int shpl_mv3d_voxelize(const double* points, const int64_t* img_index2, int64_t n, double res, double zres,
+                       const double* ranges_host, int32_t max_points, int32_t* voxel_full_size_host,
+                       int64_t* img_index_out, int64_t* bv_index_out, double* m_val_out, int64_t capacity,
+                       double* feature_buffer, int64_t* coordinate_buffer, int64_t* number_buffer,
+                       int64_t voxel_capacity, int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -99,3 +99,49 @@ def generate_bev(point_cloud, ground_plane, area_extents, voxel_size, height_lo,
     dm[vi[:, 0], vi[:, 2]] = np.minimum(1.0, np.log(num_pts + 1) / norm_value)   # bev_generator.py:35-36
     dm = np.flip(dm.transpose(), axis=0)
     return height_maps, dm, np.vstack(idx_stack), np.vstack(pts_stack)
+
+
+# ------------------------------------------------------------------ MV3D voxel feeder
+def point_cloud_2_top_sparse(points, img_index2, res, zres, side_range, fwd_range, height_range, max_points):
+    """CPU restatement of point_cloud_2_top_sparse(points, ..., points_in_cam=True, img_index2=...)
+        /root/reference/MV3D_TF_release/lib/utils/construct_voxel.py:37-162
+    points f64 [n,4] camera frame (x, y, z, reflectance); img_index2 int [2,n] (rounded pixel of every point).
+    Returns (voxel_dict, voxel_full_size, img_index int [3,m], bv_index int [m,2], M_val f64 [m]) like the
+    reference.  The per-voxel cap loop (:133-140) is restated with a stable sort instead of the Python loop.
+    Pinned against the reference's own output (tests/golden/mv3d_*.npz)."""
+    points = np.asarray(points, dtype=np.float64)[:, [2, 0, 1, 3]]                # :59 forward, side, height
+    x_max = int((side_range[1] - side_range[0]) / res)                            # :81-84
+    y_max = int((fwd_range[1] - fwd_range[0]) / res)
+    z_max = int((height_range[1] - height_range[0]) / zres)
+    voxel_full_size = np.array([z_max + 1, x_max + 1, y_max + 1])
+    filt = ((points[:, 0] > fwd_range[0]) & (points[:, 0] < fwd_range[1]) & (points[:, 1] > side_range[0])
+            & (points[:, 1] < side_range[1]) & (points[:, 2] > height_range[0]) & (points[:, 2] < height_range[1]))   # :89-96
+    pf = points[filt]
+    img2 = np.asarray(img_index2)[:, filt]
+    xyz = np.zeros((pf.shape[0], 3), dtype=int)
+    xyz[:, 0] = ((pf[:, 1] - side_range[0]) / res).astype(np.int32)                # :116-118
+    xyz[:, 1] = ((pf[:, 0] - fwd_range[0]) / res).astype(np.int32)
+    xyz[:, 2] = ((pf[:, 2] - height_range[0]) / zres).astype(np.int32)
+    uniq, inv = np.unique(xyz, axis=0, return_inverse=True)                         # :122
+    inv = np.asarray(inv).reshape(-1)
+    V = uniq.shape[0]
+    order = np.argsort(inv, kind="stable")                                          # voxel by voxel, input order inside
+    sinv = inv[order]
+    start = np.searchsorted(sinv, np.arange(V))
+    slot_sorted = np.arange(inv.size) - start[sinv]
+    slot = np.empty(inv.size, dtype=np.int64)
+    slot[order] = slot_sorted
+    keep = slot < max_points                                                        # :135-140
+    filt_indices = np.nonzero(keep)[0]
+    number = np.minimum(np.bincount(inv, minlength=V), max_points)
+    top = np.zeros((V, max_points, 7))
+    top[inv[filt_indices], slot[filt_indices], 0:4] = pf[filt_indices]
+    top[:, :, 4:7] = top[:, :, 0:3] - np.expand_dims(np.sum(top[:, :, 0:3], axis=1) / number[:, None], 1)   # :143
+    coord = np.zeros((V, 4), dtype=int)
+    coord[:, 1:4] = uniq[:, [2, 0, 1]]                                              # :128
+    voxel_dict = {'feature_buffer': top, 'coordinate_buffer': coord, 'number_buffer': number}
+    img2 = img2[:, filt_indices]
+    img_index = np.vstack((img2, np.zeros((1, img2.shape[1])).astype(int)))         # :156-158
+    bv_index = xyz[filt_indices, :][:, [1, 0]]                                      # :159
+    M_val = 1.0 / number[inv[filt_indices]]                                         # :160
+    return voxel_dict, voxel_full_size, img_index, bv_index, M_val

@@ -153,24 +153,39 @@ def main():
         print(name, {k: v.tolist() for k, v in rec.items() if k.startswith("M_size")})
 
     # ---- MV3D feeder: reference point_cloud_2_top_sparse ---------------------
-    try:
-        cv = import_mv3d_construct_voxel()
-        f = synth.mv3d_frame(seed=5, n_points=6000)
-        cam4 = np.c_[f["points_fsh"][:, [1, 2, 0]], np.zeros(len(f["points_fsh"]))]   # x, y, z, reflectance
+    mv3d_goldens(spu)
+
+
+MV3D_CASES = {
+    # name: (seed, n_points, kwargs of synth.mv3d_frame)
+    "mv3d_seed5": (5, 6000, {}),                                  # ped/cyc ranges (config_voxels.py:50-64), cap 45
+    "mv3d_car_seed6": (6, 9000, dict(car=True)),                  # car ranges (config_voxels.py:33-48), cap 35
+}
+
+
+def mv3d_goldens(spu):
+    cv = import_mv3d_construct_voxel()
+    for name, (seed, n, kw) in MV3D_CASES.items():
+        f = synth.mv3d_frame(seed=seed, n_points=n, **kw)
+        cam4 = synth.mv3d_cam4(f)                                 # x, y, z, reflectance
         calib = np.zeros((4, 12))
         calib[0] = synth.P2_KITTI.reshape(-1)
-        _, vfs, img_index, bv_index, M_val = cv.point_cloud_2_top_sparse(
-            cam4.copy(), points_in_cam=True, calib=calib, img_index2=f["img_index2"].copy())
+        cv.MAX_NUM_POINTS = f["max_points"]                       # module global = cfg.VOXEL_POINT_COUNT (construct_voxel.py:17)
+        vd, vfs, img_index, bv_index, M_val = cv.point_cloud_2_top_sparse(
+            cam4.copy(), res=f["res"], zres=f["zres"], side_range=f["side_range"], fwd_range=f["fwd_range"],
+            height_range=f["height_range"], points_in_cam=True, calib=calib, img_index2=f["img_index2"].copy())
         o = spu.produce_sparse_pooling_input(dict(img_index=np.array(img_index, dtype=np.float64), img_size=f["img_size"],
                                                   bv_index=bv_index, bv_size=[vfs[1], vfs[2]]), M_val=M_val, stride=[8, 2])
-        np.savez_compressed(os.path.join(OUT, "mv3d_seed5.npz"), input_sha=digest(f["points_fsh"], f["img_index2"]),
+        fb = vd["feature_buffer"]
+        assert fb.dtype == np.float64 and fb.shape[1:] == (f["max_points"], 7)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), input_sha=digest(f["points_fsh"], f["img_index2"]),
                             voxel_full_size=vfs, img_index=np.asarray(img_index).astype(np.int32), bv_index=bv_index.astype(np.int32),
                             M_val=M_val, row=o["Mij_pool"][:, 0].astype(np.int32), M_size=o["M_size"],
-                            flip=o["img_index_flip_pool"].astype(np.int32))
-        print("mv3d", vfs, "pairs", len(M_val), "M_size", o["M_size"], "min w", M_val.min())
-    except Exception as e:  # pragma: no cover
-        print("MV3D golden skipped:", repr(e))
-        raise
+                            flip=o["img_index_flip_pool"].astype(np.int32),
+                            coordinate_buffer=vd["coordinate_buffer"].astype(np.int32),
+                            number_buffer=vd["number_buffer"].astype(np.int32),
+                            feature_buffer_sha=digest(fb), feature_buffer_head=fb[:64])
+        print(name, vfs, "voxels", fb.shape[0], "pairs", len(M_val), "M_size", o["M_size"], "min w", M_val.min())
 
 
 def feeder_goldens():

@@ -131,7 +131,14 @@ def direct_pairs(seed, n, bev_hw=(700, 800), img_wh=(1200, 360), skew="uniform")
                 bv_size=np.array(bev_hw), img_size=np.array(img_wh))
 
 
-def mv3d_frame(seed, n_points=20000, max_points=45):
+def mv3d_cam4(frame):
+    """camera-frame [n,4] = (x, y, z, reflectance) of a mv3d_frame, as point_cloud_2_top_sparse(points_in_cam=True) takes it."""
+    fsh = frame["points_fsh"]
+    refl = (np.arange(len(fsh)) % 97) / 97.0
+    return np.c_[fsh[:, [1, 2, 0]], refl]
+
+
+def mv3d_frame(seed, n_points=20000, max_points=45, car=False):
     """MV3D ped/cyc feeder inputs: camera-frame points in
     fwd (0,48) x side (-20,20) x height (-1,3) at 0.2/0.2/0.4 m, a dense cluster so
     the 45-point cap bites, image padded to 1280x384 (config.py:229)."""
@@ -145,6 +152,15 @@ def mv3d_frame(seed, n_points=20000, max_points=45):
     cam = fsh[:, [1, 2, 0]]
     hom = np.c_[cam, np.ones(n_points)] @ P2_KITTI.T
     img_index2 = np.rint(np.stack((hom[:, 0] / hom[:, 2], hom[:, 1] / hom[:, 2]))).astype(int)
+    if car:      # config_voxels.py:33-48: side (-40,40), fwd (0,70.4), height (-3,1), 35 points per voxel
+        fsh = fsh * np.array([70.4 / 48.0, 2.0, 1.0]) - np.array([0.0, 0.0, 2.0])
+        cam = fsh[:, [1, 2, 0]]
+        hom = np.c_[cam, np.ones(n_points)] @ P2_KITTI.T
+        img_index2 = np.rint(np.stack((hom[:, 0] / hom[:, 2], hom[:, 1] / hom[:, 2]))).astype(int)
+        return dict(points_fsh=fsh, img_index2=img_index2, res=0.2, zres=0.4,
+                    side_range=(-40, 40 - 0.01), fwd_range=(0, 70.4 - 0.01), height_range=(-3, 1 - 0.01), max_points=35,
+                    bv_size=[int((40 - 0.01 - -40) / 0.2) + 1, int((70.4 - 0.01 - 0) / 0.2) + 1],
+                    img_size=np.array([1280, 384]), stride=[8, 2])
     return dict(points_fsh=fsh, img_index2=img_index2, res=0.2, zres=0.4,
                 # construct_voxel.py:11-13: ranges are (MIN, MAX-0.01) of config_voxels.py:50-57
                 side_range=(-20, 20 - 0.01), fwd_range=(0, 48 - 0.01), height_range=(-1, 3 - 0.01),

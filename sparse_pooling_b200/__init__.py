@@ -8,6 +8,7 @@ Layout (only what the hot path needs):
   sparse_pool_utils.py drop-in mirror of the reference module (same names / signatures)
   builder.py           batched device-resident correspondence builder
   bev_slices.py        drop-in mirror of the BEV slicing feeder (BevSlices.generate_bev)
+  construct_voxel.py   drop-in mirror of the MV3D voxel feeder (point_cloud_2_top_sparse)
   config.py            the model.proto / kitti_dataset.proto sparse-pooling switches
 """
 from . import _cabi  # noqa: F401  (raises ImportError when libshpl.so is missing)
@@ -19,3 +20,4 @@ from .sparse_pool_utils import (SparsePoolLayer, SparseTensor, _sparse_pool_op, 
                                 sparse_pool_layer)
 from .builder import build_avod_plan  # noqa: F401
 from .bev_slices import BevSlices  # noqa: F401
+from . import construct_voxel  # noqa: F401

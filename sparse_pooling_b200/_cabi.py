@@ -83,6 +83,10 @@ SIGNATURES = {
     "shpl_bev_slices": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, ctypes.c_double,
                                        ctypes.c_double, ctypes.c_double, c_int32, ctypes.c_double, c_void_p, c_int32,
                                        c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "shpl_mv3d_workspace_bytes": (c_size_t, [c_int64]),
+    "shpl_mv3d_voxelize": (ctypes.c_int, [c_void_p, c_void_p, c_int64, ctypes.c_double, ctypes.c_double, c_void_p, c_int32,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                          c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "shpl_pool_heavy": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p]),
 }

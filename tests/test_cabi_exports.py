@@ -30,7 +30,8 @@ def test_header_declares_the_expected_entry_points():
         "shpl_abi_version", "shpl_last_error", "shpl_kernel_launches", "shpl_build_workspace_bytes", "shpl_gen_input_avod",
         "shpl_produce_input", "shpl_build_avod", "shpl_plan_from_coo", "shpl_pool_forward", "shpl_pool_backward",
         "shpl_pool_forward_dual", "shpl_pool_backward_dual", "shpl_pool_heavy",
-        "shpl_bev_grid_dims", "shpl_bev_workspace_bytes", "shpl_bev_slices"])
+        "shpl_bev_grid_dims", "shpl_bev_workspace_bytes", "shpl_bev_slices",
+        "shpl_mv3d_workspace_bytes", "shpl_mv3d_voxelize"])
 
 
 def test_library_exports_every_declared_symbol(lib):

@@ -262,3 +262,30 @@ def test_feeder_oracle_matches_reference_bev_slices(golden_dir, seed, az):
     p2, i2 = synth.one_point_per_cell(pts)
     np.testing.assert_array_equal(i2, idx)
     np.testing.assert_array_equal(p2, upts)
+
+
+@pytest.mark.parametrize("name,seed,n,kw", [("mv3d_seed5", 5, 6000, {}), ("mv3d_car_seed6", 6, 9000, dict(car=True))])
+def test_mv3d_feeder_oracle_matches_reference(golden_dir, name, seed, n, kw):
+    """oracle/feeder_oracle.point_cloud_2_top_sparse against the reference's construct_voxel.py output:
+    pairs, weights, voxel coordinates / counts, and the [V, T, 7] feature buffer (by digest), bit for bit."""
+    from oracle import feeder_oracle as fo
+    g = load(golden_dir, name + ".npz")
+    f = synth.mv3d_frame(seed=seed, n_points=n, **kw)
+    assert digest(f["points_fsh"], f["img_index2"]) == str(g["input_sha"])
+    vd, vfs, img_index, bv_index, m_val = fo.point_cloud_2_top_sparse(
+        synth.mv3d_cam4(f), f["img_index2"], f["res"], f["zres"], f["side_range"], f["fwd_range"], f["height_range"],
+        f["max_points"])
+    np.testing.assert_array_equal(vfs, g["voxel_full_size"])
+    np.testing.assert_array_equal(img_index, g["img_index"])
+    np.testing.assert_array_equal(bv_index, g["bv_index"])
+    np.testing.assert_array_equal(m_val, g["M_val"])
+    np.testing.assert_array_equal(vd["coordinate_buffer"], g["coordinate_buffer"])
+    np.testing.assert_array_equal(vd["number_buffer"], g["number_buffer"])
+    np.testing.assert_array_equal(vd["feature_buffer"][:64], g["feature_buffer_head"])
+    assert digest(vd["feature_buffer"]) == str(g["feature_buffer_sha"])
+    assert vd["number_buffer"].max() == f["max_points"]          # the cap bites
+    # and it agrees with the weights-only restatement the other tests use
+    inrange, kept, bv2, mv2 = io.mv3d_voxel_weights(f["points_fsh"], f["res"], f["zres"], f["side_range"],
+                                                    f["fwd_range"], f["height_range"], f["max_points"])
+    np.testing.assert_array_equal(bv2, bv_index)
+    np.testing.assert_array_equal(mv2, m_val)
