@@ -18,6 +18,7 @@ N > 1: frames are independent -> each rank runs its own frames, no collective on
        NCCL is used only to take the max time over ranks.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -518,6 +519,100 @@ def run_gpu(args):
                                      "copied from pinned host memory, both plans built, forward+backward of both layers, "
                                      "4 KB of gradients + the plan counters read back to pinned host memory, every step"}
 
+    # ---- the feeder in front of the path: BevSlices.generate_bev of the raw scan on the
+    #      GPU (shpl_bev_slices), its pair count handed to the builders on the device (no host read in between)
+    feeder = None
+    try:
+        from sparse_pooling_b200 import bev_slices as bs
+        from oracle import feeder_oracle as fo
+        GP = np.array([0.0, -1.0, 0.0, 1.65])
+        scans = [np.ascontiguousarray(synth.lidar_scan(100 + rank * N_FRAMES + i, az_step_deg=AZ_STEP).T) for i in range(N_FRAMES)]
+        scan_pin = [torch.from_numpy(sc).pin_memory() for sc in scans]
+        p_max = max(sc.shape[1] for sc in scans)
+        stage_scan = torch.empty((3, p_max), dtype=torch.float64, device=dev)
+        work = bs.BevWorkspace(synth.AVOD_EXTENTS, synth.AVOD_VOXEL, 5, N_MAX, dev, with_maps=True)
+        lut = torch.from_numpy(bs.density_lut(np.log(16))).to(dev)
+        n_dev = ctypes.c_void_p(work.counts.data_ptr())
+
+        def feeder_call(fi, src=None):
+            sc = stage_scan if src is None else src
+            Pn = scans[fi].shape[1]
+            bs.bev_slices_raw(sc, sc.stride(0), sc.stride(1), Pn, GP, synth.AVOD_EXTENTS, synth.AVOD_VOXEL, -0.2, 2.3, 5,
+                              np.log(16), work, lut=lut)
+
+        scan_dev = [torch.from_numpy(sc).to(dev) for sc in scans]
+        for fi in range(N_FRAMES):
+            feeder_call(fi, scan_dev[fi])
+        torch.cuda.synchronize()
+        assert int(work.counts[0].item()) == n_pts[N_FRAMES - 1], "feeder pair count differs from the frame's"
+        fg = []
+        for fi in range(N_FRAMES):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                feeder_call(fi, scan_dev[fi])
+            fg.append(gr)
+        evf0, evf1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        evf0.record()
+        for k in range(K):
+            fg[k % N_FRAMES].replay()
+        evf1.record()
+        torch.cuda.synchronize()
+        feeder_us = evf0.elapsed_time(evf1) * 1e3 / K
+
+        def scan_step(k):
+            fi, si = k % N_FRAMES, k % n_sets
+            pipe, mp = pipes[si], maps[si]
+            Pn = scans[fi].shape[1]
+            stage_scan[:, :Pn].copy_(scan_pin[fi], non_blocking=True)
+            ms = torch.cuda.current_stream().cuda_stream
+            feeder_call(fi)
+            for li in range(len(specs)):
+                pipe.build_layer(li, work.unique_pts, work.voxel_indices, P, N_MAX, ms, n_dev=n_dev)
+            for li in range(len(specs)):
+                pipe.forward_layer(li, mp[li]["bev"], mp[li]["img"], ms, N_MAX)
+            for li in reversed(range(len(specs))):
+                pipe.backward_layer(li, mp[li]["g_bev"], mp[li]["g_img"], ms, N_MAX)
+            off = 0
+            for li in range(len(specs)):
+                res_dev[off:off + 256].copy_(pipe.layers[li].g_bev.reshape(-1)[:256])
+                res_dev[off + 256:off + 512].copy_(pipe.layers[li].g_img.reshape(-1)[:256])
+                off += 512
+            res_dev[off:off + 16].copy_(torch.cat([L.plan.counts.reshape(-1)[:8] for L in pipe.layers]).float())
+            res_pin.copy_(res_dev, non_blocking=False)
+
+        for k in range(3):
+            scan_step(k)
+        torch.cuda.synchronize()
+        ref_counts = [int(x) for x in res_pin[-16:].tolist()]
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(K_e2e):
+            scan_step(k)
+        torch.cuda.synchronize()
+        dt_scan = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt_scan], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_scan = float(t.item())
+        t0 = time.perf_counter()
+        for fi in range(N_FRAMES):
+            fo.generate_bev(scans[fi], GP, synth.AVOD_EXTENTS, synth.AVOD_VOXEL, -0.2, 2.3, 5)
+        cpu_ms = (time.perf_counter() - t0) * 1e3 / N_FRAMES
+        feeder = {"what": "BevSlices.generate_bev(output_indices=True) on the GPU: 5 height maps + density map [6,700,800] f64, "
+                          "voxel_indices, unique_pts (shpl_bev_slices, CUDA-graph replays, CUDA events)",
+                  "us_per_frame": feeder_us, "points_per_scan": [int(sc.shape[1]) for sc in scans],
+                  "cpu_oracle_ms_per_frame": cpu_ms,
+                  "e2e_from_scan": {"value": world * K_e2e / dt_scan, "unit": UNIT,
+                                    "h2d_bytes_per_step": int(scans[0].shape[1] * 24), "d2h_bytes_per_step": int(res_pin.numel() * 4),
+                                    "what": "raw scan [3,P] f64 copied from pinned host memory, feeder, both plans built from the "
+                                            "feeder's device-side pair count, forward+backward of both layers, gradients + plan "
+                                            "counters read back, every step (ctypes C-ABI calls)"},
+                  "plan_counts_check": ref_counts[:4]}
+    except Exception as ex:  # pragma: no cover
+        print("feeder leg failed: %r" % (ex,), file=sys.stderr)
+        torch.cuda.synchronize()
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -544,6 +639,8 @@ def run_gpu(args):
                        "step_frac_of_peak": step_gbs / peak},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
         }
+        if feeder is not None:
+            line["feeder"] = feeder
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))

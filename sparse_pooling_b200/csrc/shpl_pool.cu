@@ -26,6 +26,7 @@
 // Sums run in stored (ascending k) order with separately rounded multiply and add, which makes
 // the result bit-identical to the sequential oracle.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "shpl_common.cuh"
 
@@ -171,13 +172,12 @@ template <typename V, bool kAdd>
 __device__ __forceinline__ void pool_tile(const V* __restrict__ src, int src_stride, const int* __restrict__ ptr,
                                           const int* __restrict__ idx, const float* __restrict__ val,
                                           V* __restrict__ out, int out_stride, const V* __restrict__ addend,
-                                          int add_stride, int nv, int shift, int rows, int heavy_len, int lane) {
-    int lo = 0, hi = 0;
-    if (lane < rows) {
-        lo = __ldg(ptr + lane);
-        hi = __ldg(ptr + lane + 1);
-        if (heavy_len > 0 && hi - lo > heavy_len) hi = lo;     // heavy cell: shpl_pool_heavy writes it
-    }
+                                          int add_stride, int nv, int shift, int rows, int heavy_len, int lane,
+                                          int lo, int hi) {
+    // lo, hi: this lane's cell offsets ptr[lane], ptr[lane+1] (0, 0 beyond `rows`), loaded by the caller
+    // together with the dense loads so that the two latencies overlap
+    (void)ptr;
+    if (heavy_len > 0 && hi - lo > heavy_len) hi = lo;         // heavy cell: shpl_pool_heavy writes it
     const unsigned busy = __ballot_sync(kFull, hi > lo);
     const int n = rows * nv;
     if (busy == 0u) {  // the common case: nothing projects into this tile
@@ -269,6 +269,11 @@ __global__ void __launch_bounds__(kThreads, SHPL_NARROW_MIN_CTAS) shpl_pool_narr
         const int r0 = t * jb.rows_per_tile;
         const int rows = min(jb.rows_per_tile, jb.n_cells - r0);
         const V* din = dense_in + (size_t)r0 * jb.dense_in_stride;
+        int lo = 0, hi = 0;
+        if (jb.vs > 0 && lane < rows) {
+            lo = __ldg(jb.ptr + r0 + lane);
+            hi = __ldg(jb.ptr + r0 + lane + 1);
+        }
         if constexpr (!kAdd) {
             if (jb.vd > 0)
                 copy_tile<V>(din, jb.dense_in_stride, dense_out + (size_t)r0 * jb.dense_out_stride,
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, SHPL_NARROW_MIN_CTAS) shpl_pool_narr
         if (jb.vs > 0)
             pool_tile<V, kAdd>(gather_in, jb.gather_stride, jb.ptr + r0, jb.idx, jb.val,
                                pool_out + (size_t)r0 * jb.pool_out_stride, jb.pool_out_stride, din,
-                               jb.dense_in_stride, jb.vs, jb.vs_shift, rows, jb.heavy_len, lane);
+                               jb.dense_in_stride, jb.vs, jb.vs_shift, rows, jb.heavy_len, lane, lo, hi);
     }
 }
 
@@ -713,6 +718,35 @@ struct JobSpec {            // in floats / cells, before the vector width is cho
     int heavy_len = 0;
 };
 
+// resident CTAs per SM of the narrow kernel instance (occupancy query, cached); SHPL_NARROW_CTAS_PER_SM overrides
+// it for experiments
+int narrow_ctas_per_sm(int w, bool add) {
+    static int cached[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    static int env = 0;
+    static bool read_env = false;
+    if (!read_env) {
+        read_env = true;
+        const char* e = getenv("SHPL_NARROW_CTAS_PER_SM");
+        env = e ? atoi(e) : 0;      // > 0: that many; < 0 (e.g. -1): what the occupancy query says; unset: 8
+    }
+    if (env > 0) return env;
+    if (env == 0) return 8;
+    const int wi = w == 4 ? 2 : (w == 2 ? 1 : 0);
+    int& c = cached[wi][add ? 1 : 0];
+    if (c == 0) {
+        int n = 0;
+        cudaError_t e;
+        if (w == 4 && add) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shpl_pool_narrow_kernel<4, true>, kThreads, 0);
+        else if (w == 4) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shpl_pool_narrow_kernel<4, false>, kThreads, 0);
+        else if (w == 2 && add) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shpl_pool_narrow_kernel<2, true>, kThreads, 0);
+        else if (w == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shpl_pool_narrow_kernel<2, false>, kThreads, 0);
+        else if (add) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shpl_pool_narrow_kernel<1, true>, kThreads, 0);
+        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shpl_pool_narrow_kernel<1, false>, kThreads, 0);
+        c = (e == cudaSuccess && n > 0) ? n : SHPL_NARROW_MIN_CTAS;
+    }
+    return c;
+}
+
 int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* who) {
     int w = 4, max_vs = 0;
     for (int i = 0; i < n_specs; ++i) {
@@ -783,7 +817,10 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
         // partition the resident grid between the jobs in proportion to their tiles (a CTA serves one job)
         long long total_tiles = 0;
         for (int i = 0; i < a.n_jobs; ++i) total_tiles += a.job[i].tiles;
-        const long long cap = (long long)shpl::sm_count() * 8;   // resident CTAs of 256 threads per SM
+        // 8 CTAs per SM although only 3 are resident (80 registers): measured on B200 (profiles/README.md), a grid of
+        // exactly the resident CTAs is 15 % slower -- the late waves start on SMs whose first CTAs have drained and
+        // keep the memory pipes fed through the tail.
+        const long long cap = (long long)shpl::sm_count() * narrow_ctas_per_sm(w, a.job[0].add != 0);
         long long want = (total_tiles + kWarps - 1) / kWarps;
         if (want > cap) want = cap;
         a.begin[0] = 0;

@@ -15,7 +15,9 @@ _lib = _cabi.lib
 
 
 def _ptr(t):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    if t is None or isinstance(t, ctypes.c_void_p):
+        return t
+    return ctypes.c_void_p(t.data_ptr())
 
 
 def _stream():
@@ -51,6 +53,8 @@ class SparsePoolPlan:
     rows / pixels of frame f are offset by f*rows_per_frame / f*src_per_frame so a
     [B,H,W,C] batch is pooled by one launch."""
 
+    _INT_FIELDS = ("row_ptr", "pix_ptr", "csr_row", "csr_src", "csrT_pix", "csrT_dst", "heavy_row", "heavy_pix")
+
     def __init__(self, rows_per_frame, src_hw, capacity, device, frames=1):
         self.frames = int(frames)
         self.rows_per_frame = int(rows_per_frame)
@@ -61,34 +65,80 @@ class SparsePoolPlan:
         R, Q = self.rows_per_frame * self.frames, self.src_per_frame * self.frames
         if max(R, Q, self.capacity) >= 2 ** 31 - 1:
             raise ValueError("SHPL plan too large for 32-bit indices")
-        # one allocation for every int32 array, one for the weights (16-byte aligned sub-arrays)
+        # one allocation for every int32 array, one for the weights (16-byte aligned sub-arrays).  The tensor
+        # views of the sub-arrays are made on first use only (a view costs microseconds of host time and the
+        # hot path needs nothing but addresses).
         cap = self.capacity
 
         def up(x):
             return (x + 3) // 4 * 4
         self.heavy_cap = cap // _cabi.HEAVY_LEN + 1      # cells that can hold more than HEAVY_LEN of `cap` entries
         hc = up(self.heavy_cap)
+        lens = [R + 1, Q + 1, cap, cap, cap, cap, self.heavy_cap, self.heavy_cap]
         sizes = [up(R + 1), up(Q + 1), up(cap), up(cap), up(cap), up(cap), hc, hc, up(8 * self.frames) + 4]
-        ints = torch.empty(sum(sizes), dtype=torch.int32, device=device)
-        parts, off = [], 0
-        for n in sizes:
-            parts.append(ints[off:off + n])
-            off += n
-        self.row_ptr = parts[0][:R + 1]
-        self.pix_ptr = parts[1][:Q + 1]
-        self.csr_row, self.csr_src, self.csrT_pix, self.csrT_dst = (p[:cap] for p in parts[2:6])
-        self.heavy_row, self.heavy_pix = parts[6][:self.heavy_cap], parts[7][:self.heavy_cap]
-        self._meta = parts[8]                                        # counts of every frame, then the 2 heavy counters
-        self.counts = self._meta[:8 * self.frames].view(self.frames, 8)
-        self.heavy_count = self._meta[up(8 * self.frames):up(8 * self.frames) + 2]
+        self._ints = torch.empty(sum(sizes), dtype=torch.int32, device=device)
+        self._span = {}
+        off = 0
+        for name, n, sz in zip(self._INT_FIELDS, lens, sizes):
+            self._span[name] = (off, n)
+            off += sz
+        self._meta_off = off                               # counts of every frame, then the 2 heavy counters
+        self._heavy_count_off = off + up(8 * self.frames)
+        self._views = {}
+        self._meta = self._ints[off:]
         self._meta.zero_()
+        self._vals = torch.empty(2 * up(cap), dtype=torch.float32, device=device)
+        self._val_span = {"csr_val": (0, cap), "csrT_val": (up(cap), cap)}
+        self._ibase = self._ints.data_ptr()
+        self._vbase = self._vals.data_ptr()
         self.n_heavy = None   # (rows, pixels) with more than HEAVY_LEN entries; host ints after read_counts
-        vals = torch.empty(2 * up(cap), dtype=torch.float32, device=device)
-        self.csr_val = vals[:cap]
-        self.csrT_val = vals[up(cap):up(cap) + cap]
         self.entry_bound = self.capacity   # host-known upper bound on the entries (builders tighten it)
         self.nnz = None       # columns of M per frame (host ints), known after the builder's read-back
         self.n_oob = None     # entries TF-CPU would reject, per frame
+        self._ptr8 = None
+
+    def __getattr__(self, name):
+        # lazily made tensor views of the sub-arrays (row_ptr, csr_src, csr_val, counts, ...)
+        d = self.__dict__
+        views = d.get("_views")
+        if views is None:
+            raise AttributeError(name)
+        v = views.get(name)
+        if v is not None:
+            return v
+        if name in d.get("_span", ()):
+            off, n = d["_span"][name]
+            v = d["_ints"][off:off + n]
+        elif name in d.get("_val_span", ()):
+            off, n = d["_val_span"][name]
+            v = d["_vals"][off:off + n]
+        elif name == "counts":
+            v = d["_ints"][d["_meta_off"]:d["_meta_off"] + 8 * d["frames"]].view(d["frames"], 8)
+        elif name == "heavy_count":
+            v = d["_ints"][d["_heavy_count_off"]:d["_heavy_count_off"] + 2]
+        else:
+            raise AttributeError(name)
+        views[name] = v
+        return v
+
+    def addr(self, name):
+        """Device address of a sub-array (no tensor view is created)."""
+        if name in self._span:
+            return self._ibase + 4 * self._span[name][0]
+        if name in self._val_span:
+            return self._vbase + 4 * self._val_span[name][0]
+        if name == "counts":
+            return self._ibase + 4 * self._meta_off
+        if name == "heavy_count":
+            return self._ibase + 4 * self._heavy_count_off
+        raise KeyError(name)
+
+    def ptrs8(self):
+        """ctypes pointers of the eight index arrays, in the argument order of the dual-direction entry points."""
+        if self._ptr8 is None:
+            self._ptr8 = [ctypes.c_void_p(self.addr(n)) for n in ("row_ptr", "csr_row", "csr_src", "csr_val",
+                                                                  "pix_ptr", "csrT_pix", "csrT_dst", "csrT_val")]
+        return self._ptr8
 
     @property
     def n_rows(self):
@@ -100,38 +150,41 @@ class SparsePoolPlan:
 
     def by_row(self):
         """(ptr, key, idx, val, nnz_max) of the CSR keyed by destination BEV cell."""
-        return (self.row_ptr, self.csr_row, self.csr_src, self.csr_val, self.entry_bound, self.heavy(False))
+        p = self.ptrs8()
+        return (p[0], p[1], p[2], p[3], self.entry_bound, self.heavy(False))
 
     def by_pixel(self):
         """(ptr, key, idx, val, nnz_max) of the CSR^T keyed by source pixel."""
-        return (self.pix_ptr, self.csrT_pix, self.csrT_dst, self.csrT_val, self.entry_bound, self.heavy(True))
+        p = self.ptrs8()
+        return (p[4], p[5], p[6], p[7], self.entry_bound, self.heavy(True))
 
     def frame_struct(self, f):
         """shpl_plan for frame f: ptr arrays point at the frame's sub-array; entry arrays are shared."""
         s = _cabi.ShplPlan()
+        a = self.addr
         s.n_rows = self.rows_per_frame
         s.n_src = self.src_per_frame
         s.capacity = self.capacity
-        s.row_ptr = self.row_ptr.data_ptr() + 4 * f * self.rows_per_frame
-        s.pix_ptr = self.pix_ptr.data_ptr() + 4 * f * self.src_per_frame
-        s.csr_row = self.csr_row.data_ptr()
-        s.csr_src = self.csr_src.data_ptr()
-        s.csrT_pix = self.csrT_pix.data_ptr()
-        s.csr_val = self.csr_val.data_ptr()
-        s.csrT_dst = self.csrT_dst.data_ptr()
-        s.csrT_val = self.csrT_val.data_ptr()
+        s.row_ptr = a("row_ptr") + 4 * f * self.rows_per_frame
+        s.pix_ptr = a("pix_ptr") + 4 * f * self.src_per_frame
+        s.csr_row = a("csr_row")
+        s.csr_src = a("csr_src")
+        s.csrT_pix = a("csrT_pix")
+        s.csr_val = a("csr_val")
+        s.csrT_dst = a("csrT_dst")
+        s.csrT_val = a("csrT_val")
         s.heavy_cap = self.heavy_cap
-        s.heavy_row = self.heavy_row.data_ptr()
-        s.heavy_pix = self.heavy_pix.data_ptr()
-        s.heavy_count = self.heavy_count.data_ptr()
-        s.counts = self.counts.data_ptr() + 32 * f
+        s.heavy_row = a("heavy_row")
+        s.heavy_pix = a("heavy_pix")
+        s.heavy_count = a("heavy_count")
+        s.counts = a("counts") + 32 * f
         return s
 
     def entry_base(self, f):
         """Device pointer to the running entry offset frame f must start at (None for frame 0)."""
         if f == 0:
             return None
-        return ctypes.c_void_p(self.counts.data_ptr() + 32 * (f - 1) + 16)   # counts[f-1][4]
+        return ctypes.c_void_p(self.addr("counts") + 32 * (f - 1) + 16)   # counts[f-1][4]
 
     def read_counts(self):
         """One small device->host copy: fills nnz / n_oob (synchronises the stream)."""
@@ -144,9 +197,11 @@ class SparsePoolPlan:
         return c
 
     def heavy(self, by_pixel):
-        """(list, count_dev, how many to expect or None when the counters have not been read back)."""
+        """(list pointer, device counter pointer, list capacity, how many to expect or None when the counters have
+        not been read back)."""
         k = 1 if by_pixel else 0
-        return ((self.heavy_pix if by_pixel else self.heavy_row), self.heavy_count[k:k + 1],
+        return (ctypes.c_void_p(self.addr("heavy_pix" if by_pixel else "heavy_row")),
+                ctypes.c_void_p(self.addr("heavy_count") + 4 * k), self.heavy_cap,
                 None if self.n_heavy is None else self.n_heavy[k])
 
 
@@ -176,11 +231,11 @@ def plan_from_coo(indices, values, source_index, n_rows, src_hw, device=None):
 
 def _run_heavy(heavy, gather_in, gather_stride, C, ptr, idx, val, addend, addend_stride, out, out_stride):
     """shpl_pool_heavy on the listed heavy cells, unless the host already knows there are none."""
-    lst, count_dev, expected = heavy
+    lst, count_dev, cap, expected = heavy
     if expected == 0:
         return
-    rc = _lib.shpl_pool_heavy(gather_in, gather_stride, C, _ptr(ptr), _ptr(idx), _ptr(val), _ptr(lst), _ptr(count_dev),
-                              int(lst.numel()), addend, addend_stride, out, out_stride, _stream())
+    rc = _lib.shpl_pool_heavy(gather_in, gather_stride, C, _ptr(ptr), _ptr(idx), _ptr(val), lst, count_dev,
+                              int(cap), addend, addend_stride, out, out_stride, _stream())
     _cabi.check(rc, "shpl_pool_heavy")
 
 
@@ -269,8 +324,7 @@ class SparsePoolFunction(torch.autograd.Function):
 
 
 def _plan_ptrs(plan):
-    return [_ptr(t) for t in (plan.row_ptr, plan.csr_row, plan.csr_src, plan.csr_val,
-                              plan.pix_ptr, plan.csrT_pix, plan.csrT_dst, plan.csrT_val)]
+    return plan.ptrs8()
 
 
 class SparsePoolDualFunction(torch.autograd.Function):
@@ -293,12 +347,13 @@ class SparsePoolDualFunction(torch.autograd.Function):
                              % (tuple(bev.shape), tuple(img.shape), R, Q))
         fused_bev = torch.empty(tuple(bev.shape[:3]) + (Cb + Ci,), dtype=torch.float32, device=bev.device)
         fused_img = torch.empty(tuple(img.shape[:3]) + (Ci + Cb,), dtype=torch.float32, device=bev.device)
-        rc = _lib.shpl_pool_forward_dual(_ptr(b), _ptr(i), *_plan_ptrs(plan), int(plan.entry_bound), _cabi.HEAVY_LEN,
+        P8 = plan.ptrs8()
+        rc = _lib.shpl_pool_forward_dual(_ptr(b), _ptr(i), *P8, int(plan.entry_bound), _cabi.HEAVY_LEN,
                                          R, Cb, Q, Ci, _ptr(fused_bev), _ptr(fused_img), _stream())
         _cabi.check(rc, "shpl_pool_forward_dual")
-        _run_heavy(plan.heavy(False), _ptr(i), Ci, Ci, plan.row_ptr, plan.csr_src, plan.csr_val, None, 0,
+        _run_heavy(plan.heavy(False), _ptr(i), Ci, Ci, P8[0], P8[2], P8[3], None, 0,
                    _off(fused_bev, Cb), Cb + Ci)
-        _run_heavy(plan.heavy(True), _ptr(b), Cb, Cb, plan.pix_ptr, plan.csrT_dst, plan.csrT_val, None, 0,
+        _run_heavy(plan.heavy(True), _ptr(b), Cb, Cb, P8[4], P8[6], P8[7], None, 0,
                    _off(fused_img, Ci), Ci + Cb)
         ctx.plan = plan
         ctx.shapes = (tuple(bev.shape), tuple(img.shape))
@@ -313,13 +368,14 @@ class SparsePoolDualFunction(torch.autograd.Function):
         gi = g_fused_img.contiguous()
         g_bev = torch.empty(sb, dtype=torch.float32, device=gb.device)
         g_img = torch.empty(si, dtype=torch.float32, device=gb.device)
-        rc = _lib.shpl_pool_backward_dual(_ptr(gb), _ptr(gi), *_plan_ptrs(plan), int(plan.entry_bound), _cabi.HEAVY_LEN,
+        P8 = plan.ptrs8()
+        rc = _lib.shpl_pool_backward_dual(_ptr(gb), _ptr(gi), *P8, int(plan.entry_bound), _cabi.HEAVY_LEN,
                                           R, Cb, Q, Ci, _ptr(g_bev), _ptr(g_img), _stream())
         _cabi.check(rc, "shpl_pool_backward_dual")
         # g_bev[r] = g_fused_bev[r,:Cb] + sum_{k in row r} val * g_fused_img[pix_k, Ci:]   (heavy rows)
-        _run_heavy(plan.heavy(False), _off(gi, Ci), Ci + Cb, Cb, plan.row_ptr, plan.csr_src, plan.csr_val,
+        _run_heavy(plan.heavy(False), _off(gi, Ci), Ci + Cb, Cb, P8[0], P8[2], P8[3],
                    _ptr(gb), Cb + Ci, _ptr(g_bev), Cb)
-        _run_heavy(plan.heavy(True), _off(gb, Cb), Cb + Ci, Ci, plan.pix_ptr, plan.csrT_dst, plan.csrT_val,
+        _run_heavy(plan.heavy(True), _off(gb, Cb), Cb + Ci, Ci, P8[4], P8[6], P8[7],
                    _ptr(gi), Ci + Cb, _ptr(g_img), Ci)
         return g_bev, g_img, None
 

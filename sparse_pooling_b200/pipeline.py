@@ -77,8 +77,7 @@ class _LayerState:
         if spec.dual:
             self.fused_img = torch.empty((1,) + spec.img_hw + (spec.c_img + spec.c_bev,), **f32)
         pl = self.plan
-        self.plan_ptrs = [_p(t) for t in (pl.row_ptr, pl.csr_row, pl.csr_src, pl.csr_val,
-                                          pl.pix_ptr, pl.csrT_pix, pl.csrT_dst, pl.csrT_val)]
+        self.plan_ptrs = pl.ptrs8()
 
 
 class FramePipeline:
