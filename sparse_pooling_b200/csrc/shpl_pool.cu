@@ -100,6 +100,21 @@ __device__ __forceinline__ float2 vadd(const float2& a, const float2& b) {
 }
 __device__ __forceinline__ float vadd(const float& a, const float& b) { return __fadd_rn(a, b); }
 
+// w * x with one rounding per component (the first half of axpy)
+__device__ __forceinline__ float4 vscale(float w, const float4& x) {
+    return make_float4(__fmul_rn(w, x.x), __fmul_rn(w, x.y), __fmul_rn(w, x.z), __fmul_rn(w, x.w));
+}
+__device__ __forceinline__ float2 vscale(float w, const float2& x) { return make_float2(__fmul_rn(w, x.x), __fmul_rn(w, x.y)); }
+__device__ __forceinline__ float vscale(float w, const float& x) { return __fmul_rn(w, x); }
+__device__ __forceinline__ float4 vshfl(const float4& v, int src) {
+    return make_float4(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src),
+                       __shfl_sync(0xffffffffu, v.z, src), __shfl_sync(0xffffffffu, v.w, src));
+}
+__device__ __forceinline__ float2 vshfl(const float2& v, int src) {
+    return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+__device__ __forceinline__ float vshfl(const float& v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
 struct Job {
     const void* dense_in;    // [n_cells, dense_in_stride] vectors; first vd of each cell are used
     const void* gather_in;   // rows gathered through idx, gather_stride vectors apart (channel offset applied)
@@ -165,6 +180,60 @@ __device__ __forceinline__ void copy_tile(const V* __restrict__ in, int in_strid
     }
 }
 
+constexpr int kLongRow = 32;      // narrow kernels: cells with more entries are summed by the whole warp
+constexpr int kLongUnroll = 4;
+
+// One long cell by the whole warp (narrow kernels).  The lanes form E = 32 / nv groups of nv lanes; group g
+// gathers entry k0 + u*E + g, so E * kLongUnroll gathers of the cell are in flight at once instead of the 4 the
+// cell's own nv lanes would have.  The products w*x are then handed to lanes 0..nv-1 by shuffles and added
+// there in ascending k: the same roundings in the same order as the sequential walk, bit for bit.
+template <typename V>
+__device__ __forceinline__ V long_row_sum(const V* __restrict__ src, int src_stride, const int* __restrict__ idx,
+                                          const float* __restrict__ val, int beg, int end, int nv, int lane) {
+    const int E = 32 / nv;
+    const int sub = lane / nv, q = lane - sub * nv;
+    const bool active = sub < E;
+    V acc = vzero((V*)nullptr);
+    for (int k0 = beg; k0 < end; k0 += E * kLongUnroll) {
+        V prod[kLongUnroll];
+#pragma unroll
+        for (int u = 0; u < kLongUnroll; ++u) {
+            const int k = k0 + u * E + sub;
+            prod[u] = vzero((V*)nullptr);
+            if (active && k < end) {
+                const int p = __ldg(idx + k);
+                const float w = __ldg(val + k);
+                prod[u] = vscale(w, __ldg(src + (size_t)p * src_stride + q));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kLongUnroll; ++u) {
+            const int left = end - (k0 + u * E);              // warp-uniform
+            for (int e = 0; e < E && e < left; ++e) acc = vadd(acc, vshfl(prod[u], e * nv + q));
+        }
+    }
+    return acc;
+}
+
+// The long cells of a warp tile (bit mask `longs`), one after the other, each by the whole warp.  Out of line on
+// purpose: the call sits on a rare path, and inlining it cost the streaming path registers (measured: +25 % time
+// on the KITTI stride-1 forward).
+template <typename V, bool kAdd>
+__device__ __noinline__ void long_cells(const V* __restrict__ src, int src_stride, const int* __restrict__ ptr,
+                                        const int* __restrict__ idx, const float* __restrict__ val, V* __restrict__ out,
+                                        int out_stride, const V* __restrict__ addend, int add_stride, int nv,
+                                        unsigned longs, int lane) {
+    for (unsigned m = longs; m; m &= m - 1) {
+        const int r = __ffs(m) - 1;
+        const int beg = __ldg(ptr + r), end = __ldg(ptr + r + 1);
+        V acc = long_row_sum<V>(src, src_stride, idx, val, beg, end, nv, lane);
+        if (lane < nv) {
+            if constexpr (kAdd) acc = vadd(ld_stream(addend + r * add_stride + lane), acc);
+            st_stream(out + r * out_stride + lane, acc);
+        }
+    }
+}
+
 // Pooled part by one warp: out[r*out_stride + q] = (addend ? addend[r*add_stride + q] : 0) +
 // sum_k val[k] * src[idx[k]*src_stride + q], k in [ptr[r], ptr[r+1]).  nv lanes per cell, 32/nv cells
 // side by side.
@@ -176,9 +245,11 @@ __device__ __forceinline__ void pool_tile(const V* __restrict__ src, int src_str
                                           int lo, int hi) {
     // lo, hi: this lane's cell offsets ptr[lane], ptr[lane+1] (0, 0 beyond `rows`), loaded by the caller
     // together with the dense loads so that the two latencies overlap
-    (void)ptr;
     if (heavy_len > 0 && hi - lo > heavy_len) hi = lo;         // heavy cell: shpl_pool_heavy writes it
     const unsigned busy = __ballot_sync(kFull, hi > lo);
+    // long cells: left empty by the lane-per-vector walk below, then summed by the whole warp
+    const unsigned longs = __ballot_sync(kFull, hi - lo > kLongRow);
+    if (hi - lo > kLongRow) hi = lo;
     const int n = rows * nv;
     if (busy == 0u) {  // the common case: nothing projects into this tile
         if constexpr (kAdd) {
@@ -235,6 +306,10 @@ __device__ __forceinline__ void pool_tile(const V* __restrict__ src, int src_str
         }
         if constexpr (kAdd) acc = vadd(base, acc);
         if (s < n) st_stream(out + r * out_stride + q, acc);
+    }
+    if (longs != 0u) {
+        __syncwarp();      // orders the stores above before the overwrites below (other lanes, same addresses)
+        long_cells<V, kAdd>(src, src_stride, ptr, idx, val, out, out_stride, addend, add_stride, nv, longs, lane);
     }
 }
 
@@ -590,7 +665,7 @@ struct HeavyArgs {
     int nv;                                          // vectors per cell
 };
 
-template <int W>
+template <int W, bool kGroups>
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads) shpl_pool_heavy_kernel(HeavyArgs a) {
     using V = typename VecOf<W>::type;
     extern __shared__ float4 heavy_smem[];
@@ -611,6 +686,36 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
         const int piece = crank * kWarps + warp;
         const int pb = beg + (int)(L * piece / (kClusterSize * kWarps));
         const int pe = beg + (int)(L * (piece + 1) / (kClusterSize * kWarps));
+        if constexpr (kGroups) {
+            // few channels (nv <= 16): lanes would idle if they mapped to channel vectors only.  E = 32 / nv lane groups
+            // take entries pb + g, pb + g + E, ... (kGatherUnroll gathers in flight each); the group sums are
+            // then added in group order -- still a fixed tree.
+            const int nv = a.nv, E = 32 / nv;
+            const int g = lane / nv, q = lane - g * nv;
+            V acc = vzero((V*)nullptr);
+            if (g < E) {
+                for (int c = pb + g; c < pe; c += E * kGatherUnroll) {
+                    V x[kGatherUnroll];
+                    float w[kGatherUnroll];
+#pragma unroll
+                    for (int j = 0; j < kGatherUnroll; ++j) {
+                        const int k = c + j * E;
+                        w[j] = 0.f;
+                        x[j] = vzero((V*)nullptr);
+                        if (k < pe) {
+                            w[j] = __ldg(a.val + k);
+                            x[j] = __ldg(src + (size_t)__ldg(a.idx + k) * a.gather_stride + q);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < kGatherUnroll; ++j)
+                        if (c + j * E < pe) axpy(acc, w[j], x[j]);
+                }
+            }
+            V tot = vshfl(acc, q);                                  // group 0
+            for (int e = 1; e < E; ++e) tot = vadd(tot, vshfl(acc, e * nv + q));
+            if (lane < nv) part[warp * nv + lane] = tot;
+        } else {
         for (int q0 = 0; q0 < a.nv; q0 += 64) {
             V acc[2];
             acc[0] = vzero((V*)nullptr);
@@ -652,6 +757,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
                 const int q = q0 + b * 32 + lane;
                 if (q < a.nv) part[warp * a.nv + q] = acc[b];
             }
+        }
         }
         __syncthreads();
         for (int q = threadIdx.x; q < a.nv; q += kThreads) {
@@ -1008,16 +1114,20 @@ extern "C" int shpl_pool_heavy(const float* gather_in, int32_t gather_stride, in
     const int clusters = list_cap < 64 ? list_cap : 64;
     const unsigned grid = (unsigned)(clusters * kClusterSize);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (w == 4) {
-        if (smem > 48 * 1024) SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_pool_heavy_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        shpl_pool_heavy_kernel<4><<<grid, kThreads, smem, s>>>(a);
-    } else if (w == 2) {
-        if (smem > 48 * 1024) SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_pool_heavy_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        shpl_pool_heavy_kernel<2><<<grid, kThreads, smem, s>>>(a);
-    } else {
-        if (smem > 48 * 1024) SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_pool_heavy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        shpl_pool_heavy_kernel<1><<<grid, kThreads, smem, s>>>(a);
-    }
+    const bool groups = a.nv * 2 <= 32;       // few channels: lane groups over entries (see the kernel)
+#define SHPL_LAUNCH_HEAVY(WW, GG)                                                                                       \
+    do {                                                                                                                \
+        if (smem > 48 * 1024)                                                                                           \
+            SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_pool_heavy_kernel<WW, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        shpl_pool_heavy_kernel<WW, GG><<<grid, kThreads, smem, s>>>(a);                                                 \
+    } while (0)
+    if (w == 4 && groups) SHPL_LAUNCH_HEAVY(4, true);
+    else if (w == 4) SHPL_LAUNCH_HEAVY(4, false);
+    else if (w == 2 && groups) SHPL_LAUNCH_HEAVY(2, true);
+    else if (w == 2) SHPL_LAUNCH_HEAVY(2, false);
+    else if (groups) SHPL_LAUNCH_HEAVY(1, true);
+    else SHPL_LAUNCH_HEAVY(1, false);
+#undef SHPL_LAUNCH_HEAVY
     shpl::count_launches(1);
     return shpl::check_launch("shpl_pool_heavy_kernel");
 }

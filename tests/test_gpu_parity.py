@@ -414,6 +414,52 @@ def test_long_cell_below_the_heavy_threshold_is_bit_exact(shpl):
     np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd)
 
 
+@pytest.mark.parametrize("C,n", [(4, 700), (12, 333), (16, 920), (24, 100), (64, 1500), (100, 257), (2, 90), (3, 65)])
+def test_long_rows_are_summed_by_the_whole_warp_in_k_order(shpl, C, n):
+    """Narrow kernels hand cells with more than 32 entries to the whole warp (lane groups gather in parallel,
+    the adds stay in ascending k): bit-identical to the sequential oracle for every vector layout --
+    C=4 (one float4 per cell, 32 entries in parallel), C=24 (6 vectors, 5 groups), C=100 (25 vectors, 1 group),
+    C=2 / C=3 (float2 / scalar instantiations) -- next to short cells and a long pixel for the backward."""
+    rng = np.random.default_rng(C * 1000 + n)
+    n_bg = 400
+    u = np.r_[rng.integers(0, 64, n), rng.integers(0, 64, n_bg)]
+    v = np.r_[rng.integers(0, 32, n), rng.integers(0, 32, n_bg)]
+    u[: n // 2] = 9
+    v[: n // 2] = 4                                              # a long pixel (n/2 entries) for the transposed direction
+    bx = np.r_[np.full(n, 3), rng.integers(0, 16, n_bg)]
+    bz = np.r_[np.full(n, 2), rng.integers(0, 16, n_bg)]
+    perm = rng.permutation(n + n_bg)                             # long-cell entries interleaved with the others in k
+    d = dict(bv_index=np.stack((bx, bz), axis=1)[perm].astype(np.int64),
+             img_index=np.stack((u, v, np.zeros(n + n_bg)))[:, perm].astype(np.float64),
+             bv_size=np.array([16, 16]), img_size=np.array([64, 32]))
+    val = (1.0 / rng.integers(1, 46, n + n_bg)).astype(np.float32)
+    bev = rng.standard_normal((1, 16, 16, C), dtype=np.float32)
+    img = rng.standard_normal((1, 32, 64, C), dtype=np.float32)
+    o = shpl.produce_sparse_pooling_input(d)
+    Mij, flip = o["Mij_pool"], o["img_index_flip_pool"]
+    assert np.bincount(Mij[:, 0]).max() >= n and o["shpl_plan"].n_heavy == (0, 0)
+    M = shpl.SparseTensor(torch.from_numpy(Mij).cuda(), torch.from_numpy(val).cuda(), o["M_size"])
+    tb, ti = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
+    bv_fused, img_fused = shpl.sparse_pool_layer([tb, ti], [C, C], M, img_index_flip=torch.from_numpy(flip).cuda(),
+                                                 bv_index=np.zeros((1, 3)))
+    np.testing.assert_array_equal(bv_fused[0].detach().cpu().numpy(), cref.forward(bev[0], img[0], Mij, val, flip))
+    np.testing.assert_array_equal(img_fused[0].detach().cpu().numpy(), cref.forward_trans(img[0], bev[0], Mij, val, flip))
+    g1 = rng.standard_normal((16, 16, 2 * C), dtype=np.float32)
+    g2 = rng.standard_normal((32, 64, 2 * C), dtype=np.float32)
+    torch.autograd.backward([bv_fused, img_fused], [torch.from_numpy(g1[None]).cuda(), torch.from_numpy(g2[None]).cuda()])
+    gd, gs = cref.backward(g1, Mij, val, flip, C, (32, 64, C))
+    gi, gb = cref.backward_trans(g2, Mij, val, flip, C, (16, 16, C))
+    np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd + gb)
+    np.testing.assert_array_equal(ti.grad[0].cpu().numpy(), gi + gs)
+    # single direction too (concat form of the narrow kernel, no AddN)
+    tb2, ti2 = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
+    only, _ = shpl.sparse_pool_layer([tb2, ti2], [C, C], M, img_index_flip=torch.from_numpy(flip).cuda())
+    np.testing.assert_array_equal(only[0].detach().cpu().numpy(), cref.forward(bev[0], img[0], Mij, val, flip))
+    only.backward(torch.from_numpy(g1[None]).cuda())
+    np.testing.assert_array_equal(ti2.grad[0].cpu().numpy(), gs)
+    np.testing.assert_array_equal(tb2.grad[0].cpu().numpy(), gd)
+
+
 @pytest.mark.parametrize("dual", [False, True])
 def test_heavy_cells_use_the_cluster_tree(shpl, dual):
     """Stress (BASELINE config 5, Zipf-like skew): one BEV cell with 30k entries and one pixel with 5k.
