@@ -135,7 +135,7 @@ def mv3d_cam4(frame):
     """camera-frame [n,4] = (x, y, z, reflectance) of a mv3d_frame, as point_cloud_2_top_sparse(points_in_cam=True) takes it."""
     fsh = frame["points_fsh"]
     refl = (np.arange(len(fsh)) % 97) / 97.0
-    return np.c_[fsh[:, [1, 2, 0]], refl]
+    return np.ascontiguousarray(np.c_[fsh[:, [1, 2, 0]], refl])
 
 
 def mv3d_frame(seed, n_points=20000, max_points=45, car=False):

@@ -46,6 +46,8 @@ def voxelize_raw(points, img_index2, n, res, zres, side_range, fwd_range, height
     """One asynchronous shpl_mv3d_voxelize call into the preallocated buffers of `out` (dict with img_index
     [3,cap] i64, bv_index [cap,2] i64, m_val [cap] f64, counts [8] i32, ws, and optionally feature /
     coordinate / number); nothing is read back.  Returns voxel_full_size (host ints)."""
+    if not (points.is_contiguous() and img_index2.is_contiguous()):
+        raise ValueError("voxelize_raw: points [n,4] and img_index2 [2,n] must be contiguous")
     ranges = np.array([side_range[0], side_range[1], fwd_range[0], fwd_range[1], height_range[0], height_range[1]],
                       dtype=np.float64)
     vfs = (ctypes.c_int32 * 3)()

@@ -121,15 +121,21 @@ __global__ void __launch_bounds__(kThreads) shpl_bev_scatter_kernel(ScatterArgs 
     const unsigned bit = 1u << (cell & 31);
     Word* grid = static_cast<Word*>(a.ws.grid);
     bool bad = false;
+    // per-slice point counters: summed per CTA in shared memory first (one global atomic per CTA and counter
+    // instead of one per warp on the same six addresses)
+    __shared__ int s_cnt[SHPL_BEV_MAX_SLICES + 1];
+    if (threadIdx.x <= SHPL_BEV_MAX_SLICES) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
     for (int s = 0; s < g.S; ++s) {
         // kitti_utils.py:97-107: xor of the two point filters
         const bool in_s = inside && ((__dadd_rn(base, g.d_hi[s]) < 0.0) != (__dadd_rn(base, g.d_lo[s]) < 0.0));
         const unsigned m = __ballot_sync(kFull, in_s);
-        if (m && lane == 0) atomicAdd(a.ws.ctr + kCtrSlice + s, __popc(m));
+        if (m && lane == 0) atomicAdd(s_cnt + s, __popc(m));
         if (in_s) {
             if (in_grid) {
-                atomicMin(grid + (size_t)s * XZ + cell, word);
-                atomicOr(a.ws.bitmap + (size_t)s * g.W + (cell >> 5), bit);
+                // the first point to reach a cell (it finds the empty word) sets the cell's occupancy bit
+                const Word old = atomicMin(grid + (size_t)s * XZ + cell, word);
+                if (old == (Word)~(Word)0) atomicOr(a.ws.bitmap + (size_t)s * g.W + (cell >> 5), bit);
             } else {
                 bad = true;       // voxel_grid_2d.py:133-138 raises ValueError
             }
@@ -137,16 +143,18 @@ __global__ void __launch_bounds__(kThreads) shpl_bev_scatter_kernel(ScatterArgs 
     }
     const bool in_band = inside && ((__dadd_rn(base, g.d_band_hi) < 0.0) != (__dadd_rn(base, g.d_band_lo) < 0.0));
     const unsigned mb = __ballot_sync(kFull, in_band);
-    if (mb && lane == 0) atomicAdd(a.ws.ctr + kCtrBand, __popc(mb));
+    if (mb && lane == 0) atomicAdd(s_cnt + SHPL_BEV_MAX_SLICES, __popc(mb));
     if (in_band) {
         if (in_grid) {
-            atomicAdd(a.ws.dcount + cell, 1);
-            atomicOr(a.ws.bitmap + (size_t)g.S * g.W + (cell >> 5), bit);
+            if (atomicAdd(a.ws.dcount + cell, 1) == 0) atomicOr(a.ws.bitmap + (size_t)g.S * g.W + (cell >> 5), bit);
         } else {
             bad = true;
         }
     }
     if (bad) atomicOr(a.ws.ctr + kCtrFlags, SHPL_BEV_ERR_EXTENTS);
+    __syncthreads();
+    if (threadIdx.x < g.S && s_cnt[threadIdx.x]) atomicAdd(a.ws.ctr + kCtrSlice + threadIdx.x, s_cnt[threadIdx.x]);
+    if (threadIdx.x == SHPL_BEV_MAX_SLICES && s_cnt[SHPL_BEV_MAX_SLICES]) atomicAdd(a.ws.ctr + kCtrBand, s_cnt[SHPL_BEV_MAX_SLICES]);
 }
 
 struct EmitArgs {
@@ -235,39 +243,69 @@ __global__ void __launch_bounds__(kThreads) shpl_bev_emit_kernel(EmitArgs a) {
         }
     }
     const Word* grid = static_cast<const Word*>(a.ws.grid);
-    for (unsigned it = threadIdx.x; it < tot; it += kThreads) {
-        const long long cell = (long long)tip * kTileCells + s_list[it];
-        const int xi = (int)(cell / g.Z), zi = (int)(cell - (long long)xi * g.Z);
-        const size_t map_at = (size_t)(g.Z - 1 - zi) * g.X + xi;       // np.flip(map.transpose(), axis=0)  (:116-118)
-        if (plane == g.S) {
-            if (a.maps) {
-                // bev_generator.py:35-36: min(1, log(n + 1) / norm)
-                const int n = a.ws.dcount[cell];
-                double dv;
-                if (a.lut) dv = n < a.lut_len ? a.lut[n] : 1.0;
-                else dv = fmin(1.0, __ddiv_rn(log((double)n + 1.0), g.log_norm));
-                a.maps[(size_t)g.S * XZ + map_at] = dv;
+    if (plane == g.S) {          // the density band: the non-zeros of the density map
+        if (a.maps == nullptr) return;
+        for (unsigned it = threadIdx.x; it < tot; it += kThreads) {
+            const long long cell = (long long)tip * kTileCells + s_list[it];
+            const int xi = (int)(cell / g.Z), zi = (int)(cell - (long long)xi * g.Z);
+            // bev_generator.py:35-36: min(1, log(n + 1) / norm)
+            const int n = a.ws.dcount[cell];
+            double dv;
+            if (a.lut) dv = n < a.lut_len ? a.lut[n] : 1.0;
+            else dv = fmin(1.0, __ddiv_rn(log((double)n + 1.0), g.log_norm));
+            a.maps[(size_t)g.S * XZ + (size_t)(g.Z - 1 - zi) * g.X + xi] = dv;      // np.flip(map.transpose(), axis=0)
+        }
+        return;
+    }
+    // A slice: kItems occupied cells per thread and round, so that the dependent loads (winner word -> point)
+    // of several cells are in flight together; crowded near-range tiles hold > 1000 cells.
+    constexpr int kItems = 4;
+    for (unsigned it0 = threadIdx.x; it0 < tot; it0 += kItems * kThreads) {
+        long long cell[kItems];
+        Word win[kItems];
+#pragma unroll
+        for (int u = 0; u < kItems; ++u) {
+            const unsigned it = it0 + u * kThreads;
+            cell[u] = -1;
+            win[u] = 0;
+            if (it < tot) {
+                cell[u] = (long long)tip * kTileCells + s_list[it];
+                win[u] = grid[(size_t)src * XZ + cell[u]];
             }
-            continue;
         }
-        const long long pos = base + it;
-        const long long i = WordOps<Word>::index(g, grid[(size_t)src * XZ + cell]);
-        const double* p = a.pts + i * a.point_stride;
-        const double x = p[0], y = p[a.coord_stride], z = p[2 * a.coord_stride];
-        if (pos < a.cap) {
-            a.vox_out[2 * pos] = xi;
-            a.vox_out[2 * pos + 1] = g.Z - zi;                         // bev_slices.py:106-108 (num_divisions - z)
-            a.pts_out[3 * pos] = x;
-            a.pts_out[3 * pos + 1] = y;
-            a.pts_out[3 * pos + 2] = z;
+        double px[kItems], py[kItems], pz[kItems];
+#pragma unroll
+        for (int u = 0; u < kItems; ++u) {
+            px[u] = py[u] = pz[u] = 0.0;
+            if (cell[u] >= 0) {
+                const double* p = a.pts + WordOps<Word>::index(g, win[u]) * a.point_stride;
+                px[u] = p[0];
+                py[u] = p[a.coord_stride];
+                pz[u] = p[2 * a.coord_stride];
+            }
         }
-        if (a.maps) {
-            // geometry_utils.py:40: (a*x + b*y + c*z + d) / norm, numpy elementwise (no contraction)
-            double h = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(g.plane[0], x), __dmul_rn(g.plane[1], y)), __dmul_rn(g.plane[2], z)), g.plane[3]);
-            h = __ddiv_rn(h, g.norm);
-            // bev_slices.py:100: heights -= height_lo, once per slice the grid is used for
-            for (int t = src; t <= plane; ++t) h = __dsub_rn(h, g.lo[t]);
-            a.maps[(size_t)plane * XZ + map_at] = __ddiv_rn(h, g.hpd);
+#pragma unroll
+        for (int u = 0; u < kItems; ++u) {
+            if (cell[u] < 0) continue;
+            const long long pos = base + it0 + u * kThreads;
+            const int xi = (int)(cell[u] / g.Z), zi = (int)(cell[u] - (long long)xi * g.Z);
+            const double x = px[u], y = py[u], z = pz[u];
+            if (pos < a.cap) {
+                a.vox_out[2 * pos] = xi;
+                a.vox_out[2 * pos + 1] = g.Z - zi;                     // bev_slices.py:106-108 (num_divisions - z)
+                a.pts_out[3 * pos] = x;
+                a.pts_out[3 * pos + 1] = y;
+                a.pts_out[3 * pos + 2] = z;
+            }
+            if (a.maps) {
+                // geometry_utils.py:40: (a*x + b*y + c*z + d) / norm, numpy elementwise (no contraction)
+                double h = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(g.plane[0], x), __dmul_rn(g.plane[1], y)), __dmul_rn(g.plane[2], z)), g.plane[3]);
+                h = __ddiv_rn(h, g.norm);
+                // bev_slices.py:100: heights -= height_lo, once per slice the grid is used for
+                for (int t = src; t <= plane; ++t) h = __dsub_rn(h, g.lo[t]);
+                // np.flip(map.transpose(), axis=0)  (:116-118)
+                a.maps[(size_t)plane * XZ + (size_t)(g.Z - 1 - zi) * g.X + xi] = __ddiv_rn(h, g.hpd);
+            }
         }
     }
 }

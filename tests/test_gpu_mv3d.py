@@ -131,3 +131,43 @@ def test_mv3d_feeder_cuda_tensors_stay_on_device(shpl):
                                            f["height_range"], f["max_points"])
     np.testing.assert_array_equal(bv2, got[3])
     np.testing.assert_array_equal(mv2, got[4])
+
+
+def test_mv3d_config3_chain_full_shape_two_frames(shpl):
+    """BASELINE config 3 at full MV3D shape: feeder -> produce_sparse_pooling_input(stride [8, 2], M_val = 1/count)
+    -> _sparse_pool_op-style pooling of a 48x160x768 image map into the 100x120x768 BEV map (ped/cyc ranges,
+    MV3D_voxel_train.py:134-150), two frames stacked in one launch, forward and backward against the C oracle."""
+    from oracle import cref
+    frames = [synth.mv3d_frame(seed=s, n_points=20000) for s in (31, 32)]
+    C = 768
+    rng = np.random.default_rng(5)
+    plans, refs = [], []
+    bev = rng.standard_normal((2, 100, 120, 8), dtype=np.float32)            # lidar_features stand-in (narrow dense part)
+    img = rng.standard_normal((2, 48, 160, C), dtype=np.float32)
+    tb, ti = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
+    outs = []
+    g = rng.standard_normal((2, 100, 120, 8 + C), dtype=np.float32)
+    for k, f in enumerate(frames):
+        vd, vfs, img_index, bv_index, m_val = run_gpu(shpl, f)
+        assert list(vfs[1:]) == [200, 240]
+        d = dict(img_index=np.array(img_index, dtype=np.float64), img_size=f["img_size"], bv_index=bv_index, bv_size=[vfs[1], vfs[2]])
+        o = shpl.produce_sparse_pooling_input(d, M_val=m_val, stride=[8, 2])
+        assert o["M_size"].tolist() == [12000, len(m_val)]
+        rvd, _, rimg, rbv, rmv = run_oracle(f)
+        o_ref = io.produce_sparse_pooling_input(dict(img_index=np.array(rimg, dtype=np.float64), img_size=f["img_size"], bv_index=rbv,
+                                                     bv_size=[200, 240]), M_val=rmv, stride=[8, 2])
+        np.testing.assert_array_equal(o["Mij_pool"], o_ref["Mij_pool"])
+        np.testing.assert_array_equal(o["img_index_flip_pool"], o_ref["img_index_flip_pool"])
+        M = shpl.SparseTensor.from_sparse_pooling_input(o)
+        M.values = np.asarray(m_val, dtype=np.float32)
+        fused, _ = shpl.sparse_pool_layer([tb[k:k + 1], ti[k:k + 1]], [C, 8], M, img_index_flip=o["img_index_flip_pool"])
+        val = np.asarray(rmv, dtype=np.float32)                              # f64 -> f32 like the placeholder feed
+        ref = cref.forward(bev[k], img[k], o_ref["Mij_pool"], val, o_ref["img_index_flip_pool"])
+        np.testing.assert_array_equal(fused[0].detach().cpu().numpy(), ref)
+        outs.append(fused)
+        refs.append((o_ref, val))
+    torch.autograd.backward(outs, [torch.from_numpy(g[k:k + 1]).cuda() for k in range(2)])
+    for k, (o_ref, val) in enumerate(refs):
+        gd, gs = cref.backward(g[k], o_ref["Mij_pool"], val, o_ref["img_index_flip_pool"], 8, (48, 160, C))
+        np.testing.assert_array_equal(tb.grad[k].cpu().numpy(), gd)
+        np.testing.assert_array_equal(ti.grad[k].cpu().numpy(), gs)
