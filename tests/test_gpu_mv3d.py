@@ -148,18 +148,22 @@ def test_mv3d_config3_chain_full_shape_two_frames(shpl):
     outs = []
     g = rng.standard_normal((2, 100, 120, 8 + C), dtype=np.float32)
     for k, f in enumerate(frames):
-        vd, vfs, img_index, bv_index, m_val = run_gpu(shpl, f)
-        assert list(vfs[1:]) == [200, 240]
+        # keep the points that project inside the padded 1280x384 image, as the MV3D pipeline does before this call
+        # (minibatch_mv3d_img.py clips the cloud to the camera view); TF-CPU rejects out-of-range gather indices
+        u, v = f["img_index2"]
+        inside = (u >= 0) & (u < 1280) & (v >= 0) & (v < 384)
+        cam4, img2 = np.ascontiguousarray(synth.mv3d_cam4(f)[inside]), np.ascontiguousarray(f["img_index2"][:, inside])
+        vd, vfs, img_index, bv_index, m_val = run_gpu(shpl, f, points=cam4, img2=img2)
+        assert list(vfs[1:]) == [200, 240] and len(m_val) > 3000
         d = dict(img_index=np.array(img_index, dtype=np.float64), img_size=f["img_size"], bv_index=bv_index, bv_size=[vfs[1], vfs[2]])
         o = shpl.produce_sparse_pooling_input(d, M_val=m_val, stride=[8, 2])
         assert o["M_size"].tolist() == [12000, len(m_val)]
-        rvd, _, rimg, rbv, rmv = run_oracle(f)
+        rvd, _, rimg, rbv, rmv = run_oracle(f, points=cam4, img2=img2)
         o_ref = io.produce_sparse_pooling_input(dict(img_index=np.array(rimg, dtype=np.float64), img_size=f["img_size"], bv_index=rbv,
                                                      bv_size=[200, 240]), M_val=rmv, stride=[8, 2])
         np.testing.assert_array_equal(o["Mij_pool"], o_ref["Mij_pool"])
         np.testing.assert_array_equal(o["img_index_flip_pool"], o_ref["img_index_flip_pool"])
         M = shpl.SparseTensor.from_sparse_pooling_input(o)
-        M.values = np.asarray(m_val, dtype=np.float32)
         fused, _ = shpl.sparse_pool_layer([tb[k:k + 1], ti[k:k + 1]], [C, 8], M, img_index_flip=o["img_index_flip_pool"])
         val = np.asarray(rmv, dtype=np.float32)                              # f64 -> f32 like the placeholder feed
         ref = cref.forward(bev[k], img[k], o_ref["Mij_pool"], val, o_ref["img_index_flip_pool"])
