@@ -244,3 +244,18 @@ def test_bev_slices_full_scan_properties(shpl):
     np.testing.assert_array_equal(idx, ridx)
     np.testing.assert_array_equal(upts, rupts)
     np.testing.assert_array_equal(maps['density_map'], dm)
+
+
+def test_bev_slices_million_points_uniform_cloud(shpl):
+    """1.2 M points spread over the whole grid (975 k occupied (slice, cell) pairs, 28 % of all cells): every emit
+    tile is crowded, the look-back runs with arrival tickets and the scatter has heavy same-cell contention."""
+    rng = np.random.default_rng(5)
+    n = 1200000
+    pts = np.stack((rng.uniform(-39.9, 39.9, n), 1.65 - rng.uniform(-0.15, 2.25, n), rng.uniform(0.05, 69.9, n)), axis=1)
+    hms, dm, idx, upts = fo.generate_bev(pts.T, GP, synth.AVOD_EXTENTS, synth.AVOD_VOXEL, -0.2, 2.3, 5)
+    assert len(idx) > 900000
+    maps, gidx, gupts = shpl.BevSlices(CFG, None).generate_bev("lidar", pts.T, GP, synth.AVOD_EXTENTS, synth.AVOD_VOXEL,
+                                                              output_indices=True)
+    np.testing.assert_array_equal(gidx, idx)
+    np.testing.assert_array_equal(gupts, upts)
+    assert_maps_equal(maps, hms, dm)
