@@ -318,19 +318,78 @@ def run_gpu(args):
             graphs, use_graph = [], False
             torch.cuda.synchronize()
 
+    # ---- G consecutive steps in ONE graph: the same kernels, but the per-step fork/join and the gap between two
+    #      graph launches are paid once per G steps, and the dependencies are per layer (the plans of frame k+1 are
+    #      built as soon as the pooling that last used their buffer set has finished; the pooling of frame k starts as
+    #      soon as its plans are there) instead of a barrier at every step boundary.
+    G = 8
+    multi = None
+
+    def multi_step(k0, n_steps):
+        main = torch.cuda.current_stream()
+        for st_ in (side, side2, side3):
+            st_.wait_stream(main)
+        pool_done, build_done = {}, {}
+        for j in range(n_steps):
+            k = k0 + j
+            fi, si = k % N_FRAMES, k % n_sets
+            nf, ns = (k + 1) % N_FRAMES, (k + 1) % n_sets
+            pipe, mp = pipes[si], maps[si]
+            for li, bst in ((0, side2), (1, side3)):           # plans of frame k+1 into buffer set ns
+                if (li, k - 1) in pool_done:
+                    bst.wait_event(pool_done[(li, k - 1)])      # the pooling of step k-1 read buffer set ns
+                with torch.cuda.stream(bst):
+                    pipes[ns].build_layer(li, pts_dev[nf], vox_dev[nf], P, n_pts[nf], bst.cuda_stream)
+                    ev = torch.cuda.Event()
+                    ev.record(bst)
+                    build_done[(li, k + 1)] = ev
+            for li, pst in ((0, main), (1, side)):             # pooling of frame k
+                if (li, k) in build_done:
+                    pst.wait_event(build_done[(li, k)])
+                with torch.cuda.stream(pst):
+                    ps = pst.cuda_stream
+                    pipe.forward_layer(li, mp[li]["bev"], mp[li]["img"], ps, n_pts[fi])
+                    pipe.backward_layer(li, mp[li]["g_bev"], mp[li]["g_img"], ps, n_pts[fi])
+                    ev = torch.cuda.Event()
+                    ev.record(pst)
+                    pool_done[(li, k)] = ev
+        for st_ in (side, side2, side3):
+            main.wait_stream(st_)
+
+    if use_graph and K >= 2 * G and not args.single_step_graphs:
+        try:
+            assert G % N_FRAMES == 0 and G % n_sets == 0
+            multi = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(multi):
+                multi_step(0, G)
+        except Exception as e:  # pragma: no cover
+            print("multi-step graph capture failed (%r); one graph per step" % (e,), file=sys.stderr)
+            multi = None
+            torch.cuda.synchronize()
+
     def step(k):
         if use_graph:
             graphs[k % len(graphs)].replay()
         else:
             lean_step(k)
 
+    def run_steps(k_begin, k_end):
+        """steps k_begin .. k_end-1, G at a time where the multi-step graph lines up"""
+        k = k_begin
+        while k < k_end:
+            if multi is not None and k % G == 0 and k + G <= k_end:
+                multi.replay()
+                k += G
+            else:
+                step(k)
+                k += 1
+
     def barrier():
         if world > 1:
             dist.barrier()
 
     prologue_build(0)
-    for k in range(W):
-        step(k)
+    run_steps(0, W)
     torch.cuda.synchronize()
     # after W steps the plans of frame W are built; the timed region continues the same sequence
 
@@ -342,8 +401,7 @@ def run_gpu(args):
     torch.cuda.synchronize()
     sampler.start()
     ev0.record()
-    for k in range(W, W + K):
-        step(k)
+    run_steps(W, W + K)
     ev1.record()
     torch.cuda.synchronize()
     barrier()
@@ -634,7 +692,8 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": 1, "candidate_pairs_per_frame": n_pts,
                        "nnz_per_layer": nnz, "sharding": "frames by rank, no data-path collective",
                        "l2": "inputs larger than L2: %.0f MB touched per step, %d rotating buffer sets" % (bytes_step / 1e6, n_sets),
-                       "launch": "CUDA graph replay" if use_graph else "eager launches",
+                       "launch": ("CUDA graph replay, %d steps per graph where the step index lines up" % G if multi is not None
+                                  else "CUDA graph replay, one step per graph") if use_graph else "eager launches",
                        "algorithmic_bytes_per_step": bytes_step, "step_gbs_per_gpu": step_gbs,
                        "step_frac_of_peak": step_gbs / peak},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
@@ -657,6 +716,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--single-step-graphs", action="store_true", help="one CUDA graph per step (no multi-step graph)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

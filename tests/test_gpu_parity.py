@@ -254,6 +254,11 @@ POOL_CASES = [
     (4, 2000, (33, 47), (21, 35), 6, 10, "zipf", True),         # float2 path
     (5, 4000, (25, 30), (12, 40), 256, 256, "uniform", False),  # stride-8 VGG conv4 depth
     (6, 5000, (20, 24), (12, 40), 768, 768, "ground", True),    # MV3D depth, long rows
+    # few entries per cell: the sparse-regime kernel (entry CTAs + stream CTAs), every vector width, dual = add form
+    (7, 200, (40, 50), (30, 60), 32, 32, "uniform", True),
+    (8, 150, (33, 47), (21, 35), 3, 3, "uniform", True),
+    (9, 300, (40, 50), (30, 60), 6, 10, "zipf", True),
+    (10, 400, (60, 70), (30, 60), 64, 16, "ground", False),
 ]
 
 
@@ -521,6 +526,48 @@ def test_heavy_cells_use_the_cluster_tree(shpl, dual):
         close(got_b[heavy_row], want_b[heavy_row], 1e3)
     else:
         np.testing.assert_array_equal(got_b, want_b)
+
+
+def test_sparse_regime_with_a_heavy_cell(shpl):
+    """Few entries next to the cells (sparse-regime kernel) but 2600 of them in ONE BEV cell (> SHPL_HEAVY_LEN):
+    the entry CTAs skip the heavy cell, the stream CTAs write it as empty, shpl_pool_heavy fills it in.  Everything
+    but the heavy cell is bit-exact; the heavy cell is within 1e-5 of the sum of |terms|."""
+    rng = np.random.default_rng(21)
+    n_heavy, n_bg = 2600, 300
+    n = n_heavy + n_bg
+    bx = np.r_[np.full(n_heavy, 7), rng.integers(0, 110, n_bg)]
+    bz = np.r_[np.full(n_heavy, 5), rng.integers(0, 120, n_bg)]
+    u, v = rng.integers(0, 64, n), rng.integers(0, 32, n)
+    perm = rng.permutation(n)
+    d = dict(bv_index=np.stack((bx, bz), axis=1)[perm].astype(np.int64), img_index=np.stack((u, v, np.zeros(n)))[:, perm].astype(np.float64),
+             bv_size=np.array([120, 110]), img_size=np.array([64, 32]))
+    val = (1.0 / rng.integers(1, 46, n)).astype(np.float32)
+    C = 32
+    bev = rng.standard_normal((1, 120, 110, C), dtype=np.float32)
+    img = rng.standard_normal((1, 32, 64, C), dtype=np.float32)
+    o = shpl.produce_sparse_pooling_input(d, M_val=val.astype(np.float64))
+    plan = o["shpl_plan"]
+    assert plan.n_heavy == (1, 0) and 4 * n <= 120 * 110
+    Mij, flip = o["Mij_pool"], o["img_index_flip_pool"]
+    M = shpl.SparseTensor.from_sparse_pooling_input(o)
+    tb, ti = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
+    fused, _ = shpl.sparse_pool_layer([tb, ti], [C, C], M, img_index_flip=flip)
+    ref = cref.forward(bev[0], img[0], Mij, val, flip).reshape(-1, 2 * C)
+    got = fused[0].detach().cpu().numpy().reshape(-1, 2 * C)
+    heavy_row = 5 * 110 + 7
+    mask = np.ones(len(ref), bool)
+    mask[heavy_row] = False
+    np.testing.assert_array_equal(got[mask], ref[mask])
+    np.testing.assert_array_equal(got[heavy_row, :C], ref[heavy_row, :C])
+    pix = flip[:, 1] * 64 + flip[:, 2]
+    rows = Mij[:, 0]
+    scale = np.abs(val[rows == heavy_row, None] * img[0].reshape(-1, C)[pix[rows == heavy_row]]).sum(0).max()
+    assert np.abs(got[heavy_row, C:] - ref[heavy_row, C:]).max() <= 1e-5 * scale
+    g = rng.standard_normal((120, 110, 2 * C), dtype=np.float32)
+    fused.backward(torch.from_numpy(g[None]).cuda())
+    gd, gs = cref.backward(g, Mij, val, flip, C, (32, 64, C))
+    np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd)
+    np.testing.assert_array_equal(ti.grad[0].cpu().numpy(), gs)       # no pixel is heavy: the backward stays bit-exact
 
 
 def test_lazy_gen_dict_behaves_like_the_reference_dict(shpl, golden_dir):
