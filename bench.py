@@ -459,7 +459,7 @@ def run_gpu(args):
     fwd_avg = float(np.mean(fwd_ms)) * 1e-3
     bwd_avg = float(np.mean(bwd_ms)) * 1e-3
     achieved = bytes_fwd_B / fwd_avg / 1e9
-    roofline = {"bound": "hbm", "kernel": "shpl_pool_narrow_kernel<4,false> as layer B forward (700x800x32 <- 360x1200x32)",
+    roofline = {"bound": "hbm", "kernel": "shpl_pool_sparse_kernel<4,false> as layer B forward (700x800x32 <- 360x1200x32)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(), "bytes_per_launch": bytes_fwd_B, "us_per_launch": fwd_avg * 1e6,
                 "peak_source": peak_src, "frac_of_8TBs_nominal": achieved / 8000.0, "timing": roof_how,

@@ -674,17 +674,20 @@ __global__ void __launch_bounds__(kThreads, SHPL_SPARSE_MIN_CTAS) shpl_pool_spar
         const int e_begin = __ldg(jb.ptr), e_end = __ldg(jb.ptr + jb.n_cells);
         const int e0 = e_begin + (b * kWarps + warp) * jb.entry_chunk;
         if (e0 >= e_end) return;
+        // cells with more than kLongRow entries are left to the stream CTAs (whole-warp sum) or to shpl_pool_heavy:
+        // the entry walk skips them exactly like it skips heavy cells
         pool_entries_wide<V, 1, SHPL_SPARSE_GATHERS>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.key, jb.idx, jb.val, e0,
                                 min(e0 + jb.entry_chunk, e_end), e_begin, e_end, pout, jb.pool_out_stride,
-                                kAdd ? din : nullptr, jb.dense_in_stride, jb.vs, jb.ptr, jb.heavy_len, lane);
+                                kAdd ? din : nullptr, jb.dense_in_stride, jb.vs, jb.ptr, kLongRow, lane);
         return;
     }
     const int stream_ctas = jb.stream_ctas;
     V* dout = static_cast<V*>(jb.dense_out);
+    unsigned any_long = 0u;
     for (int t = (b - jb.entry_ctas) * kWarps + warp; t < jb.tiles; t += stream_ctas * kWarps) {
         const int r0 = t * jb.rows_per_tile;
         const int rows = min(jb.rows_per_tile, jb.n_cells - r0);
-        unsigned busy = 0u;
+        unsigned busy = 0u, longs = 0u;
         if (jb.vs > 0) {
             int lo = 0, hi = 0;
             if (lane < rows) {
@@ -692,7 +695,8 @@ __global__ void __launch_bounds__(kThreads, SHPL_SPARSE_MIN_CTAS) shpl_pool_spar
                 hi = __ldg(jb.ptr + r0 + lane + 1);
                 if (jb.heavy_len > 0 && hi - lo > jb.heavy_len) hi = lo;   // heavy cell: written as empty here
             }
-            busy = __ballot_sync(kFull, hi > lo);
+            busy = __ballot_sync(kFull, hi > lo);                          // cells somebody else writes (entry CTAs) ...
+            longs = __ballot_sync(kFull, hi - lo > kLongRow);               // ... or this warp sums as a whole, below
         }
         if (jb.vd > 0) {
             // concat form: the dense part of every cell; add form: a plain copy for the cells that receive nothing
@@ -738,6 +742,22 @@ __global__ void __launch_bounds__(kThreads, SHPL_SPARSE_MIN_CTAS) shpl_pool_spar
                 }
             }
         }
+        any_long |= longs;
+    }
+    if (any_long == 0u) return;
+    // Second walk, only for warps that met a long cell (none at KITTI / MV3D shapes): the whole-warp sum is kept out
+    // of the streaming loop so that its registers and its call do not weigh on it.
+    for (int t = (b - jb.entry_ctas) * kWarps + warp; t < jb.tiles; t += stream_ctas * kWarps) {
+        const int r0 = t * jb.rows_per_tile;
+        const int rows = min(jb.rows_per_tile, jb.n_cells - r0);
+        int len = 0;
+        if (lane < rows) len = __ldg(jb.ptr + r0 + lane + 1) - __ldg(jb.ptr + r0 + lane);
+        if (jb.heavy_len > 0 && len > jb.heavy_len) len = 0;
+        const unsigned longs = __ballot_sync(kFull, len > kLongRow);
+        if (longs != 0u)
+            long_cells<V, kAdd>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.ptr + r0, jb.idx, jb.val,
+                                pout + (size_t)r0 * jb.pool_out_stride, jb.pool_out_stride,
+                                kAdd ? din + (size_t)r0 * jb.dense_in_stride : nullptr, jb.dense_in_stride, jb.vs, longs, lane);
     }
 }
 

@@ -419,8 +419,13 @@ def test_long_cell_below_the_heavy_threshold_is_bit_exact(shpl):
     np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd)
 
 
-@pytest.mark.parametrize("C,n", [(4, 700), (12, 333), (16, 920), (24, 100), (64, 1500), (100, 257), (2, 90), (3, 65)])
-def test_long_rows_are_summed_by_the_whole_warp_in_k_order(shpl, C, n):
+@pytest.mark.parametrize("C,n,bev_hw", [(4, 700, (16, 16)), (12, 333, (16, 16)), (16, 920, (16, 16)), (24, 100, (16, 16)),
+                                        (64, 1500, (16, 16)), (100, 257, (16, 16)), (2, 90, (16, 16)), (3, 65, (16, 16)),
+                                        # the same on a map with few entries per cell: the sparse-regime kernel, whose
+                                        # stream warps take the long cells over from the entry CTAs
+                                        (16, 920, (120, 110)), (4, 700, (120, 110)), (24, 100, (120, 110)), (100, 257, (120, 110)),
+                                        (6, 333, (120, 110))])
+def test_long_rows_are_summed_by_the_whole_warp_in_k_order(shpl, C, n, bev_hw):
     """Narrow kernels hand cells with more than 32 entries to the whole warp (lane groups gather in parallel,
     the adds stay in ascending k): bit-identical to the sequential oracle for every vector layout --
     C=4 (one float4 per cell, 32 entries in parallel), C=24 (6 vectors, 5 groups), C=100 (25 vectors, 1 group),
@@ -431,14 +436,14 @@ def test_long_rows_are_summed_by_the_whole_warp_in_k_order(shpl, C, n):
     v = np.r_[rng.integers(0, 32, n), rng.integers(0, 32, n_bg)]
     u[: n // 2] = 9
     v[: n // 2] = 4                                              # a long pixel (n/2 entries) for the transposed direction
-    bx = np.r_[np.full(n, 3), rng.integers(0, 16, n_bg)]
-    bz = np.r_[np.full(n, 2), rng.integers(0, 16, n_bg)]
+    bx = np.r_[np.full(n, 3), rng.integers(0, bev_hw[1], n_bg)]
+    bz = np.r_[np.full(n, 2), rng.integers(0, bev_hw[0], n_bg)]
     perm = rng.permutation(n + n_bg)                             # long-cell entries interleaved with the others in k
     d = dict(bv_index=np.stack((bx, bz), axis=1)[perm].astype(np.int64),
              img_index=np.stack((u, v, np.zeros(n + n_bg)))[:, perm].astype(np.float64),
-             bv_size=np.array([16, 16]), img_size=np.array([64, 32]))
+             bv_size=np.array(bev_hw), img_size=np.array([64, 32]))
     val = (1.0 / rng.integers(1, 46, n + n_bg)).astype(np.float32)
-    bev = rng.standard_normal((1, 16, 16, C), dtype=np.float32)
+    bev = rng.standard_normal((1,) + tuple(bev_hw) + (C,), dtype=np.float32)
     img = rng.standard_normal((1, 32, 64, C), dtype=np.float32)
     o = shpl.produce_sparse_pooling_input(d)
     Mij, flip = o["Mij_pool"], o["img_index_flip_pool"]
@@ -449,11 +454,11 @@ def test_long_rows_are_summed_by_the_whole_warp_in_k_order(shpl, C, n):
                                                  bv_index=np.zeros((1, 3)))
     np.testing.assert_array_equal(bv_fused[0].detach().cpu().numpy(), cref.forward(bev[0], img[0], Mij, val, flip))
     np.testing.assert_array_equal(img_fused[0].detach().cpu().numpy(), cref.forward_trans(img[0], bev[0], Mij, val, flip))
-    g1 = rng.standard_normal((16, 16, 2 * C), dtype=np.float32)
+    g1 = rng.standard_normal(tuple(bev_hw) + (2 * C,), dtype=np.float32)
     g2 = rng.standard_normal((32, 64, 2 * C), dtype=np.float32)
     torch.autograd.backward([bv_fused, img_fused], [torch.from_numpy(g1[None]).cuda(), torch.from_numpy(g2[None]).cuda()])
     gd, gs = cref.backward(g1, Mij, val, flip, C, (32, 64, C))
-    gi, gb = cref.backward_trans(g2, Mij, val, flip, C, (16, 16, C))
+    gi, gb = cref.backward_trans(g2, Mij, val, flip, C, tuple(bev_hw) + (C,))
     np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd + gb)
     np.testing.assert_array_equal(ti.grad[0].cpu().numpy(), gi + gs)
     # single direction too (concat form of the narrow kernel, no AddN)

@@ -13,7 +13,7 @@ ncu --set full --clock-control none --import-source on -k regex:shpl_pool_wide -
 
 N="python tools/microbench.py --config b --iters 3"
 $N > gpurun_out/plain_${tag}_micro_b.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:narrow -c 6 -o gpurun_out/${tag}_narrow_kernels -f $N > gpurun_out/ncu_${tag}_micro_b.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:shpl_pool_sparse -c 6 -o gpurun_out/${tag}_narrow_kernels -f $N > gpurun_out/ncu_${tag}_micro_b.log 2>&1
 
 F="python tools/feeder_bench.py"
 $F > gpurun_out/plain_${tag}_feeder.log 2>&1 &&
