@@ -70,7 +70,7 @@ def ncu_traffic():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
 
-    def __init__(self, index, period=0.004):
+    def __init__(self, index, period=0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -82,6 +82,7 @@ class ClockSampler(threading.Thread):
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)      # first NVML query is slow: pay for it here
             self.ok = True
         except Exception:
             self.ok = False
@@ -543,13 +544,19 @@ def run_gpu(args):
         n = n_pts[fi]
         stage_pts[:n].copy_(pts_pin[fi], non_blocking=True)
         stage_vox[:n].copy_(vox_pin[fi], non_blocking=True)
-        ms = torch.cuda.current_stream().cuda_stream
-        for li in range(len(specs)):
-            pipe.build_layer(li, stage_pts, stage_vox, P, n, ms)
-        for li in range(len(specs)):
-            pipe.forward_layer(li, mp[li]["bev"], mp[li]["img"], ms, n)
-        for li in reversed(range(len(specs))):
-            pipe.backward_layer(li, mp[li]["g_bev"], mp[li]["g_img"], ms, n)
+        main = torch.cuda.current_stream()
+        ms = main.cuda_stream
+        # the two layers are independent: layer A (build, forward, backward) on a second stream beside layer B
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ss = side.cuda_stream
+            pipe.build_layer(0, stage_pts, stage_vox, P, n, ss)
+            pipe.forward_layer(0, mp[0]["bev"], mp[0]["img"], ss, n)
+            pipe.backward_layer(0, mp[0]["g_bev"], mp[0]["g_img"], ss, n)
+        pipe.build_layer(1, stage_pts, stage_vox, P, n, ms)
+        pipe.forward_layer(1, mp[1]["bev"], mp[1]["img"], ms, n)
+        pipe.backward_layer(1, mp[1]["g_bev"], mp[1]["g_img"], ms, n)
+        main.wait_stream(side)
         off = 0
         for li in range(len(specs)):
             res_dev[off:off + 256].copy_(pipe.layers[li].g_bev.reshape(-1)[:256])
@@ -573,7 +580,7 @@ def run_gpu(args):
         dt_cabi = float(t.item())
     e2e["c_abi_pipeline"] = {"value": world * K_e2e / dt_cabi, "unit": UNIT,
                              "h2d_bytes_per_step": int(n_pts[0] * 40), "d2h_bytes_per_step": int(res_pin.numel() * 4),
-                             "what": "same step through the ctypes C-ABI calls on preallocated buffers: points/voxel indices "
+                             "what": "same step through the ctypes C-ABI calls on preallocated buffers, the two layers on two streams: points/voxel indices "
                                      "copied from pinned host memory, both plans built, forward+backward of both layers, "
                                      "4 KB of gradients + the plan counters read back to pinned host memory, every step"}
 
@@ -623,14 +630,19 @@ def run_gpu(args):
             pipe, mp = pipes[si], maps[si]
             Pn = scans[fi].shape[1]
             stage_scan[:, :Pn].copy_(scan_pin[fi], non_blocking=True)
-            ms = torch.cuda.current_stream().cuda_stream
+            main = torch.cuda.current_stream()
+            ms = main.cuda_stream
             feeder_call(fi)
-            for li in range(len(specs)):
-                pipe.build_layer(li, work.unique_pts, work.voxel_indices, P, N_MAX, ms, n_dev=n_dev)
-            for li in range(len(specs)):
-                pipe.forward_layer(li, mp[li]["bev"], mp[li]["img"], ms, N_MAX)
-            for li in reversed(range(len(specs))):
-                pipe.backward_layer(li, mp[li]["g_bev"], mp[li]["g_img"], ms, N_MAX)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ss = side.cuda_stream
+                pipe.build_layer(0, work.unique_pts, work.voxel_indices, P, N_MAX, ss, n_dev=n_dev)
+                pipe.forward_layer(0, mp[0]["bev"], mp[0]["img"], ss, N_MAX)
+                pipe.backward_layer(0, mp[0]["g_bev"], mp[0]["g_img"], ss, N_MAX)
+            pipe.build_layer(1, work.unique_pts, work.voxel_indices, P, N_MAX, ms, n_dev=n_dev)
+            pipe.forward_layer(1, mp[1]["bev"], mp[1]["img"], ms, N_MAX)
+            pipe.backward_layer(1, mp[1]["g_bev"], mp[1]["g_img"], ms, N_MAX)
+            main.wait_stream(side)
             off = 0
             for li in range(len(specs)):
                 res_dev[off:off + 256].copy_(pipe.layers[li].g_bev.reshape(-1)[:256])
