@@ -123,7 +123,7 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------- CPU legs
 def cpu_frame_inputs(seed):
-    from oracle import synth
+    from tools import synth
     return synth.avod_frame(seed, az_step_deg=AZ_STEP)
 
 
@@ -132,7 +132,7 @@ class CpuWorkload:
     reference's algorithm; TensorFlow is not installable, so kind = "port")."""
 
     def __init__(self):
-        from oracle import cref, synth
+        from oracle import cref
         cref.build()
         self.specs = layer_specs()
         rng = np.random.default_rng(0)
@@ -214,7 +214,7 @@ def run_gpu(args):
     import sparse_pooling_b200 as shpl
     from sparse_pooling_b200 import _cabi
     from sparse_pooling_b200.pipeline import FramePipeline
-    from oracle import synth
+    from tools import synth
 
     lib = _cabi.lib
     specs = layer_specs()

@@ -40,6 +40,12 @@ namespace {
 #ifndef SHPL_UNROLL
 #define SHPL_UNROLL 8
 #endif
+#ifndef SHPL_WIDE_MIN_CTAS
+#define SHPL_WIDE_MIN_CTAS 2
+#endif
+#ifndef SHPL_WIDE_GATHERS
+#define SHPL_WIDE_GATHERS 8       // gathers in flight per warp in the entry CTAs of the wide kernel
+#endif
 #ifndef SHPL_SPARSE_MIN_CTAS
 #define SHPL_SPARSE_MIN_CTAS 4
 #endif
@@ -584,7 +590,7 @@ __device__ __forceinline__ void cta_copy_tile(const V* __restrict__ in, int in_s
 }
 
 template <int W, int ACC>
-__global__ void __launch_bounds__(kThreads, 2) shpl_pool_wide_kernel(PoolArgs a) {
+__global__ void __launch_bounds__(kThreads, SHPL_WIDE_MIN_CTAS) shpl_pool_wide_kernel(PoolArgs a) {
     using V = typename VecOf<W>::type;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -598,7 +604,7 @@ __global__ void __launch_bounds__(kThreads, 2) shpl_pool_wide_kernel(PoolArgs a)
         const int e_begin = __ldg(jb.ptr), e_end = __ldg(jb.ptr + jb.n_cells);
         const int e0 = e_begin + (b * kWarps + warp) * jb.entry_chunk;
         if (e0 >= e_end) return;
-        pool_entries_wide<V, ACC>(src, jb.gather_stride, jb.key, jb.idx, jb.val, e0, min(e0 + jb.entry_chunk, e_end),
+        pool_entries_wide<V, ACC, SHPL_WIDE_GATHERS>(src, jb.gather_stride, jb.key, jb.idx, jb.val, e0, min(e0 + jb.entry_chunk, e_end),
                                   e_begin, e_end, pout, jb.pool_out_stride, jb.add ? din : nullptr,
                                   jb.dense_in_stride, jb.vs, jb.ptr, jb.heavy_len, lane);
         return;

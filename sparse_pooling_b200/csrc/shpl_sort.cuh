@@ -9,7 +9,10 @@ using shpl::kFull;
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kChunks = 8;                       // 32-wide chunks per warp in a radix tile
+#ifndef SHPL_SORT_CHUNKS
+#define SHPL_SORT_CHUNKS 8
+#endif
+constexpr int kChunks = SHPL_SORT_CHUNKS;        // 32-wide chunks per warp in a radix tile
 constexpr int kTile = kThreads * kChunks;        // 2048 sort items per radix CTA
 constexpr int kPairsTile = kThreads;             // one candidate pair per thread in shpl_pairs_kernel
 constexpr int kMaxRadixBits = 10;
@@ -98,7 +101,7 @@ struct RadixArgs {
 // per-tile digit counts the previous kernel accumulated.
 __global__ void __launch_bounds__(kThreads) shpl_radix_pass_kernel(RadixArgs a) {
     __shared__ unsigned long long s_items[kTile];
-    __shared__ unsigned short s_wh[kWarps][kMaxRadix];   // per-warp digit counts, then exclusive warp prefix
+    __shared__ __align__(16) unsigned short s_wh[kWarps][kMaxRadix];   // per-warp digit counts, then exclusive warp prefix
     __shared__ unsigned short s_rank[kTile];
     __shared__ unsigned s_gb[kMaxRadix];                 // global base of each digit for this tile
     __shared__ unsigned s_scan[kWarps];
@@ -126,7 +129,11 @@ __global__ void __launch_bounds__(kThreads) shpl_radix_pass_kernel(RadixArgs a) 
         const int i = tile_base + j * kThreads + threadIdx.x;
         s_items[j * kThreads + threadIdx.x] = i < n ? in[i] : ~0ull;
     }
-    for (int d = threadIdx.x; d < radix * kWarps; d += kThreads) (&s_wh[0][0])[(d / radix) * kMaxRadix + (d % radix)] = 0;
+    {   // clear the per-warp digit counters (16 KB) with 128-bit stores
+        uint4* z = reinterpret_cast<uint4*>(&s_wh[0][0]);
+        constexpr int kVec = (int)(sizeof(s_wh) / sizeof(uint4));
+        for (int d = threadIdx.x; d < kVec; d += kThreads) z[d] = make_uint4(0u, 0u, 0u, 0u);
+    }
 
     // this thread's digits: how many such items sit in earlier tiles / in all tiles (loads overlap phase A)
     unsigned below[kDigitsPerThread], all[kDigitsPerThread];

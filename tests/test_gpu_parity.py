@@ -370,6 +370,46 @@ def test_kitti_stride1_full_size_against_c_oracle(shpl):
     assert abs(got - want) <= 1e-5 * np.abs(img[0].reshape(-1, 32)[pix]).astype(np.float64).sum()
 
 
+def test_avod_fpn_two_layer_config_full_size(shpl):
+    """Config 2 (the bench workload) and 2' (RetinaNet P2) at full size from ONE frame's points: layer A after VGG conv4
+    (stride 8, dual, 88x100x256 <-> 45x150x256 on the padded 704-row BEV, kitti_dataset.py:384-388) and the P2 layer
+    (stride 4, 175x200x256 <- 90x300x256, retinanet_model.py:337-340): indices against the numpy oracle, forward and
+    backward bit-exact against the plain-C oracle."""
+    frame = synth.avod_frame(3, az_step_deg=0.04)
+    rng = np.random.default_rng(9)
+    for stride, bv_size, bev_hw, img_hw, dual in ((8, (704, 800), (88, 100), (45, 150), True), (4, (700, 800), (175, 200), (90, 300), False)):
+        C = 256
+        d = shpl.gen_sparse_pooling_input_avod(frame["points"], frame["voxel_indices"], Calib(frame["P"]), frame["im_size"], bv_size)
+        o = shpl.produce_sparse_pooling_input(d, stride=[stride, stride])
+        d_ref = io.gen_sparse_pooling_input_avod(frame["points"], frame["voxel_indices"], frame["P"], frame["im_size"], bv_size)
+        o_ref = io.produce_sparse_pooling_input(d_ref, stride=[stride, stride])
+        for k in ("Mij_pool", "M_size", "img_index_flip_pool"):
+            np.testing.assert_array_equal(np.asarray(o[k]), o_ref[k], err_msg=k)
+        Mij, flip = o_ref["Mij_pool"], o_ref["img_index_flip_pool"]
+        val = np.ones(len(Mij), np.float32)
+        bev = rng.standard_normal((1,) + bev_hw + (C,), dtype=np.float32)
+        img = rng.standard_normal((1,) + img_hw + (C,), dtype=np.float32)
+        tb, ti = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
+        M = shpl.SparseTensor.from_sparse_pooling_input(o)
+        bv_fused, img_fused = shpl.sparse_pool_layer([tb, ti], [C, C], M, img_index_flip=o["img_index_flip_pool"],
+                                                     bv_index=(np.zeros((1, 3)) if dual else None))
+        np.testing.assert_array_equal(bv_fused[0].detach().cpu().numpy(), cref.forward(bev[0], img[0], Mij, val, flip))
+        g1 = rng.standard_normal(bev_hw + (2 * C,), dtype=np.float32)
+        gd, gs = cref.backward(g1, Mij, val, flip, C, img_hw + (C,))
+        if dual:
+            np.testing.assert_array_equal(img_fused[0].detach().cpu().numpy(), cref.forward_trans(img[0], bev[0], Mij, val, flip))
+            g2 = rng.standard_normal(img_hw + (2 * C,), dtype=np.float32)
+            torch.autograd.backward([bv_fused, img_fused], [torch.from_numpy(g1[None]).cuda(), torch.from_numpy(g2[None]).cuda()])
+            gi, gb = cref.backward_trans(g2, Mij, val, flip, C, bev_hw + (C,))
+            np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd + gb)
+            np.testing.assert_array_equal(ti.grad[0].cpu().numpy(), gi + gs)
+        else:
+            assert img_fused is ti
+            bv_fused.backward(torch.from_numpy(g1[None]).cuda())
+            np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd)
+            np.testing.assert_array_equal(ti.grad[0].cpu().numpy(), gs)
+
+
 def test_full_scan_c128_skewed_rows(shpl):
     """Config 4 / 5 shape: 120k pairs, C=128, ground-plane-skewed rows, non-homogeneous weights."""
     o, val, bev, img = _case(9, 120000, (700, 800), (360, 1200), 128, 128, "ground", True)

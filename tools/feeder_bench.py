@@ -9,7 +9,8 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import feeder_oracle as fo, synth  # noqa: E402
+from oracle import feeder_oracle as fo  # noqa: E402  (CPU timing beside the GPU number only)
+from tools import synth  # noqa: E402
 from sparse_pooling_b200 import bev_slices as bs  # noqa: E402
 
 GP = np.array([0.0, -1.0, 0.0, 1.65])

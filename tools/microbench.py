@@ -14,7 +14,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from oracle import synth  # noqa: E402
+from tools import synth  # noqa: E402
 from sparse_pooling_b200.pipeline import FramePipeline, LayerSpec  # noqa: E402
 
 

@@ -11,7 +11,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import sparse_pooling_b200 as shpl  # noqa: E402
-from oracle import synth  # noqa: E402
+from tools import synth  # noqa: E402
 
 dev = torch.device("cuda", 0)
 f = synth.avod_frame(100, az_step_deg=0.028)

@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 
 import sparse_pooling_b200 as shpl  # noqa: E402
 from sparse_pooling_b200 import ops  # noqa: E402
-from oracle import synth  # noqa: E402
+from tools import synth  # noqa: E402
 
 
 def timeit(fn, iters=10, reps=2):
