@@ -481,7 +481,7 @@ def run_gpu(args):
         nonlocal h2d, d2h
         fi, si = k % N_FRAMES, k % n_sets
         mp = maps[si]
-        outs = []
+        outs, roots, grads, leaves = [], [], [], []
         h2d = d2h = 0
         for li, s in enumerate(specs):
             d = shpl.gen_sparse_pooling_input_avod(pts_pin[fi], vox_pin[fi], Calib, list(s.im_size), s.bv_size)
@@ -497,10 +497,14 @@ def run_gpu(args):
             bv_fused, img_fused = shpl.sparse_pool_layer([bev, img], [s.c_img, s.c_bev], M,
                                                          img_index_flip=o["img_index_flip_pool"],
                                                          bv_index=(np.zeros((1, 3)) if s.dual else None))
+            roots.append(bv_fused)
+            grads.append(mp[li]["g_bev"])
             if s.dual:
-                torch.autograd.backward([bv_fused, img_fused], [mp[li]["g_bev"], mp[li]["g_img"]])
-            else:
-                torch.autograd.backward([bv_fused], [mp[li]["g_bev"]])
+                roots.append(img_fused)
+                grads.append(mp[li]["g_img"])
+            leaves.append((bev, img))
+        torch.autograd.backward(roots, grads)      # one backward over both layers, like one sess.run(train_op)
+        for bev, img in leaves:
             outs.append(bev.grad.reshape(-1)[:256])
             outs.append(img.grad.reshape(-1)[:256])
         result_pin.copy_(torch.cat(outs), non_blocking=False)          # D2H read of the step's result
@@ -526,8 +530,8 @@ def run_gpu(args):
             m["img"].requires_grad_(False)
     e2e = {"value": world * K_e2e / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "steps": K_e2e,
-           "what": "gen_sparse_pooling_input_avod + produce_sparse_pooling_input + sparse_pool_layer + autograd backward "
-                   "per layer through the public API; points/voxel indices copied from pinned host memory every step, "
+           "what": "gen_sparse_pooling_input_avod + produce_sparse_pooling_input + sparse_pool_layer per layer, then one autograd "
+                   "backward over both layers, through the public API; points/voxel indices copied from pinned host memory every step, "
                    "feature maps device-resident (they are device-resident TF tensors in the reference), 2 KB of the "
                    "gradients read back to pinned host memory every step"}
 
