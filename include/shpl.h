@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SHPL_ABI_VERSION 4
+#define SHPL_ABI_VERSION 5
 
 /* Cells with more entries than this are "heavy": the builder lists them in the plan and their sum
  * is formed by shpl_pool_heavy (a thread-block cluster per cell, fixed summation tree) instead of
@@ -283,6 +283,26 @@ int shpl_mv3d_voxelize(const double* points, const int64_t* img_index2, int64_t 
                        int64_t* img_index_out, int64_t* bv_index_out, double* m_val_out, int64_t capacity,
                        double* feature_buffer, int64_t* coordinate_buffer, int64_t* number_buffer,
                        int64_t voxel_capacity, int32_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Point-cloud ingest.  Replaces the arithmetic of
+ *   obj_utils.get_lidar_point_cloud   avod/wavedata/wavedata/tools/obj_detection/obj_utils.py:220-268
+ *   calib_utils.lidar_to_cam_frame    avod/wavedata/wavedata/tools/core/calib_utils.py:371-410
+ *   calib_utils.project_to_image      avod/wavedata/wavedata/tools/core/calib_utils.py:281-297
+ * (reading the calibration .txt and the velodyne .bin stays on the host).
+ *   velo_xyzi f32 [N,4] (DEVICE): the raw scan as the KITTI .bin holds it (x, y, z, intensity);
+ *   rectified_host f64 [12]: rows 0..2 of R0_rect(4x4) . Tr_velo_to_cam(4x4)  (calib_utils.py:406);
+ *   p2_host f64 [12]: the camera matrix; im_w, im_h: the image size to filter with, or 0, 0 for every point
+ *   (im_size = None); use_min_intensity / min_intensity: the reference's optional intensity filter (:264-268).
+ * Output cam_out f64 [3, capacity], coordinate-major (row stride = capacity; first counts[0] columns valid): the
+ * camera-frame points with z > 0 that project strictly inside the image, input order kept -- what
+ * shpl_bev_slices takes with coord_stride = capacity, point_stride = 1.
+ * counts i32 [4] (device): [0] = points kept, [1] = points with z > 0, [2] = 1 if capacity was exceeded. */
+size_t shpl_lidar_workspace_bytes(int64_t n_max);
+int shpl_lidar_to_cam(const float* velo_xyzi, int64_t N, const double* rectified_host, const double* p2_host,
+                      int32_t im_w, int32_t im_h, int32_t use_min_intensity, float min_intensity,
+                      double* cam_out, int64_t capacity, int32_t* counts, void* workspace, size_t workspace_bytes,
+                      void* stream);
 
 #ifdef __cplusplus
 }

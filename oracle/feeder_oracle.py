@@ -145,3 +145,43 @@ def point_cloud_2_top_sparse(points, img_index2, res, zres, side_range, fwd_rang
     bv_index = xyz[filt_indices, :][:, [1, 0]]                                      # :159
     M_val = 1.0 / number[inv[filt_indices]]                                         # :160
     return voxel_dict, voxel_full_size, img_index, bv_index, M_val
+
+
+# ------------------------------------------------------------------ point-cloud ingest
+def lidar_to_cam_frame(xyz_lidar, r0_rect, tr_velodyne_to_cam):
+    """calib_utils.py:371-410: p_cam = R0_rect(4x4) . Tr_velo_to_cam(4x4) . [x y z 1]."""
+    r0 = np.pad(np.asarray(r0_rect, dtype=np.float64), ((0, 1), (0, 1)), 'constant', constant_values=0)
+    r0[3, 3] = 1
+    tf = np.pad(np.asarray(tr_velodyne_to_cam, dtype=np.float64), ((0, 1), (0, 0)), 'constant', constant_values=0)
+    tf[3, 3] = 1
+    one_pad = np.ones(xyz_lidar.shape[0]).reshape(-1, 1)
+    xyz = np.append(xyz_lidar, one_pad, axis=1)
+    rectified = np.dot(r0, tf)                                                   # :406
+    return np.dot(rectified, xyz.T)[0:3].T                                       # :407-410
+
+
+def project_to_image(point_cloud, p):
+    """calib_utils.py:281-297: (3, N) camera-frame points -> (2, N) pixels."""
+    pts_2d = np.dot(p, np.append(point_cloud, np.ones((1, point_cloud.shape[1])), axis=0))
+    pts_2d[0, :] = pts_2d[0, :] / pts_2d[2, :]
+    pts_2d[1, :] = pts_2d[1, :] / pts_2d[2, :]
+    return np.delete(pts_2d, 2, 0)
+
+
+def get_lidar_point_cloud(velo_xyzi, p2, r0_rect, tr_velodyne_to_cam, im_size=None, min_intensity=None):
+    """obj_utils.get_lidar_point_cloud (obj_utils.py:220-268) after the two file reads: velo_xyzi float32 [N,4] as
+    calib_utils.read_lidar returns it (x, y, z, i).  Returns the (3, M) float64 camera-frame cloud."""
+    x, y, z, i = (velo_xyzi[:, c] for c in range(4))
+    pts = np.vstack((x, y, z)).T                                                 # float32 [N,3]  (:241)
+    pts = lidar_to_cam_frame(pts, r0_rect, tr_velodyne_to_cam)                   # float64
+    if not im_size:
+        return pts.T                                                             # :245-247
+    pts = pts[pts[:, 2] > 0]                                                     # :251
+    point_cloud = pts.T
+    point_in_im = project_to_image(point_cloud, p=p2).T                          # :255
+    image_filter = ((point_in_im[:, 0] > 0) & (point_in_im[:, 0] < im_size[0]) &
+                    (point_in_im[:, 1] > 0) & (point_in_im[:, 1] < im_size[1]))  # :258-261
+    if not min_intensity:
+        return pts[image_filter].T
+    intensity_filter = i > min_intensity                                         # :266: `i` was NOT cut by z > 0 above
+    return pts[np.logical_and(image_filter, intensity_filter)].T                 # raises when a point had z <= 0

@@ -222,6 +222,34 @@ def feeder_goldens():
             assert n_in[2] == 1 and n_in[4] == 0 and min(n_in[0], n_in[1], n_in[3]) > 1, n_in
 
 
+def ingest_goldens():
+    """obj_utils.get_lidar_point_cloud of the reference on synthetic KITTI files (a calib .txt and a velodyne .bin
+    written to a temporary directory in the format calib_utils.read_calibration / read_lidar parse)."""
+    import tempfile
+    import_avod()
+    from wavedata.tools.obj_detection import obj_utils
+    for seed, az, im_size in ((1, 0.4, [1242, 375]), (2, 0.15, [1242, 375])):
+        scan = synth.velodyne_scan(seed, az_step_deg=az)
+        with tempfile.TemporaryDirectory() as tmp:
+            os.makedirs(tmp + "/calib")
+            os.makedirs(tmp + "/velodyne")
+            with open(tmp + "/calib/%06d.txt" % seed, "w") as f:
+                f.write(synth.kitti_calib_text())
+            scan.tofile(tmp + "/velodyne/%06d.bin" % seed)
+            pc = obj_utils.get_lidar_point_cloud(seed, tmp + "/calib", tmp + "/velodyne", im_size=im_size)
+            pc_all = obj_utils.get_lidar_point_cloud(seed, tmp + "/calib", tmp + "/velodyne")
+            from wavedata.tools.core import calib_utils
+            cal = calib_utils.read_calibration(tmp + "/calib", seed)
+        assert pc.dtype == np.float64 and pc.shape[0] == 3
+        rec = dict(input_sha=digest(scan), n_in=len(scan), im_size=np.array(im_size), fov_sha=digest(pc), all_sha=digest(pc_all),
+                   n_fov=pc.shape[1], p2=cal.p2, r0_rect=cal.r0_rect, tr_velodyne_to_cam=cal.tr_velodyne_to_cam)
+        if seed == 1:
+            rec["fov_points"] = pc
+        np.savez_compressed(os.path.join(OUT, "lidar_ingest_seed%d.npz" % seed), **rec)
+        print("lidar ingest seed", seed, "points", len(scan), "in FOV", pc.shape[1])
+
+
 if __name__ == "__main__":
     main()
     feeder_goldens()
+    ingest_goldens()

@@ -9,6 +9,7 @@ Layout (only what the hot path needs):
   builder.py           batched device-resident correspondence builder
   bev_slices.py        drop-in mirror of the BEV slicing feeder (BevSlices.generate_bev)
   construct_voxel.py   drop-in mirror of the MV3D voxel feeder (point_cloud_2_top_sparse)
+  lidar_ingest.py      drop-in mirror of the point-cloud ingest (get_lidar_point_cloud)
   config.py            the model.proto / kitti_dataset.proto sparse-pooling switches
 """
 from . import _cabi  # noqa: F401  (raises ImportError when libshpl.so is missing)
@@ -21,3 +22,4 @@ from .sparse_pool_utils import (SparsePoolLayer, SparseTensor, _sparse_pool_op, 
 from .builder import build_avod_plan  # noqa: F401
 from .bev_slices import BevSlices  # noqa: F401
 from . import construct_voxel  # noqa: F401
+from . import lidar_ingest  # noqa: F401

@@ -22,7 +22,7 @@ SHPL_ERR_CUDA = -2
 SHPL_ERR_WORKSPACE_TOO_SMALL = -3
 SHPL_ERR_UNSUPPORTED = -4
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 HEAVY_LEN = 2048          # SHPL_HEAVY_LEN of include/shpl.h
 
 
@@ -87,6 +87,9 @@ SIGNATURES = {
     "shpl_mv3d_voxelize": (ctypes.c_int, [c_void_p, c_void_p, c_int64, ctypes.c_double, ctypes.c_double, c_void_p, c_int32,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                           c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "shpl_lidar_workspace_bytes": (c_size_t, [c_int64]),
+    "shpl_lidar_to_cam": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, ctypes.c_float,
+                                         c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "shpl_pool_heavy": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p]),
 }

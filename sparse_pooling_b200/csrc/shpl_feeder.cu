@@ -462,3 +462,149 @@ extern "C" int shpl_bev_slices(const double* points, int64_t coord_stride, int64
     shpl::count_launches(1);
     return shpl::check_launch("shpl_bev_emit_kernel");
 }
+
+// ------------------------------------------------------------------------------------------------ ingest
+// Point-cloud ingest: velodyne scan -> camera frame -> points in front of the camera that
+// project inside the image.  Replaces the arithmetic of
+//   obj_utils.get_lidar_point_cloud   /root/reference/avod/wavedata/wavedata/tools/obj_detection/obj_utils.py:220-268
+//   calib_utils.lidar_to_cam_frame    /root/reference/avod/wavedata/wavedata/tools/core/calib_utils.py:371-410
+//   calib_utils.project_to_image      /root/reference/avod/wavedata/wavedata/tools/core/calib_utils.py:281-297
+// (the two file reads stay on the host).  One point per thread, fp64 in the rounding order of the reference's BLAS
+// calls (a 4-term dot = mul, fma, fma, fma: probed on this image for both dgemm shapes), STABLE compaction by a
+// decoupled look-back, output coordinate-major [3, capacity] so that shpl_bev_slices reads it through its strides.
+namespace {
+
+struct IngestArgs {
+    const float* velo;            // [N,4] x, y, z, intensity
+    long long N;
+    double R[12];                 // rows 0..2 of R0_rect(4x4) . Tr_velo_to_cam(4x4)
+    double P[12];                 // p2
+    int filter;                   // 0: every point (im_size = None)
+    double im_w, im_h;
+    int use_intensity;
+    float min_intensity;
+    unsigned* ticket;
+    unsigned long long* status;
+    int use_ticket;
+    double* out;                  // [3,cap]
+    long long cap;
+    int* counts;
+};
+
+__device__ __forceinline__ double dot4(const double* m, double x, double y, double z) {
+    double t = __dmul_rn(m[0], x);
+    t = __fma_rn(m[1], y, t);
+    t = __fma_rn(m[2], z, t);
+    t = __fma_rn(m[3], 1.0, t);
+    return t;
+}
+
+__global__ void __launch_bounds__(kThreads) shpl_lidar_to_cam_kernel(IngestArgs a) {
+    __shared__ int s_tile;
+    __shared__ unsigned s_w[kWarps], s_f[kWarps];
+    __shared__ unsigned long long s_ex;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int tile = blockIdx.x;
+    if (a.use_ticket) {
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        tile = s_tile;
+    }
+    const long long i = (long long)tile * kThreads + threadIdx.x;
+    bool keep = false, front = false;
+    double cx = 0, cy = 0, cz = 0;
+    if (i < a.N) {
+        const float4 p = reinterpret_cast<const float4*>(a.velo)[i];
+        const double x = (double)p.x, y = (double)p.y, z = (double)p.z;      // np.append(float32, float64 ones) -> float64
+        cx = dot4(a.R + 0, x, y, z);                                         // calib_utils.py:407
+        cy = dot4(a.R + 4, x, y, z);
+        cz = dot4(a.R + 8, x, y, z);
+        keep = true;
+        front = true;
+        if (a.filter) {
+            front = cz > 0.0;                                                // obj_utils.py:251
+            const double w = dot4(a.P + 8, cx, cy, cz);
+            const double u = __ddiv_rn(dot4(a.P + 0, cx, cy, cz), w);        // calib_utils.py:290-295
+            const double v = __ddiv_rn(dot4(a.P + 4, cx, cy, cz), w);
+            keep = front && (u > 0.0) && (u < a.im_w) && (v > 0.0) && (v < a.im_h);   // obj_utils.py:258-261 (strict)
+            if (a.use_intensity) keep = keep && (p.w > a.min_intensity);     // :266
+        }
+    }
+    const unsigned m = __ballot_sync(kFull, keep), mf = __ballot_sync(kFull, front);
+    if (lane == 0) {
+        s_w[warp] = __popc(m);
+        s_f[warp] = __popc(mf);
+    }
+    __syncthreads();
+    unsigned before = 0, tot = 0, totf = 0;
+#pragma unroll
+    for (int q = 0; q < kWarps; ++q) {
+        if (q < warp) before += s_w[q];
+        tot += s_w[q];
+        totf += s_f[q];
+    }
+    if (warp == 0) {
+        const unsigned long long ex = lookback(a.status, tile, ((unsigned long long)totf << 31) | tot, lane);
+        if (lane == 0) s_ex = ex;
+    }
+    __syncthreads();
+    const long long base = (long long)(s_ex & ((1ull << 31) - 1));
+    const long long n_tiles = (a.N + kThreads - 1) / kThreads > 0 ? (a.N + kThreads - 1) / kThreads : 1;
+    if (tile == n_tiles - 1 && threadIdx.x == 0) {
+        a.counts[0] = (int)(base + tot);
+        a.counts[1] = (int)((long long)(s_ex >> 31) + totf);
+        a.counts[2] = (base + tot > a.cap) ? 1 : 0;
+    }
+    const long long j = base + before + __popc(m & ((1u << lane) - 1u));
+    if (keep && j < a.cap) {
+        a.out[j] = cx;
+        a.out[a.cap + j] = cy;
+        a.out[2 * a.cap + j] = cz;
+    }
+}
+
+}  // namespace
+
+extern "C" size_t shpl_lidar_workspace_bytes(int64_t n_max) {
+    if (n_max < 0) n_max = 0;
+    const size_t tiles = (size_t)((n_max + kThreads - 1) / kThreads) + 1;
+    return 64 + align_up(sizeof(unsigned long long) * tiles, 64);
+}
+
+extern "C" int shpl_lidar_to_cam(const float* velo_xyzi, int64_t N, const double* rectified_host, const double* p2_host,
+                                 int32_t im_w, int32_t im_h, int32_t use_min_intensity, float min_intensity,
+                                 double* cam_out, int64_t capacity, int32_t* counts, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+    const char* who = "shpl_lidar_to_cam";
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    SHPL_REQUIRE(N >= 0 && N < (1ll << 30), SHPL_ERR_INVALID_ARGUMENT, "%s: N=%lld out of range", who, (long long)N);
+    SHPL_REQUIRE((N == 0 || velo_xyzi) && rectified_host && counts && workspace && capacity >= 0 && (capacity == 0 || cam_out),
+                 SHPL_ERR_INVALID_ARGUMENT, "%s: null pointer", who);
+    SHPL_REQUIRE(shpl::aligned(velo_xyzi, 16) && shpl::aligned(workspace, 64), SHPL_ERR_INVALID_ARGUMENT,
+                 "%s: the scan must be 16-byte aligned ([N,4] float32) and the workspace 64-byte aligned", who);
+    const bool filter = im_w > 0 && im_h > 0;
+    SHPL_REQUIRE(!filter || p2_host, SHPL_ERR_INVALID_ARGUMENT, "%s: an image size needs p2", who);
+    SHPL_REQUIRE(workspace_bytes >= shpl_lidar_workspace_bytes(N), SHPL_ERR_WORKSPACE_TOO_SMALL, "%s: workspace %zu bytes < %zu needed",
+                 who, workspace_bytes, shpl_lidar_workspace_bytes(N));
+    IngestArgs a{};
+    a.velo = velo_xyzi;
+    a.N = N;
+    for (int i = 0; i < 12; ++i) a.R[i] = rectified_host[i];
+    for (int i = 0; i < 12; ++i) a.P[i] = p2_host ? p2_host[i] : 0.0;
+    a.filter = filter ? 1 : 0;
+    a.im_w = (double)im_w;
+    a.im_h = (double)im_h;
+    a.use_intensity = (filter && use_min_intensity) ? 1 : 0;
+    a.min_intensity = min_intensity;
+    a.ticket = static_cast<unsigned*>(workspace);
+    a.status = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + 64);
+    a.out = cam_out;
+    a.cap = capacity;
+    a.counts = counts;
+    SHPL_CUDA_OK(cudaMemsetAsync(workspace, 0, shpl_lidar_workspace_bytes(N), s));
+    const long long tiles = (N + kThreads - 1) / kThreads > 0 ? (N + kThreads - 1) / kThreads : 1;
+    a.use_ticket = tiles > (long long)shpl::sm_count() * 4 ? 1 : 0;
+    shpl_lidar_to_cam_kernel<<<(unsigned)tiles, kThreads, 0, s>>>(a);
+    shpl::count_launches(1);
+    return shpl::check_launch("shpl_lidar_to_cam_kernel");
+}

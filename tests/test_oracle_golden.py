@@ -289,3 +289,25 @@ def test_mv3d_feeder_oracle_matches_reference(golden_dir, name, seed, n, kw):
                                                     f["fwd_range"], f["height_range"], f["max_points"])
     np.testing.assert_array_equal(bv2, bv_index)
     np.testing.assert_array_equal(mv2, m_val)
+
+
+# ------------------------------------------------------------ point-cloud ingest
+@pytest.mark.parametrize("seed,az", [(1, 0.4), (2, 0.15)])
+def test_ingest_oracle_matches_reference_get_lidar_point_cloud(golden_dir, seed, az):
+    """oracle/feeder_oracle.get_lidar_point_cloud against obj_utils.get_lidar_point_cloud of the reference, which read
+    the same scan and calibration from KITTI-format files (oracle/gen_goldens.ingest_goldens)."""
+    from oracle import feeder_oracle as fo
+    g = load(golden_dir, "lidar_ingest_seed%d.npz" % seed)
+    scan = synth.velodyne_scan(seed, az_step_deg=az)
+    assert digest(scan) == str(g["input_sha"])
+    # the calibration went through the text file: use the parsed values
+    pc = fo.get_lidar_point_cloud(scan, g["p2"], g["r0_rect"], g["tr_velodyne_to_cam"], im_size=list(g["im_size"]))
+    assert pc.shape == (3, int(g["n_fov"])) and pc.dtype == np.float64
+    assert digest(pc) == str(g["fov_sha"])
+    if "fov_points" in g:
+        np.testing.assert_array_equal(pc, g["fov_points"])
+    pc_all = fo.get_lidar_point_cloud(scan, g["p2"], g["r0_rect"], g["tr_velodyne_to_cam"])
+    assert pc_all.shape == (3, len(scan)) and digest(pc_all) == str(g["all_sha"])
+    # the reference's min_intensity branch indexes the z-filtered cloud with an unfiltered intensity mask (obj_utils.py:266)
+    with pytest.raises((ValueError, IndexError)):
+        fo.get_lidar_point_cloud(scan, g["p2"], g["r0_rect"], g["tr_velodyne_to_cam"], im_size=list(g["im_size"]), min_intensity=0.5)

@@ -171,3 +171,47 @@ def mv3d_frame(seed, n_points=20000, max_points=45, car=False):
 
 def features(seed, shape):
     return np.random.default_rng(seed).standard_normal(shape, dtype=np.float32)
+
+
+# ------------------------------------------------------------------ raw velodyne scans
+# KITTI object calibration 000000-like values (R0_rect, Tr_velo_to_cam; P2 as above)
+R0_RECT_KITTI = np.array([[9.999239e-01, 9.837760e-03, -7.445048e-03],
+                          [-9.869795e-03, 9.999421e-01, -4.278459e-03],
+                          [7.402527e-03, 4.351614e-03, 9.999631e-01]])
+TR_VELO_TO_CAM_KITTI = np.array([[7.533745e-03, -9.999714e-01, -6.166020e-04, -4.069766e-03],
+                                 [1.480249e-02, 7.280733e-04, -9.998902e-01, -7.631618e-02],
+                                 [9.998621e-01, 7.523790e-03, 1.480755e-02, -2.717806e-01]])
+
+
+def velodyne_scan(seed, az_step_deg=0.2, n_beams=64, obstacle_p=0.35):
+    """Raw 360-degree velodyne scan, float32 [N,4] = (x forward, y left, z up, intensity) in the LIDAR frame, as a KITTI
+    .bin file holds it (calib_utils.read_lidar): ground 1.73 m below the sensor, random obstacles."""
+    rng = np.random.default_rng(seed)
+    elev = np.deg2rad(np.linspace(2.0, -24.8, n_beams))
+    az = np.deg2rad(np.arange(-180.0, 180.0, az_step_deg))
+    E, A = np.meshgrid(elev, az, indexing="ij")
+    down = -np.sin(E)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ground = np.where(down > 1e-6, 1.73 / down, np.inf)
+    hit = rng.random(E.shape) < obstacle_p
+    rng_m = np.where(hit, np.minimum(rng.uniform(3.0, 75.0, E.shape), ground), ground)
+    ok = np.isfinite(rng_m) & (rng_m < 80.0)
+    r, e, a = rng_m[ok], E[ok], A[ok]
+    xyz = np.stack((r * np.cos(e) * np.cos(a), r * np.cos(e) * np.sin(a), r * np.sin(e)), axis=1)
+    xyz += rng.normal(0.0, 0.01, xyz.shape)
+    inten = rng.random(len(xyz))
+    return np.ascontiguousarray(np.c_[xyz, inten].astype(np.float32))
+
+
+def kitti_calib_text(p2=None, r0=None, tr=None):
+    """A KITTI object calib file (7 lines: P0..P3, R0_rect, Tr_velo_to_cam, Tr_imu_to_velo) as read_calibration parses it."""
+    p2 = P2_KITTI if p2 is None else p2
+    r0 = R0_RECT_KITTI if r0 is None else r0
+    tr = TR_VELO_TO_CAM_KITTI if tr is None else tr
+
+    def line(name, m):
+        return name + ": " + " ".join("%.12e" % v for v in np.asarray(m).reshape(-1))
+    p0 = p2.copy()
+    p0[:, 3] = 0.0
+    return "\n".join([line("P0", p0), line("P1", p0), line("P2", p2), line("P3", p2), line("R0_rect", r0),
+                      line("Tr_velo_to_cam", tr), line("Tr_imu_to_velo", tr)]) + "\n"
