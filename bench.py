@@ -673,6 +673,63 @@ def run_gpu(args):
         for fi in range(N_FRAMES):
             fo.generate_bev(scans[fi], GP, synth.AVOD_EXTENTS, synth.AVOD_VOXEL, -0.2, 2.3, 5)
         cpu_ms = (time.perf_counter() - t0) * 1e3 / N_FRAMES
+
+        # ---- the whole widened chain from a RAW velodyne scan: float32 [N,4] in pinned host
+        #      memory -> H2D -> ingest (camera frame + FOV filter) -> feeder -> both plans -> forward -> backward ->
+        #      D2H, every intermediate count handed on as a device pointer (no host read inside the step)
+        from sparse_pooling_b200 import lidar_ingest as li
+        import types as _types
+        cal = _types.SimpleNamespace(p2=P, r0_rect=synth.R0_RECT_KITTI, tr_velodyne_to_cam=synth.TR_VELO_TO_CAM_KITTI)
+        velos = [synth.velodyne_scan(300 + rank * N_FRAMES + i, az_step_deg=0.09) for i in range(N_FRAMES)]
+        velo_pin = [torch.from_numpy(v).pin_memory() for v in velos]
+        v_max = max(v.shape[0] for v in velos)
+        stage_velo = torch.empty((v_max, 4), dtype=torch.float32, device=dev)
+        cam_buf = torch.empty((3, v_max), dtype=torch.float64, device=dev)
+        ing_counts = torch.zeros(4, dtype=torch.int32, device=dev)
+        p_dev = ctypes.c_void_p(ing_counts.data_ptr())
+
+        def velo_step(k):
+            fi, si = k % N_FRAMES, k % n_sets
+            pipe, mp = pipes[si], maps[si]
+            nv = velos[fi].shape[0]
+            stage_velo[:nv].copy_(velo_pin[fi], non_blocking=True)
+            main = torch.cuda.current_stream()
+            ms = main.cuda_stream
+            li.lidar_to_cam_raw(stage_velo, nv, cal, [1242, 375], cam_buf, ing_counts)
+            bs.bev_slices_raw(cam_buf, cam_buf.stride(0), cam_buf.stride(1), nv, GP, synth.AVOD_EXTENTS, synth.AVOD_VOXEL,
+                              -0.2, 2.3, 5, np.log(16), work, lut=lut, p_dev=p_dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ss = side.cuda_stream
+                pipe.build_layer(0, work.unique_pts, work.voxel_indices, P, N_MAX, ss, n_dev=n_dev)
+                pipe.forward_layer(0, mp[0]["bev"], mp[0]["img"], ss, N_MAX)
+                pipe.backward_layer(0, mp[0]["g_bev"], mp[0]["g_img"], ss, N_MAX)
+            pipe.build_layer(1, work.unique_pts, work.voxel_indices, P, N_MAX, ms, n_dev=n_dev)
+            pipe.forward_layer(1, mp[1]["bev"], mp[1]["img"], ms, N_MAX)
+            pipe.backward_layer(1, mp[1]["g_bev"], mp[1]["g_img"], ms, N_MAX)
+            main.wait_stream(side)
+            off = 0
+            for li_ in range(len(specs)):
+                res_dev[off:off + 256].copy_(pipe.layers[li_].g_bev.reshape(-1)[:256])
+                res_dev[off + 256:off + 512].copy_(pipe.layers[li_].g_img.reshape(-1)[:256])
+                off += 512
+            res_dev[off:off + 16].copy_(torch.cat([L.plan.counts.reshape(-1)[:8] for L in pipe.layers]).float())
+            res_pin.copy_(res_dev, non_blocking=False)
+
+        for k in range(3):
+            velo_step(k)
+        torch.cuda.synchronize()
+        velo_counts = [int(x) for x in res_pin[-16:].tolist()][:4] + [int(ing_counts[0].item()), int(work.counts[0].item())]
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(K_e2e):
+            velo_step(k)
+        torch.cuda.synchronize()
+        dt_velo = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt_velo], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_velo = float(t.item())
         feeder = {"what": "BevSlices.generate_bev(output_indices=True) on the GPU: 5 height maps + density map [6,700,800] f64, "
                           "voxel_indices, unique_pts (shpl_bev_slices, CUDA-graph replays, CUDA events)",
                   "us_per_frame": feeder_us, "points_per_scan": [int(sc.shape[1]) for sc in scans],
@@ -682,7 +739,14 @@ def run_gpu(args):
                                     "what": "raw scan [3,P] f64 copied from pinned host memory, feeder, both plans built from the "
                                             "feeder's device-side pair count, forward+backward of both layers, gradients + plan "
                                             "counters read back, every step (ctypes C-ABI calls)"},
-                  "plan_counts_check": ref_counts[:4]}
+                  "plan_counts_check": ref_counts[:4],
+                  "e2e_from_velodyne": {"value": world * K_e2e / dt_velo, "unit": UNIT,
+                                        "h2d_bytes_per_step": int(velos[0].shape[0] * 16), "d2h_bytes_per_step": int(res_pin.numel() * 4),
+                                        "points_per_scan": [int(v.shape[0]) for v in velos],
+                                        "what": "raw 360-degree velodyne scan float32 [N,4] from pinned host memory, ingest (camera "
+                                                "frame, FOV filter), feeder, both plans, forward+backward of both layers, read-back; "
+                                                "all intermediate counts stay on the device",
+                                        "counts_check(nclip,nnz,oob,csr,fov_points,pairs)": velo_counts}}
     except Exception as ex:  # pragma: no cover
         print("feeder leg failed: %r" % (ex,), file=sys.stderr)
         torch.cuda.synchronize()

@@ -239,6 +239,8 @@ size_t shpl_bev_workspace_bytes(const double* extents_host, double voxel_size, i
 /* generate_bev(output_indices=True).
  *   points f64: coordinate c of point i at points[c*coord_stride + i*point_stride] -- the reference's
  *   point_cloud [3,P] is (coord_stride=P, point_stride=1), an [P,3] array (1, 3);
+ *   P_dev (device int32*, may be NULL): when given, only the first min(P, *P_dev) points exist -- lets the ingest's
+ *   device-side count (shpl_lidar_to_cam counts[0]) flow in without a host read;
  *   ground_plane_host f64 [4]; extents_host f64 [6]; slices of (height_hi-height_lo)/num_slices above the plane;
  *   log_norm = NORM_VALUES[source] (log 16 for lidar, bev_slices.py:12-14);
  *   density_lut (DEVICE f64 [lut_len], may be NULL): the density value of a cell holding n points for
@@ -253,7 +255,7 @@ size_t shpl_bev_workspace_bytes(const double* extents_host, double voxel_size, i
  * A slice with <= 1 point repeats the previous slice's cells and compounds its heights, like the
  * reference does (:79-112). */
 int shpl_bev_slices(const double* points, int64_t coord_stride, int64_t point_stride, int64_t P,
-                    const double* ground_plane_host, const double* extents_host, double voxel_size,
+                    const int32_t* P_dev, const double* ground_plane_host, const double* extents_host, double voxel_size,
                     double height_lo, double height_hi, int32_t num_slices, double log_norm,
                     const double* density_lut, int32_t lut_len,
                     int64_t* voxel_indices_out, double* unique_pts_out, int64_t capacity,

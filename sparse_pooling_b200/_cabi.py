@@ -80,7 +80,7 @@ SIGNATURES = {
     "shpl_pool_backward_dual": (ctypes.c_int, [c_void_p] * 10 + [c_int32] * 6 + [c_void_p] * 3),
     "shpl_bev_grid_dims": (ctypes.c_int, [c_void_p, ctypes.c_double, c_void_p, c_void_p]),
     "shpl_bev_workspace_bytes": (c_size_t, [c_void_p, ctypes.c_double, c_int32]),
-    "shpl_bev_slices": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, ctypes.c_double,
+    "shpl_bev_slices": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, ctypes.c_double,
                                        ctypes.c_double, ctypes.c_double, c_int32, ctypes.c_double, c_void_p, c_int32,
                                        c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "shpl_mv3d_workspace_bytes": (c_size_t, [c_int64]),

@@ -61,11 +61,12 @@ class BevWorkspace:
 
 
 def bev_slices_raw(points, coord_stride, point_stride, P, ground_plane, extents, voxel_size, height_lo, height_hi,
-                   num_slices, norm_value, work, lut=None, stream=None):
-    """One asynchronous shpl_bev_slices call into `work` (a BevWorkspace); nothing is read back."""
+                   num_slices, norm_value, work, lut=None, stream=None, p_dev=None):
+    """One asynchronous shpl_bev_slices call into `work` (a BevWorkspace); nothing is read back.  p_dev: optional
+    device pointer (ctypes.c_void_p) to the int32 number of valid points (P is then the capacity)."""
     gp = _f64_array(ground_plane, 4)
     ext = _f64_array(np.asarray(extents, dtype=np.float64), 6)
-    rc = _lib.shpl_bev_slices(_ptr(points), int(coord_stride), int(point_stride), int(P),
+    rc = _lib.shpl_bev_slices(_ptr(points), int(coord_stride), int(point_stride), int(P), p_dev,
                               gp.ctypes.data_as(ctypes.c_void_p), ext.ctypes.data_as(ctypes.c_void_p), float(voxel_size),
                               float(height_lo), float(height_hi), int(num_slices), float(norm_value),
                               _ptr(lut), 0 if lut is None else int(lut.numel()),

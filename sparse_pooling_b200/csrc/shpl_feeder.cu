@@ -66,6 +66,7 @@ struct ScatterArgs {
     const double* pts;
     long long coord_stride, point_stride;
     long long P;
+    const int* P_dev;             // optional device count: points i >= *P_dev do not exist
     BevGeom g;
     FeederWs ws;
 };
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kThreads) shpl_bev_scatter_kernel(ScatterArgs 
     const BevGeom& g = a.g;
     bool inside = false;
     double x = 0, y = 0, z = 0;
-    if (i < a.P) {
+    if (i < a.P && (a.P_dev == nullptr || i < (long long)*a.P_dev)) {
         const double* p = a.pts + i * a.point_stride;
         x = p[0];
         y = p[a.coord_stride];
@@ -403,7 +404,7 @@ extern "C" size_t shpl_bev_workspace_bytes(const double* extents_host, double vo
 }
 
 extern "C" int shpl_bev_slices(const double* points, int64_t coord_stride, int64_t point_stride, int64_t P,
-                               const double* ground_plane_host, const double* extents_host, double voxel_size,
+                               const int32_t* P_dev, const double* ground_plane_host, const double* extents_host, double voxel_size,
                                double height_lo, double height_hi, int32_t num_slices, double log_norm,
                                const double* density_lut, int32_t lut_len,
                                int64_t* voxel_indices_out, double* unique_pts_out, int64_t capacity,
@@ -434,6 +435,7 @@ extern "C" int shpl_bev_slices(const double* points, int64_t coord_stride, int64
         sa.coord_stride = coord_stride;
         sa.point_stride = point_stride;
         sa.P = P;
+        sa.P_dev = P_dev;
         sa.g = g;
         sa.ws = w;
         const unsigned blocks = (unsigned)((P + kThreads - 1) / kThreads);

@@ -91,9 +91,9 @@ def test_ingest_min_intensity_branch_behaves_like_the_reference(shpl, golden_dir
 
 
 def test_raw_scan_to_plans_without_host_reads(shpl, golden_dir):
-    """scan -> shpl_lidar_to_cam -> shpl_bev_slices -> shpl_build_avod, each count handed on as a device pointer... the
-    feeder needs the point count on the host (its grid is sized by it), so ONE 4-byte read sits between ingest and
-    feeder; everything after runs off device-side counts.  Same plan as the host-side chain through the oracles."""
+    """scan -> shpl_lidar_to_cam -> shpl_bev_slices -> shpl_build_avod with every count handed on as a DEVICE pointer
+    (P_dev, N_dev): no host read between the raw scan and the CSR plan.  Same plan as the host-side chain through
+    the oracles; stale data beyond the counts is ignored."""
     import ctypes
     from oracle import index_oracle as io
     from sparse_pooling_b200 import bev_slices as bs
@@ -105,21 +105,23 @@ def test_raw_scan_to_plans_without_host_reads(shpl, golden_dir):
     GP = np.array([0.0, -1.0, 0.0, 1.65])
     velo = torch.from_numpy(scan).to(dev)
     n = scan.shape[0]
-    cam = torch.empty((3, n), dtype=torch.float64, device=dev)
+    cam = torch.full((3, n), 3.0, dtype=torch.float64, device=dev)          # stale points inside the extents
     counts = torch.zeros(4, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
     shpl.lidar_ingest.lidar_to_cam_raw(velo, n, cal, [1242, 375], cam, counts)
-    m = int(counts[0].item())
-    cap = 5 * m
+    cap = 65536
     work = bs.BevWorkspace(synth.AVOD_EXTENTS, synth.AVOD_VOXEL, 5, cap, dev, with_maps=False)
-    bs.bev_slices_raw(cam, cam.stride(0), cam.stride(1), m, GP, synth.AVOD_EXTENTS, synth.AVOD_VOXEL, -0.2, 2.3, 5, np.log(16), work)
+    bs.bev_slices_raw(cam, cam.stride(0), cam.stride(1), n, GP, synth.AVOD_EXTENTS, synth.AVOD_VOXEL, -0.2, 2.3, 5, np.log(16), work,
+                      p_dev=ctypes.c_void_p(counts.data_ptr()))
     spec = LayerSpec("s1", (700, 800), (360, 1200), 8, 8, (1, 1), False, (1200, 360), (700, 800))
     pipe = FramePipeline([spec], cap, dev)
-    pipe.build_layer(0, work.unique_pts, work.voxel_indices, cal.p2, cap, torch.cuda.current_stream().cuda_stream,
-                     n_dev=ctypes.c_void_p(work.counts.data_ptr()))
+    pipe.build_layer(0, work.unique_pts, work.voxel_indices, cal.p2, cap, stream, n_dev=ctypes.c_void_p(work.counts.data_ptr()))
     torch.cuda.synchronize()
     # host chain through the oracles
     pc = fo.get_lidar_point_cloud(scan, cal.p2, cal.r0_rect, cal.tr_velodyne_to_cam, im_size=[1242, 375])
+    assert int(counts[0].item()) == pc.shape[1]
     _, _, idx, upts = fo.generate_bev(pc, GP, synth.AVOD_EXTENTS, synth.AVOD_VOXEL, -0.2, 2.3, 5)
+    assert int(work.counts[0].item()) == len(idx) < cap
     d = io.gen_sparse_pooling_input_avod(upts, idx, cal.p2, [1200, 360], (700, 800))
     o = io.produce_sparse_pooling_input(d, stride=[1, 1])
     ref = io.build_plan(o["Mij_pool"], np.ones(len(o["Mij_pool"]), np.float32), o["img_index_flip_pool"], 560000, 360, 1200)
