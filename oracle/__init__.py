@@ -15,6 +15,9 @@ Pinning status
   reference's own numpy code (imported from /root/reference by
   ``oracle/gen_goldens.py``; fixtures under ``tests/golden/``) and against the
   known-answer vectors KAT-1 / KAT-2 of SURVEY.md Appendix B.
+* feeders and ingest (BevSlices.generate_bev, MV3D point_cloud_2_top_sparse, get_lidar_point_cloud): PINNED --
+  ``feeder_oracle.py`` is checked against outputs of the reference's own classes / functions run by
+  ``gen_goldens.py`` on seeded synthetic scans (for the ingest: through KITTI-format files in a temporary directory).
 * value path (gather -> SpMM -> concat, scatter, gradients): the arithmetic lives
   in TensorFlow 1.8 (third-party, not vendored, not installable here) and the
   reference holds no golden vector, test or fixture for it:
