@@ -52,6 +52,38 @@ def main():
         fo.generate_bev(pts.T, GP, synth.AVOD_EXTENTS, synth.AVOD_VOXEL, -0.2, 2.3, 5)
         res["cpu_oracle_ms"] = (time.perf_counter() - t0) * 1e3
         out[name] = res
+    # the ingest in front of the feeder (shpl_lidar_to_cam): raw velodyne scans
+    import types
+    from sparse_pooling_b200 import lidar_ingest as li
+    cal = types.SimpleNamespace(p2=synth.P2_KITTI, r0_rect=synth.R0_RECT_KITTI, tr_velodyne_to_cam=synth.TR_VELO_TO_CAM_KITTI)
+    for name, seed, az in (("velodyne_118k", 1, 0.18), ("velodyne_235k", 2, 0.09)):
+        scan = synth.velodyne_scan(seed, az_step_deg=az)
+        n = scan.shape[0]
+        velo = torch.from_numpy(scan).to(dev)
+        cam = torch.empty((3, n), dtype=torch.float64, device=dev)
+        counts = torch.zeros(4, dtype=torch.int32, device=dev)
+
+        def call():
+            li.lidar_to_cam_raw(velo, n, cal, [1242, 375], cam, counts)
+        for _ in range(5):
+            call()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            call()
+        for _ in range(5):
+            g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(100):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fo.get_lidar_point_cloud(scan, cal.p2, cal.r0_rect, cal.tr_velodyne_to_cam, im_size=[1242, 375])
+        out[name] = {"points": int(n), "fov_points": int(counts[0].item()), "us_ingest": e0.elapsed_time(e1) * 10.0,
+                     "cpu_oracle_ms": (time.perf_counter() - t0) * 1e3}
     print(json.dumps(out))
     if len(sys.argv) > 1:
         with open(sys.argv[1], "w") as f:
