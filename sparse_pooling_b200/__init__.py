@@ -19,7 +19,7 @@ from .ops import SparsePoolFunction, SparsePoolPlan, sparse_pool  # noqa: F401
 from .sparse_pool_utils import (SparsePoolLayer, SparseTensor, _sparse_pool_op, _sparse_pool_trans_op,  # noqa: F401
                                 concat_bn_op, gen_sparse_pooling_input_avod, produce_sparse_pooling_input,
                                 sparse_pool_layer)
-from .builder import build_avod_plan  # noqa: F401
+from .builder import build_avod_plan, build_pairs_plan  # noqa: F401
 from .bev_slices import BevSlices  # noqa: F401
 from . import construct_voxel  # noqa: F401
 from . import lidar_ingest  # noqa: F401

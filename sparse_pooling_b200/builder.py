@@ -91,3 +91,60 @@ def build_avod_plan(points, voxel_indices, P, im_size, bv_size, stride=(1, 1), s
     if read_counts:
         plan.read_counts()
     return (plan, coo) if want_coo else plan
+
+
+def build_pairs_plan(img_index, bv_index, im_size, bv_size, stride=(1, 1), src_hw=None, m_val=None, read_counts=True,
+                     plan=None):
+    """Batched form of produce_sparse_pooling_input for callers that already hold (img_index, bv_index) pairs -- the
+    MV3D path (minibatch_mv3d_img.py:93 -> train_mv_voxel.py:325-326), whose reference is batch-1 only.
+
+    img_index: one [3,n] (or [2,n]) array per frame, bv_index: one [n,2] array per frame, m_val: one [n] array per
+    frame or None (numpy or CUDA tensors).  The frames are stacked into ONE plan (rows / pixels offset by the frame
+    index), so a [B,H,W,C] batch is pooled by one launch.  Unlike produce_sparse_pooling_input the callers' img_index
+    arrays are NOT modified in place (the floor / clamp is applied to device copies)."""
+    if not isinstance(img_index, (list, tuple)):
+        img_index, bv_index = [img_index], [bv_index]
+        m_val = [m_val]
+    elif m_val is None:
+        m_val = [None] * len(img_index)
+    frames = len(img_index)
+    first = img_index[0]
+    dev = first.device if isinstance(first, torch.Tensor) and first.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    s_img, s_bv = int(stride[0]), int(stride[1])
+    im_w, im_h = int(im_size[0]), int(im_size[1])
+    bv_h, bv_w = int(bv_size[0]), int(bv_size[1])
+    if src_hw is None:
+        src_hw = (im_h // s_img, im_w // s_img)
+    R = (bv_h // s_bv) * (bv_w // s_bv)
+    uv = [_dev_f64(np.asarray(a)[0:2] if not isinstance(a, torch.Tensor) else a[0:2], dev).contiguous() for a in img_index]
+    bv = [(b.to(device=dev, dtype=torch.int64) if isinstance(b, torch.Tensor)
+           else torch.from_numpy(np.ascontiguousarray(np.asarray(b), dtype=np.int64)).to(dev)).reshape(-1, 2).contiguous() for b in bv_index]
+    ns = [int(u.shape[1]) for u in uv]
+    for f in range(frames):
+        if bv[f].shape[0] != ns[f]:
+            raise ValueError("frame %d: bv_index has %d rows, img_index %d columns" % (f, bv[f].shape[0], ns[f]))
+    n_total = sum(ns)
+    if plan is None:
+        plan = SparsePoolPlan(R, src_hw, n_total, dev, frames=frames)
+    elif plan.capacity < n_total or plan.frames != frames or plan.rows_per_frame != R:
+        raise ValueError("the plan passed in does not fit this batch")
+    ws = ops.workspace(dev, max(ns + [1]))
+    keep = []
+    for f in range(frames):
+        mv = None
+        if m_val[f] is not None:
+            mv = _dev_f64(m_val[f], dev).reshape(-1)
+            if mv.shape[0] < ns[f]:
+                mv = torch.cat([mv, torch.zeros(ns[f] - mv.shape[0], dtype=torch.float64, device=dev)])
+            keep.append(mv)
+        st = plan.frame_struct(f)
+        rc = _lib.shpl_produce_input(_ptr(uv[f][0]), _ptr(uv[f][1]), _ptr(bv[f]), ns[f], im_w, im_h, bv_h, bv_w, s_img, s_bv,
+                                     _ptr(mv), int(src_hw[0]), int(src_hw[1]), None, None, None, None, ctypes.byref(st),
+                                     f * plan.rows_per_frame, f * plan.src_per_frame, plan.entry_base(f),
+                                     _ptr(ws), ws.numel(), _stream())
+        _cabi.check(rc, "shpl_produce_input")
+    plan.entry_bound = max(n_total, 1)
+    plan._keep = (uv, bv, keep)
+    if read_counts:
+        plan.read_counts()
+    return plan

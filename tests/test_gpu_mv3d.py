@@ -184,3 +184,40 @@ def test_mv3d_feeder_large_cloud_ticketed_scans(shpl):
     got, ref = run_gpu(shpl, f), run_oracle(f)
     assert ref[4].shape[0] > 150000
     assert_same(got, ref)
+
+
+def test_mv3d_config3_batch_of_8_frames_one_launch(shpl):
+    """BASELINE config 3, batch 8: eight MV3D frames (feeder -> pairs with 1/count weights) stacked into ONE plan by
+    build_pairs_plan and pooled by one launch each way, against the per-frame oracle chain.  (The reference is batch-1:
+    minibatch_mv3d_img.py:49-50; the batch is this repo's sharding unit.)"""
+    from oracle import cref
+    C, B = 64, 8
+    rng = np.random.default_rng(17)
+    frames = [synth.mv3d_frame(seed=50 + k, n_points=6000) for k in range(B)]
+    img_index, bv_index, m_val, refs = [], [], [], []
+    for f in frames:
+        u, v = f["img_index2"]
+        inside = (u >= 0) & (u < 1280) & (v >= 0) & (v < 384)
+        cam4, img2 = np.ascontiguousarray(synth.mv3d_cam4(f)[inside]), np.ascontiguousarray(f["img_index2"][:, inside])
+        _, vfs, ii, bi, mv = run_gpu(shpl, f, points=cam4, img2=img2)
+        img_index.append(ii)
+        bv_index.append(bi)
+        m_val.append(mv)
+        _, _, rimg, rbv, rmv = run_oracle(f, points=cam4, img2=img2)
+        o_ref = io.produce_sparse_pooling_input(dict(img_index=np.array(rimg, dtype=np.float64), img_size=f["img_size"], bv_index=rbv,
+                                                     bv_size=[200, 240]), M_val=rmv, stride=[8, 2])
+        refs.append((o_ref, np.asarray(rmv, dtype=np.float32)))
+    plan = shpl.build_pairs_plan(img_index, bv_index, frames[0]["img_size"], [200, 240], stride=(8, 2), m_val=m_val)
+    assert plan.frames == B and plan.nnz == [len(r[1]) for r in refs] and sum(plan.n_oob) == 0
+    bev = rng.standard_normal((B, 100, 120, 16), dtype=np.float32)
+    img = rng.standard_normal((B, 48, 160, C), dtype=np.float32)
+    tb, ti = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
+    fused = shpl.sparse_pool(tb, ti, plan)
+    g = rng.standard_normal(tuple(fused.shape), dtype=np.float32)
+    fused.backward(torch.from_numpy(g).cuda())
+    for k, (o_ref, val) in enumerate(refs):
+        np.testing.assert_array_equal(fused[k].detach().cpu().numpy(),
+                                      cref.forward(bev[k], img[k], o_ref["Mij_pool"], val, o_ref["img_index_flip_pool"]))
+        gd, gs = cref.backward(g[k], o_ref["Mij_pool"], val, o_ref["img_index_flip_pool"], 16, (48, 160, C))
+        np.testing.assert_array_equal(tb.grad[k].cpu().numpy(), gd)
+        np.testing.assert_array_equal(ti.grad[k].cpu().numpy(), gs)
