@@ -49,6 +49,9 @@ namespace {
 #ifndef SHPL_SPARSE_MIN_CTAS
 #define SHPL_SPARSE_MIN_CTAS 4
 #endif
+#ifndef SHPL_SPARSE_MIN_CTAS_WIDE
+#define SHPL_SPARSE_MIN_CTAS_WIDE 3
+#endif
 #ifndef SHPL_SPARSE_GATHERS
 #define SHPL_SPARSE_GATHERS 4     // gathers in flight per warp in the entry CTAs of the sparse kernel
 #endif
@@ -666,8 +669,8 @@ __global__ void __launch_bounds__(kThreads, SHPL_WIDE_MIN_CTAS) shpl_pool_wide_k
 // L2 (tools/probe/pattern_probe.cu).  Here the roles are split like in the wide kernel: ENTRY CTAs gather by entry
 // chunk and own the busy cells; STREAM CTAs copy the dense parts and write the zeros of the cells that receive
 // nothing, one dependent load (the tile's offsets) away from a bare copy.  Same sums in the same order.
-template <int W, bool kAdd>
-__global__ void __launch_bounds__(kThreads, SHPL_SPARSE_MIN_CTAS) shpl_pool_sparse_kernel(PoolArgs a) {
+template <int W, bool kAdd, int ACC>
+__global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SHPL_SPARSE_MIN_CTAS_WIDE) shpl_pool_sparse_kernel(PoolArgs a) {
     using V = typename VecOf<W>::type;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -682,9 +685,11 @@ __global__ void __launch_bounds__(kThreads, SHPL_SPARSE_MIN_CTAS) shpl_pool_spar
         if (e0 >= e_end) return;
         // cells with more than kLongRow entries are left to the stream CTAs (whole-warp sum) or to shpl_pool_heavy:
         // the entry walk skips them exactly like it skips heavy cells
-        pool_entries_wide<V, 1, SHPL_SPARSE_GATHERS>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.key, jb.idx, jb.val, e0,
+        // (with more than 32 vectors per cell there is no whole-warp path: the entry walk sums every length)
+        pool_entries_wide<V, ACC, SHPL_SPARSE_GATHERS>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.key, jb.idx, jb.val, e0,
                                 min(e0 + jb.entry_chunk, e_end), e_begin, e_end, pout, jb.pool_out_stride,
-                                kAdd ? din : nullptr, jb.dense_in_stride, jb.vs, jb.ptr, kLongRow, lane);
+                                kAdd ? din : nullptr, jb.dense_in_stride, jb.vs, jb.ptr,
+                                jb.vs <= 32 ? kLongRow : jb.heavy_len, lane);
         return;
     }
     const int stream_ctas = jb.stream_ctas;
@@ -702,7 +707,7 @@ __global__ void __launch_bounds__(kThreads, SHPL_SPARSE_MIN_CTAS) shpl_pool_spar
                 if (jb.heavy_len > 0 && hi - lo > jb.heavy_len) hi = lo;   // heavy cell: written as empty here
             }
             busy = __ballot_sync(kFull, hi > lo);                          // cells somebody else writes (entry CTAs) ...
-            longs = __ballot_sync(kFull, hi - lo > kLongRow);               // ... or this warp sums as a whole, below
+            longs = jb.vs <= 32 ? __ballot_sync(kFull, hi - lo > kLongRow) : 0u;   // ... or this warp sums as a whole, below
         }
         if (jb.vd > 0) {
             // concat form: the dense part of every cell; add form: a plain copy for the cells that receive nothing
@@ -976,6 +981,15 @@ int narrow_ctas_per_sm(int w, bool add) {
     return c;
 }
 
+int wide_stream_env() {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("SHPL_WIDE_STREAM");
+        env = e ? atoi(e) : 2;      // 0: the CTA-tiled wide kernel; 1: entry + stream kernel up to 64 vectors per cell; 2: always
+    }
+    return env;
+}
+
 // Sparse regime of the narrow channel counts: every pooled job comes with its key array and the entries are few
 // next to the cells (KITTI stride 1: 20 k entries for 560 k cells).  SHPL_SPARSE=0 forces the one-kernel path.
 bool sparse_regime(const PoolArgs& a, const JobSpec* const* spec) {
@@ -1037,7 +1051,19 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
         max_vs = o.vs > max_vs ? o.vs : max_vs;
     }
     if (a.n_jobs == 0) return SHPL_OK;
-    const bool wide = max_vs >= 32;
+    bool wide = max_vs >= 32;
+    bool stream_split = !wide && sparse_regime(a, src_spec);
+    // Wide jobs take the entry + stream kernel too whenever their key arrays are there (measured on B200: full scan
+    // C = 128 forward 218 -> 165 us, RetinaNet P2 24.0 -> 20.4 us, the bench step 142 -> 131 us); the CTA-tiled
+    // shpl_pool_wide_kernel stays as the path without key arrays.
+    if (wide && wide_stream_env() && (max_vs <= 64 || wide_stream_env() > 1)) {
+        bool keys = true;
+        for (int i = 0; i < a.n_jobs; ++i) keys = keys && (a.job[i].vs == 0 || a.job[i].key != nullptr);
+        if (keys) {
+            wide = false;
+            stream_split = true;
+        }
+    }
     a.begin[0] = 0;
     for (int i = 0; i < a.n_jobs; ++i) {
         Job& o = a.job[i];
@@ -1063,7 +1089,7 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
         else if (w == 2) shpl_pool_wide_kernel<2, 2><<<g, kThreads, 0, s>>>(a);
         else if (one) shpl_pool_wide_kernel<1, 1><<<g, kThreads, 0, s>>>(a);
         else shpl_pool_wide_kernel<1, 2><<<g, kThreads, 0, s>>>(a);
-    } else if (sparse_regime(a, src_spec)) {
+    } else if (stream_split) {
         // sparse regime: entry CTAs (gathers) + stream CTAs (dense parts, zeros) in one launch
         long long total_tiles = 0;
         for (int i = 0; i < a.n_jobs; ++i) total_tiles += a.job[i].tiles;
@@ -1084,12 +1110,19 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
         }
         const unsigned g = (unsigned)a.begin[a.n_jobs];
         const bool add = a.job[0].add != 0;
-        if (w == 4 && add) shpl_pool_sparse_kernel<4, true><<<g, kThreads, 0, s>>>(a);
-        else if (w == 4) shpl_pool_sparse_kernel<4, false><<<g, kThreads, 0, s>>>(a);
-        else if (w == 2 && add) shpl_pool_sparse_kernel<2, true><<<g, kThreads, 0, s>>>(a);
-        else if (w == 2) shpl_pool_sparse_kernel<2, false><<<g, kThreads, 0, s>>>(a);
-        else if (add) shpl_pool_sparse_kernel<1, true><<<g, kThreads, 0, s>>>(a);
-        else shpl_pool_sparse_kernel<1, false><<<g, kThreads, 0, s>>>(a);
+        if (max_vs > 32) {
+            if (w == 4 && add) shpl_pool_sparse_kernel<4, true, 2><<<g, kThreads, 0, s>>>(a);
+            else if (w == 4) shpl_pool_sparse_kernel<4, false, 2><<<g, kThreads, 0, s>>>(a);
+            else if (w == 2 && add) shpl_pool_sparse_kernel<2, true, 2><<<g, kThreads, 0, s>>>(a);
+            else if (w == 2) shpl_pool_sparse_kernel<2, false, 2><<<g, kThreads, 0, s>>>(a);
+            else if (add) shpl_pool_sparse_kernel<1, true, 2><<<g, kThreads, 0, s>>>(a);
+            else shpl_pool_sparse_kernel<1, false, 2><<<g, kThreads, 0, s>>>(a);
+        } else if (w == 4 && add) shpl_pool_sparse_kernel<4, true, 1><<<g, kThreads, 0, s>>>(a);
+        else if (w == 4) shpl_pool_sparse_kernel<4, false, 1><<<g, kThreads, 0, s>>>(a);
+        else if (w == 2 && add) shpl_pool_sparse_kernel<2, true, 1><<<g, kThreads, 0, s>>>(a);
+        else if (w == 2) shpl_pool_sparse_kernel<2, false, 1><<<g, kThreads, 0, s>>>(a);
+        else if (add) shpl_pool_sparse_kernel<1, true, 1><<<g, kThreads, 0, s>>>(a);
+        else shpl_pool_sparse_kernel<1, false, 1><<<g, kThreads, 0, s>>>(a);
     } else {
         // partition the resident grid between the jobs in proportion to their tiles (a CTA serves one job)
         long long total_tiles = 0;
