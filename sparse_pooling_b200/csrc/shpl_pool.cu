@@ -52,6 +52,9 @@ namespace {
 #ifndef SHPL_SPARSE_MIN_CTAS_WIDE
 #define SHPL_SPARSE_MIN_CTAS_WIDE 3
 #endif
+#ifndef SHPL_SPARSE_GATHERS_WIDE
+#define SHPL_SPARSE_GATHERS_WIDE 4
+#endif
 #ifndef SHPL_SPARSE_GATHERS
 #define SHPL_SPARSE_GATHERS 4     // gathers in flight per warp in the entry CTAs of the sparse kernel
 #endif
@@ -686,7 +689,7 @@ __global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SH
         // cells with more than kLongRow entries are left to the stream CTAs (whole-warp sum) or to shpl_pool_heavy:
         // the entry walk skips them exactly like it skips heavy cells
         // (with more than 32 vectors per cell there is no whole-warp path: the entry walk sums every length)
-        pool_entries_wide<V, ACC, SHPL_SPARSE_GATHERS>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.key, jb.idx, jb.val, e0,
+        pool_entries_wide<V, ACC, (ACC == 1 ? SHPL_SPARSE_GATHERS : SHPL_SPARSE_GATHERS_WIDE)>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.key, jb.idx, jb.val, e0,
                                 min(e0 + jb.entry_chunk, e_end), e_begin, e_end, pout, jb.pool_out_stride,
                                 kAdd ? din : nullptr, jb.dense_in_stride, jb.vs, jb.ptr,
                                 jb.vs <= 32 ? kLongRow : jb.heavy_len, lane);
@@ -1008,7 +1011,7 @@ bool sparse_regime(const PoolArgs& a, const JobSpec* const* spec) {
         }
         cells += o.n_cells;
     }
-    return nnz * 4 <= cells;
+    return env > 1 || nnz * 4 <= cells;      // SHPL_SPARSE=2: always (experiments)
 }
 
 int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* who) {
