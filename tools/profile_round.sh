@@ -9,7 +9,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-fil
 
 M="python tools/microbench.py --config bench --iters 3"
 $M > gpurun_out/plain_${tag}_micro.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:shpl_pool_wide -c 12 -o gpurun_out/${tag}_pool_kernels -f $M > gpurun_out/ncu_${tag}_micro.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:shpl_pool_sparse -c 12 -o gpurun_out/${tag}_pool_kernels -f $M > gpurun_out/ncu_${tag}_micro.log 2>&1
 
 N="python tools/microbench.py --config b --iters 3"
 $N > gpurun_out/plain_${tag}_micro_b.log 2>&1 &&
