@@ -66,6 +66,33 @@ def test_invalid_arguments_return_error_codes_without_a_gpu(lib):
     assert rc == _cabi.SHPL_ERR_INVALID_ARGUMENT and b"stride" in L.shpl_last_error()
 
 
+def test_feeder_host_side_queries_and_argument_checks(lib):
+    """The feeders' host-side entry points run without a GPU: grid geometry (voxel_grid_2d.py:126-149), workspace
+    sizes, and the argument checks in front of any launch."""
+    import numpy as np
+    from sparse_pooling_b200 import _cabi
+    L = _cabi.lib
+    ext = np.array([-40.0, 40.0, -5.0, 3.0, 0.0, 70.0])
+    nx, nz = ctypes.c_int32(0), ctypes.c_int32(0)
+    assert L.shpl_bev_grid_dims(ext.ctypes.data_as(ctypes.c_void_p), 0.1, ctypes.byref(nx), ctypes.byref(nz)) == 0
+    assert (nx.value, nz.value) == (800, 700)          # voxel_grid_2d_test.py:38-59: num_divisions == [800, 1, 700]
+    w5 = L.shpl_bev_workspace_bytes(ext.ctypes.data_as(ctypes.c_void_p), 0.1, 5)
+    w2 = L.shpl_bev_workspace_bytes(ext.ctypes.data_as(ctypes.c_void_p), 0.1, 2)
+    assert w5 > w2 > 560000 * 8
+    assert L.shpl_bev_workspace_bytes(ext.ctypes.data_as(ctypes.c_void_p), 0.1, 9) == 0          # > SHPL_BEV_MAX_SLICES
+    assert L.shpl_bev_workspace_bytes(ext.ctypes.data_as(ctypes.c_void_p), -1.0, 5) == 0
+    assert L.shpl_mv3d_workspace_bytes(1000) < L.shpl_mv3d_workspace_bytes(100000)
+    assert L.shpl_lidar_workspace_bytes(1000) < L.shpl_lidar_workspace_bytes(1000000)
+    gp = np.array([0.0, -1.0, 0.0, 1.65])
+    rc = L.shpl_bev_slices(None, 1, 1, 10, None, gp.ctypes.data_as(ctypes.c_void_p), ext.ctypes.data_as(ctypes.c_void_p), 0.1,
+                           -0.2, 2.3, 5, float(np.log(16)), None, 0, None, None, 0, None, None, None, 0, None)
+    assert rc == _cabi.SHPL_ERR_INVALID_ARGUMENT and b"null pointer" in L.shpl_last_error()
+    rc = L.shpl_mv3d_voxelize(None, None, 5, 0.2, 0.4, None, 45, None, None, None, None, 0, None, None, None, 0, None, None, 0, None)
+    assert rc == _cabi.SHPL_ERR_INVALID_ARGUMENT
+    rc = L.shpl_lidar_to_cam(None, 5, None, None, 0, 0, 0, 0.0, None, 0, None, None, 0, None)
+    assert rc == _cabi.SHPL_ERR_INVALID_ARGUMENT
+
+
 def test_product_package_does_not_import_the_oracle():
     """The oracle is test infrastructure: nothing under sparse_pooling_b200/ may reference it."""
     pkg = os.path.join(ROOT, "sparse_pooling_b200")
