@@ -984,6 +984,15 @@ int narrow_ctas_per_sm(int w, bool add) {
     return c;
 }
 
+int entry_chunk_env() {      // entries per warp in the entry CTAs (experiment knob)
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("SHPL_ENTRY_CHUNK");
+        env = (e && atoi(e) > 0) ? atoi(e) : 0;
+    }
+    return env;
+}
+
 int wide_stream_env() {
     static int env = -1;
     if (env < 0) {
@@ -1107,7 +1116,9 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
             if (c > need) c = need;
             if (c < 1) c = 1;
             o.stream_ctas = (int)c;
-            o.entry_chunk = 8;
+            // entries per warp: 16 measured best for rows up to 1 KB (bench step 130 -> 123 us against 8; 24 gains 2 % more
+            // there but hurts skewed maps); 3 KB rows (MV3D, C = 768) want the shorter chains of 8
+            o.entry_chunk = entry_chunk_env() > 0 ? entry_chunk_env() : (o.vs * w > 256 ? 8 : 16);
             o.entry_ctas = o.vs > 0 ? (src_spec[i]->nnz_max + o.entry_chunk * kWarps - 1) / (o.entry_chunk * kWarps) : 0;
             a.begin[i + 1] = a.begin[i] + o.entry_ctas + o.stream_ctas;
         }
