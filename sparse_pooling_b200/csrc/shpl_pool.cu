@@ -993,6 +993,15 @@ int entry_chunk_env() {      // entries per warp in the entry CTAs (experiment k
     return env;
 }
 
+int stream_ctas_per_sm() {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("SHPL_STREAM_CTAS_PER_SM");
+        env = (e && atoi(e) > 0) ? atoi(e) : 6;
+    }
+    return env;
+}
+
 int wide_stream_env() {
     static int env = -1;
     if (env < 0) {
@@ -1105,7 +1114,10 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
         // sparse regime: entry CTAs (gathers) + stream CTAs (dense parts, zeros) in one launch
         long long total_tiles = 0;
         for (int i = 0; i < a.n_jobs; ++i) total_tiles += a.job[i].tiles;
-        const long long cap = (long long)shpl::sm_count() * narrow_ctas_per_sm(w, a.job[0].add != 0);
+        // stream CTAs per SM: 6.  Measured in the bench step (4 streams): 4 -> 8479 frames/s but layer B forward alone
+        // 45.1 us; 6 -> 8353 / 42.7 us; 8 -> 8172 / 42.2 us; 12 -> 7836 / 41.1 us.  Fewer CTAs leave room for the kernels
+        // of the other streams, more CTAs make the kernel itself faster.
+        const long long cap = (long long)shpl::sm_count() * stream_ctas_per_sm();
         long long want = (total_tiles + kWarps - 1) / kWarps;
         if (want > cap) want = cap;
         a.begin[0] = 0;
