@@ -323,7 +323,7 @@ def run_gpu(args):
     #      graph launches are paid once per G steps, and the dependencies are per layer (the plans of frame k+1 are
     #      built as soon as the pooling that last used their buffer set has finished; the pooling of frame k starts as
     #      soon as its plans are there) instead of a barrier at every step boundary.
-    G = 8
+    G = max(4, int(args.graph_steps) // 4 * 4)
     multi = None
 
     def multi_step(k0, n_steps):
@@ -797,6 +797,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--single-step-graphs", action="store_true", help="one CUDA graph per step (no multi-step graph)")
+    ap.add_argument("--graph-steps", type=int, default=8, help="consecutive steps captured in one CUDA graph (multiple of 4)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -698,15 +698,29 @@ __global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SH
     const int stream_ctas = jb.stream_ctas;
     V* dout = static_cast<V*>(jb.dense_out);
     unsigned any_long = 0u;
-    for (int t = (b - jb.entry_ctas) * kWarps + warp; t < jb.tiles; t += stream_ctas * kWarps) {
+    const int t_step = stream_ctas * kWarps;
+    int t = (b - jb.entry_ctas) * kWarps + warp;
+    // the CSR offsets of a tile are its only dependent load: they are fetched one tile ahead
+    int lo_n = 0, hi_n = 0;
+    if (jb.vs > 0 && t < jb.tiles && t * jb.rows_per_tile + lane < jb.n_cells && lane < jb.rows_per_tile) {
+        lo_n = __ldg(jb.ptr + t * jb.rows_per_tile + lane);
+        hi_n = __ldg(jb.ptr + t * jb.rows_per_tile + lane + 1);
+    }
+    for (; t < jb.tiles; t += t_step) {
         const int r0 = t * jb.rows_per_tile;
         const int rows = min(jb.rows_per_tile, jb.n_cells - r0);
         unsigned busy = 0u, longs = 0u;
         if (jb.vs > 0) {
-            int lo = 0, hi = 0;
+            int lo = lo_n, hi = hi_n;
+            lo_n = hi_n = 0;
+            {
+                const int tn = t + t_step;
+                if (tn < jb.tiles && lane < jb.rows_per_tile && tn * jb.rows_per_tile + lane < jb.n_cells) {
+                    lo_n = __ldg(jb.ptr + tn * jb.rows_per_tile + lane);
+                    hi_n = __ldg(jb.ptr + tn * jb.rows_per_tile + lane + 1);
+                }
+            }
             if (lane < rows) {
-                lo = __ldg(jb.ptr + r0 + lane);
-                hi = __ldg(jb.ptr + r0 + lane + 1);
                 if (jb.heavy_len > 0 && hi - lo > jb.heavy_len) hi = lo;   // heavy cell: written as empty here
             }
             busy = __ballot_sync(kFull, hi > lo);                          // cells somebody else writes (entry CTAs) ...
