@@ -11,6 +11,7 @@ Layout (only what the hot path needs):
   construct_voxel.py   drop-in mirror of the MV3D voxel feeder (point_cloud_2_top_sparse)
   lidar_ingest.py      drop-in mirror of the point-cloud ingest (get_lidar_point_cloud)
   config.py            the model.proto / kitti_dataset.proto sparse-pooling switches
+  torch_op.py          the pooling kernels as registered PyTorch custom ops (torch.ops.shpl.pool) with autograd
 """
 from . import _cabi  # noqa: F401  (raises ImportError when libshpl.so is missing)
 from .config import (KittiDatasetSparsePoolingConfig, RetinaNetSparsePoolingConfig,  # noqa: F401
@@ -23,3 +24,4 @@ from .builder import build_avod_plan, build_pairs_plan  # noqa: F401
 from .bev_slices import BevSlices  # noqa: F401
 from . import construct_voxel  # noqa: F401
 from . import lidar_ingest  # noqa: F401
+from . import torch_op  # noqa: F401  (registers torch.ops.shpl.pool / pool_backward)
