@@ -151,6 +151,8 @@ struct Job {
     int rows_per_tile;       // narrow: cells per warp tile
     int entry_ctas;          // wide / sparse: leading CTAs of this job that gather by entry; narrow: CTAs serving the job
     int stream_ctas;         // sparse: CTAs of this job that stream the dense parts and zeros
+    int packed;              // sparse: 1 = lane-group entry walk for few vectors per cell (SHPL_PACKED=0 switches it off)
+    int long_len;            // sparse: cells with more entries are summed by the stream warps as a whole (kLongRow; 512 when packed)
     int entry_chunk;         // wide: entries per warp
     int tiles;               // narrow: warp tiles; wide: CTA tiles of kWideTile cells
 };
@@ -433,6 +435,109 @@ __device__ __forceinline__ void pool_row_wide(const V* __restrict__ src, int src
     }
 }
 
+// Entry-parallel gather for FEW channel vectors per cell (nv a power of two <= 16): the lanes of a warp form
+// G = 32 / nv groups and every group gathers a different entry, so kPackedUnroll * G gathers are in flight per warp
+// instead of leaving 32 - nv lanes idle.  The products are then handed to lanes 0..nv-1 by shuffles ONE ENTRY AT A
+// TIME, in ascending k, with a flush whenever the key changes: the same additions in the same order as the
+// sequential walk (bit-identical).  The hand-over costs ~60 issue cycles per entry, so it pays where entries are many
+// and rows short (the dense regime: 1 M pairs, C = 64: 201 -> 130 us); with a few entries per cell the plain walk of
+// pool_entries_wide is faster, and long rows go to the whole-warp path.  Chunk ownership as in pool_entries_wide: a warp owns the cells whose first entry lies in its chunk.
+constexpr int kPackedUnroll = 4;
+
+template <typename V>
+__device__ __forceinline__ void pool_entries_packed(const V* __restrict__ src, int src_stride,
+                                                    const int* __restrict__ key, const int* __restrict__ idx,
+                                                    const float* __restrict__ val, int e0, int e1, int e_begin,
+                                                    int e_end, V* __restrict__ out, int out_stride,
+                                                    const V* __restrict__ addend, int add_stride, int nv,
+                                                    const int* __restrict__ ptr, int heavy_len, int lane) {
+    const int G = 32 / nv;
+    const int g = lane / nv, q = lane & (nv - 1);
+    int base = e0;
+    if (e0 > e_begin) {       // skip the entries that continue a cell begun in an earlier chunk
+        const int prev_row = __ldg(key + e0 - 1);
+        while (true) {
+            const int k = base + lane;
+            const bool fresh = k >= e_end || __ldg(key + k) != prev_row;
+            const unsigned m = __ballot_sync(kFull, fresh);
+            if (m) {
+                base += __ffs(m) - 1;
+                break;
+            }
+            base += 32;
+            if (base >= e1) return;
+        }
+        if (base >= e1) return;          // no cell starts in this chunk
+    }
+    if (base >= e_end) return;
+    int cur_row = -1, run_len = 0;
+    V acc = vzero((V*)nullptr);
+    bool done = false;
+    while (!done) {
+        V prod[kPackedUnroll];
+        int row[kPackedUnroll];
+#pragma unroll
+        for (int u = 0; u < kPackedUnroll; ++u) {
+            const int k = base + u * G + g;
+            row[u] = -1;
+            prod[u] = vzero((V*)nullptr);
+            if (k < e_end && g < G) {
+                row[u] = __ldg(key + k);
+                const int p = __ldg(idx + k);
+                const float w = __ldg(val + k);
+                prod[u] = vscale(w, __ldg(src + (size_t)p * src_stride + q));
+            }
+        }
+        int next_base = base + kPackedUnroll * G;
+        bool leave = false;
+#pragma unroll
+        for (int u = 0; u < kPackedUnroll; ++u) {
+            if (done || leave) break;
+            for (int gg = 0; gg < G; ++gg) {
+                const int k = base + u * G + gg;
+                if (k >= e_end) {
+                    done = true;
+                    break;
+                }
+                const int r = __shfl_sync(kFull, row[u], gg * nv);
+                if (r != cur_row) {
+                    if (cur_row >= 0 && lane < nv) {
+                        V o = acc;
+                        if (addend != nullptr) o = vadd(ld_stream(addend + (size_t)cur_row * add_stride + q), acc);
+                        st_stream(out + (size_t)cur_row * out_stride + q, o);
+                    }
+                    cur_row = -1;
+                    if (k >= e1) {           // the next cell belongs to a later warp
+                        done = true;
+                        break;
+                    }
+                    cur_row = r;
+                    run_len = 0;
+                    acc = vzero((V*)nullptr);
+                }
+                ++run_len;
+                if (heavy_len > 0 && run_len > heavy_len) {
+                    // a heavy cell: shpl_pool_heavy sums it; drop the partial sum and continue after the cell
+                    const int cell_end = __ldg(ptr + cur_row + 1);
+                    cur_row = -1;
+                    if (cell_end >= e1 || cell_end >= e_end) done = true;
+                    next_base = cell_end;
+                    leave = true;            // leave both loops; the products already gathered are dropped
+                    break;
+                }
+                acc = vadd(acc, vshfl(prod[u], gg * nv + q));
+            }
+        }
+        base = next_base;
+        if (base >= e_end) done = true;
+    }
+    if (cur_row >= 0 && lane < nv) {
+        V o = acc;
+        if (addend != nullptr) o = vadd(ld_stream(addend + (size_t)cur_row * add_stride + q), acc);
+        st_stream(out + (size_t)cur_row * out_stride + q, o);
+    }
+}
+
 // Entry-parallel gather: one warp takes `chunk` consecutive entries of the key-sorted entry list and
 // owns every cell whose FIRST entry lies in that chunk (a cell is never split, so its sum keeps the
 // ascending-k order; the warp reads on past the chunk until the cell ends, and skips leading entries
@@ -672,6 +777,8 @@ __global__ void __launch_bounds__(kThreads, SHPL_WIDE_MIN_CTAS) shpl_pool_wide_k
 // L2 (tools/probe/pattern_probe.cu).  Here the roles are split like in the wide kernel: ENTRY CTAs gather by entry
 // chunk and own the busy cells; STREAM CTAs copy the dense parts and write the zeros of the cells that receive
 // nothing, one dependent load (the tile's offsets) away from a bare copy.  Same sums in the same order.
+__host__ __device__ __forceinline__ bool packed_ok(const Job& jb) { return jb.vs_shift >= 0 && jb.vs <= 16 && jb.packed; }
+
 template <int W, bool kAdd, int ACC>
 __global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SHPL_SPARSE_MIN_CTAS_WIDE) shpl_pool_sparse_kernel(PoolArgs a) {
     using V = typename VecOf<W>::type;
@@ -686,13 +793,19 @@ __global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SH
         const int e_begin = __ldg(jb.ptr), e_end = __ldg(jb.ptr + jb.n_cells);
         const int e0 = e_begin + (b * kWarps + warp) * jb.entry_chunk;
         if (e0 >= e_end) return;
+        if (ACC == 1 && packed_ok(jb)) {      // few vectors per cell: lane groups gather different entries
+            pool_entries_packed<V>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.key, jb.idx, jb.val, e0,
+                                   min(e0 + jb.entry_chunk, e_end), e_begin, e_end, pout, jb.pool_out_stride,
+                                   kAdd ? din : nullptr, jb.dense_in_stride, jb.vs, jb.ptr, jb.long_len, lane);
+            return;
+        }
         // cells with more than kLongRow entries are left to the stream CTAs (whole-warp sum) or to shpl_pool_heavy:
         // the entry walk skips them exactly like it skips heavy cells
         // (with more than 32 vectors per cell there is no whole-warp path: the entry walk sums every length)
         pool_entries_wide<V, ACC, (ACC == 1 ? SHPL_SPARSE_GATHERS : SHPL_SPARSE_GATHERS_WIDE)>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.key, jb.idx, jb.val, e0,
                                 min(e0 + jb.entry_chunk, e_end), e_begin, e_end, pout, jb.pool_out_stride,
                                 kAdd ? din : nullptr, jb.dense_in_stride, jb.vs, jb.ptr,
-                                jb.vs <= 32 ? kLongRow : jb.heavy_len, lane);
+                                jb.vs <= 32 ? jb.long_len : jb.heavy_len, lane);
         return;
     }
     const int stream_ctas = jb.stream_ctas;
@@ -724,7 +837,7 @@ __global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SH
                 if (jb.heavy_len > 0 && hi - lo > jb.heavy_len) hi = lo;   // heavy cell: written as empty here
             }
             busy = __ballot_sync(kFull, hi > lo);                          // cells somebody else writes (entry CTAs) ...
-            longs = jb.vs <= 32 ? __ballot_sync(kFull, hi - lo > kLongRow) : 0u;   // ... or this warp sums as a whole, below
+            longs = jb.vs <= 32 ? __ballot_sync(kFull, hi - lo > jb.long_len) : 0u;   // ... or this warp sums as a whole, below
         }
         if (jb.vd > 0) {
             // concat form: the dense part of every cell; add form: a plain copy for the cells that receive nothing
@@ -781,7 +894,7 @@ __global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SH
         int len = 0;
         if (lane < rows) len = __ldg(jb.ptr + r0 + lane + 1) - __ldg(jb.ptr + r0 + lane);
         if (jb.heavy_len > 0 && len > jb.heavy_len) len = 0;
-        const unsigned longs = __ballot_sync(kFull, len > kLongRow);
+        const unsigned longs = __ballot_sync(kFull, len > jb.long_len);
         if (longs != 0u)
             long_cells<V, kAdd>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.ptr + r0, jb.idx, jb.val,
                                 pout + (size_t)r0 * jb.pool_out_stride, jb.pool_out_stride,
@@ -1007,6 +1120,24 @@ int entry_chunk_env() {      // entries per warp in the entry CTAs (experiment k
     return env;
 }
 
+int packed_env() {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("SHPL_PACKED");
+        env = e ? atoi(e) : 1;
+    }
+    return env;
+}
+
+int packed_chunk_env() {     // entries per warp with the packed entry walk
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("SHPL_PACKED_CHUNK");
+        env = (e && atoi(e) > 0) ? atoi(e) : 64;
+    }
+    return env;
+}
+
 int stream_ctas_per_sm() {
     static int env = -1;
     if (env < 0) {
@@ -1088,6 +1219,17 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
     if (a.n_jobs == 0) return SHPL_OK;
     bool wide = max_vs >= 32;
     bool stream_split = !wide && sparse_regime(a, src_spec);
+    bool packed = false;
+    if (!wide && !stream_split && packed_env()) {
+        // dense regime (many entries per cell on average): the entry + stream kernel with the PACKED entry walk, when
+        // every pooled job has its key array and a power-of-two number of vectors per cell <= 16
+        bool ok = true;
+        for (int i = 0; i < a.n_jobs; ++i) {
+            const Job& o = a.job[i];
+            if (o.vs > 0 && (o.key == nullptr || o.vs_shift < 0 || o.vs > 16)) ok = false;
+        }
+        stream_split = packed = ok;
+    }
     // Wide jobs take the entry + stream kernel too whenever their key arrays are there (measured on B200: full scan
     // C = 128 forward 218 -> 165 us, RetinaNet P2 24.0 -> 20.4 us, the bench step 142 -> 131 us); the CTA-tiled
     // shpl_pool_wide_kernel stays as the path without key arrays.
@@ -1145,6 +1287,9 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
             // entries per warp: 16 measured best for rows up to 1 KB (bench step 130 -> 123 us against 8; 24 gains 2 % more
             // there but hurts skewed maps); 3 KB rows (MV3D, C = 768) want the shorter chains of 8
             o.entry_chunk = entry_chunk_env() > 0 ? entry_chunk_env() : (o.vs * w > 256 ? 8 : 16);
+            o.packed = packed ? 1 : 0;
+            o.long_len = packed ? 512 : kLongRow;     // the packed walk hands a row over at ~60 cycles per entry: fine up to 512
+            if (packed && o.vs > 0) o.entry_chunk = packed_chunk_env();
             o.entry_ctas = o.vs > 0 ? (src_spec[i]->nnz_max + o.entry_chunk * kWarps - 1) / (o.entry_chunk * kWarps) : 0;
             a.begin[i + 1] = a.begin[i] + o.entry_ctas + o.stream_ctas;
         }
