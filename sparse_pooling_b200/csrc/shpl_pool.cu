@@ -15,14 +15,21 @@
 // directions' jobs in one launch, and the dual backward uses the add form so that no
 // intermediate gradient is materialised.
 //
-// Two kernel families, picked by the pooled width:
-//   narrow (vs < 32 vectors, C_s < 128): the work is a streaming copy with rare gathers (2 % of
-//     BEV cells are hit at KITTI stride 1).  A WARP owns a tile of <= 32 cells: 128-bit coalesced
-//     accesses, 8 independent loads in flight per lane, streaming cache hints, one lane per cell
-//     holds the CSR offsets and the tile's emptiness is one ballot.
-//   wide (vs >= 32): a WARP PER OUTPUT CELL, lanes own channel vectors.  Dense tiles of 32 cells
-//     are streamed by whole CTAs; the gathers are split BY ENTRY (chunks of the key-sorted entry
-//     list), not by cell, so crowded near-range cells of a stride-8 BEV map cannot serialise.
+// Kernels (dispatch in launch_jobs; DESIGN.md section 4.1 has the measurements behind every choice):
+//   shpl_pool_sparse_kernel<W, kAdd, ACC>  the entry + stream kernel, used whenever the key arrays are there:
+//       ENTRY CTAs walk the key-sorted entry list in chunks and own the busy cells (segmented sum, ascending k);
+//       STREAM CTAs (a warp per tile of <= 32 cells, 8 x 128-bit ld/st.global.cs in flight per lane) copy the dense
+//       parts and write the zeros of the cells that receive nothing -- one dependent load (the tile's CSR offsets,
+//       fetched one tile ahead) away from a bare copy.
+//         ACC = 1, few entries per cell (KITTI stride 1): plain entry walk, lanes = channel vectors
+//         ACC = 1, many entries per cell, power-of-two vectors per cell <= 16: PACKED entry walk (lane groups gather
+//                  different entries, products handed over one entry at a time)
+//         ACC = 2, wide channel counts (C_s >= 128): lanes own two channel vectors each
+//   shpl_pool_narrow_kernel<W, kAdd>       C_s < 128 without key arrays or with odd vector counts: gathers inside the
+//       streaming warp, cells with more than 32 entries summed by the whole warp
+//   shpl_pool_wide_kernel<W, ACC>          C_s >= 128 without key arrays: a warp per output cell, CTA-tiled dense copy
+//   shpl_pool_heavy_kernel<W, kGroups>     cells with more than SHPL_HEAVY_LEN entries: a thread-block cluster per cell,
+//       fixed summation tree over distributed shared memory
 // Sums run in stored (ascending k) order with separately rounded multiply and add, which makes
 // the result bit-identical to the sequential oracle.
 #include <cooperative_groups.h>
