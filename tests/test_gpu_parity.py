@@ -573,8 +573,10 @@ def test_heavy_cells_use_the_cluster_tree(shpl, dual):
         np.testing.assert_array_equal(got_b, want_b)
 
 
-def test_sparse_regime_with_a_heavy_cell(shpl):
-    """Few entries next to the cells (sparse-regime kernel) but 2600 of them in ONE BEV cell (> SHPL_HEAVY_LEN):
+@pytest.mark.parametrize("C", [32, 128])
+def test_sparse_regime_with_a_heavy_cell(shpl, C):
+    """(C = 32: narrow channel count, sparse regime; C = 128: the wide variant of the same kernel.)
+    Few entries next to the cells (sparse-regime kernel) but 2600 of them in ONE BEV cell (> SHPL_HEAVY_LEN):
     the entry CTAs skip the heavy cell, the stream CTAs write it as empty, shpl_pool_heavy fills it in.  Everything
     but the heavy cell is bit-exact; the heavy cell is within 1e-5 of the sum of |terms|."""
     rng = np.random.default_rng(21)
@@ -587,7 +589,6 @@ def test_sparse_regime_with_a_heavy_cell(shpl):
     d = dict(bv_index=np.stack((bx, bz), axis=1)[perm].astype(np.int64), img_index=np.stack((u, v, np.zeros(n)))[:, perm].astype(np.float64),
              bv_size=np.array([120, 110]), img_size=np.array([64, 32]))
     val = (1.0 / rng.integers(1, 46, n)).astype(np.float32)
-    C = 32
     bev = rng.standard_normal((1, 120, 110, C), dtype=np.float32)
     img = rng.standard_normal((1, 32, 64, C), dtype=np.float32)
     o = shpl.produce_sparse_pooling_input(d, M_val=val.astype(np.float64))
