@@ -638,3 +638,48 @@ def test_lazy_gen_dict_behaves_like_the_reference_dict(shpl, golden_dir):
     np.testing.assert_array_equal(o2["img_index_flip_pool"], ref_o2["img_index_flip_pool"])
     np.testing.assert_array_equal(d["img_index"], ref["img_index"])
     assert sorted(d.keys()) == ["bv_index", "bv_size", "img_index", "img_size"]
+
+
+def test_randomized_shapes_every_dispatch_path(shpl):
+    """Forty seeded random layers -- map sizes, channel counts (every vector width, odd counts, narrow and wide), pair
+    counts from empty to dense, uniform / ground-plane / Zipf row skew, single and dual direction, unit and 1/count
+    weights -- each forward + backward bit-exact against the plain-C oracle.  Sweeps the dispatch rules of
+    launch_jobs (entry + stream kernel in its three forms, narrow kernel, long-row paths) with shapes nobody hand-picked."""
+    rng = np.random.default_rng(20241018)
+    channels = [1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64, 100, 128, 160, 256]
+    for case in range(40):
+        bev_hw = (int(rng.integers(3, 48)), int(rng.integers(3, 56)))
+        img_hw = (int(rng.integers(3, 40)), int(rng.integers(3, 64)))
+        cb, ci = int(rng.choice(channels)), int(rng.choice(channels))
+        n = int(rng.choice([0, 1, 7, 60, 300, 1500, 4000]))
+        skew = str(rng.choice(["uniform", "ground", "zipf"]))
+        dual = bool(rng.integers(0, 2))
+        weights = bool(rng.integers(0, 2))
+        tag = "case %d: bev %s img %s C %dx%d n %d %s dual %s" % (case, bev_hw, img_hw, cb, ci, n, skew, dual)
+        d = synth.direct_pairs(1000 + case, max(n, 1), bev_hw=bev_hw, img_wh=(img_hw[1], img_hw[0]), skew=skew)
+        if n == 0:
+            d = dict(bv_index=d["bv_index"][:0], img_index=d["img_index"][:, :0], bv_size=d["bv_size"], img_size=d["img_size"])
+        o = io.produce_sparse_pooling_input({k: np.array(v, copy=True) for k, v in d.items()}, stride=[1, 1])
+        Mij, flip = o["Mij_pool"], o["img_index_flip_pool"]
+        nnz = len(Mij)
+        val = (1.0 / rng.integers(1, 46, nnz)).astype(np.float32) if weights else np.ones(nnz, np.float32)
+        bev = rng.standard_normal((1,) + bev_hw + (cb,), dtype=np.float32)
+        img = rng.standard_normal((1,) + img_hw + (ci,), dtype=np.float32)
+        M = shpl.SparseTensor(torch.from_numpy(Mij).cuda(), torch.from_numpy(val).cuda(), o["M_size"])
+        tb, ti = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
+        bv_fused, img_fused = shpl.sparse_pool_layer([tb, ti], [ci, cb], M, img_index_flip=torch.from_numpy(flip).cuda(),
+                                                     bv_index=(np.zeros((1, 3)) if dual else None))
+        np.testing.assert_array_equal(bv_fused[0].detach().cpu().numpy(), cref.forward(bev[0], img[0], Mij, val, flip), err_msg=tag)
+        g1 = rng.standard_normal(bev_hw + (cb + ci,), dtype=np.float32)
+        gd, gs = cref.backward(g1, Mij, val, flip, cb, img.shape[1:])
+        if dual:
+            np.testing.assert_array_equal(img_fused[0].detach().cpu().numpy(), cref.forward_trans(img[0], bev[0], Mij, val, flip), err_msg=tag)
+            g2 = rng.standard_normal(img_hw + (ci + cb,), dtype=np.float32)
+            torch.autograd.backward([bv_fused, img_fused], [torch.from_numpy(g1[None]).cuda(), torch.from_numpy(g2[None]).cuda()])
+            gi, gb = cref.backward_trans(g2, Mij, val, flip, ci, bev.shape[1:])
+            np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd + gb, err_msg=tag)
+            np.testing.assert_array_equal(ti.grad[0].cpu().numpy(), gi + gs, err_msg=tag)
+        else:
+            bv_fused.backward(torch.from_numpy(g1[None]).cuda())
+            np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd, err_msg=tag)
+            np.testing.assert_array_equal(ti.grad[0].cpu().numpy(), gs, err_msg=tag)
