@@ -683,3 +683,38 @@ def test_randomized_shapes_every_dispatch_path(shpl):
             bv_fused.backward(torch.from_numpy(g1[None]).cuda())
             np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd, err_msg=tag)
             np.testing.assert_array_equal(ti.grad[0].cpu().numpy(), gs, err_msg=tag)
+
+
+def test_randomized_builder_against_the_index_oracle(shpl):
+    """Thirty seeded random calls of produce_sparse_pooling_input -- map sizes, strides 1..8 on either side, pixel and
+    cell indices that leave the maps on both sides (MV3D's augment_fv does that, minibatch_mv3d_img.py:205-206), with
+    and without weights -- COO outputs, in-place mutation and the CSR / CSR^T plan against the numpy oracle, bit for bit."""
+    rng = np.random.default_rng(777)
+    for case in range(30):
+        im_w, im_h = int(rng.integers(16, 400)), int(rng.integers(8, 200))
+        bv_h, bv_w = int(rng.integers(8, 300)), int(rng.integers(8, 300))
+        s_img, s_bv = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+        n = int(rng.choice([0, 1, 5, 200, 3000]))
+        wild = bool(rng.integers(0, 2))                     # indices outside the maps
+        lo, hi = (-0.2, 1.3) if wild else (0.0, 1.0)
+        u = np.floor(rng.uniform(lo, hi, n) * im_w)
+        v = np.floor(rng.uniform(lo, hi, n) * im_h)
+        img_index = np.stack((u, v, np.zeros(n))).astype(np.float64)
+        bx = np.floor(rng.uniform(lo, hi, n) * bv_w).astype(np.int64)
+        bz = np.floor(rng.uniform(lo, hi, n) * bv_h).astype(np.int64)
+        d = dict(img_index=img_index, bv_index=np.stack((bx, bz), axis=1), bv_size=np.array([bv_h, bv_w]), img_size=np.array([im_w, im_h]))
+        d_ref = {k: np.array(vv, copy=True) for k, vv in d.items()}
+        o_ref = io.produce_sparse_pooling_input(d_ref, stride=[s_img, s_bv])
+        nnz = len(o_ref["Mij_pool"])
+        m_val = (1.0 / rng.integers(1, 46, nnz)) if (rng.integers(0, 2) and nnz) else None
+        tag = "case %d: img %dx%d bev %dx%d stride (%d,%d) n %d wild %s" % (case, im_w, im_h, bv_h, bv_w, s_img, s_bv, n, wild)
+        o = shpl.produce_sparse_pooling_input(d, M_val=m_val, stride=[s_img, s_bv])
+        for k in ("Mij_pool", "M_size", "img_index_flip_pool"):
+            np.testing.assert_array_equal(np.asarray(o[k]), o_ref[k], err_msg=tag + " " + k)
+        np.testing.assert_array_equal(d["img_index"], d_ref["img_index"], err_msg=tag + " in-place floor/clamp")
+        Hp, Wp = im_h // s_img, im_w // s_img
+        R = (bv_h // s_bv) * (bv_w // s_bv)
+        if R == 0 or Hp == 0 or Wp == 0:
+            continue
+        val = np.ones(nnz, np.float32) if m_val is None else m_val.astype(np.float32)
+        assert_plan_equals_oracle(o["shpl_plan"], o_ref["Mij_pool"], val, o_ref["img_index_flip_pool"], R, (Hp, Wp))
