@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SHPL_ABI_VERSION 5
+#define SHPL_ABI_VERSION 6
 
 /* Cells with more entries than this are "heavy": the builder lists them in the plan and their sum
  * is formed by shpl_pool_heavy (a thread-block cluster per cell, fixed summation tree) instead of
@@ -144,6 +144,22 @@ int shpl_plan_from_coo(const int64_t* Mij, const float* val, int64_t m,
                        int32_t src_h, int32_t src_w,
                        const shpl_plan* plan, int32_t row_base, int32_t pix_base, const int32_t* entry_base_dev,
                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Plan of the VFE scatter: tf.scatter_nd(coordinate, voxelwise, [B, 10, H, W, 128])
+ * (MV3D_TF_release/lib/networks/group_pointcloud.py:84-85; coordinate rows are
+ * (batch, d, h, w), built by build_input :88-105 from the feeder's coordinate_buffer).
+ *   coordinate [K,4] int32 (index_is_i64 = 0) or int64 (= 1), 16-byte aligned;
+ *   K_dev (device int32*, may be NULL): only the first min(K, *K_dev) rows exist
+ *   (the voxel count shpl_mv3d_voxelize leaves on the device).
+ * Row k of the feature matrix becomes the single entry (cell(coordinate[k]), k) with
+ * weight 1; plan->n_rows must equal batch*depth*height*width and plan->n_src >= K.
+ * The scatter itself is shpl_pool_forward with C_d = 0 on the CSR arrays (duplicate
+ * coordinates are summed in row order k, like TF-CPU), its gradient -- a gather of
+ * the grid gradient at the coordinates -- shpl_pool_backward on the CSR^T arrays.
+ * counts[1] = K, counts[2] = rows whose coordinate is outside the grid. */
+int shpl_plan_from_voxel_coords(const void* coordinate, int32_t index_is_i64, int64_t K, const int32_t* K_dev,
+                                int32_t batch, int32_t depth, int32_t height, int32_t width,
+                                const shpl_plan* plan, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Forward of one direction: _sparse_pool_op + tf.concat
  * (avod/avod/utils/sparse_pool_utils.py:96-103 with :67-72; for the reverse

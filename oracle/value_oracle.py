@@ -164,3 +164,34 @@ def sparse_pool_layer_grad(inputs, feature_depths, M, img_index_flip, bv_index, 
     if g_img_pool is not None:
         g_img = (g_img + g_img_pool).astype(F32)          # AddN of the direct path and the pooled path
     return g_bv, g_img
+
+
+# ------------------------------------------------------------- the VFE scatter
+def voxel_scatter(coordinate, voxelwise, shape, strict=True):
+    """tf.scatter_nd(coordinate, voxelwise, [B, 10, H, W, C])
+    (/root/reference/MV3D_TF_release/lib/networks/group_pointcloud.py:84-85): zeros, then
+    out[coordinate[k]] += voxelwise[k] in k order.  strict: TF-CPU's InvalidArgumentError for a coordinate
+    outside the grid; otherwise such rows are dropped (TF-GPU)."""
+    coordinate = np.asarray(coordinate, dtype=np.int64).reshape(-1, 4)
+    grid = np.array(shape[:4], dtype=np.int64)
+    C = int(shape[4])
+    out = np.zeros((int(np.prod(grid)), C), dtype=F32)
+    inside = ((coordinate >= 0) & (coordinate < grid)).all(axis=1)
+    if strict and not inside.all():
+        raise IndexError("scatter_nd: index out of range (TF-CPU: InvalidArgumentError)")
+    c = coordinate[inside]
+    lin = ((c[:, 0] * grid[1] + c[:, 1]) * grid[2] + c[:, 2]) * grid[3] + c[:, 3]
+    if lin.shape[0]:
+        segment_accumulate(out, lin, np.asarray(voxelwise, dtype=F32)[inside])
+    return out.reshape(tuple(int(g) for g in grid) + (C,))
+
+
+def voxel_scatter_grad(coordinate, g_out):
+    """Gradient of the scatter wrt voxelwise: gather_nd(g_out, coordinate); rows dropped by the forward get zeros."""
+    coordinate = np.asarray(coordinate, dtype=np.int64).reshape(-1, 4)
+    grid = np.array(g_out.shape[:4], dtype=np.int64)
+    inside = ((coordinate >= 0) & (coordinate < grid)).all(axis=1)
+    g = np.zeros((coordinate.shape[0], g_out.shape[4]), dtype=F32)
+    c = coordinate[inside]
+    g[inside] = g_out[c[:, 0], c[:, 1], c[:, 2], c[:, 3]]
+    return g

@@ -9,6 +9,7 @@ Layout (only what the hot path needs):
   builder.py           batched device-resident correspondence builder
   bev_slices.py        drop-in mirror of the BEV slicing feeder (BevSlices.generate_bev)
   construct_voxel.py   drop-in mirror of the MV3D voxel feeder (point_cloud_2_top_sparse)
+  group_pointcloud.py  the VFE scatter_nd into the dense voxel grid (FeatureNet's sparse half) + build_input
   lidar_ingest.py      drop-in mirror of the point-cloud ingest (get_lidar_point_cloud)
   config.py            the model.proto / kitti_dataset.proto sparse-pooling switches
   torch_op.py          the pooling kernels as registered PyTorch custom ops (torch.ops.shpl.pool) with autograd
@@ -23,5 +24,6 @@ from .sparse_pool_utils import (SparsePoolLayer, SparseTensor, _sparse_pool_op, 
 from .builder import build_avod_plan, build_pairs_plan  # noqa: F401
 from .bev_slices import BevSlices  # noqa: F401
 from . import construct_voxel  # noqa: F401
+from . import group_pointcloud  # noqa: F401
 from . import lidar_ingest  # noqa: F401
 from . import torch_op  # noqa: F401  (registers torch.ops.shpl.pool / pool_backward)

@@ -22,7 +22,7 @@ SHPL_ERR_CUDA = -2
 SHPL_ERR_WORKSPACE_TOO_SMALL = -3
 SHPL_ERR_UNSUPPORTED = -4
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 HEAVY_LEN = 2048          # SHPL_HEAVY_LEN of include/shpl.h
 
 
@@ -72,6 +72,8 @@ SIGNATURES = {
                                           c_int32, c_int32,
                                           ctypes.POINTER(ShplPlan), c_int32, c_int32, c_void_p,
                                           c_void_p, c_size_t, c_void_p]),
+    "shpl_plan_from_voxel_coords": (ctypes.c_int, [c_void_p, c_int32, c_int64, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                                   ctypes.POINTER(ShplPlan), c_void_p, c_size_t, c_void_p]),
     "shpl_pool_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "shpl_pool_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

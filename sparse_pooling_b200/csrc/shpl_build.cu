@@ -27,7 +27,7 @@
 namespace {
 using shpl::lookback;
 
-enum Mode { kModeAvod = 0, kModePairs = 1, kModeCoo = 2, kModeGenOnly = 3 };
+enum Mode { kModeAvod = 0, kModePairs = 1, kModeCoo = 2, kModeGenOnly = 3, kModeVoxel = 4 };
 
 struct PairsArgs {
     int mode;
@@ -47,6 +47,8 @@ struct PairsArgs {
     const void* src_index;
     int index_is_i64;
     long long ncol;
+    // kModeVoxel: src_index holds the [K,4] (batch, d, h, w) coordinates, index_is_i64 their width
+    int grid[4];                 // B, D, H, W of the dense voxel grid
     // common
     const double* m_val;
     int im_w, im_h;              // raw image size (clip)
@@ -124,6 +126,30 @@ __device__ __forceinline__ Cand eval_candidate(const PairsArgs& a, long long i, 
         const bool ok = (b == 0) && v >= 0 && v < a.src_h && u >= 0 && u < a.src_w;
         c.vp = ok ? (int)v : -1;
         c.up = ok ? (int)u : -1;
+        return c;
+    }
+    if (a.mode == kModeVoxel) {
+        // group_pointcloud.py:84-85: row k of the voxel-wise features lands in grid cell coordinate[k]
+        long long q[4];
+        if (a.index_is_i64) {
+            const longlong2* p = reinterpret_cast<const longlong2*>(static_cast<const long long*>(a.src_index) + 4 * i);
+            const longlong2 lo = p[0], hi = p[1];
+            q[0] = lo.x; q[1] = lo.y; q[2] = hi.x; q[3] = hi.y;
+        } else {
+            const int4 t = *reinterpret_cast<const int4*>(static_cast<const int*>(a.src_index) + 4 * i);
+            q[0] = t.x; q[1] = t.y; q[2] = t.z; q[3] = t.w;
+        }
+        bool in = true;
+        long long r = 0;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            in = in && q[d] >= 0 && q[d] < (long long)a.grid[d];
+            r = r * a.grid[d] + q[d];
+        }
+        c.clip = c.keep = true;
+        c.row = in ? r : -1;
+        c.vp = (int)i;       // the source "pixel" is the feature row itself
+        c.up = 0;
         return c;
     }
     double u, v;
@@ -572,4 +598,35 @@ extern "C" int shpl_plan_from_coo(const int64_t* Mij, const float* val, int64_t 
     pa.pix_base = pix_base;
     pa.counts = plan->counts;
     return run_build(pa, plan, entry_base_dev, workspace, workspace_bytes, stream, who);
+}
+
+extern "C" int shpl_plan_from_voxel_coords(const void* coordinate, int32_t index_is_i64, int64_t K, const int32_t* K_dev,
+                                           int32_t batch, int32_t depth, int32_t height, int32_t width,
+                                           const shpl_plan* plan, void* workspace, size_t workspace_bytes, void* stream) {
+    const char* who = "shpl_plan_from_voxel_coords";
+    SHPL_REQUIRE(plan && (K == 0 || coordinate), SHPL_ERR_INVALID_ARGUMENT, "%s: null pointer", who);
+    SHPL_REQUIRE(shpl::aligned(coordinate, 16), SHPL_ERR_INVALID_ARGUMENT, "%s: coordinate must be 16-byte aligned", who);
+    SHPL_REQUIRE(batch > 0 && depth > 0 && height > 0 && width > 0 &&
+                     (long long)batch * depth * height * width == plan->n_rows, SHPL_ERR_INVALID_ARGUMENT,
+                 "%s: plan.n_rows=%d but the grid is %d x %d x %d x %d", who, plan->n_rows, batch, depth, height, width);
+    SHPL_REQUIRE(plan->n_src >= K, SHPL_ERR_INVALID_ARGUMENT, "%s: plan.n_src=%d < %lld feature rows", who, plan->n_src,
+                 (long long)K);
+    PairsArgs pa{};
+    pa.mode = kModeVoxel;
+    pa.n = K;
+    pa.n_dev = K_dev;
+    pa.src_index = coordinate;
+    pa.index_is_i64 = index_is_i64;
+    pa.grid[0] = batch;
+    pa.grid[1] = depth;
+    pa.grid[2] = height;
+    pa.grid[3] = width;
+    pa.s_img = pa.s_bv = 1;
+    pa.Hb = 1;
+    pa.Wb = plan->n_rows;
+    pa.n_rows = plan->n_rows;
+    pa.src_h = plan->n_src;
+    pa.src_w = 1;
+    pa.counts = plan->counts;
+    return run_build(pa, plan, nullptr, workspace, workspace_bytes, stream, who);
 }

@@ -6,6 +6,7 @@ arithmetic happens in the CUDA kernels reached through the ctypes C ABI
 (``_cabi.py`` / ``include/shpl.h``).  Nothing here computes on the CPU.
 """
 import ctypes
+import threading
 
 import torch
 
@@ -45,6 +46,18 @@ def workspace(device, n_max):
     return ws
 
 
+_staging = threading.local()
+
+
+def _count_staging(n):
+    """(pinned int32 tensor, its numpy view) of at least n elements, one per host thread."""
+    st = getattr(_staging, "buf", None)
+    if st is None or st[0].shape[0] < n:
+        t = torch.empty(max(int(n), 64), dtype=torch.int32).pin_memory()
+        st = _staging.buf = (t, t.numpy())
+    return st
+
+
 class SparsePoolPlan:
     """Canonical CSR (by destination BEV cell) + CSR^T (by source pixel) of one M,
     or of the Ms of several frames stacked (struct shpl_plan of include/shpl.h).
@@ -55,7 +68,9 @@ class SparsePoolPlan:
 
     _INT_FIELDS = ("row_ptr", "pix_ptr", "csr_row", "csr_src", "csrT_pix", "csrT_dst", "heavy_row", "heavy_pix")
 
-    def __init__(self, rows_per_frame, src_hw, capacity, device, frames=1):
+    def __init__(self, rows_per_frame, src_hw, capacity, device, frames=1, zero_meta=True):
+        """zero_meta=False skips clearing the counters: for callers that run a builder on the plan at once (every
+        builder writes the counters of its frame, and the first frame's clears the heavy-cell counters)."""
         self.frames = int(frames)
         self.rows_per_frame = int(rows_per_frame)
         self.src_hw = (int(src_hw[0]), int(src_hw[1]))
@@ -86,7 +101,8 @@ class SparsePoolPlan:
         self._heavy_count_off = off + up(8 * self.frames)
         self._views = {}
         self._meta = self._ints[off:]
-        self._meta.zero_()
+        if zero_meta:
+            self._meta.zero_()
         self._vals = torch.empty(2 * up(cap), dtype=torch.float32, device=device)
         self._val_span = {"csr_val": (0, cap), "csrT_val": (up(cap), cap)}
         self._ibase = self._ints.data_ptr()
@@ -187,13 +203,17 @@ class SparsePoolPlan:
         return ctypes.c_void_p(self.addr("counts") + 32 * (f - 1) + 16)   # counts[f-1][4]
 
     def read_counts(self):
-        """One small device->host copy: fills nnz / n_oob (synchronises the stream)."""
-        m = self._meta.cpu()
-        c = m[:8 * self.frames].view(self.frames, 8)
-        self.nnz = [int(x) for x in c[:, 1]]
-        self.n_oob = [int(x) for x in c[:, 2]]
-        h = m[(8 * self.frames + 3) // 4 * 4:]
-        self.n_heavy = (min(int(h[0]), self.heavy_cap), min(int(h[1]), self.heavy_cap))
+        """One small device->host copy into pinned staging memory: fills nnz / n_oob / n_heavy (synchronises the
+        stream).  Returns the [frames, 8] counters as a numpy array."""
+        n = self._meta.shape[0]
+        stage = _count_staging(n)
+        stage[0][:n].copy_(self._meta)               # pinned destination: one async copy + a stream synchronise
+        m = stage[1][:n].copy()
+        c = m[:8 * self.frames].reshape(self.frames, 8)
+        self.nnz = c[:, 1].tolist()
+        self.n_oob = c[:, 2].tolist()
+        h = (8 * self.frames + 3) // 4 * 4
+        self.n_heavy = (min(int(m[h]), self.heavy_cap), min(int(m[h + 1]), self.heavy_cap))
         return c
 
     def heavy(self, by_pixel):

@@ -38,6 +38,11 @@ def _device():
 
 def _to_dev(a, dtype, device):
     if isinstance(a, torch.Tensor):
+        if not a.is_cuda and a.dtype == dtype and a.is_contiguous() and a.is_pinned():
+            # pinned host tensor: asynchronous upload, no stream synchronise.  Like torch's non_blocking=True the
+            # caller keeps the buffer unchanged until the next call that synchronises (produce_sparse_pooling_input
+            # reads the counters back, so: until it returns).
+            return a.to(device=device, non_blocking=True)
         return a.to(device=device, dtype=dtype).contiguous()
     arr = np.ascontiguousarray(np.asarray(a), dtype={torch.float64: np.float64, torch.int64: np.int64,
                                                      torch.float32: np.float32, torch.int32: np.int32}[dtype])
@@ -170,7 +175,7 @@ def gen_sparse_pooling_input_avod(points, voxel_indices, stereo_calib, im_size, 
     dev = points.device if (not as_numpy and points.is_cuda) else _device()
     pts = _to_dev(points, torch.float64, dev).reshape(-1, 3)
     vox = voxel_indices if isinstance(voxel_indices, torch.Tensor) else np.asarray(voxel_indices)
-    vox = _to_dev(vox[:, :2], torch.int64, dev)
+    vox = _to_dev(vox if vox.shape[1] == 2 else vox[:, :2], torch.int64, dev)
     P = np.ascontiguousarray(np.asarray(stereo_calib.p2, dtype=np.float64).reshape(12))
     _as_int(im_size[0], "im_size"), _as_int(im_size[1], "im_size")
     return SparsePoolingInput(pts, vox, P, im_size, bv_size, as_numpy, dev)
@@ -181,19 +186,31 @@ def _produce_outputs(plan, Mij, flip, R, M_val, n_mval, as_numpy, dev):
     nnz = plan.nnz[0]
     if M_val is not None and n_mval != nnz:
         raise ValueError("M_val has %d entries but M has %d columns (tf.SparseTensor would reject it)" % (n_mval, nnz))
-    plan.flip = flip[:nnz]
-    plan.Mij = Mij[:nnz]
+    plan.flip = out_flip = flip[:nnz]
+    plan.Mij = out_Mij = Mij[:nnz]
     M_size = np.array([R, nnz]).astype(int)
     if as_numpy:
-        out_Mij, out_flip = Mij[:nnz].cpu().numpy(), flip[:nnz].cpu().numpy()
+        out_Mij, out_flip = out_Mij.cpu().numpy(), out_flip.cpu().numpy()
         out_val = np.ones(nnz) if M_val is None else M_val
         bev_flip = np.zeros((0, 3))
     else:
-        out_Mij, out_flip = Mij[:nnz], flip[:nnz]
-        out_val = torch.ones(nnz, dtype=torch.float64, device=dev) if M_val is None else M_val
+        out_val = _ones(nnz, dev) if M_val is None else M_val
         bev_flip = torch.zeros((0, 3), device=dev)
     return {"Mij_pool": out_Mij, "M_val": out_val, "M_size": M_size, "img_index_flip_pool": out_flip,
             "bev_index_flip_pool": bev_flip, PLAN_KEY: plan}
+
+
+_ones_cache = {}
+
+
+def _ones(n, dev):
+    """np.ones(n) of the reference (:52) as a device tensor: a view of a cached block of ones (read-only by
+    convention -- the reference's M_val is a feed value nobody writes to), so no fill kernel runs per call."""
+    key = (dev.type, dev.index)
+    t = _ones_cache.get(key)
+    if t is None or t.shape[0] < n:
+        t = _ones_cache[key] = torch.ones(max(n, 1 << 16), dtype=torch.float64, device=dev)
+    return t[:n]
 
 
 def _mval_to_dev(M_val, n, dev):
@@ -223,7 +240,7 @@ def produce_sparse_pooling_input(input_dict, M_val=None, stride=[1, 1]):
         dev, pts, vox = input_dict._device, input_dict._pts, input_dict._vox
         N = int(pts.shape[0])
         mval_dev, n_mval = (None, 0) if M_val is None else _mval_to_dev(M_val, N, dev)
-        plan = SparsePoolPlan(R, (Hp, Wp), N, dev)
+        plan = SparsePoolPlan(R, (Hp, Wp), N, dev, zero_meta=False)
         plan.entry_bound = max(N, 1)
         cap = max(N, 1)
         Mij = torch.empty((cap, 2), dtype=torch.int64, device=dev)
@@ -250,7 +267,7 @@ def produce_sparse_pooling_input(input_dict, M_val=None, stride=[1, 1]):
         raise ValueError("bv_index has %d rows, img_index %d columns" % (bv.shape[0], n))
     mval_dev, n_mval = (None, 0) if M_val is None else _mval_to_dev(M_val, n, dev)
 
-    plan = SparsePoolPlan(R, (Hp, Wp), n, dev)
+    plan = SparsePoolPlan(R, (Hp, Wp), n, dev, zero_meta=False)
     plan.entry_bound = max(n, 1)
     cap = max(n, 1)
     Mij = torch.empty((cap, 2), dtype=torch.int64, device=dev)

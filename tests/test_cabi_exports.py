@@ -28,7 +28,7 @@ def lib():
 def test_header_declares_the_expected_entry_points():
     assert declared_functions() == sorted([
         "shpl_abi_version", "shpl_last_error", "shpl_kernel_launches", "shpl_build_workspace_bytes", "shpl_gen_input_avod",
-        "shpl_produce_input", "shpl_build_avod", "shpl_plan_from_coo", "shpl_pool_forward", "shpl_pool_backward",
+        "shpl_produce_input", "shpl_build_avod", "shpl_plan_from_coo", "shpl_plan_from_voxel_coords", "shpl_pool_forward", "shpl_pool_backward",
         "shpl_pool_forward_dual", "shpl_pool_backward_dual", "shpl_pool_heavy",
         "shpl_bev_grid_dims", "shpl_bev_workspace_bytes", "shpl_bev_slices",
         "shpl_mv3d_workspace_bytes", "shpl_mv3d_voxelize", "shpl_lidar_workspace_bytes", "shpl_lidar_to_cam"])
@@ -42,7 +42,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_binding_covers_the_header(lib):
     from sparse_pooling_b200 import _cabi
     assert sorted(_cabi.SIGNATURES) == declared_functions()
-    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 5
+    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 6
 
 
 def test_workspace_query_grows_with_n(lib):

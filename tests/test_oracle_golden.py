@@ -311,3 +311,28 @@ def test_ingest_oracle_matches_reference_get_lidar_point_cloud(golden_dir, seed,
     # the reference's min_intensity branch indexes the z-filtered cloud with an unfiltered intensity mask (obj_utils.py:266)
     with pytest.raises((ValueError, IndexError)):
         fo.get_lidar_point_cloud(scan, g["p2"], g["r0_rect"], g["tr_velodyne_to_cam"], im_size=list(g["im_size"]), min_intensity=0.5)
+
+
+def test_voxel_scatter_oracle_vs_torch_autograd():
+    """The VFE scatter oracle (tf.scatter_nd, group_pointcloud.py:84-85) against torch CPU: index_put_ with
+    accumulate adds duplicates in index order too, and autograd's gradient of it is the gather."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(3)
+    B, grid, C, K = 2, (3, 4, 5), 8, 300
+    coord = np.stack([rng.integers(0, B, K)] + [rng.integers(0, g, K) for g in grid], axis=1)
+    vw = rng.standard_normal((K, C)).astype(np.float32)
+    out = vo.voxel_scatter(coord, vw, (B, *grid, C))
+    x = torch.from_numpy(vw).requires_grad_(True)
+    ref = torch.zeros((B, *grid, C)).index_put(tuple(torch.from_numpy(coord[:, j]) for j in range(4)), x, accumulate=True)
+    np.testing.assert_allclose(out, ref.detach().numpy(), rtol=1e-6, atol=1e-6)
+    g = rng.standard_normal(out.shape).astype(np.float32)
+    ref.backward(torch.from_numpy(g))
+    np.testing.assert_array_equal(vo.voxel_scatter_grad(coord, g), x.grad.numpy())
+    # known answer: two rows on one cell, one row outside the grid
+    c = np.array([[0, 1, 2, 3], [0, 1, 2, 3], [0, 3, 0, 0]])
+    v = np.array([[1, 2, 3, 4], [10, 20, 30, 40], [5, 5, 5, 5]], dtype=np.float32)
+    with pytest.raises(IndexError):
+        vo.voxel_scatter(c, v, (1, *grid, 4))
+    o = vo.voxel_scatter(c, v, (1, *grid, 4), strict=False)
+    assert o[0, 1, 2, 3].tolist() == [11, 22, 33, 44] and o.sum() == 110
+    assert vo.voxel_scatter_grad(c, np.ones((1, *grid, 4), np.float32)).tolist() == [[1] * 4, [1] * 4, [0] * 4]

@@ -55,6 +55,43 @@ for _ in range(50):
     step()
 torch.cuda.synchronize()
 print("per step ms", (time.perf_counter() - t0) / 50 * 1e3)
+# host time per phase (perf_counter around each call; the syncs inside produce / the final read are part of their phase)
+ph = {}
+
+
+def timed(name, fn, *a, **k):
+    t = time.perf_counter()
+    r = fn(*a, **k)
+    ph[name] = ph.get(name, 0.0) + time.perf_counter() - t
+    return r
+
+
+def step_phases():
+    roots, grads = [], []
+    for (bev_hw, img_hw, C, stride, dual, bv), (bev, img, gb, gi) in zip(layers, maps):
+        d = timed("gen", shpl.gen_sparse_pooling_input_avod, pts, vox, Calib, [1200, 360], bv)
+        o = timed("produce", shpl.produce_sparse_pooling_input, d, stride=list(stride))
+        M = timed("SparseTensor", shpl.SparseTensor.from_sparse_pooling_input, o)
+        bev.grad = None
+        img.grad = None
+        a, b = timed("layer", shpl.sparse_pool_layer, [bev, img], [C, C], M, img_index_flip=o["img_index_flip_pool"],
+                     bv_index=(np.zeros((1, 3)) if dual else None))
+        roots += [a, b] if dual else [a]
+        grads += [gb, gi] if dual else [gb]
+    timed("backward", torch.autograd.backward, roots, grads)
+    return timed("read", lambda: float(maps[0][0].grad.reshape(-1)[0]))
+
+
+for _ in range(5):
+    step_phases()
+ph.clear()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(200):
+    step_phases()
+torch.cuda.synchronize()
+tot = (time.perf_counter() - t0) / 200 * 1e6
+print("phases, us per step (2 layers, one backward): total %.0f  " % tot + "  ".join("%s %.0f" % (k, v / 200 * 1e6) for k, v in ph.items()))
 pr = cProfile.Profile()
 pr.enable()
 for _ in range(50):
