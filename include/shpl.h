@@ -322,6 +322,33 @@ int shpl_lidar_to_cam(const float* velo_xyzi, int64_t N, const double* rectified
                       double* cam_out, int64_t capacity, int32_t* counts, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Augmentation hooks that touch the arrays the correspondence builder reads.
+ * Element-wise, in place, asynchronous; n_dev (device int32*, may be NULL) = device-side element count as above. */
+
+/* kitti_aug.flip_point_cloud (avod/avod/datasets/kitti/kitti_aug.py:24-29): x -> -x.
+ *   points: address of the first point's x; point_stride: doubles between consecutive points' x
+ *   (1 for the reference's [3,N] point cloud, 3 for an [N,3] array). */
+int shpl_flip_point_cloud(double* points, int64_t point_stride, int64_t n, const int32_t* n_dev, void* stream);
+
+/* MV3D sample preparation (MV3D_TF_release/lib/roi_data_layer/minibatch_mv3d_img.py):
+ *   img_index2 = np.round(projectToImage(lidar_pc[:, 0:3].T, P)).astype(int)   (:172-174, :183-185;
+ *   projectToImage = lib/utils/transform.py:429-452) into img_index2_out i64 [2,n] (NULL: not wanted), computed
+ *   from the points BEFORE the augmentation, then, when augment != 0, augment_voxel's point transforms (:176-181):
+ *   x += sx, z += sz; (x, y, z) *= expansion_ratio; (x, z) = rot_mat . (x, z) with rot_host f64 [4] =
+ *   [[cos a, sin a], [-sin a, cos a]] row-major as the host evaluated it.
+ *   lidar_pc f64 [n,4] (x, y, z, reflectance), camera frame, 16-byte aligned, transformed in place.
+ * The outputs are the (points, img_index2) inputs of shpl_mv3d_voxelize. */
+int shpl_mv3d_project_augment(double* lidar_pc, int64_t n, const int32_t* n_dev, const double* P_host,
+                              int32_t augment, double sx, double sz, double expansion_ratio,
+                              const double* rot_host, int64_t* img_index2_out, void* stream);
+
+/* augment_fv's index update (minibatch_mv3d_img.py:205-206):
+ *   img_index[0,:] = (img_index[0,:]*expansion_ratio + sx).astype(int), row 1 with sy (truncation toward zero).
+ *   img_index i64 [3, ld] row-major (ld >= n: row stride). */
+int shpl_augment_fv_index(int64_t* img_index, int64_t ld, int64_t n, const int32_t* n_dev,
+                          double expansion_ratio, double sx, double sy, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

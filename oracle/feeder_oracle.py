@@ -185,3 +185,42 @@ def get_lidar_point_cloud(velo_xyzi, p2, r0_rect, tr_velodyne_to_cam, im_size=No
         return pts[image_filter].T
     intensity_filter = i > min_intensity                                         # :266: `i` was NOT cut by z > 0 above
     return pts[np.logical_and(image_filter, intensity_filter)].T                 # raises when a point had z <= 0
+
+
+# ------------------------------------------------------------------ augmentation hooks
+def flip_point_cloud(point_cloud):
+    """/root/reference/avod/avod/datasets/kitti/kitti_aug.py:24-29."""
+    flipped = np.copy(point_cloud)
+    flipped[0] = -point_cloud[0]
+    return flipped
+
+
+def mv3d_project_round(lidar_pc, P):
+    """img_index2 of /root/reference/MV3D_TF_release/lib/roi_data_layer/minibatch_mv3d_img.py:172-174 (:183-185):
+    np.round(projectToImage(lidar_pc[:, 0:3].T, P)).astype(int), projectToImage = lib/utils/transform.py:429-452."""
+    pts = lidar_pc[:, 0:3].transpose()
+    mat = np.vstack((pts, np.ones((pts.shape[1]))))
+    uvw = np.dot(np.asarray(P, dtype=np.float64), mat)
+    uv = np.stack((uvw[0] / uvw[2], uvw[1] / uvw[2]))
+    with np.errstate(invalid="ignore"):
+        return np.round(uv).astype(int)
+
+
+def mv3d_augment_points(lidar_pc, sx, sz, expansion_ratio, rotation_angle):
+    """The point-cloud half of augment_voxel (minibatch_mv3d_img.py:148, :176-181), on a copy."""
+    pc = np.array(lidar_pc, dtype=np.float64)
+    rot_mat = np.array([[np.cos(rotation_angle), np.sin(rotation_angle)],
+                        [-np.sin(rotation_angle), np.cos(rotation_angle)]]).reshape(2, 2)
+    pc[:, 0] += sx
+    pc[:, 2] += sz
+    pc[:, 0:3] *= expansion_ratio
+    pc[:, [0, 2]] = np.dot(rot_mat, pc[:, [0, 2]].transpose()).transpose()
+    return pc
+
+
+def augment_fv_index(img_index, sx, sy, expansion_ratio):
+    """minibatch_mv3d_img.py:205-206, on a copy."""
+    out = np.array(img_index)
+    out[0, :] = (out[0, :] * expansion_ratio + sx).astype(int)
+    out[1, :] = (out[1, :] * expansion_ratio + sy).astype(int)
+    return out

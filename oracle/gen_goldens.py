@@ -249,7 +249,71 @@ def ingest_goldens():
         print("lidar ingest seed", seed, "points", len(scan), "in FOV", pc.shape[1])
 
 
+def _mv3d_minibatch_functions(names):
+    """The reference's minibatch_mv3d_img.py is Python 2 as a whole (print statements), but augment_voxel and
+    augment_fv themselves are version-neutral: their source is read where it lies and executed in a namespace that
+    holds what they use (numpy, cv2, cfg, and calib_to_P / projectToImage from the reference's lib/utils/transform.py)."""
+    import importlib.util
+    import cv2
+    lib = os.path.join(REF, "MV3D_TF_release", "lib")
+    spec = importlib.util.spec_from_file_location("mv3d_transform", lib + "/utils/transform.py")
+    tr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tr)
+    lines = open(lib + "/roi_data_layer/minibatch_mv3d_img.py").read().split("\n")
+    cfg = types.SimpleNamespace(PAD_IMAGE_TO=[1280, 384], TRAIN=types.SimpleNamespace(AUGMENT_PC=False))
+    # augment_fv hands cv2.resize a 1-element array as fx / fy, which the OpenCV of the reference's day accepted and
+    # 4.13 rejects: the shim converts the two factors to float and changes nothing else
+    cv2_shim = types.SimpleNamespace(resize=lambda img, dsize, fx, fy: cv2.resize(img, dsize, fx=float(np.ravel(fx)[0]),
+                                                                              fy=float(np.ravel(fy)[0])),
+                                     warpAffine=cv2.warpAffine)
+    ns = dict(np=np, cv2=cv2_shim, cfg=cfg, calib_to_P=tr.calib_to_P, projectToImage=tr.projectToImage)
+    for name in names:
+        i = [k for k, l in enumerate(lines) if l.startswith("def " + name + "(")][0]
+        j = i + 1
+        while j < len(lines) and not lines[j].startswith("def "):
+            j += 1
+        exec(compile("\n".join(lines[i:j]), name, "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def augment_goldens():
+    """The augmentation hooks of the reference run here: kitti_aug's flips (imported) and MV3D's augment_voxel /
+    augment_fv (executed from their source, see above) with np.random seeded."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("kitti_aug", os.path.join(REF, "avod/avod/datasets/kitti/kitti_aug.py"))
+    ka = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ka)
+    pts = synth.lidar_scan(1, az_step_deg=0.09).T                 # [3,N] camera frame
+    gp = np.array([0.01, -1.0, 0.02, 1.65])
+    rec = dict(flip_input_sha=digest(pts), flip_sha=digest(ka.flip_point_cloud(pts)), flip_head=ka.flip_point_cloud(pts)[:, :16],
+               flip_plane=ka.flip_ground_plane(gp), flip_p2=ka.flip_stereo_calib_p2(synth.P2_KITTI, (375, 1242)))
+    augment_voxel, augment_fv = _mv3d_minibatch_functions(["augment_voxel", "augment_fv"])
+    f = synth.mv3d_frame(seed=7, n_points=5000)
+    pc = synth.mv3d_cam4(f)
+    calib = np.zeros((4, 12))
+    calib[0] = synth.P2_KITTI.reshape(-1)
+    np.random.seed(1234)
+    blobs = dict(gt_boxes_3d=np.zeros((1, 7)), gt_rys=np.zeros((1, 1)))
+    _, pc_aug, img_index2 = augment_voxel(blobs, scale=0.8, lidar_pc=pc.copy(), calib=calib)
+    np.random.seed(1234)                                         # the draws augment_voxel made, in its order (:133-136)
+    sx, sz = np.random.uniform(-0.8, 0.8, 2)
+    ratio = np.random.uniform(0.95, 1.05, 1)
+    angle = np.random.uniform(-np.pi / 10, np.pi / 10, 1)
+    rec.update(voxel_input_sha=digest(pc), voxel_params=np.array([sx, sz, ratio[0], angle[0]]), voxel_pc_sha=digest(pc_aug),
+               voxel_pc_head=pc_aug[:16], voxel_img_index2=img_index2.astype(np.int32))
+    img_index = np.vstack((f["img_index2"], np.zeros((1, f["img_index2"].shape[1]), dtype=int)))
+    np.random.seed(99)
+    blobs = dict(image_data=np.zeros((375, 1242, 3), np.float32), gt_boxes=np.zeros((1, 5)), img_index=img_index.copy())
+    blobs, shift, fv_ratio = augment_fv(blobs, scale=10)
+    rec.update(fv_input_sha=digest(img_index), fv_params=np.array([shift[0], shift[1], fv_ratio[0]]),
+               fv_img_index=blobs["img_index"].astype(np.int32), fv_image_shape=np.array(blobs["image_data"].shape))
+    np.savez_compressed(os.path.join(OUT, "augment_hooks.npz"), **rec)
+    print("augment hooks: flip", pts.shape, "voxel params", rec["voxel_params"], "fv params", rec["fv_params"],
+          "fv image", rec["fv_image_shape"])
+
+
 if __name__ == "__main__":
     main()
     feeder_goldens()
     ingest_goldens()
+    augment_goldens()

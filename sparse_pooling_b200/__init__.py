@@ -11,6 +11,7 @@ Layout (only what the hot path needs):
   construct_voxel.py   drop-in mirror of the MV3D voxel feeder (point_cloud_2_top_sparse)
   group_pointcloud.py  the VFE scatter_nd into the dense voxel grid (FeatureNet's sparse half) + build_input
   lidar_ingest.py      drop-in mirror of the point-cloud ingest (get_lidar_point_cloud)
+  augment.py           augmentation hooks on the correspondence arrays (avod flip, MV3D augment_fv / augment_voxel points)
   config.py            the model.proto / kitti_dataset.proto sparse-pooling switches
   torch_op.py          the pooling kernels as registered PyTorch custom ops (torch.ops.shpl.pool) with autograd
 """
@@ -26,4 +27,5 @@ from .bev_slices import BevSlices  # noqa: F401
 from . import construct_voxel  # noqa: F401
 from . import group_pointcloud  # noqa: F401
 from . import lidar_ingest  # noqa: F401
+from . import augment  # noqa: F401
 from . import torch_op  # noqa: F401  (registers torch.ops.shpl.pool / pool_backward)

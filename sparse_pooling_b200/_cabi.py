@@ -92,6 +92,11 @@ SIGNATURES = {
     "shpl_lidar_workspace_bytes": (c_size_t, [c_int64]),
     "shpl_lidar_to_cam": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, ctypes.c_float,
                                          c_void_p, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "shpl_flip_point_cloud": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "shpl_mv3d_project_augment": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, ctypes.c_double, ctypes.c_double,
+                                                 ctypes.c_double, c_void_p, c_void_p, c_void_p]),
+    "shpl_augment_fv_index": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_void_p, ctypes.c_double, ctypes.c_double,
+                                             ctypes.c_double, c_void_p]),
     "shpl_pool_heavy": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p]),
 }

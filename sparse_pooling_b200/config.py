@@ -39,3 +39,8 @@ class KittiDatasetSparsePoolingConfig:
     def feat_stride(self):
         """kitti_dataset.py:375: 2 ** int(level[-1])."""
         return 2 ** int(self.use_pyramid_level_at_SHPL[-1])
+
+
+# MV3D: /root/reference/MV3D_TF_release/lib/fast_rcnn/config.py:229 -- images are padded to [W, H] before the image
+# network; augment_fv clips to it (minibatch_mv3d_img.py:200-203).
+PAD_IMAGE_TO = [1280, 384]

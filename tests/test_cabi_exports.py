@@ -31,7 +31,8 @@ def test_header_declares_the_expected_entry_points():
         "shpl_produce_input", "shpl_build_avod", "shpl_plan_from_coo", "shpl_plan_from_voxel_coords", "shpl_pool_forward", "shpl_pool_backward",
         "shpl_pool_forward_dual", "shpl_pool_backward_dual", "shpl_pool_heavy",
         "shpl_bev_grid_dims", "shpl_bev_workspace_bytes", "shpl_bev_slices",
-        "shpl_mv3d_workspace_bytes", "shpl_mv3d_voxelize", "shpl_lidar_workspace_bytes", "shpl_lidar_to_cam"])
+        "shpl_mv3d_workspace_bytes", "shpl_mv3d_voxelize", "shpl_lidar_workspace_bytes", "shpl_lidar_to_cam",
+        "shpl_flip_point_cloud", "shpl_mv3d_project_augment", "shpl_augment_fv_index"])
 
 
 def test_library_exports_every_declared_symbol(lib):

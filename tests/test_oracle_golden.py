@@ -336,3 +336,27 @@ def test_voxel_scatter_oracle_vs_torch_autograd():
     o = vo.voxel_scatter(c, v, (1, *grid, 4), strict=False)
     assert o[0, 1, 2, 3].tolist() == [11, 22, 33, 44] and o.sum() == 110
     assert vo.voxel_scatter_grad(c, np.ones((1, *grid, 4), np.float32)).tolist() == [[1] * 4, [1] * 4, [0] * 4]
+
+
+def test_augment_oracle_matches_reference_hooks(golden_dir):
+    """The augmentation-hook restatements against what the reference's own functions returned here
+    (oracle/gen_goldens.py augment_goldens: kitti_aug.flip_* imported, augment_voxel / augment_fv executed from source)."""
+    from oracle import feeder_oracle as fo
+    g = load(golden_dir, "augment_hooks.npz")
+    pts = synth.lidar_scan(1, az_step_deg=0.09).T
+    assert digest(pts) == str(g["flip_input_sha"])
+    fl = fo.flip_point_cloud(pts)
+    assert digest(fl) == str(g["flip_sha"])
+    np.testing.assert_array_equal(fl[:, :16], g["flip_head"])
+    f = synth.mv3d_frame(seed=7, n_points=5000)
+    pc = synth.mv3d_cam4(f)
+    assert digest(pc) == str(g["voxel_input_sha"])
+    sx, sz, ratio, angle = g["voxel_params"]
+    np.testing.assert_array_equal(fo.mv3d_project_round(pc, synth.P2_KITTI), g["voxel_img_index2"])
+    aug = fo.mv3d_augment_points(pc, sx, sz, np.array([ratio]), np.array([angle]))
+    assert digest(aug) == str(g["voxel_pc_sha"])
+    np.testing.assert_array_equal(aug[:16], g["voxel_pc_head"])
+    img_index = np.vstack((f["img_index2"], np.zeros((1, f["img_index2"].shape[1]), dtype=int)))
+    assert digest(img_index) == str(g["fv_input_sha"])
+    fsx, fsy, fratio = g["fv_params"]
+    np.testing.assert_array_equal(fo.augment_fv_index(img_index, fsx, fsy, np.array([fratio])), g["fv_img_index"])
