@@ -143,7 +143,7 @@ def test_car_grid_full_size_properties(shpl):
     got = out[coord[:, 0], coord[:, 1], coord[:, 2], coord[:, 3]]
     assert torch.equal(got, x.detach())                         # unique coordinates: the rows themselves
     assert int((out != 0).any(dim=-1).sum()) == K
-    assert float(out.double().sum()) == pytest.approx(float(x.detach().double().sum()), rel=1e-12, abs=1e-9)
+    assert float(out.detach().double().sum()) == pytest.approx(float(x.detach().double().sum()), rel=1e-12, abs=1e-9)
     g = torch.randn_like(out)
     out.backward(g)
     assert torch.equal(x.grad, g[coord[:, 0], coord[:, 1], coord[:, 2], coord[:, 3]])
