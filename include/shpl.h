@@ -27,12 +27,15 @@
 extern "C" {
 #endif
 
-#define SHPL_ABI_VERSION 6
+#define SHPL_ABI_VERSION 7
 
 /* Cells with more entries than this are "heavy": the builder lists them in the plan and their sum
- * is formed by shpl_pool_heavy (a thread-block cluster per cell, fixed summation tree) instead of
- * one warp walking the cell. */
-#define SHPL_HEAVY_LEN 2048
+ * is formed by shpl_pool_heavy (a thread-block cluster per cell) instead of one warp walking the cell.
+ * Listed cells of up to SHPL_EXACT_LEN entries are still summed in the reference's sequential order
+ * (bit-exact: the cluster gathers and multiplies in parallel, one warp per 32 channel vectors adds in
+ * entry order); longer ones by a fixed summation tree (deterministic, within 1e-5 of the sum of |terms|). */
+#define SHPL_HEAVY_LEN 512
+#define SHPL_EXACT_LEN 16384
 
 typedef enum shpl_status {
     SHPL_OK = 0,

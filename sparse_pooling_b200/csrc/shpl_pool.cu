@@ -928,6 +928,8 @@ struct HeavyArgs {
     int list_cap;
     int gather_stride, addend_stride, out_stride;   // in vectors
     int nv;                                          // vectors per cell
+    int exact_len;                                   // listed cells up to this many entries: exact kernel; longer: tree kernel
+    int eu;                                          // exact kernel: entries per warp per round
 };
 
 template <int W, bool kGroups>
@@ -948,6 +950,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
         const int cell = __ldg(a.list + h);
         const int beg = __ldg(a.ptr + cell), end = __ldg(a.ptr + cell + 1);
         const long long L = end - beg;
+        if (L <= a.exact_len) continue;                // summed in sequential order by shpl_pool_heavy_exact_kernel
         const int piece = crank * kWarps + warp;
         const int pb = beg + (int)(L * piece / (kClusterSize * kWarps));
         const int pe = beg + (int)(L * (piece + 1) / (kClusterSize * kWarps));
@@ -1041,6 +1044,90 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
             }
         }
         cluster.sync();      // the peers' shared memory stays valid until CTA 0 has read it
+    }
+}
+
+// Listed cells of up to SHPL_EXACT_LEN entries, in the REFERENCE'S order (bit-exact like the short cells): the
+// serial part of a sequential fp32 sum is only the chain of additions (4 cycles each); the gathers and the products
+// w*x are independent.  So the 64 warps of the cluster gather a round of entries in parallel and park the rounded
+// products in their CTA's shared memory; then the adder warps of CTA 0 (one per 32 channel vectors) walk the round in
+// entry order through distributed shared memory, adding product after product to the running sums.  A cell of 2048
+// entries takes ~10 us here against ~230 us for one warp gathering and adding in turn.
+template <int W>
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads) shpl_pool_heavy_exact_kernel(HeavyArgs a) {
+    using V = typename VecOf<W>::type;
+    extern __shared__ float4 heavy_smem[];
+    V* stage = reinterpret_cast<V*>(heavy_smem);        // [kWarps * eu][nv] products of this CTA's share of the round
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nv = a.nv, eu = a.eu;
+    const int E = nv >= 32 ? 1 : 32 / nv;               // entries one warp-wide load covers
+    const int sub = nv >= 32 ? 0 : lane / nv;           // which of them this lane works on
+    const int q0 = nv >= 32 ? lane : lane - sub * nv;   // first channel vector of this lane
+    const bool lane_on = sub < E;
+    const int U = eu / E;                               // warp-wide loads per round (eu is a multiple of E, eu <= 32)
+    const int per_cta = kWarps * eu, per_round = kClusterSize * per_cta;
+    const int n_clusters = gridDim.x / kClusterSize;
+    const int n_heavy = min(__ldg(a.count_dev), a.list_cap);
+    const V* src = static_cast<const V*>(a.gather_in);
+    const V* addend = static_cast<const V*>(a.addend);
+    V* out = static_cast<V*>(a.out);
+    const int aq = warp * 32 + lane;                    // adder warps: channel vector of this lane
+    const bool adder = crank == 0 && aq < nv;
+    constexpr int kG = 4;                               // warp-wide loads in flight
+    for (int h = blockIdx.x / kClusterSize; h < n_heavy; h += n_clusters) {
+        const int cell = __ldg(a.list + h);
+        const int beg = __ldg(a.ptr + cell), end = __ldg(a.ptr + cell + 1);
+        if (end - beg > a.exact_len) continue;          // the tree kernel's (the whole cluster agrees)
+        V acc = vzero((V*)nullptr);
+        for (int rb = beg; rb < end; rb += per_round) {
+            // ---- gather: warp (crank, warp) owns entries [wb, wb + eu) of the round
+            const int wb = rb + (crank * kWarps + warp) * eu;
+            int my_p = 0;
+            float my_w = 0.f;
+            if (lane < eu && wb + lane < end) {
+                my_p = __ldg(a.idx + wb + lane);
+                my_w = __ldg(a.val + wb + lane);
+            }
+            V* mine = stage + (size_t)warp * eu * nv;
+            for (int u0 = 0; u0 < U; u0 += kG) {
+#pragma unroll
+                for (int j = 0; j < kG; ++j) {
+                    const int slot = (u0 + j) * E + sub;
+                    const int p = __shfl_sync(kFull, my_p, slot & 31);
+                    const float w = __shfl_sync(kFull, my_w, slot & 31);
+                    if (lane_on && u0 + j < U && wb + slot < end) {
+                        const V* row = src + (size_t)p * a.gather_stride;
+                        for (int q = q0; q < nv; q += 32) mine[slot * nv + q] = vscale(w, __ldg(row + q));
+                    }
+                }
+            }
+            cluster.sync();
+            // ---- add: entry order = CTA rank, then warp, then slot
+            if (adder) {
+                const int n_round = min(per_round, end - rb);
+                for (int r = 0; r < kClusterSize; ++r) {
+                    const int cnt = min(per_cta, n_round - r * per_cta);
+                    if (cnt <= 0) break;
+                    const V* base = cluster.map_shared_rank(stage, r) + aq;
+                    for (int s0 = 0; s0 < cnt; s0 += 8) {
+                        V x[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (s0 + j < cnt) x[j] = base[(size_t)(s0 + j) * nv];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (s0 + j < cnt) acc = vadd(acc, x[j]);
+                    }
+                }
+            }
+            cluster.sync();      // the round's products have been consumed: the buffers may be refilled
+        }
+        if (adder) {
+            if (addend != nullptr) acc = vadd(addend[(size_t)cell * a.addend_stride + aq], acc);
+            out[(size_t)cell * a.out_stride + aq] = acc;
+        }
     }
 }
 
@@ -1510,6 +1597,29 @@ extern "C" int shpl_pool_heavy(const float* gather_in, int32_t gather_stride, in
     const int clusters = list_cap < 64 ? list_cap : 64;
     const unsigned grid = (unsigned)(clusters * kClusterSize);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // exact kernel: 8 adder warps cover 256 channel vectors; a round parks at most 32 KB of products per CTA
+    a.exact_len = a.nv <= kWarps * 32 ? SHPL_EXACT_LEN : 0;
+    if (a.exact_len > 0) {
+        const int E = a.nv >= 32 ? 1 : 32 / a.nv;
+        int eu = (int)((32 * 1024) / ((size_t)kWarps * C * sizeof(float)));
+        if (eu > 32) eu = 32;
+        eu = eu / E * E;
+        if (eu < E) eu = E;
+        a.eu = eu;
+        const size_t smem_x = (size_t)kWarps * eu * C * sizeof(float);
+        const int clusters_x = list_cap < 128 ? list_cap : 128;
+        const unsigned grid_x = (unsigned)(clusters_x * kClusterSize);
+        if (smem_x > 48 * 1024) {
+            if (w == 4) SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_pool_heavy_exact_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
+            else if (w == 2) SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_pool_heavy_exact_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
+            else SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_pool_heavy_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
+        }
+        if (w == 4) shpl_pool_heavy_exact_kernel<4><<<grid_x, kThreads, smem_x, s>>>(a);
+        else if (w == 2) shpl_pool_heavy_exact_kernel<2><<<grid_x, kThreads, smem_x, s>>>(a);
+        else shpl_pool_heavy_exact_kernel<1><<<grid_x, kThreads, smem_x, s>>>(a);
+        shpl::count_launches(1);
+        if (int rc = shpl::check_launch("shpl_pool_heavy_exact_kernel")) return rc;
+    }
     const bool groups = a.nv * 2 <= 32;       // few channels: lane groups over entries (see the kernel)
 #define SHPL_LAUNCH_HEAVY(WW, GG)                                                                                       \
     do {                                                                                                                \

@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_binding_covers_the_header(lib):
     from sparse_pooling_b200 import _cabi
     assert sorted(_cabi.SIGNATURES) == declared_functions()
-    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 6
+    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 7
 
 
 def test_workspace_query_grows_with_n(lib):

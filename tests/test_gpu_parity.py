@@ -441,12 +441,15 @@ def _long_cell_case(n, n_same_pixel, seed=12):
     return d, val, bev, img
 
 
-def test_long_cell_below_the_heavy_threshold_is_bit_exact(shpl):
-    """Every pair lands in one BEV cell (2048 entries = SHPL_HEAVY_LEN, the longest cell still summed
-    strictly sequentially) and 1k pairs share one pixel: identical to the sequential oracle."""
-    d, val, bev, img = _long_cell_case(2048, 1000)
+@pytest.mark.parametrize("n_cell,n_pix,listed", [(512, 300, (0, 0)), (513, 513, (1, 1)), (2048, 1000, (1, 1)), (16384, 9000, (1, 1))])
+def test_long_and_listed_cells_up_to_exact_len_are_bit_exact(shpl, n_cell, n_pix, listed):
+    """Every pair lands in one BEV cell and n_pix pairs share one pixel.  Up to SHPL_HEAVY_LEN = 512 entries the cell is
+    summed by one warp in the main kernel; above, the builder lists it and shpl_pool_heavy's exact kernel (a cluster
+    gathers and multiplies in parallel, the adds stay in entry order) forms the sum, up to SHPL_EXACT_LEN = 16384
+    entries: identical to the sequential oracle, bit for bit, on both sides of both thresholds."""
+    d, val, bev, img = _long_cell_case(n_cell, n_pix)
     o = shpl.produce_sparse_pooling_input(d)
-    assert o["shpl_plan"].n_heavy == (0, 0)
+    assert o["shpl_plan"].n_heavy == listed
     M = shpl.SparseTensor(torch.from_numpy(o["Mij_pool"]).cuda(), torch.from_numpy(val).cuda(), o["M_size"])
     tb, ti = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
     fused, _ = shpl.sparse_pool_layer([tb, ti], [32, 32], M, img_index_flip=torch.from_numpy(o["img_index_flip_pool"]).cuda())
@@ -464,7 +467,11 @@ def test_long_cell_below_the_heavy_threshold_is_bit_exact(shpl):
                                         # the same on a map with few entries per cell: the sparse-regime kernel, whose
                                         # stream warps take the long cells over from the entry CTAs
                                         (16, 920, (120, 110)), (4, 700, (120, 110)), (24, 100, (120, 110)), (100, 257, (120, 110)),
-                                        (6, 333, (120, 110))])
+                                        (6, 333, (120, 110)),
+                                        # listed cells (> 512 entries) through the exact cluster kernel: one / two / six
+                                        # adder warps, three lane groups (C = 36), and the sparse-regime map
+                                        (128, 1500, (16, 16)), (256, 700, (16, 16)), (768, 600, (16, 16)), (36, 800, (16, 16)),
+                                        (128, 1100, (120, 110)), (8, 5000, (16, 16))])
 def test_long_rows_are_summed_by_the_whole_warp_in_k_order(shpl, C, n, bev_hw):
     """Narrow kernels hand cells with more than 32 entries to the whole warp (lane groups gather in parallel,
     the adds stay in ascending k): bit-identical to the sequential oracle for every vector layout --
@@ -487,7 +494,9 @@ def test_long_rows_are_summed_by_the_whole_warp_in_k_order(shpl, C, n, bev_hw):
     img = rng.standard_normal((1, 32, 64, C), dtype=np.float32)
     o = shpl.produce_sparse_pooling_input(d)
     Mij, flip = o["Mij_pool"], o["img_index_flip_pool"]
-    assert np.bincount(Mij[:, 0]).max() >= n and o["shpl_plan"].n_heavy == (0, 0)
+    pixel = flip[:, 1] * 64 + flip[:, 2]
+    assert np.bincount(Mij[:, 0]).max() >= n
+    assert o["shpl_plan"].n_heavy == (int((np.bincount(Mij[:, 0]) > 512).sum()), int((np.bincount(pixel) > 512).sum()))
     M = shpl.SparseTensor(torch.from_numpy(Mij).cuda(), torch.from_numpy(val).cuda(), o["M_size"])
     tb, ti = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
     bv_fused, img_fused = shpl.sparse_pool_layer([tb, ti], [C, C], M, img_index_flip=torch.from_numpy(flip).cuda(),
@@ -607,8 +616,7 @@ def test_sparse_regime_with_a_heavy_cell(shpl, C):
     np.testing.assert_array_equal(got[heavy_row, :C], ref[heavy_row, :C])
     pix = flip[:, 1] * 64 + flip[:, 2]
     rows = Mij[:, 0]
-    scale = np.abs(val[rows == heavy_row, None] * img[0].reshape(-1, C)[pix[rows == heavy_row]]).sum(0).max()
-    assert np.abs(got[heavy_row, C:] - ref[heavy_row, C:]).max() <= 1e-5 * scale
+    np.testing.assert_array_equal(got[heavy_row, C:], ref[heavy_row, C:])      # 2600 <= SHPL_EXACT_LEN: sequential order kept
     g = rng.standard_normal((120, 110, 2 * C), dtype=np.float32)
     fused.backward(torch.from_numpy(g[None]).cuda())
     gd, gs = cref.backward(g, Mij, val, flip, C, (32, 64, C))
