@@ -33,9 +33,11 @@ extern "C" {
  * is formed by shpl_pool_heavy (a thread-block cluster per cell) instead of one warp walking the cell.
  * Listed cells of up to SHPL_EXACT_LEN entries are still summed in the reference's sequential order
  * (bit-exact: the cluster gathers and multiplies in parallel, one warp per 32 channel vectors adds in
- * entry order); longer ones by a fixed summation tree (deterministic, within 1e-5 of the sum of |terms|). */
+ * entry order); longer ones by a fixed summation tree (deterministic, within 1e-5 of the sum of |terms|).
+ * With 16 or fewer pooled channels the main kernels keep cells of up to 2048 entries themselves (one warp, 32
+ * gathers in flight, sequential order) whatever heavy_len > 0 they are given, and shpl_pool_heavy leaves those alone. */
 #define SHPL_HEAVY_LEN 512
-#define SHPL_EXACT_LEN 16384
+#define SHPL_EXACT_LEN 2048
 
 typedef enum shpl_status {
     SHPL_OK = 0,

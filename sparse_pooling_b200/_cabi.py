@@ -24,7 +24,7 @@ SHPL_ERR_UNSUPPORTED = -4
 
 ABI_VERSION = 7
 HEAVY_LEN = 512           # SHPL_HEAVY_LEN of include/shpl.h
-EXACT_LEN = 16384         # SHPL_EXACT_LEN: listed cells up to this many entries keep the sequential order
+EXACT_LEN = 2048          # SHPL_EXACT_LEN: listed cells up to this many entries keep the sequential order
 
 
 class ShplPlan(ctypes.Structure):

@@ -928,6 +928,7 @@ struct HeavyArgs {
     int list_cap;
     int gather_stride, addend_stride, out_stride;   // in vectors
     int nv;                                          // vectors per cell
+    int skip_le;                                     // listed cells up to this many entries were summed by the main kernel
     int exact_len;                                   // listed cells up to this many entries: exact kernel; longer: tree kernel
     int eu;                                          // exact kernel: entries per warp per round
 };
@@ -950,7 +951,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
         const int cell = __ldg(a.list + h);
         const int beg = __ldg(a.ptr + cell), end = __ldg(a.ptr + cell + 1);
         const long long L = end - beg;
-        if (L <= a.exact_len) continue;                // summed in sequential order by shpl_pool_heavy_exact_kernel
+        if (L <= a.exact_len || L <= a.skip_le) continue;   // the exact kernel's / the main kernel's
         const int piece = crank * kWarps + warp;
         const int pb = beg + (int)(L * piece / (kClusterSize * kWarps));
         const int pe = beg + (int)(L * (piece + 1) / (kClusterSize * kWarps));
@@ -1050,16 +1051,17 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
 // Listed cells of up to SHPL_EXACT_LEN entries, in the REFERENCE'S order (bit-exact like the short cells): the
 // serial part of a sequential fp32 sum is only the chain of additions (4 cycles each); the gathers and the products
 // w*x are independent.  So the 64 warps of the cluster gather a round of entries in parallel and park the rounded
-// products in their CTA's shared memory; then the adder warps of CTA 0 (one per 32 channel vectors) walk the round in
-// entry order through distributed shared memory, adding product after product to the running sums.  A cell of 2048
-// entries takes ~10 us here against ~230 us for one warp gathering and adding in turn.
+// products, in entry order, in the shared memory of CTA 0 (remote stores through distributed shared memory: fire and
+// forget, no latency on anybody's critical path); then the adder warps of CTA 0 (one per 32 channel vectors) walk the
+// round out of their own shared memory, adding product after product to the running sums.
 template <int W>
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads) shpl_pool_heavy_exact_kernel(HeavyArgs a) {
     using V = typename VecOf<W>::type;
     extern __shared__ float4 heavy_smem[];
-    V* stage = reinterpret_cast<V*>(heavy_smem);        // [kWarps * eu][nv] products of this CTA's share of the round
+    V* stage = reinterpret_cast<V*>(heavy_smem);        // CTA 0's copy: [kClusterSize * kWarps * eu][nv] products of a round
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
+    V* stage0 = cluster.map_shared_rank(stage, 0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nv = a.nv, eu = a.eu;
     const int E = nv >= 32 ? 1 : 32 / nv;               // entries one warp-wide load covers
@@ -1067,7 +1069,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
     const int q0 = nv >= 32 ? lane : lane - sub * nv;   // first channel vector of this lane
     const bool lane_on = sub < E;
     const int U = eu / E;                               // warp-wide loads per round (eu is a multiple of E, eu <= 32)
-    const int per_cta = kWarps * eu, per_round = kClusterSize * per_cta;
+    const int per_round = kClusterSize * kWarps * eu;
     const int n_clusters = gridDim.x / kClusterSize;
     const int n_heavy = min(__ldg(a.count_dev), a.list_cap);
     const V* src = static_cast<const V*>(a.gather_in);
@@ -1076,21 +1078,23 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
     const int aq = warp * 32 + lane;                    // adder warps: channel vector of this lane
     const bool adder = crank == 0 && aq < nv;
     constexpr int kG = 4;                               // warp-wide loads in flight
+    constexpr int kA = 8;                               // products an adder lane fetches ahead of its additions
     for (int h = blockIdx.x / kClusterSize; h < n_heavy; h += n_clusters) {
         const int cell = __ldg(a.list + h);
         const int beg = __ldg(a.ptr + cell), end = __ldg(a.ptr + cell + 1);
-        if (end - beg > a.exact_len) continue;          // the tree kernel's (the whole cluster agrees)
+        if (end - beg > a.exact_len || end - beg <= a.skip_le) continue;   // the tree kernel's / the main kernel's (the whole cluster agrees)
         V acc = vzero((V*)nullptr);
         for (int rb = beg; rb < end; rb += per_round) {
             // ---- gather: warp (crank, warp) owns entries [wb, wb + eu) of the round
-            const int wb = rb + (crank * kWarps + warp) * eu;
+            const int w_first = (crank * kWarps + warp) * eu;
+            const int wb = rb + w_first;
             int my_p = 0;
             float my_w = 0.f;
             if (lane < eu && wb + lane < end) {
                 my_p = __ldg(a.idx + wb + lane);
                 my_w = __ldg(a.val + wb + lane);
             }
-            V* mine = stage + (size_t)warp * eu * nv;
+            V* mine = stage0 + (size_t)w_first * nv;
             for (int u0 = 0; u0 < U; u0 += kG) {
 #pragma unroll
                 for (int j = 0; j < kG; ++j) {
@@ -1104,25 +1108,32 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
                 }
             }
             cluster.sync();
-            // ---- add: entry order = CTA rank, then warp, then slot
+            // ---- add, in entry order, out of CTA 0's own shared memory
             if (adder) {
                 const int n_round = min(per_round, end - rb);
-                for (int r = 0; r < kClusterSize; ++r) {
-                    const int cnt = min(per_cta, n_round - r * per_cta);
-                    if (cnt <= 0) break;
-                    const V* base = cluster.map_shared_rank(stage, r) + aq;
-                    for (int s0 = 0; s0 < cnt; s0 += 8) {
-                        V x[8];
+                const V* base = stage + aq;
+                int s0 = 0;
+                if (n_round >= kA) {
+                    // full batches, no predicates on the chain: batch b+1 is fetched while batch b is added
+                    V x[kA];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (s0 + j < cnt) x[j] = base[(size_t)(s0 + j) * nv];
+                    for (int j = 0; j < kA; ++j) x[j] = base[(size_t)j * nv];
+                    for (; s0 + 2 * kA <= n_round; s0 += kA) {
+                        V y[kA];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (s0 + j < cnt) acc = vadd(acc, x[j]);
+                        for (int j = 0; j < kA; ++j) y[j] = base[(size_t)(s0 + kA + j) * nv];
+#pragma unroll
+                        for (int j = 0; j < kA; ++j) acc = vadd(acc, x[j]);
+#pragma unroll
+                        for (int j = 0; j < kA; ++j) x[j] = y[j];
                     }
+#pragma unroll
+                    for (int j = 0; j < kA; ++j) acc = vadd(acc, x[j]);
+                    s0 += kA;
                 }
+                for (; s0 < n_round; ++s0) acc = vadd(acc, base[(size_t)s0 * nv]);
             }
-            cluster.sync();      // the round's products have been consumed: the buffers may be refilled
+            cluster.sync();      // the round's products have been consumed: the buffer may be refilled
         }
         if (adder) {
             if (addend != nullptr) acc = vadd(addend[(size_t)cell * a.addend_stride + aq], acc);
@@ -1132,6 +1143,14 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
 }
 
 // --------------------------------------------------------------------------------------- host
+// Narrow channel counts (C <= 16) keep listed cells of up to 2048 entries in the main kernels: the whole-warp walk has
+// 32 gathers of such a cell in flight there and many long cells run side by side, which beats one cluster per cell
+// (measured, Zipf stress rows: 261 us against 312 us at 1 M pairs).  shpl_pool_heavy applies the same rule from its C.
+constexpr int kNarrowKeep = 2048;
+int main_kernel_heavy_len(int heavy_len, int c_pool) {
+    return heavy_len > 0 && c_pool <= 16 && heavy_len < kNarrowKeep ? kNarrowKeep : heavy_len;
+}
+
 int log2_or_neg(int v) {
     if (v <= 0 || (v & (v - 1))) return -1;
     int s = 0;
@@ -1307,7 +1326,7 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
         o.vs_shift = log2_or_neg(o.vs);
         o.n_cells = j.n_cells;
         o.add = j.add;
-        o.heavy_len = j.heavy_len;
+        o.heavy_len = main_kernel_heavy_len(j.heavy_len, j.c_pool);
         max_vs = o.vs > max_vs ? o.vs : max_vs;
     }
     if (a.n_jobs == 0) return SHPL_OK;
@@ -1597,16 +1616,18 @@ extern "C" int shpl_pool_heavy(const float* gather_in, int32_t gather_stride, in
     const int clusters = list_cap < 64 ? list_cap : 64;
     const unsigned grid = (unsigned)(clusters * kClusterSize);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    // exact kernel: 8 adder warps cover 256 channel vectors; a round parks at most 32 KB of products per CTA
-    a.exact_len = a.nv <= kWarps * 32 ? SHPL_EXACT_LEN : 0;
-    if (a.exact_len > 0) {
+    // exact kernel: 8 adder warps cover 256 channel vectors; a round of products (64 warps x eu entries) is parked in
+    // CTA 0's shared memory: up to 128 KB of it, 196 KB when one entry per warp already needs that much (C = 768)
+    a.exact_len = a.nv <= kWarps * 32 && (size_t)kClusterSize * kWarps * C * sizeof(float) <= 200 * 1024 ? SHPL_EXACT_LEN : 0;
+    a.skip_le = main_kernel_heavy_len(SHPL_HEAVY_LEN, C) > SHPL_HEAVY_LEN ? main_kernel_heavy_len(SHPL_HEAVY_LEN, C) : 0;
+    if (a.exact_len > a.skip_le) {
         const int E = a.nv >= 32 ? 1 : 32 / a.nv;
-        int eu = (int)((32 * 1024) / ((size_t)kWarps * C * sizeof(float)));
+        int eu = (int)((128 * 1024) / ((size_t)kClusterSize * kWarps * C * sizeof(float)));
         if (eu > 32) eu = 32;
         eu = eu / E * E;
         if (eu < E) eu = E;
         a.eu = eu;
-        const size_t smem_x = (size_t)kWarps * eu * C * sizeof(float);
+        const size_t smem_x = (size_t)kClusterSize * kWarps * eu * C * sizeof(float);
         const int clusters_x = list_cap < 128 ? list_cap : 128;
         const unsigned grid_x = (unsigned)(clusters_x * kClusterSize);
         if (smem_x > 48 * 1024) {
