@@ -28,8 +28,10 @@
 //   shpl_pool_narrow_kernel<W, kAdd>       C_s < 128 without key arrays or with odd vector counts: gathers inside the
 //       streaming warp, cells with more than 32 entries summed by the whole warp
 //   shpl_pool_wide_kernel<W, ACC>          C_s >= 128 without key arrays: a warp per output cell, CTA-tiled dense copy
-//   shpl_pool_heavy_kernel<W, kGroups>     cells with more than SHPL_HEAVY_LEN entries: a thread-block cluster per cell,
-//       fixed summation tree over distributed shared memory
+//   shpl_pool_heavy_exact_kernel<W>        listed cells (more than SHPL_HEAVY_LEN entries) up to SHPL_EXACT_LEN: a thread-block
+//       cluster per cell gathers and multiplies in parallel, adder warps add in entry order (sequential sum, bit-exact)
+//   shpl_pool_heavy_kernel<W, kGroups>     longer listed cells: a cluster per cell, fixed summation tree over distributed
+//       shared memory
 // Sums run in stored (ascending k) order with separately rounded multiply and add, which makes
 // the result bit-identical to the sequential oracle.
 #include <cooperative_groups.h>
