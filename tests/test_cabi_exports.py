@@ -92,6 +92,20 @@ def test_feeder_host_side_queries_and_argument_checks(lib):
     assert rc == _cabi.SHPL_ERR_INVALID_ARGUMENT
     rc = L.shpl_lidar_to_cam(None, 5, None, None, 0, 0, 0, 0.0, None, 0, None, None, 0, None)
     assert rc == _cabi.SHPL_ERR_INVALID_ARGUMENT
+    # the VFE scatter plan and the augmentation hooks: argument checks in front of any launch
+    st = _cabi.ShplPlan()
+    st.n_rows, st.n_src = 10 * 20 * 24, 100
+    rc = L.shpl_plan_from_voxel_coords(None, 1, 5, None, 1, 10, 20, 24, ctypes.byref(st), None, 0, None)
+    assert rc == _cabi.SHPL_ERR_INVALID_ARGUMENT and b"null pointer" in L.shpl_last_error()
+    rc = L.shpl_plan_from_voxel_coords(None, 1, 0, None, 1, 10, 20, 25, ctypes.byref(st), None, 0, None)
+    assert rc == _cabi.SHPL_ERR_INVALID_ARGUMENT and b"grid" in L.shpl_last_error()
+    assert L.shpl_flip_point_cloud(None, 1, 0, None, None) == 0                       # nothing to do, nothing launched
+    assert L.shpl_flip_point_cloud(None, 1, 5, None, None) == _cabi.SHPL_ERR_INVALID_ARGUMENT
+    assert L.shpl_flip_point_cloud(None, 0, 5, None, None) == _cabi.SHPL_ERR_INVALID_ARGUMENT
+    assert L.shpl_mv3d_project_augment(None, 5, None, None, 0, 0.0, 0.0, 1.0, None, None, None) == _cabi.SHPL_ERR_INVALID_ARGUMENT
+    assert L.shpl_mv3d_project_augment(None, 0, None, None, 0, 0.0, 0.0, 1.0, None, None, None) == 0
+    assert L.shpl_augment_fv_index(None, 3, 5, None, 1.0, 0.0, 0.0, None) == _cabi.SHPL_ERR_INVALID_ARGUMENT    # ld < n
+    assert L.shpl_augment_fv_index(None, 8, 0, None, 1.0, 0.0, 0.0, None) == 0
 
 
 def test_product_package_does_not_import_the_oracle():
