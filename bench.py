@@ -867,6 +867,84 @@ def run_gpu(args):
             t = torch.tensor([dt_velo], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt_velo = float(t.item())
+        # ---- the same chain as the headline e2e leg runs it: captured in CUDA graphs (upload of the raw scan, ingest,
+        #      feeder, builds, pooling, D2H), launched on alternating streams with every buffer of the chain doubled,
+        #      each step's result read on the host one step later
+        velo_graph = None
+        try:
+            vsets = []
+            for b in range(2):
+                vsets.append(dict(stage=torch.empty((v_max, 4), dtype=torch.float32, device=dev),
+                                  cam=torch.empty((3, v_max), dtype=torch.float64, device=dev),
+                                  cnt=torch.zeros(4, dtype=torch.int32, device=dev),
+                                  work=bs.BevWorkspace(synth.AVOD_EXTENTS, synth.AVOD_VOXEL, 5, N_MAX, dev, with_maps=True),
+                                  ws=torch.empty(int(_cabi.lib.shpl_lidar_workspace_bytes(int(v_max))) + 64, dtype=torch.uint8, device=dev)))
+
+            def velo_enqueue(k):
+                fi, si, b = k % N_FRAMES, k % n_sets, k % 2
+                pipe, mp, vs = pipes[si], maps[si], vsets[b]
+                nv = velos[fi].shape[0]
+                vs["stage"][:nv].copy_(velo_pin[fi], non_blocking=True)
+                main = torch.cuda.current_stream()
+                ms = main.cuda_stream
+                li.lidar_to_cam_raw(vs["stage"], nv, cal, [1242, 375], vs["cam"], vs["cnt"], ws=vs["ws"])
+                bs.bev_slices_raw(vs["cam"], vs["cam"].stride(0), vs["cam"].stride(1), nv, GP, synth.AVOD_EXTENTS, synth.AVOD_VOXEL,
+                                  -0.2, 2.3, 5, np.log(16), vs["work"], lut=lut, p_dev=ctypes.c_void_p(vs["cnt"].data_ptr()))
+                nd = ctypes.c_void_p(vs["work"].counts.data_ptr())
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    ss = side.cuda_stream
+                    pipe.build_layer(0, vs["work"].unique_pts, vs["work"].voxel_indices, P, N_MAX, ss, n_dev=nd)
+                    pipe.forward_layer(0, mp[0]["bev"], mp[0]["img"], ss, N_MAX)
+                    pipe.backward_layer(0, mp[0]["g_bev"], mp[0]["g_img"], ss, N_MAX)
+                pipe.build_layer(1, vs["work"].unique_pts, vs["work"].voxel_indices, P, N_MAX, ms, n_dev=nd)
+                pipe.forward_layer(1, mp[1]["bev"], mp[1]["img"], ms, N_MAX)
+                pipe.backward_layer(1, mp[1]["g_bev"], mp[1]["g_img"], ms, N_MAX)
+                main.wait_stream(side)
+                torch.cat(res_views[si], out=res_dev2[b])
+                res_pin2[b].copy_(res_dev2[b], non_blocking=True)
+
+            for k in range(n_combo):
+                velo_enqueue(k)
+            torch.cuda.synchronize()
+            vgraphs = []
+            for k in range(n_combo):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    velo_enqueue(k)
+                vgraphs.append(gr)
+
+            def velo_step_graph(k, last=False):
+                with torch.cuda.stream(lanes[k % 2]):
+                    vgraphs[k % n_combo].replay()
+                    read_results(k, last)
+
+            for k in range(4):
+                velo_step_graph(k, last=(k == 3))
+            torch.cuda.synchronize()
+            vg_counts = [int(x) for x in res_pin2[0][-16:].tolist()][:4]        # step k = 2: the frame the eager check read
+            barrier()
+            seen.clear()
+            t0 = time.perf_counter()
+            for k in range(K_fast):
+                velo_step_graph(k, last=(k == K_fast - 1))
+            torch.cuda.synchronize()
+            dt_vg = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt_vg], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt_vg = float(t.item())
+            assert len(seen) == K_fast + 1 and all(x > 0 for x in seen[1:]), "velodyne graph leg: a result was not read back"
+            assert vg_counts == velo_counts[:4], "velodyne graph leg: plan counters differ from the eager chain's"
+            velo_graph = {"value": world * K_fast / dt_vg, "unit": UNIT, "steps": K_fast,
+                          "h2d_bytes_per_step": int(velos[0].shape[0] * 16), "d2h_bytes_per_step": int(res_pin2[0].numel() * 4),
+                          "what": "the velodyne chain captured in CUDA graphs (upload of the raw scan, ingest, feeder, both plans, "
+                                  "forward + backward, D2H), one graph launch per step on alternating streams with every buffer "
+                                  "doubled, every step's result read on the host one step later"}
+        except Exception as ex:  # pragma: no cover
+            print("velodyne graph leg failed: %r" % (ex,), file=sys.stderr)
+            torch.cuda.synchronize()
+
         feeder = {"what": "BevSlices.generate_bev(output_indices=True) on the GPU: 5 height maps + density map [6,700,800] f64, "
                           "voxel_indices, unique_pts (shpl_bev_slices, CUDA-graph replays, CUDA events)",
                   "us_per_frame": feeder_us, "points_per_scan": [int(sc.shape[1]) for sc in scans],
@@ -883,7 +961,8 @@ def run_gpu(args):
                                         "what": "raw 360-degree velodyne scan float32 [N,4] from pinned host memory, ingest (camera "
                                                 "frame, FOV filter), feeder, both plans, forward+backward of both layers, read-back; "
                                                 "all intermediate counts stay on the device",
-                                        "counts_check(nclip,nnz,oob,csr,fov_points,pairs)": velo_counts}}
+                                        "counts_check(nclip,nnz,oob,csr,fov_points,pairs)": velo_counts},
+                  "e2e_from_velodyne_graph": velo_graph}
     except Exception as ex:  # pragma: no cover
         print("feeder leg failed: %r" % (ex,), file=sys.stderr)
         torch.cuda.synchronize()

@@ -75,14 +75,17 @@ def _workspace(device, n):
     return ws
 
 
-def lidar_to_cam_raw(velo, n, frame_calib, im_size, out, counts, min_intensity=None, stream=None):
-    """One asynchronous shpl_lidar_to_cam call: velo f32 [N,4] CUDA (contiguous), out f64 [3,cap] CUDA, counts i32 [4]."""
+def lidar_to_cam_raw(velo, n, frame_calib, im_size, out, counts, min_intensity=None, stream=None, ws=None):
+    """One asynchronous shpl_lidar_to_cam call: velo f32 [N,4] CUDA (contiguous), out f64 [3,cap] CUDA, counts i32 [4].
+    ws: scratch of shpl_lidar_workspace_bytes(n) bytes; by default the per-device one, which calls in flight on
+    different streams must not share."""
     if not velo.is_contiguous() or velo.dtype != torch.float32:
         raise ValueError("lidar_to_cam_raw: the scan must be a contiguous float32 [N,4] CUDA tensor")
     R = np.ascontiguousarray(rectified_matrix(frame_calib)[0:3].reshape(12))
     P = np.ascontiguousarray(np.asarray(frame_calib.p2, dtype=np.float64).reshape(12))
     w, h = (int(im_size[0]), int(im_size[1])) if im_size else (0, 0)
-    ws = _workspace(velo.device, n)
+    if ws is None:
+        ws = _workspace(velo.device, n)
     rc = _lib.shpl_lidar_to_cam(_ptr(velo), int(n), R.ctypes.data_as(ctypes.c_void_p), P.ctypes.data_as(ctypes.c_void_p), w, h,
                                 1 if min_intensity else 0, float(min_intensity or 0.0), _ptr(out), int(out.shape[1]),
                                 _ptr(counts), _ptr(ws), ws.numel(), _stream() if stream is None else stream)
