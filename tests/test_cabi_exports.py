@@ -136,3 +136,33 @@ def test_config_dataclasses_mirror_the_proto_fields():
     c.rpn_dual_sparse_pooling_after_vgg = True
     assert np.array_equal(c.bv_index_indicator(), np.zeros((1, 3)))                            # rpn_model.py:295
     assert KittiDatasetSparsePoolingConfig(use_pyramid_level_at_SHPL="P3").feat_stride() == 8    # kitti_dataset.py:375
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path, lib):
+    """include/shpl.h is the boundary a non-Python host binds: it must compile as C99 and as C++ with warnings as
+    errors, and a C program linked against libshpl.so must see the declared ABI version (no GPU needed for that call)."""
+    import shutil
+    import subprocess
+    gcc, gxx = shutil.which("gcc"), shutil.which("g++")
+    if not gcc or not gxx:
+        pytest.skip("no host compiler")
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "shpl.h"\n'
+                   'int main(void) {\n'
+                   '    shpl_plan p;\n'
+                   '    (void)p;\n'
+                   '    printf("%d %d %d %d\\n", shpl_abi_version(), SHPL_ABI_VERSION, SHPL_HEAVY_LEN, (int)sizeof(shpl_plan));\n'
+                   '    return shpl_pool_forward(0, 0, 0, 0, 0, 0, 0, 0, -1, 4, 10, 4, 0, 0) == SHPL_ERR_INVALID_ARGUMENT ? 0 : 1;\n'
+                   '}\n')
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(LIB)
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, str(src), "-o", str(exe),
+                    "-L", libdir, "-lshpl", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out[0] == out[1] == "7" and out[2] == "512"
+    from sparse_pooling_b200 import _cabi
+    assert int(out[3]) == ctypes.sizeof(_cabi.ShplPlan)                   # the ctypes mirror of struct shpl_plan has its layout
+    cxx = tmp_path / "abi.cpp"
+    cxx.write_text('#include "shpl.h"\nint main() { return shpl_abi_version() == SHPL_ABI_VERSION ? 0 : 1; }\n')
+    subprocess.run([gxx, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", str(cxx)], check=True)
