@@ -18,7 +18,10 @@ Pinning status
 * feeders and ingest (BevSlices.generate_bev, MV3D point_cloud_2_top_sparse, get_lidar_point_cloud): PINNED --
   ``feeder_oracle.py`` is checked against outputs of the reference's own classes / functions run by
   ``gen_goldens.py`` on seeded synthetic scans (for the ingest: through KITTI-format files in a temporary directory).
-* value path (gather -> SpMM -> concat, scatter, gradients): the arithmetic lives
+* augmentation hooks (kitti_aug flips, MV3D augment_voxel's point transforms + img_index2, augment_fv's index
+  update): PINNED -- ``gen_goldens.py augment_goldens`` imports kitti_aug.py and executes the source of augment_voxel /
+  augment_fv where it lies (the file as a whole is Python 2) with np.random seeded.
+* value path (gather -> SpMM -> concat, scatter, the VFE scatter_nd, gradients): the arithmetic lives
   in TensorFlow 1.8 (third-party, not vendored, not installable here) and the
   reference holds no golden vector, test or fixture for it:
   PARITY UNPINNED at the TF boundary.  The restatement follows TF's documented
