@@ -1,5 +1,5 @@
 """Times shpl_pool_heavy alone (exact kernel + tree kernel) for ONE listed cell of L entries, per channel count.
-CUDA events around 20 back-to-back calls.  Usage: python tools/heavy_bench.py"""
+CUDA events around 20 back-to-back calls.  Usage: python tools/heavy_bench.py [C ...]   (default: 16 64 256)"""
 import json
 import os
 import sys
@@ -15,7 +15,7 @@ from sparse_pooling_b200.ops import _ptr, _stream  # noqa: E402
 dev = torch.device("cuda", 0)
 rng = np.random.default_rng(0)
 out = []
-for C in (16, 64, 256):
+for C in ([int(x) for x in sys.argv[1:]] or [16, 64, 256]):
     for L in (600, 2048, 8192, 16384, 40000):
         n = L + 500
         bx = np.r_[np.full(L, 3), rng.integers(0, 110, 500)]
