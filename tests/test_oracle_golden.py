@@ -360,3 +360,31 @@ def test_augment_oracle_matches_reference_hooks(golden_dir):
     assert digest(img_index) == str(g["fv_input_sha"])
     fsx, fsy, fratio = g["fv_params"]
     np.testing.assert_array_equal(fo.augment_fv_index(img_index, fsx, fsy, np.array([fratio])), g["fv_img_index"])
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_value_oracle_vs_scipy_sparse_matmul(seed):
+    """A third engine for the restated TF semantics (SURVEY.md 8c suggests it): M as a scipy COO matrix,
+    pooled = M @ gather(img) and, transposed, M^T @ bev scattered to the pixels -- fp64 accumulation in scipy, so the
+    fp32 oracle must agree to the north_star's 1e-5 of the term sum."""
+    sp = pytest.importorskip("scipy.sparse")
+    o, val, bev, img = _small_case(seed)
+    flip, Mij = o["img_index_flip_pool"], o["Mij_pool"]
+    Hb, Wb, Cb = bev.shape[1:]
+    Hi, Wi, Ci = img.shape[1:]
+    R, n = int(o["M_size"][0]), int(o["M_size"][1])
+    M = sp.coo_matrix((val.astype(np.float64), (Mij[:, 0], Mij[:, 1])), shape=(R, n)).tocsr()
+    pix = flip[:, 1] * Wi + flip[:, 2]
+    G = img.reshape(-1, Ci).astype(np.float64)[pix]                        # gather_nd
+    Y = M @ G                                                             # sparse_tensor_dense_matmul
+    S = M.T @ bev.reshape(-1, Cb).astype(np.float64)                      # sparse_transpose + matmul: [n, Cb]
+    Pm = np.zeros((Hi * Wi, Cb))
+    np.add.at(Pm, pix, S)                                                 # scatter_nd sums duplicates
+    o_bv, o_img = vo.sparse_pool_layer([bev, img], [Ci, Cb], (Mij, val, o["M_size"]), flip, np.zeros((1, 3)))
+    absM = abs(M)
+    tol_bv = 1e-5 * (absM @ np.abs(G)).max() + 1e-12
+    tol_img = 1e-5 * np.abs(Pm).max() + 1e-6
+    assert np.abs(o_bv[0, ..., Cb:].reshape(-1, Ci) - Y).max() <= tol_bv
+    assert np.abs(o_img[0, ..., Ci:].reshape(-1, Cb) - Pm).max() <= max(tol_img, tol_bv)
+    np.testing.assert_array_equal(o_bv[0, ..., :Cb], bev[0])              # the concatenated halves are the inputs themselves
+    np.testing.assert_array_equal(o_img[0, ..., :Ci], img[0])
