@@ -732,3 +732,43 @@ def test_randomized_builder_against_the_index_oracle(shpl):
             continue
         val = np.ones(nnz, np.float32) if m_val is None else m_val.astype(np.float32)
         assert_plan_equals_oracle(o["shpl_plan"], o_ref["Mij_pool"], val, o_ref["img_index_flip_pool"], R, (Hp, Wp))
+
+
+@pytest.mark.parametrize("C", [32, 128])
+def test_many_listed_cells_share_the_clusters(shpl, C):
+    """More listed cells than clusters in the launch (200 cells of 520..900 entries, 128 clusters for the exact kernel, 64 for
+    the tree) plus three cells above SHPL_EXACT_LEN: every cluster walks several cells one after the other, re-using its
+    staging buffer.  Exact-kernel cells and everything else bit-identical to the sequential oracle, tree cells within 1e-5
+    of the sum of |terms|."""
+    rng = np.random.default_rng(100 + C)
+    Hb, Wb, Hi, Wi = 120, 110, 32, 64
+    cells = rng.choice(Hb * Wb, 203, replace=False)
+    lens = np.r_[rng.integers(520, 901, 200), [2100, 3000, 5000]]
+    rows = np.r_[np.repeat(cells, lens), rng.integers(0, Hb * Wb, 3000)]
+    n = len(rows)
+    perm = rng.permutation(n)
+    rows = rows[perm]
+    u, v = rng.integers(0, Wi, n), rng.integers(0, Hi, n)
+    d = dict(bv_index=np.stack((rows % Wb, rows // Wb), axis=1).astype(np.int64), img_index=np.stack((u, v, np.zeros(n))).astype(np.float64),
+             bv_size=np.array([Hb, Wb]), img_size=np.array([Wi, Hi]))
+    val = (1.0 / rng.integers(1, 46, n)).astype(np.float32)
+    bev = rng.standard_normal((1, Hb, Wb, C), dtype=np.float32)
+    img = rng.standard_normal((1, Hi, Wi, C), dtype=np.float32)
+    o = shpl.produce_sparse_pooling_input(d, M_val=val.astype(np.float64))
+    Mij, flip = o["Mij_pool"], o["img_index_flip_pool"]
+    counts = np.bincount(Mij[:, 0], minlength=Hb * Wb)
+    assert o["shpl_plan"].n_heavy[0] == int((counts > 512).sum()) >= 203
+    M = shpl.SparseTensor.from_sparse_pooling_input(o)
+    tb, ti = torch.from_numpy(bev).cuda(), torch.from_numpy(img).cuda()
+    fused, _ = shpl.sparse_pool_layer([tb, ti], [C, C], M, img_index_flip=torch.from_numpy(flip).cuda())
+    got = fused[0].cpu().numpy().reshape(Hb * Wb, 2 * C)
+    ref = cref.forward(bev[0], img[0], Mij, val, flip).reshape(Hb * Wb, 2 * C)
+    tree = counts > 2048
+    assert tree.sum() == 3
+    np.testing.assert_array_equal(got[~tree], ref[~tree])
+    pix = flip[:, 1] * Wi + flip[:, 2]
+    for r in np.nonzero(tree)[0]:
+        sel = Mij[:, 0] == r
+        scale = np.abs(val[sel, None] * img[0].reshape(-1, C)[pix[sel]]).sum(0).max()
+        np.testing.assert_array_equal(got[r, :C], ref[r, :C])
+        assert np.abs(got[r, C:] - ref[r, C:]).max() <= 1e-5 * scale
