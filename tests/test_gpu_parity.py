@@ -772,3 +772,43 @@ def test_many_listed_cells_share_the_clusters(shpl, C):
         scale = np.abs(val[sel, None] * img[0].reshape(-1, C)[pix[sel]]).sum(0).max()
         np.testing.assert_array_equal(got[r, :C], ref[r, :C])
         assert np.abs(got[r, C:] - ref[r, C:]).max() <= 1e-5 * scale
+
+
+def test_stacked_frames_with_listed_cells(shpl):
+    """Three frames stacked into one plan (build_pairs_plan), each with its own listed cell / pixel (600..1900 entries) at a
+    different place: the heavy lists carry the stacked row / pixel numbers and the entry offsets of the later frames, the
+    exact kernel serves all of them -- forward and backward of every frame bit-identical to the per-frame oracle."""
+    rng = np.random.default_rng(77)
+    B, C, Hb, Wb, Hi, Wi = 3, 32, 40, 50, 24, 64
+    img_index, bv_index, m_val, refs = [], [], [], []
+    for f in range(B):
+        L, Lp = int(rng.integers(600, 1900)), int(rng.integers(520, 900))
+        n = L + 1500
+        bx = np.r_[np.full(L, 3 + f), rng.integers(0, Wb, 1500)]
+        bz = np.r_[np.full(L, 7 + 2 * f), rng.integers(0, Hb, 1500)]
+        u, v = rng.integers(0, Wi, n), rng.integers(0, Hi, n)
+        u[L:L + Lp], v[L:L + Lp] = 5 + f, 9                                  # a listed pixel for the transposed arrays
+        perm = rng.permutation(n)
+        ii = np.stack((u, v, np.zeros(n)))[:, perm].astype(np.float64)
+        bi = np.stack((bx, bz), axis=1)[perm].astype(np.int64)
+        mv = 1.0 / rng.integers(1, 46, n)
+        o_ref = io.produce_sparse_pooling_input(dict(img_index=ii.copy(), img_size=np.array([Wi, Hi]), bv_index=bi, bv_size=np.array([Hb, Wb])),
+                                                M_val=mv)
+        img_index.append(ii)
+        bv_index.append(bi)
+        m_val.append(mv)
+        refs.append((o_ref, mv.astype(np.float32)))
+    plan = shpl.build_pairs_plan(img_index, bv_index, [Wi, Hi], [Hb, Wb], m_val=m_val)
+    assert plan.frames == B and plan.n_heavy == (B, B)
+    bev = rng.standard_normal((B, Hb, Wb, C), dtype=np.float32)
+    img = rng.standard_normal((B, Hi, Wi, C), dtype=np.float32)
+    tb, ti = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
+    fused = shpl.sparse_pool(tb, ti, plan)
+    g = rng.standard_normal(tuple(fused.shape), dtype=np.float32)
+    fused.backward(torch.from_numpy(g).cuda())
+    for k, (o_ref, val) in enumerate(refs):
+        np.testing.assert_array_equal(fused[k].detach().cpu().numpy(),
+                                      cref.forward(bev[k], img[k], o_ref["Mij_pool"], val, o_ref["img_index_flip_pool"]))
+        gd, gs = cref.backward(g[k], o_ref["Mij_pool"], val, o_ref["img_index_flip_pool"], C, (Hi, Wi, C))
+        np.testing.assert_array_equal(tb.grad[k].cpu().numpy(), gd)
+        np.testing.assert_array_equal(ti.grad[k].cpu().numpy(), gs)
