@@ -219,12 +219,17 @@ int shpl_pool_backward_dual(const float* g_fused_bev, const float* g_fused_img,
                             int32_t nnz_max, int32_t heavy_len, int32_t n_rows, int32_t C_b, int32_t n_src, int32_t C_i,
                             float* g_bev, float* g_img, void* stream);
 
-/* Heavy cells (more than SHPL_HEAVY_LEN entries; none at KITTI / MV3D shapes, the Zipf stress case has
- * a 178 000-entry cell): one thread-block CLUSTER of 8 CTAs per listed cell.  The cell's entries are cut
- * into 64 contiguous pieces (8 CTAs x 8 warps); every warp sums its piece in stored order, the 8 warp sums
- * of a CTA are added in order in shared memory, and CTA 0 adds the 8 CTA sums in order through
- * distributed shared memory: a fixed tree, deterministic, within fp32 rounding of the sequential sum
- * (not bit-identical to it).  Overwrites what the main kernel left for those cells:
+/* Listed ("heavy") cells (more than SHPL_HEAVY_LEN entries; none at KITTI / MV3D shapes, the Zipf stress case has
+ * a 178 000-entry cell): one thread-block CLUSTER of 8 CTAs per listed cell, in two kernels.
+ *   up to SHPL_EXACT_LEN entries: the sequential sum, bit-identical to what the main kernels produce -- the 64
+ *     warps of the cluster gather a round of entries and park the rounded products w*x, in entry order, in CTA 0's
+ *     shared memory (remote stores through distributed shared memory); adder warps of CTA 0 (one per 32 channel
+ *     vectors) then add them in entry order;
+ *   longer cells: the entries are cut into 64 contiguous pieces (8 CTAs x 8 warps); every warp sums its piece in
+ *     stored order, the 8 warp sums of a CTA are added in order in shared memory, and CTA 0 adds the 8 CTA sums in
+ *     order through distributed shared memory: a fixed tree, deterministic, within fp32 rounding of the sequential
+ *     sum (not bit-identical to it).
+ * Overwrites what the main kernel left for those cells:
  *   out[c*out_stride + 0:C] = (addend ? addend[c*addend_stride + 0:C] : 0) + sum_k val[k] * gather_in[idx[k]*gather_stride + 0:C]
  * for every c in list[0:*count_dev].  All strides in floats; the channel offsets are folded into the
  * pointers (e.g. out = fused + C_d, out_stride = C_d + C_s for the forward). */

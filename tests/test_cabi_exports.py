@@ -166,3 +166,14 @@ def test_header_is_plain_c_and_links_from_c(tmp_path, lib):
     cxx = tmp_path / "abi.cpp"
     cxx.write_text('#include "shpl.h"\nint main() { return shpl_abi_version() == SHPL_ABI_VERSION ? 0 : 1; }\n')
     subprocess.run([gxx, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", str(cxx)], check=True)
+
+
+def test_cpp_host_example_builds_against_the_library(lib):
+    """examples/cabi_step.cu -- a C++ host on the bare C ABI, no Python -- compiles and links (running it needs a GPU)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "examples"), "-B", "NVCC=" + nvcc], check=True, capture_output=True)
+    assert os.path.exists(os.path.join(ROOT, "examples", "cabi_step"))
