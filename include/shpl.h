@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SHPL_ABI_VERSION 7
+#define SHPL_ABI_VERSION 8
 
 /* Cells with more entries than this are "heavy": the builder lists them in the plan and their sum
  * is formed by shpl_pool_heavy (a thread-block cluster per cell) instead of one warp walking the cell.
@@ -358,6 +358,31 @@ int shpl_mv3d_project_augment(double* lidar_pc, int64_t n, const int32_t* n_dev,
  *   img_index i64 [3, ld] row-major (ld >= n: row stride). */
 int shpl_augment_fv_index(int64_t* img_index, int64_t ld, int64_t n, const int32_t* n_dev,
                           double expansion_ratio, double sx, double sy, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Post-fusion 3x3 convolution fused with the pooling: the fused (concat) map is never
+ * written.  Replaces, for the rpn_sparse_pooling_conv_after_fusion switch (model.proto:89, default true),
+ *   sparse_pool_layer(...) -> slim.conv2d(bev_fused, C, [3, 3], ...)   avod/avod/core/models/rpn_model.py:335-346
+ *   the RetinaNet form                                                  avod/avod/core/models/retinanet_model.py:337-348
+ * with  conv(concat(dst, pooled)) = conv(dst; W[:, :, :C_d, :]) + conv(pooled; W[:, :, C_d:, :]):
+ * the first term is a dense implicit GEMM on the tcgen05 tensor cores (3xTF32 split: fp32-level accuracy, TMA halo
+ * loads with the SAME zero padding, TMEM accumulators), the second a sparse update of the 3x3 neighbourhoods of the
+ * cells that receive pooled features.
+ *   dst [frames, H, W, C_d], src [n_src, C_s] (the map gathered from), CSR by destination cell (ptr, key, idx, val,
+ *   nnz_max as in shpl_pool_forward; plan rows of frame f are offset by f*H*W; key is required),
+ *   weight: the slim.conv2d variable, HWIO [3, 3, C_d + C_s, C_out], stride 1, padding SAME;
+ *   scale / shift [C_out] (either may be NULL = 1 / 0): bias or folded inference batch norm; relu != 0: ReLU;
+ *   out [frames, H, W, C_out] = act(scale * conv(concat(dst, pooled)) + shift).
+ * Built for C_d = C_out = 32 and C_s in {0, 32, 64} (the KITTI pre-RPN layer: 32 + 32 -> 32); other shapes return
+ * SHPL_ERR_UNSUPPORTED.  workspace: shpl_conv3x3_workspace_bytes(frames, H, W) bytes, 256-byte aligned.
+ * Accuracy: |error| <= 1e-5 * sum |terms| per output (3xTF32 products, fp32 accumulation); not bit-reproducible
+ * against a sequential fp32 loop (neither is cuDNN / TF). */
+size_t shpl_conv3x3_workspace_bytes(int32_t frames, int32_t H, int32_t W);
+int shpl_pool_conv3x3_forward(const float* dst, const float* src,
+                              const int32_t* ptr, const int32_t* key, const int32_t* idx, const float* val,
+                              int32_t nnz_max, int32_t frames, int32_t H, int32_t W, int32_t C_d, int32_t n_src, int32_t C_s,
+                              const float* weight, int32_t C_out, const float* scale, const float* shift, int32_t relu,
+                              float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

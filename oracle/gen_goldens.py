@@ -156,6 +156,44 @@ def main():
     mv3d_goldens(spu)
 
 
+
+# ---- the sparse-pooling switches, parsed out of the reference's .proto TEXT (protoc is not available here) ----
+PROTO_SOURCES = (("avod/avod/protos/model.proto", ("RpnConfig", "RetinaNetConfig")),
+                 ("avod/avod/protos/kitti_dataset.proto", ("KittiDatasetConfig",)))
+PROTO_WANTED = ("rpn_use_sparse_pooling", "rpn_sparse_pooling_use_batch_norm", "rpn_sparse_pooling_conv_after_fusion",
+                "rpn_sparse_pooling_after_vgg", "rpn_dual_sparse_pooling_after_vgg", "use_sparse_pooling",
+                "use_pyramid_level_at_SHPL", "output_indices")
+
+
+def proto_goldens(ref_root="/root/reference"):
+    """tests/golden/proto_fields.json: for every sparse-pooling field of model.proto / kitti_dataset.proto its message,
+    label, type, field number, default and source line, read from the .proto text itself."""
+    import json
+    import re
+    field_re = re.compile(r"^\s*(optional|required|repeated)\s+(\w+)\s+(\w+)\s*=\s*(\d+)\s*(?:\[\s*default\s*=\s*([^\]]+?)\s*\])?\s*;")
+    out = []
+    for rel, messages in PROTO_SOURCES:
+        message = None
+        for ln, line in enumerate(open(os.path.join(ref_root, rel)), 1):
+            m = re.match(r"^\s*message\s+(\w+)", line)
+            if m:
+                message = m.group(1)
+                continue
+            f = field_re.match(line)
+            if f and message in messages and f.group(3) in PROTO_WANTED:
+                default = f.group(5)
+                if default is not None:
+                    default = default.strip("'\"")
+                    if f.group(2) == "bool":
+                        default = {"true": True, "false": False}[default]
+                out.append(dict(file=rel, line=ln, message=message, label=f.group(1), type=f.group(2), name=f.group(3),
+                                number=int(f.group(4)), default=default))
+    with open(os.path.join(OUT, "proto_fields.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+    print("proto_fields:", [(r["message"], r["name"], r["number"], r["default"]) for r in out])
+    return out
+
+
 MV3D_CASES = {
     # name: (seed, n_points, kwargs of synth.mv3d_frame)
     "mv3d_seed5": (5, 6000, {}),                                  # ped/cyc ranges (config_voxels.py:50-64), cap 45
@@ -313,7 +351,11 @@ def augment_goldens():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "proto":      # only the .proto fixture (cheap)
+        proto_goldens()
+        sys.exit(0)
     main()
+    proto_goldens()
     feeder_goldens()
     ingest_goldens()
     augment_goldens()

@@ -195,3 +195,41 @@ def voxel_scatter_grad(coordinate, g_out):
     c = coordinate[inside]
     g[inside] = g_out[c[:, 0], c[:, 1], c[:, 2], c[:, 3]]
     return g
+
+
+# ---------------------------------------------------------------------------------------------
+# Post-fusion 3x3 convolution: slim.conv2d(fused, C, [3, 3]) right after sparse_pool_layer,
+# /root/reference/avod/avod/core/models/rpn_model.py:338-354, retinanet_model.py:344-348.  slim.conv2d defaults:
+# stride 1, padding SAME, weights HWIO [3, 3, C_in, C_out]; then biases (or the normalizer) and ReLU.  The
+# arithmetic again lives in TensorFlow (cuDNN / Eigen): PARITY UNPINNED, cross-checked against torch conv2d in the
+# tests.  Accumulated in float64 here, so that the comparison bound (1e-5 * sum |terms|) is about the CUDA kernel
+# alone.
+def conv3x3_same(x, w):
+    """x [B, H, W, Cin], w [3, 3, Cin, Cout] -> (y [B, H, W, Cout] float64, sum of |terms| per output, float64)."""
+    x = np.asarray(x, dtype=np.float64)
+    w = np.asarray(w, dtype=np.float64)
+    B, H, W, _ = x.shape
+    xp = np.zeros((B, H + 2, W + 2, x.shape[3]))
+    xp[:, 1:H + 1, 1:W + 1] = x
+    y = np.zeros((B, H, W, w.shape[3]))
+    mag = np.zeros_like(y)
+    for dy in range(3):
+        for dx in range(3):
+            win = xp[:, dy:dy + H, dx:dx + W]
+            y += win @ w[dy, dx]
+            mag += np.abs(win) @ np.abs(w[dy, dx])
+    return y, mag
+
+
+def conv3x3_after_fusion(fused, w, scale=None, shift=None, relu=False):
+    """act(scale * conv3x3_same(fused, w) + shift); returns (y float64, magnitude of the un-activated sum)."""
+    y, mag = conv3x3_same(fused, w)
+    if scale is not None:
+        y = y * np.asarray(scale, dtype=np.float64)
+        mag = mag * np.abs(np.asarray(scale, dtype=np.float64))
+    if shift is not None:
+        y = y + np.asarray(shift, dtype=np.float64)
+        mag = mag + np.abs(np.asarray(shift, dtype=np.float64))
+    if relu:
+        y = np.maximum(y, 0.0)
+    return y, mag

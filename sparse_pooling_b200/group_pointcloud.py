@@ -34,11 +34,15 @@ GRID_DEPTH = 10
 STRICT_INDEX_CHECK = True
 
 
-def build_input(voxel_dict_list):
-    """group_pointcloud.py:88-105: concatenate the per-sample buffers and put the sample number in front of
-    each coordinate.  The reference pads a new first column (written for [K,3] (d,h,w) buffers); this fork's feeder
-    already emits [K,4] = (0, d, h, w) (construct_voxel.py:128, :147), for which the pad would give five columns and
-    break the scatter -- for 4-column buffers the sample number overwrites the leading zero instead.
+def build_input(voxel_dict_list, fix_coordinate_columns=False):
+    """group_pointcloud.py:88-105: concatenate the per-sample buffers and put the sample number in front of each
+    coordinate row with np.pad -- ALWAYS a new first column, exactly like the reference (default).
+
+    The reference's pad was written for [K,3] (d,h,w) buffers, but this fork's feeder emits [K,4] = (0, d, h, w)
+    (construct_voxel.py:128, :147), for which the pad gives FIVE columns that tf.scatter_nd into the rank-5 grid then
+    reads as (batch, 0, d, h, w) -- a reference inconsistency (reproduce, do not fix silently).
+    fix_coordinate_columns=True is the explicit opt-in repair: for 4-column buffers the sample number overwrites the
+    leading zero instead, giving the (batch, d, h, w) rows voxel_scatter takes.
     numpy in -> numpy out, CUDA tensors in -> CUDA tensors out."""
     batch_size = len(voxel_dict_list)
     features, numbers, coords = [], [], []
@@ -47,14 +51,14 @@ def build_input(voxel_dict_list):
         numbers.append(vd['number_buffer'])
         c = vd['coordinate_buffer']
         if isinstance(c, torch.Tensor):
-            if c.shape[1] == 4:
+            if fix_coordinate_columns and c.shape[1] == 4:
                 c = c.clone()
                 c[:, 0] = i
             else:
                 c = torch.nn.functional.pad(c, (1, 0), value=i)
         else:
             c = np.asarray(c)
-            if c.shape[1] == 4:
+            if fix_coordinate_columns and c.shape[1] == 4:
                 c = c.copy()
                 c[:, 0] = i
             else:

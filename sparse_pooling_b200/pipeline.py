@@ -11,51 +11,14 @@ copied to the host, and the only thing that changes between steps is the content
 of the buffers.
 """
 import ctypes
-from dataclasses import dataclass
-from typing import Tuple
-
 import numpy as np
 import torch
 
 from . import _cabi, ops
+from .layer_spec import LayerSpec  # noqa: F401  (re-exported: pipeline.LayerSpec)
 from .ops import SparsePoolPlan
 
 _lib = _cabi.lib
-
-
-@dataclass
-class LayerSpec:
-    """One SHPL instance of a model."""
-    name: str
-    bev_hw: Tuple[int, int]      # BEV feature map H, W   (= floor(bv_size / stride_bv))
-    img_hw: Tuple[int, int]      # image feature map H, W (= floor(im_size / stride_img))
-    c_bev: int
-    c_img: int
-    stride: Tuple[int, int]      # (stride_img, stride_bv): produce_sparse_pooling_input's stride argument
-    dual: bool                   # bev -> img as well (bv_index is not None)
-    im_size: Tuple[int, int]     # (W, H) handed to gen_sparse_pooling_input_avod
-    bv_size: Tuple[int, int]     # (H_b, W_b) handed to gen_sparse_pooling_input_avod
-
-    @property
-    def R(self):
-        return self.bev_hw[0] * self.bev_hw[1]
-
-    @property
-    def Q(self):
-        return self.img_hw[0] * self.img_hw[1]
-
-    def bytes_forward(self, nnz):
-        """Algorithmic bytes of the forward launches."""
-        b = 4 * (self.R * self.c_bev + self.R * (self.c_bev + self.c_img) + nnz * (self.c_img + 2) + self.R + 1)
-        if self.dual:
-            b += 4 * (self.Q * self.c_img + self.Q * (self.c_img + self.c_bev) + nnz * (self.c_bev + 2) + self.Q + 1)
-        return b
-
-    def bytes_backward(self, nnz):
-        b = 4 * (2 * self.R * self.c_bev + nnz * (self.c_img + 2) + self.Q * self.c_img + self.Q + 1)
-        if self.dual:
-            b += 4 * (2 * self.Q * self.c_img + nnz * (self.c_bev + 2) + self.R * self.c_bev + self.R + 1)
-        return b
 
 
 def _p(t):

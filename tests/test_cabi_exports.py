@@ -32,7 +32,8 @@ def test_header_declares_the_expected_entry_points():
         "shpl_pool_forward_dual", "shpl_pool_backward_dual", "shpl_pool_heavy",
         "shpl_bev_grid_dims", "shpl_bev_workspace_bytes", "shpl_bev_slices",
         "shpl_mv3d_workspace_bytes", "shpl_mv3d_voxelize", "shpl_lidar_workspace_bytes", "shpl_lidar_to_cam",
-        "shpl_flip_point_cloud", "shpl_mv3d_project_augment", "shpl_augment_fv_index"])
+        "shpl_flip_point_cloud", "shpl_mv3d_project_augment", "shpl_augment_fv_index",
+        "shpl_conv3x3_workspace_bytes", "shpl_pool_conv3x3_forward"])
 
 
 def test_library_exports_every_declared_symbol(lib):
@@ -43,7 +44,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_binding_covers_the_header(lib):
     from sparse_pooling_b200 import _cabi
     assert sorted(_cabi.SIGNATURES) == declared_functions()
-    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 7
+    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 8
 
 
 def test_workspace_query_grows_with_n(lib):
@@ -126,16 +127,58 @@ def test_ops_refuse_cpu_tensors():
         ops.require_cuda(torch.zeros(2), "x")
 
 
-def test_config_dataclasses_mirror_the_proto_fields():
+def test_config_dataclasses_mirror_the_proto_fields(golden_dir):
+    """Names, field numbers and DEFAULTS of the sparse-pooling switches come from tests/golden/proto_fields.json, which
+    oracle/gen_goldens.py parsed out of the reference's .proto text (model.proto:87-91, :120-121; kitti_dataset.proto:38-40)."""
+    import json
     import numpy as np
-    from sparse_pooling_b200 import KittiDatasetSparsePoolingConfig, RpnSparsePoolingConfig
+    from sparse_pooling_b200 import (KittiDatasetSparsePoolingConfig, RetinaNetSparsePoolingConfig, RpnSparsePoolingConfig,
+                                     config)
+    fields = json.load(open(os.path.join(golden_dir, "proto_fields.json")))
+    assert len(fields) == 9
+    by_message = {"RpnConfig": RpnSparsePoolingConfig(), "RetinaNetConfig": RetinaNetSparsePoolingConfig(),
+                  "KittiDatasetConfig": KittiDatasetSparsePoolingConfig()}
+    for f in fields:
+        obj = by_message[f["message"]]
+        assert hasattr(obj, f["name"]), f
+        assert getattr(obj, f["name"]) == f["default"], (f, getattr(obj, f["name"]))
+        assert f["label"] == "optional"
+        key = ("dataset." + f["name"]) if (f["message"] == "KittiDatasetConfig" and f["name"] == "use_pyramid_level_at_SHPL") else f["name"]
+        assert config.PROTO_FIELDS[key] == (f["message"], f["number"]), f
+    assert len(config.PROTO_FIELDS) == len(fields)
+    # the two defaults round 1 had wrong
+    assert RpnSparsePoolingConfig().rpn_sparse_pooling_conv_after_fusion is True            # model.proto:89
+    assert KittiDatasetSparsePoolingConfig().use_pyramid_level_at_SHPL == "P2"              # kitti_dataset.proto:40
+    assert KittiDatasetSparsePoolingConfig().feat_stride() == 4                             # kitti_dataset.py:375
     c = RpnSparsePoolingConfig()
-    assert [c.rpn_use_sparse_pooling, c.rpn_sparse_pooling_use_batch_norm, c.rpn_sparse_pooling_conv_after_fusion,
-            c.rpn_sparse_pooling_after_vgg, c.rpn_dual_sparse_pooling_after_vgg] == [False] * 5   # model.proto:87-91
     assert c.bv_index_indicator() is None
     c.rpn_dual_sparse_pooling_after_vgg = True
     assert np.array_equal(c.bv_index_indicator(), np.zeros((1, 3)))                            # rpn_model.py:295
     assert KittiDatasetSparsePoolingConfig(use_pyramid_level_at_SHPL="P3").feat_stride() == 8    # kitti_dataset.py:375
+    assert KittiDatasetSparsePoolingConfig(use_pyramid_level_at_SHPL="P0").feat_stride() == 1
+
+
+def test_build_input_pads_like_the_reference_and_repairs_only_on_request():
+    """group_pointcloud.py:88-105 ALWAYS pads a new first column (np.pad): with this fork's [K,4] coordinate buffers
+    that gives five columns.  The default reproduces it; fix_coordinate_columns=True is the explicit repair."""
+    import numpy as np
+    from sparse_pooling_b200 import group_pointcloud as gp
+    rng = np.random.default_rng(0)
+    dicts = []
+    for k in (5, 3):
+        c4 = np.concatenate([np.zeros((k, 1), np.int64), rng.integers(0, 10, (k, 3))], axis=1)
+        dicts.append(dict(feature_buffer=rng.standard_normal((k, 45, 7)), number_buffer=rng.integers(1, 45, k), coordinate_buffer=c4))
+    B, feat, num, coord = gp.build_input(dicts)
+    ref = np.concatenate([np.pad(d["coordinate_buffer"], ((0, 0), (1, 0)), mode="constant", constant_values=i) for i, d in enumerate(dicts)])
+    assert B == 2 and coord.shape == (8, 5) and np.array_equal(coord, ref)
+    assert np.array_equal(feat, np.concatenate([d["feature_buffer"] for d in dicts])) and num.shape == (8,)
+    _, _, _, fixed = gp.build_input(dicts, fix_coordinate_columns=True)
+    assert fixed.shape == (8, 4) and np.array_equal(fixed[:, 0], [0] * 5 + [1] * 3)
+    assert np.array_equal(fixed[:, 1:], np.concatenate([d["coordinate_buffer"][:, 1:] for d in dicts]))
+    # [K,3] buffers (what the pad was written for): both modes agree
+    d3 = [dict(d, coordinate_buffer=d["coordinate_buffer"][:, 1:]) for d in dicts]
+    assert np.array_equal(gp.build_input(d3)[3], gp.build_input(d3, fix_coordinate_columns=True)[3])
+    assert np.array_equal(gp.build_input(d3)[3], fixed)
 
 
 def test_header_is_plain_c_and_links_from_c(tmp_path, lib):
@@ -160,7 +203,7 @@ def test_header_is_plain_c_and_links_from_c(tmp_path, lib):
     subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, str(src), "-o", str(exe),
                     "-L", libdir, "-lshpl", "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
-    assert out[0] == out[1] == "7" and out[2] == "512"
+    assert out[0] == out[1] == "8" and out[2] == "512"
     from sparse_pooling_b200 import _cabi
     assert int(out[3]) == ctypes.sizeof(_cabi.ShplPlan)                   # the ctypes mirror of struct shpl_plan has its layout
     cxx = tmp_path / "abi.cpp"

@@ -87,14 +87,15 @@ def test_batch_from_build_input_and_device_side_count(shpl):
     device (k_dev): rows past the count do not exist, nothing is read back."""
     gp = shpl.group_pointcloud
     dicts, grids = zip(*(feeder_frame(s, n=6000) for s in (71, 72)))
-    B, feature, number, coord = gp.build_input(list(dicts))
+    B, feature, number, coord = gp.build_input(list(dicts), fix_coordinate_columns=True)   # the feeder emits [K,4]: see build_input
+    assert gp.build_input(list(dicts))[3].shape[1] == 5      # the reference's pad, reproduced by default
     assert B == 2 and coord.shape[1] == 4 and feature.shape[0] == number.shape[0] == coord.shape[0]
     K0 = dicts[0]["coordinate_buffer"].shape[0]
     assert (coord[:K0, 0] == 0).all() and (coord[K0:, 0] == 1).all()
     np.testing.assert_array_equal(coord[:, 1:], np.concatenate([d["coordinate_buffer"][:, 1:] for d in dicts]))
     # torch in -> torch out
     tdicts = [{k: torch.from_numpy(v).cuda() for k, v in d.items()} for d in dicts]
-    tB, tf_, tn, tc = gp.build_input(tdicts)
+    tB, tf_, tn, tc = gp.build_input(tdicts, fix_coordinate_columns=True)
     assert tc.is_cuda and tB == 2
     np.testing.assert_array_equal(tc.cpu().numpy(), coord)
     K = coord.shape[0]
