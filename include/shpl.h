@@ -73,7 +73,11 @@ typedef struct shpl_plan {
     int32_t* counts;    /* [8] device: [0]=n after image clip, [1]=nnz (columns of M),
                            [2]=entries left out of the CSRs because an index is out of
                            range (TF-CPU raises InvalidArgumentError for those),
-                           [3]=entries in the CSRs; [4..7] reserved                   */
+                           [3]=entries in the CSRs; [4]=running entry offset after this
+                           frame (the next stacked frame starts there); [5]=1 if this
+                           frame's entries did not fit the plan behind the frames stacked
+                           before it (capacity < entry base + n: nothing is written out
+                           of bounds, the entries are dropped); [6..7] reserved        */
 } shpl_plan;
 
 int         shpl_abi_version(void);
@@ -374,10 +378,11 @@ int shpl_augment_fv_index(int64_t* img_index, int64_t ld, int64_t n, const int32
  *   scale / shift [C_out] (either may be NULL = 1 / 0): bias or folded inference batch norm; relu != 0: ReLU;
  *   out [frames, H, W, C_out] = act(scale * conv(concat(dst, pooled)) + shift).
  * Built for C_d = C_out = 32 and C_s in {0, 32, 64} (the KITTI pre-RPN layer: 32 + 32 -> 32); other shapes return
- * SHPL_ERR_UNSUPPORTED.  workspace: shpl_conv3x3_workspace_bytes(frames, H, W) bytes, 256-byte aligned.
+ * SHPL_ERR_UNSUPPORTED.  workspace: shpl_conv3x3_workspace_bytes(frames, H, W, nnz_max) bytes, 256-byte aligned
+ * (weights in the tensor-core operand layout, two cell bitmaps, and 1152 bytes per entry for the sparse half).
  * Accuracy: |error| <= 1e-5 * sum |terms| per output (3xTF32 products, fp32 accumulation); not bit-reproducible
  * against a sequential fp32 loop (neither is cuDNN / TF). */
-size_t shpl_conv3x3_workspace_bytes(int32_t frames, int32_t H, int32_t W);
+size_t shpl_conv3x3_workspace_bytes(int32_t frames, int32_t H, int32_t W, int32_t nnz_max);
 int shpl_pool_conv3x3_forward(const float* dst, const float* src,
                               const int32_t* ptr, const int32_t* key, const int32_t* idx, const float* val,
                               int32_t nnz_max, int32_t frames, int32_t H, int32_t W, int32_t C_d, int32_t n_src, int32_t C_s,

@@ -98,7 +98,7 @@ SIGNATURES = {
                                                  ctypes.c_double, c_void_p, c_void_p, c_void_p]),
     "shpl_augment_fv_index": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_void_p, ctypes.c_double, ctypes.c_double,
                                              ctypes.c_double, c_void_p]),
-    "shpl_conv3x3_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "shpl_conv3x3_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "shpl_pool_conv3x3_forward": (ctypes.c_int, [c_void_p] * 6 + [c_int32] * 7 + [c_void_p, c_int32, c_void_p, c_void_p, c_int32,
                                                  c_void_p, c_void_p, c_size_t, c_void_p]),
     "shpl_pool_heavy": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

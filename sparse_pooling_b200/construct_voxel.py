@@ -29,17 +29,10 @@ zres = 0.4
 NUM_VOXEL_FEATURES = 7
 MAX_NUM_POINTS = 45
 
-_workspaces = {}
-
-
 def _workspace(device, n):
-    need = int(_lib.shpl_mv3d_workspace_bytes(int(n)))
-    key = str(device)
-    ws = _workspaces.get(key)
-    if ws is None or ws.numel() < need:
-        ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
-    return ws
+    """scratch of shpl_mv3d_voxelize for the current stream (ops.scratch: never shared between streams / threads)"""
+    from . import ops
+    return ops.scratch("mv3d", device, int(_lib.shpl_mv3d_workspace_bytes(int(n))))
 
 
 def voxelize_raw(points, img_index2, n, res, zres, side_range, fwd_range, height_range, max_points, out, stream=None):

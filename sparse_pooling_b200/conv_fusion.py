@@ -18,8 +18,8 @@ from .sparse_pool_utils import _check_oob, _resolve_plan
 _lib = _cabi.lib
 
 
-def conv_workspace(frames, H, W, device):
-    need = int(_lib.shpl_conv3x3_workspace_bytes(int(frames), int(H), int(W)))
+def conv_workspace(frames, H, W, device, nnz_max=0):
+    need = int(_lib.shpl_conv3x3_workspace_bytes(int(frames), int(H), int(W), int(nnz_max)))
     return torch.empty(need + 256, dtype=torch.uint8, device=device)
 
 
@@ -53,7 +53,7 @@ def sparse_pool_conv3x3(inputs, M, img_index_flip, weight, scale=None, shift=Non
     b = bev.contiguous()
     if out is None:
         out = torch.empty((B, H, W, Cout), dtype=torch.float32, device=bev.device)
-    ws = conv_workspace(B, H, W, bev.device) if workspace is None else workspace
+    ws = conv_workspace(B, H, W, bev.device, nnz_max) if workspace is None else workspace
     off = (-ws.data_ptr()) % 256
     sc = None if scale is None else scale.to(device=bev.device, dtype=torch.float32).contiguous()
     sh = None if shift is None else shift.to(device=bev.device, dtype=torch.float32).contiguous()

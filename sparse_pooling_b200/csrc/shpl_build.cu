@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(kThreads) shpl_pairs_kernel(PairsArgs a, int u
         const long long nnz = (long long)(s_excl & ((1ull << 31) - 1)) + tot_keep;
         a.counts[0] = (int)n_clip;
         a.counts[1] = (a.mode == kModeGenOnly) ? 0 : (int)nnz;
+        a.counts[5] = 0;                          // set by the finalize kernel when a stacked frame overruns the plan
         if (a.msize_out) { a.msize_out[0] = R; a.msize_out[1] = nnz; }
     }
 
@@ -377,6 +378,10 @@ __global__ void __launch_bounds__(kThreads) shpl_finalize_kernel(FinalArgs a, in
     }
     b -= nb_row + nb_pix;
     for (int j = b * kFinalKeys + threadIdx.x; j < min((b + 1) * kFinalKeys, n); j += kThreads) {
+        if (ebase + j >= a.plan.capacity) {       // stacked frames: the host only knows capacity >= this frame's n
+            a.counts[5] = 1;                      // nothing is written out of bounds; the caller sees the flag
+            continue;
+        }
         const unsigned long long ir = by_row[j];
         if ((unsigned)(ir >> 32) < (unsigned)a.plan.n_rows) {
             const unsigned k = (unsigned)ir;
@@ -424,8 +429,10 @@ int run_build(PairsArgs& pa, const shpl_plan* plan, const int32_t* entry_base_de
     SHPL_CUDA_OK(cudaMemsetAsync(workspace, 0, pa.ws.header_bytes, s));
     const long long tiles = (pa.n + kTile - 1) / kTile > 0 ? (pa.n + kTile - 1) / kTile : 1;
     const long long ptiles = (pa.n + kPairsTile - 1) / kPairsTile > 0 ? (pa.n + kPairsTile - 1) / kPairsTile : 1;
-    // the look-back spins on earlier CTAs: safe without an arrival ticket while every CTA is resident
-    const int use_ticket = ptiles > (long long)shpl::sm_count() * 4 ? 1 : 0;
+    // The look-back spins on earlier tiles, so tile ids are ALWAYS handed out by arrival (one atomicAdd per CTA on a
+    // header word the memset above cleared): CUDA gives no blockIdx-order dispatch guarantee, and these kernels run on
+    // side streams beside pooling kernels that fill the SMs -- a spinning high tile must never wait for an unscheduled low one.
+    const int use_ticket = 1;
     shpl_pairs_kernel<<<(unsigned)ptiles, kThreads, 0, s>>>(pa, use_ticket);
     shpl::count_launches(1);
     if (int rc = shpl::check_launch("shpl_pairs_kernel")) return rc;

@@ -13,13 +13,17 @@
 // dense kernel leaves the marked cells un-activated, and a small warp-per-cell kernel adds W_pooled . pooled there
 // (the pooled sums formed in the reference's entry order, like the pooling kernels do) and applies the epilogue.
 //
-// Dense kernel, one persistent CTA per SM, 6 warps:
-//   warp 4  TMA producer   halo tile [18 x 10 pixels x 32 ch] fp32 -> staging (2 stages)
-//   warps 0-3 workers      staging -> hi / lo operand planes ([chunk of 4 ch][halo pixel][16 B]: the K-major,
-//                          no-swizzle core-matrix layout; a tap (dy, dx) is just a different start address), and
-//                          the epilogue TMEM -> registers -> swizzled smem -> TMA store
-//   warp 5  MMA issuer     per tile 9 taps x 4 K-steps x {A_hi x [B_hi | B_lo] (N = 64), A_lo x B_hi (N = 32)}
-// Tile = 16 rows x 8 columns of output pixels = the 128 rows (TMEM lanes) of one MMA.
+// Dense kernel, one persistent CTA per SM, 10 warps, every stage double-buffered so that they all overlap:
+//   warp 8    TMA producer   halo tile [10 x 16 pixels x 32 ch] fp32 -> staging
+//   warps 4-7 conversion     staging -> hi / lo operand planes ([chunk of 4 ch][halo pixel][16 B]: the K-major,
+//                            no-swizzle core-matrix layout, so a row shift dy is just a different start address)
+//   warps 0-3 epilogue       TMEM -> registers (+ the dx shuffle-sum, scale / shift / ReLU) -> swizzled smem -> TMA store
+//   warp 9    MMA issuer     per tile 3 dy x 4 K-steps x {A_hi x [B_hi | B_lo] (N = 192), A_lo x B_hi (N = 96)}
+// The 128 rows of an MMA are 8 image rows x 16 HALO columns; the N dimension carries the three dx taps side by side
+// (and hi | lo of the weights), so one read of A serves three taps: the tensor core fetches its shared-memory operands
+// at only ~64-75 B/clk (measured, profiles/r2_conv_*), which -- not the math -- bounds this small-N problem.  The
+// epilogue adds the three dx partial sums of neighbouring halo columns (adjacent TMEM lanes = adjacent threads:
+// two shuffles per channel); the two halo columns of a tile produce no output (tile = 8 x 14 output pixels).
 #include <cuda.h>
 
 #include "shpl_common.cuh"
@@ -27,26 +31,32 @@
 namespace {
 
 constexpr int kC = 32;                     // dense input channels = output channels of this kernel
-constexpr int kTileY = 16, kTileX = 8;     // output pixels per tile (M = 128)
-constexpr int kHaloY = kTileY + 2, kHaloX = kTileX + 2, kHaloPix = kHaloY * kHaloX;   // 18 x 10 = 180
+constexpr int kTileY = 8, kTileX = 14;     // output pixels per tile
+constexpr int kHaloY = kTileY + 2, kHaloX = kTileX + 2, kHaloPix = kHaloY * kHaloX;   // 10 x 16 = 160
+static_assert(kHaloX == 16 && kTileY * kHaloX == 128, "M = 128 rows = 8 image rows x 16 halo columns");
 constexpr int kChunks = kC / 4;            // 16-byte channel chunks per pixel
 constexpr int kPlanePitch = (kHaloPix + 1) * 16;     // bytes between channel chunks (+16: bank spread)
 constexpr int kPlaneBytes = kChunks * kPlanePitch;   // one hi or lo plane set
 constexpr int kOpndBytes = 2 * kPlaneBytes;          // hi + lo
-constexpr int kStageBytes = kHaloPix * kC * 4;       // 23040: one TMA box
-constexpr int kWChunkBytes = 64 * 16;                // [n = 64 (hi 32 | lo 32)][4 ci]
-constexpr int kWTapBytes = kChunks * kWChunkBytes;   // 8192
-constexpr int kWBytes = 9 * kWTapBytes;              // 73728
-constexpr int kOutBytes = kTileY * kTileX * kC * 4;  // 16384
-constexpr int kConvThreads = 192;
-constexpr int kWorkers = 128;
-constexpr int kTmemCols = 128;             // 2 accumulator buffers x 64 columns
+constexpr int kStageBytes = kHaloPix * kC * 4;       // 20480: one TMA box
+constexpr int kNB = 192;                             // B rows per dy: [hi | lo][dx 0..2][co 32]
+constexpr int kWChunkBytes = kNB * 16;               // [n = 192][4 ci]
+constexpr int kWDyBytes = kChunks * kWChunkBytes;    // 24576
+constexpr int kWBytes = 3 * kWDyBytes;               // 73728
+constexpr int kWElems = kWBytes / 4;
+constexpr int kOutRows = kTileY * kTileX;            // 112
+constexpr int kOutBytes = 16384;                     // 112 x 128 B used
+static_assert(kOutRows * 128 <= kOutBytes, "output staging");
+constexpr int kWorkers = 256;
+constexpr int kConvThreads = kWorkers + 64;
+constexpr int kAccCols = kNB;                        // columns of one accumulator buffer
+constexpr int kTmemCols = 512;                       // 2 x 192 used
 
 // dynamic shared memory map (byte offsets from a 1024-aligned base)
-constexpr int kSmOut = 0;                                  // 16384, 1024-aligned (128B-swizzled TMA store source)
-constexpr int kSmStage = kSmOut + kOutBytes;               // 2 x 23040
+constexpr int kSmOut = 0;                                  // 1024-aligned (128B-swizzled TMA store source)
+constexpr int kSmStage = kSmOut + kOutBytes;               // 2 x 20480
 constexpr int kSmW = kSmStage + 2 * kStageBytes;           // 73728
-constexpr int kSmOpnd = kSmW + kWBytes;                    // 2 x 46336
+constexpr int kSmOpnd = kSmW + kWBytes;                    // 2 x 41216
 constexpr int kSmBar = kSmOpnd + 2 * kOpndBytes;           // mbarriers
 constexpr int kSmScale = kSmBar + 128;                     // scale[32], shift[32]
 constexpr int kSmEnd = kSmScale + 256;
@@ -138,22 +148,18 @@ __device__ __forceinline__ float to_tf32(float x) {
     return __uint_as_float(r);
 }
 
-#define SHPL_TMEM_LD32(taddr, v)                                                                                         \
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                               \
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                               \
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"               \
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),       \
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), \
-                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),            \
-                   "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),            \
-                   "=r"(v[30]), "=r"(v[31])                                                                              \
+#define SHPL_TMEM_LD8(taddr, v)                                                                               \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                  \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
                  : "r"(taddr))
 
 struct ConvArgs {
-    const float* wprep;          // [9][8][64][4] hi | lo weights in the B-operand layout (shpl_conv_prep_kernel)
+    const float* wprep;          // [3 dy][8 chunks][192 = (hi | lo) x dx x co][4 ci]: B-operand layout (shpl_conv_prep_kernel)
     const float* scale;          // [32] or NULL (1)
     const float* shift;          // [32] or NULL (0)
-    const uint32_t* active;      // bitmap over cells, or NULL: marked cells are stored un-activated (the sparse kernel finishes them)
+    const uint32_t* busy;        // bitmap of the cells that receive pooled features, or NULL (no pooled half)
+    const int* ptr;              // CSR offsets by cell: ptr[c] - ptr[0] = the Z row of a busy cell
+    const float* Z;              // [entries][9 taps][32]: W_pooled[tap]^T . pooled[cell], from the Z kernel
     int relu;
     int frames, H, W;
     int tiles_x, tiles_y, n_tiles;
@@ -175,17 +181,17 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar(BAR_STAGE_FULL + s), 1);
-            mbar_init(bar(BAR_STAGE_EMPTY + s), 4);
+            mbar_init(bar(BAR_STAGE_EMPTY + s), 4);      // the four conversion warps
             mbar_init(bar(BAR_OPND_FULL + s), 4);
             mbar_init(bar(BAR_OPND_EMPTY + s), 1);
             mbar_init(bar(BAR_ACC_FULL + s), 1);
-            mbar_init(bar(BAR_ACC_EMPTY + s), 4);
+            mbar_init(bar(BAR_ACC_EMPTY + s), 4);        // the four epilogue warps
         }
         mbar_init(bar(BAR_W), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 64) sc[tid] = tid < 32 ? (a.scale ? a.scale[tid] : 1.f) : (a.shift ? a.shift[tid - 32] : 0.f);
-    if (warp == 5) {
+    if (warp == 9) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -205,11 +211,11 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
         x0 = (t - ty * a.tiles_x) * kTileX;
     };
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ===== TMA producer =====
         if (lane == 0) {
             mbar_expect_tx(bar(BAR_W), kWBytes);
-            for (int t = 0; t < 9; ++t) bulk_load_1d(base + kSmW + t * kWTapBytes, reinterpret_cast<const uint8_t*>(a.wprep) + t * kWTapBytes, kWTapBytes, bar(BAR_W));
+            for (int t = 0; t < 3; ++t) bulk_load_1d(base + kSmW + t * kWDyBytes, reinterpret_cast<const uint8_t*>(a.wprep) + t * kWDyBytes, kWDyBytes, bar(BAR_W));
             for (int i = 0; i < n_mine; ++i) {
                 const int s = i & 1, u = i >> 1;
                 int f, y0, x0;
@@ -219,51 +225,57 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
                 tma_load_4d(base + kSmStage + s * kStageBytes, &map_in, bar(BAR_STAGE_FULL + s), 0, x0 - 1, y0 - 1, f);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ===== MMA issuer =====
         if (lane == 0) {
             mbar_wait(bar(BAR_W), 0);
-            constexpr uint32_t idesc64 = instr_desc(64), idesc32 = instr_desc(32);
+            constexpr uint32_t idesc_hi = instr_desc(kNB), idesc_lo = instr_desc(kNB / 2);
             for (int i = 0; i < n_mine; ++i) {
                 const int s = i & 1, u = i >> 1;
                 mbar_wait(bar(BAR_OPND_FULL + s), u & 1);
                 mbar_wait(bar(BAR_ACC_EMPTY + s), (u & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(s * 64);
+                const uint32_t d = tmem_base + (uint32_t)(s * kAccCols);
                 const uint32_t a_hi = base + kSmOpnd + s * kOpndBytes, a_lo = a_hi + kPlaneBytes;
                 const uint32_t w0 = base + kSmW;
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int dy = tap / 3, dx = tap % 3;
+                for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
                     for (int j = 0; j < kChunks / 2; ++j) {
-                        const uint32_t aoff = (uint32_t)((dy * kHaloX + dx) * 16 + 2 * j * kPlanePitch);
-                        const uint64_t bd = smem_desc(w0 + tap * kWTapBytes + 2 * j * kWChunkBytes, kWChunkBytes, 128);
-                        // A_hi x [B_hi | B_lo] -> columns 0..63 (the tile's first MMA initialises all of them)
-                        umma_tf32(d, smem_desc(a_hi + aoff, kPlanePitch, kHaloX * 16), bd, idesc64, (tap | j) != 0);
-                        // A_lo x B_hi -> columns 0..31
-                        umma_tf32(d, smem_desc(a_lo + aoff, kPlanePitch, kHaloX * 16), bd, idesc32, 1u);
+                        const uint32_t aoff = (uint32_t)(dy * kHaloX * 16 + 2 * j * kPlanePitch);
+                        const uint64_t bd = smem_desc(w0 + dy * kWDyBytes + 2 * j * kWChunkBytes, kWChunkBytes, 128);
+                        // A_hi x [B_hi | B_lo], three dx taps side by side -> all 192 columns (the tile's first MMA initialises them)
+                        umma_tf32(d, smem_desc(a_hi + aoff, kPlanePitch, 128), bd, idesc_hi, (dy | j) != 0);
+                        // A_lo x B_hi -> columns 0..95
+                        umma_tf32(d, smem_desc(a_lo + aoff, kPlanePitch, 128), bd, idesc_lo, 1u);
                     }
                 }
                 umma_commit(bar(BAR_OPND_EMPTY + s));
                 umma_commit(bar(BAR_ACC_FULL + s));
             }
         }
-    } else {
-        // ===== workers: conversion + epilogue =====
-        auto convert = [&](int i) {
+    } else if (warp >= 4) {
+        // ===== conversion warps (4..7): staging -> hi / lo operand planes =====
+        const int ctid = tid - 128;
+        for (int i = 0; i < n_mine; ++i) {
             const int s = i & 1, u = i >> 1;
             mbar_wait(bar(BAR_STAGE_FULL + s), u & 1);
             mbar_wait(bar(BAR_OPND_EMPTY + s), (u & 1) ^ 1);
             const uint8_t* st = gbase + kSmStage + s * kStageBytes;
             uint8_t* op = gbase + kSmOpnd + s * kOpndBytes;
-#pragma unroll 4
-            for (int item = tid; item < kHaloPix * kChunks; item += kWorkers) {
+            static_assert(kHaloPix * kChunks == 10 * 128, "ten items per conversion thread");
+#pragma unroll 5
+            for (int it = 0; it < 10; ++it) {
+                const int item = ctid + it * 128;
                 const int px = item >> 3, ck = item & 7;
                 const float4 v = *reinterpret_cast<const float4*>(st + px * (kC * 4) + ck * 16);
+                // hi = the tf32 the tensor core would read anyway (top 19 bits); lo = the exact remainder
                 float4 hi, lo;
-                hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
-                lo.x = to_tf32(v.x - hi.x); lo.y = to_tf32(v.y - hi.y); lo.z = to_tf32(v.z - hi.z); lo.w = to_tf32(v.w - hi.w);
+                hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
                 *reinterpret_cast<float4*>(op + ck * kPlanePitch + px * 16) = hi;
                 *reinterpret_cast<float4*>(op + kPlaneBytes + ck * kPlanePitch + px * 16) = lo;
             }
@@ -273,60 +285,104 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
                 mbar_arrive(bar(BAR_OPND_FULL + s));
                 mbar_arrive(bar(BAR_STAGE_EMPTY + s));
             }
-        };
-        auto epilogue = [&](int i) {
+        }
+    } else {
+        // ===== epilogue warps (0..3): TMEM -> registers -> swizzled smem -> TMA store =====
+        const int q = warp;                                  // TMEM lane quadrant
+        const int m = q * 32 + lane, yl = m >> 4, xq = m & 15;
+        const bool col_ok = xq >= 1 && xq <= kTileX;
+        for (int i = 0; i < n_mine; ++i) {
             const int s = i & 1, u = i >> 1;
             int f, y0, x0;
             tile_coord(i, f, y0, x0);
-            const int m = tid, gy = y0 + (m >> 3), gx = x0 + (m & 7);
-            bool raw_out = false;
-            if (a.active != nullptr && gy < a.H && gx < a.W) {
-                const long long cell = ((long long)f * a.H + gy) * a.W + gx;
-                raw_out = (__ldg(a.active + (cell >> 5)) >> (cell & 31)) & 1u;
+            // The pooled half: which of this pixel's nine neighbours receive pooled features, and where their Z rows are.
+            // The lookups (bitmap -> CSR offset) are issued now; their latency hides under the wait for the accumulators.
+            int zrow[9];
+            if (a.busy != nullptr) {
+                const int gy = y0 + yl, gx = x0 + xq - 1;
+                const bool px_ok = col_ok && gy < a.H && gx < a.W;
+                const int e_begin = __ldg(a.ptr);
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int yy = gy + t / 3 - 1, xx = gx + t % 3 - 1;
+                    zrow[t] = -1;
+                    if (px_ok && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
+                        const int nb = (f * a.H + yy) * a.W + xx;
+                        if ((__ldg(a.busy + (nb >> 5)) >> (nb & 31)) & 1u) zrow[t] = (__ldg(a.ptr + nb) - e_begin) * 9 + t;
+                    }
+                }
             }
             mbar_wait(bar(BAR_ACC_FULL + s), u & 1);
             tc_fence_after();
-            uint32_t r0[32], r1[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * 64);
-            SHPL_TMEM_LD32(taddr, r0);
-            SHPL_TMEM_LD32(taddr + 32, r1);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols);
+            float o[32];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int c0 = g * 8;
+                uint32_t h[3][8], l[3][8];
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    SHPL_TMEM_LD8(taddr + dx * 32 + c0, h[dx]);
+                    SHPL_TMEM_LD8(taddr + 96 + dx * 32 + c0, l[dx]);
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float t0 = __uint_as_float(h[0][c]) + __uint_as_float(l[0][c]);
+                    const float t1 = __uint_as_float(h[1][c]) + __uint_as_float(l[1][c]);
+                    const float t2 = __uint_as_float(h[2][c]) + __uint_as_float(l[2][c]);
+                    // output at halo column xq = tap dx=0 of column xq-1 + dx=1 of xq + dx=2 of xq+1
+                    o[c0 + c] = __shfl_up_sync(0xffffffffu, t0, 1) + t1 + __shfl_down_sync(0xffffffffu, t2, 1);
+                }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY + s));
-            float v[32];
+            if (a.busy != nullptr) {
+                // + sum over the busy neighbours, in tap order (a fixed order: deterministic), of their Z rows
+                unsigned any = 0u;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) any |= __ballot_sync(0xffffffffu, zrow[t] >= 0) ? (1u << t) : 0u;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    if (!((any >> t) & 1u)) continue;        // warp-uniform: nobody in this warp has a busy neighbour at tap t
+                    if (zrow[t] >= 0) {
+                        const float4* z = reinterpret_cast<const float4*>(a.Z + (size_t)zrow[t] * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 zv = __ldg(z + j);
+                            o[4 * j] += zv.x; o[4 * j + 1] += zv.y; o[4 * j + 2] += zv.z; o[4 * j + 3] += zv.w;
+                        }
+                    }
+                }
+            }
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-                float x = __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
-                if (!raw_out) {
-                    x = fmaf(x, sc[c], sc[32 + c]);
-                    if (a.relu) x = fmaxf(x, 0.f);
-                }
-                v[c] = x;
+                float x = fmaf(o[c], sc[c], sc[32 + c]);
+                if (a.relu) x = fmaxf(x, 0.f);
+                o[c] = x;
             }
             if (tid == 0) bulk_wait_read0();       // the previous tile's store has read the staging buffer
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            uint8_t* orow = gbase + kSmOut + m * 128;
+            if (col_ok) {
+                const int r = yl * kTileX + xq - 1;
+                uint8_t* orow = gbase + kSmOut + r * 128;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                *reinterpret_cast<float4*>(orow + ((j ^ (m & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(orow + ((j ^ (r & 7)) << 4)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
             fence_proxy_async();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (tid == 0) {
                 tma_store_4d(&map_out, base + kSmOut, 0, x0, y0, f);
                 bulk_commit();
             }
-        };
-        if (n_mine > 0) convert(0);
-        for (int i = 0; i < n_mine; ++i) {
-            if (i + 1 < n_mine) convert(i + 1);
-            epilogue(i);
         }
         if (tid == 0) bulk_wait0();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == 9) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
@@ -337,121 +393,268 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
 // transposed (input gradient, SAME padding, stride 1): B[n = ci][k = co] = W[8 - tap][ci_off + ci][co].
 __global__ void shpl_conv_prep_kernel(const float* __restrict__ w, int c_in_total, int c_out_total, int ci_off, int transposed,
                                       float* __restrict__ wprep) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // over [9][8][64][4]
-    if (i >= 9 * kChunks * 64 * 4) return;
-    const int e = i & 3, n = (i >> 2) & 63, ck = (i >> 8) & 7, tap = i >> 11;
-    const int k = ck * 4 + e, nn = n & 31;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // over [3 dy][8 chunks][192][4]
+    if (i >= kWElems) return;
+    const int e = i & 3, n = (i >> 2) % kNB, ck = (i / (kNB * 4)) % kChunks, dy = i / (kNB * 4 * kChunks);
+    const int part = n / 96, dx = (n % 96) / 32, nn = n & 31;
+    const int k = ck * 4 + e, tap = dy * 3 + dx;
     float x;
     if (!transposed) x = w[((size_t)tap * c_in_total + ci_off + k) * c_out_total + nn];
     else x = w[((size_t)(8 - tap) * c_in_total + ci_off + nn) * c_out_total + k];
     const float hi = to_tf32(x);
-    wprep[i] = n < 32 ? hi : to_tf32(x - hi);
+    wprep[i] = part == 0 ? hi : to_tf32(x - hi);
 }
 
 // ------------------------------------------------------------------------------------ sparse half
-// Marks the cells that receive pooled features (busy) and their 3x3 neighbourhoods (active) from the key-sorted
-// entry list; one thread per entry, the first entry of a cell does the work.
+// Marks the cells that receive pooled features in the `busy` bitmap, from the key-sorted entry list; one thread per
+// entry, the first entry of a cell sets the bit (atomicOr: order-independent, deterministic).
 __global__ void shpl_conv_mark_kernel(const int* __restrict__ ptr, const int* __restrict__ key, int n_rows, int nnz_max,
-                                      int H, int W, uint32_t* __restrict__ busy, uint32_t* __restrict__ active) {
+                                      uint32_t* __restrict__ busy) {
     const int e_begin = __ldg(ptr), e_end = __ldg(ptr + n_rows);
     const int e = e_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= e_end || e - e_begin >= nnz_max) return;
     const int r = __ldg(key + e);
     if (e > e_begin && __ldg(key + e - 1) == r) return;
     atomicOr(busy + (r >> 5), 1u << (r & 31));
-    const int f = r / (H * W), rem = r - f * (H * W), y = rem / W, x = rem - y * W;
-    for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int yy = y + dy, xx = x + dx;
-            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const int c = (f * H + yy) * W + xx;
-            atomicOr(active + (c >> 5), 1u << (c & 31));
-        }
 }
 
-struct SparseConvArgs {
-    const float* src;            // [n_src, C_s] gathered map
-    const int* ptr;              // CSR by destination cell
+// ---- Z[e][tap][co] = sum_ci pooled[cell(e)][ci] * W[tap][C_d + ci][co] for every cell that receives pooled features,
+// e = index of the cell's first CSR entry: what the cell contributes to each of its nine neighbours.  A small GEMM
+// [cells x C_s] . [C_s x 288]; the dense kernel's epilogue gathers the rows.
+struct ZArgs {
+    const float* src;
+    const int* ptr;
+    const int* key;
     const int* idx;
     const float* val;
-    const float* w;              // HWIO weights; the pooled channels start at ci_off
+    const float* w;              // FFMA form: the HWIO weights
+    const float* wprep;          // tensor-core form: the pooled channels' weights in the B-operand layout
     int c_in_total, c_out_total, ci_off, C_s;
-    const float* scale;
-    const float* shift;
-    int relu;
-    const uint32_t* busy;
-    const uint32_t* active;
-    int frames, H, W, n_words;
-    float* out;                  // [cells, 32]: holds the dense term (un-activated) for the marked cells
+    int n_rows, nnz_max;
+    float* Z;                    // [nnz_max][9][32]
 };
 
-// One warp per 32-cell word of the `active` bitmap (lane = output channel while a cell is processed):
-//   out = act(scale * (dense + sum_taps W_pooled[tap]^T . pooled[nbr]) + shift).
-// pooled[nbr] is formed like the pooling kernels form it: entries in stored order, separately rounded multiply and add.
-// The dependent loads of a cell (busy bits -> CSR offsets -> first entry -> gathered row) are issued side by side for
-// all nine taps by lanes 0..8, so a cell costs three round trips whatever the number of busy neighbours.
-constexpr int kSparseThreads = 512;
+// Tensor-core form (C_s = 32): a CTA takes 128 consecutive entries; row m of the MMA is entry e0 + m, holding the
+// pooled vector of its cell if the entry is the cell's first (entries in stored order, two roundings each -- the
+// pooling kernels' sum), zeros otherwise.  3xTF32 like the dense kernel: A_hi.B_hi + A_hi.B_lo + A_lo.B_hi into
+// 288 TMEM columns = [tap][co], the layout of a Z row.
+constexpr int kZtcThreads = 256;
+constexpr int kZtcPitch = 128 * 16 + 16;                 // bytes between channel chunks of the A planes
+constexpr int kZtcPlane = kChunks * kZtcPitch;
+constexpr int kZtcSmA = 0;                               // hi, lo planes
+constexpr int kZtcSmW = 2 * kZtcPlane;                   // 33024: 128-byte aligned (bulk-copy destination)
+constexpr int kZtcSmBar = kZtcSmW + kWBytes;
+constexpr int kZtcSmFlag = kZtcSmBar + 64;               // first-entry flags, one byte per row
+constexpr int kZtcSmem = kZtcSmFlag + 128 + 128;         // + slack for the 128-byte alignment of the base
+static_assert(kZtcSmW % 128 == 0 && kZtcSmBar % 8 == 0, "Z kernel smem alignment");
+constexpr int kZtcSmemRequest = kZtcSmem > 116 * 1024 ? kZtcSmem : 116 * 1024;   // > half an SM: one CTA (one 512-column TMEM allocation) per SM
 
-__global__ void __launch_bounds__(kSparseThreads) shpl_conv_sparse_kernel(SparseConvArgs a) {
-    extern __shared__ float wsm[];           // [9][C_s][32]
-    const int n_w = 9 * a.C_s * 32;
-    for (int i = threadIdx.x; i < n_w; i += blockDim.x) {
-        const int co = i & 31, ci = (i >> 5) % a.C_s, tap = (i >> 5) / a.C_s;
-        wsm[i] = a.w[((size_t)tap * a.c_in_total + a.ci_off + ci) * a.c_out_total + co];
+__global__ void __launch_bounds__(kZtcThreads, 1) shpl_conv_z_tc_kernel(ZArgs a) {
+    extern __shared__ uint8_t z_smem_raw[];
+    __shared__ uint32_t tmem_slot;
+    const int e_begin = __ldg(a.ptr), e_end = min(__ldg(a.ptr + a.n_rows), e_begin + a.nnz_max);
+    const int e0 = e_begin + (int)blockIdx.x * 128;
+    if (e0 >= e_end) return;                              // whole CTA: nnz_max is only an upper bound
+    const uint32_t raw = smem_u32(z_smem_raw);
+    const uint32_t base = (raw + 127u) & ~127u;
+    uint8_t* gbase = z_smem_raw + (base - raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    const uint32_t bar_w = base + kZtcSmBar, bar_mma = bar_w + 8;
+    uint8_t* flags = gbase + kZtcSmFlag;
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar_w, kWBytes);
+        for (int t = 0; t < 3; ++t) bulk_load_1d(base + kZtcSmW + t * kWDyBytes, reinterpret_cast<const uint8_t*>(a.wprep) + t * kWDyBytes, kWDyBytes, bar_w);
     }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
-    const float s_c = a.scale ? a.scale[lane] : 1.f, b_c = a.shift ? a.shift[lane] : 0.f;
-    const int HW = a.H * a.W;
-    const int t_dy = lane / 3 - 1, t_dx = lane % 3 - 1;          // lanes 0..8: the tap this lane looks after
-    for (int word = blockIdx.x * warps + warp; word < a.n_words; word += gridDim.x * warps) {
-        uint32_t bits = __ldg(a.active + word);
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const int c = word * 32 + b;
-            const int f = c / HW, rem = c - f * HW, y = rem / a.W, x = rem - y * a.W;
-            const float o_in = a.out[(size_t)c * 32 + lane];
-            // lanes 0..8: is the neighbour of tap `lane` busy, and where are its entries
-            int beg = 0, end = 0, p0 = 0;
-            float w0 = 0.f;
-            if (lane < 9) {
-                const int yy = y + t_dy, xx = x + t_dx;
-                if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
-                    const int nb = (f * a.H + yy) * a.W + xx;
-                    if ((__ldg(a.busy + (nb >> 5)) >> (nb & 31)) & 1u) {
-                        beg = __ldg(a.ptr + nb);
-                        end = __ldg(a.ptr + nb + 1);
-                        p0 = __ldg(a.idx + beg);
-                        w0 = __ldg(a.val + beg);
-                    }
-                }
-            }
-            const uint32_t taps = __ballot_sync(0xffffffffu, end > beg) & 0x1ffu;
-            float acc = 0.f;
-            for (int c0 = 0; c0 < a.C_s; c0 += 32) {
-                float xrow[9];
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // ---- gather: warp w fills rows 16w .. 16w+15 (entries ew .. ew+15); lane = channel
+    {
+        const int ew = e0 + warp * 16;
+        int k_l = ew + lane, key_l = -1, idx_l = 0, end_l = 0;
+        float val_l = 0.f;
+        bool first_l = false;
+        if (lane < 16 && k_l < e_end) {
+            key_l = __ldg(a.key + k_l);
+            idx_l = __ldg(a.idx + k_l);
+            val_l = __ldg(a.val + k_l);
+            first_l = (k_l == e_begin) || (__ldg(a.key + k_l - 1) != key_l);
+            if (first_l) end_l = __ldg(a.ptr + key_l + 1);
+        }
+        float x[16];
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {          // the first entry of every busy tap: all gathers in flight together
-                    const int p = __shfl_sync(0xffffffffu, p0, t);
-                    xrow[t] = ((taps >> t) & 1u) ? __ldg(a.src + (size_t)p * a.C_s + c0 + lane) : 0.f;
+        for (int j = 0; j < 16; ++j) {                    // the 16 gathered rows in flight together
+            const int p = __shfl_sync(0xffffffffu, idx_l, j);
+            x[j] = (ew + j < e_end) ? __ldg(a.src + (size_t)p * 32 + lane) : 0.f;
+        }
+        const unsigned firsts = __ballot_sync(0xffffffffu, first_l) & 0xffffu;
+        uint8_t* hi_p = gbase + kZtcSmA + (lane >> 2) * kZtcPitch + (lane & 3) * 4;
+        uint8_t* lo_p = hi_p + kZtcPlane;
+        float acc = 0.f;
+        int open = -1, open_end = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const bool fj = (firsts >> j) & 1u;
+            if (fj) {
+                if (open >= 0) {                          // the previous cell ended inside the window
+                    const float h = __uint_as_float(__float_as_uint(acc) & 0xffffe000u);
+                    *reinterpret_cast<float*>(hi_p + (warp * 16 + open) * 16) = h;
+                    *reinterpret_cast<float*>(lo_p + (warp * 16 + open) * 16) = acc - h;
                 }
+                open = j;
+                open_end = __shfl_sync(0xffffffffu, end_l, j);
+                acc = 0.f;
+            }
+            if (open >= 0 && ew + j < open_end)
+                acc = __fadd_rn(acc, __fmul_rn(__shfl_sync(0xffffffffu, val_l, j), x[j]));
+            if (!fj) {                                    // not a first entry: an all-zero row
+                *reinterpret_cast<float*>(hi_p + (warp * 16 + j) * 16) = 0.f;
+                *reinterpret_cast<float*>(lo_p + (warp * 16 + j) * 16) = 0.f;
+            }
+        }
+        if (open >= 0) {
+            for (int k = ew + 16; k < open_end; ++k)      // the last cell runs on past the window
+                acc = __fadd_rn(acc, __fmul_rn(__ldg(a.val + k), __ldg(a.src + (size_t)__ldg(a.idx + k) * 32 + lane)));
+            const float h = __uint_as_float(__float_as_uint(acc) & 0xffffe000u);
+            *reinterpret_cast<float*>(hi_p + (warp * 16 + open) * 16) = h;
+            *reinterpret_cast<float*>(lo_p + (warp * 16 + open) * 16) = acc - h;
+        }
+        if (lane < 16) flags[warp * 16 + lane] = first_l ? 1 : 0;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (tid == 0) {
+        mbar_wait(bar_w, 0);
+        constexpr uint32_t idesc = instr_desc(96);
+        const uint32_t a_hi = base + kZtcSmA, a_lo = a_hi + kZtcPlane, w0 = base + kZtcSmW;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+            for (int j = 0; j < kChunks / 2; ++j) {
+                const uint32_t aoff = (uint32_t)(2 * j * kZtcPitch);
+                const uint32_t wb = w0 + dy * kWDyBytes + 2 * j * kWChunkBytes;
+                const uint64_t b_hi = smem_desc(wb, kWChunkBytes, 128), b_lo = smem_desc(wb + 96 * 16, kWChunkBytes, 128);
+                const uint32_t d = tmem + (uint32_t)(dy * 96);
+                umma_tf32(d, smem_desc(a_hi + aoff, kZtcPitch, 128), b_hi, idesc, j != 0);
+                umma_tf32(d, smem_desc(a_hi + aoff, kZtcPitch, 128), b_lo, idesc, 1u);
+                umma_tf32(d, smem_desc(a_lo + aoff, kZtcPitch, 128), b_hi, idesc, 1u);
+            }
+        }
+        umma_commit(bar_mma);
+    }
+    // ---- epilogue: rows that are first entries go out as Z rows (1152 contiguous bytes per row)
+    mbar_wait(bar_mma, 0);
+    tc_fence_after();
+    {
+        const int q = warp & 3, half = warp >> 2;
+        const int m = q * 32 + lane;
+        const bool on = flags[m] != 0;
+        float* zrow = a.Z + (size_t)(e0 - e_begin + m) * 288;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+#pragma unroll 3
+        for (int cc = 0; cc < 18; ++cc) {
+            const int col = half * 144 + cc * 8;
+            uint32_t v[8];
+            SHPL_TMEM_LD8(taddr + col, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (on) {
+                *reinterpret_cast<float4*>(zrow + col) = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+                *reinterpret_cast<float4*>(zrow + col + 4) = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+    }
+}
+
+// FFMA form (any C_s that is a multiple of 32): a warp takes a window of 4 entries and owns the cells whose first
+// entry lies in it; the four pooled vectors go through shared memory ([ci][4]: one broadcast LDS.128 per ci serves four
+// cells and nine taps), lane = output channel, 36 accumulators; the weights are read through L1.
+constexpr int kZThreads = 256;
+constexpr int kZWindow = 4;
+
+__global__ void __launch_bounds__(kZThreads, 3) shpl_conv_z_kernel(ZArgs a) {
+    __shared__ float4 pbuf_all[kZThreads / 32][32];      // per warp [32 ci][4 cells] pooled values
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    float4* pbuf = pbuf_all[warp];
+    const int e_begin = __ldg(a.ptr), e_end = min(__ldg(a.ptr + a.n_rows), e_begin + a.nnz_max);
+    const int n_windows = (e_end - e_begin + kZWindow - 1) / kZWindow;
+    const float* wbase = a.w + (size_t)a.ci_off * a.c_out_total + lane;
+    const size_t tap_stride = (size_t)a.c_in_total * a.c_out_total;
+    for (int win = blockIdx.x * warps + warp; win < n_windows; win += gridDim.x * warps) {
+        const int e0 = e_begin + win * kZWindow;
+        int my_row = -1, my_end = 0;
+        bool first = false;
+        if (lane < kZWindow && e0 + lane < e_end) {
+            my_row = __ldg(a.key + e0 + lane);
+            first = (e0 + lane == e_begin) || (__ldg(a.key + e0 + lane - 1) != my_row);
+            if (first) my_end = __ldg(a.ptr + my_row + 1);
+        }
+        uint32_t firsts = __ballot_sync(0xffffffffu, first);
+        if (!firsts) continue;
+        int fe[4], fend[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            fe[c] = -1;
+            fend[c] = 0;
+            if (firsts) {
+                const int l = __ffs(firsts) - 1;
+                firsts &= firsts - 1;
+                fe[c] = e0 + l;
+                fend[c] = __shfl_sync(0xffffffffu, my_end, l);
+            }
+        }
+        float acc[9][4];
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[t][c] = 0.f;
+        for (int c0 = 0; c0 < a.C_s; c0 += 32) {
+            float p[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {    // pooled[cell c][c0 + lane]: entries in stored order, two roundings each
+                p[c] = 0.f;
+                if (fe[c] >= 0)
+                    for (int k = fe[c]; k < fend[c]; ++k)
+                        p[c] = __fadd_rn(p[c], __fmul_rn(__ldg(a.val + k), __ldg(a.src + (size_t)__ldg(a.idx + k) * a.C_s + c0 + lane)));
+            }
+            __syncwarp();
+            pbuf[lane] = make_float4(p[0], p[1], p[2], p[3]);
+            __syncwarp();
+            const float* wt = wbase + (size_t)c0 * a.c_out_total;
+#pragma unroll 2
+            for (int ci = 0; ci < 32; ++ci) {
+                const float4 pv = pbuf[ci];
+                float wv[9];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) wv[t] = __ldg(wt + t * tap_stride + (size_t)ci * a.c_out_total);
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
-                    if (!((taps >> t) & 1u)) continue;   // warp-uniform
-                    const int tb = __shfl_sync(0xffffffffu, beg, t), te = __shfl_sync(0xffffffffu, end, t);
-                    float p = __fadd_rn(0.f, __fmul_rn(__shfl_sync(0xffffffffu, w0, t), xrow[t]));
-                    for (int k = tb + 1; k < te; ++k)
-                        p = __fadd_rn(p, __fmul_rn(__ldg(a.val + k), __ldg(a.src + (size_t)__ldg(a.idx + k) * a.C_s + c0 + lane)));
-                    const float* wt = wsm + ((size_t)t * a.C_s + c0) * 32 + lane;
-#pragma unroll 8
-                    for (int ci = 0; ci < 32; ++ci) acc = fmaf(__shfl_sync(0xffffffffu, p, ci), wt[ci * 32], acc);
+                    acc[t][0] = fmaf(pv.x, wv[t], acc[t][0]);
+                    acc[t][1] = fmaf(pv.y, wv[t], acc[t][1]);
+                    acc[t][2] = fmaf(pv.z, wv[t], acc[t][2]);
+                    acc[t][3] = fmaf(pv.w, wv[t], acc[t][3]);
                 }
             }
-            float o = fmaf(o_in + acc, s_c, b_c);
-            if (a.relu) o = fmaxf(o, 0.f);
-            a.out[(size_t)c * 32 + lane] = o;
         }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (fe[c] >= 0) {
+                float* z = a.Z + (size_t)(fe[c] - e_begin) * 288 + lane;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) z[t * 32] = acc[t][c];
+            }
     }
 }
 
@@ -489,27 +692,30 @@ int make_map(CUtensorMap* m, const float* base, int frames, int H, int W, int pi
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct ConvWorkspace {
-    float* wprep;
+    float* wprep;       // dense channels' weights, B-operand layout
+    float* wprep_p;     // pooled channels' weights, B-operand layout (tensor-core Z kernel)
     uint32_t* busy;
-    uint32_t* active;
+    float* Z;           // [nnz_max][9][32]
     size_t words;
     size_t bytes;
 };
 
-ConvWorkspace carve(void* ws, long long cells) {
+ConvWorkspace carve(void* ws, long long cells, long long nnz_max) {
     ConvWorkspace c;
     c.words = (size_t)((cells + 31) / 32);
     const size_t bm = align_up(c.words * 4, 256);
     uint8_t* p = static_cast<uint8_t*>(ws);
     c.wprep = reinterpret_cast<float*>(p);
-    c.busy = reinterpret_cast<uint32_t*>(p + kWBytes);
-    c.active = reinterpret_cast<uint32_t*>(p + kWBytes + bm);
-    c.bytes = kWBytes + 2 * bm;
+    c.wprep_p = reinterpret_cast<float*>(p + kWBytes);
+    c.busy = reinterpret_cast<uint32_t*>(p + 2 * kWBytes);
+    c.bytes = 2 * kWBytes + bm;
+    c.Z = reinterpret_cast<float*>(p + c.bytes);
+    c.bytes += align_up((size_t)(nnz_max > 0 ? nnz_max : 0) * 288 * sizeof(float), 256);
     return c;
 }
 
 int launch_dense(const float* in, int in_pitch, float* out, const float* wprep, const float* scale, const float* shift, int relu,
-                 const uint32_t* active, int frames, int H, int W, cudaStream_t s) {
+                 const uint32_t* busy, const int* ptr, const float* Z, int frames, int H, int W, cudaStream_t s) {
     CUtensorMap map_in, map_out;
     if (int rc = make_map(&map_in, in, frames, H, W, in_pitch, kHaloY, kHaloX, false)) return rc;
     if (int rc = make_map(&map_out, out, frames, H, W, kC, kTileY, kTileX, true)) return rc;
@@ -517,7 +723,9 @@ int launch_dense(const float* in, int in_pitch, float* out, const float* wprep, 
     a.wprep = wprep;
     a.scale = scale;
     a.shift = shift;
-    a.active = active;
+    a.busy = busy;
+    a.ptr = ptr;
+    a.Z = Z;
     a.relu = relu;
     a.frames = frames;
     a.H = H;
@@ -538,9 +746,9 @@ int launch_dense(const float* in, int in_pitch, float* out, const float* wprep, 
 
 }  // namespace
 
-extern "C" size_t shpl_conv3x3_workspace_bytes(int32_t frames, int32_t H, int32_t W) {
-    if (frames <= 0 || H <= 0 || W <= 0) return 0;
-    return carve(nullptr, (long long)frames * H * W).bytes;
+extern "C" size_t shpl_conv3x3_workspace_bytes(int32_t frames, int32_t H, int32_t W, int32_t nnz_max) {
+    if (frames <= 0 || H <= 0 || W <= 0 || nnz_max < 0) return 0;
+    return carve(nullptr, (long long)frames * H * W, nnz_max).bytes;
 }
 
 extern "C" int shpl_pool_conv3x3_forward(const float* dst, const float* src, const int32_t* ptr, const int32_t* key,
@@ -559,56 +767,57 @@ extern "C" int shpl_pool_conv3x3_forward(const float* dst, const float* src, con
     SHPL_REQUIRE(shpl::aligned(dst, 16) && shpl::aligned(out, 16) && shpl::aligned(workspace, 256), SHPL_ERR_INVALID_ARGUMENT,
                  "shpl_pool_conv3x3_forward: dst / out must be 16-byte aligned, workspace 256-byte aligned");
     const long long cells = (long long)frames * H * W;
-    const ConvWorkspace c = carve(workspace, cells);
+    const ConvWorkspace c = carve(workspace, cells, C_s > 0 ? nnz_max : 0);
     SHPL_REQUIRE(workspace_bytes >= c.bytes, SHPL_ERR_WORKSPACE_TOO_SMALL, "shpl_pool_conv3x3_forward: workspace %zu < %zu bytes",
                  workspace_bytes, c.bytes);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int c_in_total = C_d + C_s;
-    shpl_conv_prep_kernel<<<(9 * kChunks * 64 * 4 + 255) / 256, 256, 0, s>>>(weight, c_in_total, C_out, 0, 0, c.wprep);
+    shpl_conv_prep_kernel<<<(kWElems + 255) / 256, 256, 0, s>>>(weight, c_in_total, C_out, 0, 0, c.wprep);
     shpl::count_launches(1);
     if (int rc = shpl::check_launch("shpl_conv_prep_kernel")) return rc;
     const bool sparse = C_s > 0 && nnz_max > 0;
     if (sparse) {
-        SHPL_CUDA_OK(cudaMemsetAsync(c.busy, 0, (size_t)(reinterpret_cast<uint8_t*>(c.active) - reinterpret_cast<uint8_t*>(c.busy)) + c.words * 4, s));
-        shpl_conv_mark_kernel<<<(nnz_max + 255) / 256, 256, 0, s>>>(ptr, key, (int)cells, nnz_max, H, W, c.busy, c.active);
+        SHPL_CUDA_OK(cudaMemsetAsync(c.busy, 0, c.words * 4, s));
+        shpl_conv_mark_kernel<<<(nnz_max + 255) / 256, 256, 0, s>>>(ptr, key, (int)cells, nnz_max, c.busy);
         shpl::count_launches(1);
         if (int rc = shpl::check_launch("shpl_conv_mark_kernel")) return rc;
-    }
-    if (int rc = launch_dense(dst, C_d, out, c.wprep, scale, shift, relu, sparse ? c.active : nullptr, frames, H, W, s)) return rc;
-    if (sparse) {
-        SparseConvArgs sa{};
-        sa.src = src;
-        sa.ptr = ptr;
-        sa.idx = idx;
-        sa.val = val;
-        sa.w = weight;
-        sa.c_in_total = c_in_total;
-        sa.c_out_total = C_out;
-        sa.ci_off = C_d;
-        sa.C_s = C_s;
-        sa.scale = scale;
-        sa.shift = shift;
-        sa.relu = relu;
-        sa.busy = c.busy;
-        sa.active = c.active;
-        sa.frames = frames;
-        sa.H = H;
-        sa.W = W;
-        sa.n_words = (int)c.words;
-        sa.out = out;
-        const size_t smem = (size_t)9 * C_s * 32 * sizeof(float);
-        static bool attr_set = false;
-        if (smem > 48 * 1024 && !attr_set) {
-            SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_conv_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 64 * 32 * 4));
-            attr_set = true;
+        ZArgs za{};
+        za.src = src;
+        za.ptr = ptr;
+        za.key = key;
+        za.idx = idx;
+        za.val = val;
+        za.w = weight;
+        za.wprep = c.wprep_p;
+        za.c_in_total = c_in_total;
+        za.c_out_total = C_out;
+        za.ci_off = C_d;
+        za.C_s = C_s;
+        za.n_rows = (int)cells;
+        za.nnz_max = nnz_max;
+        za.Z = c.Z;
+        if (C_s == kC) {
+            shpl_conv_prep_kernel<<<(kWElems + 255) / 256, 256, 0, s>>>(weight, c_in_total, C_out, C_d, 0, c.wprep_p);
+            shpl::count_launches(1);
+            if (int rc = shpl::check_launch("shpl_conv_prep_kernel")) return rc;
+            static bool z_attr = false;
+            if (!z_attr) {
+                SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_conv_z_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kZtcSmemRequest));
+                z_attr = true;
+            }
+            shpl_conv_z_tc_kernel<<<(nnz_max + 127) / 128, kZtcThreads, kZtcSmemRequest, s>>>(za);
+            shpl::count_launches(1);
+            if (int rc = shpl::check_launch("shpl_conv_z_tc_kernel")) return rc;
+        } else {
+            const int windows = (nnz_max + kZWindow - 1) / kZWindow;
+            int zgrid = (windows + kZThreads / 32 - 1) / (kZThreads / 32);
+            const int zcap = shpl::sm_count() * 6;
+            if (zgrid > zcap) zgrid = zcap;
+            shpl_conv_z_kernel<<<zgrid, kZThreads, 0, s>>>(za);
+            shpl::count_launches(1);
+            if (int rc = shpl::check_launch("shpl_conv_z_kernel")) return rc;
         }
-        constexpr int kW = kSparseThreads / 32;
-        int grid = ((int)c.words + kW - 1) / kW;
-        const int cap = shpl::sm_count() * 4;
-        if (grid > cap) grid = cap;
-        shpl_conv_sparse_kernel<<<grid, kSparseThreads, smem, s>>>(sa);
-        shpl::count_launches(1);
-        if (int rc = shpl::check_launch("shpl_conv_sparse_kernel")) return rc;
     }
+    if (int rc = launch_dense(dst, C_d, out, c.wprep, scale, shift, relu, sparse ? c.busy : nullptr, ptr, c.Z, frames, H, W, s)) return rc;
     return SHPL_OK;
 }

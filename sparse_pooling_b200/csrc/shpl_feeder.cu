@@ -451,7 +451,7 @@ extern "C" int shpl_bev_slices(const double* points, int64_t coord_stride, int64
     ea.g = g;
     ea.ws = w;
     const int n_tiles = (g.S + 1) * g.tiles_per_plane;
-    ea.use_ticket = n_tiles > shpl::sm_count() * 2 ? 1 : 0;
+    ea.use_ticket = 1;      // always order the look-back by arrival (no blockIdx-order dispatch guarantee; see shpl_build.cu)
     ea.cap = capacity;
     ea.vox_out = reinterpret_cast<long long*>(voxel_indices_out);
     ea.pts_out = unique_pts_out;
@@ -605,7 +605,7 @@ extern "C" int shpl_lidar_to_cam(const float* velo_xyzi, int64_t N, const double
     a.counts = counts;
     SHPL_CUDA_OK(cudaMemsetAsync(workspace, 0, shpl_lidar_workspace_bytes(N), s));
     const long long tiles = (N + kThreads - 1) / kThreads > 0 ? (N + kThreads - 1) / kThreads : 1;
-    a.use_ticket = tiles > (long long)shpl::sm_count() * 4 ? 1 : 0;
+    a.use_ticket = 1;       // always order the look-back by arrival
     shpl_lidar_to_cam_kernel<<<(unsigned)tiles, kThreads, 0, s>>>(a);
     shpl::count_launches(1);
     return shpl::check_launch("shpl_lidar_to_cam_kernel");

@@ -368,7 +368,7 @@ extern "C" int shpl_mv3d_voxelize(const double* points, const int64_t* img_index
     SHPL_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * 8, s));
     const long long ptiles = (n + kPairsTile - 1) / kPairsTile > 0 ? (n + kPairsTile - 1) / kPairsTile : 1;
     const long long tiles = (n + kTile - 1) / kTile > 0 ? (n + kTile - 1) / kTile : 1;
-    a.use_ticket = ptiles > (long long)shpl::sm_count() * 4 ? 1 : 0;
+    a.use_ticket = 1;       // always order the look-back by arrival
     shpl_mv3d_cells_kernel<<<(unsigned)ptiles, kThreads, 0, s>>>(a);
     shpl::count_launches(1);
     if (int rc = shpl::check_launch("shpl_mv3d_cells_kernel")) return rc;

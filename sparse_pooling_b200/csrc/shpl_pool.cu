@@ -1197,89 +1197,38 @@ struct JobSpec {            // in floats / cells, before the vector width is cho
     int heavy_len = 0;
 };
 
-// resident CTAs per SM of the narrow kernel instance (occupancy query, cached); SHPL_NARROW_CTAS_PER_SM overrides
-// it for experiments
-int narrow_ctas_per_sm(int w, bool add) {
-    static int cached[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-    static int env = 0;
-    static bool read_env = false;
-    if (!read_env) {
-        read_env = true;
-        const char* e = getenv("SHPL_NARROW_CTAS_PER_SM");
-        env = e ? atoi(e) : 0;      // > 0: that many; < 0 (e.g. -1): what the occupancy query says; unset: 8
-    }
-    if (env > 0) return env;
-    if (env == 0) return 8;
-    const int wi = w == 4 ? 2 : (w == 2 ? 1 : 0);
-    int& c = cached[wi][add ? 1 : 0];
-    if (c == 0) {
-        int n = 0;
-        cudaError_t e;
-        if (w == 4 && add) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shpl_pool_narrow_kernel<4, true>, kThreads, 0);
-        else if (w == 4) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shpl_pool_narrow_kernel<4, false>, kThreads, 0);
-        else if (w == 2 && add) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shpl_pool_narrow_kernel<2, true>, kThreads, 0);
-        else if (w == 2) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shpl_pool_narrow_kernel<2, false>, kThreads, 0);
-        else if (add) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shpl_pool_narrow_kernel<1, true>, kThreads, 0);
-        else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, shpl_pool_narrow_kernel<1, false>, kThreads, 0);
-        c = (e == cudaSuccess && n > 0) ? n : SHPL_NARROW_MIN_CTAS;
-    }
-    return c;
-}
+// Tuning constants.  The product library is stateless: every value below is a compile-time constant (the measured
+// optimum).  Only a build with -DSHPL_EXPERIMENT (make exp -> libshpl_exp.so, used by tools/ for A/B
+// runs through SHPL_LIB) reads the environment variable of the same name instead, once per process.
+#ifdef SHPL_EXPERIMENT
+#define SHPL_KNOB(name, dflt)                                   \
+    ([]() -> int {                                              \
+        static const int v = []() {                             \
+            const char* e = getenv(name);                       \
+            return e ? atoi(e) : (dflt);                        \
+        }();                                                    \
+        return v;                                               \
+    }())
+#else
+#define SHPL_KNOB(name, dflt) (dflt)
+#endif
 
-int entry_chunk_env() {      // entries per warp in the entry CTAs (experiment knob)
-    static int env = -1;
-    if (env < 0) {
-        const char* e = getenv("SHPL_ENTRY_CHUNK");
-        env = (e && atoi(e) > 0) ? atoi(e) : 0;
-    }
-    return env;
-}
-
-int packed_env() {
-    static int env = -1;
-    if (env < 0) {
-        const char* e = getenv("SHPL_PACKED");
-        env = e ? atoi(e) : 1;
-    }
-    return env;
-}
-
-int packed_chunk_env() {     // entries per warp with the packed entry walk
-    static int env = -1;
-    if (env < 0) {
-        const char* e = getenv("SHPL_PACKED_CHUNK");
-        env = (e && atoi(e) > 0) ? atoi(e) : 64;
-    }
-    return env;
-}
-
-int stream_ctas_per_sm() {
-    static int env = -1;
-    if (env < 0) {
-        const char* e = getenv("SHPL_STREAM_CTAS_PER_SM");
-        env = (e && atoi(e) > 0) ? atoi(e) : 6;
-    }
-    return env;
-}
-
-int wide_stream_env() {
-    static int env = -1;
-    if (env < 0) {
-        const char* e = getenv("SHPL_WIDE_STREAM");
-        env = e ? atoi(e) : 2;      // 0: the CTA-tiled wide kernel; 1: entry + stream kernel up to 64 vectors per cell; 2: always
-    }
-    return env;
-}
+// grid of the narrow kernel: 8 CTAs per SM although only 3 are resident (see launch_jobs)
+int narrow_ctas_per_sm() { const int v = SHPL_KNOB("SHPL_NARROW_CTAS_PER_SM", 8); return v > 0 ? v : 8; }
+// entries per warp in the entry CTAs (0: the per-width default)
+int entry_chunk_knob() { const int v = SHPL_KNOB("SHPL_ENTRY_CHUNK", 0); return v > 0 ? v : 0; }
+int packed_knob() { return SHPL_KNOB("SHPL_PACKED", 1); }
+// entries per warp with the packed entry walk
+int packed_chunk_knob() { const int v = SHPL_KNOB("SHPL_PACKED_CHUNK", 64); return v > 0 ? v : 64; }
+int stream_ctas_per_sm() { const int v = SHPL_KNOB("SHPL_STREAM_CTAS_PER_SM", 6); return v > 0 ? v : 6; }
+// 0: the CTA-tiled wide kernel; 1: entry + stream kernel up to 64 vectors per cell; 2: always
+int wide_stream_knob() { return SHPL_KNOB("SHPL_WIDE_STREAM", 2); }
 
 // Sparse regime of the narrow channel counts: every pooled job comes with its key array and the entries are few
-// next to the cells (KITTI stride 1: 20 k entries for 560 k cells).  SHPL_SPARSE=0 forces the one-kernel path.
+// next to the cells (KITTI stride 1: 20 k entries for 560 k cells).
 bool sparse_regime(const PoolArgs& a, const JobSpec* const* spec) {
-    static int env = -1;
-    if (env < 0) {
-        const char* e = getenv("SHPL_SPARSE");
-        env = e ? atoi(e) : 1;
-    }
-    if (!env) return false;
+    const int mode = SHPL_KNOB("SHPL_SPARSE", 1);      // 0: never, 1: by density, 2: always (experiments)
+    if (!mode) return false;
     long long nnz = 0, cells = 0;
     for (int i = 0; i < a.n_jobs; ++i) {
         const Job& o = a.job[i];
@@ -1289,7 +1238,7 @@ bool sparse_regime(const PoolArgs& a, const JobSpec* const* spec) {
         }
         cells += o.n_cells;
     }
-    return env > 1 || nnz * 4 <= cells;      // SHPL_SPARSE=2: always (experiments)
+    return mode > 1 || nnz * 4 <= cells;
 }
 
 int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* who) {
@@ -1335,7 +1284,7 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
     bool wide = max_vs >= 32;
     bool stream_split = !wide && sparse_regime(a, src_spec);
     bool packed = false;
-    if (!wide && !stream_split && packed_env()) {
+    if (!wide && !stream_split && packed_knob()) {
         // dense regime (many entries per cell on average): the entry + stream kernel with the PACKED entry walk, when
         // every pooled job has its key array and a power-of-two number of vectors per cell <= 16
         bool ok = true;
@@ -1348,7 +1297,7 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
     // Wide jobs take the entry + stream kernel too whenever their key arrays are there (measured on B200: full scan
     // C = 128 forward 218 -> 165 us, RetinaNet P2 24.0 -> 20.4 us, the bench step 142 -> 131 us); the CTA-tiled
     // shpl_pool_wide_kernel stays as the path without key arrays.
-    if (wide && wide_stream_env() && (max_vs <= 64 || wide_stream_env() > 1)) {
+    if (wide && wide_stream_knob() && (max_vs <= 64 || wide_stream_knob() > 1)) {
         bool keys = true;
         for (int i = 0; i < a.n_jobs; ++i) keys = keys && (a.job[i].vs == 0 || a.job[i].key != nullptr);
         if (keys) {
@@ -1401,10 +1350,10 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
             o.stream_ctas = (int)c;
             // entries per warp: 16 measured best for rows up to 1 KB (bench step 130 -> 123 us against 8; 24 gains 2 % more
             // there but hurts skewed maps); 3 KB rows (MV3D, C = 768) want the shorter chains of 8
-            o.entry_chunk = entry_chunk_env() > 0 ? entry_chunk_env() : (o.vs * w > 256 ? 8 : 16);
+            o.entry_chunk = entry_chunk_knob() > 0 ? entry_chunk_knob() : (o.vs * w > 256 ? 8 : 16);
             o.packed = packed ? 1 : 0;
             o.long_len = packed ? 512 : kLongRow;     // the packed walk hands a row over at ~60 cycles per entry: fine up to 512
-            if (packed && o.vs > 0) o.entry_chunk = packed_chunk_env();
+            if (packed && o.vs > 0) o.entry_chunk = packed_chunk_knob();
             o.entry_ctas = o.vs > 0 ? (src_spec[i]->nnz_max + o.entry_chunk * kWarps - 1) / (o.entry_chunk * kWarps) : 0;
             a.begin[i + 1] = a.begin[i] + o.entry_ctas + o.stream_ctas;
         }
@@ -1430,7 +1379,7 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
         // 8 CTAs per SM although only 3 are resident (80 registers): measured on B200 (profiles/README.md), a grid of
         // exactly the resident CTAs is 15 % slower -- the late waves start on SMs whose first CTAs have drained and
         // keep the memory pipes fed through the tail.
-        const long long cap = (long long)shpl::sm_count() * narrow_ctas_per_sm(w, a.job[0].add != 0);
+        const long long cap = (long long)shpl::sm_count() * narrow_ctas_per_sm();
         long long want = (total_tiles + kWarps - 1) / kWarps;
         if (want > cap) want = cap;
         a.begin[0] = 0;

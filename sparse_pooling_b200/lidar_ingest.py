@@ -63,22 +63,15 @@ def rectified_matrix(frame_calib):
     return np.dot(r0, tf)
 
 
-_workspaces = {}
-
-
 def _workspace(device, n):
-    need = int(_lib.shpl_lidar_workspace_bytes(int(n)))
-    ws = _workspaces.get(str(device))
-    if ws is None or ws.numel() < need:
-        ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
-        _workspaces[str(device)] = ws
-    return ws
+    """scratch of shpl_lidar_to_cam for the current stream (ops.scratch: never shared between streams / threads)"""
+    from . import ops
+    return ops.scratch("lidar", device, int(_lib.shpl_lidar_workspace_bytes(int(n))))
 
 
 def lidar_to_cam_raw(velo, n, frame_calib, im_size, out, counts, min_intensity=None, stream=None, ws=None):
     """One asynchronous shpl_lidar_to_cam call: velo f32 [N,4] CUDA (contiguous), out f64 [3,cap] CUDA, counts i32 [4].
-    ws: scratch of shpl_lidar_workspace_bytes(n) bytes; by default the per-device one, which calls in flight on
-    different streams must not share."""
+    ws: scratch of shpl_lidar_workspace_bytes(n) bytes; by default the one cached for the current stream."""
     if not velo.is_contiguous() or velo.dtype != torch.float32:
         raise ValueError("lidar_to_cam_raw: the scan must be a contiguous float32 [N,4] CUDA tensor")
     R = np.ascontiguousarray(rectified_matrix(frame_calib)[0:3].reshape(12))

@@ -32,18 +32,32 @@ def require_cuda(t, name):
         raise RuntimeError("%s must be a CUDA tensor: the SHPL kernels run on the GPU only (no CPU fallback)" % name)
 
 
-_workspaces = {}
+_scratch = {}
+_scratch_lock = threading.Lock()
+
+
+def scratch(tag, device, nbytes):
+    """Scratch bytes for one asynchronous library call, cached per (purpose, device, CUDA STREAM, host thread).
+
+    Two calls in flight on different streams (or threads) therefore never share a buffer -- the library's scratch
+    holds tile tickets, look-back words and sort items, which concurrent builds would corrupt.  A buffer is only ever
+    used on the stream it was allocated under, so when it is replaced by a larger one torch's caching allocator (which
+    is stream-ordered) cannot hand the old block to anybody before the kernels queued on it have run."""
+    dev_index = device.index if device.index is not None else torch.cuda.current_device()
+    stream = torch._C._cuda_getCurrentRawStream(dev_index)
+    key = (tag, dev_index, stream, threading.get_ident())
+    ws = _scratch.get(key)
+    if ws is None or ws.numel() < nbytes:
+        with torch.cuda.device(dev_index):
+            ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        with _scratch_lock:
+            _scratch[key] = ws
+    return ws
 
 
 def workspace(device, n_max):
-    """Scratch for the builder, cached per device and grown on demand."""
-    need = int(_lib.shpl_build_workspace_bytes(int(n_max)))
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
-    ws = _workspaces.get(key)
-    if ws is None or ws.numel() < need:
-        ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[key] = ws
-    return ws
+    """Scratch for the correspondence builder (shpl_build_* / shpl_plan_from_*), for the current stream."""
+    return scratch("build", device, int(_lib.shpl_build_workspace_bytes(int(n_max))))
 
 
 _staging = threading.local()

@@ -97,3 +97,58 @@ class FramePipeline:
         rc = _lib.shpl_pool_backward(_p(g_fused_bev), _p(pl.pix_ptr), _p(pl.csrT_pix), _p(pl.csrT_dst), _p(pl.csrT_val),
                                      bound, 0, s.R, s.c_bev, s.Q, s.c_img, _p(L.g_bev), _p(L.g_img), stream)
         _cabi.check(rc, "shpl_pool_backward")
+
+
+class PairsPipeline:
+    """The same lean pipeline for callers that already hold (img_index, bv_index, M_val) pairs -- the MV3D path
+    (minibatch_mv3d_img.py:93 -> train_mv_voxel.py:325-326 -> network.py:242-246) and the direct-pair configs of
+    BASELINE.json -- for a BATCH of frames stacked into one plan (rows / pixels offset by the frame index), so that a
+    [B,H,W,C] batch is pooled by one launch each way.  The reference is batch-1 (sparse_pool_utils.py:98); the batch
+    is this repo's sharding unit.  Single direction (img -> bev), like every MV3D / pre-RPN call site."""
+
+    def __init__(self, spec, frames, n_max_per_frame, device):
+        if spec.dual:
+            raise ValueError("PairsPipeline pools img -> bev only")
+        self.spec, self.frames, self.n_max, self.device = spec, int(frames), int(n_max_per_frame), device
+        f32 = dict(dtype=torch.float32, device=device)
+        self.plan = SparsePoolPlan(spec.R, spec.img_hw, self.frames * self.n_max, device, frames=self.frames)
+        self.structs = []
+        for f in range(self.frames):
+            st = self.plan.frame_struct(f)
+            st.heavy_cap = 0                  # every cell summed sequentially in the main kernels (heavy_len = 0)
+            self.structs.append(st)
+        self.ws = torch.empty(int(_lib.shpl_build_workspace_bytes(self.n_max)), dtype=torch.uint8, device=device)
+        self.uv = torch.empty((self.frames, 2, self.n_max), dtype=torch.float64, device=device)   # floored in place by the builder
+        self.fused_bev = torch.empty((self.frames,) + spec.bev_hw + (spec.c_bev + spec.c_img,), **f32)
+        self.g_bev = torch.empty((self.frames,) + spec.bev_hw + (spec.c_bev,), **f32)
+        self.g_img = torch.empty((self.frames,) + spec.img_hw + (spec.c_img,), **f32)
+
+    def build_frame(self, f, uv, bv_index, m_val, n, stream):
+        """produce_sparse_pooling_input for frame f of the batch: uv f64 [2, >=n] (rows 0, 1 of img_index; copied, the
+        caller's array is not touched), bv_index i64 [n,2], m_val f64 [n] or None.  Call with f = 0, 1, ... in order
+        (the entry offsets chain through the plan counters on the device).  torch's current stream must be `stream`."""
+        s, n = self.spec, int(n)
+        if n > self.n_max:
+            raise ValueError("frame of %d pairs, pipeline sized for %d" % (n, self.n_max))
+        self.uv[f, :, :n].copy_(uv[:, :n], non_blocking=True)
+        u, v = self.uv[f, 0], self.uv[f, 1]
+        rc = _lib.shpl_produce_input(_p(u), _p(v), _p(bv_index), n, s.im_size[0], s.im_size[1], s.bv_size[0], s.bv_size[1],
+                                     s.stride[0], s.stride[1], None if m_val is None else _p(m_val), s.img_hw[0], s.img_hw[1],
+                                     None, None, None, None, ctypes.byref(self.structs[f]), f * s.R, f * s.Q,
+                                     self.plan.entry_base(f), _p(self.ws), self.ws.numel(), stream)
+        _cabi.check(rc, "shpl_produce_input")
+
+    def forward(self, bev, img, stream, nnz_max=None):
+        s, pl = self.spec, self.plan
+        bound = int(nnz_max) if nnz_max else pl.capacity
+        rc = _lib.shpl_pool_forward(_p(bev), _p(img), _p(pl.row_ptr), _p(pl.csr_row), _p(pl.csr_src), _p(pl.csr_val),
+                                    bound, 0, self.frames * s.R, s.c_bev, self.frames * s.Q, s.c_img, _p(self.fused_bev), stream)
+        _cabi.check(rc, "shpl_pool_forward")
+
+    def backward(self, g_fused_bev, stream, nnz_max=None):
+        s, pl = self.spec, self.plan
+        bound = int(nnz_max) if nnz_max else pl.capacity
+        rc = _lib.shpl_pool_backward(_p(g_fused_bev), _p(pl.pix_ptr), _p(pl.csrT_pix), _p(pl.csrT_dst), _p(pl.csrT_val),
+                                     bound, 0, self.frames * s.R, s.c_bev, self.frames * s.Q, s.c_img, _p(self.g_bev),
+                                     _p(self.g_img), stream)
+        _cabi.check(rc, "shpl_pool_backward")

@@ -200,17 +200,10 @@ def _produce_outputs(plan, Mij, flip, R, M_val, n_mval, as_numpy, dev):
             "bev_index_flip_pool": bev_flip, PLAN_KEY: plan}
 
 
-_ones_cache = {}
-
-
 def _ones(n, dev):
-    """np.ones(n) of the reference (:52) as a device tensor: a view of a cached block of ones (read-only by
-    convention -- the reference's M_val is a feed value nobody writes to), so no fill kernel runs per call."""
-    key = (dev.type, dev.index)
-    t = _ones_cache.get(key)
-    if t is None or t.shape[0] < n:
-        t = _ones_cache[key] = torch.ones(max(n, 1 << 16), dtype=torch.float64, device=dev)
-    return t[:n]
+    """np.ones(n) of the reference (:52) as a device tensor.  A FRESH tensor every call, like the reference's: a
+    caller that scales or normalises M_val in place must not change any other frame's weights."""
+    return torch.ones(n, dtype=torch.float64, device=dev)
 
 
 def _mval_to_dev(M_val, n, dev):

@@ -24,7 +24,23 @@ def _check(t, name, dtype):
     if not t.is_cuda:
         raise RuntimeError("%s must be a CUDA tensor: the SHPL kernels run on the GPU only (no CPU fallback)" % name)
     if t.dtype != dtype:
-        raise ValueError("%s must be %s" % (name, dtype))
+        raise ValueError("%s must be %s, got %s" % (name, dtype, t.dtype))
+
+
+def _check_csr(ptr, key, idx, val, nnz_max, device, what):
+    """The index arrays are handed to the kernels as raw addresses: wrong dtype / device / strides / lengths would be
+    read out of bounds instead of raising, so they are checked here."""
+    for t, name, dtype in ((ptr, "ptr", torch.int32), (key, "key", torch.int32), (idx, "idx", torch.int32), (val, "val", torch.float32)):
+        _check(t, "%s %s" % (what, name), dtype)
+        if t.device != device:
+            raise ValueError("%s %s is on %s, the feature maps on %s" % (what, name, t.device, device))
+        if t.dim() != 1 or not t.is_contiguous():
+            raise ValueError("%s %s must be a contiguous 1-D tensor" % (what, name))
+    if ptr.shape[0] < 1:
+        raise ValueError("%s ptr must hold n_rows + 1 offsets" % what)
+    if nnz_max < 0 or min(key.shape[0], idx.shape[0], val.shape[0]) < nnz_max:
+        raise ValueError("%s key / idx / val hold %d / %d / %d entries, nnz_max = %d"
+                         % (what, key.shape[0], idx.shape[0], val.shape[0], nnz_max))
 
 
 @torch.library.custom_op("shpl::pool", mutates_args=(), device_types="cuda")
@@ -34,8 +50,18 @@ def pool(dst: Optional[torch.Tensor], src: torch.Tensor, ptr: torch.Tensor, key:
     """dst [n_rows, C_d] or None, src [n_src, C_s] -> fused [n_rows, C_d + C_s].  (ptr, key, idx, val): CSR by
     destination cell; (ptrT, keyT, idxT, valT): CSR by source cell, carried for the backward."""
     _check(src, "src", torch.float32)
+    if src.dim() != 2:
+        raise ValueError("src must be [n_src, C_s]")
+    _check_csr(ptr, key, idx, val, nnz_max, src.device, "forward CSR")
+    _check_csr(ptrT, keyT, idxT, valT, nnz_max, src.device, "transposed CSR")
     n_src, C_s = src.shape
     n_rows = ptr.shape[0] - 1
+    if ptrT.shape[0] - 1 != n_src:
+        raise ValueError("transposed CSR has %d rows, src %d" % (ptrT.shape[0] - 1, n_src))
+    if dst is not None:
+        _check(dst, "dst", torch.float32)
+        if dst.dim() != 2 or dst.shape[0] != n_rows or dst.device != src.device:
+            raise ValueError("dst must be [n_rows = %d, C_d] on %s, got %s on %s" % (n_rows, src.device, tuple(dst.shape), dst.device))
     C_d = 0 if dst is None else dst.shape[1]
     s = src.contiguous()
     d = None if dst is None else dst.contiguous()
@@ -57,6 +83,9 @@ def pool_backward(g_fused: torch.Tensor, ptrT: torch.Tensor, keyT: torch.Tensor,
                   nnz_max: int, C_d: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """g_fused [n_rows, C_d + C_s] -> (g_dst [n_rows, C_d], g_src [n_src, C_s]); deterministic, no atomics."""
     _check(g_fused, "g_fused", torch.float32)
+    if g_fused.dim() != 2 or not (0 <= C_d < g_fused.shape[1]):
+        raise ValueError("g_fused must be [n_rows, C_d + C_s] with C_s > 0")
+    _check_csr(ptrT, keyT, idxT, valT, nnz_max, g_fused.device, "transposed CSR")
     g = g_fused.contiguous()
     n_rows, C = g.shape
     C_s = C - C_d

@@ -1,0 +1,107 @@
+"""GPU parity tests of the fused post-fusion 3x3 convolution: shpl_pool_conv3x3_forward through the
+C ABI against the CPU oracle -- oracle.value_oracle.conv3x3_after_fusion (float64) over the value oracle's fused map, the
+restatement of  sparse_pool_layer -> slim.conv2d(fused, C, [3, 3])  (rpn_model.py:335-346).
+
+The arithmetic of that conv lives in TensorFlow / cuDNN (parity unpinned, like the rest of the value path); the bound
+asserted here is the north star's 1e-5, relative to the sum of |terms| of each output (what an fp32 accumulation's
+error is proportional to): |out - ref| <= 1e-5 * sum |x_i w_i|.  Measured: <= 4e-7."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import cref, index_oracle as io, synth, value_oracle as vo  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def shpl():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import sparse_pooling_b200 as m
+    return m
+
+
+def _pairs(seed, n, H, W, Hi, Wi, dup_rows=False):
+    rng = np.random.default_rng(seed)
+    rows = rng.integers(0, H * W, n)
+    if dup_rows and n:                       # several pairs per cell and neighbouring busy cells
+        rows[: n // 2] = rows[n // 2: 2 * (n // 2)]
+        rows[: n // 4] = np.clip(rows[n // 4: 2 * (n // 4)] + 1, 0, H * W - 1)
+    flip = np.stack([np.zeros(n, np.int64), rng.integers(0, Hi, n), rng.integers(0, Wi, n)], 1)
+    Mij = np.stack([rows, np.arange(n)], 1).astype(np.int64)
+    val = (rng.random(n) + 0.5).astype(np.float32)
+    return Mij, val, flip
+
+
+def _run(shpl, B, H, W, Hi, Wi, n, seed, relu, affine, pooled=True, dup_rows=False):
+    from sparse_pooling_b200 import conv_fusion
+    rng = np.random.default_rng(seed)
+    bev = rng.standard_normal((B, H, W, 32), dtype=np.float32)
+    img = rng.standard_normal((B, Hi, Wi, 32), dtype=np.float32)
+    w = (rng.standard_normal((3, 3, 64 if pooled else 32, 32)) * 0.1).astype(np.float32)
+    scale = (rng.random(32) + 0.5).astype(np.float32) if affine else None
+    shift = rng.standard_normal(32).astype(np.float32) if affine else None
+    tb, ti, tw = (torch.from_numpy(x).cuda() for x in (bev, img, w))
+    ts = None if scale is None else torch.from_numpy(scale).cuda()
+    th = None if shift is None else torch.from_numpy(shift).cuda()
+    if pooled:
+        assert B == 1
+        Mij, val, flip = _pairs(seed + 1, n, H, W, Hi, Wi, dup_rows)
+        M = shpl.SparseTensor(torch.from_numpy(Mij).cuda(), torch.from_numpy(val).cuda(), np.array([H * W, n]))
+        out = conv_fusion.sparse_pool_conv3x3([tb, ti], M, torch.from_numpy(flip).cuda(), tw, ts, th, relu)
+        fused = cref.forward(bev[0], img[0], Mij, val, flip)[None] if n else np.concatenate([bev, np.zeros_like(bev)], axis=3)
+    else:
+        out = conv_fusion.sparse_pool_conv3x3([tb, None], None, None, tw, ts, th, relu)
+        fused = bev
+    ref, mag = vo.conv3x3_after_fusion(fused, w, scale, shift, relu)
+    err = np.abs(out.cpu().numpy().astype(np.float64) - ref)
+    rel = float((err / np.maximum(mag, 1e-30)).max())
+    assert rel <= TOL, "max |err| / sum|terms| = %.3e" % rel
+    return rel
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 8, 14), (1, 16, 8), (1, 9, 15), (2, 50, 44), (3, 7, 100), (1, 1, 1)])
+def test_dense_half_alone_matches_the_oracle(shpl, B, H, W):
+    """No pooled channels: a plain SAME-padded 3x3 conv of the BEV map, tile-aligned and ragged sizes, batches."""
+    _run(shpl, B, H, W, 4, 4, 0, 10 + H, relu=False, affine=False, pooled=False)
+    _run(shpl, B, H, W, 4, 4, 0, 20 + H, relu=True, affine=True, pooled=False)
+
+
+@pytest.mark.parametrize("n,dup", [(0, False), (1, False), (300, False), (3000, True), (129, True)])
+def test_fused_conv_matches_pool_then_conv(shpl, n, dup):
+    """conv(concat(bev, pooled)) with the fused map never written == the oracle's pool -> concat -> conv."""
+    _run(shpl, 1, 50, 44, 20, 30, n, 30 + n, relu=False, affine=False, dup_rows=dup)
+    _run(shpl, 1, 50, 44, 20, 30, n, 40 + n, relu=True, affine=True, dup_rows=dup)
+
+
+def test_fused_conv_at_the_kitti_size(shpl):
+    """700x800x(32+32 -> 32) <- 360x1200x32, 20 000 pairs: the pre-RPN layer of the pyramid people config."""
+    rel = _run(shpl, 1, 700, 800, 360, 1200, 20000, 5, relu=True, affine=True)
+    print("KITTI size: max |err| / sum|terms| = %.2e" % rel)
+
+
+def test_fused_conv_through_the_builder_plan(shpl):
+    """The plan the correspondence builder leaves (produce_sparse_pooling_input's dict) goes straight in."""
+    from sparse_pooling_b200 import conv_fusion
+    d = synth.direct_pairs(3, 5000, (88, 100), (150, 45))
+    o = shpl.produce_sparse_pooling_input({k: np.array(v, copy=True) for k, v in d.items()}, stride=[1, 1])
+    rng = np.random.default_rng(2)
+    bev = rng.standard_normal((1, 88, 100, 32), dtype=np.float32)
+    img = rng.standard_normal((1, 45, 150, 32), dtype=np.float32)
+    w = (rng.standard_normal((3, 3, 64, 32)) * 0.1).astype(np.float32)
+    out = conv_fusion.sparse_pool_conv3x3([torch.from_numpy(bev).cuda(), torch.from_numpy(img).cuda()], o,
+                                          o["img_index_flip_pool"], torch.from_numpy(w).cuda())
+    oref = io.produce_sparse_pooling_input({k: np.array(v, copy=True) for k, v in d.items()}, stride=(1, 1))
+    fused = cref.forward(bev[0], img[0], oref["Mij_pool"], np.ones(len(oref["Mij_pool"]), np.float32), oref["img_index_flip_pool"])[None]
+    ref, mag = vo.conv3x3_after_fusion(fused, w)
+    assert float((np.abs(out.cpu().numpy() - ref) / np.maximum(mag, 1e-30)).max()) <= TOL
+
+
+def test_unsupported_shapes_are_refused_not_miscomputed(shpl):
+    from sparse_pooling_b200 import conv_fusion
+    bev = torch.zeros((1, 8, 8, 16), device="cuda")
+    w = torch.zeros((3, 3, 16, 16), device="cuda")
+    with pytest.raises(ValueError):
+        conv_fusion.sparse_pool_conv3x3([bev, None], None, None, w)

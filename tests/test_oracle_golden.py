@@ -388,3 +388,22 @@ def test_value_oracle_vs_scipy_sparse_matmul(seed):
     assert np.abs(o_img[0, ..., Ci:].reshape(-1, Cb) - Pm).max() <= max(tol_img, tol_bv)
     np.testing.assert_array_equal(o_bv[0, ..., :Cb], bev[0])              # the concatenated halves are the inputs themselves
     np.testing.assert_array_equal(o_img[0, ..., :Ci], img[0])
+
+
+def test_conv_oracle_agrees_with_torch_cpu_conv2d():
+    """oracle.value_oracle.conv3x3_same (the f3 oracle: slim.conv2d's SAME-padded, stride-1 3x3 conv in HWIO layout,
+    rpn_model.py:338-346) against an independent engine, torch CPU conv2d in float64."""
+    import torch
+    from oracle import value_oracle as vo
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, 9, 11, 6))
+    w = rng.standard_normal((3, 3, 6, 5))
+    y, mag = vo.conv3x3_same(x, w)
+    t = torch.nn.functional.conv2d(torch.from_numpy(x).permute(0, 3, 1, 2), torch.from_numpy(w).permute(3, 2, 0, 1), padding=1)
+    np.testing.assert_allclose(y, t.permute(0, 2, 3, 1).numpy(), rtol=1e-12, atol=1e-12)
+    assert (mag >= np.abs(y) - 1e-12).all()
+    # a hand-checkable case: all-ones 3x3x1x1 kernel = count of in-image neighbours times the value
+    y1, _ = vo.conv3x3_same(np.ones((1, 3, 3, 1)), np.ones((3, 3, 1, 1)))
+    assert y1[0, :, :, 0].tolist() == [[4, 6, 4], [6, 9, 6], [4, 6, 4]]
+    ya, _ = vo.conv3x3_after_fusion(-np.ones((1, 3, 3, 1)), np.ones((3, 3, 1, 1)), scale=[2.0], shift=[1.0], relu=True)
+    assert (ya == 0).all()

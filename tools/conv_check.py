@@ -72,7 +72,7 @@ def timing():
         sets.append((bev, img, d))
     w = torch.randn(3, 3, 64, 32, device=dev) * 0.1
     outs = [torch.empty(1, H, W, 32, device=dev) for _ in range(3)]
-    ws = conv_fusion.conv_workspace(1, H, W, dev)
+    ws = conv_fusion.conv_workspace(1, H, W, dev, 20000)
     Ms = []
     for bev, img, d in sets:
         o = shpl.produce_sparse_pooling_input(dict(d), stride=[1, 1])
