@@ -405,12 +405,13 @@ def run_gpu_avod(args, name, cfg):
     def pool_stream(li, main):
         return side if (li == nL - 1 and nL > 1) else main
 
-    def lean_step(k, timing_events=None, overlap=True):
+    def lean_step(k, timing_events=None, overlap=True, PP=None):
         """build + fwd + bwd of every layer on preallocated buffers.  overlap=True: layers on their own streams and
         the builders of frame k+1 beside the pooling of frame k; overlap=False keeps one stream so that an event pair
-        brackets exactly one kernel."""
+        brackets exactly one kernel.  PP: the pipelines to run (default: the drop-in concat form)."""
+        PP = pipes if PP is None else PP
         fi, si = k % N_FRAMES, k % n_sets
-        pipe, mp = pipes[si], maps[si]
+        pipe, mp = PP[si], maps[si]
         main = torch.cuda.current_stream()
         ms = main.cuda_stream
         if not overlap:
@@ -441,7 +442,7 @@ def run_gpu_avod(args, name, cfg):
             st_.wait_stream(main)
         for li in range(nL):
             with torch.cuda.stream(build_streams[li]):
-                pipes[ns].build_layer(li, pts_dev[nf], vox_dev[nf], P, n_pts[nf], build_streams[li].cuda_stream)
+                PP[ns].build_layer(li, pts_dev[nf], vox_dev[nf], P, n_pts[nf], build_streams[li].cuda_stream)
         for li in range(nL):
             pst = pool_stream(li, main)
             with torch.cuda.stream(pst):
@@ -450,12 +451,13 @@ def run_gpu_avod(args, name, cfg):
         for st_ in others:
             main.wait_stream(st_)
 
-    def prologue_build(k):
+    def prologue_build(k, PP=None):
         """plans of frame k (the first frame of a timed region has no previous step to build them)"""
+        PP = pipes if PP is None else PP
         fi, si = k % N_FRAMES, k % n_sets
         ms = torch.cuda.current_stream().cuda_stream
         for li in range(nL):
-            pipes[si].build_layer(li, pts_dev[fi], vox_dev[fi], P, n_pts[fi], ms)
+            PP[si].build_layer(li, pts_dev[fi], vox_dev[fi], P, n_pts[fi], ms)
 
     # ---- PARITY CHECK before timing: one step of the timed path (FramePipeline -> C ABI), every layer, against the CPU
     #      oracle (oracle/cref: the plain-C restatement), bit for bit; a mismatch aborts the run
@@ -655,6 +657,84 @@ def run_gpu_avod(args, name, cfg):
                                     "bytes_per_launch": bytes_bwd_B, "us_per_launch": bwd_avg * 1e6}}
     bytes_step = sum(s.bytes_forward(n) + s.bytes_backward(n) for s, n in zip(specs, nnz))
     step_gbs = bytes_step * KT / (ms_total * 1e-3) / 1e9
+
+    # ---- the no-concat ("sparse-only") form of SURVEY.md 8(d): the producer of a destination map writes its channels
+    #      straight into the fused buffer, so the forward writes only the pooled channels and the single-direction
+    #      backward only the gradient of the gathered map (g_dst is a view).  Same step, same plans, own byte formulas.
+    no_concat = None
+    if not args.no_no_concat:
+        try:
+            pipes_nc = [FramePipeline(specs, N_MAX, dev, no_concat=True) for _ in range(n_sets)]
+            for si_ in range(n_sets):
+                for li in range(nL):          # the "producer": the destination channels are already in the fused buffers
+                    pipes_nc[si_].layers[li].fused_bev[..., :specs[li].c_bev].copy_(maps[si_][li]["bev"])
+                    if specs[li].dual:
+                        pipes_nc[si_].layers[li].fused_img[..., :specs[li].c_img].copy_(maps[si_][li]["img"])
+            prologue_build(0, pipes_nc)
+            lean_step(0, PP=pipes_nc)
+            torch.cuda.synchronize()
+            if not args.no_parity_check:       # same values as the concat form, bit for bit (which equals the oracle, above)
+                prologue_build(0)
+                lean_step(0)
+                torch.cuda.synchronize()
+                for li in range(nL):
+                    a_, b_ = pipes_nc[0].layers[li], pipes[0].layers[li]
+                    if not (torch.equal(a_.fused_bev, b_.fused_bev) and torch.equal(a_.g_img, b_.g_img)):
+                        raise SystemExit("bench.py: PARITY CHECK FAILED: no-concat form of layer %s differs from the concat form" % specs[li].name)
+            ngr = []
+            for v in range(N_FRAMES if N_FRAMES % n_sets == 0 else N_FRAMES * n_sets):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    lean_step(v, PP=pipes_nc)
+                ngr.append(gr)
+            prologue_build(0, pipes_nc)
+            for k in range(W):
+                ngr[k % len(ngr)].replay()
+            evn0, evn1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            KN = max(K, int(math.ceil(0.2 / max(est, 1e-9))))
+            torch.cuda.synchronize()
+            barrier()
+            evn0.record()
+            for k in range(W, W + KN):
+                ngr[k % len(ngr)].replay()
+            evn1.record()
+            torch.cuda.synchronize()
+            ms_nc = D.max(evn0.elapsed_time(evn1))
+            nf_ms, nb_ms = [], []
+            tg2, te2 = [], []
+            for v in range(N_FRAMES):
+                ev3 = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(3)]
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    lean_step(v, ev3, overlap=False, PP=pipes_nc)
+                tg2.append(gr)
+                te2.append(ev3)
+            for k in range(3):
+                tg2[k % N_FRAMES].replay()
+            torch.cuda.synchronize()
+            for k in range(KR):
+                tg2[k % N_FRAMES].replay()
+                torch.cuda.synchronize()
+                e = te2[k % N_FRAMES]
+                nf_ms.append(e[0].elapsed_time(e[1]))
+                nb_ms.append(e[1].elapsed_time(e[2]))
+            bf, bb = sB.bytes_forward_sparse_only(nnz[dom]), sB.bytes_backward_sparse_only(nnz[dom])
+            tf_, tb_ = float(np.mean(nf_ms)) * 1e-3, float(np.mean(nb_ms)) * 1e-3
+            bytes_step_nc = sum((s.bytes_forward_sparse_only(n) + (s.bytes_backward(n) if s.dual else s.bytes_backward_sparse_only(n)))
+                                for s, n in zip(specs, nnz))
+            no_concat = {"what": "the same step with every layer in the no-concat form (shpl_pool_forward_into / _into_dual, "
+                                 "shpl_pool_backward_from; the dual layer's backward keeps the AddN form): frames/s, and layer %s's "
+                                 "kernels against the sparse-only byte formulas of SURVEY.md 8(d)" % sB.name,
+                         "value": world * KN / (ms_nc * 1e-3), "unit": UNIT, "steps": KN, "ms_per_step": ms_nc / KN,
+                         "algorithmic_bytes_per_step": bytes_step_nc,
+                         "forward_kernel": {"bytes_per_launch": bf, "us_per_launch": tf_ * 1e6, "achieved": bf / tf_ / 1e9, "frac": bf / tf_ / 1e9 / peak},
+                         "backward_kernel": {"bytes_per_launch": bb, "us_per_launch": tb_ * 1e6, "achieved": bb / tb_ / 1e9, "frac": bb / tb_ / 1e9 / peak}}
+            del pipes_nc, ngr, tg2
+        except SystemExit:
+            raise
+        except Exception as ex:  # pragma: no cover
+            print("no-concat leg failed: %r" % (ex,), file=sys.stderr)
+            torch.cuda.synchronize()
 
     # ---- e2e: the public drop-in API, frame inputs in pinned host memory, result read back
     class Calib:
@@ -923,6 +1003,8 @@ def run_gpu_avod(args, name, cfg):
                     "parity_check": parity},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
         }
+        if no_concat is not None:
+            line["no_concat"] = no_concat
         if feeder is not None:
             line["feeder"] = feeder
         if cpu is not None:
@@ -1410,6 +1492,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle comparison before timing")
     ap.add_argument("--no-feeder", action="store_true", help="skip the feeder / velodyne chain legs (config 2)")
+    ap.add_argument("--no-no-concat", action="store_true", help="skip the no-concat (sparse-only) leg")
     ap.add_argument("--single-step-graphs", action="store_true", help="one CUDA graph per step (no multi-step graph)")
     ap.add_argument("--graph-steps", type=int, default=8, help="consecutive steps captured in one CUDA graph (multiple of 4)")
     args = ap.parse_args()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SHPL_ABI_VERSION 8
+#define SHPL_ABI_VERSION 9
 
 /* Cells with more entries than this are "heavy": the builder lists them in the plan and their sum
  * is formed by shpl_pool_heavy (a thread-block cluster per cell) instead of one warp walking the cell.
@@ -222,6 +222,47 @@ int shpl_pool_backward_dual(const float* g_fused_bev, const float* g_fused_img,
                             const int32_t* pix_ptr, const int32_t* csrT_pix, const int32_t* csrT_dst, const float* csrT_val,
                             int32_t nnz_max, int32_t heavy_len, int32_t n_rows, int32_t C_b, int32_t n_src, int32_t C_i,
                             float* g_bev, float* g_img, void* stream);
+
+/* shpl_pool_heavy with the LONG listed cells (more than SHPL_EXACT_LEN entries) split over many CTAs instead of one
+ * cluster per cell: a cell of L entries is cut into ceil(L / 2048) contiguous pieces, a CTA sums one piece in stored
+ * order into the workspace, and a second kernel adds a cell's partial sums in order -- a fixed tree that depends only on
+ * L (deterministic, within 1e-5 of the sum of |terms|; not bit-identical to the sequential sum).  The Zipf stress case's
+ * 178 000-entry cell runs on ~90 SMs instead of 8.  Cells up to SHPL_EXACT_LEN entries take the exact cluster kernel as
+ * in shpl_pool_heavy.  nnz_max >= total entries of the plan; workspace: shpl_pool_heavy_workspace_bytes(C, nnz_max,
+ * list_cap) bytes, 16-byte aligned.  (More than 4096 listed cells: falls back to shpl_pool_heavy's cluster tree.) */
+size_t shpl_pool_heavy_workspace_bytes(int32_t C, int64_t nnz_max, int32_t list_cap);
+int shpl_pool_heavy_split(const float* gather_in, int32_t gather_stride, int32_t C,
+                          const int32_t* ptr, const int32_t* idx, const float* val,
+                          const int32_t* list, const int32_t* count_dev, int32_t list_cap,
+                          const float* addend, int32_t addend_stride,
+                          float* out, int32_t out_stride, int64_t nnz_max,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- No-concat ("sparse-only") forms of the three calls above: for callers whose producer of the
+ * destination map writes its C_d channels straight into the fused buffer (what tf.concat would otherwise copy).
+ * Two thirds of the bytes of the KITTI pre-RPN forward are that copy (220 MB -> 74 MB).
+ *   shpl_pool_forward_into:   fused[r*fused_stride + chan_off + 0:C_s] = sum over the entries of row r, in stored order,
+ *                             of val * src[idx, :]  (0 for an empty row); every other channel of `fused` is left alone.
+ *   shpl_pool_forward_into_dual: both directions of the layer in one launch, into fused_bev [n_rows, C_b+C_i] at channel
+ *                             C_b and fused_img [n_src, C_i+C_b] at channel C_i (bev / img are only gathered from).
+ *   shpl_pool_backward_from:  g_src[p, :] = sum over the entries of source p of valT * g_fused[idxT*g_stride + chan_off + :]
+ *                             -- the gradient of the gathered map; the gradient of the destination map is the VIEW
+ *                             g_fused[:, 0:chan_off] (no copy is made, nothing to compute).
+ * Same values, bit for bit, as the concat forms; key / nnz_max / heavy_len as in shpl_pool_forward (for heavy cells follow
+ * with shpl_pool_heavy, whose strides are general). */
+int shpl_pool_forward_into(const float* src,
+                           const int32_t* ptr, const int32_t* key, const int32_t* idx, const float* val,
+                           int32_t nnz_max, int32_t heavy_len, int32_t n_rows, int32_t n_src, int32_t C_s,
+                           float* fused, int32_t fused_stride, int32_t chan_off, void* stream);
+int shpl_pool_forward_into_dual(const float* bev, const float* img,
+                                const int32_t* row_ptr, const int32_t* csr_row, const int32_t* csr_src, const float* csr_val,
+                                const int32_t* pix_ptr, const int32_t* csrT_pix, const int32_t* csrT_dst, const float* csrT_val,
+                                int32_t nnz_max, int32_t heavy_len, int32_t n_rows, int32_t C_b, int32_t n_src, int32_t C_i,
+                                float* fused_bev, float* fused_img, void* stream);
+int shpl_pool_backward_from(const float* g_fused, int32_t g_stride, int32_t chan_off,
+                            const int32_t* ptrT, const int32_t* keyT, const int32_t* idxT, const float* valT,
+                            int32_t nnz_max, int32_t heavy_len, int32_t n_rows, int32_t n_src, int32_t C_s,
+                            float* g_src, void* stream);
 
 /* Listed ("heavy") cells (more than SHPL_HEAVY_LEN entries; none at KITTI / MV3D shapes, the Zipf stress case has
  * a 178 000-entry cell): one thread-block CLUSTER of 8 CTAs per listed cell, in two kernels.

@@ -22,7 +22,7 @@ SHPL_ERR_CUDA = -2
 SHPL_ERR_WORKSPACE_TOO_SMALL = -3
 SHPL_ERR_UNSUPPORTED = -4
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 HEAVY_LEN = 512           # SHPL_HEAVY_LEN of include/shpl.h
 EXACT_LEN = 2048          # SHPL_EXACT_LEN: listed cells up to this many entries keep the sequential order
 
@@ -98,6 +98,12 @@ SIGNATURES = {
                                                  ctypes.c_double, c_void_p, c_void_p, c_void_p]),
     "shpl_augment_fv_index": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_void_p, ctypes.c_double, ctypes.c_double,
                                              ctypes.c_double, c_void_p]),
+    "shpl_pool_heavy_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int32]),
+    "shpl_pool_heavy_split": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int64, c_void_p, c_size_t, c_void_p]),
+    "shpl_pool_forward_into": (ctypes.c_int, [c_void_p] * 5 + [c_int32] * 5 + [c_void_p, c_int32, c_int32, c_void_p]),
+    "shpl_pool_forward_into_dual": (ctypes.c_int, [c_void_p] * 10 + [c_int32] * 6 + [c_void_p] * 3),
+    "shpl_pool_backward_from": (ctypes.c_int, [c_void_p, c_int32, c_int32] + [c_void_p] * 4 + [c_int32] * 5 + [c_void_p, c_void_p]),
     "shpl_conv3x3_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "shpl_pool_conv3x3_forward": (ctypes.c_int, [c_void_p] * 6 + [c_int32] * 7 + [c_void_p, c_int32, c_void_p, c_void_p, c_int32,
                                                  c_void_p, c_void_p, c_size_t, c_void_p]),

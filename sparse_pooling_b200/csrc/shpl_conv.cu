@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out, ConvArgs a) {
     extern __shared__ uint8_t conv_smem_raw[];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ uint32_t halo_bits[kHaloY];       // busy bits of the current tile's halo rows (epilogue warps)
     const uint32_t raw = smem_u32(conv_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* gbase = conv_smem_raw + (base - raw);
@@ -296,20 +297,41 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
             int f, y0, x0;
             tile_coord(i, f, y0, x0);
             // The pooled half: which of this pixel's nine neighbours receive pooled features, and where their Z rows are.
-            // The lookups (bitmap -> CSR offset) are issued now; their latency hides under the wait for the accumulators.
+            // Ten threads fetch the busy bits of the tile's halo (10 rows x 16 columns) into shared memory; every thread
+            // then tests its nine bits there and issues the (few) CSR-offset loads side by side, predicated -- all of it
+            // before the wait for the accumulators, which hides the latency.
             int zrow[9];
             if (a.busy != nullptr) {
+                if (tid < kHaloY) {
+                    const int yy = y0 - 1 + tid;
+                    uint32_t bits = 0u;
+                    if (yy >= 0 && yy < a.H) {
+                        const int xs = x0 > 0 ? x0 - 1 : 0;                       // first in-image halo column
+                        const long long c = ((long long)f * a.H + yy) * a.W + xs;
+                        const long long last = ((long long)a.frames * a.H * a.W - 1) >> 5;
+                        const long long wi = c >> 5;
+                        const uint64_t lo = __ldg(a.busy + wi), hi = wi + 1 <= last ? __ldg(a.busy + wi + 1) : 0u;
+                        bits = (uint32_t)(((hi << 32) | lo) >> (c & 31)) & 0xffffu;
+                        const int n_valid = min(a.W - xs, kHaloX - (xs - (x0 - 1)));     // columns of this row inside the image
+                        bits &= (1u << n_valid) - 1u;
+                        bits <<= (xs - (x0 - 1));
+                    }
+                    halo_bits[tid] = bits;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
                 const int gy = y0 + yl, gx = x0 + xq - 1;
                 const bool px_ok = col_ok && gy < a.H && gx < a.W;
                 const int e_begin = __ldg(a.ptr);
+                uint32_t near9 = 0u;                                                  // bit t: neighbour of tap t is busy
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) near9 |= ((halo_bits[yl + dy] >> (xq > 0 ? xq - 1 : 0)) & 7u) << (3 * dy);
+                if (!px_ok) near9 = 0u;
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
-                    const int yy = gy + t / 3 - 1, xx = gx + t % 3 - 1;
-                    zrow[t] = -1;
-                    if (px_ok && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
-                        const int nb = (f * a.H + yy) * a.W + xx;
-                        if ((__ldg(a.busy + (nb >> 5)) >> (nb & 31)) & 1u) zrow[t] = (__ldg(a.ptr + nb) - e_begin) * 9 + t;
-                    }
+                    const int nb = (f * a.H + gy + t / 3 - 1) * a.W + gx + t % 3 - 1;
+                    const bool on = (near9 >> t) & 1u;
+                    const int off = on ? __ldg(a.ptr + nb) : 0;
+                    zrow[t] = on ? (off - e_begin) * 9 + t : -1;
                 }
             }
             mbar_wait(bar(BAR_ACC_FULL + s), u & 1);
@@ -453,8 +475,8 @@ __global__ void __launch_bounds__(kZtcThreads, 1) shpl_conv_z_tc_kernel(ZArgs a)
     extern __shared__ uint8_t z_smem_raw[];
     __shared__ uint32_t tmem_slot;
     const int e_begin = __ldg(a.ptr), e_end = min(__ldg(a.ptr + a.n_rows), e_begin + a.nnz_max);
-    const int e0 = e_begin + (int)blockIdx.x * 128;
-    if (e0 >= e_end) return;                              // whole CTA: nnz_max is only an upper bound
+    const int n_tiles = (e_end - e_begin + 127) / 128;
+    if ((int)blockIdx.x >= n_tiles) return;               // whole CTA: nnz_max is only an upper bound
     const uint32_t raw = smem_u32(z_smem_raw);
     const uint32_t base = (raw + 127u) & ~127u;
     uint8_t* gbase = z_smem_raw + (base - raw);
@@ -472,108 +494,115 @@ __global__ void __launch_bounds__(kZtcThreads, 1) shpl_conv_z_tc_kernel(ZArgs a)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // ---- gather: warp w fills rows 16w .. 16w+15 (entries ew .. ew+15); lane = channel
-    {
-        const int ew = e0 + warp * 16;
-        int k_l = ew + lane, key_l = -1, idx_l = 0, end_l = 0;
-        float val_l = 0.f;
-        bool first_l = false;
-        if (lane < 16 && k_l < e_end) {
-            key_l = __ldg(a.key + k_l);
-            idx_l = __ldg(a.idx + k_l);
-            val_l = __ldg(a.val + k_l);
-            first_l = (k_l == e_begin) || (__ldg(a.key + k_l - 1) != key_l);
-            if (first_l) end_l = __ldg(a.ptr + key_l + 1);
-        }
-        float x[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {                    // the 16 gathered rows in flight together
-            const int p = __shfl_sync(0xffffffffu, idx_l, j);
-            x[j] = (ew + j < e_end) ? __ldg(a.src + (size_t)p * 32 + lane) : 0.f;
-        }
-        const unsigned firsts = __ballot_sync(0xffffffffu, first_l) & 0xffffu;
-        uint8_t* hi_p = gbase + kZtcSmA + (lane >> 2) * kZtcPitch + (lane & 3) * 4;
-        uint8_t* lo_p = hi_p + kZtcPlane;
-        float acc = 0.f;
-        int open = -1, open_end = 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const bool fj = (firsts >> j) & 1u;
-            if (fj) {
-                if (open >= 0) {                          // the previous cell ended inside the window
-                    const float h = __uint_as_float(__float_as_uint(acc) & 0xffffe000u);
-                    *reinterpret_cast<float*>(hi_p + (warp * 16 + open) * 16) = h;
-                    *reinterpret_cast<float*>(lo_p + (warp * 16 + open) * 16) = acc - h;
-                }
-                open = j;
-                open_end = __shfl_sync(0xffffffffu, end_l, j);
-                acc = 0.f;
-            }
-            if (open >= 0 && ew + j < open_end)
-                acc = __fadd_rn(acc, __fmul_rn(__shfl_sync(0xffffffffu, val_l, j), x[j]));
-            if (!fj) {                                    // not a first entry: an all-zero row
-                *reinterpret_cast<float*>(hi_p + (warp * 16 + j) * 16) = 0.f;
-                *reinterpret_cast<float*>(lo_p + (warp * 16 + j) * 16) = 0.f;
-            }
-        }
-        if (open >= 0) {
-            for (int k = ew + 16; k < open_end; ++k)      // the last cell runs on past the window
-                acc = __fadd_rn(acc, __fmul_rn(__ldg(a.val + k), __ldg(a.src + (size_t)__ldg(a.idx + k) * 32 + lane)));
-            const float h = __uint_as_float(__float_as_uint(acc) & 0xffffe000u);
-            *reinterpret_cast<float*>(hi_p + (warp * 16 + open) * 16) = h;
-            *reinterpret_cast<float*>(lo_p + (warp * 16 + open) * 16) = acc - h;
-        }
-        if (lane < 16) flags[warp * 16 + lane] = first_l ? 1 : 0;
-    }
-    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
-    if (tid == 0) {
-        mbar_wait(bar_w, 0);
-        constexpr uint32_t idesc = instr_desc(96);
-        const uint32_t a_hi = base + kZtcSmA, a_lo = a_hi + kZtcPlane, w0 = base + kZtcSmW;
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-#pragma unroll
-            for (int j = 0; j < kChunks / 2; ++j) {
-                const uint32_t aoff = (uint32_t)(2 * j * kZtcPitch);
-                const uint32_t wb = w0 + dy * kWDyBytes + 2 * j * kWChunkBytes;
-                const uint64_t b_hi = smem_desc(wb, kWChunkBytes, 128), b_lo = smem_desc(wb + 96 * 16, kWChunkBytes, 128);
-                const uint32_t d = tmem + (uint32_t)(dy * 96);
-                umma_tf32(d, smem_desc(a_hi + aoff, kZtcPitch, 128), b_hi, idesc, j != 0);
-                umma_tf32(d, smem_desc(a_hi + aoff, kZtcPitch, 128), b_lo, idesc, 1u);
-                umma_tf32(d, smem_desc(a_lo + aoff, kZtcPitch, 128), b_hi, idesc, 1u);
+    int it = 0;
+    for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++it) {
+        const int e0 = e_begin + tile * 128;
+        // ---- gather: warp w fills rows 16w .. 16w+15 (entries ew .. ew+15); lane = channel
+        {
+            const int ew = e0 + warp * 16;
+            int k_l = ew + lane, key_l = -1, idx_l = 0, end_l = 0;
+            float val_l = 0.f;
+            bool first_l = false;
+            if (lane < 16 && k_l < e_end) {
+                key_l = __ldg(a.key + k_l);
+                idx_l = __ldg(a.idx + k_l);
+                val_l = __ldg(a.val + k_l);
+                first_l = (k_l == e_begin) || (__ldg(a.key + k_l - 1) != key_l);
+                if (first_l) end_l = __ldg(a.ptr + key_l + 1);
             }
-        }
-        umma_commit(bar_mma);
-    }
-    // ---- epilogue: rows that are first entries go out as Z rows (1152 contiguous bytes per row)
-    mbar_wait(bar_mma, 0);
-    tc_fence_after();
-    {
-        const int q = warp & 3, half = warp >> 2;
-        const int m = q * 32 + lane;
-        const bool on = flags[m] != 0;
-        float* zrow = a.Z + (size_t)(e0 - e_begin + m) * 288;
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
-#pragma unroll 3
-        for (int cc = 0; cc < 18; ++cc) {
-            const int col = half * 144 + cc * 8;
-            uint32_t v[8];
-            SHPL_TMEM_LD8(taddr + col, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (on) {
-                *reinterpret_cast<float4*>(zrow + col) = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-                *reinterpret_cast<float4*>(zrow + col + 4) = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+            float x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {                    // the 16 gathered rows in flight together
+                const int p = __shfl_sync(0xffffffffu, idx_l, j);
+                x[j] = (ew + j < e_end) ? __ldg(a.src + (size_t)p * 32 + lane) : 0.f;
             }
+            const unsigned firsts = __ballot_sync(0xffffffffu, first_l) & 0xffffu;
+            uint8_t* hi_p = gbase + kZtcSmA + (lane >> 2) * kZtcPitch + (lane & 3) * 4;
+            uint8_t* lo_p = hi_p + kZtcPlane;
+            float acc = 0.f;
+            int open = -1, open_end = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const bool fj = (firsts >> j) & 1u;
+                if (fj) {
+                    if (open >= 0) {                          // the previous cell ended inside the window
+                        const float h = __uint_as_float(__float_as_uint(acc) & 0xffffe000u);
+                        *reinterpret_cast<float*>(hi_p + (warp * 16 + open) * 16) = h;
+                        *reinterpret_cast<float*>(lo_p + (warp * 16 + open) * 16) = acc - h;
+                    }
+                    open = j;
+                    open_end = __shfl_sync(0xffffffffu, end_l, j);
+                    acc = 0.f;
+                }
+                if (open >= 0 && ew + j < open_end)
+                    acc = __fadd_rn(acc, __fmul_rn(__shfl_sync(0xffffffffu, val_l, j), x[j]));
+                if (!fj) {                                    // not a first entry: an all-zero row
+                    *reinterpret_cast<float*>(hi_p + (warp * 16 + j) * 16) = 0.f;
+                    *reinterpret_cast<float*>(lo_p + (warp * 16 + j) * 16) = 0.f;
+                }
+            }
+            if (open >= 0) {
+                for (int k = ew + 16; k < open_end; ++k)      // the last cell runs on past the window
+                    acc = __fadd_rn(acc, __fmul_rn(__ldg(a.val + k), __ldg(a.src + (size_t)__ldg(a.idx + k) * 32 + lane)));
+                const float h = __uint_as_float(__float_as_uint(acc) & 0xffffe000u);
+                *reinterpret_cast<float*>(hi_p + (warp * 16 + open) * 16) = h;
+                *reinterpret_cast<float*>(lo_p + (warp * 16 + open) * 16) = acc - h;
+            }
+            if (lane < 16) flags[warp * 16 + lane] = first_l ? 1 : 0;
         }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();                                      // A planes + flags complete; the previous tile's TMEM reads are done
         tc_fence_after();
+        if (tid == 0) {
+            if (it == 0) mbar_wait(bar_w, 0);
+            constexpr uint32_t idesc = instr_desc(96);
+            const uint32_t a_hi = base + kZtcSmA, a_lo = a_hi + kZtcPlane, w0 = base + kZtcSmW;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                for (int j = 0; j < kChunks / 2; ++j) {
+                    const uint32_t aoff = (uint32_t)(2 * j * kZtcPitch);
+                    const uint32_t wb = w0 + dy * kWDyBytes + 2 * j * kWChunkBytes;
+                    const uint64_t b_hi = smem_desc(wb, kWChunkBytes, 128), b_lo = smem_desc(wb + 96 * 16, kWChunkBytes, 128);
+                    const uint32_t d = tmem + (uint32_t)(dy * 96);
+                    umma_tf32(d, smem_desc(a_hi + aoff, kZtcPitch, 128), b_hi, idesc, j != 0);
+                    umma_tf32(d, smem_desc(a_hi + aoff, kZtcPitch, 128), b_lo, idesc, 1u);
+                    umma_tf32(d, smem_desc(a_lo + aoff, kZtcPitch, 128), b_hi, idesc, 1u);
+                }
+            }
+            umma_commit(bar_mma);
+        }
+        // ---- epilogue: rows that are first entries go out as Z rows (1152 contiguous bytes per row)
+        mbar_wait(bar_mma, (uint32_t)(it & 1));
+        tc_fence_after();
+        {
+            const int q = warp & 3, half = warp >> 2;
+            const int m = q * 32 + lane;
+            const bool on = flags[m] != 0;
+            float* zrow = a.Z + (size_t)(e0 - e_begin + m) * 288;
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+#pragma unroll 3
+            for (int cc = 0; cc < 18; ++cc) {
+                const int col = half * 144 + cc * 8;
+                uint32_t v[8];
+                SHPL_TMEM_LD8(taddr + col, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (on) {
+                    *reinterpret_cast<float4*>(zrow + col) = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+                    *reinterpret_cast<float4*>(zrow + col + 4) = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                                      // the A planes, the flags and the accumulators are free again
+        tc_fence_after();
+    }
+    if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
     }
 }
@@ -805,7 +834,8 @@ extern "C" int shpl_pool_conv3x3_forward(const float* dst, const float* src, con
                 SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_conv_z_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kZtcSmemRequest));
                 z_attr = true;
             }
-            shpl_conv_z_tc_kernel<<<(nnz_max + 127) / 128, kZtcThreads, kZtcSmemRequest, s>>>(za);
+            const int ztiles = (nnz_max + 127) / 128;
+            shpl_conv_z_tc_kernel<<<ztiles < shpl::sm_count() ? ztiles : shpl::sm_count(), kZtcThreads, kZtcSmemRequest, s>>>(za);
             shpl::count_launches(1);
             if (int rc = shpl::check_launch("shpl_conv_z_tc_kernel")) return rc;
         } else {

@@ -935,6 +935,88 @@ struct HeavyArgs {
     int eu;                                          // exact kernel: entries per warp per round
 };
 
+// One warp sums the entries [pb, pe) of a cell in stored order into part[warp][0:nv] (shared memory).  kGroups (few
+// channels, nv <= 16): lanes would idle if they mapped to channel vectors only, so E = 32 / nv lane groups take entries
+// pb + g, pb + g + E, ... (kGatherUnroll gathers in flight each) and the group sums are then added in group order --
+// still a fixed tree.
+template <typename V, bool kGroups>
+__device__ __forceinline__ void heavy_piece_sum(const HeavyArgs& a, const V* __restrict__ src, int pb, int pe, V* __restrict__ part,
+                                                int warp, int lane) {
+    if constexpr (kGroups) {
+        // few channels (nv <= 16): lanes would idle if they mapped to channel vectors only.  E = 32 / nv lane groups
+        // take entries pb + g, pb + g + E, ... (kGatherUnroll gathers in flight each); the group sums are
+        // then added in group order -- still a fixed tree.
+        const int nv = a.nv, E = 32 / nv;
+        const int g = lane / nv, q = lane - g * nv;
+        V acc = vzero((V*)nullptr);
+        if (g < E) {
+            for (int c = pb + g; c < pe; c += E * kGatherUnroll) {
+                V x[kGatherUnroll];
+                float w[kGatherUnroll];
+#pragma unroll
+                for (int j = 0; j < kGatherUnroll; ++j) {
+                    const int k = c + j * E;
+                    w[j] = 0.f;
+                    x[j] = vzero((V*)nullptr);
+                    if (k < pe) {
+                        w[j] = __ldg(a.val + k);
+                        x[j] = __ldg(src + (size_t)__ldg(a.idx + k) * a.gather_stride + q);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kGatherUnroll; ++j)
+                    if (c + j * E < pe) axpy(acc, w[j], x[j]);
+            }
+        }
+        V tot = vshfl(acc, q);                                  // group 0
+        for (int e = 1; e < E; ++e) tot = vadd(tot, vshfl(acc, e * nv + q));
+        if (lane < nv) part[warp * nv + lane] = tot;
+    } else {
+    for (int q0 = 0; q0 < a.nv; q0 += 64) {
+        V acc[2];
+        acc[0] = vzero((V*)nullptr);
+        acc[1] = vzero((V*)nullptr);
+        for (int c = pb; c < pe; c += 32) {
+            int my_p = 0;
+            float my_w = 0.f;
+            if (c + lane < pe) {
+                my_p = __ldg(a.idx + c + lane);
+                my_w = __ldg(a.val + c + lane);
+            }
+            const int cnt = min(32, pe - c);
+            for (int e = 0; e < cnt; e += kGatherUnroll) {
+                V x[kGatherUnroll][2];
+                float w[kGatherUnroll];
+#pragma unroll
+                for (int j = 0; j < kGatherUnroll; ++j) {
+                    const int p = __shfl_sync(kFull, my_p, (e + j) & 31);
+                    w[j] = __shfl_sync(kFull, my_w, (e + j) & 31);
+                    const V* row = src + (size_t)p * a.gather_stride;
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        const int q = q0 + b * 32 + lane;
+                        if (e + j < cnt && q < a.nv) x[j][b] = __ldg(row + q);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kGatherUnroll; ++j) {
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        const int q = q0 + b * 32 + lane;
+                        if (e + j < cnt && q < a.nv) axpy(acc[b], w[j], x[j][b]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int q = q0 + b * 32 + lane;
+            if (q < a.nv) part[warp * a.nv + q] = acc[b];
+        }
+    }
+    }
+}
+
 template <int W, bool kGroups>
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads) shpl_pool_heavy_kernel(HeavyArgs a) {
     using V = typename VecOf<W>::type;
@@ -957,79 +1039,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
         const int piece = crank * kWarps + warp;
         const int pb = beg + (int)(L * piece / (kClusterSize * kWarps));
         const int pe = beg + (int)(L * (piece + 1) / (kClusterSize * kWarps));
-        if constexpr (kGroups) {
-            // few channels (nv <= 16): lanes would idle if they mapped to channel vectors only.  E = 32 / nv lane groups
-            // take entries pb + g, pb + g + E, ... (kGatherUnroll gathers in flight each); the group sums are
-            // then added in group order -- still a fixed tree.
-            const int nv = a.nv, E = 32 / nv;
-            const int g = lane / nv, q = lane - g * nv;
-            V acc = vzero((V*)nullptr);
-            if (g < E) {
-                for (int c = pb + g; c < pe; c += E * kGatherUnroll) {
-                    V x[kGatherUnroll];
-                    float w[kGatherUnroll];
-#pragma unroll
-                    for (int j = 0; j < kGatherUnroll; ++j) {
-                        const int k = c + j * E;
-                        w[j] = 0.f;
-                        x[j] = vzero((V*)nullptr);
-                        if (k < pe) {
-                            w[j] = __ldg(a.val + k);
-                            x[j] = __ldg(src + (size_t)__ldg(a.idx + k) * a.gather_stride + q);
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < kGatherUnroll; ++j)
-                        if (c + j * E < pe) axpy(acc, w[j], x[j]);
-                }
-            }
-            V tot = vshfl(acc, q);                                  // group 0
-            for (int e = 1; e < E; ++e) tot = vadd(tot, vshfl(acc, e * nv + q));
-            if (lane < nv) part[warp * nv + lane] = tot;
-        } else {
-        for (int q0 = 0; q0 < a.nv; q0 += 64) {
-            V acc[2];
-            acc[0] = vzero((V*)nullptr);
-            acc[1] = vzero((V*)nullptr);
-            for (int c = pb; c < pe; c += 32) {
-                int my_p = 0;
-                float my_w = 0.f;
-                if (c + lane < pe) {
-                    my_p = __ldg(a.idx + c + lane);
-                    my_w = __ldg(a.val + c + lane);
-                }
-                const int cnt = min(32, pe - c);
-                for (int e = 0; e < cnt; e += kGatherUnroll) {
-                    V x[kGatherUnroll][2];
-                    float w[kGatherUnroll];
-#pragma unroll
-                    for (int j = 0; j < kGatherUnroll; ++j) {
-                        const int p = __shfl_sync(kFull, my_p, (e + j) & 31);
-                        w[j] = __shfl_sync(kFull, my_w, (e + j) & 31);
-                        const V* row = src + (size_t)p * a.gather_stride;
-#pragma unroll
-                        for (int b = 0; b < 2; ++b) {
-                            const int q = q0 + b * 32 + lane;
-                            if (e + j < cnt && q < a.nv) x[j][b] = __ldg(row + q);
-                        }
-                    }
-#pragma unroll
-                    for (int j = 0; j < kGatherUnroll; ++j) {
-#pragma unroll
-                        for (int b = 0; b < 2; ++b) {
-                            const int q = q0 + b * 32 + lane;
-                            if (e + j < cnt && q < a.nv) axpy(acc[b], w[j], x[j][b]);
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const int q = q0 + b * 32 + lane;
-                if (q < a.nv) part[warp * a.nv + q] = acc[b];
-            }
-        }
-        }
+        heavy_piece_sum<V, kGroups>(a, src, pb, pe, part, warp, lane);
         __syncthreads();
         for (int q = threadIdx.x; q < a.nv; q += kThreads) {
             V s = part[q];
@@ -1047,6 +1057,112 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
             }
         }
         cluster.sync();      // the peers' shared memory stays valid until CTA 0 has read it
+    }
+}
+
+// ---- Long listed cells split over MANY CTAs (the Zipf stress case has one cell with 178 000 entries: on a single
+// cluster it kept 8 of 148 SMs busy for 600 us).  A cell of L > exact_len entries is cut into P = ceil(L / kPieceLen)
+// contiguous pieces; a CTA sums one piece (its 8 warps take sub-pieces in stored order, the warp sums are added in
+// order) into partial[piece][0:C] in the caller's workspace; shpl_pool_heavy_combine_kernel then adds the P partials in
+// order.  A fixed tree that depends only on L: deterministic, within fp32 rounding of the sequential sum.
+constexpr int kPieceLen = 2048;
+constexpr int kMaxListed = 4096;           // listed cells whose piece counts fit the shared-memory prefix array
+
+struct SplitArgs {
+    int* prefix;                 // workspace: [kMaxListed + 1] exclusive prefix of the piece counts (written by CTA 0)
+    void* partial;               // workspace: [total pieces][nv] vectors
+    int max_pieces;              // capacity of `partial`
+};
+
+__device__ __forceinline__ int heavy_pieces(const HeavyArgs& a, int cell) {
+    const long long L = (long long)__ldg(a.ptr + cell + 1) - __ldg(a.ptr + cell);
+    if (L <= a.exact_len || L <= a.skip_le) return 0;          // the exact kernel's / the main kernel's
+    return (int)((L + kPieceLen - 1) / kPieceLen);
+}
+
+// exclusive prefix of the piece counts of the listed cells into pre[0 .. n] (shared memory); all threads call it
+__device__ __forceinline__ void heavy_prefix(const HeavyArgs& a, int n, int* pre, int* warp_tot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = (n + kThreads - 1) / kThreads;              // contiguous chunk of cells per thread
+    const int h0 = threadIdx.x * per, h1 = min(h0 + per, n);
+    int sum = 0;
+    for (int h = h0; h < h1; ++h) sum += heavy_pieces(a, __ldg(a.list + h));
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    int run = base + incl - sum;
+    for (int h = h0; h < h1; ++h) {
+        pre[h] = run;
+        run += heavy_pieces(a, __ldg(a.list + h));
+    }
+    if (threadIdx.x == kThreads - 1) pre[n] = run;
+    __syncthreads();
+}
+
+template <int W, bool kGroups>
+__global__ void __launch_bounds__(kThreads) shpl_pool_heavy_split_kernel(HeavyArgs a, SplitArgs sa) {
+    using V = typename VecOf<W>::type;
+    extern __shared__ float4 heavy_smem[];
+    V* part = reinterpret_cast<V*>(heavy_smem);                 // [kWarps][nv] warp sums
+    __shared__ int pre[kMaxListed + 1];
+    __shared__ int warp_tot[kWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_heavy = min(min(__ldg(a.count_dev), a.list_cap), kMaxListed);
+    heavy_prefix(a, n_heavy, pre, warp_tot);
+    if (blockIdx.x == 0)
+        for (int h = threadIdx.x; h <= n_heavy; h += kThreads) sa.prefix[h] = pre[h];
+    const int total = min(pre[n_heavy], sa.max_pieces);
+    const V* src = static_cast<const V*>(a.gather_in);
+    V* partial = static_cast<V*>(sa.partial);
+    for (int g = blockIdx.x; g < total; g += gridDim.x) {
+        int lo = 0, hi = n_heavy;                               // the cell h with pre[h] <= g < pre[h + 1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (pre[mid] <= g) lo = mid; else hi = mid;
+        }
+        const int h = lo, p = g - pre[h], P = pre[h + 1] - pre[h];
+        const int cell = __ldg(a.list + h);
+        const int beg = __ldg(a.ptr + cell);
+        const long long L = (long long)__ldg(a.ptr + cell + 1) - beg;
+        const int qb = beg + (int)(L * p / P), qe = beg + (int)(L * (p + 1) / P);      // this CTA's piece
+        const long long Lp = qe - qb;
+        const int pb = qb + (int)(Lp * warp / kWarps), pe = qb + (int)(Lp * (warp + 1) / kWarps);
+        heavy_piece_sum<V, kGroups>(a, src, pb, pe, part, warp, lane);
+        __syncthreads();
+        for (int q = threadIdx.x; q < a.nv; q += kThreads) {
+            V s = part[q];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) s = vadd(s, part[w * a.nv + q]);
+            partial[(size_t)g * a.nv + q] = s;
+        }
+        __syncthreads();
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads) shpl_pool_heavy_combine_kernel(HeavyArgs a, SplitArgs sa) {
+    using V = typename VecOf<W>::type;
+    const int n_heavy = min(min(__ldg(a.count_dev), a.list_cap), kMaxListed);
+    const V* partial = static_cast<const V*>(sa.partial);
+    const V* addend = static_cast<const V*>(a.addend);
+    V* out = static_cast<V*>(a.out);
+    for (int h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+        const int g0 = __ldg(sa.prefix + h), g1 = min(__ldg(sa.prefix + h + 1), sa.max_pieces);
+        if (g1 <= g0) continue;
+        const int cell = __ldg(a.list + h);
+        for (int q = threadIdx.x; q < a.nv; q += kThreads) {
+            V s = partial[(size_t)g0 * a.nv + q];
+            for (int g = g0 + 1; g < g1; ++g) s = vadd(s, partial[(size_t)g * a.nv + q]);
+            if (addend != nullptr) s = vadd(addend[(size_t)cell * a.addend_stride + q], s);
+            out[(size_t)cell * a.out_stride + q] = s;
+        }
     }
 }
 
@@ -1538,10 +1654,122 @@ extern "C" int shpl_pool_backward_dual(const float* g_fused_bev, const float* g_
     return launch_jobs(js, 2, static_cast<cudaStream_t>(stream), "shpl_pool_backward_dual");
 }
 
+// ---- no-concat ("sparse-only") forms, SURVEY.md 8(d): the producer of the destination map writes its channels straight
+// into the fused buffer, the op writes only the pooled channels (zeros for cells that receive nothing); the backward
+// reads the pooled channels of g_fused in place and g_dst is simply the view g_fused[:, :C_d] -- no slice copy.
+namespace {
+JobSpec into_job(const float* src, const int32_t* ptr, const int32_t* key, const int32_t* idx, const float* val, int nnz_max,
+                 int heavy_len, int n_rows, int C_s, float* fused, int fused_stride, int chan_off) {
+    JobSpec j;
+    j.gather_in = src;
+    j.gather_stride = C_s;
+    j.c_pool = C_s;
+    j.pool_out = fused + chan_off;
+    j.pool_out_stride = fused_stride;
+    j.ptr = ptr;
+    j.key = key;
+    j.idx = idx;
+    j.val = val;
+    j.nnz_max = nnz_max;
+    j.heavy_len = heavy_len;
+    j.n_cells = n_rows;
+    return j;
+}
+}  // namespace
+
+extern "C" int shpl_pool_forward_into(const float* src, const int32_t* ptr, const int32_t* key, const int32_t* idx,
+                                      const float* val, int32_t nnz_max, int32_t heavy_len, int32_t n_rows, int32_t n_src,
+                                      int32_t C_s, float* fused, int32_t fused_stride, int32_t chan_off, void* stream) {
+    SHPL_REQUIRE(n_rows >= 0 && n_src >= 0 && C_s > 0 && chan_off >= 0 && fused_stride >= chan_off + C_s, SHPL_ERR_INVALID_ARGUMENT,
+                 "shpl_pool_forward_into: bad sizes n_rows=%d n_src=%d C_s=%d fused_stride=%d chan_off=%d", n_rows, n_src, C_s,
+                 fused_stride, chan_off);
+    SHPL_REQUIRE(src && ptr && idx && val && fused, SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_forward_into: null pointer");
+    if (n_rows == 0) return SHPL_OK;
+    const JobSpec j = into_job(src, ptr, key, idx, val, nnz_max, heavy_len, n_rows, C_s, fused, fused_stride, chan_off);
+    return launch_jobs(&j, 1, static_cast<cudaStream_t>(stream), "shpl_pool_forward_into");
+}
+
+extern "C" int shpl_pool_forward_into_dual(const float* bev, const float* img, const int32_t* row_ptr, const int32_t* csr_row,
+                                           const int32_t* csr_src, const float* csr_val, const int32_t* pix_ptr,
+                                           const int32_t* csrT_pix, const int32_t* csrT_dst, const float* csrT_val,
+                                           int32_t nnz_max, int32_t heavy_len, int32_t n_rows, int32_t C_b, int32_t n_src,
+                                           int32_t C_i, float* fused_bev, float* fused_img, void* stream) {
+    SHPL_REQUIRE(n_rows >= 0 && n_src >= 0 && C_b > 0 && C_i > 0, SHPL_ERR_INVALID_ARGUMENT,
+                 "shpl_pool_forward_into_dual: bad sizes n_rows=%d n_src=%d C_b=%d C_i=%d", n_rows, n_src, C_b, C_i);
+    SHPL_REQUIRE(bev && img && row_ptr && csr_src && csr_val && pix_ptr && csrT_dst && csrT_val && fused_bev && fused_img,
+                 SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_forward_into_dual: null pointer");
+    JobSpec js[2];
+    js[0] = into_job(img, row_ptr, csr_row, csr_src, csr_val, nnz_max, heavy_len, n_rows, C_i, fused_bev, C_b + C_i, C_b);
+    js[1] = into_job(bev, pix_ptr, csrT_pix, csrT_dst, csrT_val, nnz_max, heavy_len, n_src, C_b, fused_img, C_i + C_b, C_i);
+    return launch_jobs(js, 2, static_cast<cudaStream_t>(stream), "shpl_pool_forward_into_dual");
+}
+
+extern "C" int shpl_pool_backward_from(const float* g_fused, int32_t g_stride, int32_t chan_off, const int32_t* ptrT,
+                                       const int32_t* keyT, const int32_t* idxT, const float* valT, int32_t nnz_max,
+                                       int32_t heavy_len, int32_t n_rows, int32_t n_src, int32_t C_s, float* g_src, void* stream) {
+    SHPL_REQUIRE(n_rows >= 0 && n_src >= 0 && C_s > 0 && chan_off >= 0 && g_stride >= chan_off + C_s, SHPL_ERR_INVALID_ARGUMENT,
+                 "shpl_pool_backward_from: bad sizes n_rows=%d n_src=%d C_s=%d g_stride=%d chan_off=%d", n_rows, n_src, C_s, g_stride,
+                 chan_off);
+    SHPL_REQUIRE(g_fused && ptrT && idxT && valT && g_src, SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_backward_from: null pointer");
+    if (n_src == 0) return SHPL_OK;
+    JobSpec j;
+    j.gather_in = g_fused + chan_off;
+    j.gather_stride = g_stride;
+    j.c_pool = C_s;
+    j.pool_out = g_src;
+    j.pool_out_stride = C_s;
+    j.ptr = ptrT;
+    j.key = keyT;
+    j.idx = idxT;
+    j.val = valT;
+    j.nnz_max = nnz_max;
+    j.heavy_len = heavy_len;
+    j.n_cells = n_src;
+    return launch_jobs(&j, 1, static_cast<cudaStream_t>(stream), "shpl_pool_backward_from");
+}
+
+namespace {
+size_t heavy_ws_pieces(int64_t nnz_max, int32_t list_cap) {
+    // ceil(L / kPieceLen) summed over the listed cells <= nnz_max / kPieceLen + number of listed cells
+    const int listed = list_cap < kMaxListed ? (list_cap > 0 ? list_cap : 0) : kMaxListed;
+    return (size_t)(nnz_max > 0 ? nnz_max : 0) / kPieceLen + (size_t)listed + 1;
+}
+}  // namespace
+
+extern "C" size_t shpl_pool_heavy_workspace_bytes(int32_t C, int64_t nnz_max, int32_t list_cap) {
+    if (C <= 0) return 0;
+    return 256 + (size_t)(kMaxListed + 64) * sizeof(int) + heavy_ws_pieces(nnz_max, list_cap) * (size_t)C * sizeof(float);
+}
+
+static int pool_heavy_impl(const float* gather_in, int32_t gather_stride, int32_t C, const int32_t* ptr,
+                           const int32_t* idx, const float* val, const int32_t* list, const int32_t* count_dev,
+                           int32_t list_cap, const float* addend, int32_t addend_stride, float* out,
+                           int32_t out_stride, int64_t nnz_max, void* workspace, size_t workspace_bytes, void* stream);
+
 extern "C" int shpl_pool_heavy(const float* gather_in, int32_t gather_stride, int32_t C, const int32_t* ptr,
                                const int32_t* idx, const float* val, const int32_t* list, const int32_t* count_dev,
                                int32_t list_cap, const float* addend, int32_t addend_stride, float* out,
                                int32_t out_stride, void* stream) {
+    return pool_heavy_impl(gather_in, gather_stride, C, ptr, idx, val, list, count_dev, list_cap, addend, addend_stride, out,
+                           out_stride, 0, nullptr, 0, stream);
+}
+
+extern "C" int shpl_pool_heavy_split(const float* gather_in, int32_t gather_stride, int32_t C, const int32_t* ptr,
+                                     const int32_t* idx, const float* val, const int32_t* list, const int32_t* count_dev,
+                                     int32_t list_cap, const float* addend, int32_t addend_stride, float* out,
+                                     int32_t out_stride, int64_t nnz_max, void* workspace, size_t workspace_bytes, void* stream) {
+    SHPL_REQUIRE(workspace != nullptr && shpl::aligned(workspace, 16), SHPL_ERR_INVALID_ARGUMENT,
+                 "shpl_pool_heavy_split: workspace must be a 16-byte aligned device buffer");
+    SHPL_REQUIRE(workspace_bytes >= shpl_pool_heavy_workspace_bytes(C, nnz_max, list_cap), SHPL_ERR_WORKSPACE_TOO_SMALL,
+                 "shpl_pool_heavy_split: workspace %zu < %zu bytes", workspace_bytes, shpl_pool_heavy_workspace_bytes(C, nnz_max, list_cap));
+    return pool_heavy_impl(gather_in, gather_stride, C, ptr, idx, val, list, count_dev, list_cap, addend, addend_stride, out,
+                           out_stride, nnz_max, workspace, workspace_bytes, stream);
+}
+
+static int pool_heavy_impl(const float* gather_in, int32_t gather_stride, int32_t C, const int32_t* ptr,
+                           const int32_t* idx, const float* val, const int32_t* list, const int32_t* count_dev,
+                           int32_t list_cap, const float* addend, int32_t addend_stride, float* out,
+                           int32_t out_stride, int64_t nnz_max, void* workspace, size_t workspace_bytes, void* stream) {
     SHPL_REQUIRE(gather_in && ptr && idx && val && list && count_dev && out, SHPL_ERR_INVALID_ARGUMENT,
                  "shpl_pool_heavy: null pointer");
     SHPL_REQUIRE(C > 0 && list_cap >= 0, SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_heavy: bad sizes C=%d list_cap=%d", C,
@@ -1593,6 +1821,38 @@ extern "C" int shpl_pool_heavy(const float* gather_in, int32_t gather_stride, in
         if (int rc = shpl::check_launch("shpl_pool_heavy_exact_kernel")) return rc;
     }
     const bool groups = a.nv * 2 <= 32;       // few channels: lane groups over entries (see the kernel)
+    if (workspace != nullptr && list_cap <= kMaxListed) {
+        // long cells split over many CTAs + in-order combine (two launches); partials in the caller's workspace
+        (void)workspace_bytes;
+        SplitArgs sa{};
+        uint8_t* wsb = static_cast<uint8_t*>(workspace);
+        sa.prefix = reinterpret_cast<int*>(wsb);
+        sa.partial = wsb + 256 + (size_t)(kMaxListed + 64) * sizeof(int) - ((size_t)(kMaxListed + 64) * sizeof(int)) % 16;
+        sa.max_pieces = (int)heavy_ws_pieces(nnz_max, list_cap);
+        const size_t smem_s = (size_t)kWarps * a.nv * sizeof(float) * w;
+        const unsigned grid_s = (unsigned)(shpl::sm_count() * 2);
+#define SHPL_LAUNCH_SPLIT(WW, GG)                                                                                       \
+    do {                                                                                                                \
+        if (smem_s > 48 * 1024)                                                                                         \
+            SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_pool_heavy_split_kernel<WW, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)); \
+        shpl_pool_heavy_split_kernel<WW, GG><<<grid_s, kThreads, smem_s, s>>>(a, sa);                                   \
+    } while (0)
+        if (w == 4 && groups) SHPL_LAUNCH_SPLIT(4, true);
+        else if (w == 4) SHPL_LAUNCH_SPLIT(4, false);
+        else if (w == 2 && groups) SHPL_LAUNCH_SPLIT(2, true);
+        else if (w == 2) SHPL_LAUNCH_SPLIT(2, false);
+        else if (groups) SHPL_LAUNCH_SPLIT(1, true);
+        else SHPL_LAUNCH_SPLIT(1, false);
+#undef SHPL_LAUNCH_SPLIT
+        shpl::count_launches(1);
+        if (int rc = shpl::check_launch("shpl_pool_heavy_split_kernel")) return rc;
+        const unsigned grid_c = (unsigned)(list_cap < 256 ? list_cap : 256);
+        if (w == 4) shpl_pool_heavy_combine_kernel<4><<<grid_c, kThreads, 0, s>>>(a, sa);
+        else if (w == 2) shpl_pool_heavy_combine_kernel<2><<<grid_c, kThreads, 0, s>>>(a, sa);
+        else shpl_pool_heavy_combine_kernel<1><<<grid_c, kThreads, 0, s>>>(a, sa);
+        shpl::count_launches(1);
+        return shpl::check_launch("shpl_pool_heavy_combine_kernel");
+    }
 #define SHPL_LAUNCH_HEAVY(WW, GG)                                                                                       \
     do {                                                                                                                \
         if (smem > 48 * 1024)                                                                                           \

@@ -236,7 +236,7 @@ class SparsePoolPlan:
         k = 1 if by_pixel else 0
         return (ctypes.c_void_p(self.addr("heavy_pix" if by_pixel else "heavy_row")),
                 ctypes.c_void_p(self.addr("heavy_count") + 4 * k), self.heavy_cap,
-                None if self.n_heavy is None else self.n_heavy[k])
+                None if self.n_heavy is None else self.n_heavy[k], self.entry_bound, self.device)
 
 
 def plan_from_coo(indices, values, source_index, n_rows, src_hw, device=None):
@@ -265,12 +265,15 @@ def plan_from_coo(indices, values, source_index, n_rows, src_hw, device=None):
 
 def _run_heavy(heavy, gather_in, gather_stride, C, ptr, idx, val, addend, addend_stride, out, out_stride):
     """shpl_pool_heavy on the listed heavy cells, unless the host already knows there are none."""
-    lst, count_dev, cap, expected = heavy
+    lst, count_dev, cap, expected, nnz_max, device = heavy
     if expected == 0:
         return
-    rc = _lib.shpl_pool_heavy(gather_in, gather_stride, C, _ptr(ptr), _ptr(idx), _ptr(val), lst, count_dev,
-                              int(cap), addend, addend_stride, out, out_stride, _stream())
-    _cabi.check(rc, "shpl_pool_heavy")
+    # long cells are split over many CTAs (shpl_pool_heavy_split); the partial sums live in per-stream scratch
+    need = int(_lib.shpl_pool_heavy_workspace_bytes(int(C), int(nnz_max), int(cap)))
+    ws = scratch("heavy", device, need)
+    rc = _lib.shpl_pool_heavy_split(gather_in, gather_stride, C, _ptr(ptr), _ptr(idx), _ptr(val), lst, count_dev,
+                                    int(cap), addend, addend_stride, out, out_stride, int(nnz_max), _ptr(ws), ws.numel(), _stream())
+    _cabi.check(rc, "shpl_pool_heavy_split")
 
 
 def _off(t, n_floats):
@@ -301,6 +304,76 @@ def pool_backward(g_fused, csrT, n_rows, C_d, n_src, C_s, want_dst=True):
     _cabi.check(rc, "shpl_pool_backward")
     _run_heavy(heavy, _off(g_fused, C_d), C_d + C_s, C_s, ptrT, idxT, valT, None, 0, _ptr(g_src), C_s)
     return g_dst, g_src
+
+
+def pool_forward_into(fused, src, csr, n_rows, n_src, chan_off):
+    """No-concat forward (shpl_pool_forward_into): fused [n_rows, F] gets its channels chan_off : chan_off + C_s
+    overwritten with the pooled sums (zeros for cells that receive nothing); the other channels are left alone."""
+    ptr, key, idx, val, nnz_max, heavy = csr
+    C_s, F = src.shape[-1], fused.shape[-1]
+    rc = _lib.shpl_pool_forward_into(_ptr(src), _ptr(ptr), _ptr(key), _ptr(idx), _ptr(val), int(nnz_max), _cabi.HEAVY_LEN,
+                                     n_rows, n_src, C_s, _ptr(fused), F, int(chan_off), _stream())
+    _cabi.check(rc, "shpl_pool_forward_into")
+    _run_heavy(heavy, _ptr(src), C_s, C_s, ptr, idx, val, None, 0, _off(fused, chan_off), F)
+    return fused
+
+
+def pool_backward_from(g_fused, csrT, n_rows, n_src, C_s, chan_off):
+    """No-concat backward (shpl_pool_backward_from): the gradient of the gathered map from the pooled channels of
+    g_fused, read in place; the gradient of the destination map is the view g_fused[:, :chan_off]."""
+    ptrT, keyT, idxT, valT, nnz_max, heavy = csrT
+    F = g_fused.shape[-1]
+    g_src = torch.empty((n_src, C_s), dtype=torch.float32, device=g_fused.device)
+    rc = _lib.shpl_pool_backward_from(_ptr(g_fused), F, int(chan_off), _ptr(ptrT), _ptr(keyT), _ptr(idxT), _ptr(valT),
+                                      int(nnz_max), _cabi.HEAVY_LEN, n_rows, n_src, C_s, _ptr(g_src), _stream())
+    _cabi.check(rc, "shpl_pool_backward_from")
+    _run_heavy(heavy, _off(g_fused, chan_off), F, C_s, ptrT, idxT, valT, None, 0, _ptr(g_src), C_s)
+    return g_src
+
+
+class SparsePoolIntoFunction(torch.autograd.Function):
+    """One direction of SHPL in the no-concat form (SURVEY.md 8(d) "sparse-only"): `fused` [B,H,W,C_d+C_s] already
+    holds the destination map in its first C_d channels (its producer wrote there); the pooled channels are written in
+    place and the same tensor is returned.  Backward: the gradient handed back for `fused` is g_fused itself (no slice
+    copy; its pooled channels mean nothing to a producer that wrote only the first C_d), the gradient of `src` comes
+    from the deterministic transpose-CSR kernel."""
+
+    @staticmethod
+    def forward(ctx, fused, src, plan, transposed):
+        require_cuda(fused, "fused buffer")
+        require_cuda(src, "source feature map")
+        if fused.dtype != torch.float32 or src.dtype != torch.float32:
+            raise ValueError("SHPL feature maps must be float32 (the reference's dtype)")
+        if not fused.is_contiguous():
+            raise ValueError("the fused buffer must be contiguous (NHWC)")
+        if transposed:
+            csr, n_rows, n_src = plan.by_pixel(), plan.n_src, plan.n_rows
+        else:
+            csr, n_rows, n_src = plan.by_row(), plan.n_rows, plan.n_src
+        src_c = src.contiguous()
+        C_s, F = src_c.shape[-1], fused.shape[-1]
+        if src_c.numel() != n_src * C_s or fused.numel() != n_rows * F or F <= C_s:
+            raise ValueError("maps %s / %s do not match the plan (%d cells <- %d cells)" % (tuple(fused.shape), tuple(src.shape), n_rows, n_src))
+        pool_forward_into(fused, src_c, csr, n_rows, n_src, F - C_s)
+        ctx.mark_dirty(fused)
+        ctx.plan, ctx.transposed, ctx.src_shape, ctx.chan_off = plan, transposed, tuple(src.shape), F - C_s
+        return fused
+
+    @staticmethod
+    def backward(ctx, g_fused):
+        plan = ctx.plan
+        if ctx.transposed:
+            csrT, n_rows, n_src = plan.by_row(), plan.n_src, plan.n_rows
+        else:
+            csrT, n_rows, n_src = plan.by_pixel(), plan.n_rows, plan.n_src
+        g = g_fused.contiguous()
+        g_src = pool_backward_from(g, csrT, n_rows, n_src, ctx.src_shape[-1], ctx.chan_off)
+        return g, g_src.reshape(ctx.src_shape), None, None
+
+
+def sparse_pool_into(fused, src, plan, transposed=False):
+    """fused [B,Hd,Wd,Cd+Cs] (first Cd channels already written), src [B,Hs,Ws,Cs] -> fused, pooled channels filled in."""
+    return SparsePoolIntoFunction.apply(fused, src, plan, transposed)
 
 
 class SparsePoolFunction(torch.autograd.Function):

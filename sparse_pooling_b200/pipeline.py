@@ -44,9 +44,16 @@ class _LayerState:
 
 
 class FramePipeline:
-    def __init__(self, layers, n_points_max, device):
+    """no_concat=True runs the layers in the "sparse-only" form of SURVEY.md 8(d): the producer of a destination map is
+    taken to have written its channels straight into the fused buffer (L.fused_bev[..., :C_b], L.fused_img[..., :C_i]),
+    so the forward writes only the pooled channels (shpl_pool_forward_into) and the single-direction backward computes
+    only the gradient of the gathered map (shpl_pool_backward_from): the gradient of the destination map is the view
+    g_fused[..., :C_d].  The `bev` argument of forward_layer is then unused for single-direction layers."""
+
+    def __init__(self, layers, n_points_max, device, no_concat=False):
         self.device = device
         self.n_max = int(n_points_max)
+        self.no_concat = bool(no_concat)
         self.layers = [_LayerState(s, self.n_max, device) for s in layers]
 
     # -- correspondence build: shpl_build_avod per layer (different strides, same points) --
@@ -75,6 +82,16 @@ class FramePipeline:
         L = self.layers[i]
         s, pl = L.spec, L.plan
         bound = int(nnz_max) if nnz_max else pl.capacity
+        if self.no_concat:
+            if s.dual:
+                rc = _lib.shpl_pool_forward_into_dual(_p(bev), _p(img), *L.plan_ptrs, bound, 0, s.R, s.c_bev, s.Q, s.c_img,
+                                                      _p(L.fused_bev), _p(L.fused_img), stream)
+                _cabi.check(rc, "shpl_pool_forward_into_dual")
+                return
+            rc = _lib.shpl_pool_forward_into(_p(img), _p(pl.row_ptr), _p(pl.csr_row), _p(pl.csr_src), _p(pl.csr_val),
+                                             bound, 0, s.R, s.Q, s.c_img, _p(L.fused_bev), s.c_bev + s.c_img, s.c_bev, stream)
+            _cabi.check(rc, "shpl_pool_forward_into")
+            return
         if s.dual:
             rc = _lib.shpl_pool_forward_dual(_p(bev), _p(img), *L.plan_ptrs, bound, 0, s.R, s.c_bev, s.Q, s.c_img,
                                              _p(L.fused_bev), _p(L.fused_img), stream)
@@ -93,6 +110,11 @@ class FramePipeline:
             rc = _lib.shpl_pool_backward_dual(_p(g_fused_bev), _p(g_fused_img), *L.plan_ptrs, bound, 0, s.R, s.c_bev,
                                               s.Q, s.c_img, _p(L.g_bev), _p(L.g_img), stream)
             _cabi.check(rc, "shpl_pool_backward_dual")
+            return
+        if self.no_concat:                                   # g_bev is the view g_fused_bev[..., :C_b]: nothing to do for it
+            rc = _lib.shpl_pool_backward_from(_p(g_fused_bev), s.c_bev + s.c_img, s.c_bev, _p(pl.pix_ptr), _p(pl.csrT_pix),
+                                              _p(pl.csrT_dst), _p(pl.csrT_val), bound, 0, s.R, s.Q, s.c_img, _p(L.g_img), stream)
+            _cabi.check(rc, "shpl_pool_backward_from")
             return
         rc = _lib.shpl_pool_backward(_p(g_fused_bev), _p(pl.pix_ptr), _p(pl.csrT_pix), _p(pl.csrT_dst), _p(pl.csrT_val),
                                      bound, 0, s.R, s.c_bev, s.Q, s.c_img, _p(L.g_bev), _p(L.g_img), stream)

@@ -375,15 +375,24 @@ def concat_bn_op(inputs, axis, training, bn_modules=None):
 
 
 def sparse_pool_layer(inputs, feature_depths, M, img_index_flip=None, bv_index=None, use_bn=False, training=True,
-                      bn_modules=None):
+                      bn_modules=None, out=None):
     """sparse_pool_utils.py:61-92.
 
     inputs = [input_bv, input_img] NHWC float32 CUDA tensors; feature_depths =
     [C_img, C_bev] (depths of the pooled maps, :62); M a SparseTensor (or the dict
     from produce_sparse_pooling_input); img->bev runs when img_index_flip is given,
     bev->img when bv_index is not None (its content is ignored, :79).
-    Returns (bv_fused, img_fused)."""
+    Returns (bv_fused, img_fused).
+
+    out (extension, SURVEY.md 8(d) "sparse-only"): (bv_fused_buffer, img_fused_buffer or None) -- preallocated fused maps
+    whose leading channels ARE inputs[0] / inputs[1] (their producers wrote straight into them: inputs[k] must be the
+    view out[k][..., :C]).  Then no concat copy is made: only the pooled channels are written, and the buffers are
+    returned."""
     input_bv, input_img = inputs[0], inputs[1]
+    if out is not None:
+        if use_bn:
+            raise ValueError("out= (no-concat form) cannot be combined with use_bn")
+        return _sparse_pool_layer_into(input_bv, input_img, feature_depths, M, img_index_flip, bv_index, out)
     ops.require_cuda(input_bv, "inputs[0]")
     ops.require_cuda(input_img, "inputs[1]")
     plan = None
@@ -422,6 +431,32 @@ def sparse_pool_layer(inputs, feature_depths, M, img_index_flip=None, bv_index=N
             img_fused = ops.sparse_pool(input_img, input_bv, plan, transposed=True)
     else:
         img_fused = input_img
+    return bv_fused, img_fused
+
+
+def _sparse_pool_layer_into(input_bv, input_img, feature_depths, M, img_index_flip, bv_index, out):
+    ops.require_cuda(input_bv, "inputs[0]")
+    ops.require_cuda(input_img, "inputs[1]")
+    bv_buf, img_buf = out[0], out[1]
+    plan = _resolve_plan(M, img_index_flip, input_bv.shape[1] * input_bv.shape[2], (input_img.shape[1], input_img.shape[2]),
+                         input_bv.device)
+    _check_oob(plan)
+
+    def leading_view(buf, x, what):
+        if buf.data_ptr() != x.data_ptr() or tuple(buf.shape[:3]) != tuple(x.shape[:3]) or x.stride(2) != buf.shape[3]:
+            raise ValueError("%s must be the view out[...][..., :C] of its fused buffer (no-concat form)" % what)
+    bv_fused, img_fused = input_bv, input_img
+    if img_index_flip is not None:
+        leading_view(bv_buf, input_bv, "inputs[0]")
+        if bv_buf.shape[3] != input_bv.shape[3] + input_img.shape[3] or int(feature_depths[0]) != input_img.shape[3]:
+            raise ValueError("fused BEV buffer must have C_bev + C_img channels")
+        bv_fused = ops.sparse_pool_into(bv_buf, input_img, plan, transposed=False)
+    if bv_index is not None:
+        leading_view(img_buf, input_img, "inputs[1]")
+        if img_buf.shape[3] != input_img.shape[3] + input_bv.shape[3] or int(feature_depths[1]) != input_bv.shape[3]:
+            raise ValueError("fused image buffer must have C_img + C_bev channels")
+        _announce_dual()
+        img_fused = ops.sparse_pool_into(img_buf, input_bv, plan, transposed=True)
     return bv_fused, img_fused
 
 

@@ -33,7 +33,9 @@ def test_header_declares_the_expected_entry_points():
         "shpl_bev_grid_dims", "shpl_bev_workspace_bytes", "shpl_bev_slices",
         "shpl_mv3d_workspace_bytes", "shpl_mv3d_voxelize", "shpl_lidar_workspace_bytes", "shpl_lidar_to_cam",
         "shpl_flip_point_cloud", "shpl_mv3d_project_augment", "shpl_augment_fv_index",
-        "shpl_conv3x3_workspace_bytes", "shpl_pool_conv3x3_forward"])
+        "shpl_conv3x3_workspace_bytes", "shpl_pool_conv3x3_forward",
+        "shpl_pool_forward_into", "shpl_pool_forward_into_dual", "shpl_pool_backward_from",
+        "shpl_pool_heavy_workspace_bytes", "shpl_pool_heavy_split"])
 
 
 def test_library_exports_every_declared_symbol(lib):
@@ -44,7 +46,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_binding_covers_the_header(lib):
     from sparse_pooling_b200 import _cabi
     assert sorted(_cabi.SIGNATURES) == declared_functions()
-    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 8
+    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 9
 
 
 def test_workspace_query_grows_with_n(lib):
@@ -203,7 +205,7 @@ def test_header_is_plain_c_and_links_from_c(tmp_path, lib):
     subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, str(src), "-o", str(exe),
                     "-L", libdir, "-lshpl", "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
-    assert out[0] == out[1] == "8" and out[2] == "512"
+    assert out[0] == out[1] == "9" and out[2] == "512"
     from sparse_pooling_b200 import _cabi
     assert int(out[3]) == ctypes.sizeof(_cabi.ShplPlan)                   # the ctypes mirror of struct shpl_plan has its layout
     cxx = tmp_path / "abi.cpp"

@@ -812,3 +812,63 @@ def test_stacked_frames_with_listed_cells(shpl):
         gd, gs = cref.backward(g[k], o_ref["Mij_pool"], val, o_ref["img_index_flip_pool"], C, (Hi, Wi, C))
         np.testing.assert_array_equal(tb.grad[k].cpu().numpy(), gd)
         np.testing.assert_array_equal(ti.grad[k].cpu().numpy(), gs)
+
+
+# ------------------------------------------------------------------ no-concat ("sparse-only") forms, SURVEY.md 8(d)
+@pytest.mark.parametrize("C_b,C_i,n,skew", [(32, 32, 3000, "uniform"), (16, 64, 5000, "ground"), (256, 256, 2000, "uniform"), (4, 12, 900, "zipf")])
+def test_no_concat_forms_equal_the_concat_forms_bit_for_bit(shpl, C_b, C_i, n, skew):
+    """shpl_pool_forward_into writes only the pooled channels of a fused buffer whose destination channels its producer
+    already wrote; shpl_pool_backward_from reads the pooled channels of g_fused in place.  Same values as the concat
+    forms (and therefore as the oracle), the untouched channels stay untouched."""
+    from sparse_pooling_b200 import ops
+    bev_hw, img_hw = (60, 70), (30, 50)
+    d = synth.direct_pairs(11, n, bev_hw, (img_hw[1], img_hw[0]), skew=skew)
+    o = shpl.produce_sparse_pooling_input({k: np.array(v, copy=True) for k, v in d.items()})
+    plan = o["shpl_plan"]
+    rng = np.random.default_rng(5)
+    bev = rng.standard_normal((1,) + bev_hw + (C_b,), dtype=np.float32)
+    img = rng.standard_normal((1,) + img_hw + (C_i,), dtype=np.float32)
+    tb, ti = torch.from_numpy(bev).cuda(), torch.from_numpy(img).cuda()
+    ref = shpl.sparse_pool(tb, ti, plan)                                   # concat form (bit-exact vs the oracle elsewhere)
+    buf = torch.full((1,) + bev_hw + (C_b + C_i,), 7.0, device="cuda")
+    buf[..., :C_b] = tb                                                    # "the producer wrote its channels there"
+    out = ops.sparse_pool_into(buf, ti, plan)
+    assert out.data_ptr() == buf.data_ptr()
+    np.testing.assert_array_equal(out.cpu().numpy(), ref.cpu().numpy())
+    # backward: gradient of the gathered map from g_fused in place; the destination gradient is a view
+    g = torch.from_numpy(rng.standard_normal(tuple(ref.shape), dtype=np.float32)).cuda()
+    R, Q = bev_hw[0] * bev_hw[1], img_hw[0] * img_hw[1]
+    gd_ref, gs_ref = ops.pool_backward(g.reshape(R, -1), plan.by_pixel(), R, C_b, Q, C_i)
+    gs = ops.pool_backward_from(g.reshape(R, -1), plan.by_pixel(), R, Q, C_i, C_b)
+    np.testing.assert_array_equal(gs.cpu().numpy(), gs_ref.cpu().numpy())
+    np.testing.assert_array_equal(g.reshape(R, -1)[:, :C_b].cpu().numpy(), gd_ref.cpu().numpy())
+    # through the drop-in layer with out= and autograd
+    buf2 = torch.zeros((1,) + bev_hw + (C_b + C_i,), device="cuda")
+    buf2[..., :C_b] = tb
+    ti2 = ti.clone().requires_grad_(True)
+    fused, same_img = shpl.sparse_pool_layer([buf2[..., :C_b], ti2], [C_i, C_b], o, img_index_flip=o["img_index_flip_pool"], out=(buf2, None))
+    assert same_img is ti2
+    np.testing.assert_array_equal(fused.detach().cpu().numpy(), ref.cpu().numpy())
+    fused.backward(g)
+    np.testing.assert_array_equal(ti2.grad.reshape(Q, -1).cpu().numpy(), gs_ref.cpu().numpy())
+
+
+def test_no_concat_dual_forward_in_one_launch(shpl):
+    from sparse_pooling_b200 import _cabi, ops
+    bev_hw, img_hw, C = (44, 50), (23, 75), 64
+    d = synth.direct_pairs(2, 4000, bev_hw, (img_hw[1], img_hw[0]))
+    o = shpl.produce_sparse_pooling_input({k: np.array(v, copy=True) for k, v in d.items()})
+    plan = o["shpl_plan"]
+    rng = np.random.default_rng(6)
+    tb = torch.from_numpy(rng.standard_normal((1,) + bev_hw + (C,), dtype=np.float32)).cuda()
+    ti = torch.from_numpy(rng.standard_normal((1,) + img_hw + (C,), dtype=np.float32)).cuda()
+    ref_b, ref_i = ops.sparse_pool_dual(tb, ti, plan)
+    fb = torch.zeros_like(ref_b)
+    fi = torch.zeros_like(ref_i)
+    fb[..., :C] = tb
+    fi[..., :C] = ti
+    rc = _cabi.lib.shpl_pool_forward_into_dual(ops._ptr(tb), ops._ptr(ti), *plan.ptrs8(), int(plan.entry_bound), 0, plan.n_rows, C,
+                                               plan.n_src, C, ops._ptr(fb), ops._ptr(fi), ops._stream())
+    assert rc == 0
+    np.testing.assert_array_equal(fb.cpu().numpy(), ref_b.cpu().numpy())
+    np.testing.assert_array_equal(fi.cpu().numpy(), ref_i.cpu().numpy())
