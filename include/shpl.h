@@ -87,6 +87,13 @@ const char* shpl_last_error(void);
  * threads).  bench.py differences it around the timed region ("gpu_launches"). */
 uint64_t shpl_kernel_launches(void);
 
+/* Memory-safety evidence without compute-sanitizer: `make -C sparse_pooling_b200/csrc debug` builds libshpl_debug.so with
+ * in-kernel checks of every gather index, entry range and output slot against the caller's sizes.
+ * shpl_debug_checks_enabled(): 1 in that build, 0 in the product library (where the checks are compiled out).
+ * shpl_debug_check_failures(): failed checks so far (synchronises the device; always 0 in the product library). */
+int     shpl_debug_checks_enabled(void);
+int64_t shpl_debug_check_failures(void);
+
 /* Bytes of scratch the shpl_build_* / shpl_plan_from_coo calls need for up to
  * n_max candidate pairs. */
 size_t shpl_build_workspace_bytes(int64_t n_max);

@@ -54,6 +54,8 @@ SIGNATURES = {
     "shpl_abi_version": (ctypes.c_int, []),
     "shpl_last_error": (ctypes.c_char_p, []),
     "shpl_kernel_launches": (ctypes.c_uint64, []),
+    "shpl_debug_checks_enabled": (ctypes.c_int, []),
+    "shpl_debug_check_failures": (c_int64, []),
     "shpl_build_workspace_bytes": (c_size_t, [c_int64]),
     "shpl_gen_input_avod": (ctypes.c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32,
                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(kThreads) shpl_pairs_kernel(PairsArgs a, int u
     const bool pix_ok = cd.vp >= 0 && cd.vp < a.src_h && cd.up >= 0 && cd.up < a.src_w;
     const bool ok = pix_ok && r >= 0 && r < (long long)a.n_rows;
     const int pix = cd.vp * a.src_w + cd.up;
+    SHPL_DASSERT(k >= 0 && k < a.n && j >= 0 && j <= i);          // compacted slots never run ahead of the candidate index
     if (a.mij) { a.mij[2 * k] = r; a.mij[2 * k + 1] = k; }
     if (a.flip) { a.flip[3 * k] = 0; a.flip[3 * k + 1] = cd.vp; a.flip[3 * k + 2] = cd.up; }
     if (a.mval_out) a.mval_out[k] = w;
@@ -357,6 +358,7 @@ __global__ void __launch_bounds__(kThreads) shpl_finalize_kernel(FinalArgs a, in
         int lb = w1;
         if (j < j1) {
             lb = lower_bound_key(items, w0, w1, (unsigned)j);
+            SHPL_DASSERT(lb >= 0 && lb <= n);
             ptr[j] = ebase + lb;
             if (is_row && j == n_keys) {
                 a.counts[2] = n - lb;
@@ -385,6 +387,8 @@ __global__ void __launch_bounds__(kThreads) shpl_finalize_kernel(FinalArgs a, in
         const unsigned long long ir = by_row[j];
         if ((unsigned)(ir >> 32) < (unsigned)a.plan.n_rows) {
             const unsigned k = (unsigned)ir;
+            SHPL_DASSERT((int)k < n && a.ws.rowk[k] >= a.row_base && a.ws.rowk[k] < a.row_base + a.plan.n_rows &&
+                         a.ws.pixk[k] >= a.pix_base && a.ws.pixk[k] < a.pix_base + a.plan.n_src);
             a.plan.csr_row[ebase + j] = a.ws.rowk[k];
             a.plan.csr_src[ebase + j] = a.ws.pixk[k];
             a.plan.csr_val[ebase + j] = a.ws.valk[k];

@@ -43,6 +43,23 @@ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 
 
 #ifdef __CUDACC__
+// ---- in-kernel index checks of the DEBUG build (make debug -> libshpl_debug.so; compiled out of the product library).
+// compute-sanitizer is closed on this pool, so this is the memory-safety evidence: every gather index, entry range and
+// output slot the kernels compute is checked against the caller's sizes; a failure is counted (and the first few are
+// printed) instead of trapping, so that a whole test run reports a total.  tools/memsafety_run.py reads the counter.
+#ifdef SHPL_DEBUG_CHECKS
+extern __device__ unsigned long long g_debug_failures;
+#define SHPL_DASSERT(cond)                                                                                        \
+    do {                                                                                                          \
+        if (!(cond)) {                                                                                            \
+            if (atomicAdd(&::shpl::g_debug_failures, 1ull) < 8ull)                                                \
+                printf("SHPL_DASSERT failed: %s (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); \
+        }                                                                                                         \
+    } while (0)
+#else
+#define SHPL_DASSERT(cond) ((void)0)
+#endif
+
 // ---- single-pass prefix over CTAs (decoupled look-back), shared by the builder and the feeder
 constexpr unsigned kFull = 0xffffffffu;
 constexpr unsigned long long kFlagAgg = 1ull << 62;

@@ -160,6 +160,7 @@ struct ConvArgs {
     const uint32_t* busy;        // bitmap of the cells that receive pooled features, or NULL (no pooled half)
     const int* ptr;              // CSR offsets by cell: ptr[c] - ptr[0] = the Z row of a busy cell
     const float* Z;              // [entries][9 taps][32]: W_pooled[tap]^T . pooled[cell], from the Z kernel
+    int z_rows;                  // entries Z holds (debug build: every gathered Z row is checked against it)
     int relu;
     int frames, H, W;
     int tiles_x, tiles_y, n_tiles;
@@ -330,6 +331,7 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
                 for (int t = 0; t < 9; ++t) {
                     const int nb = (f * a.H + gy + t / 3 - 1) * a.W + gx + t % 3 - 1;
                     const bool on = (near9 >> t) & 1u;
+                    SHPL_DASSERT(!on || (nb >= 0 && nb < a.frames * a.H * a.W));
                     const int off = on ? __ldg(a.ptr + nb) : 0;
                     zrow[t] = on ? (off - e_begin) * 9 + t : -1;
                 }
@@ -369,6 +371,7 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
                 for (int t = 0; t < 9; ++t) {
                     if (!((any >> t) & 1u)) continue;        // warp-uniform: nobody in this warp has a busy neighbour at tap t
                     if (zrow[t] >= 0) {
+                        SHPL_DASSERT(zrow[t] / 9 < a.z_rows);
                         const float4* z = reinterpret_cast<const float4*>(a.Z + (size_t)zrow[t] * 32);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -518,7 +521,8 @@ __global__ void __launch_bounds__(kZtcThreads, 1) shpl_conv_z_tc_kernel(ZArgs a)
 #pragma unroll
             for (int j = 0; j < 16; ++j) {                    // the 16 gathered rows in flight together
                 const int p = __shfl_sync(0xffffffffu, idx_l, j);
-                x[j] = (ew + j < e_end) ? __ldg(a.src + (size_t)p * 32 + lane) : 0.f;
+                SHPL_DASSERT(ew + j >= e_end || p >= 0);
+            x[j] = (ew + j < e_end) ? __ldg(a.src + (size_t)p * 32 + lane) : 0.f;
             }
             const unsigned firsts = __ballot_sync(0xffffffffu, first_l) & 0xffffu;
             uint8_t* hi_p = gbase + kZtcSmA + (lane >> 2) * kZtcPitch + (lane & 3) * 4;
@@ -744,7 +748,7 @@ ConvWorkspace carve(void* ws, long long cells, long long nnz_max) {
 }
 
 int launch_dense(const float* in, int in_pitch, float* out, const float* wprep, const float* scale, const float* shift, int relu,
-                 const uint32_t* busy, const int* ptr, const float* Z, int frames, int H, int W, cudaStream_t s) {
+                 const uint32_t* busy, const int* ptr, const float* Z, int z_rows, int frames, int H, int W, cudaStream_t s) {
     CUtensorMap map_in, map_out;
     if (int rc = make_map(&map_in, in, frames, H, W, in_pitch, kHaloY, kHaloX, false)) return rc;
     if (int rc = make_map(&map_out, out, frames, H, W, kC, kTileY, kTileX, true)) return rc;
@@ -755,6 +759,7 @@ int launch_dense(const float* in, int in_pitch, float* out, const float* wprep, 
     a.busy = busy;
     a.ptr = ptr;
     a.Z = Z;
+    a.z_rows = z_rows;
     a.relu = relu;
     a.frames = frames;
     a.H = H;
@@ -848,6 +853,6 @@ extern "C" int shpl_pool_conv3x3_forward(const float* dst, const float* src, con
             if (int rc = shpl::check_launch("shpl_conv_z_kernel")) return rc;
         }
     }
-    if (int rc = launch_dense(dst, C_d, out, c.wprep, scale, shift, relu, sparse ? c.busy : nullptr, ptr, c.Z, frames, H, W, s)) return rc;
+    if (int rc = launch_dense(dst, C_d, out, c.wprep, scale, shift, relu, sparse ? c.busy : nullptr, ptr, c.Z, nnz_max, frames, H, W, s)) return rc;
     return SHPL_OK;
 }

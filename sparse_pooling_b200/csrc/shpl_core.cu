@@ -36,6 +36,32 @@ int sm_count() {
 
 }  // namespace shpl
 
+#ifdef SHPL_DEBUG_CHECKS
+namespace shpl { __device__ unsigned long long g_debug_failures; }      // zero-initialised; one copy for all translation units (-rdc)
+#endif
+
+// Failed in-kernel index checks so far: always 0 in the product library (the checks are compiled out); the debug
+// build (make debug) counts them on the device.  Synchronises the device.
+extern "C" int64_t shpl_debug_check_failures(void) {
+#ifdef SHPL_DEBUG_CHECKS
+    unsigned long long n = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(&n, shpl::g_debug_failures, sizeof(n)) != cudaSuccess) return -1;
+    return (int64_t)n;
+#else
+    return 0;
+#endif
+}
+
+// 1 when the library was built with the in-kernel checks (libshpl_debug.so), else 0.
+extern "C" int shpl_debug_checks_enabled(void) {
+#ifdef SHPL_DEBUG_CHECKS
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 extern "C" int shpl_abi_version(void) { return SHPL_ABI_VERSION; }
 extern "C" const char* shpl_last_error(void) { return shpl::g_error; }
 namespace shpl { uint64_t launches(); }

@@ -155,6 +155,7 @@ struct Job {
     int vd, vs;              // vectors per cell: dense part / pooled part (either may be 0)
     int vd_shift, vs_shift;  // log2 or -1
     int n_cells;
+    int n_gather;            // rows of gather_in (debug build: every gathered index is checked against it)
     int add;                 // 1: pool_out[c] = dense_in[c] + sum (vd == vs); 0: concat form
     int heavy_len;           // > 0: cells with more entries are left to shpl_pool_heavy (treated as empty here)
     int rows_per_tile;       // narrow: cells per warp tile
@@ -219,7 +220,7 @@ constexpr int kLongUnroll = 4;
 // there in ascending k: the same roundings in the same order as the sequential walk, bit for bit.
 template <typename V>
 __device__ __forceinline__ V long_row_sum(const V* __restrict__ src, int src_stride, const int* __restrict__ idx,
-                                          const float* __restrict__ val, int beg, int end, int nv, int lane) {
+                                          const float* __restrict__ val, int beg, int end, int nv, int lane, int n_gather) {
     const int E = 32 / nv;
     const int sub = lane / nv, q = lane - sub * nv;
     const bool active = sub < E;
@@ -232,6 +233,7 @@ __device__ __forceinline__ V long_row_sum(const V* __restrict__ src, int src_str
             prod[u] = vzero((V*)nullptr);
             if (active && k < end) {
                 const int p = __ldg(idx + k);
+                SHPL_DASSERT((unsigned)p < (unsigned)n_gather);
                 const float w = __ldg(val + k);
                 prod[u] = vscale(w, __ldg(src + (size_t)p * src_stride + q));
             }
@@ -252,11 +254,12 @@ template <typename V, bool kAdd>
 __device__ __noinline__ void long_cells(const V* __restrict__ src, int src_stride, const int* __restrict__ ptr,
                                         const int* __restrict__ idx, const float* __restrict__ val, V* __restrict__ out,
                                         int out_stride, const V* __restrict__ addend, int add_stride, int nv,
-                                        unsigned longs, int lane) {
+                                        unsigned longs, int lane, int n_gather) {
     for (unsigned m = longs; m; m &= m - 1) {
         const int r = __ffs(m) - 1;
         const int beg = __ldg(ptr + r), end = __ldg(ptr + r + 1);
-        V acc = long_row_sum<V>(src, src_stride, idx, val, beg, end, nv, lane);
+        SHPL_DASSERT(beg >= 0 && beg <= end);
+        V acc = long_row_sum<V>(src, src_stride, idx, val, beg, end, nv, lane, n_gather);
         if (lane < nv) {
             if constexpr (kAdd) acc = vadd(ld_stream(addend + r * add_stride + lane), acc);
             st_stream(out + r * out_stride + lane, acc);
@@ -272,7 +275,8 @@ __device__ __forceinline__ void pool_tile(const V* __restrict__ src, int src_str
                                           const int* __restrict__ idx, const float* __restrict__ val,
                                           V* __restrict__ out, int out_stride, const V* __restrict__ addend,
                                           int add_stride, int nv, int shift, int rows, int heavy_len, int lane,
-                                          int lo, int hi) {
+                                          int lo, int hi, int n_gather) {
+    SHPL_DASSERT(lo >= 0 && lo <= hi);
     // lo, hi: this lane's cell offsets ptr[lane], ptr[lane+1] (0, 0 beyond `rows`), loaded by the caller
     // together with the dense loads so that the two latencies overlap
     if (heavy_len > 0 && hi - lo > heavy_len) hi = lo;         // heavy cell: shpl_pool_heavy writes it
@@ -324,12 +328,16 @@ __device__ __forceinline__ void pool_tile(const V* __restrict__ src, int src_str
                 w[j] = __ldg(val + k + j);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = __ldg(src + (size_t)p[j] * src_stride + q);
+            for (int j = 0; j < 4; ++j) {
+                SHPL_DASSERT((unsigned)p[j] < (unsigned)n_gather);
+                x[j] = __ldg(src + (size_t)p[j] * src_stride + q);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) axpy(acc, w[j], x[j]);
         }
         for (; k < end; ++k) {
             const int p = __ldg(idx + k);
+            SHPL_DASSERT((unsigned)p < (unsigned)n_gather);
             const float w = __ldg(val + k);
             const V x = __ldg(src + (size_t)p * src_stride + q);
             axpy(acc, w, x);
@@ -339,7 +347,7 @@ __device__ __forceinline__ void pool_tile(const V* __restrict__ src, int src_str
     }
     if (longs != 0u) {
         __syncwarp();      // orders the stores above before the overwrites below (other lanes, same addresses)
-        long_cells<V, kAdd>(src, src_stride, ptr, idx, val, out, out_stride, addend, add_stride, nv, longs, lane);
+        long_cells<V, kAdd>(src, src_stride, ptr, idx, val, out, out_stride, addend, add_stride, nv, longs, lane, n_gather);
     }
 }
 
@@ -387,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, SHPL_NARROW_MIN_CTAS) shpl_pool_narr
         if (jb.vs > 0)
             pool_tile<V, kAdd>(gather_in, jb.gather_stride, jb.ptr + r0, jb.idx, jb.val,
                                pool_out + (size_t)r0 * jb.pool_out_stride, jb.pool_out_stride, din,
-                               jb.dense_in_stride, jb.vs, jb.vs_shift, rows, jb.heavy_len, lane, lo, hi);
+                               jb.dense_in_stride, jb.vs, jb.vs_shift, rows, jb.heavy_len, lane, lo, hi, jb.n_gather);
     }
 }
 
@@ -396,7 +404,8 @@ __global__ void __launch_bounds__(kThreads, SHPL_NARROW_MIN_CTAS) shpl_pool_narr
 template <typename V, int ACC>
 __device__ __forceinline__ void pool_row_wide(const V* __restrict__ src, int src_stride, int beg, int end,
                                               const int* __restrict__ idx, const float* __restrict__ val,
-                                              V* __restrict__ orow, const V* __restrict__ arow, int nv, int lane) {
+                                              V* __restrict__ orow, const V* __restrict__ arow, int nv, int lane, int n_gather) {
+    SHPL_DASSERT(beg >= 0 && beg <= end);
     for (int q0 = 0; q0 < nv; q0 += 32 * ACC) {
         V acc[ACC];
 #pragma unroll
@@ -415,6 +424,7 @@ __device__ __forceinline__ void pool_row_wide(const V* __restrict__ src, int src
 #pragma unroll
                 for (int j = 0; j < kGatherUnroll; ++j) {
                     const int p = __shfl_sync(kFull, my_p, (e + j) & 31);
+                    SHPL_DASSERT(e + j >= cnt || (unsigned)p < (unsigned)n_gather);
                     w[j] = __shfl_sync(kFull, my_w, (e + j) & 31);
                     const V* row = src + (size_t)p * src_stride;
 #pragma unroll
@@ -459,7 +469,7 @@ __device__ __forceinline__ void pool_entries_packed(const V* __restrict__ src, i
                                                     const float* __restrict__ val, int e0, int e1, int e_begin,
                                                     int e_end, V* __restrict__ out, int out_stride,
                                                     const V* __restrict__ addend, int add_stride, int nv,
-                                                    const int* __restrict__ ptr, int heavy_len, int lane) {
+                                                    const int* __restrict__ ptr, int heavy_len, int lane, int n_gather, int n_cells) {
     const int G = 32 / nv;
     const int g = lane / nv, q = lane & (nv - 1);
     int base = e0;
@@ -493,6 +503,7 @@ __device__ __forceinline__ void pool_entries_packed(const V* __restrict__ src, i
             if (k < e_end && g < G) {
                 row[u] = __ldg(key + k);
                 const int p = __ldg(idx + k);
+                SHPL_DASSERT((unsigned)p < (unsigned)n_gather && (unsigned)row[u] < (unsigned)n_cells);
                 const float w = __ldg(val + k);
                 prod[u] = vscale(w, __ldg(src + (size_t)p * src_stride + q));
             }
@@ -559,7 +570,7 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
                                                   const float* __restrict__ val, int e0, int e1, int e_begin,
                                                   int e_end, V* __restrict__ out, int out_stride,
                                                   const V* __restrict__ addend, int add_stride, int nv,
-                                                  const int* __restrict__ ptr, int heavy_len, int lane) {
+                                                  const int* __restrict__ ptr, int heavy_len, int lane, int n_gather, int n_cells) {
     const int prev_row = (e0 > e_begin) ? __ldg(key + e0 - 1) : -1;
     for (int q0 = 0; q0 < nv; q0 += 32 * ACC) {
         int base = e0;
@@ -610,6 +621,7 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
                     const int ej = pos + j;
                     row[j] = __shfl_sync(kFull, my_row, ej & 31);
                     const int p = __shfl_sync(kFull, my_p, ej & 31);
+                    SHPL_DASSERT(ej >= cnt || ((unsigned)p < (unsigned)n_gather && (unsigned)row[j] < (unsigned)n_cells));
                     w[j] = __shfl_sync(kFull, my_w, ej & 31);
                     const V* srow = src + (size_t)p * src_stride;
 #pragma unroll
@@ -726,7 +738,7 @@ __global__ void __launch_bounds__(kThreads, SHPL_WIDE_MIN_CTAS) shpl_pool_wide_k
         if (e0 >= e_end) return;
         pool_entries_wide<V, ACC, SHPL_WIDE_GATHERS>(src, jb.gather_stride, jb.key, jb.idx, jb.val, e0, min(e0 + jb.entry_chunk, e_end),
                                   e_begin, e_end, pout, jb.pool_out_stride, jb.add ? din : nullptr,
-                                  jb.dense_in_stride, jb.vs, jb.ptr, jb.heavy_len, lane);
+                                  jb.dense_in_stride, jb.vs, jb.ptr, jb.heavy_len, lane, jb.n_gather, jb.n_cells);
         return;
     }
     const int r0 = (b - jb.entry_ctas) * kWideTile;
@@ -773,7 +785,7 @@ __global__ void __launch_bounds__(kThreads, SHPL_WIDE_MIN_CTAS) shpl_pool_wide_k
         const int beg = __shfl_sync(kFull, lo, r);
         const int end = __shfl_sync(kFull, hi, r);
         pool_row_wide<V, ACC>(src, jb.gather_stride, beg, end, jb.idx, jb.val, out + r * jb.pool_out_stride,
-                              jb.add ? din + (size_t)(r0 + r) * jb.dense_in_stride : nullptr, jb.vs, lane);
+                              jb.add ? din + (size_t)(r0 + r) * jb.dense_in_stride : nullptr, jb.vs, lane, jb.n_gather);
     }
 }
 
@@ -805,7 +817,7 @@ __global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SH
         if (ACC == 1 && packed_ok(jb)) {      // few vectors per cell: lane groups gather different entries
             pool_entries_packed<V>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.key, jb.idx, jb.val, e0,
                                    min(e0 + jb.entry_chunk, e_end), e_begin, e_end, pout, jb.pool_out_stride,
-                                   kAdd ? din : nullptr, jb.dense_in_stride, jb.vs, jb.ptr, jb.long_len, lane);
+                                   kAdd ? din : nullptr, jb.dense_in_stride, jb.vs, jb.ptr, jb.long_len, lane, jb.n_gather, jb.n_cells);
             return;
         }
         // cells with more than kLongRow entries are left to the stream CTAs (whole-warp sum) or to shpl_pool_heavy:
@@ -814,7 +826,7 @@ __global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SH
         pool_entries_wide<V, ACC, (ACC == 1 ? SHPL_SPARSE_GATHERS : SHPL_SPARSE_GATHERS_WIDE)>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.key, jb.idx, jb.val, e0,
                                 min(e0 + jb.entry_chunk, e_end), e_begin, e_end, pout, jb.pool_out_stride,
                                 kAdd ? din : nullptr, jb.dense_in_stride, jb.vs, jb.ptr,
-                                jb.vs <= 32 ? jb.long_len : jb.heavy_len, lane);
+                                jb.vs <= 32 ? jb.long_len : jb.heavy_len, lane, jb.n_gather, jb.n_cells);
         return;
     }
     const int stream_ctas = jb.stream_ctas;
@@ -907,7 +919,7 @@ __global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SH
         if (longs != 0u)
             long_cells<V, kAdd>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.ptr + r0, jb.idx, jb.val,
                                 pout + (size_t)r0 * jb.pool_out_stride, jb.pool_out_stride,
-                                kAdd ? din + (size_t)r0 * jb.dense_in_stride : nullptr, jb.dense_in_stride, jb.vs, longs, lane);
+                                kAdd ? din + (size_t)r0 * jb.dense_in_stride : nullptr, jb.dense_in_stride, jb.vs, longs, lane, jb.n_gather);
     }
 }
 
@@ -933,6 +945,7 @@ struct HeavyArgs {
     int skip_le;                                     // listed cells up to this many entries were summed by the main kernel
     int exact_len;                                   // listed cells up to this many entries: exact kernel; longer: tree kernel
     int eu;                                          // exact kernel: entries per warp per round
+    int n_gather;                                    // rows of gather_in when the caller knows it (debug checks), else INT_MAX
 };
 
 // One warp sums the entries [pb, pe) of a cell in stored order into part[warp][0:nv] (shared memory).  kGroups (few
@@ -960,6 +973,7 @@ __device__ __forceinline__ void heavy_piece_sum(const HeavyArgs& a, const V* __r
                     x[j] = vzero((V*)nullptr);
                     if (k < pe) {
                         w[j] = __ldg(a.val + k);
+                        SHPL_DASSERT((unsigned)__ldg(a.idx + k) < (unsigned)a.n_gather);
                         x[j] = __ldg(src + (size_t)__ldg(a.idx + k) * a.gather_stride + q);
                     }
                 }
@@ -1140,6 +1154,7 @@ __global__ void __launch_bounds__(kThreads) shpl_pool_heavy_split_kernel(HeavyAr
             V s = part[q];
 #pragma unroll
             for (int w = 1; w < kWarps; ++w) s = vadd(s, part[w * a.nv + q]);
+            SHPL_DASSERT(g < sa.max_pieces && pb >= beg && pe <= beg + (int)L);
             partial[(size_t)g * a.nv + q] = s;
         }
         __syncthreads();
@@ -1309,6 +1324,7 @@ struct JobSpec {            // in floats / cells, before the vector width is cho
     const float* val = nullptr;
     int nnz_max = 0;
     int n_cells = 0;
+    int n_gather = 0x7fffffff;   // rows of gather_in; entry points set it (debug build checks gathered indices against it)
     int add = 0;
     int heavy_len = 0;
 };
@@ -1392,6 +1408,7 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
         o.vd_shift = log2_or_neg(o.vd);
         o.vs_shift = log2_or_neg(o.vs);
         o.n_cells = j.n_cells;
+        o.n_gather = j.n_gather;
         o.add = j.add;
         o.heavy_len = main_kernel_heavy_len(j.heavy_len, j.c_pool);
         max_vs = o.vs > max_vs ? o.vs : max_vs;
@@ -1553,7 +1570,8 @@ extern "C" int shpl_pool_forward(const float* dst, const float* src, const int32
     SHPL_REQUIRE(src && ptr && fused && (C_d == 0 || dst), SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_forward: null pointer");
     SHPL_REQUIRE(idx && val, SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_forward: null idx/val");
     if (n_rows == 0) return SHPL_OK;
-    const JobSpec j = forward_job(dst, src, ptr, key, idx, val, nnz_max, heavy_len, n_rows, C_d, C_s, fused);
+    JobSpec j = forward_job(dst, src, ptr, key, idx, val, nnz_max, heavy_len, n_rows, C_d, C_s, fused);
+    j.n_gather = n_src;
     return launch_jobs(&j, 1, static_cast<cudaStream_t>(stream), "shpl_pool_forward");
 }
 
@@ -1577,6 +1595,7 @@ extern "C" int shpl_pool_backward(const float* g_fused, const int32_t* ptrT, con
     js[0].nnz_max = nnz_max;
     js[0].heavy_len = heavy_len;
     js[0].n_cells = n_src;
+    js[0].n_gather = n_rows;
     // job 1: g_dst = g_fused[:, :C_d]
     if (g_dst != nullptr && C_d > 0) {
         js[1].dense_in = g_fused;
@@ -1602,6 +1621,8 @@ extern "C" int shpl_pool_forward_dual(const float* bev, const float* img, const 
     JobSpec js[2];
     js[0] = forward_job(bev, img, row_ptr, csr_row, csr_src, csr_val, nnz_max, heavy_len, n_rows, C_b, C_i, fused_bev);
     js[1] = forward_job(img, bev, pix_ptr, csrT_pix, csrT_dst, csrT_val, nnz_max, heavy_len, n_src, C_i, C_b, fused_img);
+    js[0].n_gather = n_src;
+    js[1].n_gather = n_rows;
     return launch_jobs(js, 2, static_cast<cudaStream_t>(stream), "shpl_pool_forward_dual");
 }
 
@@ -1632,6 +1653,7 @@ extern "C" int shpl_pool_backward_dual(const float* g_fused_bev, const float* g_
     js[0].val = csr_val;
     js[0].nnz_max = nnz_max;
     js[0].n_cells = n_rows;
+    js[0].n_gather = n_src;
     js[0].add = 1;
     js[0].heavy_len = heavy_len;
     // g_img[p] = g_fused_img[p, :C_i] + sum_{k at pixel p} val * g_fused_bev[row_k, C_b:]
@@ -1649,6 +1671,7 @@ extern "C" int shpl_pool_backward_dual(const float* g_fused_bev, const float* g_
     js[1].val = csrT_val;
     js[1].nnz_max = nnz_max;
     js[1].n_cells = n_src;
+    js[1].n_gather = n_rows;
     js[1].add = 1;
     js[1].heavy_len = heavy_len;
     return launch_jobs(js, 2, static_cast<cudaStream_t>(stream), "shpl_pool_backward_dual");
@@ -1685,7 +1708,8 @@ extern "C" int shpl_pool_forward_into(const float* src, const int32_t* ptr, cons
                  fused_stride, chan_off);
     SHPL_REQUIRE(src && ptr && idx && val && fused, SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_forward_into: null pointer");
     if (n_rows == 0) return SHPL_OK;
-    const JobSpec j = into_job(src, ptr, key, idx, val, nnz_max, heavy_len, n_rows, C_s, fused, fused_stride, chan_off);
+    JobSpec j = into_job(src, ptr, key, idx, val, nnz_max, heavy_len, n_rows, C_s, fused, fused_stride, chan_off);
+    j.n_gather = n_src;
     return launch_jobs(&j, 1, static_cast<cudaStream_t>(stream), "shpl_pool_forward_into");
 }
 
@@ -1701,6 +1725,8 @@ extern "C" int shpl_pool_forward_into_dual(const float* bev, const float* img, c
     JobSpec js[2];
     js[0] = into_job(img, row_ptr, csr_row, csr_src, csr_val, nnz_max, heavy_len, n_rows, C_i, fused_bev, C_b + C_i, C_b);
     js[1] = into_job(bev, pix_ptr, csrT_pix, csrT_dst, csrT_val, nnz_max, heavy_len, n_src, C_b, fused_img, C_i + C_b, C_i);
+    js[0].n_gather = n_src;
+    js[1].n_gather = n_rows;
     return launch_jobs(js, 2, static_cast<cudaStream_t>(stream), "shpl_pool_forward_into_dual");
 }
 
@@ -1725,6 +1751,7 @@ extern "C" int shpl_pool_backward_from(const float* g_fused, int32_t g_stride, i
     j.nnz_max = nnz_max;
     j.heavy_len = heavy_len;
     j.n_cells = n_src;
+    j.n_gather = n_rows;
     return launch_jobs(&j, 1, static_cast<cudaStream_t>(stream), "shpl_pool_backward_from");
 }
 
@@ -1790,6 +1817,7 @@ static int pool_heavy_impl(const float* gather_in, int32_t gather_stride, int32_
     a.addend_stride = addend_stride / w;
     a.out_stride = out_stride / w;
     a.nv = C / w;
+    a.n_gather = 0x7fffffff;
     const size_t smem = (size_t)(kWarps + 1) * a.nv * sizeof(float) * w;
     SHPL_REQUIRE(smem <= 200 * 1024, SHPL_ERR_UNSUPPORTED, "shpl_pool_heavy: C=%d needs %zu bytes of shared memory", C, smem);
     const int clusters = list_cap < 64 ? list_cap : 64;

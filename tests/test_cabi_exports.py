@@ -28,6 +28,7 @@ def lib():
 def test_header_declares_the_expected_entry_points():
     assert declared_functions() == sorted([
         "shpl_abi_version", "shpl_last_error", "shpl_kernel_launches", "shpl_build_workspace_bytes", "shpl_gen_input_avod",
+        "shpl_debug_checks_enabled", "shpl_debug_check_failures",
         "shpl_produce_input", "shpl_build_avod", "shpl_plan_from_coo", "shpl_plan_from_voxel_coords", "shpl_pool_forward", "shpl_pool_backward",
         "shpl_pool_forward_dual", "shpl_pool_backward_dual", "shpl_pool_heavy",
         "shpl_bev_grid_dims", "shpl_bev_workspace_bytes", "shpl_bev_slices",
