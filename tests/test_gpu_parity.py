@@ -872,3 +872,34 @@ def test_no_concat_dual_forward_in_one_launch(shpl):
     assert rc == 0
     np.testing.assert_array_equal(fb.cpu().numpy(), ref_b.cpu().numpy())
     np.testing.assert_array_equal(fi.cpu().numpy(), ref_i.cpu().numpy())
+
+
+def test_value_path_exact_arithmetic_kat_on_the_gpu(shpl):
+    """tests/kat_value.py: the hand-derived literals (duplicate rows, duplicate pixels, an empty row, both directions,
+    both gradients; integer features and power-of-two weights, so no summation order can change a bit) through the
+    drop-in layer and autograd, the no-concat form and the registered custom op."""
+    from tests import kat_value as K
+    from sparse_pooling_b200 import ops
+    M = shpl.SparseTensor(torch.from_numpy(K.MIJ).cuda(), torch.from_numpy(K.VAL).cuda(), K.M_SIZE)
+    flip = torch.from_numpy(K.FLIP).cuda()
+    for dual in (False, True):
+        tb, ti = torch.from_numpy(K.BEV).cuda().requires_grad_(True), torch.from_numpy(K.IMG).cuda().requires_grad_(True)
+        bv, im = shpl.sparse_pool_layer([tb, ti], [2, 2], M, img_index_flip=flip, bv_index=(np.zeros((1, 3)) if dual else None))
+        np.testing.assert_array_equal(bv.detach().cpu().numpy(), K.FUSED_BEV)
+        if dual:
+            np.testing.assert_array_equal(im.detach().cpu().numpy(), K.FUSED_IMG)
+            torch.autograd.backward([bv, im], [torch.from_numpy(K.G_FUSED_BEV).cuda(), torch.from_numpy(K.G_FUSED_IMG).cuda()])
+            np.testing.assert_array_equal(tb.grad.cpu().numpy(), K.G_BEV_DUAL)
+            np.testing.assert_array_equal(ti.grad.cpu().numpy(), K.G_IMG_DUAL)
+        else:
+            bv.backward(torch.from_numpy(K.G_FUSED_BEV).cuda())
+            np.testing.assert_array_equal(tb.grad.cpu().numpy(), K.G_BEV_SINGLE)
+            np.testing.assert_array_equal(ti.grad.cpu().numpy(), K.G_IMG_SINGLE)
+    # bare ops
+    np.testing.assert_array_equal(shpl._sparse_pool_op(M, torch.from_numpy(K.IMG).cuda(), flip, [1, 2, 2, 2]).cpu().numpy(), K.FUSED_BEV[..., 2:])
+    np.testing.assert_array_equal(shpl._sparse_pool_trans_op(M, torch.from_numpy(K.BEV).cuda(), flip, [1, 2, 3, 2]).cpu().numpy(), K.FUSED_IMG[..., 2:])
+    # the no-concat form
+    plan = M._coo_plans[(4, (2, 3))]
+    buf = torch.zeros((1, 2, 2, 4), device="cuda")
+    buf[..., :2] = torch.from_numpy(K.BEV).cuda()
+    np.testing.assert_array_equal(ops.sparse_pool_into(buf, torch.from_numpy(K.IMG).cuda(), plan).cpu().numpy(), K.FUSED_BEV)

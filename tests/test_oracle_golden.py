@@ -407,3 +407,31 @@ def test_conv_oracle_agrees_with_torch_cpu_conv2d():
     assert y1[0, :, :, 0].tolist() == [[4, 6, 4], [6, 9, 6], [4, 6, 4]]
     ya, _ = vo.conv3x3_after_fusion(-np.ones((1, 3, 3, 1)), np.ones((3, 3, 1, 1)), scale=[2.0], shift=[1.0], relu=True)
     assert (ya == 0).all()
+
+
+def test_value_path_exact_arithmetic_kat_numpy_and_c_oracles():
+    """tests/kat_value.py: hand-derived expected values on inputs where every summation order gives the same bits --
+    the limit of what can be pinned for the value path without TensorFlow.  Both oracles must reproduce the literals."""
+    from tests import kat_value as K
+    M = (K.MIJ, K.VAL, K.M_SIZE)
+    bv, im = vo.sparse_pool_layer([K.BEV, K.IMG], [2, 2], M, img_index_flip=K.FLIP, bv_index=np.zeros((1, 3)))
+    np.testing.assert_array_equal(bv, K.FUSED_BEV)
+    np.testing.assert_array_equal(im, K.FUSED_IMG)
+    bv1, im1 = vo.sparse_pool_layer([K.BEV, K.IMG], [2, 2], M, img_index_flip=K.FLIP, bv_index=None)
+    np.testing.assert_array_equal(bv1, K.FUSED_BEV)
+    assert im1 is K.IMG
+    gb, gi = vo.sparse_pool_layer_grad([K.BEV, K.IMG], [2, 2], M, K.FLIP, None, K.G_FUSED_BEV, np.zeros_like(K.IMG))   # img passes through
+    np.testing.assert_array_equal(gb, K.G_BEV_SINGLE)
+    np.testing.assert_array_equal(gi, K.G_IMG_SINGLE)
+    gb, gi = vo.sparse_pool_layer_grad([K.BEV, K.IMG], [2, 2], M, K.FLIP, np.zeros((1, 3)), K.G_FUSED_BEV, K.G_FUSED_IMG)
+    np.testing.assert_array_equal(gb, K.G_BEV_DUAL)
+    np.testing.assert_array_equal(gi, K.G_IMG_DUAL)
+    # the plain-C oracle
+    np.testing.assert_array_equal(cref.forward(K.BEV[0], K.IMG[0], K.MIJ, K.VAL, K.FLIP), K.FUSED_BEV[0])
+    np.testing.assert_array_equal(cref.forward_trans(K.IMG[0], K.BEV[0], K.MIJ, K.VAL, K.FLIP), K.FUSED_IMG[0])
+    gd, gs = cref.backward(K.G_FUSED_BEV[0], K.MIJ, K.VAL, K.FLIP, 2, (2, 3, 2))
+    np.testing.assert_array_equal(gd, K.G_BEV_SINGLE[0])
+    np.testing.assert_array_equal(gs, K.G_IMG_SINGLE[0])
+    gi2, gb2 = cref.backward_trans(K.G_FUSED_IMG[0], K.MIJ, K.VAL, K.FLIP, 2, (2, 2, 2))
+    np.testing.assert_array_equal(gd + gb2, K.G_BEV_DUAL[0])
+    np.testing.assert_array_equal(gi2 + gs, K.G_IMG_DUAL[0])
