@@ -736,6 +736,93 @@ def run_gpu_avod(args, name, cfg):
             print("no-concat leg failed: %r" % (ex,), file=sys.stderr)
             torch.cuda.synchronize()
 
+    # ---- the post-fusion 3x3 conv fused with the pooling (rpn_model.py:335-346, the
+    #      rpn_sparse_pooling_conv_after_fusion switch): conv(concat(bev, pooled)) without ever writing the fused map.
+    #      Dense half on the tcgen05 tensor cores (3xTF32), pooled half as a Z gather in the epilogue.
+    conv = None
+    if (sB.c_bev, sB.c_img) == (32, 32) and not sB.dual and not args.no_conv:
+        try:
+            from sparse_pooling_b200 import conv_fusion
+            wt = randn(3, 3, 64, 32) * 0.1
+            wt_d = wt[:, :, :32].contiguous()
+            outs_c = [torch.empty(1, *sB.bev_hw, 32, device=dev) for _ in range(n_sets)]
+            prologue_build(0)
+            prologue_build(1)
+            torch.cuda.synchronize()
+            plans_c = [pipes[si_].layers[dom].plan for si_ in range(n_sets)]
+            for pl_ in plans_c:
+                pl_.entry_bound = N_MAX
+            ws_c = conv_fusion.conv_workspace(1, sB.bev_hw[0], sB.bev_hw[1], dev, N_MAX)
+
+            def conv_call(k, pooled_=True):
+                si_ = k % n_sets
+                mp_ = maps[si_][dom]
+                if pooled_:
+                    conv_fusion.sparse_pool_conv3x3([mp_["bev"], mp_["img"]], plans_c[si_], None, wt, None, None, True, out=outs_c[si_], workspace=ws_c)
+                else:
+                    conv_fusion.sparse_pool_conv3x3([mp_["bev"], None], None, None, wt_d, None, None, True, out=outs_c[si_], workspace=ws_c)
+
+            def time_conv(pooled_):
+                for k in range(4):
+                    conv_call(k, pooled_)
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    for k in range(4):
+                        conv_call(k, pooled_)
+                for _ in range(3):
+                    gr.replay()
+                e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n_ = 25
+                torch.cuda.synchronize()
+                e0_.record()
+                for _ in range(n_):
+                    gr.replay()
+                e1_.record()
+                torch.cuda.synchronize()
+                return e0_.elapsed_time(e1_) * 1e3 / (4 * n_)
+            us_fused, us_dense = time_conv(True), time_conv(False)
+            # spot check of the fused result against the concat form + a float64 conv on a crop of the map
+            conv_call(0, True)
+            fused_ref = pipes[0].layers[dom].fused_bev
+            pipes[0].forward_layer(dom, maps[0][dom]["bev"], maps[0][dom]["img"], torch.cuda.current_stream().cuda_stream, N_MAX)
+            crop = fused_ref[:, 100:164, 200:328].double().permute(0, 3, 1, 2)
+            ref_c = torch.nn.functional.conv2d(crop, wt.double().permute(3, 2, 0, 1)).clamp_min(0).permute(0, 2, 3, 1)
+            mag_c = torch.nn.functional.conv2d(crop.abs(), wt.double().abs().permute(3, 2, 0, 1)).permute(0, 2, 3, 1)
+            got_c = outs_c[0][:, 101:163, 201:327].double()
+            rel_c = float(((got_c - ref_c).abs() / mag_c.clamp_min(1e-30)).max().item())
+            if not rel_c <= 1e-5:
+                raise SystemExit("bench.py: PARITY CHECK FAILED: fused conv differs from pool -> concat -> conv by %.3e of sum|terms|" % rel_c)
+            R_ = sB.R
+            flops_alg = 2.0 * R_ * 9 * 64 * 32                      # what slim.conv2d(fused 64 -> 32) computes
+            flops_tc = 3 * 2.0 * R_ * 9 * 32 * 32                   # executed on the tensor cores: the dense half, three TF32 products
+            try:
+                bf16_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+                tf_src = "measured bf16 burst peak / 2 (MEASURED_PEAKS.json bf16_tflops)"
+            except Exception:
+                bf16_peak, tf_src = 1590.0, "fallback bf16 1.59 PFLOP/s / 2 (B200_PROFILING.md)"
+            tf32_peak = bf16_peak / 2.0
+            io_bytes = 4.0 * R_ * (32 + 32) + 4.0 * nnz[dom] * 34
+            conv = {"what": "shpl_pool_conv3x3_forward on layer %s: relu(conv3x3(concat(bev, pooled(img)), W[3,3,64,32])) with the fused map never "
+                            "written; CUDA-graph replays, CUDA events; includes the weight prep, the busy-cell bitmap and the Z kernel" % sB.name,
+                    "us_per_call": us_fused, "us_dense_half_only": us_dense,
+                    "max_err_over_sum_abs_terms_on_a_64x128_crop": rel_c,
+                    "roofline": {"bound": "tensor", "unit": "TFLOP/s",
+                                 "achieved": flops_tc / us_dense / 1e6, "peak": tf32_peak, "frac": flops_tc / us_dense / 1e6 / tf32_peak,
+                                 "peak_source": tf_src + "; TF32 dense = half the bf16 rate",
+                                 "note": "dense-half kernel alone (C_s = 0 call): executed tensor flops = 3 TF32 products per fp32 product (3xTF32 "
+                                         "split for 1e-5 parity). The kernel is bound by the tensor core's shared-memory operand fetch at N = 192 "
+                                         "(profiles/r2_conv_*), not by this peak",
+                                 "fp32_equivalent_tflops_of_the_whole_conv": flops_alg / us_fused / 1e6},
+                    "hbm": {"bytes_per_call": io_bytes, "achieved_GBs": io_bytes / us_fused / 1e3, "frac_of_peak": io_bytes / us_fused / 1e3 / peak},
+                    "unfused_bytes": {"pool_forward_concat": sB.bytes_forward(nnz[dom]), "conv_reads_fused_writes_out": 4.0 * R_ * (64 + 32),
+                                      "fused_path": io_bytes}}
+        except SystemExit:
+            raise
+        except Exception as ex:  # pragma: no cover
+            print("conv leg failed: %r" % (ex,), file=sys.stderr)
+            torch.cuda.synchronize()
+
     # ---- e2e: the public drop-in API, frame inputs in pinned host memory, result read back
     class Calib:
         p2 = P
@@ -1005,6 +1092,8 @@ def run_gpu_avod(args, name, cfg):
         }
         if no_concat is not None:
             line["no_concat"] = no_concat
+        if conv is not None:
+            line["conv_after_fusion"] = conv
         if feeder is not None:
             line["feeder"] = feeder
         if cpu is not None:
@@ -1493,6 +1582,7 @@ def main():
     ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle comparison before timing")
     ap.add_argument("--no-feeder", action="store_true", help="skip the feeder / velodyne chain legs (config 2)")
     ap.add_argument("--no-no-concat", action="store_true", help="skip the no-concat (sparse-only) leg")
+    ap.add_argument("--no-conv", action="store_true", help="skip the fused post-fusion conv leg")
     ap.add_argument("--single-step-graphs", action="store_true", help="one CUDA graph per step (no multi-step graph)")
     ap.add_argument("--graph-steps", type=int, default=8, help="consecutive steps captured in one CUDA graph (multiple of 4)")
     args = ap.parse_args()

@@ -293,47 +293,86 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
         const int q = warp;                                  // TMEM lane quadrant
         const int m = q * 32 + lane, yl = m >> 4, xq = m & 15;
         const bool col_ok = xq >= 1 && xq <= kTileX;
+        // ---- The pooled half's lookups, software-pipelined so that no global latency sits on the epilogue's critical path:
+        //   tile i+2: ten threads load the busy-bitmap words of the tile's halo rows (10 rows x 16 columns)
+        //   tile i+1: the words go to shared memory; every thread tests its nine neighbour bits and issues the (few)
+        //             CSR-offset loads of the busy ones, predicated, side by side
+        //   tile i  : offsets -> Z rows; an L1 prefetch of each (one 128-byte line), then the wait for the accumulators
+        const bool pooled = a.busy != nullptr;
+        const int e_begin = pooled ? __ldg(a.ptr) : 0;
+        uint32_t hw_lo = 0u, hw_hi = 0u;           // tid < 10: raw bitmap words of the halo row, tile in flight
+        int hw_sh = 0, hw_nv = 0, hw_ls = 0;       //           bit offset, valid columns, left shift
+        int poff[9];                                // CSR offsets of the busy neighbours (loads in flight)
+        uint32_t pnear = 0u;
+        auto issue_halo = [&](int j) {
+            hw_nv = 0;
+            if (j >= n_mine || tid >= kHaloY) return;
+            int f, y0, x0;
+            tile_coord(j, f, y0, x0);
+            const int yy = y0 - 1 + tid;
+            if (yy < 0 || yy >= a.H) return;
+            const int xs = x0 > 0 ? x0 - 1 : 0;                           // first in-image halo column
+            const long long c = ((long long)f * a.H + yy) * a.W + xs;
+            const long long last = ((long long)a.frames * a.H * a.W - 1) >> 5;
+            const long long wi = c >> 5;
+            hw_lo = __ldg(a.busy + wi);
+            hw_hi = wi + 1 <= last ? __ldg(a.busy + wi + 1) : 0u;
+            hw_sh = (int)(c & 31);
+            hw_ls = xs - (x0 - 1);
+            hw_nv = min(a.W - xs, kHaloX - hw_ls);                       // columns of this row inside the image
+        };
+        auto issue_offsets = [&](int j) {                                 // needs halo_bits of tile j in shared memory
+            int f, y0, x0;
+            tile_coord(j, f, y0, x0);
+            const int gy = y0 + yl, gx = x0 + xq - 1;
+            pnear = 0u;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) pnear |= ((halo_bits[yl + dy] >> (xq > 0 ? xq - 1 : 0)) & 7u) << (3 * dy);
+            if (!(col_ok && gy < a.H && gx < a.W)) pnear = 0u;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int nb = (f * a.H + gy + t / 3 - 1) * a.W + gx + t % 3 - 1;
+                const bool on = (pnear >> t) & 1u;
+                SHPL_DASSERT(!on || (nb >= 0 && nb < a.frames * a.H * a.W));
+                poff[t] = on ? __ldg(a.ptr + nb) : 0;
+            }
+        };
+        auto publish_halo = [&]() {                                       // the words loaded by issue_halo -> shared memory
+            if (tid < kHaloY) {
+                uint32_t bits = 0u;
+                if (hw_nv > 0) {
+                    bits = (uint32_t)(((((uint64_t)hw_hi) << 32) | hw_lo) >> hw_sh) & 0xffffu;
+                    bits &= (1u << hw_nv) - 1u;
+                    bits <<= hw_ls;
+                }
+                halo_bits[tid] = bits;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        };
+        if (pooled && n_mine > 0) {
+            issue_halo(0);
+            publish_halo();
+            issue_offsets(0);
+            issue_halo(1);
+        }
         for (int i = 0; i < n_mine; ++i) {
             const int s = i & 1, u = i >> 1;
             int f, y0, x0;
             tile_coord(i, f, y0, x0);
-            // The pooled half: which of this pixel's nine neighbours receive pooled features, and where their Z rows are.
-            // Ten threads fetch the busy bits of the tile's halo (10 rows x 16 columns) into shared memory; every thread
-            // then tests its nine bits there and issues the (few) CSR-offset loads side by side, predicated -- all of it
-            // before the wait for the accumulators, which hides the latency.
             int zrow[9];
-            if (a.busy != nullptr) {
-                if (tid < kHaloY) {
-                    const int yy = y0 - 1 + tid;
-                    uint32_t bits = 0u;
-                    if (yy >= 0 && yy < a.H) {
-                        const int xs = x0 > 0 ? x0 - 1 : 0;                       // first in-image halo column
-                        const long long c = ((long long)f * a.H + yy) * a.W + xs;
-                        const long long last = ((long long)a.frames * a.H * a.W - 1) >> 5;
-                        const long long wi = c >> 5;
-                        const uint64_t lo = __ldg(a.busy + wi), hi = wi + 1 <= last ? __ldg(a.busy + wi + 1) : 0u;
-                        bits = (uint32_t)(((hi << 32) | lo) >> (c & 31)) & 0xffffu;
-                        const int n_valid = min(a.W - xs, kHaloX - (xs - (x0 - 1)));     // columns of this row inside the image
-                        bits &= (1u << n_valid) - 1u;
-                        bits <<= (xs - (x0 - 1));
-                    }
-                    halo_bits[tid] = bits;
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                const int gy = y0 + yl, gx = x0 + xq - 1;
-                const bool px_ok = col_ok && gy < a.H && gx < a.W;
-                const int e_begin = __ldg(a.ptr);
-                uint32_t near9 = 0u;                                                  // bit t: neighbour of tap t is busy
-#pragma unroll
-                for (int dy = 0; dy < 3; ++dy) near9 |= ((halo_bits[yl + dy] >> (xq > 0 ? xq - 1 : 0)) & 7u) << (3 * dy);
-                if (!px_ok) near9 = 0u;
+            uint32_t zmask = 0u;                 // bit t: this pixel's neighbour at tap t contributes a Z row
+            if (pooled) {
+                zmask = pnear;
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
-                    const int nb = (f * a.H + gy + t / 3 - 1) * a.W + gx + t % 3 - 1;
-                    const bool on = (near9 >> t) & 1u;
-                    SHPL_DASSERT(!on || (nb >= 0 && nb < a.frames * a.H * a.W));
-                    const int off = on ? __ldg(a.ptr + nb) : 0;
-                    zrow[t] = on ? (off - e_begin) * 9 + t : -1;
+                    zrow[t] = ((zmask >> t) & 1u) ? (poff[t] - e_begin) * 9 + t : -1;
+                    // a Z row is one 128-byte line: pull it into L1 now; the loads after the accumulator wait can hit
+                    if (zrow[t] >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.Z + (size_t)zrow[t] * 32));
+                }
+                if (i + 1 < n_mine) {
+                    publish_halo();              // tile i+1's halo bits (loaded during the previous tile)
+                    issue_offsets(i + 1);
+                    issue_halo(i + 2);
                 }
             }
             mbar_wait(bar(BAR_ACC_FULL + s), u & 1);
@@ -362,21 +401,25 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY + s));
-            if (a.busy != nullptr) {
-                // + sum over the busy neighbours, in tap order (a fixed order: deterministic), of their Z rows
-                unsigned any = 0u;
+            if (pooled) {
+                // + sum over the busy neighbours, in tap order (a fixed order: deterministic), of their Z rows.  Round k
+                // handles the k-th busy tap of every lane together, so a warp pays one latency per round and there are as
+                // many rounds as the busiest pixel of the warp has busy neighbours (1-3), not nine.
+                while (__any_sync(0xffffffffu, zmask != 0u)) {
+                    if (zmask != 0u) {
+                        const int t = __ffs(zmask) - 1;
+                        zmask &= zmask - 1u;
+                        int zr = zrow[0];
 #pragma unroll
-                for (int t = 0; t < 9; ++t) any |= __ballot_sync(0xffffffffu, zrow[t] >= 0) ? (1u << t) : 0u;
+                        for (int tt = 1; tt < 9; ++tt) zr = (t == tt) ? zrow[tt] : zr;
+                        SHPL_DASSERT(zr >= 0 && zr / 9 < a.z_rows);
+                        const float4* z = reinterpret_cast<const float4*>(a.Z + (size_t)zr * 32);
+                        float4 zv[8];
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    if (!((any >> t) & 1u)) continue;        // warp-uniform: nobody in this warp has a busy neighbour at tap t
-                    if (zrow[t] >= 0) {
-                        SHPL_DASSERT(zrow[t] / 9 < a.z_rows);
-                        const float4* z = reinterpret_cast<const float4*>(a.Z + (size_t)zrow[t] * 32);
+                        for (int j = 0; j < 8; ++j) zv[j] = __ldg(z + j);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 zv = __ldg(z + j);
-                            o[4 * j] += zv.x; o[4 * j + 1] += zv.y; o[4 * j + 2] += zv.z; o[4 * j + 3] += zv.w;
+                            o[4 * j] += zv[j].x; o[4 * j + 1] += zv[j].y; o[4 * j + 2] += zv[j].z; o[4 * j + 3] += zv[j].w;
                         }
                     }
                 }
@@ -472,9 +515,10 @@ constexpr int kZtcSmBar = kZtcSmW + kWBytes;
 constexpr int kZtcSmFlag = kZtcSmBar + 64;               // first-entry flags, one byte per row
 constexpr int kZtcSmem = kZtcSmFlag + 128 + 128;         // + slack for the 128-byte alignment of the base
 static_assert(kZtcSmW % 128 == 0 && kZtcSmBar % 8 == 0, "Z kernel smem alignment");
-constexpr int kZtcSmemRequest = kZtcSmem > 116 * 1024 ? kZtcSmem : 116 * 1024;   // > half an SM: one CTA (one 512-column TMEM allocation) per SM
+constexpr int kZtcSmemRequest = kZtcSmem;            // ~107 KB: two CTAs per SM
+constexpr int kZtcTmemCols = 256;                    // 192 columns used per pass: two CTAs share the SM's 512
 
-__global__ void __launch_bounds__(kZtcThreads, 1) shpl_conv_z_tc_kernel(ZArgs a) {
+__global__ void __launch_bounds__(kZtcThreads, 2) shpl_conv_z_tc_kernel(ZArgs a) {
     extern __shared__ uint8_t z_smem_raw[];
     __shared__ uint32_t tmem_slot;
     const int e_begin = __ldg(a.ptr), e_end = min(__ldg(a.ptr + a.n_rows), e_begin + a.nnz_max);
@@ -494,7 +538,7 @@ __global__ void __launch_bounds__(kZtcThreads, 1) shpl_conv_z_tc_kernel(ZArgs a)
         for (int t = 0; t < 3; ++t) bulk_load_1d(base + kZtcSmW + t * kWDyBytes, reinterpret_cast<const uint8_t*>(a.wprep) + t * kWDyBytes, kWDyBytes, bar_w);
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kZtcTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -562,44 +606,56 @@ __global__ void __launch_bounds__(kZtcThreads, 1) shpl_conv_z_tc_kernel(ZArgs a)
         tc_fence_before();
         __syncthreads();                                      // A planes + flags complete; the previous tile's TMEM reads are done
         tc_fence_after();
-        if (tid == 0) {
-            if (it == 0) mbar_wait(bar_w, 0);
-            constexpr uint32_t idesc = instr_desc(96);
-            const uint32_t a_hi = base + kZtcSmA, a_lo = a_hi + kZtcPlane, w0 = base + kZtcSmW;
+        // Two passes over the taps (dy = 0, 1 -> 192 columns; dy = 2 -> 96 columns) so that 256 TMEM columns suffice and two
+        // CTAs share an SM: every tile of a KITTI frame is then resident at once (no second wave).
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            const int dy0 = pass * 2, ndy = 2 - pass;
+            if (tid == 0) {
+                if (it == 0 && pass == 0) mbar_wait(bar_w, 0);
+                constexpr uint32_t idesc = instr_desc(96);
+                const uint32_t a_hi = base + kZtcSmA, a_lo = a_hi + kZtcPlane, w0 = base + kZtcSmW;
+                for (int d = 0; d < ndy; ++d) {
+                    const int dy = dy0 + d;
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-#pragma unroll
-                for (int j = 0; j < kChunks / 2; ++j) {
-                    const uint32_t aoff = (uint32_t)(2 * j * kZtcPitch);
-                    const uint32_t wb = w0 + dy * kWDyBytes + 2 * j * kWChunkBytes;
-                    const uint64_t b_hi = smem_desc(wb, kWChunkBytes, 128), b_lo = smem_desc(wb + 96 * 16, kWChunkBytes, 128);
-                    const uint32_t d = tmem + (uint32_t)(dy * 96);
-                    umma_tf32(d, smem_desc(a_hi + aoff, kZtcPitch, 128), b_hi, idesc, j != 0);
-                    umma_tf32(d, smem_desc(a_hi + aoff, kZtcPitch, 128), b_lo, idesc, 1u);
-                    umma_tf32(d, smem_desc(a_lo + aoff, kZtcPitch, 128), b_hi, idesc, 1u);
+                    for (int j = 0; j < kChunks / 2; ++j) {
+                        const uint32_t aoff = (uint32_t)(2 * j * kZtcPitch);
+                        const uint32_t wb = w0 + dy * kWDyBytes + 2 * j * kWChunkBytes;
+                        const uint64_t b_hi = smem_desc(wb, kWChunkBytes, 128), b_lo = smem_desc(wb + 96 * 16, kWChunkBytes, 128);
+                        const uint32_t dcol = tmem + (uint32_t)(d * 96);
+                        umma_tf32(dcol, smem_desc(a_hi + aoff, kZtcPitch, 128), b_hi, idesc, j != 0);
+                        umma_tf32(dcol, smem_desc(a_hi + aoff, kZtcPitch, 128), b_lo, idesc, 1u);
+                        umma_tf32(dcol, smem_desc(a_lo + aoff, kZtcPitch, 128), b_hi, idesc, 1u);
+                    }
+                }
+                umma_commit(bar_mma);
+            }
+            // ---- epilogue of the pass: rows that are first entries go out as (part of) their Z row
+            mbar_wait(bar_mma, (uint32_t)((2 * it + pass) & 1));
+            tc_fence_after();
+            {
+                const int q = warp & 3, half = warp >> 2;
+                const int m = q * 32 + lane;
+                const bool on = flags[m] != 0;
+                float* zrow = a.Z + (size_t)(e0 - e_begin + m) * 288 + dy0 * 96;
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+                const int ncc = ndy * 6;                      // 8-column chunks per half
+#pragma unroll 3
+                for (int cc = 0; cc < ncc; ++cc) {
+                    const int col = half * ncc * 8 + cc * 8;
+                    uint32_t v[8];
+                    SHPL_TMEM_LD8(taddr + col, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (on) {
+                        *reinterpret_cast<float4*>(zrow + col) = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+                        *reinterpret_cast<float4*>(zrow + col + 4) = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+                    }
                 }
             }
-            umma_commit(bar_mma);
-        }
-        // ---- epilogue: rows that are first entries go out as Z rows (1152 contiguous bytes per row)
-        mbar_wait(bar_mma, (uint32_t)(it & 1));
-        tc_fence_after();
-        {
-            const int q = warp & 3, half = warp >> 2;
-            const int m = q * 32 + lane;
-            const bool on = flags[m] != 0;
-            float* zrow = a.Z + (size_t)(e0 - e_begin + m) * 288;
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
-#pragma unroll 3
-            for (int cc = 0; cc < 18; ++cc) {
-                const int col = half * 144 + cc * 8;
-                uint32_t v[8];
-                SHPL_TMEM_LD8(taddr + col, v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (on) {
-                    *reinterpret_cast<float4*>(zrow + col) = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-                    *reinterpret_cast<float4*>(zrow + col + 4) = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
-                }
+            if (pass == 0) {
+                tc_fence_before();
+                __syncthreads();                              // the accumulators are free for the second pass
+                tc_fence_after();
             }
         }
         tc_fence_before();
@@ -607,7 +663,7 @@ __global__ void __launch_bounds__(kZtcThreads, 1) shpl_conv_z_tc_kernel(ZArgs a)
         tc_fence_after();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kZtcTmemCols) : "memory");
     }
 }
 
@@ -840,7 +896,7 @@ extern "C" int shpl_pool_conv3x3_forward(const float* dst, const float* src, con
                 z_attr = true;
             }
             const int ztiles = (nnz_max + 127) / 128;
-            shpl_conv_z_tc_kernel<<<ztiles < shpl::sm_count() ? ztiles : shpl::sm_count(), kZtcThreads, kZtcSmemRequest, s>>>(za);
+            shpl_conv_z_tc_kernel<<<ztiles < 2 * shpl::sm_count() ? ztiles : 2 * shpl::sm_count(), kZtcThreads, kZtcSmemRequest, s>>>(za);
             shpl::count_launches(1);
             if (int rc = shpl::check_launch("shpl_conv_z_tc_kernel")) return rc;
         } else {

@@ -40,9 +40,9 @@ def timeit(fn, iters=10, reps=2):
     return float(np.median(ts))
 
 
-def case(name, bev_hw, img_hw, C, n_pairs, skew, stride=(1, 1), weights=False, peak=6544.0):
+def case(name, bev_hw, img_hw, C, n_pairs, skew, stride=(1, 1), weights=False, peak=6544.0, seed=11):
     dev = torch.device("cuda", 0)
-    d = synth.direct_pairs(11, n_pairs, bev_hw=(bev_hw[0] * stride[1], bev_hw[1] * stride[1]),
+    d = synth.direct_pairs(seed, n_pairs, bev_hw=(bev_hw[0] * stride[1], bev_hw[1] * stride[1]),
                            img_wh=(img_hw[1] * stride[0], img_hw[0] * stride[0]), skew=skew)
     dd = dict(bv_index=torch.from_numpy(d["bv_index"]).to(dev), img_index=torch.from_numpy(d["img_index"]).to(dev),
               bv_size=d["bv_size"], img_size=d["img_size"])
@@ -81,7 +81,7 @@ def case(name, bev_hw, img_hw, C, n_pairs, skew, stride=(1, 1), weights=False, p
     tf, tb = timeit(fwd), timeit(bwd)
     bf = 4 * (R * C + R * 2 * C + nnz * (C + 2) + R + 1)
     bb = 4 * (2 * R * C + nnz * (C + 2) + Q * C + Q + 1)
-    return dict(case=name, R=R, Q=Q, C=C, nnz=nnz, max_row=max_row, skew=skew, build_api_ms=round(build_ms, 3),
+    return dict(case=name, seed=seed, R=R, Q=Q, C=C, nnz=nnz, max_row=max_row, skew=skew, build_api_ms=round(build_ms, 3),
                 fwd_us=round(tf, 1), fwd_GBs=round(bf / tf / 1e3), fwd_frac=round(bf / tf / 1e3 / peak, 3),
                 bwd_us=round(tb, 1), bwd_GBs=round(bb / tb / 1e3), bwd_frac=round(bb / tb / 1e3 / peak, 3))
 
@@ -89,6 +89,8 @@ def case(name, bev_hw, img_hw, C, n_pairs, skew, stride=(1, 1), weights=False, p
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--full", action="store_true", help="the whole BASELINE config-5 grid: nnz {5k,20k,100k,1M} x C {16,32,64,128,256} x "
+                                                        "{uniform, zipf, ground} x seeds 0-4, plus a per-cell summary")
     args = ap.parse_args()
     peak = 6544.0
     try:
@@ -102,6 +104,26 @@ def main():
     rows.append(case("cfg2A vgg conv4 s8 C256", (88, 100), (45, 150), 256, 20000, "uniform", stride=(8, 8), peak=peak))
     rows.append(case("cfg3 mv3d ped C768 (8,2)", (100, 120), (48, 160), 768, 20000, "ground", stride=(8, 2), weights=True, peak=peak))
     rows.append(case("cfg4 full scan C128", *K, 128, 120000, "ground", weights=True, peak=peak))
+    if args.full:
+        grid = []
+        for nnz in (5000, 20000, 100000, 1000000):
+            for C in (16, 32, 64, 128, 256):
+                for skew in ("uniform", "zipf", "ground"):
+                    per_seed = []
+                    for seed in range(5):
+                        r = case("cfg5 nnz%d C%d %s" % (nnz, C, skew), *K, C, nnz, skew, weights=True, peak=peak, seed=seed)
+                        per_seed.append(r)
+                        rows.append(r)
+                        torch.cuda.empty_cache()
+                    grid.append(dict(nnz=nnz, C=C, skew=skew, seeds=5, max_row=max(r["max_row"] for r in per_seed),
+                                     fwd_us_median=float(np.median([r["fwd_us"] for r in per_seed])),
+                                     fwd_frac_median=float(np.median([r["fwd_frac"] for r in per_seed])),
+                                     fwd_frac_min=min(r["fwd_frac"] for r in per_seed),
+                                     bwd_us_median=float(np.median([r["bwd_us"] for r in per_seed])),
+                                     bwd_frac_median=float(np.median([r["bwd_frac"] for r in per_seed])),
+                                     bwd_frac_min=min(r["bwd_frac"] for r in per_seed)))
+        print(json.dumps({"peak_GBs": peak, "grid": grid, "rows": rows}, indent=1))
+        return
     if not args.quick:
         for nnz in (5000, 100000, 1000000):
             for C in (16, 64, 256):
