@@ -718,6 +718,28 @@ def run_gpu_avod(args, name, cfg):
                 e = te2[k % N_FRAMES]
                 nf_ms.append(e[0].elapsed_time(e[1]))
                 nb_ms.append(e[1].elapsed_time(e[2]))
+            # ... and alone: back-to-back graph replays on the rotating buffer sets (what tools/sweep.py measures for the
+            # concat forms), without the other kernels of the step around them
+            def alone(fn):
+                for k in range(n_sets):
+                    fn(k)
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    for k in range(2 * n_sets):
+                        fn(k)
+                gr.replay()
+                ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                ea.record()
+                for _ in range(20):
+                    gr.replay()
+                eb.record()
+                torch.cuda.synchronize()
+                return ea.elapsed_time(eb) * 1e-3 / (20 * 2 * n_sets)
+            cs_ = torch.cuda.current_stream().cuda_stream
+            tf_alone = alone(lambda k: pipes_nc[k % n_sets].forward_layer(dom, maps[k % n_sets][dom]["bev"], maps[k % n_sets][dom]["img"], cs_, n_pts[0]))
+            tb_alone = alone(lambda k: pipes_nc[k % n_sets].backward_layer(dom, maps[k % n_sets][dom]["g_bev"], maps[k % n_sets][dom]["g_img"], cs_, n_pts[0]))
             bf, bb = sB.bytes_forward_sparse_only(nnz[dom]), sB.bytes_backward_sparse_only(nnz[dom])
             tf_, tb_ = float(np.mean(nf_ms)) * 1e-3, float(np.mean(nb_ms)) * 1e-3
             bytes_step_nc = sum((s.bytes_forward_sparse_only(n) + (s.bytes_backward(n) if s.dual else s.bytes_backward_sparse_only(n)))
@@ -727,8 +749,13 @@ def run_gpu_avod(args, name, cfg):
                                  "kernels against the sparse-only byte formulas of SURVEY.md 8(d)" % sB.name,
                          "value": world * KN / (ms_nc * 1e-3), "unit": UNIT, "steps": KN, "ms_per_step": ms_nc / KN,
                          "algorithmic_bytes_per_step": bytes_step_nc,
-                         "forward_kernel": {"bytes_per_launch": bf, "us_per_launch": tf_ * 1e6, "achieved": bf / tf_ / 1e9, "frac": bf / tf_ / 1e9 / peak},
-                         "backward_kernel": {"bytes_per_launch": bb, "us_per_launch": tb_ * 1e6, "achieved": bb / tb_ / 1e9, "frac": bb / tb_ / 1e9 / peak}}
+                         "forward_kernel": {"bytes_per_launch": bf, "us_per_launch": tf_ * 1e6, "achieved": bf / tf_ / 1e9, "frac": bf / tf_ / 1e9 / peak,
+                                            "alone_us_per_launch": tf_alone * 1e6, "alone_frac": bf / tf_alone / 1e9 / peak},
+                         "backward_kernel": {"bytes_per_launch": bb, "us_per_launch": tb_ * 1e6, "achieved": bb / tb_ / 1e9, "frac": bb / tb_ / 1e9 / peak,
+                                             "alone_us_per_launch": tb_alone * 1e6, "alone_frac": bb / tb_alone / 1e9 / peak},
+                         "timing": "us_per_launch / frac: CUDA events around the kernel inside graph replays of the whole single-stream step "
+                                   "(launch gaps and the other kernels' dirty L2 lines weigh on a 15 us kernel); alone_*: the kernel back to back "
+                                   "on rotating buffers"}
             del pipes_nc, ngr, tg2
         except SystemExit:
             raise
@@ -1369,9 +1396,12 @@ def run_gpu_pairs(args, name, cfg):
     def prologue_build(k):
         build_unit(pipes[(k * units) % n_sets], k, 0, torch.cuda.current_stream().cuda_stream)
 
-    # ---- PARITY CHECK before timing: the first launch unit of step 0 against the CPU oracle, bit for bit
-    prologue_build(0)
-    lean_step(0)
+    # ---- PARITY CHECK before timing: the first launch unit of step 0 (build + forward + backward through PairsPipeline ->
+    #      C ABI) against the CPU oracle, bit for bit
+    ms0 = torch.cuda.current_stream().cuda_stream
+    build_unit(pipes[0], 0, 0, ms0)
+    pipes[0].forward(maps[0]["bev"], maps[0]["img"], ms0, bound)
+    pipes[0].backward(maps[0]["g_bev"], ms0, bound)
     torch.cuda.synchronize()
     c0 = pipes[0].plan.counts.cpu().numpy()
     nnz = [int(c0[f, 1]) for f in range(Bp)]
@@ -1382,7 +1412,7 @@ def run_gpu_pairs(args, name, cfg):
         cref.build()
         check_frames = range(min(Bp, 2))
         for f in check_frames:
-            h = host[frame_of(0, f)]
+            h = host[frame_of(0, f if stacked else 0)]
             o = io.produce_sparse_pooling_input(dict(img_index=h["img_index"].copy(), bv_index=h["bv_index"], img_size=h["img_size"],
                                                      bv_size=h["bv_size"]), M_val=h["m_val"], stride=list(spec.stride))
             val = np.asarray(o["M_val"], dtype=np.float32)
@@ -1395,6 +1425,9 @@ def run_gpu_pairs(args, name, cfg):
             assert_equal_bits(pipes[0].g_img[f], gs, "frame %d: gradient of the image map" % f)
         parity = {"checked": True, "frames": len(list(check_frames)),
                   "what": "PairsPipeline (build + forward + backward) == oracle/index_oracle + oracle/cref, bit for bit"}
+    prologue_build(0)
+    lean_step(0)
+    torch.cuda.synchronize()
 
     # ---- CUDA graphs of the step
     use_graph = not args.no_graph

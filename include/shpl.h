@@ -188,9 +188,10 @@ int shpl_plan_from_voxel_coords(const void* coordinate, int32_t index_is_i64, in
  * key [nnz] = destination row of each entry (plan.csr_row / plan.csrT_pix) and
  * nnz_max >= number of entries (e.g. plan.capacity) let the kernel balance the
  * gathers by entry; key may be NULL (then rows are walked cell by cell).
- * heavy_len > 0: cells with more than heavy_len entries are NOT summed here (their pooled part is
- * left zero / their dense part copied); the caller follows with shpl_pool_heavy on the listed
- * cells.  heavy_len = 0: every cell is summed here, strictly sequentially. */
+ * heavy_len > 0: cells with more than heavy_len entries are NOT summed here and their pooled part (in the
+ * add forms: their whole output) is left UNWRITTEN; the caller runs shpl_pool_heavy / shpl_pool_heavy_split on
+ * the listed cells -- after this call, or concurrently on another stream (the two write disjoint cells).
+ * heavy_len = 0: every cell is summed here, strictly sequentially. */
 int shpl_pool_forward(const float* dst, const float* src,
                       const int32_t* ptr, const int32_t* key, const int32_t* idx, const float* val,
                       int32_t nnz_max, int32_t heavy_len, int32_t n_rows, int32_t C_d, int32_t n_src, int32_t C_s,
@@ -231,7 +232,7 @@ int shpl_pool_backward_dual(const float* g_fused_bev, const float* g_fused_img,
                             float* g_bev, float* g_img, void* stream);
 
 /* shpl_pool_heavy with the LONG listed cells (more than SHPL_EXACT_LEN entries) split over many CTAs instead of one
- * cluster per cell: a cell of L entries is cut into ceil(L / 2048) contiguous pieces, a CTA sums one piece in stored
+ * cluster per cell: a cell of L entries is cut into ceil(L / 1024) contiguous pieces, a CTA sums one piece in stored
  * order into the workspace, and a second kernel adds a cell's partial sums in order -- a fixed tree that depends only on
  * L (deterministic, within 1e-5 of the sum of |terms|; not bit-identical to the sequential sum).  The Zipf stress case's
  * 178 000-entry cell runs on ~90 SMs instead of 8.  Cells up to SHPL_EXACT_LEN entries take the exact cluster kernel as

@@ -279,8 +279,11 @@ __device__ __forceinline__ void pool_tile(const V* __restrict__ src, int src_str
     SHPL_DASSERT(lo >= 0 && lo <= hi);
     // lo, hi: this lane's cell offsets ptr[lane], ptr[lane+1] (0, 0 beyond `rows`), loaded by the caller
     // together with the dense loads so that the two latencies overlap
-    if (heavy_len > 0 && hi - lo > heavy_len) hi = lo;         // heavy cell: shpl_pool_heavy writes it
-    const unsigned busy = __ballot_sync(kFull, hi > lo);
+    // heavy cell: shpl_pool_heavy writes its pooled part (or dense + pooled in the add form); nothing is written for it
+    // here, so that the heavy kernels may run CONCURRENTLY with this one on another stream
+    const unsigned heavy_m = __ballot_sync(kFull, heavy_len > 0 && hi - lo > heavy_len);
+    if (heavy_len > 0 && hi - lo > heavy_len) hi = lo;
+    const unsigned busy = __ballot_sync(kFull, hi > lo) | heavy_m;
     // long cells: left empty by the lane-per-vector walk below, then summed by the whole warp
     const unsigned longs = __ballot_sync(kFull, hi - lo > kLongRow);
     if (hi - lo > kLongRow) hi = lo;
@@ -312,8 +315,9 @@ __device__ __forceinline__ void pool_tile(const V* __restrict__ src, int src_str
         int end = __shfl_sync(kFull, hi, r & 31);
         if (s >= n) end = beg;
         V base = vzero((V*)nullptr);
+        const bool mine = s < n && !((heavy_m >> (r & 31)) & 1u);
         if constexpr (kAdd) {
-            if (s < n) base = ld_stream(addend + r * add_stride + q);
+            if (mine) base = ld_stream(addend + r * add_stride + q);
         }
         V acc = vzero((V*)nullptr);
         int k = beg;
@@ -343,7 +347,7 @@ __device__ __forceinline__ void pool_tile(const V* __restrict__ src, int src_str
             axpy(acc, w, x);
         }
         if constexpr (kAdd) acc = vadd(base, acc);
-        if (s < n) st_stream(out + r * out_stride + q, acc);
+        if (mine) st_stream(out + r * out_stride + q, acc);
     }
     if (longs != 0u) {
         __syncwarp();      // orders the stores above before the overwrites below (other lanes, same addresses)
@@ -743,14 +747,16 @@ __global__ void __launch_bounds__(kThreads, SHPL_WIDE_MIN_CTAS) shpl_pool_wide_k
     }
     const int r0 = (b - jb.entry_ctas) * kWideTile;
     const int rows = min(kWideTile, jb.n_cells - r0);
-    unsigned busy = 0u;
+    unsigned busy = 0u, heavy_m = 0u;
     int lo = 0, hi = 0;
     if (jb.vs > 0) {
         if (lane < rows) {
             lo = __ldg(jb.ptr + r0 + lane);
             hi = __ldg(jb.ptr + r0 + lane + 1);
-            if (jb.heavy_len > 0 && hi - lo > jb.heavy_len) hi = lo;   // heavy cell: written as empty here
         }
+        // heavy cells: shpl_pool_heavy writes them (possibly concurrently, on another stream): counted busy so that
+        // nothing is written for them here, but never summed here
+        heavy_m = __ballot_sync(kFull, jb.heavy_len > 0 && hi - lo > jb.heavy_len);
         busy = __ballot_sync(kFull, hi > lo);
     }
     const bool by_entry = jb.key != nullptr;
@@ -776,7 +782,7 @@ __global__ void __launch_bounds__(kThreads, SHPL_WIDE_MIN_CTAS) shpl_pool_wide_k
     }
     if (by_entry) return;
     // no key array: busy cells dealt round-robin (by rank) to the warps of this CTA
-    unsigned m = busy;
+    unsigned m = busy & ~heavy_m;
     int rank = 0;
     while (m) {
         const int r = __ffs(m) - 1;
@@ -854,11 +860,11 @@ __global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SH
                     hi_n = __ldg(jb.ptr + tn * jb.rows_per_tile + lane + 1);
                 }
             }
-            if (lane < rows) {
-                if (jb.heavy_len > 0 && hi - lo > jb.heavy_len) hi = lo;   // heavy cell: written as empty here
-            }
-            busy = __ballot_sync(kFull, hi > lo);                          // cells somebody else writes (entry CTAs) ...
-            longs = jb.vs <= 32 ? __ballot_sync(kFull, hi - lo > jb.long_len) : 0u;   // ... or this warp sums as a whole, below
+            // heavy cells (shpl_pool_heavy writes them, possibly concurrently on another stream) count as busy: nothing is
+            // written for them here
+            const bool heavy = lane < rows && jb.heavy_len > 0 && hi - lo > jb.heavy_len;
+            busy = __ballot_sync(kFull, hi > lo);                          // cells somebody else writes (entry CTAs, heavy kernels) ...
+            longs = jb.vs <= 32 ? __ballot_sync(kFull, !heavy && hi - lo > jb.long_len) : 0u;   // ... or this warp sums as a whole, below
         }
         if (jb.vd > 0) {
             // concat form: the dense part of every cell; add form: a plain copy for the cells that receive nothing
@@ -1079,7 +1085,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
 // contiguous pieces; a CTA sums one piece (its 8 warps take sub-pieces in stored order, the warp sums are added in
 // order) into partial[piece][0:C] in the caller's workspace; shpl_pool_heavy_combine_kernel then adds the P partials in
 // order.  A fixed tree that depends only on L: deterministic, within fp32 rounding of the sequential sum.
-constexpr int kPieceLen = 2048;
+constexpr int kPieceLen = 1024;
 constexpr int kMaxListed = 4096;           // listed cells whose piece counts fit the shared-memory prefix array
 
 struct SplitArgs {
@@ -1187,11 +1193,13 @@ __global__ void __launch_bounds__(kThreads) shpl_pool_heavy_combine_kernel(Heavy
 // products, in entry order, in the shared memory of CTA 0 (remote stores through distributed shared memory: fire and
 // forget, no latency on anybody's critical path); then the adder warps of CTA 0 (one per 32 channel vectors) walk the
 // round out of their own shared memory, adding product after product to the running sums.
-template <int W>
-__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads) shpl_pool_heavy_exact_kernel(HeavyArgs a) {
+// CS = CTAs per cluster: 8 when a single call serves few cells (all 64 warps gather for one cell), 2 when many cells are
+// listed (four times as many cells in flight; the round length is set by the shared-memory budget either way).
+template <int W, int CS>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kThreads) shpl_pool_heavy_exact_kernel(HeavyArgs a) {
     using V = typename VecOf<W>::type;
     extern __shared__ float4 heavy_smem[];
-    V* stage = reinterpret_cast<V*>(heavy_smem);        // CTA 0's copy: [kClusterSize * kWarps * eu][nv] products of a round
+    V* stage = reinterpret_cast<V*>(heavy_smem);        // CTA 0's copy: [CS * kWarps * eu][nv] products of a round
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
     V* stage0 = cluster.map_shared_rank(stage, 0);
@@ -1202,8 +1210,8 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
     const int q0 = nv >= 32 ? lane : lane - sub * nv;   // first channel vector of this lane
     const bool lane_on = sub < E;
     const int U = eu / E;                               // warp-wide loads per round (eu is a multiple of E, eu <= 32)
-    const int per_round = kClusterSize * kWarps * eu;
-    const int n_clusters = gridDim.x / kClusterSize;
+    const int per_round = CS * kWarps * eu;
+    const int n_clusters = gridDim.x / CS;
     const int n_heavy = min(__ldg(a.count_dev), a.list_cap);
     const V* src = static_cast<const V*>(a.gather_in);
     const V* addend = static_cast<const V*>(a.addend);
@@ -1212,7 +1220,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
     const bool adder = crank == 0 && aq < nv;
     constexpr int kG = 4;                               // warp-wide loads in flight
     constexpr int kA = 8;                               // products an adder lane fetches ahead of its additions
-    for (int h = blockIdx.x / kClusterSize; h < n_heavy; h += n_clusters) {
+    for (int h = blockIdx.x / CS; h < n_heavy; h += n_clusters) {
         const int cell = __ldg(a.list + h);
         const int beg = __ldg(a.ptr + cell), end = __ldg(a.ptr + cell + 1);
         if (end - beg > a.exact_len || end - beg <= a.skip_le) continue;   // the tree kernel's / the main kernel's (the whole cluster agrees)
@@ -1828,23 +1836,35 @@ static int pool_heavy_impl(const float* gather_in, int32_t gather_stride, int32_
     a.exact_len = a.nv <= kWarps * 32 && (size_t)kClusterSize * kWarps * C * sizeof(float) <= 200 * 1024 ? SHPL_EXACT_LEN : 0;
     a.skip_le = main_kernel_heavy_len(SHPL_HEAVY_LEN, C) > SHPL_HEAVY_LEN ? main_kernel_heavy_len(SHPL_HEAVY_LEN, C) : 0;
     if (a.exact_len > a.skip_le) {
+        // with a workspace (the split path below) many cells may be listed: 2-CTA clusters, one per SM pair of CTAs, four
+        // times as many cells in flight; without one, the original 8-CTA clusters
+        const int cs = (workspace != nullptr) ? 2 : kClusterSize;
         const int E = a.nv >= 32 ? 1 : 32 / a.nv;
-        int eu = (int)((128 * 1024) / ((size_t)kClusterSize * kWarps * C * sizeof(float)));
+        int eu = (int)((128 * 1024) / ((size_t)cs * kWarps * C * sizeof(float)));
         if (eu > 32) eu = 32;
         eu = eu / E * E;
         if (eu < E) eu = E;
         a.eu = eu;
-        const size_t smem_x = (size_t)kClusterSize * kWarps * eu * C * sizeof(float);
-        const int clusters_x = list_cap < 128 ? list_cap : 128;
-        const unsigned grid_x = (unsigned)(clusters_x * kClusterSize);
-        if (smem_x > 48 * 1024) {
-            if (w == 4) SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_pool_heavy_exact_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
-            else if (w == 2) SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_pool_heavy_exact_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
-            else SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_pool_heavy_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x));
+        const size_t smem_x = (size_t)cs * kWarps * eu * C * sizeof(float);
+        const int max_clusters = cs == 2 ? shpl::sm_count() / 2 * 2 : 128;
+        const int clusters_x = list_cap < max_clusters ? list_cap : max_clusters;
+        const unsigned grid_x = (unsigned)(clusters_x * cs);
+#define SHPL_LAUNCH_EXACT(WW, CC)                                                                                       \
+    do {                                                                                                                \
+        if (smem_x > 48 * 1024)                                                                                         \
+            SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_pool_heavy_exact_kernel<WW, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x)); \
+        shpl_pool_heavy_exact_kernel<WW, CC><<<grid_x, kThreads, smem_x, s>>>(a);                                       \
+    } while (0)
+        if (cs == 2) {
+            if (w == 4) SHPL_LAUNCH_EXACT(4, 2);
+            else if (w == 2) SHPL_LAUNCH_EXACT(2, 2);
+            else SHPL_LAUNCH_EXACT(1, 2);
+        } else {
+            if (w == 4) SHPL_LAUNCH_EXACT(4, kClusterSize);
+            else if (w == 2) SHPL_LAUNCH_EXACT(2, kClusterSize);
+            else SHPL_LAUNCH_EXACT(1, kClusterSize);
         }
-        if (w == 4) shpl_pool_heavy_exact_kernel<4><<<grid_x, kThreads, smem_x, s>>>(a);
-        else if (w == 2) shpl_pool_heavy_exact_kernel<2><<<grid_x, kThreads, smem_x, s>>>(a);
-        else shpl_pool_heavy_exact_kernel<1><<<grid_x, kThreads, smem_x, s>>>(a);
+#undef SHPL_LAUNCH_EXACT
         shpl::count_launches(1);
         if (int rc = shpl::check_launch("shpl_pool_heavy_exact_kernel")) return rc;
     }
@@ -1858,7 +1878,7 @@ static int pool_heavy_impl(const float* gather_in, int32_t gather_stride, int32_
         sa.partial = wsb + 256 + (size_t)(kMaxListed + 64) * sizeof(int) - ((size_t)(kMaxListed + 64) * sizeof(int)) % 16;
         sa.max_pieces = (int)heavy_ws_pieces(nnz_max, list_cap);
         const size_t smem_s = (size_t)kWarps * a.nv * sizeof(float) * w;
-        const unsigned grid_s = (unsigned)(shpl::sm_count() * 2);
+        const unsigned grid_s = (unsigned)(shpl::sm_count() * 4);      // pieces are gather-latency bound: many CTAs in flight
 #define SHPL_LAUNCH_SPLIT(WW, GG)                                                                                       \
     do {                                                                                                                \
         if (smem_s > 48 * 1024)                                                                                         \

@@ -276,6 +276,31 @@ def _run_heavy(heavy, gather_in, gather_stride, C, ptr, idx, val, addend, addend
     _cabi.check(rc, "shpl_pool_heavy_split")
 
 
+_heavy_streams = {}
+
+
+def _launch_with_heavy(device, main, heavy_jobs):
+    """Launches `main()` (the pooling kernel) on the current stream and the heavy-cell kernels of `heavy_jobs` (argument
+    tuples of _run_heavy) on a side stream BESIDE it: the main kernel writes nothing for listed cells, the heavy kernels
+    nothing else, so the two are independent -- the long gather chains of a few giant cells hide under the bandwidth-bound
+    main kernel.  When the plan's counters say there is no heavy cell (the KITTI / MV3D case) only main() runs."""
+    jobs = [j for j in heavy_jobs if j[0][3] != 0]
+    if not jobs:
+        main()
+        return
+    cur = torch.cuda.current_stream()
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    side = _heavy_streams.get(key)
+    if side is None:
+        side = _heavy_streams[key] = torch.cuda.Stream(device=device)
+    side.wait_stream(cur)                  # the plan and the inputs are ready
+    main()
+    with torch.cuda.stream(side):
+        for j in jobs:
+            _run_heavy(*j)
+    cur.wait_stream(side)
+
+
 def _off(t, n_floats):
     return ctypes.c_void_p(t.data_ptr() + 4 * n_floats)
 
@@ -288,10 +313,12 @@ def pool_forward(dst, src, csr, n_rows, n_src):
     C_s = src.shape[-1]
     C_d = 0 if dst is None else dst.shape[-1]
     fused = torch.empty((n_rows, C_d + C_s), dtype=torch.float32, device=src.device)
-    rc = _lib.shpl_pool_forward(_ptr(dst), _ptr(src), _ptr(ptr), _ptr(key), _ptr(idx), _ptr(val), int(nnz_max),
-                                _cabi.HEAVY_LEN, n_rows, C_d, n_src, C_s, _ptr(fused), _stream())
-    _cabi.check(rc, "shpl_pool_forward")
-    _run_heavy(heavy, _ptr(src), C_s, C_s, ptr, idx, val, None, 0, _off(fused, C_d), C_d + C_s)
+
+    def main():
+        rc = _lib.shpl_pool_forward(_ptr(dst), _ptr(src), _ptr(ptr), _ptr(key), _ptr(idx), _ptr(val), int(nnz_max),
+                                    _cabi.HEAVY_LEN, n_rows, C_d, n_src, C_s, _ptr(fused), _stream())
+        _cabi.check(rc, "shpl_pool_forward")
+    _launch_with_heavy(src.device, main, [(heavy, _ptr(src), C_s, C_s, ptr, idx, val, None, 0, _off(fused, C_d), C_d + C_s)])
     return fused
 
 
@@ -299,10 +326,11 @@ def pool_backward(g_fused, csrT, n_rows, C_d, n_src, C_s, want_dst=True):
     ptrT, keyT, idxT, valT, nnz_max, heavy = csrT
     g_dst = torch.empty((n_rows, C_d), dtype=torch.float32, device=g_fused.device) if (want_dst and C_d) else None
     g_src = torch.empty((n_src, C_s), dtype=torch.float32, device=g_fused.device)
-    rc = _lib.shpl_pool_backward(_ptr(g_fused), _ptr(ptrT), _ptr(keyT), _ptr(idxT), _ptr(valT), int(nnz_max),
-                                 _cabi.HEAVY_LEN, n_rows, C_d, n_src, C_s, _ptr(g_dst), _ptr(g_src), _stream())
-    _cabi.check(rc, "shpl_pool_backward")
-    _run_heavy(heavy, _off(g_fused, C_d), C_d + C_s, C_s, ptrT, idxT, valT, None, 0, _ptr(g_src), C_s)
+    def main():
+        rc = _lib.shpl_pool_backward(_ptr(g_fused), _ptr(ptrT), _ptr(keyT), _ptr(idxT), _ptr(valT), int(nnz_max),
+                                     _cabi.HEAVY_LEN, n_rows, C_d, n_src, C_s, _ptr(g_dst), _ptr(g_src), _stream())
+        _cabi.check(rc, "shpl_pool_backward")
+    _launch_with_heavy(g_fused.device, main, [(heavy, _off(g_fused, C_d), C_d + C_s, C_s, ptrT, idxT, valT, None, 0, _ptr(g_src), C_s)])
     return g_dst, g_src
 
 
@@ -311,10 +339,11 @@ def pool_forward_into(fused, src, csr, n_rows, n_src, chan_off):
     overwritten with the pooled sums (zeros for cells that receive nothing); the other channels are left alone."""
     ptr, key, idx, val, nnz_max, heavy = csr
     C_s, F = src.shape[-1], fused.shape[-1]
-    rc = _lib.shpl_pool_forward_into(_ptr(src), _ptr(ptr), _ptr(key), _ptr(idx), _ptr(val), int(nnz_max), _cabi.HEAVY_LEN,
-                                     n_rows, n_src, C_s, _ptr(fused), F, int(chan_off), _stream())
-    _cabi.check(rc, "shpl_pool_forward_into")
-    _run_heavy(heavy, _ptr(src), C_s, C_s, ptr, idx, val, None, 0, _off(fused, chan_off), F)
+    def main():
+        rc = _lib.shpl_pool_forward_into(_ptr(src), _ptr(ptr), _ptr(key), _ptr(idx), _ptr(val), int(nnz_max), _cabi.HEAVY_LEN,
+                                         n_rows, n_src, C_s, _ptr(fused), F, int(chan_off), _stream())
+        _cabi.check(rc, "shpl_pool_forward_into")
+    _launch_with_heavy(src.device, main, [(heavy, _ptr(src), C_s, C_s, ptr, idx, val, None, 0, _off(fused, chan_off), F)])
     return fused
 
 
@@ -324,10 +353,11 @@ def pool_backward_from(g_fused, csrT, n_rows, n_src, C_s, chan_off):
     ptrT, keyT, idxT, valT, nnz_max, heavy = csrT
     F = g_fused.shape[-1]
     g_src = torch.empty((n_src, C_s), dtype=torch.float32, device=g_fused.device)
-    rc = _lib.shpl_pool_backward_from(_ptr(g_fused), F, int(chan_off), _ptr(ptrT), _ptr(keyT), _ptr(idxT), _ptr(valT),
-                                      int(nnz_max), _cabi.HEAVY_LEN, n_rows, n_src, C_s, _ptr(g_src), _stream())
-    _cabi.check(rc, "shpl_pool_backward_from")
-    _run_heavy(heavy, _off(g_fused, chan_off), F, C_s, ptrT, idxT, valT, None, 0, _ptr(g_src), C_s)
+    def main():
+        rc = _lib.shpl_pool_backward_from(_ptr(g_fused), F, int(chan_off), _ptr(ptrT), _ptr(keyT), _ptr(idxT), _ptr(valT),
+                                          int(nnz_max), _cabi.HEAVY_LEN, n_rows, n_src, C_s, _ptr(g_src), _stream())
+        _cabi.check(rc, "shpl_pool_backward_from")
+    _launch_with_heavy(g_fused.device, main, [(heavy, _off(g_fused, chan_off), F, C_s, ptrT, idxT, valT, None, 0, _ptr(g_src), C_s)])
     return g_src
 
 
@@ -455,13 +485,13 @@ class SparsePoolDualFunction(torch.autograd.Function):
         fused_bev = torch.empty(tuple(bev.shape[:3]) + (Cb + Ci,), dtype=torch.float32, device=bev.device)
         fused_img = torch.empty(tuple(img.shape[:3]) + (Ci + Cb,), dtype=torch.float32, device=bev.device)
         P8 = plan.ptrs8()
-        rc = _lib.shpl_pool_forward_dual(_ptr(b), _ptr(i), *P8, int(plan.entry_bound), _cabi.HEAVY_LEN,
-                                         R, Cb, Q, Ci, _ptr(fused_bev), _ptr(fused_img), _stream())
-        _cabi.check(rc, "shpl_pool_forward_dual")
-        _run_heavy(plan.heavy(False), _ptr(i), Ci, Ci, P8[0], P8[2], P8[3], None, 0,
-                   _off(fused_bev, Cb), Cb + Ci)
-        _run_heavy(plan.heavy(True), _ptr(b), Cb, Cb, P8[4], P8[6], P8[7], None, 0,
-                   _off(fused_img, Ci), Ci + Cb)
+        def main():
+            rc = _lib.shpl_pool_forward_dual(_ptr(b), _ptr(i), *P8, int(plan.entry_bound), _cabi.HEAVY_LEN,
+                                             R, Cb, Q, Ci, _ptr(fused_bev), _ptr(fused_img), _stream())
+            _cabi.check(rc, "shpl_pool_forward_dual")
+        _launch_with_heavy(bev.device, main,
+                           [(plan.heavy(False), _ptr(i), Ci, Ci, P8[0], P8[2], P8[3], None, 0, _off(fused_bev, Cb), Cb + Ci),
+                            (plan.heavy(True), _ptr(b), Cb, Cb, P8[4], P8[6], P8[7], None, 0, _off(fused_img, Ci), Ci + Cb)])
         ctx.plan = plan
         ctx.shapes = (tuple(bev.shape), tuple(img.shape))
         return fused_bev, fused_img
