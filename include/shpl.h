@@ -34,8 +34,7 @@ extern "C" {
  * Listed cells of up to SHPL_EXACT_LEN entries are still summed in the reference's sequential order
  * (bit-exact: the cluster gathers and multiplies in parallel, one warp per 32 channel vectors adds in
  * entry order); longer ones by a fixed summation tree (deterministic, within 1e-5 of the sum of |terms|).
- * With 16 or fewer pooled channels the main kernels keep cells of up to 2048 entries themselves (one warp, 32
- * gathers in flight, sequential order) whatever heavy_len > 0 they are given, and shpl_pool_heavy leaves those alone. */
+ */
 #define SHPL_HEAVY_LEN 512
 #define SHPL_EXACT_LEN 2048
 

@@ -1284,12 +1284,30 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kThreads) shpl_pool
 }
 
 // --------------------------------------------------------------------------------------- host
-// Narrow channel counts (C <= 16) keep listed cells of up to 2048 entries in the main kernels: the whole-warp walk has
-// 32 gathers of such a cell in flight there and many long cells run side by side, which beats one cluster per cell
-// (measured, Zipf stress rows: 261 us against 312 us at 1 M pairs).  shpl_pool_heavy applies the same rule from its C.
-constexpr int kNarrowKeep = 2048;
+// Tuning constants.  The product library is stateless: every value below is a compile-time constant (the measured
+// optimum, DESIGN.md 4.1).  Only a build with -DSHPL_EXPERIMENT (make exp -> libshpl_exp.so, used by tools/ for A/B
+// runs through SHPL_LIB) reads the environment variable of the same name instead, once per process.
+#ifdef SHPL_EXPERIMENT
+#define SHPL_KNOB(name, dflt)                                   \
+    ([]() -> int {                                              \
+        static const int v = []() {                             \
+            const char* e = getenv(name);                       \
+            return e ? atoi(e) : (dflt);                        \
+        }();                                                    \
+        return v;                                               \
+    }())
+#else
+#define SHPL_KNOB(name, dflt) (dflt)
+#endif
+
+// Round 1 kept listed cells of up to 2048 entries in the main kernels for narrow channel counts (C <= 16): one 8-CTA
+// cluster per cell was slower than the whole-warp walk there.  With 2-CTA clusters for the exact kernel and the split
+// tree for longer cells the heavy path wins at every width (profiles/r2_zipf16_probe.txt: C = 16, 100 k Zipf pairs
+// 88.7 -> 53.0 us), so nothing is kept any more; SHPL_NARROW_KEEP (experiment builds) brings the old rule back.
+constexpr int kNarrowKeep = 0;
 int main_kernel_heavy_len(int heavy_len, int c_pool) {
-    return heavy_len > 0 && c_pool <= 16 && heavy_len < kNarrowKeep ? kNarrowKeep : heavy_len;
+    const int keep = SHPL_KNOB("SHPL_NARROW_KEEP", kNarrowKeep);
+    return heavy_len > 0 && c_pool <= 16 && heavy_len < keep ? keep : heavy_len;
 }
 
 int log2_or_neg(int v) {
@@ -1336,22 +1354,6 @@ struct JobSpec {            // in floats / cells, before the vector width is cho
     int add = 0;
     int heavy_len = 0;
 };
-
-// Tuning constants.  The product library is stateless: every value below is a compile-time constant (the measured
-// optimum, DESIGN.md 4.1).  Only a build with -DSHPL_EXPERIMENT (make exp -> libshpl_exp.so, used by tools/ for A/B
-// runs through SHPL_LIB) reads the environment variable of the same name instead, once per process.
-#ifdef SHPL_EXPERIMENT
-#define SHPL_KNOB(name, dflt)                                   \
-    ([]() -> int {                                              \
-        static const int v = []() {                             \
-            const char* e = getenv(name);                       \
-            return e ? atoi(e) : (dflt);                        \
-        }();                                                    \
-        return v;                                               \
-    }())
-#else
-#define SHPL_KNOB(name, dflt) (dflt)
-#endif
 
 // grid of the narrow kernel: 8 CTAs per SM although only 3 are resident (see launch_jobs)
 int narrow_ctas_per_sm() { const int v = SHPL_KNOB("SHPL_NARROW_CTAS_PER_SM", 8); return v > 0 ? v : 8; }

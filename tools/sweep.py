@@ -91,6 +91,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--full", action="store_true", help="the whole BASELINE config-5 grid: nnz {5k,20k,100k,1M} x C {16,32,64,128,256} x "
                                                         "{uniform, zipf, ground} x seeds 0-4, plus a per-cell summary")
+    ap.add_argument("--only", default=None, help="with --full: restrict to one row distribution (uniform | zipf | ground)")
     args = ap.parse_args()
     peak = 6544.0
     try:
@@ -109,6 +110,8 @@ def main():
         for nnz in (5000, 20000, 100000, 1000000):
             for C in (16, 32, 64, 128, 256):
                 for skew in ("uniform", "zipf", "ground"):
+                    if args.only and skew != args.only:
+                        continue
                     per_seed = []
                     for seed in range(5):
                         r = case("cfg5 nnz%d C%d %s" % (nnz, C, skew), *K, C, nnz, skew, weights=True, peak=peak, seed=seed)
