@@ -437,6 +437,25 @@ int shpl_pool_conv3x3_forward(const float* dst, const float* src,
                               const float* weight, int32_t C_out, const float* scale, const float* shift, int32_t relu,
                               float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Backward of shpl_pool_conv3x3_forward's linear part, out = conv3x3(concat(dst, pooled), weight) (what TF autodiff derives
+ * for slim.conv2d + sparse_pool_layer; the gradient of scale / shift / ReLU is the caller's: pass the gradient with
+ * respect to the conv output).  Deterministic: every sum runs in a fixed order.
+ *   g_dst    [frames, H, W, C_d]  = conv3x3(g_out; W[:, :, :C_d, :] flipped and transposed): the tcgen05 kernel again;
+ *   g_src    [n_src, C_s]         = the pooled channels' input gradient at the cells that receive pooled features, pushed
+ *                                   through the transposed CSR like shpl_pool_backward does;
+ *   g_weight [3, 3, C_d+C_s, C_out] (HWIO) = sum over pixels of x[p + tap] (x) g_out[p].
+ * Any of the three outputs may be NULL.  (ptr, key, idx, val): CSR by destination cell; (ptrT, keyT, idxT, valT): CSR by
+ * source pixel, both of the same plan.  Built for C_d = C_out = 32 and C_s in {0, 32}.
+ * workspace: shpl_conv3x3_backward_workspace_bytes(nnz_max) bytes, 256-byte aligned.
+ * Accuracy: g_dst as the forward (3xTF32); g_src and g_weight fp32 FMA sums, |error| <= 1e-5 * sum |terms|. */
+size_t shpl_conv3x3_backward_workspace_bytes(int32_t nnz_max);
+int shpl_pool_conv3x3_backward(const float* g_out, const float* dst, const float* src,
+                               const int32_t* ptr, const int32_t* key, const int32_t* idx, const float* val,
+                               const int32_t* ptrT, const int32_t* keyT, const int32_t* idxT, const float* valT,
+                               int32_t nnz_max, int32_t frames, int32_t H, int32_t W, int32_t C_d, int32_t n_src, int32_t C_s,
+                               const float* weight, int32_t C_out, float* g_dst, float* g_src, float* g_weight,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

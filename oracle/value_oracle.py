@@ -233,3 +233,27 @@ def conv3x3_after_fusion(fused, w, scale=None, shift=None, relu=False):
     if relu:
         y = np.maximum(y, 0.0)
     return y, mag
+
+
+def conv3x3_same_grad(x, w, g_out):
+    """Gradients of y = conv3x3_same(x, w) (float64): (g_x, g_w) and the sums of |terms| behind each of their elements."""
+    x = np.asarray(x, dtype=np.float64)
+    w = np.asarray(w, dtype=np.float64)
+    g = np.asarray(g_out, dtype=np.float64)
+    B, H, W, Ci = x.shape
+    gp = np.zeros((B, H + 2, W + 2, g.shape[3]))
+    gp[:, 1:H + 1, 1:W + 1] = g
+    xp = np.zeros((B, H + 2, W + 2, Ci))
+    xp[:, 1:H + 1, 1:W + 1] = x
+    g_x, mag_x = np.zeros_like(x), np.zeros_like(x)
+    g_w, mag_w = np.zeros_like(w), np.zeros_like(w)
+    for dy in range(3):
+        for dx in range(3):
+            # y[p] += x[p + (dy-1, dx-1)] . w[dy, dx]  =>  g_x[q] += g[q - (dy-1, dx-1)] . w[dy, dx]^T
+            win = gp[:, 2 - dy:2 - dy + H, 2 - dx:2 - dx + W]
+            g_x += win @ w[dy, dx].T
+            mag_x += np.abs(win) @ np.abs(w[dy, dx]).T
+            xwin = xp[:, dy:dy + H, dx:dx + W].reshape(-1, Ci)
+            g_w[dy, dx] = xwin.T @ g.reshape(-1, g.shape[3])
+            mag_w[dy, dx] = np.abs(xwin).T @ np.abs(g.reshape(-1, g.shape[3]))
+    return g_x, g_w, mag_x, mag_w

@@ -109,6 +109,8 @@ SIGNATURES = {
     "shpl_conv3x3_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "shpl_pool_conv3x3_forward": (ctypes.c_int, [c_void_p] * 6 + [c_int32] * 7 + [c_void_p, c_int32, c_void_p, c_void_p, c_int32,
                                                  c_void_p, c_void_p, c_size_t, c_void_p]),
+    "shpl_conv3x3_backward_workspace_bytes": (c_size_t, [c_int32]),
+    "shpl_pool_conv3x3_backward": (ctypes.c_int, [c_void_p] * 11 + [c_int32] * 7 + [c_void_p, c_int32] + [c_void_p] * 4 + [c_size_t, c_void_p]),
     "shpl_pool_heavy": (ctypes.c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p]),
 }

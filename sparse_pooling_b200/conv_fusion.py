@@ -63,3 +63,49 @@ def sparse_pool_conv3x3(inputs, M, img_index_flip, weight, scale=None, shift=Non
                                         _ptr(out), ctypes.c_void_p(ws.data_ptr() + off), ws.numel() - off, _stream())
     _cabi.check(rc, "shpl_pool_conv3x3_forward")
     return out
+
+
+class SparsePoolConv3x3Function(torch.autograd.Function):
+    """conv3x3(concat(bev, pooled(img)), weight) with autograd: forward = shpl_pool_conv3x3_forward without epilogue,
+    backward = shpl_pool_conv3x3_backward (g_bev on the tensor cores, g_img through the transposed CSR, g_weight).
+    Bias / batch norm / ReLU follow as ordinary torch ops, like slim's normalizer and activation follow the conv."""
+
+    @staticmethod
+    def forward(ctx, bev, img, weight, plan):
+        out = sparse_pool_conv3x3([bev, img], plan, None, weight)
+        ctx.save_for_backward(bev, img, weight)
+        ctx.plan = plan
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        import ctypes
+        bev, img, weight = ctx.saved_tensors
+        plan = ctx.plan
+        B, H, W, Cb = bev.shape
+        Ci = img.shape[3]
+        g = g_out.contiguous()
+        need_b, need_i, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        g_bev = torch.empty_like(bev) if need_b else None
+        g_img = torch.empty_like(img) if need_i else None
+        g_w = torch.empty_like(weight) if need_w else None
+        ptr, key, idx, val, nnz_max, _ = plan.by_row()
+        ptrT, keyT, idxT, valT, _, _ = plan.by_pixel()
+        need = int(_lib.shpl_conv3x3_backward_workspace_bytes(int(nnz_max)))
+        ws = ops.scratch("conv_bwd", bev.device, need + 256)
+        off = (-ws.data_ptr()) % 256
+        rc = _lib.shpl_pool_conv3x3_backward(_ptr(g), _ptr(bev.contiguous()), _ptr(img.contiguous()), _ptr(ptr), _ptr(key), _ptr(idx),
+                                             _ptr(val), _ptr(ptrT), _ptr(keyT), _ptr(idxT), _ptr(valT), int(nnz_max), B, H, W, Cb,
+                                             int(plan.n_src), Ci, _ptr(weight.contiguous()), weight.shape[3], _ptr(g_bev), _ptr(g_img),
+                                             _ptr(g_w), ctypes.c_void_p(ws.data_ptr() + off), ws.numel() - off, _stream())
+        _cabi.check(rc, "shpl_pool_conv3x3_backward")
+        return g_bev, g_img, g_w, None
+
+
+def sparse_pool_conv3x3_autograd(inputs, M, img_index_flip, weight):
+    """The differentiable form: [bev, img] NHWC float32 CUDA tensors, M / img_index_flip as in sparse_pool_layer,
+    weight [3, 3, C_b + C_i, C_out] -> conv3x3(concat(bev, pooled(img)), weight) (no bias / activation)."""
+    bev, img = inputs[0], inputs[1]
+    plan = _resolve_plan(M, img_index_flip, bev.shape[1] * bev.shape[2], (img.shape[1], img.shape[2]), bev.device)
+    _check_oob(plan)
+    return SparsePoolConv3x3Function.apply(bev, img, weight, plan)

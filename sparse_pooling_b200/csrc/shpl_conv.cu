@@ -747,6 +747,164 @@ __global__ void __launch_bounds__(kZThreads, 3) shpl_conv_z_kernel(ZArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------ backward
+// out = conv3x3(concat(dst, pooled), W)  (the linear part; the activation's gradient is the caller's).  Given g_out:
+//   g_dst    = conv3x3(g_out, W_d flipped and transposed)            -> the dense tcgen05 kernel on re-prepped weights
+//   g_pooled = the same for the pooled channels, only at the cells that receive pooled features (shpl_conv_gp_kernel),
+//   g_src    = transpose-CSR gather of g_pooled                       -> shpl_pool_backward_from on a remapped index
+//   g_W[t][ci][co] = sum_p x[p + off(t)][ci] * g_out[p][co]           -> dense channels: shpl_conv_gwd_kernel (a pixel
+//                    reduction, FFMA, per-CTA partial sums combined in order); pooled channels: shpl_conv_gwp_kernel
+// All sums run in a fixed order: deterministic.
+struct GpArgs {
+    const float* src;
+    const float* g_out;
+    const int* ptr;
+    const int* key;
+    const int* idx;
+    const float* val;
+    const float* w;              // HWIO weights
+    int c_in_total, ci_off;      // C_out = 32, C_s = 32
+    int n_rows, nnz_max, H, W;
+    float* PB;                   // [entries][32] pooled vector of the cell whose first entry is e
+    float* GP;                   // [entries][32] its gradient
+};
+
+__global__ void __launch_bounds__(256) shpl_conv_gp_kernel(GpArgs a) {
+    __shared__ float wt[9 * 32 * 32];            // [tap][co][ci]: lane = ci reads conflict-free
+    for (int i = threadIdx.x; i < 9 * 32 * 32; i += blockDim.x) {
+        const int ci = i & 31, co = (i >> 5) & 31, t = i >> 10;
+        wt[i] = a.w[((size_t)t * a.c_in_total + a.ci_off + ci) * 32 + co];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int e_begin = __ldg(a.ptr), e_end = min(__ldg(a.ptr + a.n_rows), e_begin + a.nnz_max);
+    const int HW = a.H * a.W;
+    for (int e = e_begin + blockIdx.x * warps + warp; e < e_end; e += gridDim.x * warps) {
+        const int r = __ldg(a.key + e);
+        if (e > e_begin && __ldg(a.key + e - 1) == r) continue;          // not the first entry of its cell (warp-uniform)
+        const int end = __ldg(a.ptr + r + 1);
+        float p = 0.f;                                                    // pooled[r][lane]: entries in stored order
+        for (int k = e; k < end; ++k)
+            p = __fadd_rn(p, __fmul_rn(__ldg(a.val + k), __ldg(a.src + (size_t)__ldg(a.idx + k) * 32 + lane)));
+        a.PB[(size_t)(e - e_begin) * 32 + lane] = p;
+        const int f = r / HW, rem = r - f * HW, y = rem / a.W, x = rem - y * a.W;
+        float acc = 0.f;                                                  // g_pooled[r][ci = lane]
+        for (int t = 0; t < 9; ++t) {
+            const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);         // the output pixel that saw this cell through tap t
+            if (yy < 0 || yy >= a.H || xx < 0 || xx >= a.W) continue;
+            const float g = __ldg(a.g_out + ((size_t)(f * a.H + yy) * a.W + xx) * 32 + lane);     // lane = co
+            const float* wrow = wt + t * 1024 + lane;
+#pragma unroll 8
+            for (int co = 0; co < 32; ++co) acc = fmaf(__shfl_sync(0xffffffffu, g, co), wrow[co * 32], acc);
+        }
+        a.GP[(size_t)(e - e_begin) * 32 + lane] = acc;
+    }
+}
+
+// idx_remap[k] = first-entry index of the destination cell of transposed entry k (the row of GP to gather)
+__global__ void shpl_conv_remap_kernel(const int* __restrict__ ptr, const int* __restrict__ ptrT, const int* __restrict__ idxT, int n_rows,
+                                       int n_src, int nnz_max, int* __restrict__ remap) {
+    const int e_begin = __ldg(ptr), t_begin = __ldg(ptrT), t_end = min(__ldg(ptrT + n_src), t_begin + nnz_max);
+    const int k = t_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= t_end) return;
+    const int r = __ldg(idxT + k);
+    SHPL_DASSERT(r >= 0 && r < n_rows);
+    remap[k] = __ldg(ptr + r) - e_begin;
+}
+
+constexpr int kGwChunks = 32;          // chunks of entries the pooled weight gradient is split into
+
+// pooled channels: part_p[t][chunk][ci][co] = sum over the chunk's cells of pooled[cell][ci] * g_out[cell - off(t)][co]
+__global__ void __launch_bounds__(256) shpl_conv_gwp_kernel(const float* __restrict__ PB, const float* __restrict__ g_out, const int* __restrict__ ptr,
+                                                            const int* __restrict__ key, int n_rows, int nnz_max, int H, int W,
+                                                            float* __restrict__ part_p) {
+    const int t = blockIdx.x / kGwChunks, chunk = blockIdx.x % kGwChunks;
+    const int e_begin = __ldg(ptr), e_end = min(__ldg(ptr + n_rows), e_begin + nnz_max);
+    const int per = (e_end - e_begin + kGwChunks - 1) / kGwChunks;
+    const int c0 = e_begin + chunk * per, c1 = min(c0 + per, e_end);
+    const int ci = threadIdx.x >> 3, cq = threadIdx.x & 7;
+    const int HW = H * W;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int e = c0; e < c1; ++e) {
+        const int r = __ldg(key + e);
+        if (e > e_begin && __ldg(key + e - 1) == r) continue;
+        const int f = r / HW, rem = r - f * HW, y = rem / W, x = rem - y * W;
+        const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const float xv = __ldg(PB + (size_t)(e - e_begin) * 32 + ci);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(g_out + ((size_t)(f * H + yy) * W + xx) * 32) + cq);
+        acc.x = fmaf(xv, g.x, acc.x); acc.y = fmaf(xv, g.y, acc.y); acc.z = fmaf(xv, g.z, acc.z); acc.w = fmaf(xv, g.w, acc.w);
+    }
+    reinterpret_cast<float4*>(part_p + ((size_t)(t * kGwChunks + chunk) * 32 + ci) * 32)[cq] = acc;
+}
+
+// dense channels: persistent CTAs over 8 x 32-pixel tiles; thread (ci, co quad) keeps 9 taps x 4 sums in registers
+constexpr int kGwTileY = 8, kGwTileX = 32;
+constexpr int kGwHaloFloats = (kGwTileY + 2) * (kGwTileX + 2) * 32, kGwTileFloats = kGwTileY * kGwTileX * 32;
+constexpr int kGwdSmem = (kGwHaloFloats + kGwTileFloats) * 4;
+
+__global__ void __launch_bounds__(256, 2) shpl_conv_gwd_kernel(const float* __restrict__ x, const float* __restrict__ g_out, int frames, int H, int W,
+                                                               float* __restrict__ part_d) {
+    extern __shared__ float gw_smem[];
+    float* xs = gw_smem;                    // [10][34][32] halo of the input map (zeros outside the image)
+    float* gs = gw_smem + kGwHaloFloats;    // [8][32][32] the output-gradient tile (zeros outside the image)
+    const int tiles_x = (W + kGwTileX - 1) / kGwTileX, tiles_y = (H + kGwTileY - 1) / kGwTileY;
+    const int n_tiles = frames * tiles_x * tiles_y;
+    const int ci = threadIdx.x >> 3, cq = threadIdx.x & 7;
+    float4 acc[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int f = tile / (tiles_x * tiles_y), tt = tile - f * tiles_x * tiles_y;
+        const int y0 = (tt / tiles_x) * kGwTileY, x0 = (tt % tiles_x) * kGwTileX;
+        __syncthreads();
+        for (int i = threadIdx.x; i < kGwHaloFloats / 4; i += 256) {      // float4 units: [10][34][8]
+            const int q = i & 7, px = (i >> 3) % (kGwTileX + 2), py = (i >> 3) / (kGwTileX + 2);
+            const int yy = y0 - 1 + py, xx = x0 - 1 + px;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)(f * H + yy) * W + xx) * 32) + q);
+            reinterpret_cast<float4*>(xs)[i] = v;
+        }
+        for (int i = threadIdx.x; i < kGwTileFloats / 4; i += 256) {
+            const int q = i & 7, px = (i >> 3) % kGwTileX, py = (i >> 3) / kGwTileX;
+            const int yy = y0 + py, xx = x0 + px;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (yy < H && xx < W) v = __ldg(reinterpret_cast<const float4*>(g_out + ((size_t)(f * H + yy) * W + xx) * 32) + q);
+            reinterpret_cast<float4*>(gs)[i] = v;
+        }
+        __syncthreads();
+        for (int py = 0; py < kGwTileY; ++py) {
+#pragma unroll 2
+            for (int px = 0; px < kGwTileX; ++px) {
+                const float4 g = reinterpret_cast<const float4*>(gs + (py * kGwTileX + px) * 32)[cq];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const float xv = xs[((py + t / 3) * (kGwTileX + 2) + px + t % 3) * 32 + ci];
+                    acc[t].x = fmaf(xv, g.x, acc[t].x); acc[t].y = fmaf(xv, g.y, acc[t].y);
+                    acc[t].z = fmaf(xv, g.z, acc[t].z); acc[t].w = fmaf(xv, g.w, acc[t].w);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) reinterpret_cast<float4*>(part_d + (((size_t)blockIdx.x * 9 + t) * 32 + ci) * 32)[cq] = acc[t];
+}
+
+// g_weight[t][ci][co] = the partial sums added in CTA / chunk order (fixed: deterministic)
+__global__ void shpl_conv_gw_reduce_kernel(const float* __restrict__ part_d, int n_ctas, const float* __restrict__ part_p, int c_in_total,
+                                           float* __restrict__ g_weight) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;            // over [9][c_in_total][32]
+    if (i >= 9 * c_in_total * 32) return;
+    const int co = i & 31, ci = (i >> 5) % c_in_total, t = (i >> 5) / c_in_total;
+    float s = 0.f;
+    if (ci < 32) {
+        for (int c = 0; c < n_ctas; ++c) s += part_d[(((size_t)c * 9 + t) * 32 + ci) * 32 + co];
+    } else if (part_p != nullptr) {
+        for (int c = 0; c < kGwChunks; ++c) s += part_p[((size_t)(t * kGwChunks + c) * 32 + ci - 32) * 32 + co];
+    }
+    g_weight[i] = s;
+}
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -910,5 +1068,123 @@ extern "C" int shpl_pool_conv3x3_forward(const float* dst, const float* src, con
         }
     }
     if (int rc = launch_dense(dst, C_d, out, c.wprep, scale, shift, relu, sparse ? c.busy : nullptr, ptr, c.Z, nnz_max, frames, H, W, s)) return rc;
+    return SHPL_OK;
+}
+
+namespace {
+struct BwdWorkspace {
+    float* wprep;
+    float* PB;
+    float* GP;
+    int* remap;
+    float* part_d;
+    float* part_p;
+    int n_ctas;
+    size_t bytes;
+};
+BwdWorkspace carve_bwd(void* ws, long long nnz_max) {
+    BwdWorkspace b;
+    uint8_t* p = static_cast<uint8_t*>(ws);
+    size_t off = 0;
+    auto take = [&](size_t n) { uint8_t* q = p + off; off += align_up(n, 256); return q; };
+    const size_t n = (size_t)(nnz_max > 0 ? nnz_max : 0);
+    b.n_ctas = 2 * 148;                       // persistent CTAs of the dense weight-gradient kernel (fixed: part of the summation tree)
+    b.wprep = reinterpret_cast<float*>(take(kWBytes));
+    b.PB = reinterpret_cast<float*>(take(n * 32 * 4));
+    b.GP = reinterpret_cast<float*>(take(n * 32 * 4));
+    b.remap = reinterpret_cast<int*>(take(n * 4));
+    b.part_d = reinterpret_cast<float*>(take((size_t)b.n_ctas * 9 * 1024 * 4));
+    b.part_p = reinterpret_cast<float*>(take((size_t)9 * kGwChunks * 1024 * 4));
+    b.bytes = off;
+    return b;
+}
+}  // namespace
+
+extern "C" size_t shpl_conv3x3_backward_workspace_bytes(int32_t nnz_max) {
+    if (nnz_max < 0) return 0;
+    return carve_bwd(nullptr, nnz_max).bytes;
+}
+
+extern "C" int shpl_pool_conv3x3_backward(const float* g_out, const float* dst, const float* src, const int32_t* ptr, const int32_t* key,
+                                          const int32_t* idx, const float* val, const int32_t* ptrT, const int32_t* keyT,
+                                          const int32_t* idxT, const float* valT, int32_t nnz_max, int32_t frames, int32_t H, int32_t W,
+                                          int32_t C_d, int32_t n_src, int32_t C_s, const float* weight, int32_t C_out, float* g_dst,
+                                          float* g_src, float* g_weight, void* workspace, size_t workspace_bytes, void* stream) {
+    SHPL_REQUIRE(frames > 0 && H > 0 && W > 0 && n_src >= 0 && nnz_max >= 0, SHPL_ERR_INVALID_ARGUMENT,
+                 "shpl_pool_conv3x3_backward: bad sizes frames=%d H=%d W=%d n_src=%d", frames, H, W, n_src);
+    SHPL_REQUIRE(g_out && weight && workspace && (g_weight == nullptr || dst), SHPL_ERR_INVALID_ARGUMENT,
+                 "shpl_pool_conv3x3_backward: null pointer");
+    SHPL_REQUIRE(C_d == kC && C_out == kC && (C_s == 0 || C_s == 32), SHPL_ERR_UNSUPPORTED,
+                 "shpl_pool_conv3x3_backward: built for C_d = C_out = 32 and C_s in {0, 32} (got %d, %d, %d)", C_d, C_out, C_s);
+    SHPL_REQUIRE(C_s == 0 || (src && ptr && key && idx && val && ptrT && keyT && idxT && valT), SHPL_ERR_INVALID_ARGUMENT,
+                 "shpl_pool_conv3x3_backward: pooled channels need src and both CSR forms");
+    SHPL_REQUIRE((long long)frames * H * W < (1ll << 31), SHPL_ERR_UNSUPPORTED, "shpl_pool_conv3x3_backward: map too large");
+    SHPL_REQUIRE(shpl::aligned(g_out, 16) && shpl::aligned(workspace, 256) && (!g_dst || shpl::aligned(g_dst, 16)) && (!dst || shpl::aligned(dst, 16)),
+                 SHPL_ERR_INVALID_ARGUMENT, "shpl_pool_conv3x3_backward: maps must be 16-byte aligned, workspace 256-byte aligned");
+    const long long cells = (long long)frames * H * W;
+    const bool sparse = C_s > 0 && nnz_max > 0;
+    BwdWorkspace b = carve_bwd(workspace, sparse ? nnz_max : 0);
+    b.n_ctas = 2 * shpl::sm_count() < b.n_ctas ? 2 * shpl::sm_count() : b.n_ctas;
+    SHPL_REQUIRE(workspace_bytes >= b.bytes, SHPL_ERR_WORKSPACE_TOO_SMALL, "shpl_pool_conv3x3_backward: workspace %zu < %zu bytes",
+                 workspace_bytes, b.bytes);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int c_in_total = C_d + C_s;
+    if (g_dst != nullptr) {       // the dense kernel on spatially flipped, in/out-transposed weights
+        shpl_conv_prep_kernel<<<(kWElems + 255) / 256, 256, 0, s>>>(weight, c_in_total, C_out, 0, 1, b.wprep);
+        shpl::count_launches(1);
+        if (int rc = shpl::check_launch("shpl_conv_prep_kernel")) return rc;
+        if (int rc = launch_dense(g_out, kC, g_dst, b.wprep, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, frames, H, W, s)) return rc;
+    }
+    if (sparse && (g_src != nullptr || g_weight != nullptr)) {
+        GpArgs ga{};
+        ga.src = src;
+        ga.g_out = g_out;
+        ga.ptr = ptr;
+        ga.key = key;
+        ga.idx = idx;
+        ga.val = val;
+        ga.w = weight;
+        ga.c_in_total = c_in_total;
+        ga.ci_off = C_d;
+        ga.n_rows = (int)cells;
+        ga.nnz_max = nnz_max;
+        ga.H = H;
+        ga.W = W;
+        ga.PB = b.PB;
+        ga.GP = b.GP;
+        int ggrid = (nnz_max + 7) / 8;
+        const int gcap = shpl::sm_count() * 4;
+        if (ggrid > gcap) ggrid = gcap;
+        shpl_conv_gp_kernel<<<ggrid, 256, 0, s>>>(ga);
+        shpl::count_launches(1);
+        if (int rc = shpl::check_launch("shpl_conv_gp_kernel")) return rc;
+        if (g_src != nullptr) {
+            shpl_conv_remap_kernel<<<(nnz_max + 255) / 256, 256, 0, s>>>(ptr, ptrT, idxT, (int)cells, n_src, nnz_max, b.remap);
+            shpl::count_launches(1);
+            if (int rc = shpl::check_launch("shpl_conv_remap_kernel")) return rc;
+            // g_src[p] = sum over the entries at pixel p, in stored order, of val * g_pooled[cell]: the transpose-CSR kernel
+            if (int rc = shpl_pool_backward_from(b.GP, 32, 0, ptrT, keyT, b.remap, valT, nnz_max, 0, nnz_max, n_src, 32, g_src, stream)) return rc;
+        }
+    } else if (g_src != nullptr && C_s > 0) {
+        SHPL_CUDA_OK(cudaMemsetAsync(g_src, 0, (size_t)n_src * C_s * sizeof(float), s));
+    }
+    if (g_weight != nullptr) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_conv_gwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGwdSmem));
+            attr_set = true;
+        }
+        shpl_conv_gwd_kernel<<<b.n_ctas, 256, kGwdSmem, s>>>(dst, g_out, frames, H, W, b.part_d);
+        shpl::count_launches(1);
+        if (int rc = shpl::check_launch("shpl_conv_gwd_kernel")) return rc;
+        if (sparse) {
+            shpl_conv_gwp_kernel<<<9 * kGwChunks, 256, 0, s>>>(b.PB, g_out, ptr, key, (int)cells, nnz_max, H, W, b.part_p);
+            shpl::count_launches(1);
+            if (int rc = shpl::check_launch("shpl_conv_gwp_kernel")) return rc;
+        }
+        shpl_conv_gw_reduce_kernel<<<(9 * c_in_total * 32 + 255) / 256, 256, 0, s>>>(b.part_d, b.n_ctas, sparse ? b.part_p : nullptr, c_in_total, g_weight);
+        shpl::count_launches(1);
+        if (int rc = shpl::check_launch("shpl_conv_gw_reduce_kernel")) return rc;
+    }
     return SHPL_OK;
 }

@@ -36,7 +36,8 @@ def test_header_declares_the_expected_entry_points():
         "shpl_flip_point_cloud", "shpl_mv3d_project_augment", "shpl_augment_fv_index",
         "shpl_conv3x3_workspace_bytes", "shpl_pool_conv3x3_forward",
         "shpl_pool_forward_into", "shpl_pool_forward_into_dual", "shpl_pool_backward_from",
-        "shpl_pool_heavy_workspace_bytes", "shpl_pool_heavy_split"])
+        "shpl_pool_heavy_workspace_bytes", "shpl_pool_heavy_split",
+        "shpl_conv3x3_backward_workspace_bytes", "shpl_pool_conv3x3_backward"])
 
 
 def test_library_exports_every_declared_symbol(lib):

@@ -105,3 +105,39 @@ def test_unsupported_shapes_are_refused_not_miscomputed(shpl):
     w = torch.zeros((3, 3, 16, 16), device="cuda")
     with pytest.raises(ValueError):
         conv_fusion.sparse_pool_conv3x3([bev, None], None, None, w)
+
+
+@pytest.mark.parametrize("H,W,n,dup", [(50, 44, 3000, True), (23, 30, 0, False), (96, 112, 6000, False)])
+def test_fused_conv_backward_matches_the_oracle(shpl, H, W, n, dup):
+    """g_bev, g_img and g_weight of conv3x3(concat(bev, pooled(img)), W) through autograd against the float64 oracle
+    (conv gradients of the concat form, then the pooling gradient of SURVEY.md a13), each within 1e-5 of its sum of |terms|."""
+    from sparse_pooling_b200 import conv_fusion
+    Hi, Wi = 20, 30
+    rng = np.random.default_rng(7 + n)
+    bev = rng.standard_normal((1, H, W, 32), dtype=np.float32)
+    img = rng.standard_normal((1, Hi, Wi, 32), dtype=np.float32)
+    w = (rng.standard_normal((3, 3, 64, 32)) * 0.1).astype(np.float32)
+    g = rng.standard_normal((1, H, W, 32), dtype=np.float32)
+    Mij, val, flip = _pairs(3, max(n, 1), H, W, Hi, Wi, dup)
+    if n == 0:
+        Mij, val, flip = Mij[:0], val[:0], flip[:0]
+    tb, ti, tw = (torch.from_numpy(x).cuda().requires_grad_(True) for x in (bev, img, w))
+    M = shpl.SparseTensor(torch.from_numpy(Mij).cuda(), torch.from_numpy(val).cuda(), np.array([H * W, len(val)]))
+    out = conv_fusion.sparse_pool_conv3x3_autograd([tb, ti], M, torch.from_numpy(flip).cuda(), tw)
+    out.backward(torch.from_numpy(g).cuda())
+    fused = cref.forward(bev[0], img[0], Mij, val, flip)[None] if n else np.concatenate([bev, np.zeros_like(bev)], axis=3)
+    ref, mag = vo.conv3x3_same(fused, w)
+    assert float((np.abs(out.detach().cpu().numpy() - ref) / np.maximum(mag, 1e-30)).max()) <= TOL
+    g_x, g_w, mag_x, mag_w = vo.conv3x3_same_grad(fused, w, g)
+    assert float((np.abs(tb.grad.cpu().numpy() - g_x[..., :32]) / np.maximum(mag_x[..., :32], 1e-30)).max()) <= TOL
+    assert float((np.abs(tw.grad.cpu().numpy() - g_w) / np.maximum(mag_w, 1e-30)).max()) <= TOL
+    # pooled-path gradient -> image map: g_img[p] = sum_k val_k * g_pooled[row_k]  (float64, then compared at 1e-5 of the term sum)
+    gp, mp = g_x[0, :, :, 32:].reshape(-1, 32), mag_x[0, :, :, 32:].reshape(-1, 32)
+    g_img = np.zeros((Hi * Wi, 32))
+    m_img = np.zeros((Hi * Wi, 32))
+    pix = flip[:, 1] * Wi + flip[:, 2]
+    np.add.at(g_img, pix, val[:, None].astype(np.float64) * gp[Mij[:, 0]])
+    np.add.at(m_img, pix, np.abs(val[:, None].astype(np.float64)) * mp[Mij[:, 0]])
+    err = np.abs(ti.grad.cpu().numpy().reshape(-1, 32) - g_img)
+    assert float((err / np.maximum(m_img, 1e-30))[m_img > 0].max() if (m_img > 0).any() else 0.0) <= TOL
+    assert float(err[m_img == 0].max() if (m_img == 0).any() else 0.0) == 0.0

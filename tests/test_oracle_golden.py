@@ -435,3 +435,20 @@ def test_value_path_exact_arithmetic_kat_numpy_and_c_oracles():
     gi2, gb2 = cref.backward_trans(K.G_FUSED_IMG[0], K.MIJ, K.VAL, K.FLIP, 2, (2, 2, 2))
     np.testing.assert_array_equal(gd + gb2, K.G_BEV_DUAL[0])
     np.testing.assert_array_equal(gi2 + gs, K.G_IMG_DUAL[0])
+
+
+def test_conv_gradient_oracle_agrees_with_torch_autograd():
+    import torch
+    from oracle import value_oracle as vo
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((2, 7, 9, 5))
+    w = rng.standard_normal((3, 3, 5, 4))
+    g = rng.standard_normal((2, 7, 9, 4))
+    g_x, g_w, mag_x, mag_w = vo.conv3x3_same_grad(x, w, g)
+    tx = torch.from_numpy(x).permute(0, 3, 1, 2).requires_grad_(True)
+    tw = torch.from_numpy(w).permute(3, 2, 0, 1).requires_grad_(True)
+    y = torch.nn.functional.conv2d(tx, tw, padding=1)
+    y.backward(torch.from_numpy(g).permute(0, 3, 1, 2))
+    np.testing.assert_allclose(g_x, tx.grad.permute(0, 2, 3, 1).numpy(), rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(g_w, tw.grad.permute(2, 3, 1, 0).numpy(), rtol=1e-11, atol=1e-11)
+    assert (mag_x >= np.abs(g_x) - 1e-9).all() and (mag_w >= np.abs(g_w) - 1e-9).all()
