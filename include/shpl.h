@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SHPL_ABI_VERSION 9
+#define SHPL_ABI_VERSION 10
 
 /* Cells with more entries than this are "heavy": the builder lists them in the plan and their sum
  * is formed by shpl_pool_heavy (a thread-block cluster per cell) instead of one warp walking the cell.
@@ -37,6 +37,9 @@ extern "C" {
  */
 #define SHPL_HEAVY_LEN 512
 #define SHPL_EXACT_LEN 2048
+/* Cells with more entries than this are "long": the builder counts them (counts[6], counts[7]); the pooling kernels sum them
+ * through shared memory (a whole CTA gathers in parallel, the additions stay in entry order) instead of one warp walking them. */
+#define SHPL_LONG_LEN 32
 
 typedef enum shpl_status {
     SHPL_OK = 0,
@@ -76,7 +79,10 @@ typedef struct shpl_plan {
                            frame (the next stacked frame starts there); [5]=1 if this
                            frame's entries did not fit the plan behind the frames stacked
                            before it (capacity < entry base + n: nothing is written out
-                           of bounds, the entries are dropped); [6..7] reserved        */
+                           of bounds, the entries are dropped); [6], [7] = destination
+                           rows / source pixels of this frame with more than SHPL_LONG_LEN
+                           entries: a caller that reads 0 may pass heavy_len = 0 to the
+                           pooling entry points of that direction                       */
 } shpl_plan;
 
 int         shpl_abi_version(void);

@@ -22,7 +22,7 @@ SHPL_ERR_CUDA = -2
 SHPL_ERR_WORKSPACE_TOO_SMALL = -3
 SHPL_ERR_UNSUPPORTED = -4
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 HEAVY_LEN = 512           # SHPL_HEAVY_LEN of include/shpl.h
 EXACT_LEN = 2048          # SHPL_EXACT_LEN: listed cells up to this many entries keep the sequential order
 

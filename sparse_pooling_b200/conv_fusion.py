@@ -42,7 +42,7 @@ def sparse_pool_conv3x3(inputs, M, img_index_flip, weight, scale=None, shift=Non
         if plan.frames != B:
             raise ValueError("feature batch %d != frames in the plan %d" % (B, plan.frames))
         Ci, n_src = img.shape[3], plan.n_src
-        ptr, key, idx, val, nnz_max, _ = plan.by_row()
+        ptr, key, idx, val, nnz_max, _, _ = plan.by_row()
         src = img.contiguous()
     else:
         Ci, n_src, ptr, key, idx, val, nnz_max, src = 0, 0, None, None, None, None, 0, None
@@ -89,8 +89,8 @@ class SparsePoolConv3x3Function(torch.autograd.Function):
         g_bev = torch.empty_like(bev) if need_b else None
         g_img = torch.empty_like(img) if need_i else None
         g_w = torch.empty_like(weight) if need_w else None
-        ptr, key, idx, val, nnz_max, _ = plan.by_row()
-        ptrT, keyT, idxT, valT, _, _ = plan.by_pixel()
+        ptr, key, idx, val, nnz_max, _, _ = plan.by_row()
+        ptrT, keyT, idxT, valT, _, _, _ = plan.by_pixel()
         need = int(_lib.shpl_conv3x3_backward_workspace_bytes(int(nnz_max)))
         ws = ops.scratch("conv_bwd", bev.device, need + 256)
         off = (-ws.data_ptr()) % 256

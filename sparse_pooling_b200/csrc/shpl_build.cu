@@ -246,6 +246,8 @@ __global__ void __launch_bounds__(kThreads) shpl_pairs_kernel(PairsArgs a, int u
         a.counts[0] = (int)n_clip;
         a.counts[1] = (a.mode == kModeGenOnly) ? 0 : (int)nnz;
         a.counts[5] = 0;                          // set by the finalize kernel when a stacked frame overruns the plan
+        a.counts[6] = 0;                          // rows / pixels with more than SHPL_LONG_LEN entries (finalize kernel)
+        a.counts[7] = 0;
         if (a.msize_out) { a.msize_out[0] = R; a.msize_out[1] = nnz; }
     }
 
@@ -369,6 +371,13 @@ __global__ void __launch_bounds__(kThreads) shpl_finalize_kernel(FinalArgs a, in
         // heavy cells (more than SHPL_HEAVY_LEN entries) are listed for shpl_pool_heavy
         s_off[threadIdx.x] = lb;
         __syncthreads();
+        {   // cells with more than SHPL_LONG_LEN entries, counted: a caller that reads 0 back may tell the pooling entry points
+            // (heavy_len = 0) that no cell needs the long-cell paths
+            const int next = (threadIdx.x + 1 < kThreads && j + 1 < j1) ? s_off[threadIdx.x + 1] : w1;
+            const bool is_long = j < j1 && j < n_keys && next - lb > SHPL_LONG_LEN;
+            const int n_long = __syncthreads_count(is_long);
+            if (threadIdx.x == 0 && n_long > 0) atomicAdd(a.counts + (is_row ? 6 : 7), n_long);
+        }
         if (a.plan.heavy_cap > 0 && j < j1 && j < n_keys) {
             const int next = (threadIdx.x + 1 < kThreads && j + 1 < j1) ? s_off[threadIdx.x + 1] : w1;
             if (next - lb > SHPL_HEAVY_LEN) {

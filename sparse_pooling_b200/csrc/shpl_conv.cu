@@ -45,27 +45,32 @@ constexpr int kWDyBytes = kChunks * kWChunkBytes;    // 24576
 constexpr int kWBytes = 3 * kWDyBytes;               // 73728
 constexpr int kWElems = kWBytes / 4;
 constexpr int kOutRows = kTileY * kTileX;            // 112
-constexpr int kOutBytes = 16384;                     // 112 x 128 B used
-static_assert(kOutRows * 128 <= kOutBytes, "output staging");
+constexpr int kOutBytes = kOutRows * 128;            // 14336: one output tile, 128B-swizzled rows
+static_assert(kOutBytes % 1024 == 0, "output staging buffers stay 1024-byte aligned (swizzle atom)");
 constexpr int kWorkers = 256;
-constexpr int kConvThreads = kWorkers + 64;
+constexpr int kSparseWarps = 4;                      // warps 10..13: the pooled half's contributions, one tile ahead
+constexpr int kSparseRows = kOutRows / kSparseWarps; // 28 output pixels per sparse warp
+constexpr int kSparseCand = kSparseRows * 9;         // (pixel, tap) candidates per sparse warp: 252 = 8 rounds of 32 lanes
+constexpr int kSparseRounds = (kSparseCand + 31) / 32;
+constexpr int kConvThreads = kWorkers + 64 + kSparseWarps * 32;
 constexpr int kAccCols = kNB;                        // columns of one accumulator buffer
 constexpr int kTmemCols = 512;                       // 2 x 192 used
 
 // dynamic shared memory map (byte offsets from a 1024-aligned base)
-constexpr int kSmOut = 0;                                  // 1024-aligned (128B-swizzled TMA store source)
-constexpr int kSmStage = kSmOut + kOutBytes;               // 2 x 20480
+constexpr int kSmOut = 0;                                  // 2 x 14336, 1024-aligned (128B-swizzled TMA store source)
+constexpr int kSmStage = kSmOut + 2 * kOutBytes;           // 2 x 20480
 constexpr int kSmW = kSmStage + 2 * kStageBytes;           // 73728
 constexpr int kSmOpnd = kSmW + kWBytes;                    // 2 x 41216
 constexpr int kSmBar = kSmOpnd + 2 * kOpndBytes;           // mbarriers
-constexpr int kSmScale = kSmBar + 128;                     // scale[32], shift[32]
+constexpr int kSmScale = kSmBar + 256;                     // scale[32], shift[32]
 constexpr int kSmEnd = kSmScale + 256;
 constexpr int kConvSmem = kSmEnd + 1024;                   // + slack for the 1024-byte alignment of the base
 static_assert(kConvSmem <= 227 * 1024, "dense conv kernel: shared memory budget");
 static_assert(kSmStage % 128 == 0 && kSmW % 128 == 0 && kSmOpnd % 16 == 0 && kSmBar % 8 == 0, "smem alignment");
 
 enum { BAR_STAGE_FULL = 0, BAR_STAGE_EMPTY = 2, BAR_OPND_FULL = 4, BAR_OPND_EMPTY = 6, BAR_ACC_FULL = 8, BAR_ACC_EMPTY = 10,
-       BAR_W = 12, BAR_COUNT = 13 };
+       BAR_W = 12, BAR_CONTRIB_FULL = 13, BAR_OUT_EMPTY = 15, BAR_COUNT = 17 };
+static_assert(BAR_COUNT * 8 <= 256, "mbarrier region");
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,7 +120,6 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // D[tmem] (+)= A[smem] . B[smem], kind::tf32, issued by one thread for the CTA
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out, ConvArgs a) {
     extern __shared__ uint8_t conv_smem_raw[];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ uint32_t halo_bits[kHaloY];       // busy bits of the current tile's halo rows (epilogue warps)
+    __shared__ uint32_t halo_bits[2][kHaloY];    // busy bits of a tile's halo rows (sparse warps; double-buffered)
     const uint32_t raw = smem_u32(conv_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* gbase = conv_smem_raw + (base - raw);
@@ -188,6 +192,8 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
             mbar_init(bar(BAR_OPND_EMPTY + s), 1);
             mbar_init(bar(BAR_ACC_FULL + s), 1);
             mbar_init(bar(BAR_ACC_EMPTY + s), 4);        // the four epilogue warps
+            mbar_init(bar(BAR_CONTRIB_FULL + s), kSparseWarps);
+            mbar_init(bar(BAR_OUT_EMPTY + s), 1);        // the thread that commits the tile stores
         }
         mbar_init(bar(BAR_W), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -256,7 +262,7 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
                 umma_commit(bar(BAR_ACC_FULL + s));
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 8) {
         // ===== conversion warps (4..7): staging -> hi / lo operand planes =====
         const int ctid = tid - 128;
         for (int i = 0; i < n_mine; ++i) {
@@ -288,93 +294,134 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
                 mbar_arrive(bar(BAR_STAGE_EMPTY + s));
             }
         }
+    } else if (warp >= 10) {
+        // ===== sparse warps (10..13): the pooled half of the conv, one tile ahead of the epilogue =====
+        // For every output pixel of the tile: the sum, in (pixel, tap) order (a fixed order: deterministic), of the Z rows of
+        // its busy neighbours -- Z[cell][tap] = W_pooled[tap]^T . pooled[cell], from the Z kernel -- left in the tile's
+        // output staging buffer, where the epilogue adds the dense half on top.  A warp owns 28 pixels; lane = output
+        // channel, so a Z row is one coalesced 128-byte load.  No global latency is exposed per tile but the Z loads:
+        //   tile i+2: ten threads load the busy-bitmap words of the halo rows
+        //   tile i+1: the words go to shared memory, every lane tests its (pixel, tap) candidates and issues the CSR-offset
+        //             loads of the busy ones
+        //   tile i  : offsets -> Z rows -> read-modify-write of the staging rows
+        if (a.busy != nullptr && n_mine > 0) {
+            const int sw = warp - 10, stid = tid - 320;
+            const int e_begin = __ldg(a.ptr);
+            uint32_t hw_lo = 0u, hw_hi = 0u;
+            int hw_sh = 0, hw_nv = 0, hw_ls = 0;
+            auto issue_halo = [&](int j) {                               // stid < 10: raw bitmap words of halo row `stid` of tile j
+                hw_nv = 0;
+                if (j >= n_mine || stid >= kHaloY) return;
+                int f, y0, x0;
+                tile_coord(j, f, y0, x0);
+                const int yy = y0 - 1 + stid;
+                if (yy < 0 || yy >= a.H) return;
+                const int xs = x0 > 0 ? x0 - 1 : 0;                      // first in-image halo column
+                const long long c = ((long long)f * a.H + yy) * a.W + xs;
+                const long long last = ((long long)a.frames * a.H * a.W - 1) >> 5;
+                const long long wi = c >> 5;
+                hw_lo = __ldg(a.busy + wi);
+                hw_hi = wi + 1 <= last ? __ldg(a.busy + wi + 1) : 0u;
+                hw_sh = (int)(c & 31);
+                hw_ls = xs - (x0 - 1);
+                hw_nv = min(a.W - xs, kHaloX - hw_ls);                   // columns of this row inside the image
+            };
+            auto publish_halo = [&](int j) {                             // the loaded words -> halo_bits[j & 1]
+                if (stid < kHaloY) {
+                    uint32_t bits = 0u;
+                    if (hw_nv > 0) {
+                        bits = (uint32_t)(((((uint64_t)hw_hi) << 32) | hw_lo) >> hw_sh) & 0xffffu;
+                        bits &= (1u << hw_nv) - 1u;
+                        bits <<= hw_ls;
+                    }
+                    halo_bits[j & 1][stid] = bits;
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+            };
+            int poff[kSparseRounds], poff_n[kSparseRounds];              // CSR offsets of this lane's busy candidates (-1: none)
+            auto issue_offsets = [&](int j, int (&po)[kSparseRounds]) {  // needs halo_bits[j & 1]
+                int f, y0, x0;
+                tile_coord(j, f, y0, x0);
+#pragma unroll
+                for (int rd = 0; rd < kSparseRounds; ++rd) {
+                    const int c = rd * 32 + lane;
+                    po[rd] = -1;
+                    if (c < kSparseCand) {
+                        const int pl = c / 9, t = c - pl * 9;
+                        const int r = sw * kSparseRows + pl, yl = r / kTileX, xl = r - yl * kTileX;
+                        const int hy = yl + t / 3, hx = xl + t % 3;
+                        const bool on = ((halo_bits[j & 1][hy] >> hx) & 1u) && y0 + yl < a.H && x0 + xl < a.W;
+                        if (on) {
+                            const int nb = (f * a.H + y0 + hy - 1) * a.W + x0 + hx - 1;
+                            SHPL_DASSERT(nb >= 0 && nb < a.frames * a.H * a.W);
+                            po[rd] = __ldg(a.ptr + nb);
+                        }
+                    }
+                }
+            };
+            issue_halo(0);
+            publish_halo(0);
+            issue_offsets(0, poff);
+            issue_halo(1);
+            for (int i = 0; i < n_mine; ++i) {
+                const int ob = i & 1, u = i >> 1;
+                if (i + 1 < n_mine) {
+                    publish_halo(i + 1);
+                    issue_offsets(i + 1, poff_n);
+                    issue_halo(i + 2);
+                }
+                mbar_wait(bar(BAR_OUT_EMPTY + ob), (u & 1) ^ 1);         // the store of tile i-2 has read this buffer
+                uint8_t* obase = gbase + kSmOut + ob * kOutBytes;
+                {   // zeros for the warp's 28 rows (3584 contiguous bytes)
+                    float4* z = reinterpret_cast<float4*>(obase + sw * kSparseRows * 128);
+#pragma unroll
+                    for (int k = 0; k < kSparseRows * 8 / 32; ++k) z[k * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int rd = 0; rd < kSparseRounds; ++rd) {
+                    uint32_t m = __ballot_sync(0xffffffffu, poff[rd] >= 0);
+                    while (m) {                                          // up to four Z rows in flight
+                        int rr[4];
+                        float zv[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            rr[k] = -1;
+                            if (m) {
+                                const int bsel = __ffs(m) - 1;
+                                m &= m - 1;
+                                const int c = rd * 32 + bsel;
+                                const int pl = c / 9, t = c - pl * 9;
+                                const int zr = (__shfl_sync(0xffffffffu, poff[rd], bsel) - e_begin) * 9 + t;
+                                SHPL_DASSERT(zr >= 0 && zr / 9 < a.z_rows);
+                                zv[k] = __ldg(a.Z + (size_t)zr * 32 + lane);
+                                rr[k] = sw * kSparseRows + pl;
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (rr[k] >= 0) {
+                                float* cell = reinterpret_cast<float*>(obase + rr[k] * 128 + ((((lane >> 2) ^ (rr[k] & 7))) << 4)) + (lane & 3);
+                                *cell += zv[k];
+                            }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(BAR_CONTRIB_FULL + ob));
+#pragma unroll
+                for (int rd = 0; rd < kSparseRounds; ++rd) poff[rd] = poff_n[rd];
+            }
+        }
     } else {
-        // ===== epilogue warps (0..3): TMEM -> registers -> swizzled smem -> TMA store =====
+        // ===== epilogue warps (0..3): TMEM -> registers (+ the pooled half from the staging buffer) -> swizzled smem -> TMA store =====
         const int q = warp;                                  // TMEM lane quadrant
         const int m = q * 32 + lane, yl = m >> 4, xq = m & 15;
         const bool col_ok = xq >= 1 && xq <= kTileX;
-        // ---- The pooled half's lookups, software-pipelined so that no global latency sits on the epilogue's critical path:
-        //   tile i+2: ten threads load the busy-bitmap words of the tile's halo rows (10 rows x 16 columns)
-        //   tile i+1: the words go to shared memory; every thread tests its nine neighbour bits and issues the (few)
-        //             CSR-offset loads of the busy ones, predicated, side by side
-        //   tile i  : offsets -> Z rows; an L1 prefetch of each (one 128-byte line), then the wait for the accumulators
         const bool pooled = a.busy != nullptr;
-        const int e_begin = pooled ? __ldg(a.ptr) : 0;
-        uint32_t hw_lo = 0u, hw_hi = 0u;           // tid < 10: raw bitmap words of the halo row, tile in flight
-        int hw_sh = 0, hw_nv = 0, hw_ls = 0;       //           bit offset, valid columns, left shift
-        int poff[9];                                // CSR offsets of the busy neighbours (loads in flight)
-        uint32_t pnear = 0u;
-        auto issue_halo = [&](int j) {
-            hw_nv = 0;
-            if (j >= n_mine || tid >= kHaloY) return;
-            int f, y0, x0;
-            tile_coord(j, f, y0, x0);
-            const int yy = y0 - 1 + tid;
-            if (yy < 0 || yy >= a.H) return;
-            const int xs = x0 > 0 ? x0 - 1 : 0;                           // first in-image halo column
-            const long long c = ((long long)f * a.H + yy) * a.W + xs;
-            const long long last = ((long long)a.frames * a.H * a.W - 1) >> 5;
-            const long long wi = c >> 5;
-            hw_lo = __ldg(a.busy + wi);
-            hw_hi = wi + 1 <= last ? __ldg(a.busy + wi + 1) : 0u;
-            hw_sh = (int)(c & 31);
-            hw_ls = xs - (x0 - 1);
-            hw_nv = min(a.W - xs, kHaloX - hw_ls);                       // columns of this row inside the image
-        };
-        auto issue_offsets = [&](int j) {                                 // needs halo_bits of tile j in shared memory
-            int f, y0, x0;
-            tile_coord(j, f, y0, x0);
-            const int gy = y0 + yl, gx = x0 + xq - 1;
-            pnear = 0u;
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) pnear |= ((halo_bits[yl + dy] >> (xq > 0 ? xq - 1 : 0)) & 7u) << (3 * dy);
-            if (!(col_ok && gy < a.H && gx < a.W)) pnear = 0u;
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int nb = (f * a.H + gy + t / 3 - 1) * a.W + gx + t % 3 - 1;
-                const bool on = (pnear >> t) & 1u;
-                SHPL_DASSERT(!on || (nb >= 0 && nb < a.frames * a.H * a.W));
-                poff[t] = on ? __ldg(a.ptr + nb) : 0;
-            }
-        };
-        auto publish_halo = [&]() {                                       // the words loaded by issue_halo -> shared memory
-            if (tid < kHaloY) {
-                uint32_t bits = 0u;
-                if (hw_nv > 0) {
-                    bits = (uint32_t)(((((uint64_t)hw_hi) << 32) | hw_lo) >> hw_sh) & 0xffffu;
-                    bits &= (1u << hw_nv) - 1u;
-                    bits <<= hw_ls;
-                }
-                halo_bits[tid] = bits;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-        };
-        if (pooled && n_mine > 0) {
-            issue_halo(0);
-            publish_halo();
-            issue_offsets(0);
-            issue_halo(1);
-        }
         for (int i = 0; i < n_mine; ++i) {
             const int s = i & 1, u = i >> 1;
             int f, y0, x0;
             tile_coord(i, f, y0, x0);
-            int zrow[9];
-            uint32_t zmask = 0u;                 // bit t: this pixel's neighbour at tap t contributes a Z row
-            if (pooled) {
-                zmask = pnear;
-#pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    zrow[t] = ((zmask >> t) & 1u) ? (poff[t] - e_begin) * 9 + t : -1;
-                    // a Z row is one 128-byte line: pull it into L1 now; the loads after the accumulator wait can hit
-                    if (zrow[t] >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.Z + (size_t)zrow[t] * 32));
-                }
-                if (i + 1 < n_mine) {
-                    publish_halo();              // tile i+1's halo bits (loaded during the previous tile)
-                    issue_offsets(i + 1);
-                    issue_halo(i + 2);
-                }
-            }
             mbar_wait(bar(BAR_ACC_FULL + s), u & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * kAccCols);
@@ -401,27 +448,15 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY + s));
-            if (pooled) {
-                // + sum over the busy neighbours, in tap order (a fixed order: deterministic), of their Z rows.  Round k
-                // handles the k-th busy tap of every lane together, so a warp pays one latency per round and there are as
-                // many rounds as the busiest pixel of the warp has busy neighbours (1-3), not nine.
-                while (__any_sync(0xffffffffu, zmask != 0u)) {
-                    if (zmask != 0u) {
-                        const int t = __ffs(zmask) - 1;
-                        zmask &= zmask - 1u;
-                        int zr = zrow[0];
+            // the staging buffer of this tile: filled with the pooled half by the sparse warps, or just free again
+            mbar_wait(bar((pooled ? BAR_CONTRIB_FULL : BAR_OUT_EMPTY) + s), pooled ? (u & 1) : ((u & 1) ^ 1));
+            uint8_t* orow = gbase + kSmOut + s * kOutBytes + (yl * kTileX + xq - 1) * 128;
+            const int rsw = (yl * kTileX + xq - 1) & 7;
+            if (pooled && col_ok) {
 #pragma unroll
-                        for (int tt = 1; tt < 9; ++tt) zr = (t == tt) ? zrow[tt] : zr;
-                        SHPL_DASSERT(zr >= 0 && zr / 9 < a.z_rows);
-                        const float4* z = reinterpret_cast<const float4*>(a.Z + (size_t)zr * 32);
-                        float4 zv[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) zv[j] = __ldg(z + j);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            o[4 * j] += zv[j].x; o[4 * j + 1] += zv[j].y; o[4 * j + 2] += zv[j].z; o[4 * j + 3] += zv[j].w;
-                        }
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    const float4 z = *reinterpret_cast<const float4*>(orow + ((j ^ rsw) << 4));
+                    o[4 * j] += z.x; o[4 * j + 1] += z.y; o[4 * j + 2] += z.z; o[4 * j + 3] += z.w;
                 }
             }
 #pragma unroll
@@ -430,20 +465,20 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
                 if (a.relu) x = fmaxf(x, 0.f);
                 o[c] = x;
             }
-            if (tid == 0) bulk_wait_read0();       // the previous tile's store has read the staging buffer
-            asm volatile("bar.sync 1, 128;" ::: "memory");
             if (col_ok) {
-                const int r = yl * kTileX + xq - 1;
-                uint8_t* orow = gbase + kSmOut + r * 128;
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<float4*>(orow + ((j ^ (r & 7)) << 4)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    *reinterpret_cast<float4*>(orow + ((j ^ rsw) << 4)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
             }
             fence_proxy_async();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (tid == 0) {
-                tma_store_4d(&map_out, base + kSmOut, 0, x0, y0, f);
+                tma_store_4d(&map_out, base + kSmOut + s * kOutBytes, 0, x0, y0, f);
                 bulk_commit();
+                if (i > 0) {       // the store of tile i-1 has read its buffer: free for tile i+1
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    mbar_arrive(bar(BAR_OUT_EMPTY + (s ^ 1)));
+                }
             }
         }
         if (tid == 0) bulk_wait0();

@@ -163,6 +163,7 @@ struct Job {
     int stream_ctas;         // sparse: CTAs of this job that stream the dense parts and zeros
     int packed;              // sparse: 1 = lane-group entry walk for few vectors per cell (SHPL_PACKED=0 switches it off)
     int long_len;            // sparse: cells with more entries are summed by the stream warps as a whole (kLongRow; 512 when packed)
+    int staged;              // sparse, staged instantiation: 2 = every entry CTA takes the staged walk, 1 = only CTAs that meet a long cell
     int entry_chunk;         // wide: entries per warp
     int tiles;               // narrow: warp tiles; wide: CTA tiles of kWideTile cells
 };
@@ -211,7 +212,7 @@ __device__ __forceinline__ void copy_tile(const V* __restrict__ in, int in_strid
     }
 }
 
-constexpr int kLongRow = 32;      // narrow kernels: cells with more entries are summed by the whole warp
+constexpr int kLongRow = SHPL_LONG_LEN;      // narrow kernels: cells with more entries are summed by the whole warp
 constexpr int kLongUnroll = 4;
 
 // One long cell by the whole warp (narrow kernels).  The lanes form E = 32 / nv groups of nv lanes; group g
@@ -796,6 +797,163 @@ __global__ void __launch_bounds__(kThreads, SHPL_WIDE_MIN_CTAS) shpl_pool_wide_k
 }
 
 
+// ------------------------------------------------------------------------------------ staged
+// Entry walk of a whole CTA through shared memory, for many entries per cell (the dense regime, ground-plane and Zipf
+// skew).  The serial part of an fp32 sum in a fixed order is only the chain of additions; everything else is parallel:
+//   phase 0  a batch of B = min(512, 2048 / nv) consecutive entries (key, idx, val) -> shared memory, coalesced
+//   phase A  thread -> (entry, channel vector): up to 8 gathers in flight per thread, the rounded products val * row
+//            parked in shared memory in entry order
+//   phase B  run heads of the batch (key changes) numbered by ballots + a prefix over the 8 warps
+//   phase C  thread -> (run, channel vector): adds the run's products in stored order from shared memory (an LDS and
+//            the 4-cycle add per entry instead of the ~60 issue cycles of a shuffle hand-over) and writes the cell;
+//            the run left open at the end of the batch is carried (sum and length) into the next batch
+// Same products, same additions, same order as the sequential walk: bit-identical.  Ownership as everywhere: the CTA owns
+// the cells whose first entry lies in its chunk [E0, E1) and walks [end of the cell running into E0, end of the last
+// owned cell).  Cells whose running length exceeds heavy_len are dropped at that point and skipped (the heavy kernels
+// write them), so a 178 k-entry cell costs its owner heavy_len + B wasted entries.
+constexpr int kStageVecs = 2048;          // product vectors per batch (32 KB of float4)
+constexpr int kStageEntries = 512;        // entries per batch at most
+constexpr int kStageMaxVecs = 64;         // channel vectors per cell the staged walk takes (batch >= 32 entries)
+
+template <typename V> constexpr int stage_smem_bytes() {
+    return (kStageVecs + 2 * kStageMaxVecs) * (int)sizeof(V) + (4 * kStageEntries + 2 + 32) * 4;
+}
+
+template <typename V, bool kAdd>
+__device__ __noinline__ void pool_entries_staged(const V* __restrict__ src, int src_stride, const int* __restrict__ key,
+                                                 const int* __restrict__ idx, const float* __restrict__ val,
+                                                 const int* __restrict__ ptr, int E0, int E1, int e_begin, int e_end,
+                                                 V* __restrict__ out, int out_stride, const V* __restrict__ addend,
+                                                 int add_stride, int nv, int shift, int heavy_len, int n_gather,
+                                                 int n_cells, unsigned char* smem) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    V* s_prod = reinterpret_cast<V*>(smem);
+    V* s_carry = s_prod + kStageVecs;                                   // [2][kStageMaxVecs]
+    int* s_key = reinterpret_cast<int*>(s_carry + 2 * kStageMaxVecs);   // [kStageEntries + 1]: + the key after the batch
+    int* s_idx = s_key + kStageEntries + 1;
+    float* s_val = reinterpret_cast<float*>(s_idx + kStageEntries);
+    int* s_run = reinterpret_cast<int*>(s_val + kStageEntries);         // [kStageEntries + 1] run starts
+    int* s_wtot = s_run + kStageEntries + 1;                            // [8] run heads per warp
+    int* s_ctl = s_wtot + 8;                                            // [2][4]: carry_row, carry_len, next_pos, n_runs
+
+    int start = E0;
+    if (E0 > e_begin) start = __ldg(ptr + __ldg(key + E0 - 1) + 1);     // the end of the cell running into this chunk
+    if (start >= E1) return;                                            // no cell starts here
+    const int stop = E1 < e_end ? __ldg(ptr + __ldg(key + E1 - 1) + 1) : e_end;
+    SHPL_DASSERT(start >= E0 && stop >= E1 && stop <= e_end);
+    const int B = min(kStageEntries, kStageVecs / nv);
+    int par = 0;
+    if (tid == 0) {
+        s_ctl[0] = -1;
+        s_ctl[1] = 0;
+    }
+    int pos = start;
+    while (pos < stop) {
+        const int n = min(B, stop - pos);
+        // ---- phase 0: the batch's entries
+        for (int j = tid; j <= n; j += kThreads) {
+            const int k = pos + j;
+            if (j < n) {
+                s_key[j] = __ldg(key + k);
+                s_idx[j] = __ldg(idx + k);
+                s_val[j] = __ldg(val + k);
+            } else {
+                s_key[n] = k < e_end ? __ldg(key + k) : -1;
+            }
+        }
+        __syncthreads();
+        // ---- phase A (loads): thread -> (entry, vector)
+        const int total = n * nv;
+        V x[8];
+        int ej[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = u * kThreads + tid;
+            ej[u] = -1;
+            if (i < total) {
+                const int j = shift >= 0 ? (i >> shift) : i / nv;
+                const int q = i - j * nv;
+                const int p = s_idx[j];
+                SHPL_DASSERT((unsigned)p < (unsigned)n_gather && (unsigned)s_key[j] < (unsigned)n_cells);
+                x[u] = __ldg(src + (size_t)p * src_stride + q);
+                ej[u] = j;
+            }
+        }
+        // ---- phase B: run heads (entries 2 tid, 2 tid + 1 of the batch)
+        const int ja = 2 * tid, jb2 = 2 * tid + 1;
+        const bool ha = ja < n && (ja == 0 || s_key[ja] != s_key[ja - 1]);
+        const bool hb = jb2 < n && s_key[jb2] != s_key[jb2 - 1];
+        const unsigned ba = __ballot_sync(kFull, ha), bb = __ballot_sync(kFull, hb);
+        if (lane == 0) s_wtot[warp] = __popc(ba) + __popc(bb);
+        __syncthreads();
+        {
+            int wbase = 0, all = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < kWarps; ++w2) {
+                const int c = s_wtot[w2];
+                wbase += w2 < warp ? c : 0;
+                all += c;
+            }
+            const unsigned lt = (1u << lane) - 1u;
+            const int rank = wbase + __popc(ba & lt) + __popc(bb & lt);
+            if (ha) s_run[rank] = ja;
+            if (hb) s_run[rank + (ha ? 1 : 0)] = jb2;
+            if (tid == 0) {
+                s_run[all] = n;
+                s_ctl[4 * par + 3] = all;
+            }
+        }
+        // ---- phase A (products, in entry order)
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (ej[u] >= 0) s_prod[u * kThreads + tid] = vscale(s_val[ej[u]], x[u]);
+        __syncthreads();
+        // ---- phase C: thread -> (run, vector); additions in stored order
+        const int carry_row = s_ctl[4 * par], carry_len = s_ctl[4 * par + 1], n_runs = s_ctl[4 * par + 3];
+        const V* carry_in = s_carry + par * kStageMaxVecs;
+        V* carry_out = s_carry + (par ^ 1) * kStageMaxVecs;
+        const int pairs = n_runs * nv;
+        for (int i = tid; i < pairs; i += kThreads) {
+            const int r = shift >= 0 ? (i >> shift) : i / nv;
+            const int q = i - r * nv;
+            const int j0 = s_run[r], j1 = s_run[r + 1];
+            const int row = s_key[j0];
+            const bool cont = r == 0 && row == carry_row;
+            V acc = cont ? carry_in[q] : vzero((V*)nullptr);
+            const int len = (cont ? carry_len : 0) + (j1 - j0);
+            const V* pp = s_prod + j0 * nv + q;
+            for (int j = j0; j < j1; ++j, pp += nv) acc = vadd(acc, *pp);
+            if (s_key[j1] != row) {                                     // the cell ends inside the batch
+                if (!(heavy_len > 0 && len > heavy_len)) {
+                    if constexpr (kAdd) acc = vadd(ld_stream(addend + (size_t)row * add_stride + q), acc);
+                    st_stream(out + (size_t)row * out_stride + q, acc);
+                }
+            } else {
+                carry_out[q] = acc;
+            }
+        }
+        if (tid == 0) {
+            const int j0 = s_run[n_runs - 1];
+            const int row = s_key[j0];
+            int nrow = -1, nlen = 0, npos = pos + n;
+            if (s_key[n] == row) {                                      // open run: carried into the next batch
+                nlen = ((n_runs == 1 && row == carry_row) ? carry_len : 0) + (n - j0);
+                nrow = row;
+                if (heavy_len > 0 && nlen > heavy_len) {                // a heavy cell: dropped, skipped
+                    nrow = -1;
+                    npos = __ldg(ptr + row + 1);
+                }
+            }
+            s_ctl[4 * (par ^ 1)] = nrow;
+            s_ctl[4 * (par ^ 1) + 1] = nlen;
+            s_ctl[4 * (par ^ 1) + 2] = npos;
+        }
+        __syncthreads();
+        par ^= 1;
+        pos = s_ctl[4 * par + 2];
+    }
+}
+
 // ------------------------------------------------------------------------------------ sparse
 // Narrow channel counts in the SPARSE regime (few entries per cell on average: KITTI / MV3D shapes, where ~2 % of
 // the BEV cells receive anything).  shpl_pool_narrow_kernel walks a busy cell's entries inside the streaming warp:
@@ -806,7 +964,7 @@ __global__ void __launch_bounds__(kThreads, SHPL_WIDE_MIN_CTAS) shpl_pool_wide_k
 // nothing, one dependent load (the tile's offsets) away from a bare copy.  Same sums in the same order.
 __host__ __device__ __forceinline__ bool packed_ok(const Job& jb) { return jb.vs_shift >= 0 && jb.vs <= 16 && jb.packed; }
 
-template <int W, bool kAdd, int ACC>
+template <int W, bool kAdd, int ACC, bool kStaged = false>
 __global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SHPL_SPARSE_MIN_CTAS_WIDE) shpl_pool_sparse_kernel(PoolArgs a) {
     using V = typename VecOf<W>::type;
     const int lane = threadIdx.x & 31;
@@ -818,6 +976,36 @@ __global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SH
     V* pout = static_cast<V*>(jb.pool_out);
     if (b < jb.entry_ctas) {       // gather CTAs first: they hold the dependent chains
         const int e_begin = __ldg(jb.ptr), e_end = __ldg(jb.ptr + jb.n_cells);
+        if constexpr (kStaged) {
+            // The staged instantiation (launched with dynamic shared memory): the CTA as a whole takes its chunk through
+            // shared memory when the host asked for it (dense regime: jb.staged == 2) or when the chunk meets a cell of
+            // more than kLongRow entries -- a run that long covers one of the sample points 32 entries apart or the
+            // chunk's last entry; otherwise its warps walk their sub-chunks as in the plain instantiation (none of their
+            // cells is long then).
+            extern __shared__ __align__(16) unsigned char stage_smem[];
+            const int cta_chunk = jb.entry_chunk * kWarps;
+            const int E0 = e_begin + b * cta_chunk;
+            if (E0 >= e_end) return;
+            const int E1 = min(E0 + cta_chunk, e_end);
+            bool staged = jb.staged == 2;
+            if (!staged) {
+                // keys 16 entries apart, from the chunk's first entry to 48 past its end: a cell of more than 32 entries
+                // that starts in the chunk covers two neighbouring sample points (one load level; a false positive --
+                // a cell of 17 ... 32 entries, or the clipped tail -- only means the staged walk takes a chunk it did not need to)
+                bool hit = false;
+                for (int sp = lane; 16 * sp < cta_chunk + 48; sp += 32) {
+                    const int ka = E0 + 16 * sp, kb = ka + 16;
+                    if (ka < e_end - 1) hit = hit || __ldg(jb.key + ka) == __ldg(jb.key + (kb < e_end ? kb : e_end - 1));
+                }
+                staged = __any_sync(kFull, hit);
+            }
+            if (staged) {
+                pool_entries_staged<V, kAdd>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.key, jb.idx, jb.val, jb.ptr,
+                                             E0, E1, e_begin, e_end, pout, jb.pool_out_stride, kAdd ? din : nullptr,
+                                             jb.dense_in_stride, jb.vs, jb.vs_shift, jb.heavy_len, jb.n_gather, jb.n_cells, stage_smem);
+                return;
+            }
+        }
         const int e0 = e_begin + (b * kWarps + warp) * jb.entry_chunk;
         if (e0 >= e_end) return;
         if (ACC == 1 && packed_ok(jb)) {      // few vectors per cell: lane groups gather different entries
@@ -864,7 +1052,7 @@ __global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SH
             // written for them here
             const bool heavy = lane < rows && jb.heavy_len > 0 && hi - lo > jb.heavy_len;
             busy = __ballot_sync(kFull, hi > lo);                          // cells somebody else writes (entry CTAs, heavy kernels) ...
-            longs = jb.vs <= 32 ? __ballot_sync(kFull, !heavy && hi - lo > jb.long_len) : 0u;   // ... or this warp sums as a whole, below
+            longs = (!kStaged && jb.vs <= 32) ? __ballot_sync(kFull, !heavy && hi - lo > jb.long_len) : 0u;   // ... or this warp sums as a whole, below
         }
         if (jb.vd > 0) {
             // concat form: the dense part of every cell; add form: a plain copy for the cells that receive nothing
@@ -1365,6 +1553,14 @@ int packed_chunk_knob() { const int v = SHPL_KNOB("SHPL_PACKED_CHUNK", 64); retu
 int stream_ctas_per_sm() { const int v = SHPL_KNOB("SHPL_STREAM_CTAS_PER_SM", 6); return v > 0 ? v : 6; }
 // 0: the CTA-tiled wide kernel; 1: entry + stream kernel up to 64 vectors per cell; 2: always
 int wide_stream_knob() { return SHPL_KNOB("SHPL_WIDE_STREAM", 2); }
+// staged entry walk: 0 = never (packed / plain walks as in round 1), 1 = dense regime + long cells, 2 = whenever eligible
+int staged_knob() { return SHPL_KNOB("SHPL_STAGED", 1); }
+// batches per entry CTA in the dense regime
+// staged = 2 (every entry CTA) up to this many vectors per cell, when entries * density > cells
+int staged_all_vecs_knob() { return SHPL_KNOB("SHPL_STAGED_ALL_VECS", 8); }
+// measured (profiles/r2_staged_ab.txt): 100 k pairs on 560 k cells gain 10 % with every entry CTA staging, 20 k pairs lose 8 %
+int staged_density_knob() { const int v = SHPL_KNOB("SHPL_STAGED_DENSITY", 16); return v > 0 ? v : 16; }
+int staged_batches_knob() { const int v = SHPL_KNOB("SHPL_STAGED_BATCHES", 4); return v > 0 ? v : 4; }
 
 // Sparse regime of the narrow channel counts: every pooled job comes with its key array and the entries are few
 // next to the cells (KITTI stride 1: 20 k entries for 560 k cells).
@@ -1426,16 +1622,48 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
     if (a.n_jobs == 0) return SHPL_OK;
     bool wide = max_vs >= 32;
     bool stream_split = !wide && sparse_regime(a, src_spec);
+    // The staged entry walk (pool_entries_staged): every pooled job has its key array and at most kStageMaxVecs vectors per
+    // cell.  Dense regime (many entries per cell on average): every entry CTA takes it (staged = 2).  Otherwise, when the
+    // caller handles heavy cells (heavy_len > 0: the drop-in layer, the sweep), the staged INSTANTIATION is launched and
+    // an entry CTA takes the staged walk only if its chunk meets a cell of more than 32 entries (staged = 1); callers that
+    // pass heavy_len = 0 (FramePipeline, the custom op: KITTI / MV3D shapes) keep the plain instantiation.
+    int staged = 0;
+    {
+        const int mode = staged_knob();
+        bool keys = true, heavy_all = true;
+        long long nnz = 0, cells = 0;
+        for (int i = 0; i < a.n_jobs; ++i) {
+            const Job& o = a.job[i];
+            if (o.vs > 0) {
+                keys = keys && o.key != nullptr && o.vs <= kStageMaxVecs;
+                heavy_all = heavy_all && o.heavy_len > 0;
+                nnz += src_spec[i]->nnz_max;
+            }
+            cells += o.n_cells;
+        }
+        if (mode > 0 && keys && nnz > 0) {
+            // every entry CTA stages when the cells are narrow (<= 8 vectors: the plain walk leaves 24+ lanes idle per
+            // entry) and the entries many; wider cells only where a long cell is met, and only for callers that say cells
+            // may be long (heavy_len > 0)
+            if (mode > 1 || (max_vs <= staged_all_vecs_knob() && nnz * staged_density_knob() > cells)) staged = 2;
+            else if (heavy_all) staged = 1;
+        }
+        if (staged) {
+            wide = false;
+            stream_split = true;
+        }
+    }
     bool packed = false;
-    if (!wide && !stream_split && packed_knob()) {
-        // dense regime (many entries per cell on average): the entry + stream kernel with the PACKED entry walk, when
-        // every pooled job has its key array and a power-of-two number of vectors per cell <= 16
+    if (staged != 2 && !wide && (staged == 1 ? !sparse_regime(a, src_spec) : !stream_split) && packed_knob()) {
+        // dense regime, the CTAs that do not stage: the entry + stream kernel with the PACKED entry walk, when every
+        // pooled job has its key array and a power-of-two number of vectors per cell <= 16
         bool ok = true;
         for (int i = 0; i < a.n_jobs; ++i) {
             const Job& o = a.job[i];
             if (o.vs > 0 && (o.key == nullptr || o.vs_shift < 0 || o.vs > 16)) ok = false;
         }
-        stream_split = packed = ok;
+        packed = ok;
+        stream_split = stream_split || ok;
     }
     // Wide jobs take the entry + stream kernel too whenever their key arrays are there (measured on B200: full scan
     // C = 128 forward 218 -> 165 us, RetinaNet P2 24.0 -> 20.4 us, the bench step 142 -> 131 us); the CTA-tiled
@@ -1497,12 +1725,34 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
             o.packed = packed ? 1 : 0;
             o.long_len = packed ? 512 : kLongRow;     // the packed walk hands a row over at ~60 cycles per entry: fine up to 512
             if (packed && o.vs > 0) o.entry_chunk = packed_chunk_knob();
+            o.staged = staged;
+            if (staged) o.long_len = o.heavy_len > 0 ? o.heavy_len : 0x7fffffff;   // no cell is left to the stream warps
+            if (staged == 2 && o.vs > 0) {      // CTA chunk = a whole number of batches
+                const int batch = kStageVecs / o.vs < kStageEntries ? kStageVecs / o.vs : kStageEntries;
+                o.entry_chunk = batch * staged_batches_knob() / kWarps;
+                if (o.entry_chunk < 4) o.entry_chunk = 4;
+            }
             o.entry_ctas = o.vs > 0 ? (src_spec[i]->nnz_max + o.entry_chunk * kWarps - 1) / (o.entry_chunk * kWarps) : 0;
             a.begin[i + 1] = a.begin[i] + o.entry_ctas + o.stream_ctas;
         }
         const unsigned g = (unsigned)a.begin[a.n_jobs];
         const bool add = a.job[0].add != 0;
-        if (max_vs > 32) {
+        if (staged) {
+#define SHPL_LAUNCH_STAGED(WW, ACC_)                                                                                   \
+    do {                                                                                                               \
+        using VV = VecOf<WW>::type;                                                                                    \
+        if (add) shpl_pool_sparse_kernel<WW, true, ACC_, true><<<g, kThreads, stage_smem_bytes<VV>(), s>>>(a);         \
+        else shpl_pool_sparse_kernel<WW, false, ACC_, true><<<g, kThreads, stage_smem_bytes<VV>(), s>>>(a);            \
+    } while (0)
+            if (max_vs > 32) {
+                if (w == 4) SHPL_LAUNCH_STAGED(4, 2);
+                else if (w == 2) SHPL_LAUNCH_STAGED(2, 2);
+                else SHPL_LAUNCH_STAGED(1, 2);
+            } else if (w == 4) SHPL_LAUNCH_STAGED(4, 1);
+            else if (w == 2) SHPL_LAUNCH_STAGED(2, 1);
+            else SHPL_LAUNCH_STAGED(1, 1);
+#undef SHPL_LAUNCH_STAGED
+        } else if (max_vs > 32) {
             if (w == 4 && add) shpl_pool_sparse_kernel<4, true, 2><<<g, kThreads, 0, s>>>(a);
             else if (w == 4) shpl_pool_sparse_kernel<4, false, 2><<<g, kThreads, 0, s>>>(a);
             else if (w == 2 && add) shpl_pool_sparse_kernel<2, true, 2><<<g, kThreads, 0, s>>>(a);

@@ -122,6 +122,7 @@ class SparsePoolPlan:
         self._ibase = self._ints.data_ptr()
         self._vbase = self._vals.data_ptr()
         self.n_heavy = None   # (rows, pixels) with more than HEAVY_LEN entries; host ints after read_counts
+        self.n_long = None    # (rows, pixels) with more than SHPL_LONG_LEN entries; host ints after read_counts
         self.entry_bound = self.capacity   # host-known upper bound on the entries (builders tighten it)
         self.nnz = None       # columns of M per frame (host ints), known after the builder's read-back
         self.n_oob = None     # entries TF-CPU would reject, per frame
@@ -179,14 +180,14 @@ class SparsePoolPlan:
         return self.src_per_frame * self.frames
 
     def by_row(self):
-        """(ptr, key, idx, val, nnz_max) of the CSR keyed by destination BEV cell."""
+        """(ptr, key, idx, val, nnz_max, heavy list, heavy_len) of the CSR keyed by destination BEV cell."""
         p = self.ptrs8()
-        return (p[0], p[1], p[2], p[3], self.entry_bound, self.heavy(False))
+        return (p[0], p[1], p[2], p[3], self.entry_bound, self.heavy(False), self.heavy_len(False))
 
     def by_pixel(self):
-        """(ptr, key, idx, val, nnz_max) of the CSR^T keyed by source pixel."""
+        """(ptr, key, idx, val, nnz_max, heavy list, heavy_len) of the CSR^T keyed by source pixel."""
         p = self.ptrs8()
-        return (p[4], p[5], p[6], p[7], self.entry_bound, self.heavy(True))
+        return (p[4], p[5], p[6], p[7], self.entry_bound, self.heavy(True), self.heavy_len(True))
 
     def frame_struct(self, f):
         """shpl_plan for frame f: ptr arrays point at the frame's sub-array; entry arrays are shared."""
@@ -228,7 +229,17 @@ class SparsePoolPlan:
         self.n_oob = c[:, 2].tolist()
         h = (8 * self.frames + 3) // 4 * 4
         self.n_heavy = (min(int(m[h]), self.heavy_cap), min(int(m[h + 1]), self.heavy_cap))
+        self.n_long = (int(c[:, 6].sum()), int(c[:, 7].sum()))
         return c
+
+    def heavy_len(self, by_pixel=None):
+        """The heavy_len argument of the pooling entry points for this plan: SHPL_HEAVY_LEN, or 0 when the counters read
+        back say that no cell of that direction (None: of either direction) has more than SHPL_LONG_LEN entries -- the
+        kernels then skip every long-cell path (and there is no listed cell for shpl_pool_heavy)."""
+        if self.n_long is None:
+            return _cabi.HEAVY_LEN
+        n = self.n_long[0] + self.n_long[1] if by_pixel is None else self.n_long[1 if by_pixel else 0]
+        return _cabi.HEAVY_LEN if n > 0 else 0
 
     def heavy(self, by_pixel):
         """(list pointer, device counter pointer, list capacity, how many to expect or None when the counters have
@@ -308,7 +319,7 @@ def _off(t, n_floats):
 def pool_forward(dst, src, csr, n_rows, n_src):
     """fused[r] = concat(dst[r], sum_k val_k * src[idx_k])  (shpl_pool_forward, then shpl_pool_heavy for
     cells with more than HEAVY_LEN entries).  csr = (ptr, key, idx, val, nnz_max, heavy)."""
-    ptr, key, idx, val, nnz_max, heavy = csr
+    ptr, key, idx, val, nnz_max, heavy, heavy_len = csr
     require_cuda(src, "source feature map")
     C_s = src.shape[-1]
     C_d = 0 if dst is None else dst.shape[-1]
@@ -316,19 +327,19 @@ def pool_forward(dst, src, csr, n_rows, n_src):
 
     def main():
         rc = _lib.shpl_pool_forward(_ptr(dst), _ptr(src), _ptr(ptr), _ptr(key), _ptr(idx), _ptr(val), int(nnz_max),
-                                    _cabi.HEAVY_LEN, n_rows, C_d, n_src, C_s, _ptr(fused), _stream())
+                                    heavy_len, n_rows, C_d, n_src, C_s, _ptr(fused), _stream())
         _cabi.check(rc, "shpl_pool_forward")
     _launch_with_heavy(src.device, main, [(heavy, _ptr(src), C_s, C_s, ptr, idx, val, None, 0, _off(fused, C_d), C_d + C_s)])
     return fused
 
 
 def pool_backward(g_fused, csrT, n_rows, C_d, n_src, C_s, want_dst=True):
-    ptrT, keyT, idxT, valT, nnz_max, heavy = csrT
+    ptrT, keyT, idxT, valT, nnz_max, heavy, heavy_len = csrT
     g_dst = torch.empty((n_rows, C_d), dtype=torch.float32, device=g_fused.device) if (want_dst and C_d) else None
     g_src = torch.empty((n_src, C_s), dtype=torch.float32, device=g_fused.device)
     def main():
         rc = _lib.shpl_pool_backward(_ptr(g_fused), _ptr(ptrT), _ptr(keyT), _ptr(idxT), _ptr(valT), int(nnz_max),
-                                     _cabi.HEAVY_LEN, n_rows, C_d, n_src, C_s, _ptr(g_dst), _ptr(g_src), _stream())
+                                     heavy_len, n_rows, C_d, n_src, C_s, _ptr(g_dst), _ptr(g_src), _stream())
         _cabi.check(rc, "shpl_pool_backward")
     _launch_with_heavy(g_fused.device, main, [(heavy, _off(g_fused, C_d), C_d + C_s, C_s, ptrT, idxT, valT, None, 0, _ptr(g_src), C_s)])
     return g_dst, g_src
@@ -337,10 +348,10 @@ def pool_backward(g_fused, csrT, n_rows, C_d, n_src, C_s, want_dst=True):
 def pool_forward_into(fused, src, csr, n_rows, n_src, chan_off):
     """No-concat forward (shpl_pool_forward_into): fused [n_rows, F] gets its channels chan_off : chan_off + C_s
     overwritten with the pooled sums (zeros for cells that receive nothing); the other channels are left alone."""
-    ptr, key, idx, val, nnz_max, heavy = csr
+    ptr, key, idx, val, nnz_max, heavy, heavy_len = csr
     C_s, F = src.shape[-1], fused.shape[-1]
     def main():
-        rc = _lib.shpl_pool_forward_into(_ptr(src), _ptr(ptr), _ptr(key), _ptr(idx), _ptr(val), int(nnz_max), _cabi.HEAVY_LEN,
+        rc = _lib.shpl_pool_forward_into(_ptr(src), _ptr(ptr), _ptr(key), _ptr(idx), _ptr(val), int(nnz_max), heavy_len,
                                          n_rows, n_src, C_s, _ptr(fused), F, int(chan_off), _stream())
         _cabi.check(rc, "shpl_pool_forward_into")
     _launch_with_heavy(src.device, main, [(heavy, _ptr(src), C_s, C_s, ptr, idx, val, None, 0, _off(fused, chan_off), F)])
@@ -350,12 +361,12 @@ def pool_forward_into(fused, src, csr, n_rows, n_src, chan_off):
 def pool_backward_from(g_fused, csrT, n_rows, n_src, C_s, chan_off):
     """No-concat backward (shpl_pool_backward_from): the gradient of the gathered map from the pooled channels of
     g_fused, read in place; the gradient of the destination map is the view g_fused[:, :chan_off]."""
-    ptrT, keyT, idxT, valT, nnz_max, heavy = csrT
+    ptrT, keyT, idxT, valT, nnz_max, heavy, heavy_len = csrT
     F = g_fused.shape[-1]
     g_src = torch.empty((n_src, C_s), dtype=torch.float32, device=g_fused.device)
     def main():
         rc = _lib.shpl_pool_backward_from(_ptr(g_fused), F, int(chan_off), _ptr(ptrT), _ptr(keyT), _ptr(idxT), _ptr(valT),
-                                          int(nnz_max), _cabi.HEAVY_LEN, n_rows, n_src, C_s, _ptr(g_src), _stream())
+                                          int(nnz_max), heavy_len, n_rows, n_src, C_s, _ptr(g_src), _stream())
         _cabi.check(rc, "shpl_pool_backward_from")
     _launch_with_heavy(g_fused.device, main, [(heavy, _off(g_fused, chan_off), F, C_s, ptrT, idxT, valT, None, 0, _ptr(g_src), C_s)])
     return g_src
@@ -486,7 +497,7 @@ class SparsePoolDualFunction(torch.autograd.Function):
         fused_img = torch.empty(tuple(img.shape[:3]) + (Ci + Cb,), dtype=torch.float32, device=bev.device)
         P8 = plan.ptrs8()
         def main():
-            rc = _lib.shpl_pool_forward_dual(_ptr(b), _ptr(i), *P8, int(plan.entry_bound), _cabi.HEAVY_LEN,
+            rc = _lib.shpl_pool_forward_dual(_ptr(b), _ptr(i), *P8, int(plan.entry_bound), plan.heavy_len(),
                                              R, Cb, Q, Ci, _ptr(fused_bev), _ptr(fused_img), _stream())
             _cabi.check(rc, "shpl_pool_forward_dual")
         _launch_with_heavy(bev.device, main,
@@ -506,7 +517,7 @@ class SparsePoolDualFunction(torch.autograd.Function):
         g_bev = torch.empty(sb, dtype=torch.float32, device=gb.device)
         g_img = torch.empty(si, dtype=torch.float32, device=gb.device)
         P8 = plan.ptrs8()
-        rc = _lib.shpl_pool_backward_dual(_ptr(gb), _ptr(gi), *P8, int(plan.entry_bound), _cabi.HEAVY_LEN,
+        rc = _lib.shpl_pool_backward_dual(_ptr(gb), _ptr(gi), *P8, int(plan.entry_bound), plan.heavy_len(),
                                           R, Cb, Q, Ci, _ptr(g_bev), _ptr(g_img), _stream())
         _cabi.check(rc, "shpl_pool_backward_dual")
         # g_bev[r] = g_fused_bev[r,:Cb] + sum_{k in row r} val * g_fused_img[pix_k, Ci:]   (heavy rows)

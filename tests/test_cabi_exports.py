@@ -48,7 +48,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_binding_covers_the_header(lib):
     from sparse_pooling_b200 import _cabi
     assert sorted(_cabi.SIGNATURES) == declared_functions()
-    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 9
+    assert _cabi.lib.shpl_abi_version() == _cabi.ABI_VERSION == 10
 
 
 def test_workspace_query_grows_with_n(lib):
@@ -207,7 +207,7 @@ def test_header_is_plain_c_and_links_from_c(tmp_path, lib):
     subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, str(src), "-o", str(exe),
                     "-L", libdir, "-lshpl", "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
-    assert out[0] == out[1] == "9" and out[2] == "512"
+    assert out[0] == out[1] == "10" and out[2] == "512"
     from sparse_pooling_b200 import _cabi
     assert int(out[3]) == ctypes.sizeof(_cabi.ShplPlan)                   # the ctypes mirror of struct shpl_plan has its layout
     cxx = tmp_path / "abi.cpp"

@@ -519,6 +519,55 @@ def test_long_rows_are_summed_by_the_whole_warp_in_k_order(shpl, C, n, bev_hw):
     np.testing.assert_array_equal(tb2.grad[0].cpu().numpy(), gd)
 
 
+@pytest.mark.parametrize("C,max_len,bev_hw", [(4, 700, (12, 12)), (16, 500, (12, 12)), (20, 300, (12, 12)), (64, 400, (12, 12)),
+                                              (128, 300, (12, 12)), (200, 150, (10, 10)), (256, 200, (10, 10)), (6, 700, (12, 12)),
+                                              (3, 900, (12, 12)), (32, 1500, (12, 12)),
+                                              # few entries per cell on average: only the entry CTAs that meet a long cell stage it
+                                              (32, 400, (200, 180)), (8, 120, (200, 180)), (128, 90, (150, 160))])
+def test_staged_entry_walk_is_bit_exact(shpl, C, max_len, bev_hw):
+    """Cells of 1 ... max_len entries side by side (runs that cross the batches and the CTA chunks of the staged entry walk,
+    pool_entries_staged), pixels likewise for the transposed direction, every vector layout (float4 / float2 / scalar,
+    power-of-two and odd vector counts, one and two vectors per lane), dual = the add form: forward and backward of both
+    directions bit-identical to the sequential oracle.  Cells above 512 entries take the exact cluster kernel."""
+    rng = np.random.default_rng(C * 7919 + max_len)
+    n_long = 40
+    lens = rng.integers(1, max_len + 1, n_long)
+    cells = rng.choice(bev_hw[0] * bev_hw[1], n_long, replace=False)
+    rows = np.concatenate([np.full(int(l), c) for l, c in zip(lens, cells)] + [rng.integers(0, bev_hw[0] * bev_hw[1], 600)])
+    n = len(rows)
+    u, v = rng.integers(0, 64, n), rng.integers(0, 32, n)
+    k_pix = min(n // 2, max_len)
+    u[:k_pix], v[:k_pix] = 11, 5                                  # one long pixel for the transposed direction
+    perm = rng.permutation(n)
+    rows, u, v = rows[perm], u[perm], v[perm]
+    d = dict(bv_index=np.stack((rows % bev_hw[1], bev_hw[0] - 1 - rows // bev_hw[1]), axis=1).astype(np.int64),
+             img_index=np.stack((u, v, np.zeros(n))).astype(np.float64), bv_size=np.array(bev_hw), img_size=np.array([64, 32]))
+    val = (1.0 / rng.integers(1, 46, n)).astype(np.float32)
+    bev = rng.standard_normal((1,) + tuple(bev_hw) + (C,), dtype=np.float32)
+    img = rng.standard_normal((1, 32, 64, C), dtype=np.float32)
+    o = shpl.produce_sparse_pooling_input(d)
+    Mij, flip = o["Mij_pool"], o["img_index_flip_pool"]
+    assert len(Mij) == n and np.bincount(Mij[:, 0]).max() >= lens.max()
+    M = shpl.SparseTensor(torch.from_numpy(Mij).cuda(), torch.from_numpy(val).cuda(), o["M_size"])
+    tb, ti = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
+    bv_fused, img_fused = shpl.sparse_pool_layer([tb, ti], [C, C], M, img_index_flip=torch.from_numpy(flip).cuda(), bv_index=np.zeros((1, 3)))
+    np.testing.assert_array_equal(bv_fused[0].detach().cpu().numpy(), cref.forward(bev[0], img[0], Mij, val, flip))
+    np.testing.assert_array_equal(img_fused[0].detach().cpu().numpy(), cref.forward_trans(img[0], bev[0], Mij, val, flip))
+    g1 = rng.standard_normal(tuple(bev_hw) + (2 * C,), dtype=np.float32)
+    g2 = rng.standard_normal((32, 64, 2 * C), dtype=np.float32)
+    torch.autograd.backward([bv_fused, img_fused], [torch.from_numpy(g1[None]).cuda(), torch.from_numpy(g2[None]).cuda()])
+    gd, gs = cref.backward(g1, Mij, val, flip, C, (32, 64, C))
+    gi, gb = cref.backward_trans(g2, Mij, val, flip, C, tuple(bev_hw) + (C,))
+    np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd + gb)
+    np.testing.assert_array_equal(ti.grad[0].cpu().numpy(), gi + gs)
+    tb2, ti2 = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
+    only, _ = shpl.sparse_pool_layer([tb2, ti2], [C, C], M, img_index_flip=torch.from_numpy(flip).cuda())
+    np.testing.assert_array_equal(only[0].detach().cpu().numpy(), cref.forward(bev[0], img[0], Mij, val, flip))
+    only.backward(torch.from_numpy(g1[None]).cuda())
+    np.testing.assert_array_equal(ti2.grad[0].cpu().numpy(), gs)
+    np.testing.assert_array_equal(tb2.grad[0].cpu().numpy(), gd)
+
+
 @pytest.mark.parametrize("dual", [False, True])
 def test_heavy_cells_use_the_cluster_tree(shpl, dual):
     """Stress (BASELINE config 5, Zipf-like skew): one BEV cell with 30k entries and one pixel with 5k.
