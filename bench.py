@@ -809,6 +809,19 @@ def run_gpu_avod(args, name, cfg):
                 torch.cuda.synchronize()
                 return e0_.elapsed_time(e1_) * 1e3 / (4 * n_)
             us_fused, us_dense = time_conv(True), time_conv(False)
+            # backward of the fused conv (g_bev on the tensor cores, g_img through the transposed CSR, g_weight)
+            g_outs_c = [randn(1, *sB.bev_hw, 32) for _ in range(n_sets)]
+            grads_c = (torch.empty(1, *sB.bev_hw, 32, device=dev), torch.empty(1, *sB.img_hw, 32, device=dev), torch.empty_like(wt))
+            need_b_ = int(shpl._cabi.lib.shpl_conv3x3_backward_workspace_bytes(int(N_MAX)))
+            ws_b = torch.empty(need_b_ + 256, dtype=torch.uint8, device=dev)
+            _fwd_call = conv_call
+
+            def conv_call(k, pooled_=True):                   # noqa: F811  (time_conv times whatever conv_call is)
+                si_ = k % n_sets
+                mp_ = maps[si_][dom]
+                conv_fusion.sparse_pool_conv3x3_backward(g_outs_c[si_], [mp_["bev"], mp_["img"]], plans_c[si_], wt, out=grads_c, workspace=ws_b)
+            us_bwd = time_conv(True)
+            conv_call = _fwd_call
             # spot check of the fused result against the concat form + a float64 conv on a crop of the map
             conv_call(0, True)
             fused_ref = pipes[0].layers[dom].fused_bev
@@ -832,7 +845,7 @@ def run_gpu_avod(args, name, cfg):
             io_bytes = 4.0 * R_ * (32 + 32) + 4.0 * nnz[dom] * 34
             conv = {"what": "shpl_pool_conv3x3_forward on layer %s: relu(conv3x3(concat(bev, pooled(img)), W[3,3,64,32])) with the fused map never "
                             "written; CUDA-graph replays, CUDA events; includes the weight prep, the busy-cell bitmap and the Z kernel" % sB.name,
-                    "us_per_call": us_fused, "us_dense_half_only": us_dense,
+                    "us_per_call": us_fused, "us_dense_half_only": us_dense, "us_backward_call": us_bwd,
                     "max_err_over_sum_abs_terms_on_a_64x128_crop": rel_c,
                     "roofline": {"bound": "tensor", "unit": "TFLOP/s",
                                  "achieved": flops_tc / us_dense / 1e6, "peak": tf32_peak, "frac": flops_tc / us_dense / 1e6 / tf32_peak,

@@ -196,7 +196,13 @@ int shpl_plan_from_voxel_coords(const void* coordinate, int32_t index_is_i64, in
  * heavy_len > 0: cells with more than heavy_len entries are NOT summed here and their pooled part (in the
  * add forms: their whole output) is left UNWRITTEN; the caller runs shpl_pool_heavy / shpl_pool_heavy_split on
  * the listed cells -- after this call, or concurrently on another stream (the two write disjoint cells).
- * heavy_len = 0: every cell is summed here, strictly sequentially. */
+ * Pass SHPL_HEAVY_LEN for a plan with listed cells.  (For C_s <= 128 the kernels keep listed cells of up to
+ * SHPL_EXACT_LEN entries themselves -- summed in entry order through shared memory -- and the heavy entry points skip
+ * exactly those: the rule depends on C_s alone, so the two sides always agree.)  A value above SHPL_HEAVY_LEN (e.g.
+ * SHPL_EXACT_LEN) says: some cells have more than SHPL_LONG_LEN entries but none is listed -- nothing is left out, the
+ * long-cell paths stay on.
+ * heavy_len = 0: every cell is summed here, strictly sequentially, and the kernels skip their long-cell paths: right
+ * for plans whose counts[6] / counts[7] read 0 (every KITTI / MV3D plan). */
 int shpl_pool_forward(const float* dst, const float* src,
                       const int32_t* ptr, const int32_t* key, const int32_t* idx, const float* val,
                       int32_t nnz_max, int32_t heavy_len, int32_t n_rows, int32_t C_d, int32_t n_src, int32_t C_s,
@@ -237,9 +243,10 @@ int shpl_pool_backward_dual(const float* g_fused_bev, const float* g_fused_img,
                             float* g_bev, float* g_img, void* stream);
 
 /* shpl_pool_heavy with the LONG listed cells (more than SHPL_EXACT_LEN entries) split over many CTAs instead of one
- * cluster per cell: a cell of L entries is cut into ceil(L / 1024) contiguous pieces, a CTA sums one piece in stored
- * order into the workspace, and a second kernel adds a cell's partial sums in order -- a fixed tree that depends only on
- * L (deterministic, within 1e-5 of the sum of |terms|; not bit-identical to the sequential sum).  The Zipf stress case's
+ * cluster per cell: a cell of L entries is cut into ceil(L / 256) contiguous pieces, a CTA sums one piece in stored
+ * order into the workspace, and a second kernel adds a cell's partial sums as a two-level tree (32 groups in order side by
+ * side, then the group sums in order) -- a fixed tree that depends only on L (deterministic, within 1e-5 of the sum of
+ * |terms|; not bit-identical to the sequential sum).  The Zipf stress case's
  * 178 000-entry cell runs on ~90 SMs instead of 8.  Cells up to SHPL_EXACT_LEN entries take the exact cluster kernel as
  * in shpl_pool_heavy.  nnz_max >= total entries of the plan; workspace: shpl_pool_heavy_workspace_bytes(C, nnz_max,
  * list_cap) bytes, 16-byte aligned.  (More than 4096 listed cells: falls back to shpl_pool_heavy's cluster tree.) */

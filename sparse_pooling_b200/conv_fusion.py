@@ -79,27 +79,36 @@ class SparsePoolConv3x3Function(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_out):
-        import ctypes
         bev, img, weight = ctx.saved_tensors
-        plan = ctx.plan
-        B, H, W, Cb = bev.shape
-        Ci = img.shape[3]
-        g = g_out.contiguous()
         need_b, need_i, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
-        g_bev = torch.empty_like(bev) if need_b else None
-        g_img = torch.empty_like(img) if need_i else None
-        g_w = torch.empty_like(weight) if need_w else None
-        ptr, key, idx, val, nnz_max, _, _ = plan.by_row()
-        ptrT, keyT, idxT, valT, _, _, _ = plan.by_pixel()
-        need = int(_lib.shpl_conv3x3_backward_workspace_bytes(int(nnz_max)))
-        ws = ops.scratch("conv_bwd", bev.device, need + 256)
-        off = (-ws.data_ptr()) % 256
-        rc = _lib.shpl_pool_conv3x3_backward(_ptr(g), _ptr(bev.contiguous()), _ptr(img.contiguous()), _ptr(ptr), _ptr(key), _ptr(idx),
-                                             _ptr(val), _ptr(ptrT), _ptr(keyT), _ptr(idxT), _ptr(valT), int(nnz_max), B, H, W, Cb,
-                                             int(plan.n_src), Ci, _ptr(weight.contiguous()), weight.shape[3], _ptr(g_bev), _ptr(g_img),
-                                             _ptr(g_w), ctypes.c_void_p(ws.data_ptr() + off), ws.numel() - off, _stream())
-        _cabi.check(rc, "shpl_pool_conv3x3_backward")
+        g_bev, g_img, g_w = sparse_pool_conv3x3_backward(g_out, [bev, img], ctx.plan, weight, need_b, need_i, need_w)
         return g_bev, g_img, g_w, None
+
+
+def sparse_pool_conv3x3_backward(g_out, inputs, plan, weight, need_bev=True, need_img=True, need_weight=True, out=None,
+                                 workspace=None):
+    """Gradients of conv3x3(concat(bev, pooled(img)), weight) with respect to bev, img and weight
+    (shpl_pool_conv3x3_backward); `out` = preallocated (g_bev, g_img, g_weight) or None."""
+    import ctypes
+    bev, img = inputs[0], inputs[1]
+    B, H, W, Cb = bev.shape
+    Ci = img.shape[3]
+    g = g_out.contiguous()
+    g_bev = (out[0] if out is not None else torch.empty_like(bev)) if need_bev else None
+    g_img = (out[1] if out is not None else torch.empty_like(img)) if need_img else None
+    g_w = (out[2] if out is not None else torch.empty_like(weight)) if need_weight else None
+    ptr, key, idx, val, nnz_max, _, _ = plan.by_row()
+    ptrT, keyT, idxT, valT, _, _, _ = plan.by_pixel()
+    if workspace is None:
+        need = int(_lib.shpl_conv3x3_backward_workspace_bytes(int(nnz_max)))
+        workspace = ops.scratch("conv_bwd", bev.device, need + 256)
+    off = (-workspace.data_ptr()) % 256
+    rc = _lib.shpl_pool_conv3x3_backward(_ptr(g), _ptr(bev.contiguous()), _ptr(img.contiguous()), _ptr(ptr), _ptr(key), _ptr(idx),
+                                         _ptr(val), _ptr(ptrT), _ptr(keyT), _ptr(idxT), _ptr(valT), int(nnz_max), B, H, W, Cb,
+                                         int(plan.n_src), Ci, _ptr(weight.contiguous()), weight.shape[3], _ptr(g_bev), _ptr(g_img),
+                                         _ptr(g_w), ctypes.c_void_p(workspace.data_ptr() + off), workspace.numel() - off, _stream())
+    _cabi.check(rc, "shpl_pool_conv3x3_backward")
+    return g_bev, g_img, g_w
 
 
 def sparse_pool_conv3x3_autograd(inputs, M, img_index_flip, weight):

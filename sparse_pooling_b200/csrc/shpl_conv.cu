@@ -50,8 +50,7 @@ static_assert(kOutBytes % 1024 == 0, "output staging buffers stay 1024-byte alig
 constexpr int kWorkers = 256;
 constexpr int kSparseWarps = 4;                      // warps 10..13: the pooled half's contributions, one tile ahead
 constexpr int kSparseRows = kOutRows / kSparseWarps; // 28 output pixels per sparse warp
-constexpr int kSparseCand = kSparseRows * 9;         // (pixel, tap) candidates per sparse warp: 252 = 8 rounds of 32 lanes
-constexpr int kSparseRounds = (kSparseCand + 31) / 32;
+static_assert(kSparseRows == 2 * kTileX && kHaloX == 16 && kHaloY == 2 * kSparseWarps + 2, "a sparse warp: two output rows, four halo rows of 16 cells = two cells per lane");
 constexpr int kConvThreads = kWorkers + 64 + kSparseWarps * 32;
 constexpr int kAccCols = kNB;                        // columns of one accumulator buffer
 constexpr int kTmemCols = 512;                       // 2 x 192 used
@@ -175,7 +174,6 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out, ConvArgs a) {
     extern __shared__ uint8_t conv_smem_raw[];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ uint32_t halo_bits[2][kHaloY];    // busy bits of a tile's halo rows (sparse warps; double-buffered)
     const uint32_t raw = smem_u32(conv_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* gbase = conv_smem_raw + (base - raw);
@@ -296,25 +294,28 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
         }
     } else if (warp >= 10) {
         // ===== sparse warps (10..13): the pooled half of the conv, one tile ahead of the epilogue =====
-        // For every output pixel of the tile: the sum, in (pixel, tap) order (a fixed order: deterministic), of the Z rows of
-        // its busy neighbours -- Z[cell][tap] = W_pooled[tap]^T . pooled[cell], from the Z kernel -- left in the tile's
-        // output staging buffer, where the epilogue adds the dense half on top.  A warp owns 28 pixels; lane = output
-        // channel, so a Z row is one coalesced 128-byte load.  No global latency is exposed per tile but the Z loads:
-        //   tile i+2: ten threads load the busy-bitmap words of the halo rows
-        //   tile i+1: the words go to shared memory, every lane tests its (pixel, tap) candidates and issues the CSR-offset
-        //             loads of the busy ones
+        // For every output pixel of the tile: the sum, in a fixed order (deterministic), of the Z rows of its busy neighbours
+        // -- Z[cell][tap] = W_pooled[tap]^T . pooled[cell], from the Z kernel -- left in the tile's output staging buffer,
+        // where the epilogue adds the dense half on top.  A warp owns output rows 2 sw, 2 sw + 1 of the tile (28 pixels) and
+        // works on its own, no barrier between the four: it looks at the four halo rows that reach its pixels (a lane holds
+        // two halo cells: row 2 sw + (lane >> 3), columns 2 (lane & 7) and + 1), and for every busy one adds the cell's nine
+        // Z rows -- 1152 contiguous bytes = 72 float4: lane -> (tap, channel quad), three 128-bit loads -- to the pixels the
+        // taps land on.  No global latency is exposed per tile but the Z loads, and those hit L1:
+        //   tile i+2: one lane per halo row loads the row's busy-bitmap words
+        //   tile i+1: bits -> the CSR-offset loads of the busy cells (two predicated loads per lane); prefetch of their Z rows
         //   tile i  : offsets -> Z rows -> read-modify-write of the staging rows
         if (a.busy != nullptr && n_mine > 0) {
-            const int sw = warp - 10, stid = tid - 320;
+            const int sw = warp - 10;
             const int e_begin = __ldg(a.ptr);
+            const int hyl = lane >> 3, hxa = (lane & 7) * 2;
             uint32_t hw_lo = 0u, hw_hi = 0u;
             int hw_sh = 0, hw_nv = 0, hw_ls = 0;
-            auto issue_halo = [&](int j) {                               // stid < 10: raw bitmap words of halo row `stid` of tile j
+            auto issue_halo = [&](int j) {                               // lanes 0, 8, 16, 24: raw bitmap words of halo row 2 sw + hyl of tile j
                 hw_nv = 0;
-                if (j >= n_mine || stid >= kHaloY) return;
+                if (j >= n_mine || (lane & 7) != 0) return;
                 int f, y0, x0;
                 tile_coord(j, f, y0, x0);
-                const int yy = y0 - 1 + stid;
+                const int yy = y0 - 1 + 2 * sw + hyl;
                 if (yy < 0 || yy >= a.H) return;
                 const int xs = x0 > 0 ? x0 - 1 : 0;                      // first in-image halo column
                 const long long c = ((long long)f * a.H + yy) * a.W + xs;
@@ -326,48 +327,47 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
                 hw_ls = xs - (x0 - 1);
                 hw_nv = min(a.W - xs, kHaloX - hw_ls);                   // columns of this row inside the image
             };
-            auto publish_halo = [&](int j) {                             // the loaded words -> halo_bits[j & 1]
-                if (stid < kHaloY) {
-                    uint32_t bits = 0u;
-                    if (hw_nv > 0) {
-                        bits = (uint32_t)(((((uint64_t)hw_hi) << 32) | hw_lo) >> hw_sh) & 0xffffu;
-                        bits &= (1u << hw_nv) - 1u;
-                        bits <<= hw_ls;
-                    }
-                    halo_bits[j & 1][stid] = bits;
+            auto issue_offsets = [&](int j, int& pa, int& pb) {          // -1: the cell is not busy
+                uint32_t bits = 0u;
+                if (hw_nv > 0) {
+                    bits = (uint32_t)(((((uint64_t)hw_hi) << 32) | hw_lo) >> hw_sh) & 0xffffu;
+                    bits &= (1u << hw_nv) - 1u;
+                    bits <<= hw_ls;
                 }
-                asm volatile("bar.sync 2, 128;" ::: "memory");
-            };
-            int poff[kSparseRounds], poff_n[kSparseRounds];              // CSR offsets of this lane's busy candidates (-1: none)
-            auto issue_offsets = [&](int j, int (&po)[kSparseRounds]) {  // needs halo_bits[j & 1]
+                bits = __shfl_sync(0xffffffffu, bits, lane & 24) >> hxa;  // the row's 16 bits, from the lane that loaded them
                 int f, y0, x0;
                 tile_coord(j, f, y0, x0);
+                const int nb = (f * a.H + y0 + 2 * sw + hyl - 1) * a.W + x0 + hxa - 1;
+                SHPL_DASSERT(!(bits & 3u) || (nb + 1 >= 0 && nb < a.frames * a.H * a.W));
+                pa = (bits & 1u) ? __ldg(a.ptr + nb) : -1;
+                pb = (bits & 2u) ? __ldg(a.ptr + nb + 1) : -1;
+            };
+            // the nine Z rows of a busy cell: nine lines, prefetched into L1 a tile ahead
+            auto prefetch_rows = [&](int pa, int pb) {
 #pragma unroll
-                for (int rd = 0; rd < kSparseRounds; ++rd) {
-                    const int c = rd * 32 + lane;
-                    po[rd] = -1;
-                    if (c < kSparseCand) {
-                        const int pl = c / 9, t = c - pl * 9;
-                        const int r = sw * kSparseRows + pl, yl = r / kTileX, xl = r - yl * kTileX;
-                        const int hy = yl + t / 3, hx = xl + t % 3;
-                        const bool on = ((halo_bits[j & 1][hy] >> hx) & 1u) && y0 + yl < a.H && x0 + xl < a.W;
-                        if (on) {
-                            const int nb = (f * a.H + y0 + hy - 1) * a.W + x0 + hx - 1;
-                            SHPL_DASSERT(nb >= 0 && nb < a.frames * a.H * a.W);
-                            po[rd] = __ldg(a.ptr + nb);
-                        }
-                    }
+                for (int t = 0; t < 9; ++t) {
+                    if (pa >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.Z + ((size_t)(pa - e_begin) * 9 + t) * 32));
+                    if (pb >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.Z + ((size_t)(pb - e_begin) * 9 + t) * 32));
                 }
             };
+            // lane -> float4 f = lane + 32 p (p = 0, 1, 2; f < 72) of a cell's Z block: tap f >> 3, channel quad f & 7
+            int t_dy[3], t_dx[3];
+#pragma unroll
+            for (int p2 = 0; p2 < 3; ++p2) {
+                const int t = (lane + 32 * p2) >> 3;
+                t_dy[p2] = t < 9 ? t / 3 : 100;                          // 100: no such tap (never lands on a pixel)
+                t_dx[p2] = t % 3;
+            }
+            const int cq = lane & 7;
+            int pa = -1, pb = -1, pa_n = -1, pb_n = -1;
             issue_halo(0);
-            publish_halo(0);
-            issue_offsets(0, poff);
+            issue_offsets(0, pa, pb);
             issue_halo(1);
+            prefetch_rows(pa, pb);
             for (int i = 0; i < n_mine; ++i) {
                 const int ob = i & 1, u = i >> 1;
                 if (i + 1 < n_mine) {
-                    publish_halo(i + 1);
-                    issue_offsets(i + 1, poff_n);
+                    issue_offsets(i + 1, pa_n, pb_n);
                     issue_halo(i + 2);
                 }
                 mbar_wait(bar(BAR_OUT_EMPTY + ob), (u & 1) ^ 1);         // the store of tile i-2 has read this buffer
@@ -378,38 +378,48 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
                     for (int k = 0; k < kSparseRows * 8 / 32; ++k) z[k * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 __syncwarp();
+                // busy cells in (halo row, column) order; tap t of a cell at halo (hy, hx) lands on output pixel (hy - t / 3, hx - t % 3)
+                const uint32_t ma = __ballot_sync(0xffffffffu, pa >= 0), mb = __ballot_sync(0xffffffffu, pb >= 0);
+                uint32_t any = ma | mb;
+                while (any) {
+                    const int l = __ffs(any) - 1;
+                    any &= any - 1;
+                    const int h = l >> 3;                                // halo row 2 sw + h
 #pragma unroll
-                for (int rd = 0; rd < kSparseRounds; ++rd) {
-                    uint32_t m = __ballot_sync(0xffffffffu, poff[rd] >= 0);
-                    while (m) {                                          // up to four Z rows in flight
-                        int rr[4];
-                        float zv[4];
+                    for (int half = 0; half < 2; ++half) {
+                        if (!(((half ? mb : ma) >> l) & 1u)) continue;
+                        const int zr0 = (__shfl_sync(0xffffffffu, half ? pb : pa, l) - e_begin) * 9;
+                        SHPL_DASSERT(zr0 >= 0 && zr0 / 9 < a.z_rows);
+                        const int hx = (l & 7) * 2 + half;
+                        const float4* zb = reinterpret_cast<const float4*>(a.Z + (size_t)zr0 * 32) + lane;
+                        float4 zv[3];
+                        int off[3];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            rr[k] = -1;
-                            if (m) {
-                                const int bsel = __ffs(m) - 1;
-                                m &= m - 1;
-                                const int c = rd * 32 + bsel;
-                                const int pl = c / 9, t = c - pl * 9;
-                                const int zr = (__shfl_sync(0xffffffffu, poff[rd], bsel) - e_begin) * 9 + t;
-                                SHPL_DASSERT(zr >= 0 && zr / 9 < a.z_rows);
-                                zv[k] = __ldg(a.Z + (size_t)zr * 32 + lane);
-                                rr[k] = sw * kSparseRows + pl;
+                        for (int p2 = 0; p2 < 3; ++p2) {
+                            const int yo = h - t_dy[p2], xl = hx - t_dx[p2];   // output row inside the warp's pair, output column
+                            off[p2] = -1;
+                            if (yo >= 0 && yo < 2 && xl >= 0 && xl < kTileX) {
+                                const int r = (2 * sw + yo) * kTileX + xl;
+                                off[p2] = r * 128 + ((cq ^ (r & 7)) << 4);
+                                zv[p2] = __ldg(zb + 32 * p2);
                             }
                         }
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (rr[k] >= 0) {
-                                float* cell = reinterpret_cast<float*>(obase + rr[k] * 128 + ((((lane >> 2) ^ (rr[k] & 7))) << 4)) + (lane & 3);
-                                *cell += zv[k];
+                        for (int p2 = 0; p2 < 3; ++p2)
+                            if (off[p2] >= 0) {
+                                float4* cell = reinterpret_cast<float4*>(obase + off[p2]);
+                                float4 c4 = *cell;
+                                c4.x += zv[p2].x; c4.y += zv[p2].y; c4.z += zv[p2].z; c4.w += zv[p2].w;
+                                *cell = c4;
                             }
+                        __syncwarp();                                    // the next cell may touch the same pixels from other lanes
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(BAR_CONTRIB_FULL + ob));
-#pragma unroll
-                for (int rd = 0; rd < kSparseRounds; ++rd) poff[rd] = poff_n[rd];
+                pa = pa_n;
+                pb = pb_n;
+                if (i + 1 < n_mine) prefetch_rows(pa, pb);               // the next tile's rows: in L1 by the time they are read
             }
         }
     } else {
@@ -448,6 +458,12 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar(BAR_ACC_EMPTY + s));
+            if (tid == 0 && i > 0) {
+                // the store of tile i-1 (committed at the end of the last iteration) has read its staging buffer by now: free
+                // for tile i+1, which the sparse warps fill during the rest of this tile
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(bar(BAR_OUT_EMPTY + (s ^ 1)));
+            }
             // the staging buffer of this tile: filled with the pooled half by the sparse warps, or just free again
             mbar_wait(bar((pooled ? BAR_CONTRIB_FULL : BAR_OUT_EMPTY) + s), pooled ? (u & 1) : ((u & 1) ^ 1));
             uint8_t* orow = gbase + kSmOut + s * kOutBytes + (yl * kTileX + xq - 1) * 128;
@@ -475,10 +491,6 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
             if (tid == 0) {
                 tma_store_4d(&map_out, base + kSmOut + s * kOutBytes, 0, x0, y0, f);
                 bulk_commit();
-                if (i > 0) {       // the store of tile i-1 has read its buffer: free for tile i+1
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    mbar_arrive(bar(BAR_OUT_EMPTY + (s ^ 1)));
-                }
             }
         }
         if (tid == 0) bulk_wait0();
@@ -494,10 +506,15 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
 // ------------------------------------------------------------------------------------ weight prep
 // W is the slim.conv2d variable, HWIO [3][3][c_in_total][c_out_total].  forward: B[n = co][k = ci] = W[tap][ci_off + ci][co];
 // transposed (input gradient, SAME padding, stride 1): B[n = ci][k = co] = W[8 - tap][ci_off + ci][co].
+// gridDim.y = 2 preps a second block of 32 input channels (ci_off2 -> wprep2) in the same launch.
 __global__ void shpl_conv_prep_kernel(const float* __restrict__ w, int c_in_total, int c_out_total, int ci_off, int transposed,
-                                      float* __restrict__ wprep) {
+                                      float* __restrict__ wprep, int ci_off2 = 0, float* __restrict__ wprep2 = nullptr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;     // over [3 dy][8 chunks][192][4]
     if (i >= kWElems) return;
+    if (blockIdx.y == 1) {
+        ci_off = ci_off2;
+        wprep = wprep2;
+    }
     const int e = i & 3, n = (i >> 2) % kNB, ck = (i / (kNB * 4)) % kChunks, dy = i / (kNB * 4 * kChunks);
     const int part = n / 96, dx = (n % 96) / 32, nn = n & 31;
     const int k = ck * 4 + e, tap = dy * 3 + dx;
@@ -535,6 +552,7 @@ struct ZArgs {
     int c_in_total, c_out_total, ci_off, C_s;
     int n_rows, nnz_max;
     float* Z;                    // [nnz_max][9][32]
+    uint32_t* busy;              // tensor-core form: the bitmap of the cells that receive pooled features is set here too
 };
 
 // Tensor-core form (C_s = 32): a CTA takes 128 consecutive entries; row m of the MMA is entry e0 + m, holding the
@@ -594,7 +612,10 @@ __global__ void __launch_bounds__(kZtcThreads, 2) shpl_conv_z_tc_kernel(ZArgs a)
                 idx_l = __ldg(a.idx + k_l);
                 val_l = __ldg(a.val + k_l);
                 first_l = (k_l == e_begin) || (__ldg(a.key + k_l - 1) != key_l);
-                if (first_l) end_l = __ldg(a.ptr + key_l + 1);
+                if (first_l) {
+                    end_l = __ldg(a.ptr + key_l + 1);
+                    atomicOr(a.busy + (key_l >> 5), 1u << (key_l & 31));      // order-independent: deterministic
+                }
             }
             float x[16];
 #pragma unroll
@@ -1055,15 +1076,18 @@ extern "C" int shpl_pool_conv3x3_forward(const float* dst, const float* src, con
                  workspace_bytes, c.bytes);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int c_in_total = C_d + C_s;
-    shpl_conv_prep_kernel<<<(kWElems + 255) / 256, 256, 0, s>>>(weight, c_in_total, C_out, 0, 0, c.wprep);
+    const bool sparse = C_s > 0 && nnz_max > 0;
+    const bool z_tc = sparse && C_s == kC;        // the pooled half's weights are prepped by the same launch
+    shpl_conv_prep_kernel<<<dim3((kWElems + 255) / 256, z_tc ? 2 : 1), 256, 0, s>>>(weight, c_in_total, C_out, 0, 0, c.wprep, C_d, c.wprep_p);
     shpl::count_launches(1);
     if (int rc = shpl::check_launch("shpl_conv_prep_kernel")) return rc;
-    const bool sparse = C_s > 0 && nnz_max > 0;
     if (sparse) {
         SHPL_CUDA_OK(cudaMemsetAsync(c.busy, 0, c.words * 4, s));
-        shpl_conv_mark_kernel<<<(nnz_max + 255) / 256, 256, 0, s>>>(ptr, key, (int)cells, nnz_max, c.busy);
-        shpl::count_launches(1);
-        if (int rc = shpl::check_launch("shpl_conv_mark_kernel")) return rc;
+        if (!z_tc) {      // the tensor-core Z kernel sets the bitmap itself
+            shpl_conv_mark_kernel<<<(nnz_max + 255) / 256, 256, 0, s>>>(ptr, key, (int)cells, nnz_max, c.busy);
+            shpl::count_launches(1);
+            if (int rc = shpl::check_launch("shpl_conv_mark_kernel")) return rc;
+        }
         ZArgs za{};
         za.src = src;
         za.ptr = ptr;
@@ -1079,10 +1103,8 @@ extern "C" int shpl_pool_conv3x3_forward(const float* dst, const float* src, con
         za.n_rows = (int)cells;
         za.nnz_max = nnz_max;
         za.Z = c.Z;
-        if (C_s == kC) {
-            shpl_conv_prep_kernel<<<(kWElems + 255) / 256, 256, 0, s>>>(weight, c_in_total, C_out, C_d, 0, c.wprep_p);
-            shpl::count_launches(1);
-            if (int rc = shpl::check_launch("shpl_conv_prep_kernel")) return rc;
+        za.busy = c.busy;
+        if (z_tc) {
             static bool z_attr = false;
             if (!z_attr) {
                 SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_conv_z_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kZtcSmemRequest));

@@ -67,6 +67,9 @@ namespace {
 #ifndef SHPL_SPARSE_GATHERS
 #define SHPL_SPARSE_GATHERS 4     // gathers in flight per warp in the entry CTAs of the sparse kernel
 #endif
+#ifndef SHPL_PIECE_LEN
+#define SHPL_PIECE_LEN 256     // entries per piece of a split listed cell (a CTA sums one piece)
+#endif
 #ifndef SHPL_LD_POLICY
 #define SHPL_LD_POLICY 1      // 0 = default, 1 = ld.global.cs (streaming)
 #endif
@@ -164,6 +167,7 @@ struct Job {
     int packed;              // sparse: 1 = lane-group entry walk for few vectors per cell (SHPL_PACKED=0 switches it off)
     int long_len;            // sparse: cells with more entries are summed by the stream warps as a whole (kLongRow; 512 when packed)
     int staged;              // sparse, staged instantiation: 2 = every entry CTA takes the staged walk, 1 = only CTAs that meet a long cell
+    int q_slices;            // sparse: warps a cell's channel vectors are spread over (1: a warp sums the whole row)
     int entry_chunk;         // wide: entries per warp
     int tiles;               // narrow: warp tiles; wide: CTA tiles of kWideTile cells
 };
@@ -575,9 +579,11 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
                                                   const float* __restrict__ val, int e0, int e1, int e_begin,
                                                   int e_end, V* __restrict__ out, int out_stride,
                                                   const V* __restrict__ addend, int add_stride, int nv,
-                                                  const int* __restrict__ ptr, int heavy_len, int lane, int n_gather, int n_cells) {
+                                                  const int* __restrict__ ptr, int heavy_len, int lane, int n_gather, int n_cells,
+                                                  int q_lo = 0, int q_hi = 0x7fffffff) {
+    // [q_lo, q_hi): the channel vectors this warp sums (a slice of the cell when its row is spread over several warps)
     const int prev_row = (e0 > e_begin) ? __ldg(key + e0 - 1) : -1;
-    for (int q0 = 0; q0 < nv; q0 += 32 * ACC) {
+    for (int q0 = q_lo; q0 < nv && q0 < q_hi; q0 += 32 * ACC) {
         int base = e0;
         int my_row = -1, my_p = 0;
         float my_w = 0.f;
@@ -819,7 +825,7 @@ template <typename V> constexpr int stage_smem_bytes() {
     return (kStageVecs + 2 * kStageMaxVecs) * (int)sizeof(V) + (4 * kStageEntries + 2 + 32) * 4;
 }
 
-template <typename V, bool kAdd>
+template <typename V, bool kAdd, bool kLongRuns>
 __device__ __noinline__ void pool_entries_staged(const V* __restrict__ src, int src_stride, const int* __restrict__ key,
                                                  const int* __restrict__ idx, const float* __restrict__ val,
                                                  const int* __restrict__ ptr, int E0, int E1, int e_begin, int e_end,
@@ -922,7 +928,15 @@ __device__ __noinline__ void pool_entries_staged(const V* __restrict__ src, int 
             V acc = cont ? carry_in[q] : vzero((V*)nullptr);
             const int len = (cont ? carry_len : 0) + (j1 - j0);
             const V* pp = s_prod + j0 * nv + q;
-            for (int j = j0; j < j1; ++j, pp += nv) acc = vadd(acc, *pp);
+            int j = j0;
+            if constexpr (kLongRuns) {
+                for (; j + 4 <= j1; j += 4, pp += 4 * nv) {
+                    // four products loaded side by side, then added in order: the LDS latency is paid once per four entries
+                    const V t0 = pp[0], t1 = pp[nv], t2 = pp[2 * nv], t3 = pp[3 * nv];
+                    acc = vadd(vadd(vadd(vadd(acc, t0), t1), t2), t3);
+                }
+            }
+            for (; j < j1; ++j, pp += nv) acc = vadd(acc, *pp);
             if (s_key[j1] != row) {                                     // the cell ends inside the batch
                 if (!(heavy_len > 0 && len > heavy_len)) {
                     if constexpr (kAdd) acc = vadd(ld_stream(addend + (size_t)row * add_stride + q), acc);
@@ -964,8 +978,12 @@ __device__ __noinline__ void pool_entries_staged(const V* __restrict__ src, int 
 // nothing, one dependent load (the tile's offsets) away from a bare copy.  Same sums in the same order.
 __host__ __device__ __forceinline__ bool packed_ok(const Job& jb) { return jb.vs_shift >= 0 && jb.vs <= 16 && jb.packed; }
 
-template <int W, bool kAdd, int ACC, bool kStaged = false>
-__global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SHPL_SPARSE_MIN_CTAS_WIDE) shpl_pool_sparse_kernel(PoolArgs a) {
+// kStaged: 0 = the plain instantiation; 1 = staged walk tuned for short runs (the dense regime without listed cells: 64
+// registers, 4 CTAs per SM, plain add loop); 2 = tuned for long runs (plans with listed cells: 80 registers, 3 CTAs per SM,
+// the add loop unrolled by four).  Measured (profiles/r2_staged_variants.txt): 1 M uniform pairs C = 16 41.7 us with 1, 56.2 us
+// with 2; 100 k Zipf pairs C = 16 66.9 us with 1, 41.4 us with 2.
+template <int W, bool kAdd, int ACC, int kStaged = 0>
+__global__ void __launch_bounds__(kThreads, (ACC == 1 && kStaged != 2) ? SHPL_SPARSE_MIN_CTAS : SHPL_SPARSE_MIN_CTAS_WIDE) shpl_pool_sparse_kernel(PoolArgs a) {
     using V = typename VecOf<W>::type;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -1000,13 +1018,18 @@ __global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SH
                 staged = __any_sync(kFull, hit);
             }
             if (staged) {
-                pool_entries_staged<V, kAdd>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.key, jb.idx, jb.val, jb.ptr,
+                pool_entries_staged<V, kAdd, kStaged == 2>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.key, jb.idx, jb.val, jb.ptr,
                                              E0, E1, e_begin, e_end, pout, jb.pool_out_stride, kAdd ? din : nullptr,
                                              jb.dense_in_stride, jb.vs, jb.vs_shift, jb.heavy_len, jb.n_gather, jb.n_cells, stage_smem);
                 return;
             }
         }
-        const int e0 = e_begin + (b * kWarps + warp) * jb.entry_chunk;
+        // rows of more than 32 * ACC vectors (MV3D: 192) are spread over q_slices warps, each summing its own slice of
+        // the channels over the same entry chunk: the dependent gather rounds of a crowded cell shrink by that factor
+        const int gw = b * kWarps + warp;
+        const int chunk_id = jb.q_slices > 1 ? gw / jb.q_slices : gw;
+        const int q_lo = jb.q_slices > 1 ? (gw - chunk_id * jb.q_slices) * 32 * ACC : 0;
+        const int e0 = e_begin + chunk_id * jb.entry_chunk;
         if (e0 >= e_end) return;
         if (ACC == 1 && packed_ok(jb)) {      // few vectors per cell: lane groups gather different entries
             pool_entries_packed<V>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.key, jb.idx, jb.val, e0,
@@ -1020,7 +1043,8 @@ __global__ void __launch_bounds__(kThreads, ACC == 1 ? SHPL_SPARSE_MIN_CTAS : SH
         pool_entries_wide<V, ACC, (ACC == 1 ? SHPL_SPARSE_GATHERS : SHPL_SPARSE_GATHERS_WIDE)>(static_cast<const V*>(jb.gather_in), jb.gather_stride, jb.key, jb.idx, jb.val, e0,
                                 min(e0 + jb.entry_chunk, e_end), e_begin, e_end, pout, jb.pool_out_stride,
                                 kAdd ? din : nullptr, jb.dense_in_stride, jb.vs, jb.ptr,
-                                jb.vs <= 32 ? jb.long_len : jb.heavy_len, lane, jb.n_gather, jb.n_cells);
+                                jb.vs <= 32 ? jb.long_len : jb.heavy_len, lane, jb.n_gather, jb.n_cells,
+                                q_lo, jb.q_slices > 1 ? q_lo + 32 * ACC : 0x7fffffff);
         return;
     }
     const int stream_ctas = jb.stream_ctas;
@@ -1273,7 +1297,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kThreads)
 // contiguous pieces; a CTA sums one piece (its 8 warps take sub-pieces in stored order, the warp sums are added in
 // order) into partial[piece][0:C] in the caller's workspace; shpl_pool_heavy_combine_kernel then adds the P partials in
 // order.  A fixed tree that depends only on L: deterministic, within fp32 rounding of the sequential sum.
-constexpr int kPieceLen = 1024;
+constexpr int kPieceLen = SHPL_PIECE_LEN;
 constexpr int kMaxListed = 4096;           // listed cells whose piece counts fit the shared-memory prefix array
 
 struct SplitArgs {
@@ -1355,23 +1379,52 @@ __global__ void __launch_bounds__(kThreads) shpl_pool_heavy_split_kernel(HeavyAr
     }
 }
 
+// A cell's P partial sums are added as a two-level fixed tree: kCombineGroups contiguous groups of ceil(P / groups)
+// partials are summed in order side by side (thread = (group, channel vector), eight loads in flight), then the group sums
+// in order.  Depends only on P: deterministic.
+constexpr int kCombineGroups = 32;
+
 template <int W>
 __global__ void __launch_bounds__(kThreads) shpl_pool_heavy_combine_kernel(HeavyArgs a, SplitArgs sa) {
     using V = typename VecOf<W>::type;
+    extern __shared__ float4 heavy_smem[];
+    V* gsum = reinterpret_cast<V*>(heavy_smem);                 // [kCombineGroups][nv]
     const int n_heavy = min(min(__ldg(a.count_dev), a.list_cap), kMaxListed);
     const V* partial = static_cast<const V*>(sa.partial);
     const V* addend = static_cast<const V*>(a.addend);
     V* out = static_cast<V*>(a.out);
     for (int h = blockIdx.x; h < n_heavy; h += gridDim.x) {
         const int g0 = __ldg(sa.prefix + h), g1 = min(__ldg(sa.prefix + h + 1), sa.max_pieces);
-        if (g1 <= g0) continue;
+        if (g1 <= g0) continue;                                  // block-uniform
         const int cell = __ldg(a.list + h);
+        const int P = g1 - g0, per = (P + kCombineGroups - 1) / kCombineGroups;
+        for (int i = threadIdx.x; i < kCombineGroups * a.nv; i += kThreads) {
+            const int grp = i / a.nv, q = i - grp * a.nv;
+            const int b = g0 + grp * per, e = min(b + per, g1);
+            V s = vzero((V*)nullptr);
+            if (b < e) {
+                s = partial[(size_t)b * a.nv + q];
+                int g = b + 1;
+                for (; g + 8 <= e; g += 8) {
+                    V t[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t[j] = partial[(size_t)(g + j) * a.nv + q];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) s = vadd(s, t[j]);
+                }
+                for (; g < e; ++g) s = vadd(s, partial[(size_t)g * a.nv + q]);
+            }
+            gsum[i] = s;
+        }
+        __syncthreads();
+        const int groups = (P + per - 1) / per;                  // non-empty groups
         for (int q = threadIdx.x; q < a.nv; q += kThreads) {
-            V s = partial[(size_t)g0 * a.nv + q];
-            for (int g = g0 + 1; g < g1; ++g) s = vadd(s, partial[(size_t)g * a.nv + q]);
+            V s = gsum[q];
+            for (int grp = 1; grp < groups; ++grp) s = vadd(s, gsum[grp * a.nv + q]);
             if (addend != nullptr) s = vadd(addend[(size_t)cell * a.addend_stride + q], s);
             out[(size_t)cell * a.out_stride + q] = s;
         }
+        __syncthreads();
     }
 }
 
@@ -1488,14 +1541,16 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(kThreads) shpl_pool
 #define SHPL_KNOB(name, dflt) (dflt)
 #endif
 
-// Round 1 kept listed cells of up to 2048 entries in the main kernels for narrow channel counts (C <= 16): one 8-CTA
-// cluster per cell was slower than the whole-warp walk there.  With 2-CTA clusters for the exact kernel and the split
-// tree for longer cells the heavy path wins at every width (profiles/r2_zipf16_probe.txt: C = 16, 100 k Zipf pairs
-// 88.7 -> 53.0 us), so nothing is kept any more; SHPL_NARROW_KEEP (experiment builds) brings the old rule back.
-constexpr int kNarrowKeep = 0;
+// Listed cells of up to SHPL_EXACT_LEN entries stay in the MAIN kernels for C <= 128 (at C = 256 a batch of the staged walk
+// holds 32 entries and a 2048-entry cell would take 64 of them on one CTA): the staged entry walk sums them in
+// entry order on one CTA (bit-exact, like the exact cluster kernel, without its extra launches: the exact kernel was
+// 91 us of the 1 M Zipf pairs forward at C = 64 on the side stream's critical path); the heavy entry points skip them
+// (HeavyArgs::skip_le) and only split the longer ones.  The rule is a function of C alone so that both sides agree.
+// SHPL_MAIN_KEEP=0 (experiment builds) brings the round-1 rule back (everything above heavy_len goes to the heavy kernels).
+constexpr int kMainKeep = SHPL_EXACT_LEN, kMainKeepMaxC = 128;
 int main_kernel_heavy_len(int heavy_len, int c_pool) {
-    const int keep = SHPL_KNOB("SHPL_NARROW_KEEP", kNarrowKeep);
-    return heavy_len > 0 && c_pool <= 16 && heavy_len < keep ? keep : heavy_len;
+    const int keep = SHPL_KNOB("SHPL_MAIN_KEEP", kMainKeep);
+    return heavy_len > 0 && c_pool <= kMainKeepMaxC && heavy_len < keep ? keep : heavy_len;
 }
 
 int log2_or_neg(int v) {
@@ -1557,6 +1612,9 @@ int wide_stream_knob() { return SHPL_KNOB("SHPL_WIDE_STREAM", 2); }
 int staged_knob() { return SHPL_KNOB("SHPL_STAGED", 1); }
 // batches per entry CTA in the dense regime
 // staged = 2 (every entry CTA) up to this many vectors per cell, when entries * density > cells
+// -1: by the caller's heavy_len; 1 / 2: force the short-run / long-run staged instantiation (experiments)
+int staged_variant_knob() { return SHPL_KNOB("SHPL_STAGED_VARIANT", -1); }
+int q_slices_knob() { return SHPL_KNOB("SHPL_Q_SLICES", 1); }
 int staged_all_vecs_knob() { return SHPL_KNOB("SHPL_STAGED_ALL_VECS", 8); }
 // measured (profiles/r2_staged_ab.txt): 100 k pairs on 560 k cells gain 10 % with every entry CTA staging, 20 k pairs lose 8 %
 int staged_density_knob() { const int v = SHPL_KNOB("SHPL_STAGED_DENSITY", 16); return v > 0 ? v : 16; }
@@ -1628,6 +1686,9 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
     // an entry CTA takes the staged walk only if its chunk meets a cell of more than 32 entries (staged = 1); callers that
     // pass heavy_len = 0 (FramePipeline, the custom op: KITTI / MV3D shapes) keep the plain instantiation.
     int staged = 0;
+    bool listed = false;       // a caller's heavy_len <= SHPL_HEAVY_LEN says its plan has listed cells (see shpl.h): long runs
+    for (int i = 0; i < n_specs; ++i) listed = listed || (specs[i].heavy_len > 0 && specs[i].heavy_len <= SHPL_HEAVY_LEN);
+    if (staged_variant_knob() >= 0) listed = staged_variant_knob() == 2;
     {
         const int mode = staged_knob();
         bool keys = true, heavy_all = true;
@@ -1729,10 +1790,17 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
             if (staged) o.long_len = o.heavy_len > 0 ? o.heavy_len : 0x7fffffff;   // no cell is left to the stream warps
             if (staged == 2 && o.vs > 0) {      // CTA chunk = a whole number of batches
                 const int batch = kStageVecs / o.vs < kStageEntries ? kStageVecs / o.vs : kStageEntries;
-                o.entry_chunk = batch * staged_batches_knob() / kWarps;
+                // batches per entry CTA: enough CTAs to fill the machine twice over, at most staged_batches_knob()
+                long long nb = (long long)src_spec[i]->nnz_max / ((long long)batch * 2 * shpl::sm_count());
+                if (nb > staged_batches_knob()) nb = staged_batches_knob();
+                if (nb < 1) nb = 1;
+                o.entry_chunk = batch * (int)nb / kWarps;
                 if (o.entry_chunk < 4) o.entry_chunk = 4;
             }
-            o.entry_ctas = o.vs > 0 ? (src_spec[i]->nnz_max + o.entry_chunk * kWarps - 1) / (o.entry_chunk * kWarps) : 0;
+            o.q_slices = 1;
+            if (!staged && !packed && o.vs > 64 && q_slices_knob()) o.q_slices = (o.vs + 63) / 64;   // 32 lanes x ACC = 2 vectors per slice
+            const long long chunks = ((long long)src_spec[i]->nnz_max + o.entry_chunk - 1) / o.entry_chunk;
+            o.entry_ctas = o.vs > 0 ? (int)((chunks * o.q_slices + kWarps - 1) / kWarps) : 0;
             a.begin[i + 1] = a.begin[i] + o.entry_ctas + o.stream_ctas;
         }
         const unsigned g = (unsigned)a.begin[a.n_jobs];
@@ -1741,8 +1809,10 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
 #define SHPL_LAUNCH_STAGED(WW, ACC_)                                                                                   \
     do {                                                                                                               \
         using VV = VecOf<WW>::type;                                                                                    \
-        if (add) shpl_pool_sparse_kernel<WW, true, ACC_, true><<<g, kThreads, stage_smem_bytes<VV>(), s>>>(a);         \
-        else shpl_pool_sparse_kernel<WW, false, ACC_, true><<<g, kThreads, stage_smem_bytes<VV>(), s>>>(a);            \
+        if (listed && add) shpl_pool_sparse_kernel<WW, true, ACC_, 2><<<g, kThreads, stage_smem_bytes<VV>(), s>>>(a);  \
+        else if (listed) shpl_pool_sparse_kernel<WW, false, ACC_, 2><<<g, kThreads, stage_smem_bytes<VV>(), s>>>(a);   \
+        else if (add) shpl_pool_sparse_kernel<WW, true, ACC_, 1><<<g, kThreads, stage_smem_bytes<VV>(), s>>>(a);       \
+        else shpl_pool_sparse_kernel<WW, false, ACC_, 1><<<g, kThreads, stage_smem_bytes<VV>(), s>>>(a);               \
     } while (0)
             if (max_vs > 32) {
                 if (w == 4) SHPL_LAUNCH_STAGED(4, 2);
@@ -2147,9 +2217,17 @@ static int pool_heavy_impl(const float* gather_in, int32_t gather_stride, int32_
         shpl::count_launches(1);
         if (int rc = shpl::check_launch("shpl_pool_heavy_split_kernel")) return rc;
         const unsigned grid_c = (unsigned)(list_cap < 256 ? list_cap : 256);
-        if (w == 4) shpl_pool_heavy_combine_kernel<4><<<grid_c, kThreads, 0, s>>>(a, sa);
-        else if (w == 2) shpl_pool_heavy_combine_kernel<2><<<grid_c, kThreads, 0, s>>>(a, sa);
-        else shpl_pool_heavy_combine_kernel<1><<<grid_c, kThreads, 0, s>>>(a, sa);
+        const size_t smem_c = (size_t)kCombineGroups * a.nv * sizeof(float) * w;
+#define SHPL_LAUNCH_COMBINE(WW)                                                                                         \
+    do {                                                                                                                \
+        if (smem_c > 48 * 1024)                                                                                         \
+            SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_pool_heavy_combine_kernel<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c)); \
+        shpl_pool_heavy_combine_kernel<WW><<<grid_c, kThreads, smem_c, s>>>(a, sa);                                     \
+    } while (0)
+        if (w == 4) SHPL_LAUNCH_COMBINE(4);
+        else if (w == 2) SHPL_LAUNCH_COMBINE(2);
+        else SHPL_LAUNCH_COMBINE(1);
+#undef SHPL_LAUNCH_COMBINE
         shpl::count_launches(1);
         return shpl::check_launch("shpl_pool_heavy_combine_kernel");
     }

@@ -233,13 +233,16 @@ class SparsePoolPlan:
         return c
 
     def heavy_len(self, by_pixel=None):
-        """The heavy_len argument of the pooling entry points for this plan: SHPL_HEAVY_LEN, or 0 when the counters read
-        back say that no cell of that direction (None: of either direction) has more than SHPL_LONG_LEN entries -- the
-        kernels then skip every long-cell path (and there is no listed cell for shpl_pool_heavy)."""
-        if self.n_long is None:
+        """The heavy_len argument of the pooling entry points for this plan, from the counters read back (direction: rows,
+        pixels, None = either): SHPL_HEAVY_LEN when cells are listed for shpl_pool_heavy; SHPL_EXACT_LEN when some cell has
+        more than SHPL_LONG_LEN entries but none is listed (no cell is left out; the kernels take their long-cell paths);
+        0 when no cell is long (the kernels skip every long-cell path: every KITTI / MV3D plan)."""
+        if self.n_long is None or self.n_heavy is None:
             return _cabi.HEAVY_LEN
-        n = self.n_long[0] + self.n_long[1] if by_pixel is None else self.n_long[1 if by_pixel else 0]
-        return _cabi.HEAVY_LEN if n > 0 else 0
+        pick = (lambda t: t[0] + t[1]) if by_pixel is None else (lambda t: t[1 if by_pixel else 0])
+        if pick(self.n_heavy) > 0:
+            return _cabi.HEAVY_LEN          # listed cells: left to shpl_pool_heavy; the kernels tune for long runs
+        return _cabi.EXACT_LEN if pick(self.n_long) > 0 else 0     # long but not listed: nothing is left out
 
     def heavy(self, by_pixel):
         """(list pointer, device counter pointer, list capacity, how many to expect or None when the counters have

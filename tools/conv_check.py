@@ -74,9 +74,19 @@ def timing():
     outs = [torch.empty(1, H, W, 32, device=dev) for _ in range(3)]
     ws = conv_fusion.conv_workspace(1, H, W, dev, 20000)
     Ms = []
-    for bev, img, d in sets:
-        o = shpl.produce_sparse_pooling_input(dict(d), stride=[1, 1])
+    scan = "--scan" in sys.argv      # the bench's pairs: a synthetic 64-beam scan (busy cells clustered along the rings)
+    for i, (bev, img, d) in enumerate(sets):
+        if scan:
+            f = synth.avod_frame(100 + i, az_step_deg=0.028)
+
+            class Calib:
+                p2 = f["P"]
+            g = shpl.gen_sparse_pooling_input_avod(f["points"], f["voxel_indices"], Calib, f["im_size"], [H, W])
+            o = shpl.produce_sparse_pooling_input(g, stride=[1, 1])
+        else:
+            o = shpl.produce_sparse_pooling_input(dict(d), stride=[1, 1])
         Ms.append(o)
+    print("pairs per frame:", [int(o["M_size"][1]) for o in Ms], "(scan pattern)" if scan else "(uniform)")
     def run(k, pooled=True):
         bev, img, d = sets[k % 3]
         o = Ms[k % 3]
