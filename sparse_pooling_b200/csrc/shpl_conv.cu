@@ -49,8 +49,7 @@ constexpr int kOutBytes = kOutRows * 128;            // 14336: one output tile, 
 static_assert(kOutBytes % 1024 == 0, "output staging buffers stay 1024-byte aligned (swizzle atom)");
 constexpr int kWorkers = 256;
 constexpr int kSparseWarps = 4;                      // warps 10..13: the pooled half's contributions, one tile ahead
-constexpr int kSparseRows = kOutRows / kSparseWarps; // 28 output pixels per sparse warp
-static_assert(kSparseRows == 2 * kTileX && kHaloX == 16 && kHaloY == 2 * kSparseWarps + 2, "a sparse warp: two output rows, four halo rows of 16 cells = two cells per lane");
+static_assert(kOutRows <= kSparseWarps * 32 && kHaloX == 16, "a sparse thread per output pixel of the tile");
 constexpr int kConvThreads = kWorkers + 64 + kSparseWarps * 32;
 constexpr int kAccCols = kNB;                        // columns of one accumulator buffer
 constexpr int kTmemCols = 512;                       // 2 x 192 used
@@ -154,6 +153,12 @@ __device__ __forceinline__ float to_tf32(float x) {
 #define SHPL_TMEM_LD8(taddr, v)                                                                               \
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                  \
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) \
+                 : "r"(taddr))
+
+#define SHPL_TMEM_LD16(taddr, v)                                                                              \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" \
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),     \
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])                        \
                  : "r"(taddr))
 
 struct ConvArgs {
@@ -294,132 +299,119 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
         }
     } else if (warp >= 10) {
         // ===== sparse warps (10..13): the pooled half of the conv, one tile ahead of the epilogue =====
-        // For every output pixel of the tile: the sum, in a fixed order (deterministic), of the Z rows of its busy neighbours
-        // -- Z[cell][tap] = W_pooled[tap]^T . pooled[cell], from the Z kernel -- left in the tile's output staging buffer,
-        // where the epilogue adds the dense half on top.  A warp owns output rows 2 sw, 2 sw + 1 of the tile (28 pixels) and
-        // works on its own, no barrier between the four: it looks at the four halo rows that reach its pixels (a lane holds
-        // two halo cells: row 2 sw + (lane >> 3), columns 2 (lane & 7) and + 1), and for every busy one adds the cell's nine
-        // Z rows -- 1152 contiguous bytes = 72 float4: lane -> (tap, channel quad), three 128-bit loads -- to the pixels the
-        // taps land on.  No global latency is exposed per tile but the Z loads, and those hit L1:
-        //   tile i+2: one lane per halo row loads the row's busy-bitmap words
-        //   tile i+1: bits -> the CSR-offset loads of the busy cells (two predicated loads per lane); prefetch of their Z rows
-        //   tile i  : offsets -> Z rows -> read-modify-write of the staging rows
+        // Thread = output pixel of the tile (112 of the 128 threads): the sum, in tap order (a fixed order: deterministic), of
+        // the Z rows of its busy neighbours -- Z[cell][tap] = W_pooled[tap]^T . pooled[cell], from the Z kernel -- formed in
+        // registers and left in the tile's output staging buffer, where the epilogue adds the dense half on top.  The cost
+        // of a tile is bounded (as many rounds as the busiest pixel of a warp has busy neighbours, at most nine) however the
+        // busy cells cluster, and only the final store needs the staging buffer.  A warp works on its own (no barrier between
+        // the four): lanes 0..4 hold the busy bits of the five halo rows its pixels look at.  No global latency but the Z
+        // loads (which hit L1) is exposed per tile:
+        //   tile i+2: lanes 0..4 load their halo row's busy-bitmap words
+        //   tile i+1: bits -> every thread tests its nine neighbours and issues the (few) CSR-offset loads, predicated
+        //   end of tile i: offsets -> Z rows of tile i+1, each (one 128-byte line) prefetched into L1
         if (a.busy != nullptr && n_mine > 0) {
             const int sw = warp - 10;
+            const int r = sw * 32 + lane;                                // staging row = output pixel of the tile
+            const bool px_ok = r < kOutRows;
+            const int yl = px_ok ? r / kTileX : 0, xl = px_ok ? r - yl * kTileX : 0;
+            const int yb = (sw * 32) / kTileX;                           // first output row of this warp = first halo row it looks at
             const int e_begin = __ldg(a.ptr);
-            const int hyl = lane >> 3, hxa = (lane & 7) * 2;
             uint32_t hw_lo = 0u, hw_hi = 0u;
             int hw_sh = 0, hw_nv = 0, hw_ls = 0;
-            auto issue_halo = [&](int j) {                               // lanes 0, 8, 16, 24: raw bitmap words of halo row 2 sw + hyl of tile j
+            int hf = 0, hy0 = 0, hx0 = 0;                                // coordinates of the tile whose halo words are in flight
+            auto issue_halo = [&](int j) {                               // lanes 0..4: raw bitmap words of halo row yb + lane of tile j
                 hw_nv = 0;
-                if (j >= n_mine || (lane & 7) != 0) return;
-                int f, y0, x0;
-                tile_coord(j, f, y0, x0);
-                const int yy = y0 - 1 + 2 * sw + hyl;
+                if (j >= n_mine) return;
+                tile_coord(j, hf, hy0, hx0);                             // one coordinate computation per tile: issue_offsets reuses it
+                if (lane >= 5 || yb + lane >= kHaloY) return;
+                const int yy = hy0 - 1 + yb + lane;
                 if (yy < 0 || yy >= a.H) return;
-                const int xs = x0 > 0 ? x0 - 1 : 0;                      // first in-image halo column
-                const long long c = ((long long)f * a.H + yy) * a.W + xs;
+                const int xs = hx0 > 0 ? hx0 - 1 : 0;                    // first in-image halo column
+                const long long c = ((long long)hf * a.H + yy) * a.W + xs;
                 const long long last = ((long long)a.frames * a.H * a.W - 1) >> 5;
                 const long long wi = c >> 5;
                 hw_lo = __ldg(a.busy + wi);
                 hw_hi = wi + 1 <= last ? __ldg(a.busy + wi + 1) : 0u;
                 hw_sh = (int)(c & 31);
-                hw_ls = xs - (x0 - 1);
+                hw_ls = xs - (hx0 - 1);
                 hw_nv = min(a.W - xs, kHaloX - hw_ls);                   // columns of this row inside the image
             };
-            auto issue_offsets = [&](int j, int& pa, int& pb) {          // -1: the cell is not busy
+            int poff[9];                                                 // CSR offsets of the busy neighbours (loads in flight)
+            uint32_t pnear = 0u;                                         // bit t: the neighbour at tap t is busy
+            auto issue_offsets = [&]() {                                 // for the tile of the last issue_halo
                 uint32_t bits = 0u;
                 if (hw_nv > 0) {
                     bits = (uint32_t)(((((uint64_t)hw_hi) << 32) | hw_lo) >> hw_sh) & 0xffffu;
                     bits &= (1u << hw_nv) - 1u;
                     bits <<= hw_ls;
                 }
-                bits = __shfl_sync(0xffffffffu, bits, lane & 24) >> hxa;  // the row's 16 bits, from the lane that loaded them
-                int f, y0, x0;
-                tile_coord(j, f, y0, x0);
-                const int nb = (f * a.H + y0 + 2 * sw + hyl - 1) * a.W + x0 + hxa - 1;
-                SHPL_DASSERT(!(bits & 3u) || (nb + 1 >= 0 && nb < a.frames * a.H * a.W));
-                pa = (bits & 1u) ? __ldg(a.ptr + nb) : -1;
-                pb = (bits & 2u) ? __ldg(a.ptr + nb + 1) : -1;
-            };
-            // the nine Z rows of a busy cell: nine lines, prefetched into L1 a tile ahead
-            auto prefetch_rows = [&](int pa, int pb) {
+                const int gy = hy0 + yl, gx = hx0 + xl;
+                pnear = 0u;
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy)
+                    pnear |= ((__shfl_sync(0xffffffffu, bits, yl + dy - yb) >> xl) & 7u) << (3 * dy);
+                if (!(px_ok && gy < a.H && gx < a.W)) pnear = 0u;
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
-                    if (pa >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.Z + ((size_t)(pa - e_begin) * 9 + t) * 32));
-                    if (pb >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.Z + ((size_t)(pb - e_begin) * 9 + t) * 32));
+                    const int nb = (hf * a.H + gy + t / 3 - 1) * a.W + gx + t % 3 - 1;
+                    const bool on = (pnear >> t) & 1u;
+                    SHPL_DASSERT(!on || (nb >= 0 && nb < a.frames * a.H * a.W));
+                    poff[t] = on ? __ldg(a.ptr + nb) : 0;
                 }
             };
-            // lane -> float4 f = lane + 32 p (p = 0, 1, 2; f < 72) of a cell's Z block: tap f >> 3, channel quad f & 7
-            int t_dy[3], t_dx[3];
+            int zrow[9];
+            uint32_t zmask = 0u;
+            auto rows_of_offsets = [&]() {                               // offsets (arrived) -> Z rows + their L1 prefetch
+                zmask = pnear;
 #pragma unroll
-            for (int p2 = 0; p2 < 3; ++p2) {
-                const int t = (lane + 32 * p2) >> 3;
-                t_dy[p2] = t < 9 ? t / 3 : 100;                          // 100: no such tap (never lands on a pixel)
-                t_dx[p2] = t % 3;
-            }
-            const int cq = lane & 7;
-            int pa = -1, pb = -1, pa_n = -1, pb_n = -1;
+                for (int t = 0; t < 9; ++t) {
+                    zrow[t] = ((zmask >> t) & 1u) ? (poff[t] - e_begin) * 9 + t : -1;
+                    SHPL_DASSERT(zrow[t] < 0 || zrow[t] / 9 < a.z_rows);
+                    if (zrow[t] >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.Z + (size_t)zrow[t] * 32));
+                }
+            };
             issue_halo(0);
-            issue_offsets(0, pa, pb);
+            issue_offsets();
             issue_halo(1);
-            prefetch_rows(pa, pb);
+            rows_of_offsets();
             for (int i = 0; i < n_mine; ++i) {
                 const int ob = i & 1, u = i >> 1;
                 if (i + 1 < n_mine) {
-                    issue_offsets(i + 1, pa_n, pb_n);
+                    issue_offsets();                                     // tile i+1 (its halo words were loaded during the last tile)
                     issue_halo(i + 2);
                 }
-                mbar_wait(bar(BAR_OUT_EMPTY + ob), (u & 1) ^ 1);         // the store of tile i-2 has read this buffer
-                uint8_t* obase = gbase + kSmOut + ob * kOutBytes;
-                {   // zeros for the warp's 28 rows (3584 contiguous bytes)
-                    float4* z = reinterpret_cast<float4*>(obase + sw * kSparseRows * 128);
+                float o[32];
 #pragma unroll
-                    for (int k = 0; k < kSparseRows * 8 / 32; ++k) z[k * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                __syncwarp();
-                // busy cells in (halo row, column) order; tap t of a cell at halo (hy, hx) lands on output pixel (hy - t / 3, hx - t % 3)
-                const uint32_t ma = __ballot_sync(0xffffffffu, pa >= 0), mb = __ballot_sync(0xffffffffu, pb >= 0);
-                uint32_t any = ma | mb;
-                while (any) {
-                    const int l = __ffs(any) - 1;
-                    any &= any - 1;
-                    const int h = l >> 3;                                // halo row 2 sw + h
+                for (int c = 0; c < 32; ++c) o[c] = 0.f;
+                // Round k handles the k-th busy tap of every lane together: a warp pays one latency per round, and there are as
+                // many rounds as its busiest pixel has busy neighbours.
+                while (__any_sync(0xffffffffu, zmask != 0u)) {
+                    if (zmask != 0u) {
+                        const int t = __ffs(zmask) - 1;
+                        zmask &= zmask - 1u;
+                        int zr = zrow[0];
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        if (!(((half ? mb : ma) >> l) & 1u)) continue;
-                        const int zr0 = (__shfl_sync(0xffffffffu, half ? pb : pa, l) - e_begin) * 9;
-                        SHPL_DASSERT(zr0 >= 0 && zr0 / 9 < a.z_rows);
-                        const int hx = (l & 7) * 2 + half;
-                        const float4* zb = reinterpret_cast<const float4*>(a.Z + (size_t)zr0 * 32) + lane;
-                        float4 zv[3];
-                        int off[3];
+                        for (int tt = 1; tt < 9; ++tt) zr = (t == tt) ? zrow[tt] : zr;
+                        const float4* z = reinterpret_cast<const float4*>(a.Z + (size_t)zr * 32);
+                        float4 zv[8];
 #pragma unroll
-                        for (int p2 = 0; p2 < 3; ++p2) {
-                            const int yo = h - t_dy[p2], xl = hx - t_dx[p2];   // output row inside the warp's pair, output column
-                            off[p2] = -1;
-                            if (yo >= 0 && yo < 2 && xl >= 0 && xl < kTileX) {
-                                const int r = (2 * sw + yo) * kTileX + xl;
-                                off[p2] = r * 128 + ((cq ^ (r & 7)) << 4);
-                                zv[p2] = __ldg(zb + 32 * p2);
-                            }
+                        for (int j = 0; j < 8; ++j) zv[j] = __ldg(z + j);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            o[4 * j] += zv[j].x; o[4 * j + 1] += zv[j].y; o[4 * j + 2] += zv[j].z; o[4 * j + 3] += zv[j].w;
                         }
-#pragma unroll
-                        for (int p2 = 0; p2 < 3; ++p2)
-                            if (off[p2] >= 0) {
-                                float4* cell = reinterpret_cast<float4*>(obase + off[p2]);
-                                float4 c4 = *cell;
-                                c4.x += zv[p2].x; c4.y += zv[p2].y; c4.z += zv[p2].z; c4.w += zv[p2].w;
-                                *cell = c4;
-                            }
-                        __syncwarp();                                    // the next cell may touch the same pixels from other lanes
                     }
+                }
+                mbar_wait(bar(BAR_OUT_EMPTY + ob), (u & 1) ^ 1);         // the store of tile i-2 has read this buffer
+                if (px_ok) {
+                    uint8_t* orow = gbase + kSmOut + ob * kOutBytes + r * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(orow + ((j ^ (r & 7)) << 4)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(BAR_CONTRIB_FULL + ob));
-                pa = pa_n;
-                pb = pb_n;
-                if (i + 1 < n_mine) prefetch_rows(pa, pb);               // the next tile's rows: in L1 by the time they are read
+                if (i + 1 < n_mine) rows_of_offsets();                   // tile i+1's rows: in L1 by the time they are read
             }
         }
     } else {
@@ -695,16 +687,25 @@ __global__ void __launch_bounds__(kZtcThreads, 2) shpl_conv_z_tc_kernel(ZArgs a)
                 const bool on = flags[m] != 0;
                 float* zrow = a.Z + (size_t)(e0 - e_begin + m) * 288 + dy0 * 96;
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
-                const int ncc = ndy * 6;                      // 8-column chunks per half
-#pragma unroll 3
-                for (int cc = 0; cc < ncc; ++cc) {
-                    const int col = half * ncc * 8 + cc * 8;
-                    uint32_t v[8];
-                    SHPL_TMEM_LD8(taddr + col, v);
+                const int n16 = ndy * 3;                      // 16-column chunks per half (96 or 48 columns)
+                for (int cc = 0; cc < n16; cc += 2) {         // two chunks (32 columns) per TMEM round trip
+                    const int col = half * n16 * 16 + cc * 16;
+                    const bool two = cc + 1 < n16;
+                    uint32_t va[16], vb[16];
+                    SHPL_TMEM_LD16(taddr + col, va);
+                    if (two) SHPL_TMEM_LD16(taddr + col + 16, vb);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (on) {
-                        *reinterpret_cast<float4*>(zrow + col) = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-                        *reinterpret_cast<float4*>(zrow + col + 4) = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            *reinterpret_cast<float4*>(zrow + col + 4 * k) = make_float4(__uint_as_float(va[4 * k]), __uint_as_float(va[4 * k + 1]),
+                                                                                        __uint_as_float(va[4 * k + 2]), __uint_as_float(va[4 * k + 3]));
+                        if (two) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                *reinterpret_cast<float4*>(zrow + col + 16 + 4 * k) = make_float4(__uint_as_float(vb[4 * k]), __uint_as_float(vb[4 * k + 1]),
+                                                                                                 __uint_as_float(vb[4 * k + 2]), __uint_as_float(vb[4 * k + 3]));
+                        }
                     }
                 }
             }

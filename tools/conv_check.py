@@ -72,7 +72,7 @@ def timing():
         sets.append((bev, img, d))
     w = torch.randn(3, 3, 64, 32, device=dev) * 0.1
     outs = [torch.empty(1, H, W, 32, device=dev) for _ in range(3)]
-    ws = conv_fusion.conv_workspace(1, H, W, dev, 20000)
+    ws = conv_fusion.conv_workspace(1, H, W, dev, 40000)
     Ms = []
     scan = "--scan" in sys.argv      # the bench's pairs: a synthetic 64-beam scan (busy cells clustered along the rings)
     for i, (bev, img, d) in enumerate(sets):
