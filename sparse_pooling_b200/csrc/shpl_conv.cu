@@ -9,15 +9,19 @@
 // accumulators in TMEM, halo tiles brought in by TMA with the SAME padding supplied by the TMA's out-of-bounds zero
 // fill, output tiles written back by TMA); fp32 parity comes from the 3xTF32 split (x = hi + lo, both tf32:
 // hi*hi + lo*hi + hi*lo, error ~2^-21 per product).  The second term only touches the 3x3 neighbourhoods of the few
-// cells that receive pooled features (~2 % at KITTI stride 1): a bitmap of those neighbourhoods is made first, the
-// dense kernel leaves the marked cells un-activated, and a small warp-per-cell kernel adds W_pooled . pooled there
-// (the pooled sums formed in the reference's entry order, like the pooling kernels do) and applies the epilogue.
+// cells that receive pooled features (~2 % at KITTI stride 1): a second tcgen05 kernel (shpl_conv_z_tc_kernel) forms,
+// for every such cell, Z[cell][tap] = W_pooled[tap]^T . pooled[cell] (the pooled sums in the reference's entry order,
+// like the pooling kernels do) and sets the cell's bit in a bitmap; four warps of the dense kernel then add, for every
+// output pixel, the Z rows of its busy neighbours into the tile's output staging buffer one tile ahead of the epilogue.
 //
-// Dense kernel, one persistent CTA per SM, 10 warps, every stage double-buffered so that they all overlap:
-//   warp 8    TMA producer   halo tile [10 x 16 pixels x 32 ch] fp32 -> staging
-//   warps 4-7 conversion     staging -> hi / lo operand planes ([chunk of 4 ch][halo pixel][16 B]: the K-major,
-//                            no-swizzle core-matrix layout, so a row shift dy is just a different start address)
-//   warps 0-3 epilogue       TMEM -> registers (+ the dx shuffle-sum, scale / shift / ReLU) -> swizzled smem -> TMA store
+// Dense kernel, one persistent CTA per SM, 14 warps, every stage double-buffered so that they all overlap:
+//   warp 8      TMA producer   halo tile [10 x 16 pixels x 32 ch] fp32 -> staging
+//   warps 4-7   conversion     staging -> hi / lo operand planes ([chunk of 4 ch][halo pixel][16 B]: the K-major,
+//                              no-swizzle core-matrix layout, so a row shift dy is just a different start address)
+//   warps 10-13 pooled half    thread = output pixel: busy bits of its nine neighbours -> their CSR offsets -> their Z rows,
+//                              summed in registers in tap order, stored into the tile's output staging buffer
+//   warps 0-3   epilogue       TMEM -> registers (the dx shuffle-sum) + the pooled half from the staging buffer, scale / shift /
+//                              ReLU -> back into the (128B-swizzled) staging buffer -> TMA store
 //   warp 9    MMA issuer     per tile 3 dy x 4 K-steps x {A_hi x [B_hi | B_lo] (N = 192), A_lo x B_hi (N = 96)}
 // The 128 rows of an MMA are 8 image rows x 16 HALO columns; the N dimension carries the three dx taps side by side
 // (and hi | lo of the weights), so one read of A serves three taps: the tensor core fetches its shared-memory operands
@@ -895,34 +899,36 @@ __global__ void __launch_bounds__(256) shpl_conv_gwp_kernel(const float* __restr
     reinterpret_cast<float4*>(part_p + ((size_t)(t * kGwChunks + chunk) * 32 + ci) * 32)[cq] = acc;
 }
 
-// dense channels: persistent CTAs over 8 x 32-pixel tiles; thread (ci, co quad) keeps 9 taps x 4 sums in registers
-constexpr int kGwTileY = 8, kGwTileX = 32;
+// dense channels: persistent CTAs of 128 threads over 8 x 16-pixel tiles with a shared-memory halo; thread = (input-channel
+// pair, output-channel quad) keeps 9 taps x 2 x 4 sums in registers: per pixel one LDS.128 of g_out and nine LDS.64 of the
+// input feed 72 FFMAs (the first version, one input channel per thread, fed 36 and was bound by the loads).
+constexpr int kGwTileY = 8, kGwTileX = 16, kGwThreads = 128, kGwCtasPerSm = 4;
 constexpr int kGwHaloFloats = (kGwTileY + 2) * (kGwTileX + 2) * 32, kGwTileFloats = kGwTileY * kGwTileX * 32;
 constexpr int kGwdSmem = (kGwHaloFloats + kGwTileFloats) * 4;
 
-__global__ void __launch_bounds__(256, 2) shpl_conv_gwd_kernel(const float* __restrict__ x, const float* __restrict__ g_out, int frames, int H, int W,
-                                                               float* __restrict__ part_d) {
+__global__ void __launch_bounds__(kGwThreads, kGwCtasPerSm) shpl_conv_gwd_kernel(const float* __restrict__ x, const float* __restrict__ g_out, int frames, int H, int W,
+                                                                                  float* __restrict__ part_d) {
     extern __shared__ float gw_smem[];
-    float* xs = gw_smem;                    // [10][34][32] halo of the input map (zeros outside the image)
-    float* gs = gw_smem + kGwHaloFloats;    // [8][32][32] the output-gradient tile (zeros outside the image)
+    float* xs = gw_smem;                    // [10][18][32] halo of the input map (zeros outside the image)
+    float* gs = gw_smem + kGwHaloFloats;    // [8][16][32] the output-gradient tile (zeros outside the image)
     const int tiles_x = (W + kGwTileX - 1) / kGwTileX, tiles_y = (H + kGwTileY - 1) / kGwTileY;
     const int n_tiles = frames * tiles_x * tiles_y;
-    const int ci = threadIdx.x >> 3, cq = threadIdx.x & 7;
-    float4 acc[9];
+    const int cp = threadIdx.x >> 3, cq = threadIdx.x & 7;      // input channels 2 cp, 2 cp + 1; output channels 4 cq .. 4 cq + 3
+    float4 acc[9][2];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int f = tile / (tiles_x * tiles_y), tt = tile - f * tiles_x * tiles_y;
         const int y0 = (tt / tiles_x) * kGwTileY, x0 = (tt % tiles_x) * kGwTileX;
         __syncthreads();
-        for (int i = threadIdx.x; i < kGwHaloFloats / 4; i += 256) {      // float4 units: [10][34][8]
+        for (int i = threadIdx.x; i < kGwHaloFloats / 4; i += kGwThreads) {      // float4 units: [10][18][8]
             const int q = i & 7, px = (i >> 3) % (kGwTileX + 2), py = (i >> 3) / (kGwTileX + 2);
             const int yy = y0 - 1 + py, xx = x0 - 1 + px;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)(f * H + yy) * W + xx) * 32) + q);
             reinterpret_cast<float4*>(xs)[i] = v;
         }
-        for (int i = threadIdx.x; i < kGwTileFloats / 4; i += 256) {
+        for (int i = threadIdx.x; i < kGwTileFloats / 4; i += kGwThreads) {
             const int q = i & 7, px = (i >> 3) % kGwTileX, py = (i >> 3) / kGwTileX;
             const int yy = y0 + py, xx = x0 + px;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -936,15 +942,20 @@ __global__ void __launch_bounds__(256, 2) shpl_conv_gwd_kernel(const float* __re
                 const float4 g = reinterpret_cast<const float4*>(gs + (py * kGwTileX + px) * 32)[cq];
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
-                    const float xv = xs[((py + t / 3) * (kGwTileX + 2) + px + t % 3) * 32 + ci];
-                    acc[t].x = fmaf(xv, g.x, acc[t].x); acc[t].y = fmaf(xv, g.y, acc[t].y);
-                    acc[t].z = fmaf(xv, g.z, acc[t].z); acc[t].w = fmaf(xv, g.w, acc[t].w);
+                    const float2 xv = reinterpret_cast<const float2*>(xs + ((py + t / 3) * (kGwTileX + 2) + px + t % 3) * 32)[cp];
+                    acc[t][0].x = fmaf(xv.x, g.x, acc[t][0].x); acc[t][0].y = fmaf(xv.x, g.y, acc[t][0].y);
+                    acc[t][0].z = fmaf(xv.x, g.z, acc[t][0].z); acc[t][0].w = fmaf(xv.x, g.w, acc[t][0].w);
+                    acc[t][1].x = fmaf(xv.y, g.x, acc[t][1].x); acc[t][1].y = fmaf(xv.y, g.y, acc[t][1].y);
+                    acc[t][1].z = fmaf(xv.y, g.z, acc[t][1].z); acc[t][1].w = fmaf(xv.y, g.w, acc[t][1].w);
                 }
             }
         }
     }
 #pragma unroll
-    for (int t = 0; t < 9; ++t) reinterpret_cast<float4*>(part_d + (((size_t)blockIdx.x * 9 + t) * 32 + ci) * 32)[cq] = acc[t];
+    for (int t = 0; t < 9; ++t) {
+        reinterpret_cast<float4*>(part_d + (((size_t)blockIdx.x * 9 + t) * 32 + 2 * cp) * 32)[cq] = acc[t][0];
+        reinterpret_cast<float4*>(part_d + (((size_t)blockIdx.x * 9 + t) * 32 + 2 * cp + 1) * 32)[cq] = acc[t][1];
+    }
 }
 
 // g_weight[t][ci][co] = the partial sums added in CTA / chunk order (fixed: deterministic)
@@ -955,7 +966,16 @@ __global__ void shpl_conv_gw_reduce_kernel(const float* __restrict__ part_d, int
     const int co = i & 31, ci = (i >> 5) % c_in_total, t = (i >> 5) / c_in_total;
     float s = 0.f;
     if (ci < 32) {
-        for (int c = 0; c < n_ctas; ++c) s += part_d[(((size_t)c * 9 + t) * 32 + ci) * 32 + co];
+        const float* pd = part_d + ((size_t)t * 32 + ci) * 32 + co;
+        int c = 0;
+        for (; c + 8 <= n_ctas; c += 8) {             // eight partial sums in flight, added in CTA order
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = pd[(size_t)(c + j) * 9 * 1024];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[j];
+        }
+        for (; c < n_ctas; ++c) s += pd[(size_t)c * 9 * 1024];
     } else if (part_p != nullptr) {
         for (int c = 0; c < kGwChunks; ++c) s += part_p[((size_t)(t * kGwChunks + c) * 32 + ci - 32) * 32 + co];
     }
@@ -1146,7 +1166,7 @@ BwdWorkspace carve_bwd(void* ws, long long nnz_max) {
     size_t off = 0;
     auto take = [&](size_t n) { uint8_t* q = p + off; off += align_up(n, 256); return q; };
     const size_t n = (size_t)(nnz_max > 0 ? nnz_max : 0);
-    b.n_ctas = 2 * 148;                       // persistent CTAs of the dense weight-gradient kernel (fixed: part of the summation tree)
+    b.n_ctas = kGwCtasPerSm * 148;            // persistent CTAs of the dense weight-gradient kernel (fixed: part of the summation tree)
     b.wprep = reinterpret_cast<float*>(take(kWBytes));
     b.PB = reinterpret_cast<float*>(take(n * 32 * 4));
     b.GP = reinterpret_cast<float*>(take(n * 32 * 4));
@@ -1182,7 +1202,7 @@ extern "C" int shpl_pool_conv3x3_backward(const float* g_out, const float* dst, 
     const long long cells = (long long)frames * H * W;
     const bool sparse = C_s > 0 && nnz_max > 0;
     BwdWorkspace b = carve_bwd(workspace, sparse ? nnz_max : 0);
-    b.n_ctas = 2 * shpl::sm_count() < b.n_ctas ? 2 * shpl::sm_count() : b.n_ctas;
+    b.n_ctas = kGwCtasPerSm * shpl::sm_count() < b.n_ctas ? kGwCtasPerSm * shpl::sm_count() : b.n_ctas;
     SHPL_REQUIRE(workspace_bytes >= b.bytes, SHPL_ERR_WORKSPACE_TOO_SMALL, "shpl_pool_conv3x3_backward: workspace %zu < %zu bytes",
                  workspace_bytes, b.bytes);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1232,7 +1252,7 @@ extern "C" int shpl_pool_conv3x3_backward(const float* g_out, const float* dst, 
             SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_conv_gwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGwdSmem));
             attr_set = true;
         }
-        shpl_conv_gwd_kernel<<<b.n_ctas, 256, kGwdSmem, s>>>(dst, g_out, frames, H, W, b.part_d);
+        shpl_conv_gwd_kernel<<<b.n_ctas, kGwThreads, kGwdSmem, s>>>(dst, g_out, frames, H, W, b.part_d);
         shpl::count_launches(1);
         if (int rc = shpl::check_launch("shpl_conv_gwd_kernel")) return rc;
         if (sparse) {

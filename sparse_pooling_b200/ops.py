@@ -123,6 +123,7 @@ class SparsePoolPlan:
         self._vbase = self._vals.data_ptr()
         self.n_heavy = None   # (rows, pixels) with more than HEAVY_LEN entries; host ints after read_counts
         self.n_long = None    # (rows, pixels) with more than SHPL_LONG_LEN entries; host ints after read_counts
+        self._heavy_len = None
         self.entry_bound = self.capacity   # host-known upper bound on the entries (builders tighten it)
         self.nnz = None       # columns of M per frame (host ints), known after the builder's read-back
         self.n_oob = None     # entries TF-CPU would reject, per frame
@@ -230,6 +231,7 @@ class SparsePoolPlan:
         h = (8 * self.frames + 3) // 4 * 4
         self.n_heavy = (min(int(m[h]), self.heavy_cap), min(int(m[h + 1]), self.heavy_cap))
         self.n_long = (int(c[:, 6].sum()), int(c[:, 7].sum()))
+        self._heavy_len = None
         return c
 
     def heavy_len(self, by_pixel=None):
@@ -239,10 +241,15 @@ class SparsePoolPlan:
         0 when no cell is long (the kernels skip every long-cell path: every KITTI / MV3D plan)."""
         if self.n_long is None or self.n_heavy is None:
             return _cabi.HEAVY_LEN
-        pick = (lambda t: t[0] + t[1]) if by_pixel is None else (lambda t: t[1 if by_pixel else 0])
-        if pick(self.n_heavy) > 0:
-            return _cabi.HEAVY_LEN          # listed cells: left to shpl_pool_heavy; the kernels tune for long runs
-        return _cabi.EXACT_LEN if pick(self.n_long) > 0 else 0     # long but not listed: nothing is left out
+        hl = self._heavy_len
+        if hl is None:
+            def level(n_heavy, n_long):
+                if n_heavy > 0:
+                    return _cabi.HEAVY_LEN      # listed cells: left to shpl_pool_heavy; the kernels tune for long runs
+                return _cabi.EXACT_LEN if n_long > 0 else 0     # long but not listed: nothing is left out
+            h, g = self.n_heavy, self.n_long
+            hl = self._heavy_len = {False: level(h[0], g[0]), True: level(h[1], g[1]), None: level(h[0] + h[1], g[0] + g[1])}
+        return hl[by_pixel]
 
     def heavy(self, by_pixel):
         """(list pointer, device counter pointer, list capacity, how many to expect or None when the counters have
