@@ -27,7 +27,7 @@ def test_quoted_constants_match_the_header():
 
 def test_profile_files_cited_in_the_readme_exist():
     text = read("profiles", "README.md")
-    cited = set(re.findall(r"`((?:r1[a-z]?_|traffic)[A-Za-z0-9_.]*\.(?:json|csv|txt))`", text))
+    cited = set(re.findall(r"`((?:r[12][a-z]?_|traffic)[A-Za-z0-9_.]*\.(?:json|csv|txt|log))`", text))
     assert len(cited) > 20
     # earlier rounds' intermediate files were dropped from the tree on purpose; the README says so where it cites them
     missing = sorted(f for f in cited if not os.path.exists(os.path.join(ROOT, "profiles", f)))
