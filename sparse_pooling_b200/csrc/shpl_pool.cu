@@ -932,6 +932,7 @@ __device__ __noinline__ void pool_entries_staged(const V* __restrict__ src, int 
             if constexpr (kLongRuns) {
                 for (; j + 4 <= j1; j += 4, pp += 4 * nv) {
                     // four products loaded side by side, then added in order: the LDS latency is paid once per four entries
+                    // (loading the next four under the adds was measured slower: it spills at 80 registers)
                     const V t0 = pp[0], t1 = pp[nv], t2 = pp[2 * nv], t3 = pp[3 * nv];
                     acc = vadd(vadd(vadd(vadd(acc, t0), t1), t2), t3);
                 }

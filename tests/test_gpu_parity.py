@@ -568,6 +568,33 @@ def test_staged_entry_walk_is_bit_exact(shpl, C, max_len, bev_hw):
     np.testing.assert_array_equal(tb2.grad[0].cpu().numpy(), gd)
 
 
+@pytest.mark.parametrize("n_cell,n_pix", [(3, 2), (33, 10), (100, 40), (32, 600), (513, 513)])
+def test_long_cell_counters_pick_the_heavy_len(shpl, n_cell, n_pix):
+    """The builder counts the cells / pixels with more than SHPL_LONG_LEN = 32 entries next to the listed ones (counts[6],
+    counts[7]); the drop-in layer turns the counters it reads back into the heavy_len it passes to the pooling entry points:
+    0 (no long cell: the kernels skip every long-cell path), SHPL_EXACT_LEN (long but nothing listed), SHPL_HEAVY_LEN (listed
+    cells).  Whatever the level, the result is the sequential oracle's, bit for bit."""
+    from sparse_pooling_b200 import _cabi
+    d, val, bev, img = _long_cell_case(max(n_cell, n_pix) + 200, n_pix)
+    d["bv_index"][n_cell:, 0] = np.arange(len(d["bv_index"]) - n_cell) % 16        # only the first n_cell pairs share a cell
+    d["bv_index"][n_cell:, 1] = 5 + (np.arange(len(d["bv_index"]) - n_cell) // 16) % 11
+    o = shpl.produce_sparse_pooling_input(d)
+    plan, Mij, flip = o["shpl_plan"], o["Mij_pool"], o["img_index_flip_pool"]
+    rows, pix = np.bincount(Mij[:, 0]), np.bincount(flip[:, 1] * 64 + flip[:, 2])
+    assert plan.n_long == (int((rows > 32).sum()), int((pix > 32).sum()))
+    assert plan.n_heavy == (int((rows > 512).sum()), int((pix > 512).sum()))
+
+    def level(c):
+        return _cabi.HEAVY_LEN if (c > 512).any() else (_cabi.EXACT_LEN if (c > 32).any() else 0)
+    assert (plan.heavy_len(False), plan.heavy_len(True)) == (level(rows), level(pix))
+    assert plan.heavy_len() == level(np.concatenate((rows, pix)))          # the dual entry points: either direction
+    M = shpl.SparseTensor(torch.from_numpy(Mij).cuda(), torch.from_numpy(val).cuda(), o["M_size"])
+    tb, ti = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
+    bv_fused, img_fused = shpl.sparse_pool_layer([tb, ti], [32, 32], M, img_index_flip=torch.from_numpy(flip).cuda(), bv_index=np.zeros((1, 3)))
+    np.testing.assert_array_equal(bv_fused[0].detach().cpu().numpy(), cref.forward(bev[0], img[0], Mij, val, flip))
+    np.testing.assert_array_equal(img_fused[0].detach().cpu().numpy(), cref.forward_trans(img[0], bev[0], Mij, val, flip))
+
+
 @pytest.mark.parametrize("dual", [False, True])
 def test_heavy_cells_use_the_cluster_tree(shpl, dual):
     """Stress (BASELINE config 5, Zipf-like skew): one BEV cell with 30k entries and one pixel with 5k.
