@@ -167,6 +167,7 @@ struct Job {
     int packed;              // sparse: 1 = lane-group entry walk for few vectors per cell (SHPL_PACKED=0 switches it off)
     int long_len;            // sparse: cells with more entries are summed by the stream warps as a whole (kLongRow; 512 when packed)
     int staged;              // sparse, staged instantiation: 2 = every entry CTA takes the staged walk, 1 = only CTAs that meet a long cell
+    int entry_groups;        // sparse, ACC = 2: groups of 8 entry chunks of this job (>= entry_ctas: an entry CTA strides over them)
     int q_slices;            // sparse: warps a cell's channel vectors are spread over (1: a warp sums the whole row)
     int entry_chunk;         // wide: entries per warp
     int tiles;               // narrow: warp tiles; wide: CTA tiles of kWideTile cells
@@ -918,6 +919,8 @@ __device__ __noinline__ void pool_entries_staged(const V* __restrict__ src, int 
         const int carry_row = s_ctl[4 * par], carry_len = s_ctl[4 * par + 1], n_runs = s_ctl[4 * par + 3];
         const V* carry_in = s_carry + par * kStageMaxVecs;
         V* carry_out = s_carry + (par ^ 1) * kStageMaxVecs;
+        // (a thread-per-run mapping for four-vector cells -- the index work once per run -- was measured: it spills at the
+        // 64 registers of the short-run instantiation and doubles the kernel's time, profiles/r2_staged_variants.txt)
         const int pairs = n_runs * nv;
         for (int i = tid; i < pairs; i += kThreads) {
             const int r = shift >= 0 ? (i >> shift) : i / nv;
@@ -1027,9 +1030,14 @@ __global__ void __launch_bounds__(kThreads, (ACC == 1 && kStaged != 2) ? SHPL_SP
         }
         // rows of more than 32 * ACC vectors (MV3D: 192) are spread over q_slices warps, each summing its own slice of
         // the channels over the same entry chunk: the dependent gather rounds of a crowded cell shrink by that factor
-        const int gw = b * kWarps + warp;
-        const int chunk_id = jb.q_slices > 1 ? gw / jb.q_slices : gw;
-        const int q_lo = jb.q_slices > 1 ? (gw - chunk_id * jb.q_slices) * 32 * ACC : 0;
+        // Wide instantiation (ACC = 2): when the grid is a little over one wave the host gives a job fewer entry CTAs than
+        // groups of 8 chunks, and an entry CTA takes several (entry_groups: one wave instead of a wave and a tail, small maps).
+        const int cb_end = ACC == 2 ? jb.entry_groups : b + 1, cb_step = ACC == 2 ? jb.entry_ctas : 1;
+        for (int cb = b; cb < cb_end; cb += cb_step) {
+        const int gw = cb * kWarps + warp;
+        const bool sliced = ACC == 2 && jb.q_slices > 1;              // (compile-time false in the narrow instantiations)
+        const int chunk_id = sliced ? gw / jb.q_slices : gw;
+        const int q_lo = sliced ? (gw - chunk_id * jb.q_slices) * 32 * ACC : 0;
         const int e0 = e_begin + chunk_id * jb.entry_chunk;
         if (e0 >= e_end) return;
         if (ACC == 1 && packed_ok(jb)) {      // few vectors per cell: lane groups gather different entries
@@ -1045,7 +1053,8 @@ __global__ void __launch_bounds__(kThreads, (ACC == 1 && kStaged != 2) ? SHPL_SP
                                 min(e0 + jb.entry_chunk, e_end), e_begin, e_end, pout, jb.pool_out_stride,
                                 kAdd ? din : nullptr, jb.dense_in_stride, jb.vs, jb.ptr,
                                 jb.vs <= 32 ? jb.long_len : jb.heavy_len, lane, jb.n_gather, jb.n_cells,
-                                q_lo, jb.q_slices > 1 ? q_lo + 32 * ACC : 0x7fffffff);
+                                q_lo, sliced ? q_lo + 32 * ACC : 0x7fffffff);
+        }
         return;
     }
     const int stream_ctas = jb.stream_ctas;
@@ -1615,6 +1624,7 @@ int staged_knob() { return SHPL_KNOB("SHPL_STAGED", 1); }
 // staged = 2 (every entry CTA) up to this many vectors per cell, when entries * density > cells
 // -1: by the caller's heavy_len; 1 / 2: force the short-run / long-run staged instantiation (experiments)
 int staged_variant_knob() { return SHPL_KNOB("SHPL_STAGED_VARIANT", -1); }
+int one_wave_knob() { return SHPL_KNOB("SHPL_ONE_WAVE", 1); }
 int q_slices_knob() { return SHPL_KNOB("SHPL_Q_SLICES", 1); }
 int staged_all_vecs_knob() { return SHPL_KNOB("SHPL_STAGED_ALL_VECS", 8); }
 // measured (profiles/r2_staged_ab.txt): 100 k pairs on 560 k cells gain 10 % with every entry CTA staging, 20 k pairs lose 8 %
@@ -1799,10 +1809,35 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
                 if (o.entry_chunk < 4) o.entry_chunk = 4;
             }
             o.q_slices = 1;
-            if (!staged && !packed && o.vs > 64 && q_slices_knob()) o.q_slices = (o.vs + 63) / 64;   // 32 lanes x ACC = 2 vectors per slice
+            if (!staged && !packed && o.vs > 64 && q_slices_knob()) {
+                o.q_slices = (o.vs + 63) / 64;                        // 32 lanes x ACC = 2 vectors per slice
+                // the slices multiply the warps: longer chunks keep their number (measured at MV3D's C = 768, three slices:
+                // 8 entries per warp 32.3 / 25.8 us forward / backward, 24 entries 27.9 / 23.4 us)
+                if (entry_chunk_knob() == 0) o.entry_chunk *= o.q_slices;
+            }
             const long long chunks = ((long long)src_spec[i]->nnz_max + o.entry_chunk - 1) / o.entry_chunk;
             o.entry_ctas = o.vs > 0 ? (int)((chunks * o.q_slices + kWarps - 1) / kWarps) : 0;
+            o.entry_groups = o.entry_ctas;
             a.begin[i + 1] = a.begin[i] + o.entry_ctas + o.stream_ctas;
+        }
+        // Small maps (layer A: 88 x 100 x 256, 574 CTAs on 444 resident slots): a grid a little over one wave runs as a wave
+        // and a tail of stream CTAs waiting behind the entry CTAs.  Fewer entry CTAs, each striding over several groups of
+        // chunks, make it one wave.  Wide instantiation without staging only; grids beyond 1.5 waves are left alone.
+        if (!staged && max_vs > 32 && one_wave_knob()) {
+            const long long resident = (long long)shpl::sm_count() * SHPL_SPARSE_MIN_CTAS_WIDE;
+            long long total = a.begin[a.n_jobs], entry_total = 0;
+            for (int i = 0; i < a.n_jobs; ++i) entry_total += a.job[i].entry_ctas;
+            if (total > resident && total * 2 <= resident * 3 && entry_total > total - resident) {
+                const long long keep = entry_total - (total - resident);          // entry CTAs that fit
+                for (int i = 0; i < a.n_jobs; ++i) {
+                    Job& o = a.job[i];
+                    if (o.entry_ctas > 0) {
+                        long long c = (keep * o.entry_ctas) / entry_total;
+                        o.entry_ctas = (int)(c < 1 ? 1 : c);
+                    }
+                    a.begin[i + 1] = a.begin[i] + o.entry_ctas + o.stream_ctas;
+                }
+            }
         }
         const unsigned g = (unsigned)a.begin[a.n_jobs];
         const bool add = a.job[0].add != 0;
