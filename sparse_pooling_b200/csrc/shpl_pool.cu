@@ -167,7 +167,6 @@ struct Job {
     int packed;              // sparse: 1 = lane-group entry walk for few vectors per cell (SHPL_PACKED=0 switches it off)
     int long_len;            // sparse: cells with more entries are summed by the stream warps as a whole (kLongRow; 512 when packed)
     int staged;              // sparse, staged instantiation: 2 = every entry CTA takes the staged walk, 1 = only CTAs that meet a long cell
-    int entry_groups;        // sparse, ACC = 2: groups of 8 entry chunks of this job (>= entry_ctas: an entry CTA strides over them)
     int q_slices;            // sparse: warps a cell's channel vectors are spread over (1: a warp sums the whole row)
     int entry_chunk;         // wide: entries per warp
     int tiles;               // narrow: warp tiles; wide: CTA tiles of kWideTile cells
@@ -1030,11 +1029,9 @@ __global__ void __launch_bounds__(kThreads, (ACC == 1 && kStaged != 2) ? SHPL_SP
         }
         // rows of more than 32 * ACC vectors (MV3D: 192) are spread over q_slices warps, each summing its own slice of
         // the channels over the same entry chunk: the dependent gather rounds of a crowded cell shrink by that factor
-        // Wide instantiation (ACC = 2): when the grid is a little over one wave the host gives a job fewer entry CTAs than
-        // groups of 8 chunks, and an entry CTA takes several (entry_groups: one wave instead of a wave and a tail, small maps).
-        const int cb_end = ACC == 2 ? jb.entry_groups : b + 1, cb_step = ACC == 2 ? jb.entry_ctas : 1;
-        for (int cb = b; cb < cb_end; cb += cb_step) {
-        const int gw = cb * kWarps + warp;
+        // (Fewer entry CTAs striding over several groups of chunks, so that a grid a little over one wave -- layer A's dual
+        // launch: 574 CTAs on 444 resident slots -- runs as one wave, were measured: forward 21.7 -> 29.9 us. Not adopted.)
+        const int gw = b * kWarps + warp;
         const bool sliced = ACC == 2 && jb.q_slices > 1;              // (compile-time false in the narrow instantiations)
         const int chunk_id = sliced ? gw / jb.q_slices : gw;
         const int q_lo = sliced ? (gw - chunk_id * jb.q_slices) * 32 * ACC : 0;
@@ -1054,7 +1051,6 @@ __global__ void __launch_bounds__(kThreads, (ACC == 1 && kStaged != 2) ? SHPL_SP
                                 kAdd ? din : nullptr, jb.dense_in_stride, jb.vs, jb.ptr,
                                 jb.vs <= 32 ? jb.long_len : jb.heavy_len, lane, jb.n_gather, jb.n_cells,
                                 q_lo, sliced ? q_lo + 32 * ACC : 0x7fffffff);
-        }
         return;
     }
     const int stream_ctas = jb.stream_ctas;
@@ -1624,7 +1620,6 @@ int staged_knob() { return SHPL_KNOB("SHPL_STAGED", 1); }
 // staged = 2 (every entry CTA) up to this many vectors per cell, when entries * density > cells
 // -1: by the caller's heavy_len; 1 / 2: force the short-run / long-run staged instantiation (experiments)
 int staged_variant_knob() { return SHPL_KNOB("SHPL_STAGED_VARIANT", -1); }
-int one_wave_knob() { return SHPL_KNOB("SHPL_ONE_WAVE", 1); }
 int q_slices_knob() { return SHPL_KNOB("SHPL_Q_SLICES", 1); }
 int staged_all_vecs_knob() { return SHPL_KNOB("SHPL_STAGED_ALL_VECS", 8); }
 // measured (profiles/r2_staged_ab.txt): 100 k pairs on 560 k cells gain 10 % with every entry CTA staging, 20 k pairs lose 8 %
@@ -1817,27 +1812,7 @@ int launch_jobs(const JobSpec* specs, int n_specs, cudaStream_t s, const char* w
             }
             const long long chunks = ((long long)src_spec[i]->nnz_max + o.entry_chunk - 1) / o.entry_chunk;
             o.entry_ctas = o.vs > 0 ? (int)((chunks * o.q_slices + kWarps - 1) / kWarps) : 0;
-            o.entry_groups = o.entry_ctas;
             a.begin[i + 1] = a.begin[i] + o.entry_ctas + o.stream_ctas;
-        }
-        // Small maps (layer A: 88 x 100 x 256, 574 CTAs on 444 resident slots): a grid a little over one wave runs as a wave
-        // and a tail of stream CTAs waiting behind the entry CTAs.  Fewer entry CTAs, each striding over several groups of
-        // chunks, make it one wave.  Wide instantiation without staging only; grids beyond 1.5 waves are left alone.
-        if (!staged && max_vs > 32 && one_wave_knob()) {
-            const long long resident = (long long)shpl::sm_count() * SHPL_SPARSE_MIN_CTAS_WIDE;
-            long long total = a.begin[a.n_jobs], entry_total = 0;
-            for (int i = 0; i < a.n_jobs; ++i) entry_total += a.job[i].entry_ctas;
-            if (total > resident && total * 2 <= resident * 3 && entry_total > total - resident) {
-                const long long keep = entry_total - (total - resident);          // entry CTAs that fit
-                for (int i = 0; i < a.n_jobs; ++i) {
-                    Job& o = a.job[i];
-                    if (o.entry_ctas > 0) {
-                        long long c = (keep * o.entry_ctas) / entry_total;
-                        o.entry_ctas = (int)(c < 1 ? 1 : c);
-                    }
-                    a.begin[i + 1] = a.begin[i] + o.entry_ctas + o.stream_ctas;
-                }
-            }
         }
         const unsigned g = (unsigned)a.begin[a.n_jobs];
         const bool add = a.job[0].add != 0;
