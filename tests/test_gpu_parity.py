@@ -427,6 +427,39 @@ def test_full_scan_c128_skewed_rows(shpl):
     np.testing.assert_array_equal(ti.grad[0].cpu().numpy(), gs)
 
 
+@pytest.mark.parametrize("C,skew", [(16, "uniform"), (32, "ground"), (16, "zipf")])
+def test_one_million_pairs_at_the_kitti_map_size(shpl, C, skew):
+    """BASELINE config 5 at its largest: 1 M pairs on the 700 x 800 / 360 x 1200 maps -- the dense regime, where every entry
+    CTA takes the staged walk (uniform: short runs; ground-plane: runs of ~100 entries; Zipf: listed cells, the long-run
+    instantiation beside the split tree).  Forward and backward bit-exact against the plain-C oracle, except the cells above
+    SHPL_EXACT_LEN = 2048 entries (Zipf), which the split tree sums within 1e-5 of the sum of |terms|."""
+    o, val, bev, img = _case(21, 1000000, (700, 800), (360, 1200), C, C, skew, True)
+    Mij, flip = o["Mij_pool"], o["img_index_flip_pool"]
+    M = shpl.SparseTensor(torch.from_numpy(Mij).cuda(), torch.from_numpy(val).cuda(), o["M_size"])
+    tb, ti = torch.from_numpy(bev).cuda().requires_grad_(True), torch.from_numpy(img).cuda().requires_grad_(True)
+    fused, _ = shpl.sparse_pool_layer([tb, ti], [C, C], M, img_index_flip=torch.from_numpy(flip).cuda())
+    got = fused[0].detach().cpu().numpy().reshape(-1, 2 * C)
+    ref = cref.forward(bev[0], img[0], Mij, val, flip).reshape(-1, 2 * C)
+    rows = np.bincount(Mij[:, 0], minlength=700 * 800)
+    tree = rows > 2048
+    np.testing.assert_array_equal(got[~tree], ref[~tree])
+    if tree.any():
+        mag = np.zeros((700 * 800, C))
+        src = img[0].reshape(-1, C)[flip[:, 1] * 1200 + flip[:, 2]]
+        np.add.at(mag, Mij[:, 0], np.abs(val[:, None].astype(np.float64) * src))
+        err = np.abs(got[tree, C:].astype(np.float64) - ref[tree, C:])
+        assert float((err / np.maximum(mag[tree], 1e-30)).max()) <= 1e-5
+        np.testing.assert_array_equal(got[tree, :C], ref[tree, :C])
+    del ref, got
+    g = np.random.default_rng(4).standard_normal((700, 800, 2 * C), dtype=np.float32)
+    fused.backward(torch.from_numpy(g[None]).cuda())
+    gd, gs = cref.backward(g, Mij, val, flip, C, (360, 1200, C))
+    np.testing.assert_array_equal(tb.grad[0].cpu().numpy(), gd)
+    pix = np.bincount(flip[:, 1] * 1200 + flip[:, 2], minlength=360 * 1200)
+    assert pix.max() <= 2048                                    # the transposed direction has no tree cell: bit-exact
+    np.testing.assert_array_equal(ti.grad[0].cpu().numpy(), gs)
+
+
 def _long_cell_case(n, n_same_pixel, seed=12):
     rng = np.random.default_rng(seed)
     u = rng.integers(0, 64, n)
