@@ -248,7 +248,8 @@ int shpl_pool_backward_dual(const float* g_fused_bev, const float* g_fused_img,
  * side, then the group sums in order) -- a fixed tree that depends only on L (deterministic, within 1e-5 of the sum of
  * |terms|; not bit-identical to the sequential sum).  The Zipf stress case's
  * 178 000-entry cell runs on ~90 SMs instead of 8.  Cells up to SHPL_EXACT_LEN entries take the exact cluster kernel as
- * in shpl_pool_heavy.  nnz_max >= total entries of the plan; workspace: shpl_pool_heavy_workspace_bytes(C, nnz_max,
+ * in shpl_pool_heavy -- for C > 128; for C <= 128 the main kernels have summed them already (see shpl_pool_forward) and
+ * both heavy entry points skip them.  nnz_max >= total entries of the plan; workspace: shpl_pool_heavy_workspace_bytes(C, nnz_max,
  * list_cap) bytes, 16-byte aligned.  (More than 4096 listed cells: falls back to shpl_pool_heavy's cluster tree.) */
 size_t shpl_pool_heavy_workspace_bytes(int32_t C, int64_t nnz_max, int32_t list_cap);
 int shpl_pool_heavy_split(const float* gather_in, int32_t gather_stride, int32_t C,
