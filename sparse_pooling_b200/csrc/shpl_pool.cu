@@ -920,35 +920,10 @@ __device__ __noinline__ void pool_entries_staged(const V* __restrict__ src, int 
         V* carry_out = s_carry + (par ^ 1) * kStageMaxVecs;
         // (a thread-per-run mapping for four-vector cells -- the index work once per run -- was measured: it spills at the
         // 64 registers of the short-run instantiation and doubles the kernel's time, profiles/r2_staged_variants.txt)
-#ifdef SHPL_STAGED_PHASEC_SPLIT
-        // interior runs (neither the first nor the last of the batch) are complete and start from zero: a lean loop without
-        // the carry / completeness logic; the two edge runs take the general body below
-        if constexpr (!kLongRuns) {
-            const int inner = (n_runs - 2) * nv;
-            for (int i = tid; i < inner; i += kThreads) {
-                const int r = 1 + (shift >= 0 ? (i >> shift) : i / nv);
-                const int q = i - (r - 1) * nv;
-                const int j0 = s_run[r], j1 = s_run[r + 1];
-                const int row = s_key[j0];
-                V acc = vzero((V*)nullptr);
-                const V* pp = s_prod + j0 * nv + q;
-                for (int j = j0; j < j1; ++j, pp += nv) acc = vadd(acc, *pp);
-                if (!(heavy_len > 0 && j1 - j0 > heavy_len)) {
-                    if constexpr (kAdd) acc = vadd(ld_stream(addend + (size_t)row * add_stride + q), acc);
-                    st_stream(out + (size_t)row * out_stride + q, acc);
-                }
-            }
-        }
-        const int pairs = kLongRuns ? n_runs * nv : (n_runs > 1 ? 2 * nv : nv);
-        for (int i0 = tid; i0 < pairs; i0 += kThreads) {
-            const int r = kLongRuns ? (shift >= 0 ? (i0 >> shift) : i0 / nv) : (i0 < nv ? 0 : n_runs - 1);
-            const int q = kLongRuns ? i0 - r * nv : (i0 < nv ? i0 : i0 - nv);
-#else
         const int pairs = n_runs * nv;
         for (int i = tid; i < pairs; i += kThreads) {
             const int r = shift >= 0 ? (i >> shift) : i / nv;
             const int q = i - r * nv;
-#endif
             const int j0 = s_run[r], j1 = s_run[r + 1];
             const int row = s_key[j0];
             const bool cont = r == 0 && row == carry_row;
