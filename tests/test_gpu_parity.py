@@ -628,6 +628,34 @@ def test_long_cell_counters_pick_the_heavy_len(shpl, n_cell, n_pix):
     np.testing.assert_array_equal(img_fused[0].detach().cpu().numpy(), cref.forward_trans(img[0], bev[0], Mij, val, flip))
 
 
+@pytest.mark.parametrize("C", [32, 128, 256])
+def test_main_and_heavy_entry_points_agree_on_who_sums_a_listed_cell(shpl, C):
+    """Bare C ABI, the un-split heavy entry point: a listed cell of 1300 entries is summed by the main kernel (staged walk)
+    for C <= 128 and by shpl_pool_heavy's exact cluster kernel above -- never by both, never by neither: the rule depends
+    on C alone.  Either way the sequential sum, bit for bit."""
+    import ctypes
+    from sparse_pooling_b200 import _cabi, ops
+    d, val, bev, img = _long_cell_case(1300, 40)
+    o = shpl.produce_sparse_pooling_input(d)
+    plan, Mij, flip = o["shpl_plan"], o["Mij_pool"], o["img_index_flip_pool"]
+    assert plan.n_heavy[0] == 1
+    rng = np.random.default_rng(C)
+    bev = rng.standard_normal((16 * 16, C), dtype=np.float32)
+    img = rng.standard_normal((32 * 64, C), dtype=np.float32)
+    tb, ti = torch.from_numpy(bev).cuda(), torch.from_numpy(img).cuda()
+    fused = torch.full((16 * 16, 2 * C), float("nan"), device="cuda")
+    ptr, key, idx, v, nnz_max, heavy, _ = plan.by_row()
+    P = ops._ptr
+    rc = _cabi.lib.shpl_pool_forward(P(tb), P(ti), ptr, key, idx, v, int(nnz_max), _cabi.HEAVY_LEN, 16 * 16, C, 32 * 64, C, P(fused), ops._stream())
+    _cabi.check(rc, "shpl_pool_forward")
+    lst, count_dev, cap = heavy[0], heavy[1], heavy[2]
+    rc = _cabi.lib.shpl_pool_heavy(P(ti), C, C, ptr, idx, v, lst, count_dev, int(cap), None, 0,
+                                   ctypes.c_void_p(fused.data_ptr() + 4 * C), 2 * C, ops._stream())
+    _cabi.check(rc, "shpl_pool_heavy")
+    ref = cref.forward(bev.reshape(16, 16, C), img.reshape(32, 64, C), Mij, np.ones(len(Mij), np.float32), flip).reshape(-1, 2 * C)
+    np.testing.assert_array_equal(fused.cpu().numpy(), ref)
+
+
 @pytest.mark.parametrize("dual", [False, True])
 def test_heavy_cells_use_the_cluster_tree(shpl, dual):
     """Stress (BASELINE config 5, Zipf-like skew): one BEV cell with 30k entries and one pixel with 5k.
