@@ -820,6 +820,7 @@ __global__ void __launch_bounds__(kThreads, SHPL_WIDE_MIN_CTAS) shpl_pool_wide_k
 constexpr int kStageVecs = 2048;          // product vectors per batch (32 KB of float4)
 constexpr int kStageEntries = 512;        // entries per batch at most
 constexpr int kStageMaxVecs = 64;         // channel vectors per cell the staged walk takes (batch >= 32 entries)
+constexpr int kStageLongSplit = 64;       // long-run instantiation: runs of this many entries of a batch are added one thread per scalar
 
 template <typename V> constexpr int stage_smem_bytes() {
     return (kStageVecs + 2 * kStageMaxVecs) * (int)sizeof(V) + (4 * kStageEntries + 2 + 32) * 4;
@@ -841,6 +842,7 @@ __device__ __noinline__ void pool_entries_staged(const V* __restrict__ src, int 
     int* s_run = reinterpret_cast<int*>(s_val + kStageEntries);         // [kStageEntries + 1] run starts
     int* s_wtot = s_run + kStageEntries + 1;                            // [8] run heads per warp
     int* s_ctl = s_wtot + 8;                                            // [2][4]: carry_row, carry_len, next_pos, n_runs
+    int* s_long = s_ctl + 8;                                            // [0]: count, [1..8]: long runs of the batch (kLongRuns)
 
     int start = E0;
     if (E0 > e_begin) start = __ldg(ptr + __ldg(key + E0 - 1) + 1);     // the end of the cell running into this chunk
@@ -907,6 +909,7 @@ __device__ __noinline__ void pool_entries_staged(const V* __restrict__ src, int 
             if (tid == 0) {
                 s_run[all] = n;
                 s_ctl[4 * par + 3] = all;
+                if constexpr (kLongRuns) s_long[0] = 0;
             }
         }
         // ---- phase A (products, in entry order)
@@ -932,9 +935,12 @@ __device__ __noinline__ void pool_entries_staged(const V* __restrict__ src, int 
             const V* pp = s_prod + j0 * nv + q;
             int j = j0;
             if constexpr (kLongRuns) {
+                if (j1 - j0 >= kStageLongSplit) {          // summed below, one thread per scalar channel
+                    if (q == 0) s_long[1 + atomicAdd(s_long, 1)] = r;
+                    continue;
+                }
                 for (; j + 4 <= j1; j += 4, pp += 4 * nv) {
                     // four products loaded side by side, then added in order: the LDS latency is paid once per four entries
-                    // (loading the next four under the adds was measured slower: it spills at 80 registers)
                     const V t0 = pp[0], t1 = pp[nv], t2 = pp[2 * nv], t3 = pp[3 * nv];
                     acc = vadd(vadd(vadd(vadd(acc, t0), t1), t2), t3);
                 }
@@ -949,14 +955,62 @@ __device__ __noinline__ void pool_entries_staged(const V* __restrict__ src, int 
                 carry_out[q] = acc;
             }
         }
+        if constexpr (kLongRuns) {
+            // Runs of kStageLongSplit entries or more: the chain of additions (4 cycles each) is their only serial part.  One
+            // thread per SCALAR channel (four times the threads of the vector mapping, and eight registers of double buffer
+            // instead of thirty-two): the next four products are loaded from shared memory while the current four are added,
+            // so no LDS latency sits on the chain.  Same additions in the same order, component by component.
+            __syncthreads();
+            const int n_long = s_long[0];
+            constexpr int WF = (int)(sizeof(V) / sizeof(float));
+            const int ncs = nv * WF;                                    // scalar channels per cell
+            const float* carry_in_f = reinterpret_cast<const float*>(carry_in);
+            float* carry_out_f = reinterpret_cast<float*>(carry_out);
+            for (int i = tid; i < n_long * ncs; i += kThreads) {
+                const int li = i / ncs, c = i - li * ncs;
+                const int r = s_long[1 + li];
+                const int j0 = s_run[r], j1 = s_run[r + 1];
+                const int row = s_key[j0];
+                const bool cont = r == 0 && row == carry_row;
+                float acc = cont ? carry_in_f[c] : 0.f;
+                const int len = (cont ? carry_len : 0) + (j1 - j0);
+                const float* pp = reinterpret_cast<const float*>(s_prod + j0 * nv) + c;
+                int j = j0 + 4;                                         // j1 - j0 >= kStageLongSplit >= 4
+                float a0 = pp[0], a1 = pp[ncs], a2 = pp[2 * ncs], a3 = pp[3 * ncs];
+                pp += 4 * ncs;
+                for (; j + 4 <= j1; j += 4, pp += 4 * ncs) {
+                    const float b0 = pp[0], b1 = pp[ncs], b2 = pp[2 * ncs], b3 = pp[3 * ncs];
+                    acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, a0), a1), a2), a3);
+                    a0 = b0; a1 = b1; a2 = b2; a3 = b3;
+                }
+                acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, a0), a1), a2), a3);
+                for (; j < j1; ++j, pp += ncs) acc = __fadd_rn(acc, *pp);
+                if (s_key[j1] != row) {                                 // the cell ends inside the batch
+                    if (!(heavy_len > 0 && len > heavy_len)) {
+                        if constexpr (kAdd) acc = __fadd_rn(__ldcs(reinterpret_cast<const float*>(addend + (size_t)row * add_stride) + c), acc);
+                        __stcs(reinterpret_cast<float*>(out + (size_t)row * out_stride) + c, acc);
+                    }
+                } else {
+                    carry_out_f[c] = acc;
+                }
+            }
+        }
         if (tid == 0) {
             const int j0 = s_run[n_runs - 1];
             const int row = s_key[j0];
             int nrow = -1, nlen = 0, npos = pos + n;
             if (s_key[n] == row) {                                      // open run: carried into the next batch
-                nlen = ((n_runs == 1 && row == carry_row) ? carry_len : 0) + (n - j0);
+                const bool first_open = !(n_runs == 1 && row == carry_row);
+                nlen = (first_open ? 0 : carry_len) + (n - j0);
                 nrow = row;
-                if (heavy_len > 0 && nlen > heavy_len) {                // a heavy cell: dropped, skipped
+                bool heavy = heavy_len > 0 && nlen > heavy_len;
+                if constexpr (kLongRuns) {
+                    // plans with listed cells: the first time a long run runs past a batch, one look at the cell's length --
+                    // a heavy cell is skipped at once instead of after heavy_len + B gathered entries (five batches at C = 16)
+                    if (!heavy && heavy_len > 0 && first_open && n - j0 >= kStageLongSplit)
+                        heavy = __ldg(ptr + row + 1) - __ldg(ptr + row) > heavy_len;
+                }
+                if (heavy) {                                            // a heavy cell: dropped, skipped
                     nrow = -1;
                     npos = __ldg(ptr + row + 1);
                 }
@@ -986,7 +1040,10 @@ __host__ __device__ __forceinline__ bool packed_ok(const Job& jb) { return jb.vs
 // the add loop unrolled by four).  Measured (profiles/r2_staged_variants.txt): 1 M uniform pairs C = 16 41.7 us with 1, 56.2 us
 // with 2; 100 k Zipf pairs C = 16 66.9 us with 1, 41.4 us with 2.
 template <int W, bool kAdd, int ACC, int kStaged = 0>
-__global__ void __launch_bounds__(kThreads, (ACC == 1 && kStaged != 2) ? SHPL_SPARSE_MIN_CTAS : SHPL_SPARSE_MIN_CTAS_WIDE) shpl_pool_sparse_kernel(PoolArgs a) {
+#ifndef SHPL_LONG_RUN_MIN_CTAS
+#define SHPL_LONG_RUN_MIN_CTAS SHPL_SPARSE_MIN_CTAS_WIDE
+#endif
+__global__ void __launch_bounds__(kThreads, ACC == 1 ? (kStaged != 2 ? SHPL_SPARSE_MIN_CTAS : SHPL_LONG_RUN_MIN_CTAS) : SHPL_SPARSE_MIN_CTAS_WIDE) shpl_pool_sparse_kernel(PoolArgs a) {
     using V = typename VecOf<W>::type;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
