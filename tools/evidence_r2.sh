@@ -29,7 +29,7 @@ reduce ${tag}_pool_kernels
 fi
 if [[ $want == *s* ]]; then       # the config-5 sweep and captures of the staged instantiations
 python tools/sweep.py --full > gpurun_out/${tag}_stress_sweep_full.json 2> gpurun_out/${tag}_sweep.err
-for c in "1000000 16 uniform" "100000 64 zipf"; do
+for c in "1000000 16 uniform" "100000 64 zipf" "1000000 16 zipf"; do
 t=$(echo $c | tr ' ' '_')
 S="python tools/one_case.py $c"
 $S > gpurun_out/${tag}_case_$t.json 2>&1 &&
