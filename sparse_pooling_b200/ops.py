@@ -180,15 +180,27 @@ class SparsePoolPlan:
     def n_src(self):
         return self.src_per_frame * self.frames
 
+    def _by(self, by_pixel):
+        # the argument tuple of one direction, cached until the entry bound or the counters change (a hot-path call per
+        # forward and per backward: building it costs ~5 us of ctypes objects)
+        state = (self.entry_bound, self.n_heavy, self.n_long)
+        c = self.__dict__.get("_by_cache")
+        if c is None or c[0] != state:
+            c = self.__dict__["_by_cache"] = (state, {})
+        t = c[1].get(by_pixel)
+        if t is None:
+            p = self.ptrs8()
+            o = 4 if by_pixel else 0
+            t = c[1][by_pixel] = (p[o], p[o + 1], p[o + 2], p[o + 3], self.entry_bound, self.heavy(by_pixel), self.heavy_len(by_pixel))
+        return t
+
     def by_row(self):
         """(ptr, key, idx, val, nnz_max, heavy list, heavy_len) of the CSR keyed by destination BEV cell."""
-        p = self.ptrs8()
-        return (p[0], p[1], p[2], p[3], self.entry_bound, self.heavy(False), self.heavy_len(False))
+        return self._by(False)
 
     def by_pixel(self):
         """(ptr, key, idx, val, nnz_max, heavy list, heavy_len) of the CSR^T keyed by source pixel."""
-        p = self.ptrs8()
-        return (p[4], p[5], p[6], p[7], self.entry_bound, self.heavy(True), self.heavy_len(True))
+        return self._by(True)
 
     def frame_struct(self, f):
         """shpl_plan for frame f: ptr arrays point at the frame's sub-array; entry arrays are shared."""
