@@ -314,6 +314,7 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
         //   tile i+1: bits -> every thread tests its nine neighbours and issues the (few) CSR-offset loads, predicated
         //   end of tile i: offsets -> Z rows of tile i+1, each (one 128-byte line) prefetched into L1
         if (a.busy != nullptr && n_mine > 0) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");           // the Z kernel's rows and bitmap (no-op without PDL)
             const int sw = warp - 10;
             const int r = sw * 32 + lane;                                // staging row = output pixel of the tile
             const bool px_ok = r < kOutRows;
@@ -503,9 +504,12 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
 // W is the slim.conv2d variable, HWIO [3][3][c_in_total][c_out_total].  forward: B[n = co][k = ci] = W[tap][ci_off + ci][co];
 // transposed (input gradient, SAME padding, stride 1): B[n = ci][k = co] = W[8 - tap][ci_off + ci][co].
 // gridDim.y = 2 preps a second block of 32 input channels (ci_off2 -> wprep2) in the same launch.
+// zero[0 .. zero_words) is cleared by the same launch (the forward's bitmap of cells that receive pooled features).
 __global__ void shpl_conv_prep_kernel(const float* __restrict__ w, int c_in_total, int c_out_total, int ci_off, int transposed,
-                                      float* __restrict__ wprep, int ci_off2 = 0, float* __restrict__ wprep2 = nullptr) {
+                                      float* __restrict__ wprep, int ci_off2 = 0, float* __restrict__ wprep2 = nullptr,
+                                      uint32_t* __restrict__ zero = nullptr, int zero_words = 0) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;     // over [3 dy][8 chunks][192][4]
+    for (int z = blockIdx.y * gridDim.x * blockDim.x + i; z < zero_words; z += gridDim.x * gridDim.y * blockDim.x) zero[z] = 0u;
     if (i >= kWElems) return;
     if (blockIdx.y == 1) {
         ci_off = ci_off2;
@@ -549,12 +553,21 @@ struct ZArgs {
     int n_rows, nnz_max;
     float* Z;                    // [nnz_max][9][32]
     uint32_t* busy;              // tensor-core form: the bitmap of the cells that receive pooled features is set here too
+    int rows_per_tile;           // tensor-core form: entries a CTA takes per tile (multiple of 8, 8 .. 128)
 };
 
-// Tensor-core form (C_s = 32): a CTA takes 128 consecutive entries; row m of the MMA is entry e0 + m, holding the
-// pooled vector of its cell if the entry is the cell's first (entries in stored order, two roundings each -- the
-// pooling kernels' sum), zeros otherwise.  3xTF32 like the dense kernel: A_hi.B_hi + A_hi.B_lo + A_lo.B_hi into
-// 288 TMEM columns = [tap][co], the layout of a Z row.
+// Tensor-core form (C_s = 32): a CTA takes rows_per_tile <= 128 consecutive entries per tile -- the host sizes the tiles so
+// that the entries spread over two CTAs on every SM; the per-entry work (gather, Z row store) is what costs, the MMA is
+// 128 rows wide whatever the tile holds.  Entry r of the tile is row m(r) = (r & 3) * 32 + (r >> 2) of the MMA (the four
+// TMEM lane quarters, and with them the eight epilogue warps, share the rows evenly), holding the pooled vector of its
+// cell if the entry is the cell's first (entries in stored order, two roundings each -- the pooling kernels' sum);
+// other rows are never stored.  3xTF32 like the dense kernel: A_hi.B_hi + A_hi.B_lo + A_lo.B_hi into 288 TMEM columns
+// = [tap][co], the layout of a Z row.  The epilogue transposes 4 x 4 blocks of float4 inside lane quads so that a
+// store instruction writes 64 contiguous bytes per quad instead of 16 bytes per row.
+#ifndef SHPL_CONV_PDL
+#define SHPL_CONV_PDL 1
+#endif
+constexpr bool kConvPdl = SHPL_CONV_PDL != 0;
 constexpr int kZtcThreads = 256;
 constexpr int kZtcPitch = 128 * 16 + 16;                 // bytes between channel chunks of the A planes
 constexpr int kZtcPlane = kChunks * kZtcPitch;
@@ -571,7 +584,9 @@ __global__ void __launch_bounds__(kZtcThreads, 2) shpl_conv_z_tc_kernel(ZArgs a)
     extern __shared__ uint8_t z_smem_raw[];
     __shared__ uint32_t tmem_slot;
     const int e_begin = __ldg(a.ptr), e_end = min(__ldg(a.ptr + a.n_rows), e_begin + a.nnz_max);
-    const int n_tiles = (e_end - e_begin + 127) / 128;
+    asm volatile("griddepcontrol.launch_dependents;");    // the dense kernel may take the SMs as this grid leaves them
+    const int rpt = a.rows_per_tile, rpw = rpt >> 3;       // entries per tile, per warp (<= 16)
+    const int n_tiles = (e_end - e_begin + rpt - 1) / rpt;
     if ((int)blockIdx.x >= n_tiles) return;               // whole CTA: nnz_max is only an upper bound
     const uint32_t raw = smem_u32(z_smem_raw);
     const uint32_t base = (raw + 127u) & ~127u;
@@ -596,14 +611,14 @@ __global__ void __launch_bounds__(kZtcThreads, 2) shpl_conv_z_tc_kernel(ZArgs a)
     const uint32_t tmem = tmem_slot;
     int it = 0;
     for (int tile = (int)blockIdx.x; tile < n_tiles; tile += (int)gridDim.x, ++it) {
-        const int e0 = e_begin + tile * 128;
-        // ---- gather: warp w fills rows 16w .. 16w+15 (entries ew .. ew+15); lane = channel
+        const int e0 = e_begin + tile * rpt;
+        // ---- gather: warp w fills the rows of entries ew .. ew + rpw - 1; lane = channel
         {
-            const int ew = e0 + warp * 16;
+            const int r0 = warp * rpw, ew = e0 + r0;
             int k_l = ew + lane, key_l = -1, idx_l = 0, end_l = 0;
             float val_l = 0.f;
             bool first_l = false;
-            if (lane < 16 && k_l < e_end) {
+            if (lane < rpw && k_l < e_end) {
                 key_l = __ldg(a.key + k_l);
                 idx_l = __ldg(a.idx + k_l);
                 val_l = __ldg(a.val + k_l);
@@ -615,44 +630,44 @@ __global__ void __launch_bounds__(kZtcThreads, 2) shpl_conv_z_tc_kernel(ZArgs a)
             }
             float x[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {                    // the 16 gathered rows in flight together
+            for (int j = 0; j < 16; ++j) {                    // the gathered rows in flight together
                 const int p = __shfl_sync(0xffffffffu, idx_l, j);
-                SHPL_DASSERT(ew + j >= e_end || p >= 0);
-            x[j] = (ew + j < e_end) ? __ldg(a.src + (size_t)p * 32 + lane) : 0.f;
+                SHPL_DASSERT(j >= rpw || ew + j >= e_end || p >= 0);
+                x[j] = (j < rpw && ew + j < e_end) ? __ldg(a.src + (size_t)p * 32 + lane) : 0.f;
             }
             const unsigned firsts = __ballot_sync(0xffffffffu, first_l) & 0xffffu;
             uint8_t* hi_p = gbase + kZtcSmA + (lane >> 2) * kZtcPitch + (lane & 3) * 4;
             uint8_t* lo_p = hi_p + kZtcPlane;
+            auto put = [&](int j, float acc) {                // the pooled vector of the cell whose first entry is ew + j
+                const int r = r0 + j, m = (r & 3) * 32 + (r >> 2);
+                const float h = __uint_as_float(__float_as_uint(acc) & 0xffffe000u);
+                *reinterpret_cast<float*>(hi_p + m * 16) = h;
+                *reinterpret_cast<float*>(lo_p + m * 16) = acc - h;
+            };
             float acc = 0.f;
             int open = -1, open_end = 0;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const bool fj = (firsts >> j) & 1u;
-                if (fj) {
-                    if (open >= 0) {                          // the previous cell ended inside the window
-                        const float h = __uint_as_float(__float_as_uint(acc) & 0xffffe000u);
-                        *reinterpret_cast<float*>(hi_p + (warp * 16 + open) * 16) = h;
-                        *reinterpret_cast<float*>(lo_p + (warp * 16 + open) * 16) = acc - h;
+                if (j < rpw) {
+                    if ((firsts >> j) & 1u) {
+                        if (open >= 0) put(open, acc);            // the previous cell ended inside the window
+                        open = j;
+                        open_end = __shfl_sync(0xffffffffu, end_l, j);
+                        acc = 0.f;
                     }
-                    open = j;
-                    open_end = __shfl_sync(0xffffffffu, end_l, j);
-                    acc = 0.f;
-                }
-                if (open >= 0 && ew + j < open_end)
-                    acc = __fadd_rn(acc, __fmul_rn(__shfl_sync(0xffffffffu, val_l, j), x[j]));
-                if (!fj) {                                    // not a first entry: an all-zero row
-                    *reinterpret_cast<float*>(hi_p + (warp * 16 + j) * 16) = 0.f;
-                    *reinterpret_cast<float*>(lo_p + (warp * 16 + j) * 16) = 0.f;
+                    if (open >= 0 && ew + j < open_end)
+                        acc = __fadd_rn(acc, __fmul_rn(__shfl_sync(0xffffffffu, val_l, j), x[j]));
                 }
             }
             if (open >= 0) {
-                for (int k = ew + 16; k < open_end; ++k)      // the last cell runs on past the window
+                for (int k = ew + rpw; k < open_end; ++k)     // the last cell runs on past the window
                     acc = __fadd_rn(acc, __fmul_rn(__ldg(a.val + k), __ldg(a.src + (size_t)__ldg(a.idx + k) * 32 + lane)));
-                const float h = __uint_as_float(__float_as_uint(acc) & 0xffffe000u);
-                *reinterpret_cast<float*>(hi_p + (warp * 16 + open) * 16) = h;
-                *reinterpret_cast<float*>(lo_p + (warp * 16 + open) * 16) = acc - h;
+                put(open, acc);
             }
-            if (lane < 16) flags[warp * 16 + lane] = first_l ? 1 : 0;
+            if (lane < rpw) {
+                const int r = r0 + lane;
+                flags[(r & 3) * 32 + (r >> 2)] = first_l ? 1 : 0;
+            }
         }
         fence_proxy_async();
         tc_fence_before();
@@ -687,11 +702,38 @@ __global__ void __launch_bounds__(kZtcThreads, 2) shpl_conv_z_tc_kernel(ZArgs a)
             tc_fence_after();
             {
                 const int q = warp & 3, half = warp >> 2;
-                const int m = q * 32 + lane;
-                const bool on = flags[m] != 0;
-                float* zrow = a.Z + (size_t)(e0 - e_begin + m) * 288 + dy0 * 96;
+                const int sub = lane & 3, l0 = lane & ~3;     // lane quad: after the transpose this thread holds float4 `sub`
+                // of the rows of lanes l0 .. l0 + 3 = entries (l0 + i) * 4 + q of the tile
+                const uint32_t f4 = *reinterpret_cast<const uint32_t*>(flags + q * 32 + l0);
+                bool on[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) on[i] = ((f4 >> (8 * i)) & 0xffu) != 0u && (l0 + i) * 4 + q < rpt;
+                float* zq = a.Z + (size_t)(e0 - e_begin + l0 * 4 + q) * 288 + dy0 * 96 + sub * 4;
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
                 const int n16 = ndy * 3;                      // 16-column chunks per half (96 or 48 columns)
+                auto quad_transpose = [&](uint32_t (&v)[16]) {  // unit = 4 registers (16 columns = 4 units per lane)
+#pragma unroll
+                    for (int mask = 1; mask <= 2; mask <<= 1) {
+                        const bool upper = (sub & mask) != 0;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (u & mask) continue;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint32_t lo = v[4 * u + k], hi = v[4 * (u | mask) + k];
+                                const uint32_t got = __shfl_xor_sync(0xffffffffu, upper ? lo : hi, mask);
+                                if (upper) v[4 * u + k] = got; else v[4 * (u | mask) + k] = got;
+                            }
+                        }
+                    }
+                };
+                auto put16 = [&](const uint32_t (&v)[16], int col) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (on[i])
+                            *reinterpret_cast<float4*>(zq + (size_t)i * (4 * 288) + col) = make_float4(
+                                __uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                };
                 for (int cc = 0; cc < n16; cc += 2) {         // two chunks (32 columns) per TMEM round trip
                     const int col = half * n16 * 16 + cc * 16;
                     const bool two = cc + 1 < n16;
@@ -699,17 +741,11 @@ __global__ void __launch_bounds__(kZtcThreads, 2) shpl_conv_z_tc_kernel(ZArgs a)
                     SHPL_TMEM_LD16(taddr + col, va);
                     if (two) SHPL_TMEM_LD16(taddr + col + 16, vb);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (on) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            *reinterpret_cast<float4*>(zrow + col + 4 * k) = make_float4(__uint_as_float(va[4 * k]), __uint_as_float(va[4 * k + 1]),
-                                                                                        __uint_as_float(va[4 * k + 2]), __uint_as_float(va[4 * k + 3]));
-                        if (two) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                *reinterpret_cast<float4*>(zrow + col + 16 + 4 * k) = make_float4(__uint_as_float(vb[4 * k]), __uint_as_float(vb[4 * k + 1]),
-                                                                                                 __uint_as_float(vb[4 * k + 2]), __uint_as_float(vb[4 * k + 3]));
-                        }
+                    quad_transpose(va);
+                    put16(va, col);
+                    if (two) {
+                        quad_transpose(vb);
+                        put16(vb, col + 16);
                     }
                 }
             }
@@ -1095,7 +1131,19 @@ int launch_dense(const float* in, int in_pitch, float* out, const float* wprep, 
         attr_set = true;
     }
     const int grid = a.n_tiles < shpl::sm_count() ? a.n_tiles : shpl::sm_count();
-    shpl_conv3x3_dense_kernel<<<grid, kConvThreads, kConvSmem, s>>>(map_in, map_out, a);
+    // After the Z kernel the launch is a programmatic dependent one: the CTAs start as the Z kernel's CTAs leave their SMs
+    // and run the dense half at once; only the sparse warps wait (griddepcontrol.wait) for the Z rows and the bitmap.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = kConvSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (kConvPdl && busy != nullptr) ? 1 : 0;
+    SHPL_CUDA_OK(cudaLaunchKernelEx(&cfg, shpl_conv3x3_dense_kernel, map_in, map_out, a));
     shpl::count_launches(1);
     return shpl::check_launch("shpl_conv3x3_dense_kernel");
 }
@@ -1130,11 +1178,11 @@ extern "C" int shpl_pool_conv3x3_forward(const float* dst, const float* src, con
     const int c_in_total = C_d + C_s;
     const bool sparse = C_s > 0 && nnz_max > 0;
     const bool z_tc = sparse && C_s == kC;        // the pooled half's weights are prepped by the same launch
-    shpl_conv_prep_kernel<<<dim3((kWElems + 255) / 256, z_tc ? 2 : 1), 256, 0, s>>>(weight, c_in_total, C_out, 0, 0, c.wprep, C_d, c.wprep_p);
+    shpl_conv_prep_kernel<<<dim3((kWElems + 255) / 256, z_tc ? 2 : 1), 256, 0, s>>>(weight, c_in_total, C_out, 0, 0, c.wprep, C_d, c.wprep_p,
+                                                                                   sparse ? c.busy : nullptr, sparse ? (int)c.words : 0);
     shpl::count_launches(1);
     if (int rc = shpl::check_launch("shpl_conv_prep_kernel")) return rc;
     if (sparse) {
-        SHPL_CUDA_OK(cudaMemsetAsync(c.busy, 0, c.words * 4, s));
         if (!z_tc) {      // the tensor-core Z kernel sets the bitmap itself
             shpl_conv_mark_kernel<<<(nnz_max + 255) / 256, 256, 0, s>>>(ptr, key, (int)cells, nnz_max, c.busy);
             shpl::count_launches(1);
@@ -1162,8 +1210,13 @@ extern "C" int shpl_pool_conv3x3_forward(const float* dst, const float* src, con
                 SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_conv_z_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kZtcSmemRequest));
                 z_attr = true;
             }
-            const int ztiles = (nnz_max + 127) / 128;
-            shpl_conv_z_tc_kernel<<<ztiles < 2 * shpl::sm_count() ? ztiles : 2 * shpl::sm_count(), kZtcThreads, kZtcSmemRequest, s>>>(za);
+            // tiles sized so that the entries spread over two CTAs on every SM (the per-entry work is what costs)
+            const int slots = 2 * shpl::sm_count();
+            int rpt = ((nnz_max + slots - 1) / slots + 7) & ~7;
+            rpt = rpt < 32 ? 32 : rpt > 128 ? 128 : rpt;
+            za.rows_per_tile = rpt;
+            const int ztiles = (nnz_max + rpt - 1) / rpt;
+            shpl_conv_z_tc_kernel<<<ztiles < slots ? ztiles : slots, kZtcThreads, kZtcSmemRequest, s>>>(za);
             shpl::count_launches(1);
             if (int rc = shpl::check_launch("shpl_conv_z_tc_kernel")) return rc;
         } else {
