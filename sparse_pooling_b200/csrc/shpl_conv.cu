@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(kZThreads, 3) shpl_conv_z_kernel(ZArgs a) {
 //   g_pooled = the same for the pooled channels, only at the cells that receive pooled features (shpl_conv_gp_kernel),
 //   g_src    = transpose-CSR gather of g_pooled                       -> shpl_pool_backward_from on a remapped index
 //   g_W[t][ci][co] = sum_p x[p + off(t)][ci] * g_out[p][co]           -> dense channels: shpl_conv_gwd_kernel (a pixel
-//                    reduction, FFMA, per-CTA partial sums combined in order); pooled channels: shpl_conv_gwp_kernel
+//                    reduction, FFMA, per-CTA partial sums combined in order); pooled channels: inside shpl_conv_gp_kernel
 // All sums run in a fixed order: deterministic.
 struct GpArgs {
     const float* src;
@@ -862,39 +862,154 @@ struct GpArgs {
     const float* w;              // HWIO weights
     int c_in_total, ci_off;      // C_out = 32, C_s = 32
     int n_rows, nnz_max, H, W;
-    float* PB;                   // [entries][32] pooled vector of the cell whose first entry is e
-    float* GP;                   // [entries][32] its gradient
+    float* GP;                   // [entries][32] gradient of the pooled vector of the cell whose first entry is e
+    float* part_p;               // [9][gridDim.x][32 ci][32 co] per-CTA partial sums of the pooled weight gradient, or NULL
 };
 
-__global__ void __launch_bounds__(256) shpl_conv_gp_kernel(GpArgs a) {
-    __shared__ float wt[9 * 32 * 32];            // [tap][co][ci]: lane = ci reads conflict-free
+// A CTA takes batches of 32 entries; a warp takes a window of four of them and owns the cells whose first entry lies in
+// it: lane = output channel loads the 9 x 4 rows of g_out the four cells were seen through (all in flight together) and
+// leaves them in shared memory as [tap][co] float4s; lane = input channel then does, per (tap, co), one conflict-free LDS
+// of the transposed weight and one broadcast LDS.128 for four FFMAs (the first version: a cell per warp, a shuffle per
+// FFMA and one load latency per tap, 75 us).  Sums in (tap, co) order, taps outside the map contributing exact zeros.
+// The pooled channels' weight gradient is formed from the same staged rows: the eight warps share the 288 (tap, co)
+// pairs (36 sums per lane = input channel) and walk the batch's cells in entry order with the pooled vectors the
+// owners left in shared memory; per-CTA partial sums, added in CTA order by the reduce kernel (the separate kernel that
+// re-read g_out per tap took 72 us).
+constexpr int kGpWarps = 8;
+constexpr int kGpPairs = 288 / kGpWarps;     // (tap, co) pairs of the weight gradient per warp
+constexpr int kGpWtFloats = 9 * 32 * 33;     // [tap][co][33]: filled with coalesced loads, read with ci at stride 1
+constexpr int kGpSmem = (kGpWtFloats + kGpWarps * 9 * 32 * 4 + 4 * kGpWarps * 32) * 4;
+constexpr int kGpCtasPerSm = 2;
+
+__global__ void __launch_bounds__(32 * kGpWarps, kGpCtasPerSm) shpl_conv_gp_kernel(GpArgs a) {
+    extern __shared__ __align__(16) float gp_smem[];
+    __shared__ int has_cells[kGpWarps];
+    float* wt = gp_smem;
     for (int i = threadIdx.x; i < 9 * 32 * 32; i += blockDim.x) {
-        const int ci = i & 31, co = (i >> 5) & 31, t = i >> 10;
-        wt[i] = a.w[((size_t)t * a.c_in_total + a.ci_off + ci) * 32 + co];
+        const int co = i & 31, ci = (i >> 5) & 31, t = i >> 10;
+        wt[(t * 32 + co) * 33 + ci] = __ldg(a.w + ((size_t)t * a.c_in_total + a.ci_off + ci) * 32 + co);
     }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* gs_all = reinterpret_cast<float4*>(gp_smem + kGpWtFloats);     // [warp][tap][co] -> the four entries' g_out values
+    float4* gs = gs_all + warp * 288;
+    float* ps_all = gp_smem + kGpWtFloats + kGpWarps * 288 * 4;            // [entry of the batch][ci] pooled vectors (0: not a first entry)
     const int e_begin = __ldg(a.ptr), e_end = min(__ldg(a.ptr + a.n_rows), e_begin + a.nnz_max);
     const int HW = a.H * a.W;
-    for (int e = e_begin + blockIdx.x * warps + warp; e < e_end; e += gridDim.x * warps) {
-        const int r = __ldg(a.key + e);
-        if (e > e_begin && __ldg(a.key + e - 1) == r) continue;          // not the first entry of its cell (warp-uniform)
-        const int end = __ldg(a.ptr + r + 1);
-        float p = 0.f;                                                    // pooled[r][lane]: entries in stored order
-        for (int k = e; k < end; ++k)
-            p = __fadd_rn(p, __fmul_rn(__ldg(a.val + k), __ldg(a.src + (size_t)__ldg(a.idx + k) * 32 + lane)));
-        a.PB[(size_t)(e - e_begin) * 32 + lane] = p;
-        const int f = r / HW, rem = r - f * HW, y = rem / a.W, x = rem - y * a.W;
-        float acc = 0.f;                                                  // g_pooled[r][ci = lane]
-        for (int t = 0; t < 9; ++t) {
-            const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);         // the output pixel that saw this cell through tap t
-            if (yy < 0 || yy >= a.H || xx < 0 || xx >= a.W) continue;
-            const float g = __ldg(a.g_out + ((size_t)(f * a.H + yy) * a.W + xx) * 32 + lane);     // lane = co
-            const float* wrow = wt + t * 1024 + lane;
-#pragma unroll 8
-            for (int co = 0; co < 32; ++co) acc = fmaf(__shfl_sync(0xffffffffu, g, co), wrow[co * 32], acc);
+    const bool weights = a.part_p != nullptr;
+    float wacc[kGpPairs];                                                 // lane = ci; pair q = kGpPairs * warp + i = (tap, co)
+#pragma unroll
+    for (int i = 0; i < kGpPairs; ++i) wacc[i] = 0.f;
+    // a CTA owns a contiguous range of entries (every CTA the same number of batches: no uneven last round)
+    const int per = (((e_end - e_begin + (int)gridDim.x - 1) / (int)gridDim.x) + 3) & ~3;
+    const int c0 = min(e_begin + (int)blockIdx.x * per, e_end), c1 = min(c0 + per, e_end);
+    for (int b0 = c0; b0 < c1; b0 += 4 * kGpWarps) {
+        const int w0 = b0 + warp * 4;
+        int key_l = 0, idx_l = 0, end_l = 0;
+        float val_l = 0.f;
+        bool first_l = false;
+        if (lane < 4 && w0 + lane < c1) {
+            const int k = w0 + lane;
+            key_l = __ldg(a.key + k);
+            idx_l = __ldg(a.idx + k);
+            val_l = __ldg(a.val + k);
+            first_l = (k == e_begin) || (__ldg(a.key + k - 1) != key_l);
+            if (first_l) end_l = __ldg(a.ptr + key_l + 1);
         }
-        a.GP[(size_t)(e - e_begin) * 32 + lane] = acc;
+        const unsigned firsts = __ballot_sync(0xffffffffu, first_l) & 0xfu;   // warp-uniform; 0: no cell starts in this window
+        float g[9][4];                                                    // lane = co
+        float pv[4] = {0.f, 0.f, 0.f, 0.f};                               // lane = ci: pooled vectors of the cells that start here
+        if (firsts != 0u) {
+            float x[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int p = __shfl_sync(0xffffffffu, idx_l, j);
+                SHPL_DASSERT(w0 + j >= c1 || p >= 0);
+                x[j] = (w0 + j < c1) ? __ldg(a.src + (size_t)p * 32 + lane) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = __shfl_sync(0xffffffffu, key_l, j);
+                const bool fj = (firsts >> j) & 1u;
+                const int f = r / HW, rem = r - f * HW, y = rem / a.W, xq = rem - y * a.W;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int yy = y - (t / 3 - 1), xx = xq - (t % 3 - 1);    // the output pixel that saw this cell through tap t
+                    const bool ok = fj && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;
+                    g[t][j] = ok ? __ldg(a.g_out + ((size_t)(f * a.H + yy) * a.W + xx) * 32 + lane) : 0.f;
+                }
+            }
+            if (weights) {   // pooled[cell][lane]: entries in stored order
+                float p = 0.f;
+                int open = -1, open_end = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if ((firsts >> j) & 1u) {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (jj == open) pv[jj] = p;
+                        open = j;
+                        open_end = __shfl_sync(0xffffffffu, end_l, j);
+                        p = 0.f;
+                    }
+                    if (open >= 0 && w0 + j < open_end) p = __fadd_rn(p, __fmul_rn(__shfl_sync(0xffffffffu, val_l, j), x[j]));
+                }
+                for (int k = w0 + 4; k < open_end; ++k)                   // the last cell runs on past the window
+                    p = __fadd_rn(p, __fmul_rn(__ldg(a.val + k), __ldg(a.src + (size_t)__ldg(a.idx + k) * 32 + lane)));
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    if (jj == open) pv[jj] = p;
+            }
+        }
+        __syncthreads();                                                  // the last batch's reads of gs / ps (and the fill of wt) are done
+        if (firsts != 0u) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) gs[t * 32 + lane] = make_float4(g[t][0], g[t][1], g[t][2], g[t][3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ps_all[(warp * 4 + j) * 32 + lane] = pv[j];
+        }
+        if (lane == 0) has_cells[warp] = firsts != 0u;
+        __syncthreads();
+        if (firsts != 0u) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};                          // g_pooled[cell j][ci = lane]
+            const float* wl = wt + lane;
+            for (int t = 0; t < 9; ++t) {
+#pragma unroll 8
+                for (int co = 0; co < 32; ++co) {
+                    const float w = wl[(t * 32 + co) * 33];
+                    const float4 gv = gs[t * 32 + co];
+                    acc[0] = fmaf(gv.x, w, acc[0]);
+                    acc[1] = fmaf(gv.y, w, acc[1]);
+                    acc[2] = fmaf(gv.z, w, acc[2]);
+                    acc[3] = fmaf(gv.w, w, acc[3]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if ((firsts >> j) & 1u) a.GP[(size_t)(w0 + j - e_begin) * 32 + lane] = acc[j];
+        }
+        if (weights) {
+            for (int ww = 0; ww < kGpWarps; ++ww) {                       // the batch's cells in entry order
+                if (!has_cells[ww]) continue;
+                const float p0 = ps_all[(ww * 4) * 32 + lane], p1 = ps_all[(ww * 4 + 1) * 32 + lane];
+                const float p2 = ps_all[(ww * 4 + 2) * 32 + lane], p3 = ps_all[(ww * 4 + 3) * 32 + lane];
+                const float4* gq = gs_all + ww * 288 + kGpPairs * warp;
+#pragma unroll
+                for (int i = 0; i < kGpPairs; ++i) {
+                    const float4 gv = gq[i];
+                    wacc[i] = fmaf(p0, gv.x, wacc[i]);
+                    wacc[i] = fmaf(p1, gv.y, wacc[i]);
+                    wacc[i] = fmaf(p2, gv.z, wacc[i]);
+                    wacc[i] = fmaf(p3, gv.w, wacc[i]);
+                }
+            }
+        }
+    }
+    if (weights) {
+#pragma unroll
+        for (int i = 0; i < kGpPairs; ++i) {
+            const int q = kGpPairs * warp + i, t = q >> 5, co = q & 31;
+            a.part_p[(((size_t)t * gridDim.x + blockIdx.x) * 32 + lane) * 32 + co] = wacc[i];
+        }
     }
 }
 
@@ -909,101 +1024,66 @@ __global__ void shpl_conv_remap_kernel(const int* __restrict__ ptr, const int* _
     remap[k] = __ldg(ptr + r) - e_begin;
 }
 
-constexpr int kGwChunks = 128;         // chunks of entries the pooled weight gradient is split into (a CTA per tap and chunk)
-
-// pooled channels: part_p[t][chunk][ci][co] = sum over the chunk's cells of pooled[cell][ci] * g_out[cell - off(t)][co].
-// The chunk's entries go through shared memory in batches of 512: one coalesced pass turns every first entry into the
-// pixel of g_out its tap reads (-1: not a first entry, or outside the map), then thread (ci, co quad) walks the batch with
-// eight independent loads of each operand in flight and adds in entry order (the first version chased three dependent
-// global loads per entry: 421 us).
-constexpr int kGwpBatch = 512;
-
-__global__ void __launch_bounds__(256) shpl_conv_gwp_kernel(const float* __restrict__ PB, const float* __restrict__ g_out, const int* __restrict__ ptr,
-                                                            const int* __restrict__ key, int n_rows, int nnz_max, int H, int W,
-                                                            float* __restrict__ part_p) {
-    __shared__ int s_pix[kGwpBatch];
-    const int t = blockIdx.x / kGwChunks, chunk = blockIdx.x % kGwChunks;
-    const int e_begin = __ldg(ptr), e_end = min(__ldg(ptr + n_rows), e_begin + nnz_max);
-    const int per = (e_end - e_begin + kGwChunks - 1) / kGwChunks;
-    const int c0 = e_begin + chunk * per, c1 = min(c0 + per, e_end);
-    const int ci = threadIdx.x >> 3, cq = threadIdx.x & 7;
-    const int HW = H * W, dy = t / 3 - 1, dx = t % 3 - 1;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int b0 = c0; b0 < c1; b0 += kGwpBatch) {
-        const int n = min(kGwpBatch, c1 - b0);
-        __syncthreads();
-        for (int j = threadIdx.x; j < n; j += 256) {
-            const int e = b0 + j, r = __ldg(key + e);
-            int pix = -1;
-            if (e == e_begin || __ldg(key + e - 1) != r) {
-                const int f = r / HW, rem = r - f * HW, y = rem / W, x = rem - y * W;
-                const int yy = y - dy, xx = x - dx;       // the output pixel that saw this cell through tap t
-                if (yy >= 0 && yy < H && xx >= 0 && xx < W) pix = (f * H + yy) * W + xx;
-            }
-            s_pix[j] = pix;
-        }
-        __syncthreads();
-        for (int j0 = 0; j0 < n; j0 += 8) {
-            float xv[8];
-            float4 g[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int pix = j0 + u < n ? s_pix[j0 + u] : -1;       // CTA-uniform
-                xv[u] = 0.f;
-                g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (pix >= 0) {
-                    xv[u] = __ldg(PB + (size_t)(b0 + j0 + u - e_begin) * 32 + ci);
-                    g[u] = __ldg(reinterpret_cast<const float4*>(g_out + (size_t)pix * 32) + cq);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                acc.x = fmaf(xv[u], g[u].x, acc.x); acc.y = fmaf(xv[u], g[u].y, acc.y);
-                acc.z = fmaf(xv[u], g[u].z, acc.z); acc.w = fmaf(xv[u], g[u].w, acc.w);
-            }
-        }
-    }
-    reinterpret_cast<float4*>(part_p + ((size_t)(t * kGwChunks + chunk) * 32 + ci) * 32)[cq] = acc;
-}
-
-// dense channels: persistent CTAs of 128 threads over 8 x 16-pixel tiles with a shared-memory halo; thread = (input-channel
-// pair, output-channel quad) keeps 9 taps x 2 x 4 sums in registers: per pixel one LDS.128 of g_out and nine LDS.64 of the
-// input feed 72 FFMAs (the first version, one input channel per thread, fed 36 and was bound by the loads).
-constexpr int kGwTileY = 8, kGwTileX = 16, kGwThreads = 128, kGwCtasPerSm = 4;
+// dense channels: persistent CTAs of 256 threads (two per SM) over 8 x 16-pixel tiles with a shared-memory halo, double
+// buffered with cp.async (the next tile lands while this one is summed); the two halves of a CTA take the upper and
+// the lower four rows of the tile and keep their own partial sums: thread = (half, input-channel pair, output-channel
+// quad) holds 9 taps x 2 x 4 sums in registers, per pixel one LDS.128 of g_out and nine LDS.64 of the input feed 72 FFMAs
+// (the first version, one input channel per thread, fed 36 and was bound by the loads; the second, 128-thread CTAs that
+// loaded and summed in turn, left the SM idle during the loads and ended on an uneven last round: 247 us).
+constexpr int kGwTileY = 8, kGwTileX = 16, kGwThreads = 256, kGwCtasPerSm = 2;
+constexpr int kGwPartsPerCta = 2;      // the halves of a CTA
 constexpr int kGwHaloFloats = (kGwTileY + 2) * (kGwTileX + 2) * 32, kGwTileFloats = kGwTileY * kGwTileX * 32;
-constexpr int kGwdSmem = (kGwHaloFloats + kGwTileFloats) * 4;
+constexpr int kGwBufFloats = kGwHaloFloats + kGwTileFloats;
+constexpr int kGwdSmem = 2 * kGwBufFloats * 4;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int bytes) {      // bytes = 16, or 0: zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
 
 __global__ void __launch_bounds__(kGwThreads, kGwCtasPerSm) shpl_conv_gwd_kernel(const float* __restrict__ x, const float* __restrict__ g_out, int frames, int H, int W,
                                                                                   float* __restrict__ part_d) {
-    extern __shared__ float gw_smem[];
-    float* xs = gw_smem;                    // [10][18][32] halo of the input map (zeros outside the image)
-    float* gs = gw_smem + kGwHaloFloats;    // [8][16][32] the output-gradient tile (zeros outside the image)
+    extern __shared__ __align__(16) float gw_smem[];
+    // buffer b: [10][18][32] halo of the input map, then [8][16][32] the output-gradient tile (zeros outside the image)
     const int tiles_x = (W + kGwTileX - 1) / kGwTileX, tiles_y = (H + kGwTileY - 1) / kGwTileY;
     const int n_tiles = frames * tiles_x * tiles_y;
-    const int cp = threadIdx.x >> 3, cq = threadIdx.x & 7;      // input channels 2 cp, 2 cp + 1; output channels 4 cq .. 4 cq + 3
-    float4 acc[9][2];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int half = threadIdx.x >> 7, cp = (threadIdx.x & 127) >> 3, cq = threadIdx.x & 7;      // input channels 2 cp, 2 cp + 1; output channels 4 cq .. 4 cq + 3
+    const uint32_t smem0 = smem_u32(gw_smem);
+    auto issue = [&](int tile, int buf) {
         const int f = tile / (tiles_x * tiles_y), tt = tile - f * tiles_x * tiles_y;
         const int y0 = (tt / tiles_x) * kGwTileY, x0 = (tt % tiles_x) * kGwTileX;
-        __syncthreads();
+        const uint32_t xs = smem0 + buf * (kGwBufFloats * 4), gs = xs + kGwHaloFloats * 4;
         for (int i = threadIdx.x; i < kGwHaloFloats / 4; i += kGwThreads) {      // float4 units: [10][18][8]
             const int q = i & 7, px = (i >> 3) % (kGwTileX + 2), py = (i >> 3) / (kGwTileX + 2);
             const int yy = y0 - 1 + py, xx = x0 - 1 + px;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = __ldg(reinterpret_cast<const float4*>(x + ((size_t)(f * H + yy) * W + xx) * 32) + q);
-            reinterpret_cast<float4*>(xs)[i] = v;
+            const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+            cp_async16(xs + i * 16, ok ? x + ((size_t)(f * H + yy) * W + xx) * 32 + q * 4 : x, ok ? 16 : 0);
         }
         for (int i = threadIdx.x; i < kGwTileFloats / 4; i += kGwThreads) {
             const int q = i & 7, px = (i >> 3) % kGwTileX, py = (i >> 3) / kGwTileX;
             const int yy = y0 + py, xx = x0 + px;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (yy < H && xx < W) v = __ldg(reinterpret_cast<const float4*>(g_out + ((size_t)(f * H + yy) * W + xx) * 32) + q);
-            reinterpret_cast<float4*>(gs)[i] = v;
+            const bool ok = yy < H && xx < W;
+            cp_async16(gs + i * 16, ok ? g_out + ((size_t)(f * H + yy) * W + xx) * 32 + q * 4 : g_out, ok ? 16 : 0);
         }
-        __syncthreads();
-        for (int py = 0; py < kGwTileY; ++py) {
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    float4 acc[9][2];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[t][0] = acc[t][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((int)blockIdx.x < n_tiles) issue(blockIdx.x, 0);
+    int buf = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+        __syncthreads();                                   // the other buffer's sums (the tile before this one) are done
+        const int next = tile + gridDim.x;
+        if (next < n_tiles) {
+            issue(next, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();                                   // this tile has landed for every thread
+        const float* xs = gw_smem + buf * kGwBufFloats;
+        const float* gs = xs + kGwHaloFloats;
+        for (int py = half * (kGwTileY / 2); py < (half + 1) * (kGwTileY / 2); ++py) {
 #pragma unroll 2
             for (int px = 0; px < kGwTileX; ++px) {
                 const float4 g = reinterpret_cast<const float4*>(gs + (py * kGwTileX + px) * 32)[cq];
@@ -1018,35 +1098,57 @@ __global__ void __launch_bounds__(kGwThreads, kGwCtasPerSm) shpl_conv_gwd_kernel
             }
         }
     }
+    const size_t part = (size_t)blockIdx.x * kGwPartsPerCta + half;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-        reinterpret_cast<float4*>(part_d + (((size_t)blockIdx.x * 9 + t) * 32 + 2 * cp) * 32)[cq] = acc[t][0];
-        reinterpret_cast<float4*>(part_d + (((size_t)blockIdx.x * 9 + t) * 32 + 2 * cp + 1) * 32)[cq] = acc[t][1];
+        reinterpret_cast<float4*>(part_d + ((part * 9 + t) * 32 + 2 * cp) * 32)[cq] = acc[t][0];
+        reinterpret_cast<float4*>(part_d + ((part * 9 + t) * 32 + 2 * cp + 1) * 32)[cq] = acc[t][1];
     }
 }
 
-// g_weight[t][ci][co] = the partial sums added in CTA / chunk order (fixed: deterministic)
-__global__ void shpl_conv_gw_reduce_kernel(const float* __restrict__ part_d, int n_ctas, const float* __restrict__ part_p, int c_in_total,
-                                           float* __restrict__ g_weight) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;            // over [9][c_in_total][32]
-    if (i >= 9 * c_in_total * 32) return;
-    const int co = i & 31, ci = (i >> 5) % c_in_total, t = (i >> 5) / c_in_total;
-    float s = 0.f;
+// g_weight[t][ci][co] = the partial sums added in a fixed tree (deterministic): a block takes one (t, ci) row of 32 output
+// channels, slice k of its eight sums the k-th eighth of the partial sums in CTA / chunk order (eight loads in flight),
+// and the eight slice sums are added in slice order.
+constexpr int kGwReduceSlices = 8;
+
+__global__ void __launch_bounds__(32 * kGwReduceSlices) shpl_conv_gw_reduce_kernel(const float* __restrict__ part_d, int n_ctas,
+                                                                                   const float* __restrict__ part_p, int n_chunks_p,
+                                                                                   int c_in_total, float* __restrict__ g_weight) {
+    __shared__ float sums[kGwReduceSlices][32];
+    const int co = threadIdx.x & 31, k = threadIdx.x >> 5;
+    const int ci = blockIdx.x % c_in_total, t = blockIdx.x / c_in_total;
+    const float* p = nullptr;
+    size_t pitch = 0;
+    int n = 0;
     if (ci < 32) {
-        const float* pd = part_d + ((size_t)t * 32 + ci) * 32 + co;
-        int c = 0;
-        for (; c + 8 <= n_ctas; c += 8) {             // eight partial sums in flight, added in CTA order
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = pd[(size_t)(c + j) * 9 * 1024];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s += v[j];
-        }
-        for (; c < n_ctas; ++c) s += pd[(size_t)c * 9 * 1024];
+        p = part_d + ((size_t)t * 32 + ci) * 32 + co;
+        pitch = (size_t)9 * 1024;
+        n = n_ctas;
     } else if (part_p != nullptr) {
-        for (int c = 0; c < kGwChunks; ++c) s += part_p[((size_t)(t * kGwChunks + c) * 32 + ci - 32) * 32 + co];
+        p = part_p + ((size_t)t * n_chunks_p * 32 + ci - 32) * 32 + co;
+        pitch = 1024;
+        n = n_chunks_p;
     }
-    g_weight[i] = s;
+    const int per = (n + kGwReduceSlices - 1) / kGwReduceSlices;
+    const int c1 = min(n, (k + 1) * per);
+    int c = k * per;
+    float s = 0.f;
+    for (; c + 8 <= c1; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = p[(size_t)(c + j) * pitch];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[j];
+    }
+    for (; c < c1; ++c) s += p[(size_t)c * pitch];
+    sums[k][co] = s;
+    __syncthreads();
+    if (k == 0) {
+        float r = sums[0][co];
+#pragma unroll
+        for (int j = 1; j < kGwReduceSlices; ++j) r += sums[j][co];
+        g_weight[((size_t)t * c_in_total + ci) * 32 + co] = r;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -1236,7 +1338,6 @@ extern "C" int shpl_pool_conv3x3_forward(const float* dst, const float* src, con
 namespace {
 struct BwdWorkspace {
     float* wprep;
-    float* PB;
     float* GP;
     int* remap;
     float* part_d;
@@ -1250,13 +1351,12 @@ BwdWorkspace carve_bwd(void* ws, long long nnz_max) {
     size_t off = 0;
     auto take = [&](size_t n) { uint8_t* q = p + off; off += align_up(n, 256); return q; };
     const size_t n = (size_t)(nnz_max > 0 ? nnz_max : 0);
-    b.n_ctas = kGwCtasPerSm * 148;            // persistent CTAs of the dense weight-gradient kernel (fixed: part of the summation tree)
+    b.n_ctas = kGwPartsPerCta * kGwCtasPerSm * 148;   // partial sums of the dense weight-gradient kernel (fixed: part of the summation tree)
     b.wprep = reinterpret_cast<float*>(take(kWBytes));
-    b.PB = reinterpret_cast<float*>(take(n * 32 * 4));
     b.GP = reinterpret_cast<float*>(take(n * 32 * 4));
     b.remap = reinterpret_cast<int*>(take(n * 4));
     b.part_d = reinterpret_cast<float*>(take((size_t)b.n_ctas * 9 * 1024 * 4));
-    b.part_p = reinterpret_cast<float*>(take((size_t)9 * kGwChunks * 1024 * 4));
+    b.part_p = reinterpret_cast<float*>(take((size_t)9 * kGpCtasPerSm * 148 * 1024 * 4));      // per-CTA partial sums of the gp kernel
     b.bytes = off;
     return b;
 }
@@ -1286,7 +1386,7 @@ extern "C" int shpl_pool_conv3x3_backward(const float* g_out, const float* dst, 
     const long long cells = (long long)frames * H * W;
     const bool sparse = C_s > 0 && nnz_max > 0;
     BwdWorkspace b = carve_bwd(workspace, sparse ? nnz_max : 0);
-    b.n_ctas = kGwCtasPerSm * shpl::sm_count() < b.n_ctas ? kGwCtasPerSm * shpl::sm_count() : b.n_ctas;
+    b.n_ctas = kGwPartsPerCta * kGwCtasPerSm * shpl::sm_count() < b.n_ctas ? kGwPartsPerCta * kGwCtasPerSm * shpl::sm_count() : b.n_ctas;
     SHPL_REQUIRE(workspace_bytes >= b.bytes, SHPL_ERR_WORKSPACE_TOO_SMALL, "shpl_pool_conv3x3_backward: workspace %zu < %zu bytes",
                  workspace_bytes, b.bytes);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1297,6 +1397,7 @@ extern "C" int shpl_pool_conv3x3_backward(const float* g_out, const float* dst, 
         if (int rc = shpl::check_launch("shpl_conv_prep_kernel")) return rc;
         if (int rc = launch_dense(g_out, kC, g_dst, b.wprep, nullptr, nullptr, 0, nullptr, nullptr, nullptr, 0, frames, H, W, s)) return rc;
     }
+    int ggrid = 0;                 // CTAs of the gp kernel = partial sums of the pooled weight gradient
     if (sparse && (g_src != nullptr || g_weight != nullptr)) {
         GpArgs ga{};
         ga.src = src;
@@ -1312,12 +1413,17 @@ extern "C" int shpl_pool_conv3x3_backward(const float* g_out, const float* dst, 
         ga.nnz_max = nnz_max;
         ga.H = H;
         ga.W = W;
-        ga.PB = b.PB;
         ga.GP = b.GP;
-        int ggrid = (nnz_max + 7) / 8;
-        const int gcap = shpl::sm_count() * 4;
+        ga.part_p = g_weight != nullptr ? b.part_p : nullptr;
+        static bool gp_attr = false;
+        if (!gp_attr) {
+            SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_conv_gp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGpSmem));
+            gp_attr = true;
+        }
+        ggrid = (nnz_max + 4 * kGpWarps - 1) / (4 * kGpWarps);            // a window of four entries per warp
+        const int gcap = kGpCtasPerSm * (shpl::sm_count() < 148 ? shpl::sm_count() : 148);      // (the workspace holds 148 SMs' partial sums)
         if (ggrid > gcap) ggrid = gcap;
-        shpl_conv_gp_kernel<<<ggrid, 256, 0, s>>>(ga);
+        shpl_conv_gp_kernel<<<ggrid, 32 * kGpWarps, kGpSmem, s>>>(ga);
         shpl::count_launches(1);
         if (int rc = shpl::check_launch("shpl_conv_gp_kernel")) return rc;
         if (g_src != nullptr) {
@@ -1336,15 +1442,10 @@ extern "C" int shpl_pool_conv3x3_backward(const float* g_out, const float* dst, 
             SHPL_CUDA_OK(cudaFuncSetAttribute(shpl_conv_gwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGwdSmem));
             attr_set = true;
         }
-        shpl_conv_gwd_kernel<<<b.n_ctas, kGwThreads, kGwdSmem, s>>>(dst, g_out, frames, H, W, b.part_d);
+        shpl_conv_gwd_kernel<<<b.n_ctas / kGwPartsPerCta, kGwThreads, kGwdSmem, s>>>(dst, g_out, frames, H, W, b.part_d);
         shpl::count_launches(1);
         if (int rc = shpl::check_launch("shpl_conv_gwd_kernel")) return rc;
-        if (sparse) {
-            shpl_conv_gwp_kernel<<<9 * kGwChunks, 256, 0, s>>>(b.PB, g_out, ptr, key, (int)cells, nnz_max, H, W, b.part_p);
-            shpl::count_launches(1);
-            if (int rc = shpl::check_launch("shpl_conv_gwp_kernel")) return rc;
-        }
-        shpl_conv_gw_reduce_kernel<<<(9 * c_in_total * 32 + 255) / 256, 256, 0, s>>>(b.part_d, b.n_ctas, sparse ? b.part_p : nullptr, c_in_total, g_weight);
+        shpl_conv_gw_reduce_kernel<<<9 * c_in_total, 32 * kGwReduceSlices, 0, s>>>(b.part_d, b.n_ctas, sparse ? b.part_p : nullptr, ggrid, c_in_total, g_weight);
         shpl::count_launches(1);
         if (int rc = shpl::check_launch("shpl_conv_gw_reduce_kernel")) return rc;
     }
