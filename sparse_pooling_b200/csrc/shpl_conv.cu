@@ -508,6 +508,7 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
 __global__ void shpl_conv_prep_kernel(const float* __restrict__ w, int c_in_total, int c_out_total, int ci_off, int transposed,
                                       float* __restrict__ wprep, int ci_off2 = 0, float* __restrict__ wprep2 = nullptr,
                                       uint32_t* __restrict__ zero = nullptr, int zero_words = 0) {
+    asm volatile("griddepcontrol.launch_dependents;");      // the Z kernel may start its gather under this launch
     const int i = blockIdx.x * blockDim.x + threadIdx.x;     // over [3 dy][8 chunks][192][4]
     for (int z = blockIdx.y * gridDim.x * blockDim.x + i; z < zero_words; z += gridDim.x * gridDim.y * blockDim.x) zero[z] = 0u;
     if (i >= kWElems) return;
@@ -584,7 +585,6 @@ __global__ void __launch_bounds__(kZtcThreads, 2) shpl_conv_z_tc_kernel(ZArgs a)
     extern __shared__ uint8_t z_smem_raw[];
     __shared__ uint32_t tmem_slot;
     const int e_begin = __ldg(a.ptr), e_end = min(__ldg(a.ptr + a.n_rows), e_begin + a.nnz_max);
-    asm volatile("griddepcontrol.launch_dependents;");    // the dense kernel may take the SMs as this grid leaves them
     const int rpt = a.rows_per_tile, rpw = rpt >> 3;       // entries per tile, per warp (<= 16)
     const int n_tiles = (e_end - e_begin + rpt - 1) / rpt;
     if ((int)blockIdx.x >= n_tiles) return;               // whole CTA: nnz_max is only an upper bound
@@ -598,8 +598,6 @@ __global__ void __launch_bounds__(kZtcThreads, 2) shpl_conv_z_tc_kernel(ZArgs a)
         mbar_init(bar_w, 1);
         mbar_init(bar_mma, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(bar_w, kWBytes);
-        for (int t = 0; t < 3; ++t) bulk_load_1d(base + kZtcSmW + t * kWDyBytes, reinterpret_cast<const uint8_t*>(a.wprep) + t * kWDyBytes, kWDyBytes, bar_w);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kZtcTmemCols) : "memory");
@@ -623,10 +621,7 @@ __global__ void __launch_bounds__(kZtcThreads, 2) shpl_conv_z_tc_kernel(ZArgs a)
                 idx_l = __ldg(a.idx + k_l);
                 val_l = __ldg(a.val + k_l);
                 first_l = (k_l == e_begin) || (__ldg(a.key + k_l - 1) != key_l);
-                if (first_l) {
-                    end_l = __ldg(a.ptr + key_l + 1);
-                    atomicOr(a.busy + (key_l >> 5), 1u << (key_l & 31));      // order-independent: deterministic
-                }
+                if (first_l) end_l = __ldg(a.ptr + key_l + 1);
             }
             float x[16];
 #pragma unroll
@@ -635,6 +630,18 @@ __global__ void __launch_bounds__(kZtcThreads, 2) shpl_conv_z_tc_kernel(ZArgs a)
                 SHPL_DASSERT(j >= rpw || ew + j >= e_end || p >= 0);
                 x[j] = (j < rpw && ew + j < e_end) ? __ldg(a.src + (size_t)p * 32 + lane) : 0.f;
             }
+            if (it == 0) {
+                // Everything above reads the caller's arrays only.  The prep launch (this kernel is its programmatic
+                // dependent) wrote the weights and cleared the bitmap: wait for it here, then let the dense kernel queue up.
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+                asm volatile("griddepcontrol.launch_dependents;");
+                if (tid == 0) {
+                    mbar_expect_tx(bar_w, kWBytes);
+                    for (int t = 0; t < 3; ++t)
+                        bulk_load_1d(base + kZtcSmW + t * kWDyBytes, reinterpret_cast<const uint8_t*>(a.wprep) + t * kWDyBytes, kWDyBytes, bar_w);
+                }
+            }
+            if (first_l) atomicOr(a.busy + (key_l >> 5), 1u << (key_l & 31));      // order-independent: deterministic
             const unsigned firsts = __ballot_sync(0xffffffffu, first_l) & 0xffffu;
             uint8_t* hi_p = gbase + kZtcSmA + (lane >> 2) * kZtcPitch + (lane & 3) * 4;
             uint8_t* lo_p = hi_p + kZtcPlane;
@@ -1318,7 +1325,18 @@ extern "C" int shpl_pool_conv3x3_forward(const float* dst, const float* src, con
             rpt = rpt < 32 ? 32 : rpt > 128 ? 128 : rpt;
             za.rows_per_tile = rpt;
             const int ztiles = (nnz_max + rpt - 1) / rpt;
-            shpl_conv_z_tc_kernel<<<ztiles < slots ? ztiles : slots, kZtcThreads, kZtcSmemRequest, s>>>(za);
+            // a programmatic dependent of the prep launch: entries and source rows are gathered under it
+            cudaLaunchConfig_t zcfg = {};
+            zcfg.gridDim = dim3(ztiles < slots ? ztiles : slots);
+            zcfg.blockDim = dim3(kZtcThreads);
+            zcfg.dynamicSmemBytes = kZtcSmemRequest;
+            zcfg.stream = s;
+            cudaLaunchAttribute zattr[1];
+            zattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            zattr[0].val.programmaticStreamSerializationAllowed = 1;
+            zcfg.attrs = zattr;
+            zcfg.numAttrs = kConvPdl ? 1 : 0;
+            SHPL_CUDA_OK(cudaLaunchKernelEx(&zcfg, shpl_conv_z_tc_kernel, za));
             shpl::count_launches(1);
             if (int rc = shpl::check_launch("shpl_conv_z_tc_kernel")) return rc;
         } else {
