@@ -82,6 +82,13 @@ def test_fused_conv_at_the_kitti_size(shpl):
     print("KITTI size: max |err| / sum|terms| = %.2e" % rel)
 
 
+@pytest.mark.parametrize("H,W,n,dup", [(200, 176, 30000, False), (200, 176, 60000, True), (120, 96, 45000, True)])
+def test_fused_conv_with_many_pairs(shpl, H, W, n, dup):
+    """More pairs than one wave of the Z kernel's tiles holds (rows_per_tile at its cap of 128, several tiles per CTA) and
+    the tile sizes in between (30 000 pairs: 104 entries per tile), on maps where most cells receive several pairs."""
+    _run(shpl, 1, H, W, 60, 90, n, 7 + n, relu=False, affine=True, dup_rows=dup)
+
+
 def test_fused_conv_through_the_builder_plan(shpl):
     """The plan the correspondence builder leaves (produce_sparse_pooling_input's dict) goes straight in."""
     from sparse_pooling_b200 import conv_fusion
@@ -107,7 +114,7 @@ def test_unsupported_shapes_are_refused_not_miscomputed(shpl):
         conv_fusion.sparse_pool_conv3x3([bev, None], None, None, w)
 
 
-@pytest.mark.parametrize("H,W,n,dup", [(50, 44, 3000, True), (23, 30, 0, False), (96, 112, 6000, False)])
+@pytest.mark.parametrize("H,W,n,dup", [(50, 44, 3000, True), (23, 30, 0, False), (96, 112, 6000, False), (64, 80, 20000, True)])
 def test_fused_conv_backward_matches_the_oracle(shpl, H, W, n, dup):
     """g_bev, g_img and g_weight of conv3x3(concat(bev, pooled(img)), W) through autograd against the float64 oracle
     (conv gradients of the concat form, then the pooling gradient of SURVEY.md a13), each within 1e-5 of its sum of |terms|."""
