@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 evidence pass (one B200 under gpurun).  Every ncu command follows a plain run of the same command; numbers
-# quoted as bench values come from the plain runs.  Usage: bash tools/evidence_r2.sh <tag> [sections]  (sections: t b s c m a, default all)
+# quoted as bench values come from the plain runs.  Usage: bash tools/evidence_r2.sh <tag> [sections]  (sections: t b s c m a d, default all but d)
 tag=${1:-r2}
 want=${2:-tbscma}
 set -x
@@ -49,6 +49,14 @@ ncu --set full --clock-control none --import-source on -k regex:shpl_conv3x3_den
 reduce ${tag}_conv_dense_kernel
 ncu --set full --clock-control none --import-source on -k regex:shpl_conv_z_tc --launch-skip 4 -c 1 -o gpurun_out/${tag}_conv_z_kernel -f $C > gpurun_out/ncu_${tag}_conv_z.log 2>&1
 reduce ${tag}_conv_z_kernel
+W="python tools/conv_bwd_bench.py"
+$W > gpurun_out/${tag}_conv_bwd.txt 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:shpl_conv --csv --log-file gpurun_out/${tag}_conv_bwd_launches.csv $W > gpurun_out/ncu_${tag}_conv_b.log 2>&1
+python tools/ncu_summary.py gpurun_out/${tag}_conv_bwd_launches.csv > gpurun_out/${tag}_conv_bwd_launches_summary.txt
+fi
+if [[ $want == *d* ]]; then       # the bench line the driver's command prints (default flags) and configs[1] at 200 steps
+python bench.py > gpurun_out/${tag}_bench_default_flags.json 2> gpurun_out/${tag}_bench_default_flags.err
+python bench.py --config 2 --steps 200 --warmup 10 > gpurun_out/${tag}_bench_cfg2.json 2> gpurun_out/${tag}_bench_cfg2.err
 fi
 if [[ $want == *m* ]]; then       # feeders
 python tools/feeder_bench.py > gpurun_out/${tag}_feeder_bench.json 2> gpurun_out/${tag}_feeder.err
