@@ -35,12 +35,12 @@ def _pairs(seed, n, H, W, Hi, Wi, dup_rows=False):
     return Mij, val, flip
 
 
-def _run(shpl, B, H, W, Hi, Wi, n, seed, relu, affine, pooled=True, dup_rows=False):
+def _run(shpl, B, H, W, Hi, Wi, n, seed, relu, affine, pooled=True, dup_rows=False, Ci=32):
     from sparse_pooling_b200 import conv_fusion
     rng = np.random.default_rng(seed)
     bev = rng.standard_normal((B, H, W, 32), dtype=np.float32)
-    img = rng.standard_normal((B, Hi, Wi, 32), dtype=np.float32)
-    w = (rng.standard_normal((3, 3, 64 if pooled else 32, 32)) * 0.1).astype(np.float32)
+    img = rng.standard_normal((B, Hi, Wi, Ci), dtype=np.float32)
+    w = (rng.standard_normal((3, 3, 32 + Ci if pooled else 32, 32)) * 0.1).astype(np.float32)
     scale = (rng.random(32) + 0.5).astype(np.float32) if affine else None
     shift = rng.standard_normal(32).astype(np.float32) if affine else None
     tb, ti, tw = (torch.from_numpy(x).cuda() for x in (bev, img, w))
@@ -51,7 +51,8 @@ def _run(shpl, B, H, W, Hi, Wi, n, seed, relu, affine, pooled=True, dup_rows=Fal
         Mij, val, flip = _pairs(seed + 1, n, H, W, Hi, Wi, dup_rows)
         M = shpl.SparseTensor(torch.from_numpy(Mij).cuda(), torch.from_numpy(val).cuda(), np.array([H * W, n]))
         out = conv_fusion.sparse_pool_conv3x3([tb, ti], M, torch.from_numpy(flip).cuda(), tw, ts, th, relu)
-        fused = cref.forward(bev[0], img[0], Mij, val, flip)[None] if n else np.concatenate([bev, np.zeros_like(bev)], axis=3)
+        fused = (cref.forward(bev[0], img[0], Mij, val, flip)[None] if n
+                 else np.concatenate([bev, np.zeros(bev.shape[:3] + (Ci,), np.float32)], axis=3))
     else:
         out = conv_fusion.sparse_pool_conv3x3([tb, None], None, None, tw, ts, th, relu)
         fused = bev
@@ -87,6 +88,12 @@ def test_fused_conv_with_many_pairs(shpl, H, W, n, dup):
     """More pairs than one wave of the Z kernel's tiles holds (rows_per_tile at its cap of 128, several tiles per CTA) and
     the tile sizes in between (30 000 pairs: 104 entries per tile), on maps where most cells receive several pairs."""
     _run(shpl, 1, H, W, 60, 90, n, 7 + n, relu=False, affine=True, dup_rows=dup)
+
+
+@pytest.mark.parametrize("n,dup", [(0, False), (700, False), (5000, True)])
+def test_fused_conv_with_64_pooled_channels(shpl, n, dup):
+    """C_s = 64 (the FFMA form of the Z kernel and the separate marking kernel)."""
+    _run(shpl, 1, 50, 44, 20, 30, n, 90 + n, relu=True, affine=True, dup_rows=dup, Ci=64)
 
 
 def test_fused_conv_through_the_builder_plan(shpl):
