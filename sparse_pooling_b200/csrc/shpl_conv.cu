@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_out, ConvArgs a) {
     extern __shared__ uint8_t conv_smem_raw[];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ uint32_t contrib_mask[2][4];      // per staging buffer and sparse warp: the staging rows that hold a pooled contribution
     const uint32_t raw = smem_u32(conv_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* gbase = conv_smem_raw + (base - raw);
@@ -388,6 +389,10 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
                 float o[32];
 #pragma unroll
                 for (int c = 0; c < 32; ++c) o[c] = 0.f;
+                // Only the pixels with a busy neighbour (about one in five) write their staging row; the epilogue reads the
+                // rows flagged in contrib_mask and takes the others as zero.
+                const uint32_t has_rows = __ballot_sync(0xffffffffu, px_ok && zmask != 0u);
+                const bool has = px_ok && zmask != 0u;
                 // Round k handles the k-th busy tap of every lane together: a warp pays one latency per round, and there are as
                 // many rounds as its busiest pixel has busy neighbours.
                 while (__any_sync(0xffffffffu, zmask != 0u)) {
@@ -408,7 +413,8 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
                     }
                 }
                 mbar_wait(bar(BAR_OUT_EMPTY + ob), (u & 1) ^ 1);         // the store of tile i-2 has read this buffer
-                if (px_ok) {
+                if (lane == 0) contrib_mask[ob][sw] = has_rows;
+                if (has) {
                     uint8_t* orow = gbase + kSmOut + ob * kOutBytes + r * 128;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
@@ -463,9 +469,10 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
             }
             // the staging buffer of this tile: filled with the pooled half by the sparse warps, or just free again
             mbar_wait(bar((pooled ? BAR_CONTRIB_FULL : BAR_OUT_EMPTY) + s), pooled ? (u & 1) : ((u & 1) ^ 1));
-            uint8_t* orow = gbase + kSmOut + s * kOutBytes + (yl * kTileX + xq - 1) * 128;
-            const int rsw = (yl * kTileX + xq - 1) & 7;
-            if (pooled && col_ok) {
+            const int srow = yl * kTileX + xq - 1;           // staging row of this thread's pixel (col_ok)
+            uint8_t* orow = gbase + kSmOut + s * kOutBytes + srow * 128;
+            const int rsw = srow & 7;
+            if (pooled && col_ok && ((contrib_mask[s][srow >> 5] >> (srow & 31)) & 1u)) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 z = *reinterpret_cast<const float4*>(orow + ((j ^ rsw) << 4));
