@@ -443,7 +443,10 @@ int shpl_augment_fv_index(int64_t* img_index, int64_t ld, int64_t n, const int32
  * SHPL_ERR_UNSUPPORTED.  workspace: shpl_conv3x3_workspace_bytes(frames, H, W, nnz_max) bytes, 256-byte aligned
  * (weights in the tensor-core operand layout, two cell bitmaps, and 1152 bytes per entry for the sparse half).
  * Accuracy: |error| <= 1e-5 * sum |terms| per output (3xTF32 products, fp32 accumulation); not bit-reproducible
- * against a sequential fp32 loop (neither is cuDNN / TF). */
+ * against a sequential fp32 loop (neither is cuDNN / TF).
+ * The call enqueues three kernels on `stream`; the second and third are programmatic dependent launches of the one before
+ * (they start early and wait inside the kernel for what they read).  To the caller the call is stream-ordered like any
+ * other, and it can be captured in a CUDA graph. */
 size_t shpl_conv3x3_workspace_bytes(int32_t frames, int32_t H, int32_t W, int32_t nnz_max);
 int shpl_pool_conv3x3_forward(const float* dst, const float* src,
                               const int32_t* ptr, const int32_t* key, const int32_t* idx, const float* val,
