@@ -933,19 +933,35 @@ def run_gpu_avod(args, name, cfg):
     res_pin = torch.empty_like(res_dev, device="cpu").pin_memory()
 
     def pool_all(pipe, mp, pts, vox, n, n_dev=None):
-        """build + forward + backward of every layer: the last layer on the current stream, the others on `side`"""
+        """build + forward + backward of every layer: the last layer on the current stream, the others on `side`; every
+        layer's builder on its own high-priority stream when the step is being captured into a CUDA graph (its short
+        latency-bound kernels are then scheduled ahead of the pooling CTAs of the step before, which shares the GPU with
+        it: e2e 7 740 -> 7 855 frames/s; with eager launches the extra stream operations cost more than they gain)"""
         main = torch.cuda.current_stream()
         ms = main.cuda_stream
+        hp = torch.cuda.is_current_stream_capturing()
+        if hp:
+            for li in range(nL):
+                bst = build_streams[li]
+                bst.wait_stream(main)
+                with torch.cuda.stream(bst):
+                    pipe.build_layer(li, pts, vox, P, n, bst.cuda_stream, n_dev=n_dev)
         if nL > 1:
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 ss = side.cuda_stream
                 for li in range(nL - 1):
-                    pipe.build_layer(li, pts, vox, P, n, ss, n_dev=n_dev)
+                    if hp:
+                        side.wait_stream(build_streams[li])
+                    else:
+                        pipe.build_layer(li, pts, vox, P, n, ss, n_dev=n_dev)
                     pipe.forward_layer(li, mp[li]["bev"], mp[li]["img"], ss, n)
                     pipe.backward_layer(li, mp[li]["g_bev"], mp[li]["g_img"], ss, n)
         li = nL - 1
-        pipe.build_layer(li, pts, vox, P, n, ms, n_dev=n_dev)
+        if hp:
+            main.wait_stream(build_streams[li])
+        else:
+            pipe.build_layer(li, pts, vox, P, n, ms, n_dev=n_dev)
         pipe.forward_layer(li, mp[li]["bev"], mp[li]["img"], ms, n)
         pipe.backward_layer(li, mp[li]["g_bev"], mp[li]["g_img"], ms, n)
         if nL > 1:
