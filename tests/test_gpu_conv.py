@@ -155,3 +155,46 @@ def test_fused_conv_backward_matches_the_oracle(shpl, H, W, n, dup):
     err = np.abs(ti.grad.cpu().numpy().reshape(-1, 32) - g_img)
     assert float((err / np.maximum(m_img, 1e-30))[m_img > 0].max() if (m_img > 0).any() else 0.0) <= TOL
     assert float(err[m_img == 0].max() if (m_img == 0).any() else 0.0) == 0.0
+
+
+def test_fused_conv_two_frames_stacked_plan(shpl):
+    """A batch of two frames behind one stacked plan (build_avod_plan: rows / pixels of frame f offset by f * H * W and
+    f * H_i * W_i): forward and all three gradients against the per-frame oracle."""
+    from sparse_pooling_b200 import conv_fusion
+    frames = [synth.avod_frame(s, az_step_deg=0.4) for s in (11, 12)]
+    H, W, Hi, Wi = 175, 200, 90, 300
+    plan = shpl.build_avod_plan([f["points"] for f in frames], [f["voxel_indices"] for f in frames],
+                                [f["P"] for f in frames], [1200, 360], (700, 800), stride=(4, 4))
+    rng = np.random.default_rng(21)
+    bev = rng.standard_normal((2, H, W, 32), dtype=np.float32)
+    img = rng.standard_normal((2, Hi, Wi, 32), dtype=np.float32)
+    w = (rng.standard_normal((3, 3, 64, 32)) * 0.1).astype(np.float32)
+    g = rng.standard_normal((2, H, W, 32), dtype=np.float32)
+    tb, ti, tw = (torch.from_numpy(x).cuda().requires_grad_(True) for x in (bev, img, w))
+    out = conv_fusion.sparse_pool_conv3x3_autograd([tb, ti], plan, None, tw)
+    out.backward(torch.from_numpy(g).cuda())
+    fused, pairs = [], []
+    for f, fr in enumerate(frames):
+        d = io.gen_sparse_pooling_input_avod(fr["points"], fr["voxel_indices"], fr["P"], [1200, 360], (700, 800))
+        o = io.produce_sparse_pooling_input(d, stride=[4, 4])
+        Mij, flip = np.asarray(o["Mij_pool"]), np.asarray(o["img_index_flip_pool"])
+        val = np.ones(len(Mij), np.float32)
+        assert len(Mij) > 100
+        fused.append(cref.forward(bev[f], img[f], Mij, val, flip))
+        pairs.append((Mij, val, flip))
+    fused = np.stack(fused)
+    ref, mag = vo.conv3x3_same(fused, w)
+    assert float((np.abs(out.detach().cpu().numpy() - ref) / np.maximum(mag, 1e-30)).max()) <= TOL
+    g_x, g_w, mag_x, mag_w = vo.conv3x3_same_grad(fused, w, g)
+    assert float((np.abs(tb.grad.cpu().numpy() - g_x[..., :32]) / np.maximum(mag_x[..., :32], 1e-30)).max()) <= TOL
+    assert float((np.abs(tw.grad.cpu().numpy() - g_w) / np.maximum(mag_w, 1e-30)).max()) <= TOL
+    for f, (Mij, val, flip) in enumerate(pairs):
+        gp, mp = g_x[f, :, :, 32:].reshape(-1, 32), mag_x[f, :, :, 32:].reshape(-1, 32)
+        g_img = np.zeros((Hi * Wi, 32))
+        m_img = np.zeros((Hi * Wi, 32))
+        pix = flip[:, 1] * Wi + flip[:, 2]
+        np.add.at(g_img, pix, val[:, None].astype(np.float64) * gp[Mij[:, 0]])
+        np.add.at(m_img, pix, np.abs(val[:, None].astype(np.float64)) * mp[Mij[:, 0]])
+        err = np.abs(ti.grad[f].cpu().numpy().reshape(-1, 32) - g_img)
+        assert float((err / np.maximum(m_img, 1e-30))[m_img > 0].max()) <= TOL
+        assert float(err[m_img == 0].max()) == 0.0
