@@ -198,3 +198,25 @@ def test_fused_conv_two_frames_stacked_plan(shpl):
         err = np.abs(ti.grad[f].cpu().numpy().reshape(-1, 32) - g_img)
         assert float((err / np.maximum(m_img, 1e-30))[m_img > 0].max()) <= TOL
         assert float(err[m_img == 0].max()) == 0.0
+
+
+def test_fused_conv_backward_with_outputs_left_out(shpl):
+    """Any of the three gradients may be left out (NULL in the C ABI); the ones asked for do not change by a bit."""
+    from sparse_pooling_b200 import conv_fusion
+    from sparse_pooling_b200.sparse_pool_utils import _resolve_plan
+    H, W, Hi, Wi, n = 64, 80, 20, 30, 6000
+    rng = np.random.default_rng(5)
+    tb = torch.from_numpy(rng.standard_normal((1, H, W, 32), dtype=np.float32)).cuda()
+    ti = torch.from_numpy(rng.standard_normal((1, Hi, Wi, 32), dtype=np.float32)).cuda()
+    tw = torch.from_numpy((rng.standard_normal((3, 3, 64, 32)) * 0.1).astype(np.float32)).cuda()
+    tg = torch.from_numpy(rng.standard_normal((1, H, W, 32), dtype=np.float32)).cuda()
+    Mij, val, flip = _pairs(9, n, H, W, Hi, Wi, True)
+    M = shpl.SparseTensor(torch.from_numpy(Mij).cuda(), torch.from_numpy(val).cuda(), np.array([H * W, n]))
+    plan = _resolve_plan(M, torch.from_numpy(flip).cuda(), H * W, (Hi, Wi), tb.device)
+    full = conv_fusion.sparse_pool_conv3x3_backward(tg, [tb, ti], plan, tw)
+    for need in ((True, False, False), (False, True, False), (False, False, True), (True, True, False), (False, True, True)):
+        part = conv_fusion.sparse_pool_conv3x3_backward(tg, [tb, ti], plan, tw, *need)
+        for want, a, b in zip(need, part, full):
+            assert (a is None) == (not want)
+            if want:
+                assert torch.equal(a, b)
