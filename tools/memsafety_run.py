@@ -130,6 +130,14 @@ def run_case(name, bev_hw, img_hw, C_b, C_i, n, skew, dev, stride=(1, 1), dual=F
         out = G(R * 32, torch.float32, dev)
         check(lib.shpl_pool_conv3x3_forward(bev.ptr(), img.ptr(), P[0], P[1], P[2], P[3], n, 1, Hh, Ww, 32, Q, 32, w.ptr(), 32, None, None, 1,
                                             out.ptr(), ctypes.c_void_p(cws.view.data_ptr() + off), cws_b, stream), "conv3x3")
+        bws_b = int(lib.shpl_conv3x3_backward_workspace_bytes(n))
+        bws = G(bws_b + 256, torch.uint8, dev)
+        boff = (-bws.view.data_ptr()) % 256
+        g_out = G(R * 32, torch.float32, dev, torch.randn(R * 32))
+        gc_bev, gc_img, gc_w = G(R * 32, torch.float32, dev), G(Q * 32, torch.float32, dev), G(9 * 64 * 32, torch.float32, dev)
+        check(lib.shpl_pool_conv3x3_backward(g_out.ptr(), bev.ptr(), img.ptr(), *P, n, 1, Hh, Ww, 32, Q, 32, w.ptr(), 32,
+                                             gc_bev.ptr(), gc_img.ptr(), gc_w.ptr(), ctypes.c_void_p(bws.view.data_ptr() + boff), bws_b, stream),
+              "conv3x3_backward")
     torch.cuda.synchronize()
     print("case %-28s ran" % name, flush=True)
 
