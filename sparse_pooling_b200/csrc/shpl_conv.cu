@@ -402,14 +402,16 @@ shpl_conv3x3_dense_kernel(const __grid_constant__ CUtensorMap map_in, const __gr
                         int zr = zrow[0];
 #pragma unroll
                         for (int tt = 1; tt < 9; ++tt) zr = (t == tt) ? zrow[tt] : zr;
-                        const float4* z = reinterpret_cast<const float4*>(a.Z + (size_t)zr * 32);
-                        float4 zv[8];
+                        const float* z = a.Z + (size_t)zr * 32;
+                        float zv[32];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) zv[j] = __ldg(z + j);
+                        for (int j = 0; j < 4; ++j)      // 256-bit loads: a 128-byte row in four requests
+                            asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                         : "=f"(zv[8 * j]), "=f"(zv[8 * j + 1]), "=f"(zv[8 * j + 2]), "=f"(zv[8 * j + 3]),
+                                           "=f"(zv[8 * j + 4]), "=f"(zv[8 * j + 5]), "=f"(zv[8 * j + 6]), "=f"(zv[8 * j + 7])
+                                         : "l"(z + 8 * j));
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            o[4 * j] += zv[j].x; o[4 * j + 1] += zv[j].y; o[4 * j + 2] += zv[j].z; o[4 * j + 3] += zv[j].w;
-                        }
+                        for (int c = 0; c < 32; ++c) o[c] += zv[c];
                     }
                 }
                 mbar_wait(bar(BAR_OUT_EMPTY + ob), (u & 1) ^ 1);         // the store of tile i-2 has read this buffer
