@@ -95,6 +95,27 @@ template <typename V> __device__ __forceinline__ void st_stream(V* p, const V& v
     *p = v;
 #endif
 }
+// 256-bit forms (sm_100: LDG / STG .ENL2.256) for a lane that owns two adjacent float4 vectors of a row
+__device__ __forceinline__ void ld_gather_pair(const float4* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void ld_stream_pair(const float4* p, float4& a, float4& b) {
+#if SHPL_LD_POLICY == 1
+    asm volatile("ld.global.cs.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+#else
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+#endif
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_stream_pair(float4* p, const float4& a, const float4& b) {
+#if SHPL_ST_POLICY == 1
+    asm volatile("st.global.cs.v8.f32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
+#else
+    asm volatile("st.global.v8.f32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
+#endif
+                 ::"f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "l"(p) : "memory");
+}
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kMaxJobs = 4;
 constexpr int kGatherUnroll = 8;
@@ -583,6 +604,40 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
                                                   int q_lo = 0, int q_hi = 0x7fffffff) {
     // [q_lo, q_hi): the channel vectors this warp sums (a slice of the cell when its row is spread over several warps)
     const int prev_row = (e0 > e_begin) ? __ldg(key + e0 - 1) : -1;
+    // With two float4 accumulators per lane the lane owns an ADJACENT pair of vectors when every row it touches is 32-byte
+    // aligned: one 256-bit request per gathered row, addend row and output row instead of two 128-bit ones (the channel a
+    // sum belongs to does not change its entry order: bit-exact either way).
+    constexpr bool kPairs = (ACC == 2 && sizeof(V) == 16);
+    bool pairs = false;
+    if constexpr (kPairs)
+        pairs = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(addend)) & 31) == 0 &&
+                ((src_stride | out_stride | (addend != nullptr ? add_stride : 0)) & 1) == 0;
+    auto qof = [&](int q0, int a) { return pairs ? q0 + 2 * lane + a : q0 + a * 32 + lane; };
+    auto flush = [&](int q0, int row, V (&acc)[ACC]) {      // acc (+ addend) -> out, for the lane's vectors of this block
+        if constexpr (kPairs) {
+            const int q = q0 + 2 * lane;
+            if (pairs && q + 1 < nv) {
+                float4 a0 = acc[0], a1 = acc[1];
+                if (addend != nullptr) {
+                    float4 t0, t1;
+                    ld_stream_pair(reinterpret_cast<const float4*>(addend + (size_t)row * add_stride + q), t0, t1);
+                    a0 = vadd(t0, a0);
+                    a1 = vadd(t1, a1);
+                }
+                st_stream_pair(reinterpret_cast<float4*>(out + (size_t)row * out_stride + q), a0, a1);
+                return;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < ACC; ++a) {
+            const int q = qof(q0, a);
+            if (q < nv) {
+                V o = acc[a];
+                if (addend != nullptr) o = vadd(ld_stream(addend + (size_t)row * add_stride + q), o);
+                st_stream(out + (size_t)row * out_stride + q, o);
+            }
+        }
+    };
     for (int q0 = q_lo; q0 < nv && q0 < q_hi; q0 += 32 * ACC) {
         int base = e0;
         int my_row = -1, my_p = 0;
@@ -635,10 +690,20 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
                     SHPL_DASSERT(ej >= cnt || ((unsigned)p < (unsigned)n_gather && (unsigned)row[j] < (unsigned)n_cells));
                     w[j] = __shfl_sync(kFull, my_w, ej & 31);
                     const V* srow = src + (size_t)p * src_stride;
+                    bool loaded = false;
+                    if constexpr (kPairs) {
+                        const int q = q0 + 2 * lane;
+                        if (pairs && ej < cnt && q + 1 < nv) {
+                            ld_gather_pair(reinterpret_cast<const float4*>(srow + q), x[j][0], x[j][1]);
+                            loaded = true;
+                        }
+                    }
+                    if (!loaded) {
 #pragma unroll
-                    for (int a = 0; a < ACC; ++a) {
-                        const int q = q0 + a * 32 + lane;
-                        if (ej < cnt && q < nv) x[j][a] = __ldg(srow + q);
+                        for (int a = 0; a < ACC; ++a) {
+                            const int q = qof(q0, a);
+                            if (ej < cnt && q < nv) x[j][a] = __ldg(srow + q);
+                        }
                     }
                 }
 #pragma unroll
@@ -646,16 +711,9 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
                     if (finished || pos + j >= cnt) continue;
                     if (row[j] != cur_row) {
                         if (cur_row >= 0) {
+                            flush(q0, cur_row, acc);
 #pragma unroll
-                            for (int a = 0; a < ACC; ++a) {
-                                const int q = q0 + a * 32 + lane;
-                                if (q < nv) {
-                                    if (addend != nullptr)
-                                        acc[a] = vadd(ld_stream(addend + (size_t)cur_row * add_stride + q), acc[a]);
-                                    st_stream(out + (size_t)cur_row * out_stride + q, acc[a]);
-                                }
-                                acc[a] = vzero((V*)nullptr);
-                            }
+                            for (int a = 0; a < ACC; ++a) acc[a] = vzero((V*)nullptr);
                         }
                         if (base + pos + j >= e1) {   // the next cell belongs to a later warp
                             finished = true;
@@ -668,7 +726,7 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
                     ++run_len;
 #pragma unroll
                     for (int a = 0; a < ACC; ++a) {
-                        const int q = q0 + a * 32 + lane;
+                        const int q = qof(q0, a);
                         if (q < nv) axpy(acc[a], w[j], x[j][a]);
                     }
                 }
@@ -688,16 +746,7 @@ __device__ __forceinline__ void pool_entries_wide(const V* __restrict__ src, int
             }
             pos = 0;
         }
-        if (cur_row >= 0 && !(heavy_len > 0 && run_len > heavy_len)) {
-#pragma unroll
-            for (int a = 0; a < ACC; ++a) {
-                const int q = q0 + a * 32 + lane;
-                if (q < nv) {
-                    if (addend != nullptr) acc[a] = vadd(ld_stream(addend + (size_t)cur_row * add_stride + q), acc[a]);
-                    st_stream(out + (size_t)cur_row * out_stride + q, acc[a]);
-                }
-            }
-        }
+        if (cur_row >= 0 && !(heavy_len > 0 && run_len > heavy_len)) flush(q0, cur_row, acc);
     }
 }
 
